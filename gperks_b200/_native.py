@@ -1,0 +1,85 @@
+"""ctypes binding of libgpx.so (include/gpx.h).  Thin: raw device pointers in, error codes out.
+
+There is deliberately NO fallback: if the library cannot be loaded, or no CUDA device is present
+when a compute entry point is called, a RuntimeError is raised."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _build
+
+_lib: Optional[C.CDLL] = None
+
+KIND_RBF, KIND_MATERN12, KIND_MATERN32, KIND_MATERN52 = 0, 1, 2, 3
+TILE = 128
+
+_P = C.c_void_p
+_SIGS = {
+    "gpx_version": (C.c_int, []),
+    "gpx_padded": (C.c_int, [C.c_int]),
+    "gpx_max_dim": (C.c_int, []),
+    "gpx_kmat_sym": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, _P, C.c_int, _P]),
+    "gpx_kmat_cross": (C.c_int, [_P, C.c_long, _P, C.c_int, C.c_int, _P, _P, _P, C.c_int, _P, _P, C.c_int, _P,
+                                 C.c_int, _P]),
+    "gpx_potrf": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
+    "gpx_trtri": (C.c_int, [_P, _P, _P, _P, C.c_int, _P]),
+    "gpx_lauum": (C.c_int, [_P, _P, _P, C.c_int, _P]),
+    "gpx_solve_alpha": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, _P]),
+    "gpx_mll_value": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P]),
+    "gpx_mll_grad": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, _P, C.c_int, _P, _P, _P, _P]),
+    "gpx_predict_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "gpx_predict_meanvar": (C.c_int, [_P, C.c_long, _P, C.c_int, C.c_int, _P, _P, _P, C.c_int, _P, C.c_int, _P, _P,
+                                      _P, C.c_int, C.c_int, _P, _P, C.c_double, C.c_double, C.c_double, _P, _P, _P,
+                                      C.c_size_t, C.c_int, _P]),
+    "gpx_peak_dmma": (C.c_double, [C.c_int, C.c_int, _P, _P]),
+    "gpx_peak_dfma": (C.c_double, [C.c_int, C.c_int, _P, _P]),
+}
+EXPORTS = tuple(_SIGS)
+
+
+def lib() -> C.CDLL:
+    """Loads (building if absent) libgpx.so.  Raises if that is impossible -- no fallback."""
+    global _lib
+    if _lib is None:
+        path = _build.build()
+        try:
+            handle = C.CDLL(str(path))
+        except OSError as e:  # pragma: no cover
+            raise RuntimeError(f"gperks_b200: cannot load {path}: {e}") from e
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def require_cuda() -> None:
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            "gperks_b200 computes on an NVIDIA B200 (sm_100a) only: no CUDA device is available and there "
+            "is no CPU fallback."
+        )
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "gpx expects contiguous CUDA tensors"
+    return t.data_ptr()
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f"gpx: {what} failed with code {rc}")
+
+
+def padded(n: int) -> int:
+    return (max(int(n), 1) + TILE - 1) // TILE * TILE

@@ -1,0 +1,149 @@
+// extern "C" surface of libgpx.so -- see include/gpx.h for the contract of every entry point.
+#include "gpx_common.cuh"
+#include "../../include/gpx.h"
+
+namespace gpx {
+int kmat_sym(const double*, int, int, const double*, int, double*, int, cudaStream_t);
+int kmat_cross(const double*, long, const double*, int, int, const double*, const double*, const double*, int,
+               const double*, double*, int, double*, int, cudaStream_t);
+int mll_grad(const double*, int, int, const double*, int, const double*, int, const double*, double*, double*,
+             cudaStream_t);
+int potrf(double*, int, int, double*, double*, double*, int*, cudaStream_t);
+int trtri(const double*, double*, const double*, double*, int, cudaStream_t);
+int lauum(const double*, const double*, double*, int, cudaStream_t);
+int solve_alpha(const double*, const double*, int, const double*, double*, double*, cudaStream_t);
+int mll_value(const double*, const double*, int, int, const double*, double*, cudaStream_t);
+size_t predict_workspace_bytes(int, int);
+int predict_meanvar(const double*, long, const double*, int, int, const double*, const double*, const double*, int,
+                    const double*, int, const double*, const double*, const int*, int, int, const double*,
+                    const double*, double, double, double, double*, double*, void*, size_t, int, cudaStream_t);
+
+// ---- peak microbenchmarks -------------------------------------------------------------------
+__global__ void __launch_bounds__(256) peak_dmma_kernel(int iters, double* sink) {
+    double c[16][2];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { c[i][0] = 0.0; c[i][1] = 0.0; }
+    double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dmma884(c[i][0], c[i][1], a, b);
+    }
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) t += c[i][0] + c[i][1];
+    if (t == 12345.678) sink[0] = t;
+}
+__global__ void __launch_bounds__(256) peak_dfma_kernel(int iters, double* sink) {
+    double c[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) c[i] = i;
+    double a = 1.0 + threadIdx.x * 1e-9, b = 1e-9 * threadIdx.x;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) c[i] = fma(c[i], a, b);
+    }
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) t += c[i];
+    if (t == 12345.678) sink[0] = t;
+}
+}  // namespace gpx
+
+using namespace gpx;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" {
+
+int gpx_version(void) { return 100; }
+int gpx_padded(int n) { return round_up(n < 1 ? 1 : n, TILE); }
+int gpx_max_dim(void) { return MAXD; }
+
+static int check_np(int N, int Np) { return (Np % TILE == 0 && Np >= N && N >= 1) ? 0 : -1; }
+
+int gpx_kmat_sym(const double* X, int N, int D, const double* theta, int kind, double* K, int Np, void* stream) {
+    if (!X || !theta || !K) return -1;
+    if (check_np(N, Np)) return -7;
+    if (D < 1 || D > MAXD) return -3;
+    return kmat_sym(X, N, D, theta, kind, K, Np, ST(stream));
+}
+
+int gpx_kmat_cross(const double* Xs, long m_valid, const double* X, int N, int D, const double* theta,
+                   const double* xa, const double* xr, int kind, const double* alpha, double* Ks, int Np,
+                   double* mean_part, int Mc, void* stream) {
+    if (!Xs || !X || !theta || !alpha || !Ks || !mean_part) return -1;
+    if (check_np(N, Np)) return -12;
+    if (D < 1 || D > MAXD) return -5;
+    if (Mc <= 0 || Mc % TILE != 0 || m_valid > Mc) return -14;
+    if ((xa == nullptr) != (xr == nullptr)) return -7;
+    return kmat_cross(Xs, m_valid, X, N, D, theta, xa, xr, kind, alpha, Ks, Np, mean_part, Mc, ST(stream));
+}
+
+int gpx_potrf(double* K, int Np, int N, double* S, double* DT, double* logdet_blk, int* info, void* stream) {
+    if (!K || !S || !DT || !logdet_blk || !info) return -1;
+    if (check_np(N, Np)) return -2;
+    return potrf(K, Np, N, S, DT, logdet_blk, info, ST(stream));
+}
+
+int gpx_trtri(const double* L, double* S, const double* DT, double* W, int Np, void* stream) {
+    if (!L || !S || !DT || !W) return -1;
+    if (Np % TILE) return -5;
+    return trtri(L, S, DT, W, Np, ST(stream));
+}
+
+int gpx_lauum(const double* S, const double* DT, double* Kinv, int Np, void* stream) {
+    if (!S || !DT || !Kinv) return -1;
+    if (Np % TILE) return -4;
+    return lauum(S, DT, Kinv, Np, ST(stream));
+}
+
+int gpx_solve_alpha(const double* S, const double* DT, int Np, const double* r, double* u, double* alpha,
+                    void* stream) {
+    if (!S || !DT || !r || !u || !alpha) return -1;
+    if (Np % TILE) return -3;
+    return solve_alpha(S, DT, Np, r, u, alpha, ST(stream));
+}
+
+int gpx_mll_value(const double* r, const double* alpha, int Np, int N, const double* logdet_blk, double* out,
+                  void* stream) {
+    if (!r || !alpha || !logdet_blk || !out) return -1;
+    if (check_np(N, Np)) return -3;
+    return mll_value(r, alpha, Np, N, logdet_blk, out, ST(stream));
+}
+
+int gpx_mll_grad(const double* X, int N, int D, const double* theta, int kind, const double* Kinv, int Np,
+                 const double* alpha, double* partial, double* grad, void* stream) {
+    if (!X || !theta || !Kinv || !alpha || !partial || !grad) return -1;
+    if (check_np(N, Np)) return -7;
+    if (D < 1 || D > MAXD) return -3;
+    return mll_grad(X, N, D, theta, kind, Kinv, Np, alpha, partial, grad, ST(stream));
+}
+
+size_t gpx_predict_workspace_bytes(int Np, int Mc) { return predict_workspace_bytes(Np, Mc); }
+
+int gpx_predict_meanvar(const double* Xs, long M, const double* X, int N, int D, const double* theta,
+                        const double* xa, const double* xr, int kind, const double* S, int Np,
+                        const double* alpha, const double* prior_mean, const int* feat_idx, int n_feat,
+                        int degree, const double* weights, const double* bias, double y_mu, double y_sigma,
+                        double min_var, double* out_mean, double* out_std, void* workspace,
+                        size_t workspace_bytes, int Mc, void* stream) {
+    if (!Xs || !X || !theta || !S || !alpha || !out_mean || !out_std || !workspace) return -1;
+    if (M < 0) return -2;
+    if (M == 0) return 0;
+    if ((xa == nullptr) != (xr == nullptr)) return -7;
+    if (!prior_mean && weights && n_feat > 0 && (!feat_idx || degree < 1)) return -14;
+    return predict_meanvar(Xs, M, X, N, D, theta, xa, xr, kind, S, Np, alpha, prior_mean, feat_idx, n_feat, degree,
+                           weights, bias, y_mu, y_sigma, min_var, out_mean, out_std, workspace, workspace_bytes, Mc,
+                           ST(stream));
+}
+
+double gpx_peak_dmma(int blocks, int iters, double* sink, void* stream) {
+    peak_dmma_kernel<<<blocks, 256, 0, ST(stream)>>>(iters, sink);
+    // per warp per iter: 16 DMMA x (8*8*4 FMA) x 2 FLOP
+    return (double)blocks * 8.0 * iters * 16.0 * 512.0;
+}
+double gpx_peak_dfma(int blocks, int iters, double* sink, void* stream) {
+    peak_dfma_kernel<<<blocks, 256, 0, ST(stream)>>>(iters, sink);
+    return (double)blocks * 256.0 * iters * 16.0 * 2.0;
+}
+
+}  // extern "C"

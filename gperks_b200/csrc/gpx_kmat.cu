@@ -1,0 +1,324 @@
+// Pairwise-distance kernels: fused ARD RBF / Matern(1/2,3/2,5/2) + ScaleKernel + noise builders.
+//
+//   kmat_sym   : K_hat = s*k(X,X) + noise*I   (lower 128x128 tiles, identity in the padding)
+//                replaces gpytorch ScaleKernel(RBF|Matern).forward + GaussianLikelihood noise add
+//                (call sites GPErks/gp/model.py:18-21, GPErks/train/emulator.py:326).
+//   kmat_cross : K*[m][j] = s*k(x*_m, X_j) written k(=j)-contiguous for the NT TRMM, with the
+//                posterior-mean partial sums  sum_j K*[m][j]*alpha[j]  fused in
+//                (GPErks/train/emulator.py:352-357).
+//   mll_grad   : (1/2N) sum_ij (K_hat^-1 - alpha alpha^T)_ij dK_hat_ij/dtheta, kernel recomputed in
+//                registers, two-stage deterministic reduction (no N^2*D tensor ever materialised).
+//
+// All three share one tile body: a 128 x 128 tile per CTA, 256 threads, each thread an 8 x 8 micro-tile
+// strided by 16 so that a warp's stores cover two full 128-byte row segments.  Coordinates are
+// pre-multiplied by 1/lengthscale while being staged (transposed) into shared memory.
+#include "gpx_common.cuh"
+
+namespace gpx {
+
+constexpr int P_THREADS = 256;
+constexpr int P_LD = TILE + 1;   // padded smem row (transposed coordinate tile [d][128])
+
+// Stage rows [row0, row0+128) of X (row-major, ld = D) as z = ((x - a)/range) * inv_ls, transposed.
+// Rows >= n_valid are filled with zeros.  xa/xr may be null (training inputs are already scaled).
+__device__ __forceinline__ void stage_coords(double* sm, const double* __restrict__ X, long row0, long n_valid, int D,
+                                             const double* __restrict__ theta, const double* __restrict__ xa,
+                                             const double* __restrict__ xr) {
+    for (int e = threadIdx.x; e < TILE * D; e += P_THREADS) {
+        int r = e / D, d = e - r * D;
+        double v = 0.0;
+        if (row0 + r < n_valid) {
+            v = X[(row0 + r) * (long)D + d];
+            if (xa != nullptr) v = (v - xa[d]) / xr[d];
+            v *= theta[d];
+        }
+        sm[d * P_LD + r] = v;
+    }
+}
+
+// r2[a][b] for rows ty+16a (from sa) and cols tx+16b (from sb)
+__device__ __forceinline__ void tile_r2(double (&r2)[8][8], const double* sa, const double* sb, int D, int ty, int tx) {
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) r2[a][b] = 0.0;
+    for (int d = 0; d < D; ++d) {
+        double xa_[8], xb_[8];
+#pragma unroll
+        for (int a = 0; a < 8; ++a) xa_[a] = sa[d * P_LD + ty + 16 * a];
+#pragma unroll
+        for (int b = 0; b < 8; ++b) xb_[b] = sb[d * P_LD + tx + 16 * b];
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                double df = xa_[a] - xb_[b];
+                r2[a][b] = fma(df, df, r2[a][b]);
+            }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(P_THREADS) kmat_sym_kernel(const double* __restrict__ X, int N, int D,
+                                                             const double* __restrict__ theta, double* __restrict__ K,
+                                                             int Np) {
+    const int bi = blockIdx.y, bj = blockIdx.x;
+    if (bj > bi) return;
+    extern __shared__ double sm[];
+    double* sa = sm;
+    double* sb = sm + MAXD * P_LD;
+    stage_coords(sa, X, (long)bi * TILE, N, D, theta, nullptr, nullptr);
+    stage_coords(sb, X, (long)bj * TILE, N, D, theta, nullptr, nullptr);
+    __syncthreads();
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    double r2[8][8];
+    tile_r2(r2, sa, sb, D, ty, tx);
+    const double s = theta[D], noise = theta[D + 1];
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        const long i = (long)bi * TILE + ty + 16 * a;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const long j = (long)bj * TILE + tx + 16 * b;
+            double v;
+            if (i < N && j < N) {
+                v = kernel_value<KIND>(r2[a][b], s);
+                if (i == j) v += noise;
+            } else {
+                v = (i == j) ? 1.0 : 0.0;
+            }
+            K[i * Np + j] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cross kernel for one chunk of test points.  grid = (Np/128 j-tiles, Mc/128 m-tiles).
+//   Ks[m][j]  (ld = Np)            m in [0, Mc), chunk-local
+//   mean_part[jb][m]  (ld = Mc)    partial  sum_{j in tile jb} Ks[m][j] * alpha[j]
+template <int KIND>
+__global__ void __launch_bounds__(P_THREADS)
+kmat_cross_kernel(const double* __restrict__ Xs, long m_valid, const double* __restrict__ X, int N, int D,
+                  const double* __restrict__ theta, const double* __restrict__ xa, const double* __restrict__ xr,
+                  const double* __restrict__ alpha, double* __restrict__ Ks, int Np, double* __restrict__ mean_part,
+                  int Mc) {
+    const int jb = blockIdx.x, mb = blockIdx.y;
+    extern __shared__ double sm[];
+    double* sa = sm;                    // test points (rows m)
+    double* sb = sm + MAXD * P_LD;      // train points (cols j)
+    double* sal = sb + MAXD * P_LD;     // alpha tile [128]
+    double* smean = sal + TILE;         // [128]
+    stage_coords(sa, Xs, (long)mb * TILE, m_valid, D, theta, xa, xr);
+    stage_coords(sb, X, (long)jb * TILE, N, D, theta, nullptr, nullptr);
+    if (threadIdx.x < TILE) sal[threadIdx.x] = alpha[jb * TILE + threadIdx.x];   // alpha is zero-padded to Np
+    __syncthreads();
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    double r2[8][8];
+    tile_r2(r2, sa, sb, D, ty, tx);
+    const double s = theta[D];
+    double al[8];
+#pragma unroll
+    for (int b = 0; b < 8; ++b) al[b] = sal[tx + 16 * b];
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        const long m = (long)mb * TILE + ty + 16 * a;
+        double part = 0.0;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const long j = (long)jb * TILE + tx + 16 * b;
+            double v = (j < N) ? kernel_value<KIND>(r2[a][b], s) : 0.0;
+            Ks[m * Np + j] = v;
+            part = fma(v, al[b], part);
+        }
+        // reduce over the 16 tx lanes (a half-warp holds one row)
+        part += __shfl_xor_sync(0xffffffffu, part, 1);
+        part += __shfl_xor_sync(0xffffffffu, part, 2);
+        part += __shfl_xor_sync(0xffffffffu, part, 4);
+        part += __shfl_xor_sync(0xffffffffu, part, 8);
+        if (tx == 0) smean[ty + 16 * a] = part;
+    }
+    __syncthreads();
+    if (threadIdx.x < TILE) mean_part[(long)jb * Mc + (long)mb * TILE + threadIdx.x] = smean[threadIdx.x];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Gradient reduction.  grid = lower tiles (bj <= bi).  partial[(bi*nb + bj)*(D+2) + p]:
+//   p <  D : sum W_ij g(r_ij) dz_ijd^2     (weight 2 for off-diagonal tiles)
+//   p == D : sum W_ij k_ij / s
+//   p == D+1 : sum_i W_ii
+template <int KIND>
+__global__ void __launch_bounds__(P_THREADS)
+mll_grad_tile_kernel(const double* __restrict__ X, int N, int D, const double* __restrict__ theta,
+                     const double* __restrict__ Kinv, int Np, const double* __restrict__ alpha,
+                     double* __restrict__ partial) {
+    const int bi = blockIdx.y, bj = blockIdx.x, nb = gridDim.y;
+    double* out = partial + ((long)bi * nb + bj) * (D + 2);
+    if (bj > bi) return;
+    extern __shared__ double sm[];
+    double* sa = sm;
+    double* sb = sm + MAXD * P_LD;
+    double* sali = sb + MAXD * P_LD;   // alpha_i [128]
+    double* salj = sali + TILE;        // alpha_j [128]
+    double* sred = salj + TILE;        // [8 warps][MAXD+2]
+    stage_coords(sa, X, (long)bi * TILE, N, D, theta, nullptr, nullptr);
+    stage_coords(sb, X, (long)bj * TILE, N, D, theta, nullptr, nullptr);
+    if (threadIdx.x < TILE) {
+        sali[threadIdx.x] = alpha[bi * TILE + threadIdx.x];
+        salj[threadIdx.x] = alpha[bj * TILE + threadIdx.x];
+    }
+    __syncthreads();
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const double s = theta[D];
+    // pass 1: r2 -> weights  wg = W*g,  and the outputscale / noise sums
+    double wg[8][8];
+    tile_r2(wg, sa, sb, D, ty, tx);
+    double acc_s = 0.0, acc_n = 0.0;
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        const long i = (long)bi * TILE + ty + 16 * a;
+        const double ai = sali[ty + 16 * a];
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const long j = (long)bj * TILE + tx + 16 * b;
+            double w = 0.0, g = 0.0, k = 0.0;
+            if (i < N && j < N) {
+                w = Kinv[i * Np + j] - ai * salj[tx + 16 * b];
+                k = kernel_value_grad<KIND>(wg[a][b], s, g);
+            }
+            acc_s = fma(w, k, acc_s);
+            if (i == j) acc_n += w;
+            wg[a][b] = w * g;
+        }
+    }
+    const double tile_w = (bi == bj) ? 1.0 : 2.0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // pass 2: per-dimension sums  sum wg * dz_d^2
+    for (int d = 0; d < D; ++d) {
+        double xa_[8], xb_[8];
+#pragma unroll
+        for (int a = 0; a < 8; ++a) xa_[a] = sa[d * P_LD + ty + 16 * a];
+#pragma unroll
+        for (int b = 0; b < 8; ++b) xb_[b] = sb[d * P_LD + tx + 16 * b];
+        double acc = 0.0;
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                double df = xa_[a] - xb_[b];
+                acc = fma(wg[a][b], df * df, acc);
+            }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) sred[warp * (MAXD + 2) + d] = acc;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc_s += __shfl_xor_sync(0xffffffffu, acc_s, o);
+        acc_n += __shfl_xor_sync(0xffffffffu, acc_n, o);
+    }
+    if (lane == 0) {
+        sred[warp * (MAXD + 2) + D] = acc_s / s;
+        sred[warp * (MAXD + 2) + D + 1] = acc_n;
+    }
+    __syncthreads();
+    if (threadIdx.x < D + 2) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += sred[w * (MAXD + 2) + threadIdx.x];
+        out[threadIdx.x] = (threadIdx.x == D + 1) ? t : t * tile_w;
+    }
+}
+
+// final deterministic reduction over tiles: grad[p] = scale_p * sum_tiles partial
+//   grad[d] (lengthscale): * inv_ls_d / (2N)   (dz^2 = delta^2/l^2  =>  delta^2/l^3 = dz^2 / l)
+//   NOTE: d k/d l = +g * delta^2 / l^3.
+__global__ void mll_grad_final_kernel(const double* __restrict__ partial, int nb, int D, int N,
+                                      const double* __restrict__ theta, double* __restrict__ grad) {
+    const int p = blockIdx.x;
+    __shared__ double red[256];
+    double t = 0.0;
+    for (int bi = 0; bi < nb; ++bi)
+        for (int bj = threadIdx.x; bj <= bi; bj += blockDim.x) t += partial[((long)bi * nb + bj) * (D + 2) + p];
+    red[threadIdx.x] = t;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        double v = red[0] / (2.0 * N);
+        if (p < D) v *= theta[p];
+        grad[p] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------------------
+template <int KIND>
+static int launch_kmat_sym(const double* X, int N, int D, const double* theta, double* K, int Np, cudaStream_t st) {
+    const int nb = Np / TILE;
+    const size_t smem = size_t(2) * MAXD * P_LD * 8;
+    cudaFuncSetAttribute(kmat_sym_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kmat_sym_kernel<KIND><<<dim3(nb, nb), P_THREADS, smem, st>>>(X, N, D, theta, K, Np);
+    GPX_CHECK_LAUNCH();
+    return 0;
+}
+
+template <int KIND>
+static int launch_kmat_cross(const double* Xs, long m_valid, const double* X, int N, int D, const double* theta,
+                             const double* xa, const double* xr, const double* alpha, double* Ks, int Np,
+                             double* mean_part, int Mc, cudaStream_t st) {
+    const size_t smem = size_t(2) * MAXD * P_LD * 8 + 2 * TILE * 8;
+    cudaFuncSetAttribute(kmat_cross_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kmat_cross_kernel<KIND><<<dim3(Np / TILE, Mc / TILE), P_THREADS, smem, st>>>(Xs, m_valid, X, N, D, theta, xa, xr,
+                                                                                 alpha, Ks, Np, mean_part, Mc);
+    GPX_CHECK_LAUNCH();
+    return 0;
+}
+
+template <int KIND>
+static int launch_mll_grad(const double* X, int N, int D, const double* theta, const double* Kinv, int Np,
+                           const double* alpha, double* partial, double* grad, cudaStream_t st) {
+    const int nb = Np / TILE;
+    const size_t smem = size_t(2) * MAXD * P_LD * 8 + 2 * TILE * 8 + 8 * (MAXD + 2) * 8;
+    cudaFuncSetAttribute(mll_grad_tile_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    mll_grad_tile_kernel<KIND><<<dim3(nb, nb), P_THREADS, smem, st>>>(X, N, D, theta, Kinv, Np, alpha, partial);
+    GPX_CHECK_LAUNCH();
+    mll_grad_final_kernel<<<D + 2, 256, 0, st>>>(partial, nb, D, N, theta, grad);
+    GPX_CHECK_LAUNCH();
+    return 0;
+}
+
+#define GPX_DISPATCH_KIND(kind, CALL)                 \
+    switch (kind) {                                   \
+        case RBF: return CALL(RBF);                   \
+        case MATERN12: return CALL(MATERN12);         \
+        case MATERN32: return CALL(MATERN32);         \
+        case MATERN52: return CALL(MATERN52);         \
+        default: return -5;                           \
+    }
+
+int kmat_sym(const double* X, int N, int D, const double* theta, int kind, double* K, int Np, cudaStream_t st) {
+#define C_(KD) launch_kmat_sym<KD>(X, N, D, theta, K, Np, st)
+    GPX_DISPATCH_KIND(kind, C_)
+#undef C_
+}
+
+int kmat_cross(const double* Xs, long m_valid, const double* X, int N, int D, const double* theta, const double* xa,
+               const double* xr, int kind, const double* alpha, double* Ks, int Np, double* mean_part, int Mc,
+               cudaStream_t st) {
+#define C_(KD) launch_kmat_cross<KD>(Xs, m_valid, X, N, D, theta, xa, xr, alpha, Ks, Np, mean_part, Mc, st)
+    GPX_DISPATCH_KIND(kind, C_)
+#undef C_
+}
+
+int mll_grad(const double* X, int N, int D, const double* theta, int kind, const double* Kinv, int Np,
+             const double* alpha, double* partial, double* grad, cudaStream_t st) {
+#define C_(KD) launch_mll_grad<KD>(X, N, D, theta, Kinv, Np, alpha, partial, grad, st)
+    GPX_DISPATCH_KIND(kind, C_)
+#undef C_
+}
+
+}  // namespace gpx

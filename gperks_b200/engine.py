@@ -1,0 +1,226 @@
+"""Device-side exact-GP engine: owns the HBM-resident factors of one training set and drives the
+hand-written sm_100a kernels through the C ABI (include/gpx.h).
+
+HBM layout for N training points (Np = N rounded up to 128, nb = Np/128), all FP64 row-major:
+    K   [Np,Np]  K_hat lower tiles -> overwritten by L
+    S   [Np,Np]  L^-1 (lower) + L^-T mirrored in the upper off-diagonal blocks
+    W   [Np,Np]  scratch of the recursive inverse, then K_hat^-1 for the gradient
+    DT  [nb,128,128] transposed diagonal blocks of L^-1
+    r, u, alpha [Np]; theta [D+2]; logdet_blk [nb]; out [3]; grad [D+2]; partial [nb*nb*(D+2)]
+3*Np^2*8 B dominates: 1.6 GB at N=8192, 16.5 GB at N=26214 -- far below the B200's 180 GB.
+
+This module replaces the arithmetic gpytorch performs behind GPErks' call sites
+``GPErks/train/emulator.py:326-327`` (MLL forward/backward) and ``:356`` (prediction).
+"""
+from __future__ import annotations
+
+import warnings
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import torch
+
+from . import _native as nv
+
+F64 = torch.float64
+
+
+class NotPSDError(RuntimeError):
+    """Mirrors linear_operator.utils.errors.NotPSDError (raised after the jitter retries fail)."""
+
+
+class NumericalWarning(RuntimeWarning):
+    """Mirrors gpytorch.utils.warnings.NumericalWarning."""
+
+
+@dataclass
+class PolyMeanSpec:
+    """Polynomial prior mean evaluated inside the predict epilogue (GPErks/gp/mean.py:29-36)."""
+    feat_idx: torch.Tensor        # int32 [P, degree] on device, -1 padded
+    degree: int
+    weights: torch.Tensor         # [P] device f64
+    bias: Optional[torch.Tensor]  # [1] device f64 or None
+
+
+class ExactGPEngine:
+    """Factorisation cache + kernel launcher for one (X_train, kernel kind)."""
+
+    def __init__(self, X: torch.Tensor, kind: int, device: Optional[torch.device] = None):
+        nv.require_cuda()
+        self.lib = nv.lib()
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        if self.device.type != "cuda":
+            raise RuntimeError("ExactGPEngine needs a CUDA device")
+        X = X.detach()
+        if X.dim() == 1:
+            X = X.unsqueeze(-1)
+        self.X = X.to(self.device, F64).contiguous()
+        self.N, self.D = self.X.shape
+        if self.D > self.lib.gpx_max_dim():
+            raise ValueError(f"input dimension {self.D} exceeds the kernel limit {self.lib.gpx_max_dim()}")
+        self.kind = int(kind)
+        self.Np = nv.padded(self.N)
+        self.nb = self.Np // nv.TILE
+        dev = self.device
+        Np, nb, D = self.Np, self.nb, self.D
+        self.K = torch.empty(Np, Np, dtype=F64, device=dev)
+        self.S = torch.empty(Np, Np, dtype=F64, device=dev)
+        self.W = torch.empty(Np, Np, dtype=F64, device=dev)
+        self.DT = torch.empty(nb, nv.TILE, nv.TILE, dtype=F64, device=dev)
+        self.logdet_blk = torch.zeros(nb, dtype=F64, device=dev)
+        self.info = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.r = torch.zeros(Np, dtype=F64, device=dev)
+        self.u = torch.zeros(Np, dtype=F64, device=dev)
+        self.alpha = torch.zeros(Np, dtype=F64, device=dev)
+        self.out = torch.zeros(3, dtype=F64, device=dev)
+        self.grad = torch.zeros(D + 2, dtype=F64, device=dev)
+        self.partial = torch.zeros(nb * nb * (D + 2), dtype=F64, device=dev)
+        self.theta = torch.zeros(D + 2, dtype=F64, device=dev)
+        self.factor_key = None        # identifies the (theta, resid) the cached factors belong to
+        self.has_kinv = False
+        self.jitter_used = 0.0
+        self._ws: Optional[torch.Tensor] = None
+        self.n_factorizations = 0
+
+    # ------------------------------------------------------------------------------------------
+    def _launch(self, name: str, *args) -> None:
+        nv.check(getattr(self.lib, name)(*args), name)
+
+    def factorize(self, theta: torch.Tensor, resid: torch.Tensor, key=None, check: bool = True) -> None:
+        """K_hat(theta) = L L^T, S = L^-1, alpha = K_hat^-1 resid, out = (-mll, quad, logdet/2).
+
+        ``theta``: device [D+2] = (1/lengthscale, outputscale, noise).  On a failed factorisation the
+        gpytorch ``psd_safe_cholesky`` schedule is followed: jitter 1e-8 * 10^i (i<3) added to the
+        diagonal with a NumericalWarning, then NotPSDError."""
+        with torch.cuda.device(self.device):
+            st = nv.stream_ptr()
+            self.theta.copy_(theta.detach().reshape(-1))
+            self.r[: self.N].copy_(resid.detach().reshape(-1))
+            p = nv.ptr
+            jitter = 0.0
+            for attempt in range(4):
+                if attempt > 0:
+                    new_jitter = 1e-8 * 10 ** (attempt - 1)
+                    warnings.warn(f"A not p.d., added jitter of {new_jitter:.1e} to the diagonal", NumericalWarning)
+                    self.theta[self.D + 1] += new_jitter - jitter
+                    jitter = new_jitter
+                self._launch("gpx_kmat_sym", p(self.X), self.N, self.D, p(self.theta), self.kind, p(self.K),
+                             self.Np, st)
+                self._launch("gpx_potrf", p(self.K), self.Np, self.N, p(self.S), p(self.DT), p(self.logdet_blk),
+                             p(self.info), st)
+                if not check:
+                    break
+                info = int(self.info.item())       # the one host sync of a factorisation
+                if info == 0:
+                    break
+                if attempt == 3:
+                    raise NotPSDError(f"Matrix not positive definite after repeatedly adding jitter up to "
+                                      f"{jitter:.1e} (first non-positive pivot at {info}).")
+            self.jitter_used = jitter
+            self._launch("gpx_trtri", p(self.K), p(self.S), p(self.DT), p(self.W), self.Np, st)
+            self._launch("gpx_solve_alpha", p(self.S), p(self.DT), self.Np, p(self.r), p(self.u), p(self.alpha), st)
+            self._launch("gpx_mll_value", p(self.r), p(self.alpha), self.Np, self.N, p(self.logdet_blk),
+                         p(self.out), st)
+        self.has_kinv = False
+        self.factor_key = key
+        self.n_factorizations += 1
+
+    def gradients(self) -> torch.Tensor:
+        """d(-mll)/d(lengthscale_d, outputscale, noise) for the cached factors -> device [D+2]."""
+        with torch.cuda.device(self.device):
+            st = nv.stream_ptr()
+            p = nv.ptr
+            if not self.has_kinv:
+                self._launch("gpx_lauum", p(self.S), p(self.DT), p(self.W), self.Np, st)
+                self.has_kinv = True
+            self._launch("gpx_mll_grad", p(self.X), self.N, self.D, p(self.theta), self.kind, p(self.W), self.Np,
+                         p(self.alpha), p(self.partial), p(self.grad), st)
+        return self.grad
+
+    @property
+    def loss(self) -> torch.Tensor:
+        return self.out[0]
+
+    # ------------------------------------------------------------------------------------------
+    def _workspace(self, nbytes: int) -> torch.Tensor:
+        if self._ws is None or self._ws.numel() * 8 < nbytes:
+            self._ws = None
+            self._ws = torch.empty((nbytes + 7) // 8, dtype=F64, device=self.device)
+        return self._ws
+
+    def pick_chunk(self, M: int, budget_bytes: int = 2 << 30) -> int:
+        """Chunk of test points whose K* tile (Mc x Np doubles) stays within ``budget_bytes``."""
+        mc = max(nv.TILE, (budget_bytes // (self.Np * 8)) // nv.TILE * nv.TILE)
+        mc = min(mc, 32768)
+        return int(min(mc, nv.padded(M)))
+
+    def predict(self, Xs: torch.Tensor, *, xa: Optional[torch.Tensor] = None, xr: Optional[torch.Tensor] = None,
+                prior_mean: Optional[torch.Tensor] = None, poly: Optional[PolyMeanSpec] = None,
+                y_mu: float = 0.0, y_sigma: float = 1.0, min_var: float = 1e-10,
+                out_mean: Optional[torch.Tensor] = None, out_std: Optional[torch.Tensor] = None,
+                chunk: Optional[int] = None):
+        """Posterior mean and noisy std for device-resident points Xs [M, D] using the cached factors.
+
+        ``xa``/``xr``: unit-cube scaler (min, range) applied in-kernel to raw inputs; omit for inputs that
+        are already scaled.  Returns (mean, std) device tensors, un-standardised with (y_mu, y_sigma)."""
+        if self.factor_key is None and self.n_factorizations == 0:
+            raise RuntimeError("predict() before factorize()")
+        if Xs.dim() == 1:
+            Xs = Xs.unsqueeze(-1)
+        Xs = Xs.to(self.device, F64).contiguous()
+        M = Xs.shape[0]
+        if Xs.shape[1] != self.D:
+            raise ValueError(f"expected inputs with {self.D} columns, got {Xs.shape[1]}")
+        if out_mean is None:
+            out_mean = torch.empty(M, dtype=F64, device=self.device)
+        if out_std is None:
+            out_std = torch.empty(M, dtype=F64, device=self.device)
+        if M == 0:
+            return out_mean, out_std
+        Mc = int(chunk) if chunk else self.pick_chunk(M)
+        ws_bytes = int(self.lib.gpx_predict_workspace_bytes(self.Np, Mc))
+        ws = self._workspace(ws_bytes)
+        p = nv.ptr
+        feat = wts = bias = None
+        n_feat = degree = 0
+        if prior_mean is not None:
+            prior_mean = prior_mean.detach().to(self.device, F64).contiguous()
+        elif poly is not None:
+            feat, wts, bias = poly.feat_idx, poly.weights, poly.bias
+            n_feat, degree = int(feat.shape[0]), int(poly.degree)
+        with torch.cuda.device(self.device):
+            self._launch("gpx_predict_meanvar", p(Xs), M, p(self.X), self.N, self.D, p(self.theta), p(xa), p(xr),
+                         self.kind, p(self.S), self.Np, p(self.alpha), p(prior_mean), p(feat), n_feat, degree,
+                         p(wts), p(bias), float(y_mu), float(y_sigma), float(min_var), p(out_mean), p(out_std),
+                         p(ws), ws_bytes, Mc, nv.stream_ptr())
+        return out_mean, out_std
+
+    # ------------------------------------------------------------------------------------------
+    def cross_kernel(self, Xs: torch.Tensor, xa=None, xr=None) -> torch.Tensor:
+        """Dense K*[M, N] (debug / with_covar / sample paths; test-set sized M)."""
+        if Xs.dim() == 1:
+            Xs = Xs.unsqueeze(-1)
+        Xs = Xs.to(self.device, F64).contiguous()
+        M = Xs.shape[0]
+        Mc = nv.padded(M)
+        Ks = torch.empty(Mc, self.Np, dtype=F64, device=self.device)
+        mp = torch.empty(self.nb, Mc, dtype=F64, device=self.device)
+        with torch.cuda.device(self.device):
+            self._launch("gpx_kmat_cross", nv.ptr(Xs), M, nv.ptr(self.X), self.N, self.D, nv.ptr(self.theta),
+                         nv.ptr(xa), nv.ptr(xr), self.kind, nv.ptr(self.alpha), nv.ptr(Ks), self.Np, nv.ptr(mp), Mc,
+                         nv.stream_ptr())
+        return Ks[:M, : self.N]
+
+    def linv(self) -> torch.Tensor:
+        """Dense lower-triangular L^-1 [N, N] (copy; for the small-M covariance paths and tests)."""
+        return torch.tril(self.S[: self.N, : self.N])
+
+    def chol(self) -> torch.Tensor:
+        return torch.tril(self.K[: self.N, : self.N])
+
+
+def make_theta(lengthscale: torch.Tensor, outputscale: torch.Tensor, noise: torch.Tensor,
+               device: torch.device) -> torch.Tensor:
+    """(1/lengthscale_d, outputscale, noise) as one device vector -- differentiable torch plumbing."""
+    ls = lengthscale.reshape(-1).to(device, F64)
+    return torch.cat([1.0 / ls, outputscale.reshape(1).to(device, F64), noise.reshape(1).to(device, F64)])

@@ -1,0 +1,91 @@
+/* gpx.h -- C ABI of libgpx.so, the sm_100a exact-GP kernel library behind gperks_b200.
+ *
+ * The reference (stelong/GPErks) has no FFI: its exact-GP arithmetic is delegated to
+ * gpytorch/linear_operator Python calls.  Each entry point below names the reference call site whose
+ * arithmetic it replaces (paths relative to the GPErks repository root).
+ *
+ * Conventions
+ *   - plain C, raw DEVICE pointers (e.g. torch.Tensor.data_ptr()), FP64, row-major, no torch types;
+ *   - `stream` is a cudaStream_t passed as void*; every call only enqueues work on it: no internal
+ *     allocation, no host synchronisation, no static device state => re-entrant across streams;
+ *   - factor matrices use the padded leading dimension Np = gpx_padded(N) (multiple of 128); the padding
+ *     block of K_hat is the identity;
+ *   - theta (device, D+2 doubles): [0,D) = 1/lengthscale_d, [D] = outputscale, [D+1] = noise;
+ *   - return 0 = enqueued, <0 = invalid argument / launch error.  Numerical status (LAPACK-style info:
+ *     1-based index of the first non-positive pivot) is written to a device int, never thrown.
+ */
+#ifndef GPX_H
+#define GPX_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum gpx_kind { GPX_RBF = 0, GPX_MATERN12 = 1, GPX_MATERN32 = 2, GPX_MATERN52 = 3 };
+
+int gpx_version(void);
+int gpx_padded(int n);
+int gpx_max_dim(void);
+
+/* K_hat = s*k(X,X) + noise*I, lower 128x128 tiles of K[Np][Np] (identity padding).
+ * replaces: ScaleKernel(RBFKernel|MaternKernel).forward + GaussianLikelihood noise add,
+ *           GPErks/gp/model.py:18-21 and GPErks/train/emulator.py:326 (model(X_train) in train mode). */
+int gpx_kmat_sym(const double* X, int N, int D, const double* theta, int kind, double* K, int Np, void* stream);
+
+/* Ks[m][j] = s*k(x*_m, X_j) for a chunk of Mc (multiple of 128) test rows, ld = Np, plus
+ * mean_part[jb][m] = sum_{j in 128-tile jb} Ks[m][j]*alpha[j].  xa/xr (nullable): unit-cube scaler
+ * min and range applied to raw inputs ((x-a)/(b-a), GPErks/gp/data/data_scaler.py:43-45).
+ * replaces: covar_module(X_new, X_train) + K* @ mean_cache, GPErks/train/emulator.py:352-357. */
+int gpx_kmat_cross(const double* Xs, long m_valid, const double* X, int N, int D, const double* theta,
+                   const double* xa, const double* xr, int kind, const double* alpha, double* Ks, int Np,
+                   double* mean_part, int Mc, void* stream);
+
+/* In-place blocked Cholesky of K (lower) -> L; writes the inverted diagonal blocks into S and DT,
+ * per-block sum(log L_ii) into logdet_blk[Np/128], and info.
+ * replaces: psd_safe_cholesky / torch.linalg.cholesky_ex inside ExactMarginalLogLikelihood and the
+ *           prediction strategy, GPErks/train/emulator.py:326 and :356. */
+int gpx_potrf(double* K, int Np, int N, double* S, double* DT, double* logdet_blk, int* info, void* stream);
+
+/* Completes S to L^-1 (lower) with L^-T mirrored in the upper off-diagonal blocks. W: Np*Np scratch. */
+int gpx_trtri(const double* L, double* S, const double* DT, double* W, int Np, void* stream);
+
+/* Kinv = L^-T L^-1 (full symmetric).   replaces: autograd through cholesky (cholesky_backward). */
+int gpx_lauum(const double* S, const double* DT, double* Kinv, int Np, void* stream);
+
+/* alpha = K_hat^-1 r = L^-T (L^-1 r); r zero-padded to Np; u: scratch[Np].
+ * replaces: cholesky_solve for the mean cache / the MLL quadratic form. */
+int gpx_solve_alpha(const double* S, const double* DT, int Np, const double* r, double* u, double* alpha,
+                    void* stream);
+
+/* out[0] = -mll = [r.alpha/2 + sum log L_ii + N/2 log 2pi]/N, out[1] = r.alpha, out[2] = sum log L_ii.
+ * replaces: ExactMarginalLogLikelihood.forward (divided by N), GPErks/train/emulator.py:326,332. */
+int gpx_mll_value(const double* r, const double* alpha, int Np, int N, const double* logdet_blk, double* out,
+                  void* stream);
+
+/* grad[0..D) = d(-mll)/d lengthscale_d, grad[D] = d/d outputscale, grad[D+1] = d/d noise
+ * (w.r.t. the constrained values).  partial: scratch (Np/128)^2*(D+2) doubles.
+ * replaces: loss.backward() through the kernel + Cholesky graph, GPErks/train/emulator.py:327. */
+int gpx_mll_grad(const double* X, int N, int D, const double* theta, int kind, const double* Kinv, int Np,
+                 const double* alpha, double* partial, double* grad, void* stream);
+
+/* Posterior mean and noisy std for M device-resident raw points, un-standardised with (y_mu, y_sigma).
+ * prior mean: prior_mean[M] if non-null, else sum_p weights[p]*prod_q x[feat_idx[p*degree+q]] + bias
+ * on the unit-cube inputs.  workspace >= gpx_predict_workspace_bytes(Np, Mc).
+ * replaces: GPEmulator.predict, GPErks/train/emulator.py:348-363. */
+size_t gpx_predict_workspace_bytes(int Np, int Mc);
+int gpx_predict_meanvar(const double* Xs, long M, const double* X, int N, int D, const double* theta,
+                        const double* xa, const double* xr, int kind, const double* S, int Np,
+                        const double* alpha, const double* prior_mean, const int* feat_idx, int n_feat,
+                        int degree, const double* weights, const double* bias, double y_mu, double y_sigma,
+                        double min_var, double* out_mean, double* out_std, void* workspace,
+                        size_t workspace_bytes, int Mc, void* stream);
+
+/* Microbenchmarks for the roofline denominators: enqueue `iters` dependent-chain-free DMMA.8x8x4
+ * (or DFMA) per warp on `blocks` CTAs of 256 threads; returns the FLOP count of the launch. */
+double gpx_peak_dmma(int blocks, int iters, double* sink, void* stream);
+double gpx_peak_dfma(int blocks, int iters, double* sink, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
