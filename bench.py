@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""Headline benchmark: GPEmulator.predict (mean + noisy std) throughput, N_train=8192, D=8, Matern-5/2 ARD
+(BASELINE.json configs[1]), on 1..8 B200s of one node.
+
+    python bench.py --gpus 1 --steps 3 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference's CPU path (float64 oracle, all host threads)
+
+A step = one pass of the predict hot path over M points per GPU (weak scaling: each rank owns its own M-point
+shard; factors L^-1 and alpha are replicated; the only collective is the final gather of the 16 B/point
+results).  `value` = points all ranks processed / max-over-ranks device time with X* resident in HBM;
+`e2e` = the same through GPEmulator.predict with host numpy buffers (pinned H2D + D2H inside the timed
+region).  One JSON line on stdout (rank 0)."""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import warnings
+
+import numpy as np
+import torch
+
+warnings.filterwarnings("ignore", message="The balance properties of Sobol")
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+N_TRAIN, DIM = 8192, 8
+KIND_NAME = "matern52"
+NOISE = 1e-2
+
+
+def synthetic_problem(n_train=N_TRAIN, dim=DIM, m=1_000_000, seed=8, rank=0):
+    """Seeded synthetic data of BASELINE's shape: X ~ Sobol(seed 8) in [0,1]^D,
+    y = Sobol G* standardised, fixed hyper-parameters l_d = 0.5(1+d/D), s = 1, noise = 1e-2,
+    linear mean w = linspace(-1,1,D), b = 0.1; X* ~ Sobol(seed 9 + rank)."""
+    from scipy.stats import qmc
+    X = qmc.Sobol(d=dim, scramble=True, seed=seed).random(n_train)
+    a = np.array([0, 1, 4.5, 9, 99, 99, 99, 99][:dim] + [99] * max(0, dim - 8), dtype=float)
+    delta = np.random.default_rng(seed).random(dim)
+    frac = X + delta - np.floor(X + delta)
+    y = np.prod((2.0 * np.abs(2 * frac - 1) + a) / (1 + a), axis=1)
+    Xs = qmc.Sobol(d=dim, scramble=True, seed=seed + 1 + rank).random(m)
+    hyper = dict(lengthscale=[0.5 * (1 + d / dim) for d in range(dim)], outputscale=1.0, noise=NOISE,
+                 weights=np.linspace(-1, 1, dim).tolist(), bias=0.1)
+    return X, y, Xs, hyper
+
+
+def build_emulator(X, y, hyper, device):
+    from gperks_b200.gp.data.dataset import Dataset
+    from gperks_b200.gp.experiment import GPExperiment
+    from gperks_b200.gp.mean import LinearMean
+    from gperks_b200.kernels import MaternKernel, ScaleKernel
+    from gperks_b200.likelihoods import GaussianLikelihood
+    from gperks_b200.train.emulator import GPEmulator
+    D = X.shape[1]
+    exp = GPExperiment(Dataset(X, y), GaussianLikelihood(), LinearMean(1, D), ScaleKernel(MaternKernel(nu=2.5, ard_num_dims=D)),
+                       n_restarts=1, seed=8)
+    em = GPEmulator(exp, device)
+    t = lambda v: torch.as_tensor(v, dtype=torch.float64)  # noqa: E731
+    m = em.model
+    m.likelihood.noise = hyper["noise"]
+    m.covar_module.outputscale = hyper["outputscale"]
+    m.covar_module.base_kernel.lengthscale = t(hyper["lengthscale"])
+    m.initialize(**{"mean_module.weights": t(hyper["weights"]), "mean_module.bias": t([hyper["bias"]])})
+    return em
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for s in self.samples for n, v in zip(names, s[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------------
+_ORACLE_CACHE = {}
+
+
+def cpu_oracle_predict_rate(X, y, Xs, hyper, sample_pts, chunk=4096):
+    """The reference's CPU path restated (oracle/gp_oracle.py, torch float64, all host threads): factorise
+    once, then predict `sample_pts` points in chunks; returns (pts/s over the predict part, seconds, threads)."""
+    from oracle import gp_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    if "em" not in _ORACLE_CACHE:
+        em = O.OracleEmulator(X, y, kind=O.KIND_MATERN52, lengthscale=hyper["lengthscale"],
+                              outputscale=hyper["outputscale"], noise=hyper["noise"], weights=hyper["weights"],
+                              bias=hyper["bias"], degree=1)
+        t0 = time.perf_counter()
+        resid = em.y - em._mean(em.X)
+        _, L, alpha = O.factorize(em.X, resid, em.kind, em.ls, em.s, em.noise)
+        _ORACLE_CACHE.update(em=em, L=L, alpha=alpha, t_fac=time.perf_counter() - t0)
+    em, L, alpha, t_fac = (_ORACLE_CACHE[k] for k in ("em", "L", "alpha", "t_fac"))
+    Xq = torch.from_numpy(em.scx.transform(Xs[:sample_pts]))
+    t0 = time.perf_counter()
+    for lo in range(0, sample_pts, chunk):
+        xs = Xq[lo:lo + chunk]
+        Ks = O.kernel_matrix(xs, em.X, em.kind, em.ls, em.s)
+        mean = em._mean(xs) + Ks @ alpha
+        V = torch.linalg.solve_triangular(L, Ks.T, upper=False)
+        var = (em.s - (V * V).sum(0) + em.noise).clamp_min(1e-10)
+        _ = em.scy.sigma * mean + em.scy.mu, em.scy.sigma * var.sqrt()
+    t_pred = time.perf_counter() - t0
+    return sample_pts / t_pred, t_pred, t_fac, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    X, y, Xs, hyper = synthetic_problem(m=max(args.ref_points, 4096))
+    rates, secs = [], []
+    for i in range(args.warmup + args.steps):
+        r, t_pred, t_fac, threads = cpu_oracle_predict_rate(X, y, Xs, hyper, args.ref_points)
+        if i >= args.warmup:
+            rates.append(r)
+            secs.append(t_pred)
+    value = args.ref_points * len(secs) / sum(secs)
+    line = {
+        "impl": "reference", "metric": "predict points/sec (mean+var) N=8192 D=8", "value": value, "unit": "points/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "configs[1]: Matern-5/2 ARD emulator, N_train=8192 D=8, predict mean+noisy std",
+                   "points_per_step": args.ref_points, "note": "bounded sample of the same workload; cost is linear in M"},
+        "cpu_baseline": {"value": value, "unit": "points/s", "cores": threads, "kind": "port",
+                         "sample": f"{args.ref_points} of the 1e6 X* points per step, chunks of 4096, factorisation ({t_fac:.1f} s) excluded"},
+        "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--points", type=int, default=1_000_000, help="predict points per GPU per step")
+    ap.add_argument("--ref-points", type=int, default=32768, help="points per step of the CPU reference arm")
+    ap.add_argument("--cpu-sample", type=int, default=32768, help="points of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mll-evals", type=int, default=3)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    from gperks_b200 import _native as nv
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    M = args.points
+    X, y, Xs, hyper = synthetic_problem(m=M, rank=rank)
+    em = build_emulator(X, y, hyper, f"cuda:{local_rank}")
+    lib = nv.lib()
+
+    # ---- factorise once (replicated on every rank), time MLL+grad evaluations as the secondary metric
+    eng = em.model._factorized_engine()
+    torch.cuda.synchronize()
+    theta, resid = eng.theta_in.clone(), eng.r[:eng.N].clone()
+    mll_ms = []
+    for i in range(args.mll_evals + 1):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        eng.factorize(theta, resid)
+        eng.gradients()
+        b.record()
+        torch.cuda.synchronize()
+        if i > 0:
+            mll_ms.append(a.elapsed_time(b))
+
+    # ---- device-resident arm (`value`)
+    scx, scy = em.scaled_data.scx, em.scaled_data.scy
+    xa = torch.as_tensor(np.asarray(scx.a, dtype=np.float64), device=dev)
+    xr = torch.as_tensor(np.asarray(scx.b - scx.a, dtype=np.float64), device=dev)
+    poly = em._poly_spec(dev)
+    x_dev = torch.from_numpy(Xs).to(dev)
+    out_mean = torch.empty(M, dtype=torch.float64, device=dev)
+    out_std = torch.empty(M, dtype=torch.float64, device=dev)
+    Mc = eng.pick_chunk(M)
+    n_chunks = math.ceil(M / Mc)
+    gathered = [torch.empty(2, M, dtype=torch.float64, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
+    local_out = torch.empty(2, M, dtype=torch.float64, device=dev)
+
+    def step():
+        eng.predict(x_dev, xa=xa, xr=xr, poly=poly, y_mu=float(scy.mu), y_sigma=float(scy.sigma),
+                    out_mean=out_mean, out_std=out_std, chunk=Mc)
+        if world > 1:       # the path's only exchange: gather the 16 B/point results on rank 0
+            local_out[0].copy_(out_mean)
+            local_out[1].copy_(out_std)
+            dist.gather(local_out, gathered, dst=0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    with ClockSampler(local_rank) as clocks:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(args.steps):
+            step()
+        b.record()
+        barrier()
+        elapsed_ms = a.elapsed_time(b)
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    value = world * M * args.steps / (elapsed_ms / 1e3)
+
+    # ---- dominant kernel alone (roofline): the variance TRMM on one full chunk, CUDA events on its stream
+    ws = eng._workspace(int(lib.gpx_predict_workspace_bytes(eng.Np, Mc)))
+    Ks_ptr = ws.data_ptr()
+    qpart = torch.empty(eng.nb * Mc, dtype=torch.float64, device=dev)
+    st = nv.stream_ptr()
+    k_ms = []
+    for i in range(4):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        nv.check(lib.gpx_trmm_sumsq(nv.ptr(eng.S), eng.Np, Ks_ptr, Mc, nv.ptr(qpart), st), "trmm")
+        b.record()
+        torch.cuda.synchronize()
+        if i > 0:
+            k_ms.append(a.elapsed_time(b))
+    k_ms = sum(k_ms) / len(k_ms)
+    flops_per_launch = float(eng.N) ** 2 * Mc            # N^2 FLOP per point for the variance
+    achieved = flops_per_launch / (k_ms / 1e3) / 1e12
+    sink = torch.zeros(8, dtype=torch.float64, device=dev)
+    peak_ms = []
+    for i in range(3):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        peak_flops = lib.gpx_peak_dmma(148 * 8, 20000, nv.ptr(sink), st)
+        b.record()
+        torch.cuda.synchronize()
+        peak_ms.append(a.elapsed_time(b))
+    peak = peak_flops / (min(peak_ms) / 1e3) / 1e12
+    kernel_share = k_ms * (M / Mc) / (elapsed_ms / args.steps)      # TRMM work is linear in the points
+
+    # ---- end-to-end arm: GPEmulator.predict on host numpy buffers (pinned H2D + D2H inside)
+    e2e_steps = max(1, min(args.steps, 2))
+    em.predict(Xs[: min(M, 200_000)])       # warm the pinned allocator
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        y_mean, y_std = em.predict(Xs)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * M * e2e_steps / float(t.item())
+    parity = float(np.max(np.abs(y_mean - out_mean.cpu().numpy())))     # the two arms must agree bit for bit
+
+    line = {
+        "metric": "predict points/sec (mean+var) N=8192 D=8", "value": value, "unit": "points/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "configs[1]: Matern-5/2 ARD emulator, N_train=8192 D=8, predict mean+noisy std",
+                   "points_per_gpu_per_step": M, "chunk_points": Mc, "parallelism": f"x*-shard x{world}, L^-1/alpha replicated",
+                   "l2": "working set per chunk (K* 2 GiB + L^-1 0.5 GB) exceeds the 126 MB L2; no flush needed"},
+        "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": int(M * DIM * 8), "d2h_bytes_per_step": int(M * 16),
+                "steps": e2e_steps, "api": "GPEmulator.predict(numpy)", "max_abs_diff_vs_device_arm": parity},
+        "gpu_launches": int(args.steps * n_chunks * 3),
+        "roofline": {"kernel": "trmm_sumsq_kernel (variance contraction L^-1 K*^T, FP64 DMMA)", "bound": "tensor",
+                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                     "peak_source": "gpx_peak_dmma probe measured in this run (FP64 DMMA.8x8x4 issue peak; MEASURED_PEAKS.json "
+                                    "has no FP64 figure; cuBLAS DGEMM 8192^3 measured 35.5 TF/s on this pool, see profiles/)",
+                     "algorithmic_flops_per_launch": flops_per_launch, "kernel_ms": k_ms, "kernel_share_of_step": kernel_share},
+        "mll_grad": {"evals_per_s": 1e3 / (sum(mll_ms) / len(mll_ms)), "ms_per_eval": sum(mll_ms) / len(mll_ms),
+                     "n_train": eng.N, "what": "K_hat build + Cholesky + L^-1 + alpha + -mll + K_hat^-1 + gradient reduce"},
+        "clocks": clocks.summary(),
+    }
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        Xc, yc, Xsc, hyp = X, y, Xs, hyper
+        r, t_pred, t_fac, threads = cpu_oracle_predict_rate(Xc, yc, Xsc, hyp, min(args.cpu_sample, M))
+        line["cpu_baseline"] = {"value": r, "unit": "points/s", "cores": threads, "kind": "port",
+                                "sample": f"first {min(args.cpu_sample, M)} X* points, chunks of 4096, {t_pred:.1f} s "
+                                          f"(factorisation {t_fac:.1f} s excluded)"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

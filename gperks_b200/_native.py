@@ -30,6 +30,7 @@ _SIGS = {
     "gpx_solve_alpha": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, _P]),
     "gpx_mll_value": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P]),
     "gpx_mll_grad": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, _P, C.c_int, _P, _P, _P, _P]),
+    "gpx_trmm_sumsq": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P]),
     "gpx_predict_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "gpx_predict_meanvar": (C.c_int, [_P, C.c_long, _P, C.c_int, C.c_int, _P, _P, _P, C.c_int, _P, C.c_int, _P, _P,
                                       _P, C.c_int, C.c_int, _P, _P, C.c_double, C.c_double, C.c_double, _P, _P, _P,

@@ -1,0 +1,46 @@
+"""Defaults shared across the package (values follow GPErks/constants.py:1-57)."""
+import multiprocessing
+import os
+from pathlib import Path
+
+from scipy.stats import norm
+
+APPLICATION_NAME = "gperks_b200"
+
+# logging
+DEFAULT_LOG_FILE = (Path.home() / f"{APPLICATION_NAME}.log").as_posix()
+DEFAULT_LOG_FORMAT = "%(levelname)s:%(asctime)s:%(module)s:%(funcName)s:L%(lineno)d: %(message)s"
+
+# training
+DEFAULT_TRAIN_MAX_EPOCH = 100
+DEFAULT_TRAIN_SNAPSHOT_FREQUENCY = DEFAULT_TRAIN_MAX_EPOCH / 20
+DEFAULT_TRAIN_SNAPSHOT_DIR = Path(os.getcwd(), "snapshot").as_posix()
+DEFAULT_TRAIN_SNAPSHOT_SPLIT_TEMPLATE = "split_{split}"
+DEFAULT_TRAIN_SNAPSHOT_RESTART_TEMPLATE = "restart_{restart}"
+DEFAULT_TRAIN_SNAPSHOT_EPOCH_TEMPLATE = "epoch_{epoch}.pth"
+
+# inference / cross validation
+DEFAULT_INFERENCE_GRID_DIM = 50
+DEFAULT_CROSS_VALIDATION_N_SPLITS = 5
+DEFAULT_CROSS_VALIDATION_MAX_WORKERS = multiprocessing.cpu_count()
+
+# global sensitivity analysis
+DEFAULT_GSA_CONF_LEVEL = 0.95
+DEFAULT_GSA_Z = norm.ppf(0.5 + DEFAULT_GSA_CONF_LEVEL / 2)
+DEFAULT_GSA_N = 1024
+DEFAULT_GSA_N_BOOTSTRAP = 100
+DEFAULT_GSA_N_DRAWS = 1000
+DEFAULT_GSA_SKIP_VALUES = None
+DEFAULT_GSA_THRESHOLD = 0.01
+
+# plot sizes (kept for API compatibility; plotting libraries are optional)
+HEIGHT = 9.36111
+WIDTH = 5.91667
+
+# miscellanea
+DEFAULT_EXP_N_RESTARTS = 3
+DEFAULT_RANDOM_SEED = 8
+DEFAULT_TMP_OUTFILE_DIR = Path(os.getcwd(), "tmp").as_posix()
+
+# B200 path
+DEFAULT_PREDICT_CHUNK_BYTES = 2 << 30      # HBM budget for one K* chunk in GPEmulator.predict

@@ -14,6 +14,7 @@ int lauum(const double*, const double*, double*, int, cudaStream_t);
 int solve_alpha(const double*, const double*, int, const double*, double*, double*, cudaStream_t);
 int mll_value(const double*, const double*, int, int, const double*, double*, cudaStream_t);
 size_t predict_workspace_bytes(int, int);
+int trmm_sumsq(const double*, int, const double*, int, double*, cudaStream_t);
 int predict_meanvar(const double*, long, const double*, int, int, const double*, const double*, const double*, int,
                     const double*, int, const double*, const double*, const int*, int, int, const double*,
                     const double*, double, double, double, double*, double*, void*, size_t, int, cudaStream_t);
@@ -116,6 +117,12 @@ int gpx_mll_grad(const double* X, int N, int D, const double* theta, int kind, c
     if (check_np(N, Np)) return -7;
     if (D < 1 || D > MAXD) return -3;
     return mll_grad(X, N, D, theta, kind, Kinv, Np, alpha, partial, grad, ST(stream));
+}
+
+int gpx_trmm_sumsq(const double* S, int Np, const double* Ks, int Mc, double* qpart, void* stream) {
+    if (!S || !Ks || !qpart) return -1;
+    if (Np % TILE || Mc % TILE || Np <= 0 || Mc <= 0) return -2;
+    return trmm_sumsq(S, Np, Ks, Mc, qpart, ST(stream));
 }
 
 size_t gpx_predict_workspace_bytes(int Np, int Mc) { return predict_workspace_bytes(Np, Mc); }

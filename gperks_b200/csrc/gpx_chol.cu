@@ -273,9 +273,11 @@ __global__ void mll_value_kernel(const double* __restrict__ r, const double* __r
 // ------------------------------------------------------------------------------------------------
 // host drivers
 // ------------------------------------------------------------------------------------------------
-static bool g_attr_set = false;
+static bool g_attr_set[64] = {false};   // cudaFuncSetAttribute is per device
 static void set_gemm_attrs() {
-    if (g_attr_set) return;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && g_attr_set[dev]) return;
     cudaFuncSetAttribute(potrf_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES);
     cudaFuncSetAttribute(potrf_trailing_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES);
     cudaFuncSetAttribute(trtri_step1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES);
@@ -283,7 +285,7 @@ static void set_gemm_attrs() {
     cudaFuncSetAttribute(lauum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES);
     const int dg = (TILE * DG_LD + 2 * TILE + 2) * 8;
     cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dg);
-    g_attr_set = true;
+    if (dev >= 0 && dev < 64) g_attr_set[dev] = true;
 }
 
 // K (lower tiles valid) -> L in place; diagonal-block inverses into S / DT; per-block log-dets; info.

@@ -102,7 +102,9 @@ __global__ void predict_finalize_kernel(const double* __restrict__ Xs, long m_va
     out_std[m] = y_sigma * sqrt(var);
 }
 
-static bool g_pred_attr = false;
+// cudaFuncSetAttribute is per device: remember which devices have been configured
+static bool g_pred_attr_dev[64] = {false};
+static void set_pred_attrs();
 
 int kmat_cross(const double* Xs, long m_valid, const double* X, int N, int D, const double* theta, const double* xa,
                const double* xr, int kind, const double* alpha, double* Ks, int Np, double* mean_part, int Mc,
@@ -111,6 +113,14 @@ int kmat_cross(const double* Xs, long m_valid, const double* X, int N, int D, co
 size_t predict_workspace_bytes(int Np, int Mc) {
     const size_t nb = Np / TILE;
     return (size_t)Mc * Np * 8 + 2 * nb * (size_t)Mc * 8;
+}
+
+// The variance TRMM alone (bench / tests): qpart[ib][m] = sum_{i in row block ib} (L^-1 K*^T)[i][m]^2
+int trmm_sumsq(const double* S, int Np, const double* Ks, int Mc, double* qpart, cudaStream_t st) {
+    set_pred_attrs();
+    trmm_sumsq_kernel<<<(Np / TILE) * (Mc / TILE), G_THREADS, G_SMEM_BYTES, st>>>(S, Np, Ks, Mc, qpart);
+    GPX_CHECK_LAUNCH();
+    return 0;
 }
 
 // Device-resident predict over M points, processed in chunks of Mc (multiple of 128).
@@ -123,10 +133,7 @@ int predict_meanvar(const double* Xs, long M, const double* X, int N, int D, con
     if (Np % TILE != 0 || Np < N) return -11;
     if (D > MAXD || D < 1) return -5;
     if (workspace_bytes < predict_workspace_bytes(Np, Mc)) return -23;
-    if (!g_pred_attr) {
-        cudaFuncSetAttribute(trmm_sumsq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES);
-        g_pred_attr = true;
-    }
+    set_pred_attrs();
     const int nb = Np / TILE;
     double* Ks = reinterpret_cast<double*>(workspace);
     double* mean_part = Ks + (size_t)Mc * Np;
@@ -144,6 +151,14 @@ int predict_meanvar(const double* Xs, long M, const double* X, int N, int D, con
     }
     GPX_CHECK_LAUNCH();
     return 0;
+}
+
+static void set_pred_attrs() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && g_pred_attr_dev[dev]) return;
+    cudaFuncSetAttribute(trmm_sumsq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES);
+    if (dev >= 0 && dev < 64) g_pred_attr_dev[dev] = true;
 }
 
 }  // namespace gpx

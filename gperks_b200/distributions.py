@@ -1,0 +1,187 @@
+"""Distribution objects returned by ``model(x)`` / ``likelihood(model(x))``.
+
+* ``MultivariateNormal``   -- train-mode prior N(m(X), k(X,X)) with a lazy covariance: nothing is
+  evaluated until the marginal log-likelihood consumes it on the GPU.
+* ``PosteriorDistribution`` -- eval-mode predictive distribution; ``.mean`` / ``.variance`` run the fused
+  predict kernels, ``.covariance_matrix`` / ``.sample`` / ``.log_prob`` form the dense M x M covariance
+  (test-set sized M only; plain cuBLAS/cuSOLVER through torch, not a hot path).
+
+They stand in for gpytorch.distributions.MultivariateNormal as used at GPErks/gp/model.py:21 and
+GPErks/train/emulator.py:336-346, 356-360, 392-394."""
+from __future__ import annotations
+
+import warnings
+from typing import Optional
+
+import torch
+
+F64 = torch.float64
+
+
+def _psd_safe_cholesky(A: torch.Tensor) -> torch.Tensor:
+    L, info = torch.linalg.cholesky_ex(A)
+    if not bool(info.any()):
+        return L
+    eye = torch.eye(A.shape[-1], dtype=A.dtype, device=A.device)
+    for i in range(3):
+        jitter = 1e-8 * 10 ** i
+        L, info = torch.linalg.cholesky_ex(A + jitter * eye)
+        if not bool(info.any()):
+            warnings.warn(f"A not p.d., added jitter of {jitter:.1e} to the diagonal", RuntimeWarning)
+            return L
+    from .engine import NotPSDError
+    raise NotPSDError("Matrix not positive definite after repeatedly adding jitter up to 1.0e-06.")
+
+
+class MultivariateNormal:
+    def __init__(self, mean: torch.Tensor, covariance_matrix, validate_args: bool = False):
+        self._mean = mean
+        self._covar = covariance_matrix
+        self.noise_module = None       # set by likelihood(dist): adds noise * I
+
+    # gpytorch API ---------------------------------------------------------------------------
+    @property
+    def mean(self) -> torch.Tensor:
+        return self._mean
+
+    loc = mean
+
+    @property
+    def lazy_covariance_matrix(self):
+        return self._covar
+
+    @property
+    def covariance_matrix(self) -> torch.Tensor:
+        K = self._covar.to_dense() if hasattr(self._covar, "to_dense") else self._covar
+        if self.noise_module is not None:
+            nz = self.noise_module.noise.detach().reshape(()).to(K.device, K.dtype)
+            K = K + nz * torch.eye(K.shape[-1], dtype=K.dtype, device=K.device)
+        return K
+
+    @property
+    def variance(self) -> torch.Tensor:
+        if hasattr(self._covar, "diagonal") and not torch.is_tensor(self._covar):
+            v = self._covar.diagonal()
+        else:
+            v = torch.diagonal(self._covar)
+        if self.noise_module is not None:
+            v = v + self.noise_module.noise.detach().reshape(()).to(v.device, v.dtype)
+        return v
+
+    @property
+    def stddev(self) -> torch.Tensor:
+        return self.variance.sqrt()
+
+    def with_noise(self, likelihood) -> "MultivariateNormal":
+        out = MultivariateNormal(self._mean, self._covar)
+        out.noise_module = likelihood
+        return out
+
+    def rsample(self, sample_shape=torch.Size()) -> torch.Tensor:
+        K = self.covariance_matrix
+        L = _psd_safe_cholesky(K.to(F64))
+        n = int(torch.Size(sample_shape).numel()) if len(sample_shape) else 1
+        z = torch.randn(K.shape[-1], n, dtype=F64, device=K.device)
+        draws = (self._mean.to(K.device, F64).unsqueeze(-1) + L @ z).T
+        return draws.reshape(*sample_shape, K.shape[-1]).to(self._mean.dtype)
+
+    def sample(self, sample_shape=torch.Size()) -> torch.Tensor:
+        with torch.no_grad():
+            return self.rsample(sample_shape)
+
+    def confidence_region(self):
+        s2 = self.stddev * 2.0
+        return self.mean - s2, self.mean + s2
+
+
+class PosteriorDistribution:
+    """Exact-GP predictive distribution at ``x`` (scaled inputs), evaluated lazily on the GPU."""
+
+    def __init__(self, model, x: torch.Tensor, noisy: bool = False):
+        self.model = model
+        self.x = x if x.dim() > 1 else x.unsqueeze(-1)
+        self.noisy = noisy
+        self._mv = None
+        self._cov = None
+
+    # -- helpers --------------------------------------------------------------------------------
+    def _out(self, t: torch.Tensor) -> torch.Tensor:
+        dt = self.x.dtype if self.x.dtype.is_floating_point else F64
+        return t.to(self.x.device, dt)
+
+    def _mean_var_device(self):
+        if self._mv is None:
+            with torch.no_grad():
+                eng = self.model._factorized_engine()
+                xd = self.x.detach().to(eng.device, F64).contiguous()
+                prior = self.model.mean_module(xd).detach().to(eng.device, F64)
+                mean, std = eng.predict(xd, prior_mean=prior, noisy=self.noisy)
+                self._mv = (mean, std * std)
+        return self._mv
+
+    def _cov_device(self) -> torch.Tensor:
+        if self._cov is None:
+            with torch.no_grad():
+                eng = self.model._factorized_engine()
+                xd = self.x.detach().to(eng.device, F64).contiguous()
+                Ks = eng.cross_kernel(xd)                                   # [M, N]
+                V = eng.linv() @ Ks.T                                       # [N, M]  (library GEMM, small M)
+                Kss = self.model.covar_module.dense(xd, xd).to(eng.device, F64)
+                cov = Kss - V.T @ V
+                if self.noisy:
+                    cov = cov + eng.theta[eng.D + 1] * torch.eye(cov.shape[0], dtype=F64, device=eng.device)
+                self._cov = 0.5 * (cov + cov.T)
+        return self._cov
+
+    # -- gpytorch API ---------------------------------------------------------------------------
+    @property
+    def mean(self) -> torch.Tensor:
+        return self._out(self._mean_var_device()[0])
+
+    loc = mean
+
+    @property
+    def variance(self) -> torch.Tensor:
+        return self._out(self._mean_var_device()[1])
+
+    @property
+    def stddev(self) -> torch.Tensor:
+        return self.variance.sqrt()
+
+    @property
+    def covariance_matrix(self) -> torch.Tensor:
+        return self._out(self._cov_device())
+
+    @property
+    def lazy_covariance_matrix(self):
+        return self.covariance_matrix
+
+    def with_noise(self, likelihood) -> "PosteriorDistribution":
+        return PosteriorDistribution(self.model, self.x, noisy=True)
+
+    def confidence_region(self):
+        s2 = self.stddev * 2.0
+        return self.mean - s2, self.mean + s2
+
+    def rsample(self, sample_shape=torch.Size()) -> torch.Tensor:
+        mean = self._mean_var_device()[0]
+        L = _psd_safe_cholesky(self._cov_device())
+        shape = torch.Size(sample_shape)
+        n = int(shape.numel()) if len(shape) else 1
+        z = torch.randn(mean.shape[0], n, dtype=F64, device=mean.device)
+        draws = (mean.unsqueeze(-1) + L @ z).T
+        return self._out(draws.reshape(*shape, mean.shape[0]))
+
+    def sample(self, sample_shape=torch.Size()) -> torch.Tensor:
+        with torch.no_grad():
+            return self.rsample(sample_shape)
+
+    def log_prob(self, value: torch.Tensor) -> torch.Tensor:
+        mean = self._mean_var_device()[0]
+        cov = self._cov_device()
+        diff = value.detach().to(mean.device, F64).reshape(-1) - mean
+        L = _psd_safe_cholesky(cov)
+        z = torch.linalg.solve_triangular(L, diff.unsqueeze(-1), upper=False).squeeze(-1)
+        M = mean.shape[0]
+        lp = -0.5 * (z @ z) - torch.log(torch.diagonal(L)).sum() - 0.5 * M * 1.8378770664093453
+        return self._out(lp)

@@ -76,7 +76,10 @@ class ExactGPEngine:
         self.grad = torch.zeros(D + 2, dtype=F64, device=dev)
         self.partial = torch.zeros(nb * nb * (D + 2), dtype=F64, device=dev)
         self.theta = torch.zeros(D + 2, dtype=F64, device=dev)
-        self.factor_key = None        # identifies the (theta, resid) the cached factors belong to
+        self.theta_in = torch.zeros(D + 2, dtype=F64, device=dev)      # theta as passed in (before jitter)
+        self.theta_latent = torch.zeros(D + 2, dtype=F64, device=dev)  # theta with noise = 0 (latent variance)
+        self.factored = False
+        self.factor_key = None
         self.has_kinv = False
         self.jitter_used = 0.0
         self._ws: Optional[torch.Tensor] = None
@@ -94,7 +97,11 @@ class ExactGPEngine:
         diagonal with a NumericalWarning, then NotPSDError."""
         with torch.cuda.device(self.device):
             st = nv.stream_ptr()
+            self.factored = False
             self.theta.copy_(theta.detach().reshape(-1))
+            self.theta_in.copy_(self.theta)
+            self.theta_latent.copy_(self.theta)
+            self.theta_latent[self.D + 1] = 0.0
             self.r[: self.N].copy_(resid.detach().reshape(-1))
             p = nv.ptr
             jitter = 0.0
@@ -123,7 +130,19 @@ class ExactGPEngine:
                          p(self.out), st)
         self.has_kinv = False
         self.factor_key = key
+        self.factored = True
         self.n_factorizations += 1
+
+    def matches(self, theta: torch.Tensor, resid: torch.Tensor) -> bool:
+        """True when the cached factors were computed for exactly these hyper-parameters / residuals
+        (bitwise; one tiny device comparison + host read)."""
+        if not self.factored:
+            return False
+        t = theta.detach().reshape(-1)
+        r = resid.detach().reshape(-1)
+        if t.device != self.device or r.device != self.device:
+            t, r = t.to(self.device, F64), r.to(self.device, F64)
+        return bool(torch.equal(t, self.theta_in)) and bool(torch.equal(r, self.r[: self.N]))
 
     def gradients(self) -> torch.Tensor:
         """d(-mll)/d(lengthscale_d, outputscale, noise) for the cached factors -> device [D+2]."""
@@ -156,14 +175,14 @@ class ExactGPEngine:
 
     def predict(self, Xs: torch.Tensor, *, xa: Optional[torch.Tensor] = None, xr: Optional[torch.Tensor] = None,
                 prior_mean: Optional[torch.Tensor] = None, poly: Optional[PolyMeanSpec] = None,
-                y_mu: float = 0.0, y_sigma: float = 1.0, min_var: float = 1e-10,
+                y_mu: float = 0.0, y_sigma: float = 1.0, min_var: float = 1e-10, noisy: bool = True,
                 out_mean: Optional[torch.Tensor] = None, out_std: Optional[torch.Tensor] = None,
                 chunk: Optional[int] = None):
         """Posterior mean and noisy std for device-resident points Xs [M, D] using the cached factors.
 
         ``xa``/``xr``: unit-cube scaler (min, range) applied in-kernel to raw inputs; omit for inputs that
         are already scaled.  Returns (mean, std) device tensors, un-standardised with (y_mu, y_sigma)."""
-        if self.factor_key is None and self.n_factorizations == 0:
+        if not self.factored:
             raise RuntimeError("predict() before factorize()")
         if Xs.dim() == 1:
             Xs = Xs.unsqueeze(-1)
@@ -189,7 +208,8 @@ class ExactGPEngine:
             feat, wts, bias = poly.feat_idx, poly.weights, poly.bias
             n_feat, degree = int(feat.shape[0]), int(poly.degree)
         with torch.cuda.device(self.device):
-            self._launch("gpx_predict_meanvar", p(Xs), M, p(self.X), self.N, self.D, p(self.theta), p(xa), p(xr),
+            theta = self.theta if noisy else self.theta_latent
+            self._launch("gpx_predict_meanvar", p(Xs), M, p(self.X), self.N, self.D, p(theta), p(xa), p(xr),
                          self.kind, p(self.S), self.Np, p(self.alpha), p(prior_mean), p(feat), n_feat, degree,
                          p(wts), p(bias), float(y_mu), float(y_sigma), float(min_var), p(out_mean), p(out_std),
                          p(ws), ws_bytes, Mc, nv.stream_ptr())

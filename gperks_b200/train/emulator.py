@@ -1,0 +1,385 @@
+"""GPEmulator: GPErks' train / predict / sample API (GPErks/train/emulator.py:41-428) on the B200 engine.
+
+Same public surface and control flow as the reference -- restart loop with raw hyper-parameter
+re-initialisation, per-epoch metrics, early stopping and snapshotting hooks, best-restart selection, the
+``best_model.pth`` / ``best_train_stats.json`` symlinks -- while every GP quantity comes from the
+hand-written sm_100a kernels:
+
+* ``_train_step``  : -mll and its analytic gradient (one factorisation, reused by the per-epoch metrics
+  whenever the hyper-parameters did not change in between);
+* ``predict``      : fused, chunked mean + noisy std over arbitrarily many points, inputs un-scaled and
+  outputs un-standardised inside the kernels;
+* ``train_auto``   : L-BFGS-B on -mll through scipy (the reference delegates to botorch's
+  ``fit_gpytorch_mll``, which wraps the same scipy optimiser).
+
+There is no CPU path: without a CUDA device every compute entry raises.
+"""
+from __future__ import annotations
+
+import os
+from collections import defaultdict
+from copy import deepcopy
+from pathlib import Path
+from typing import Dict, List, Optional
+
+import numpy
+import torch
+
+from .. import _native as nv
+from ..constants import (
+    DEFAULT_GSA_N_DRAWS,
+    DEFAULT_PREDICT_CHUNK_BYTES,
+    DEFAULT_TRAIN_MAX_EPOCH,
+    DEFAULT_TRAIN_SNAPSHOT_DIR,
+    DEFAULT_TRAIN_SNAPSHOT_EPOCH_TEMPLATE,
+    DEFAULT_TRAIN_SNAPSHOT_RESTART_TEMPLATE,
+)
+from ..constraints import GreaterThan
+from ..engine import PolyMeanSpec
+from ..gp.experiment import GPExperiment
+from ..log.logger import get_logger
+from ..mlls import ExactMarginalLogLikelihood
+from ..serialization.path import posix_path
+from ..utils.metrics import get_metric_name
+from .early_stop import EarlyStoppingCriterion, NoEarlyStoppingCriterion
+from .snapshot import NeverSaveSnapshottingCriterion, SnapshottingCriterion
+from .train_stats import TrainStats, load_train_stats_from_file
+from .trainable import Trainable
+
+log = get_logger()
+F64 = torch.float64
+
+
+def _default_snapshotting() -> SnapshottingCriterion:
+    return NeverSaveSnapshottingCriterion(
+        posix_path(DEFAULT_TRAIN_SNAPSHOT_DIR, DEFAULT_TRAIN_SNAPSHOT_RESTART_TEMPLATE),
+        DEFAULT_TRAIN_SNAPSHOT_EPOCH_TEMPLATE,
+    )
+
+
+class GPEmulator(Trainable):
+    def __init__(self, experiment: GPExperiment, device: str):
+        self.experiment = experiment
+        self.scaled_data = experiment.scaled_data
+        self.device = torch.device(device)
+        self.learn_noise = experiment.learn_noise
+        self.model = experiment.model
+        if not self.learn_noise:
+            # fixed-noise mode (GPErks/train/emulator.py:53-58)
+            self.model.likelihood.noise_covar.register_constraint("raw_noise", GreaterThan(1e-6))
+            self.model.likelihood.noise = 1e-4
+            self.model.likelihood.noise_covar.raw_noise.requires_grad_(False)
+        self.init_state = deepcopy(self.model.state_dict())
+        self.metrics = experiment.metrics
+        self.restart_idx = None
+        self.criterion = None
+        self.best_train_metrics_score: Dict[str, float] = {}
+        self.best_val_metrics_score: Dict[str, float] = {}
+
+    # ------------------------------------------------------------------------------------------
+    # training
+    # ------------------------------------------------------------------------------------------
+    def _compute_device(self) -> torch.device:
+        """Device the kernels run on: the user's CUDA device, or the current one when ``device='cpu'``
+        (the reference's default in its examples) -- parameters may live on the host, the math never does."""
+        nv.require_cuda()
+        if self.device.type == "cuda":
+            return torch.device("cuda", self.device.index if self.device.index is not None else torch.cuda.current_device())
+        return torch.device("cuda", torch.cuda.current_device())
+
+    def train(self, optimizer,
+              early_stopping_criterion: Optional[EarlyStoppingCriterion] = None,
+              snapshotting_criterion: Optional[SnapshottingCriterion] = None):
+        if early_stopping_criterion is None:
+            early_stopping_criterion = NoEarlyStoppingCriterion(DEFAULT_TRAIN_MAX_EPOCH)
+        if snapshotting_criterion is None:
+            snapshotting_criterion = _default_snapshotting()
+        log.info("Training emulator...")
+        cdev = self._compute_device()
+        with torch.cuda.device(cdev):
+            X_train = self.scaled_data.X_train
+            y_train = self.scaled_data.y_train
+            X_val, y_val = self.scaled_data.X_val, self.scaled_data.y_val
+
+            all_stats: List[TrainStats] = []
+            best_epochs: List[int] = []
+            for restart in range(1, self.experiment.n_restarts + 1):
+                log.info(f"Running restart {restart}...")
+                self.restart_idx = restart
+                stats, best_epoch = self._train_once(X_train, y_train, optimizer, X_val, y_val,
+                                                     early_stopping_criterion, snapshotting_criterion)
+                all_stats.append(stats)
+                best_epochs.append(best_epoch)
+                log.info(f"Run restart {restart}.")
+        log.info("Trained emulator.")
+
+        # best restart: validation loss at each restart's best epoch if available, else training loss
+        key = "val_loss" if self.scaled_data.with_val else "train_loss"
+        losses = [getattr(s, key)[e - 1] for s, e in zip(all_stats, best_epochs)]
+        best_idx = int(numpy.argmin(losses))
+        self.best_train_metrics_score = _scores_at_best(best_epochs, best_idx, [s.train_metrics_score for s in all_stats])
+        if self.scaled_data.with_val:
+            self.best_val_metrics_score = _scores_at_best(best_epochs, best_idx, [s.val_metrics_score for s in all_stats])
+
+        best_restart, best_epoch = best_idx + 1, best_epochs[best_idx]
+        log.info(f"Loading best model (restart: {best_restart}, epoch: {best_epoch})...")
+        best_model_file = snapshotting_criterion.get_snapshot_file_path(best_restart, best_epoch)
+        best_model = torch.load(best_model_file, map_location=torch.device("cpu"))
+        self.model.load_state_dict(best_model)
+        log.info("Loaded best model.")
+
+        root = Path(snapshotting_criterion.snapshot_dir).parent.as_posix()
+        _relink(best_model_file, posix_path(root, "best_model.pth"))
+        best_stats_file = posix_path(Path(best_model_file).parent.as_posix(), "train_stats.json")
+        best_train_stats = load_train_stats_from_file(best_stats_file)
+        _relink(best_stats_file, posix_path(root, "best_train_stats.json"))
+        return best_model, best_train_stats
+
+    def _reinit_hyperparameters(self):
+        """Raw (pre-softplus) values ~ U(log 0.1, log 10) for lengthscales, outputscale and noise; the mean
+        parameters keep their initial state (GPErks/train/emulator.py:230-244)."""
+        lo, hi = numpy.log(1e-1), numpy.log(1e1)
+        draw = lambda n: (hi - lo) * torch.rand(n) + lo  # noqa: E731  (default dtype: same stream as the reference)
+        self.model.initialize(**{
+            "covar_module.base_kernel.raw_lengthscale": draw(self.scaled_data.input_size),
+            "covar_module.raw_outputscale": draw(1),
+        })
+        if self.learn_noise:
+            self.model.likelihood.initialize(raw_noise=draw(1))
+
+    def _train_once(self, X_train, y_train, optimizer, X_val, y_val,
+                    early_stopping_criterion: EarlyStoppingCriterion,
+                    snapshotting_criterion: SnapshottingCriterion):
+        self.model.load_state_dict(self.init_state)
+        if self.restart_idx > 0:
+            self._reinit_hyperparameters()
+        self.criterion = ExactMarginalLogLikelihood(self.model.likelihood, self.model)
+
+        stats = TrainStats(list(map(get_metric_name, self.metrics)))
+        early_stopping_criterion.enable(self.model, stats)
+        snapshotting_criterion.enable(self.model, stats)
+        best_epoch: Optional[int] = None
+        max_epochs = early_stopping_criterion.max_epochs
+        width = len(str(max_epochs))
+        while not early_stopping_criterion.is_verified:
+            stats.current_epoch += 1
+            train_loss = self._train_step(X_train, y_train, optimizer)
+            stats.train_loss.append(train_loss)
+            msg = f"[{stats.current_epoch:>{width}}/{max_epochs:>{width}}] Training Loss: {train_loss:.4f}"
+            snapshotting_criterion.maybe_save(self.restart_idx, stats.current_epoch)
+
+            self.model.eval()
+            with torch.no_grad():
+                for metric in self.metrics:
+                    name, score = self._evaluate_metric(metric, X_train, y_train)
+                    msg += f" - {name}: {score:.4f}"
+                    stats.train_metrics_score[name].append(float(score))
+                if self.scaled_data.with_val:
+                    val_loss = self._val_step(X_val, y_val)
+                    stats.val_loss.append(val_loss)
+                    msg += f" | Validation Loss: {val_loss:.4f}"
+                    for metric in self.metrics:
+                        name, score = self._evaluate_metric(metric, X_val, y_val)
+                        msg += f" - {name}: {score:.4f}"
+                        stats.val_metrics_score[name].append(float(score))
+            log.info(msg)
+
+            best_epoch, best_model = early_stopping_criterion.evaluate()
+            if early_stopping_criterion.is_verified:
+                snapshotting_criterion.model = best_model
+                snapshotting_criterion.save(self.restart_idx, best_epoch)
+
+        stats.best_epoch = best_epoch
+        stats.save_to_file(posix_path(snapshotting_criterion.snapshot_dir.format(restart=self.restart_idx),
+                                      "train_stats.json"))
+        snapshotting_criterion.keep_snapshots_until(self.restart_idx, best_epoch)
+        return stats, best_epoch
+
+    def _train_step(self, X_train, y_train, optimizer) -> float:
+        self.model.train()
+        optimizer.zero_grad()
+        loss = -self.criterion(self.model(X_train), y_train)
+        loss.backward()
+        optimizer.step()
+        return loss.item()
+
+    def _val_step(self, X_val, y_val) -> float:
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            return (-self.criterion(self.model(X_val), y_val)).item()
+
+    def _evaluate_metric(self, metric, X, y):
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")          # GPInputWarning when scoring the training set
+            predictions = self.model.likelihood(self.model(X))
+        mean = predictions.mean
+        name = get_metric_name(metric)
+        if name == "IndependentStandardError":
+            return name, metric(mean.cpu(), torch.sqrt(predictions.variance).cpu(), y.cpu())
+        return name, metric(mean.cpu(), y.cpu())
+
+    def train_auto(self, snap_dir: str = DEFAULT_TRAIN_SNAPSHOT_DIR, maxiter: int = 2000):
+        """L-BFGS-B on -mll over every trainable raw parameter (unbounded: the softplus constraints already
+        keep the constrained values positive), started from the current state."""
+        from scipy.optimize import minimize
+
+        cdev = self._compute_device()
+        self.criterion = ExactMarginalLogLikelihood(self.model.likelihood, self.model)
+        params = [p for p in self.model.parameters() if p.requires_grad]
+        sizes = [p.numel() for p in params]
+        X, y = self.scaled_data.X_train, self.scaled_data.y_train
+
+        def set_flat(x):
+            off = 0
+            with torch.no_grad():
+                for p, n in zip(params, sizes):
+                    p.copy_(torch.as_tensor(x[off:off + n], dtype=p.dtype).reshape(p.shape))
+                    off += n
+
+        def closure(x):
+            set_flat(x)
+            for p in params:
+                p.grad = None
+            try:
+                loss = -self.criterion(self.model(X), y)
+                loss.backward()
+            except RuntimeError:        # not PSD even after jitter: reject the step
+                return 1e10, numpy.zeros_like(x)
+            g = numpy.concatenate([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).cpu().numpy()
+                                   for p in params]).astype(numpy.float64)
+            return float(loss.item()), g
+
+        log.info("Training emulator...")
+        self.model.train()
+        x0 = numpy.concatenate([p.detach().reshape(-1).cpu().numpy() for p in params]).astype(numpy.float64)
+        with torch.cuda.device(cdev):
+            res = minimize(closure, x0, jac=True, method="L-BFGS-B", options={"maxiter": maxiter})
+        set_flat(res.x)
+        self.model.eval()
+        log.info("Trained emulator.")
+
+        snapshot_dir = Path(snap_dir)
+        snapshot_dir.mkdir(parents=True, exist_ok=True)
+        state = {k: v.detach().cpu() for k, v in self.model.state_dict().items()}
+        torch.save(state, posix_path(snapshot_dir, "best_model.pth"))
+        return res
+
+    # ------------------------------------------------------------------------------------------
+    # prediction
+    # ------------------------------------------------------------------------------------------
+    def _as_2d(self, X_new) -> numpy.ndarray:
+        X_new = numpy.asarray(X_new, dtype=numpy.float64)
+        if X_new.ndim == 1:
+            X_new = X_new.reshape(-1, 1) if self.scaled_data.input_size == 1 else X_new.reshape(1, -1)
+        return numpy.ascontiguousarray(X_new)
+
+    def _poly_spec(self, dev) -> Optional[PolyMeanSpec]:
+        mm = self.model.mean_module
+        spec = mm.poly_spec(self.scaled_data.input_size) if hasattr(mm, "poly_spec") else None
+        if spec is None:
+            return None
+        idx, weights, bias = spec
+        degree = max((len(i) for i in idx), default=1)
+        feat = torch.full((max(len(idx), 1), degree), -1, dtype=torch.int32)
+        for p, ids in enumerate(idx):
+            feat[p, :len(ids)] = torch.as_tensor(ids, dtype=torch.int32)
+        w = None if weights is None or len(idx) == 0 else weights.detach().to(dev, F64).reshape(-1).contiguous()
+        b = None if bias is None else bias.detach().to(dev, F64).reshape(-1).contiguous()
+        if w is None:
+            return PolyMeanSpec(feat[:0].to(dev), degree, torch.zeros(0, dtype=F64, device=dev), b)
+        return PolyMeanSpec(feat.to(dev).contiguous(), degree, w, b)
+
+    def predict(self, X_new, with_covar: bool = False):
+        """(y_mean, y_std[, y_covar]) as numpy float64 -- GPErks/train/emulator.py:348-383.
+
+        ``y_std`` is the *noisy* predictive std (likelihood noise included) as in the reference.  Points are
+        streamed through the GPU in chunks (pinned staging, H2D / compute / D2H on the same stream)."""
+        self.model.eval()
+        self.model.likelihood.eval()
+        X_new = self._as_2d(X_new)
+        cdev = self._compute_device()
+        scx, scy = self.scaled_data.scx, self.scaled_data.scy
+        with torch.no_grad(), torch.cuda.device(cdev):
+            eng = self.model._factorized_engine()
+            M = X_new.shape[0]
+            xa = torch.as_tensor(numpy.asarray(scx.a, dtype=numpy.float64).reshape(-1), device=cdev)
+            xr = torch.as_tensor((numpy.asarray(scx.b, dtype=numpy.float64) - numpy.asarray(scx.a, dtype=numpy.float64)).reshape(-1), device=cdev)
+            poly = self._poly_spec(cdev)
+            prior = None
+            x_dev = torch.from_numpy(X_new).pin_memory().to(cdev, non_blocking=True) if M > 0 else torch.empty(0, eng.D, dtype=F64, device=cdev)
+            if poly is None:   # arbitrary user mean: evaluate it with torch on the scaled inputs
+                prior = self.model.mean_module((x_dev - xa) / xr).to(cdev, F64)
+            linear_out = hasattr(scy, "mu") and type(scy).__name__ == "StandardScaler"
+            mean_d, std_d = eng.predict(
+                x_dev, xa=xa, xr=xr, prior_mean=prior, poly=poly,
+                y_mu=float(scy.mu) if linear_out else 0.0, y_sigma=float(scy.sigma) if linear_out else 1.0,
+                chunk=eng.pick_chunk(M, DEFAULT_PREDICT_CHUNK_BYTES) if M > 0 else None)
+            out = torch.empty(2, M, dtype=F64).pin_memory() if M > 0 else torch.empty(2, 0, dtype=F64)
+            out[0].copy_(mean_d, non_blocking=True)
+            out[1].copy_(std_d, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            y_mean, y_std = out[0].numpy().copy(), out[1].numpy().copy()
+            if not linear_out:
+                y_mean, y_std = scy.inverse_transform(y_mean, ystd_=y_std)
+            if not with_covar:
+                return y_mean, y_std
+            x_scaled = ((x_dev - xa) / xr)
+            covar = self.model.likelihood(self.model(x_scaled)).covariance_matrix.cpu().numpy()
+        # un-standardise the covariance the way the reference does (sign * (sigma_y * sqrt|C|)^2)
+        sign = numpy.sign(covar)
+        _, as_std = scy.inverse_transform(y_mean, ystd_=numpy.sqrt(numpy.abs(covar.reshape(-1))))
+        y_covar = sign * numpy.power(as_std.reshape(len(y_std), len(y_std)), 2)
+        return y_mean, y_std, y_covar
+
+    def sample(self, X_new: numpy.ndarray, n_draws: int = DEFAULT_GSA_N_DRAWS):
+        """(n_draws, M) joint posterior-predictive draws -- GPErks/train/emulator.py:385-401."""
+        self.model.eval()
+        self.model.likelihood.eval()
+        X_new = self._as_2d(X_new)
+        cdev = self._compute_device()
+        scx, scy = self.scaled_data.scx, self.scaled_data.scy
+        import warnings
+        with torch.no_grad(), torch.cuda.device(cdev), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            x_scaled = torch.from_numpy(scx.transform(X_new)).to(cdev, F64)
+            predictions = self.model.likelihood(self.model(x_scaled))
+            y_std = numpy.sqrt(predictions.variance.cpu().numpy())
+            draws = predictions.sample(sample_shape=torch.Size([n_draws])).cpu().numpy()
+        for i in range(n_draws):
+            draws[i] = scy.inverse_transform(draws[i], ystd_=y_std)[0]
+        return draws
+
+    # ------------------------------------------------------------------------------------------
+    def hyperparameters(self):
+        torch.set_printoptions(sci_mode=False)
+        m = self.model
+        msg = (f"\nBias: {m.mean_module.bias.data.squeeze():.4f}\n"
+               f"Weights: {m.mean_module.weights.data.squeeze()}\n"
+               f"Outputscale: {m.covar_module.outputscale.data.squeeze():.4f}\n"
+               f"Lengthscales: {m.covar_module.base_kernel.lengthscale.data.squeeze()}")
+        if self.learn_noise:
+            msg += f"\nLikelihood noise: {m.likelihood.noise_covar.noise.data.squeeze():.4f}"
+        print(msg)
+
+    def load_state(self, model_path: str):
+        log.info("Loading model from hyperparameters state dictionary...")
+        self.model.load_state_dict(torch.load(model_path, map_location=torch.device("cpu")))
+        log.info("Loaded model.")
+
+
+def _relink(target: str, link: str):
+    try:
+        os.remove(link)
+    except FileNotFoundError:
+        pass
+    os.symlink(target, link)
+
+
+def _scores_at_best(best_epochs, best_idx, metrics_scores: List[Dict[str, List[float]]]):
+    per_metric = defaultdict(list)
+    for scores, epoch in zip(metrics_scores, best_epochs):
+        for name, values in scores.items():
+            per_metric[name].append(values[epoch - 1])
+    return {name: vals[best_idx] for name, vals in per_metric.items()}

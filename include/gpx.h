@@ -68,6 +68,11 @@ int gpx_mll_value(const double* r, const double* alpha, int Np, int N, const dou
 int gpx_mll_grad(const double* X, int N, int D, const double* theta, int kind, const double* Kinv, int Np,
                  const double* alpha, double* partial, double* grad, void* stream);
 
+/* Variance contraction alone: qpart[ib][m] = sum_{i in 128-row block ib} (L^-1 Ks^T)[i][m]^2 for a chunk
+ * Ks[Mc][Np] (the dominant kernel of gpx_predict_meanvar; exposed for timing and parity tests).
+ * replaces: the K* @ R root product of fast_pred_var, GPErks/train/emulator.py:354-358. */
+int gpx_trmm_sumsq(const double* S, int Np, const double* Ks, int Mc, double* qpart, void* stream);
+
 /* Posterior mean and noisy std for M device-resident raw points, un-standardised with (y_mu, y_sigma).
  * prior mean: prior_mean[M] if non-null, else sum_p weights[p]*prod_q x[feat_idx[p*degree+q]] + bias
  * on the unit-cube inputs.  workspace >= gpx_predict_workspace_bytes(Np, Mc).

@@ -1,0 +1,350 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes -> libgpx.so), against the CPU float64
+oracle on the same seeded inputs, plus the notebook goldens through the public GPEmulator API and
+size-independent properties at BASELINE.json's full size.
+
+Tolerances (float64 path): rel 1e-9 on every intermediate at oracle-sized problems, rel 1e-6 on the
+predictive mean / std demanded by BASELINE.json's north_star (we observe ~1e-12)."""
+import math
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from gperks_b200 import _native as nv
+from oracle import gp_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+F64 = torch.float64
+KINDS = [O.KIND_RBF, O.KIND_MATERN12, O.KIND_MATERN32, O.KIND_MATERN52]
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda:0")
+
+
+def _problem(N, D, M, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    X = torch.rand(N, D, dtype=F64, generator=g)
+    y = torch.randn(N, dtype=F64, generator=g)
+    Xs = torch.rand(M, D, dtype=F64, generator=g) * 1.2 - 0.1
+    ls = torch.tensor([0.5 * (1 + d / D) for d in range(D)], dtype=F64)
+    w = torch.linspace(-1, 1, D, dtype=F64)
+    return X, y, Xs, ls, torch.tensor(1.3, dtype=F64), w, torch.tensor(0.1, dtype=F64)
+
+
+def _engine(dev, X, y, kind, ls, s, nz, w, b):
+    from gperks_b200.engine import ExactGPEngine
+    eng = ExactGPEngine(X.to(dev), kind)
+    theta = torch.cat([1.0 / ls, s.reshape(1), torch.as_tensor(nz, dtype=F64).reshape(1)]).to(dev)
+    resid = (y - (X @ w + b)).to(dev)
+    eng.factorize(theta, resid)
+    return eng
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("N,D", [(1, 1), (7, 1), (127, 3), (128, 2), (129, 4), (300, 8), (640, 12)])
+def test_stagewise_parity_with_oracle(dev, kind, N, D):
+    """kmat_sym -> potrf/logdet -> trtri -> alpha -> -mll -> lauum -> gradient, each against the oracle;
+    covers ragged sizes around the 128 tile edge and the 1-point / 1-dimension corner cases."""
+    X, y, Xs, ls, s, w, b = _problem(N, D, 33, seed=N + kind)
+    nz = 1e-2
+    eng = _engine(dev, X, y, kind, ls, s, nz, w, b)
+    mean_x = X @ w + b
+    K, L, alpha = O.factorize(X, y - mean_x, kind, ls, s, nz)
+    assert int(eng.info.item()) == 0
+    np.testing.assert_allclose(eng.chol().cpu().numpy(), L.numpy(), rtol=0, atol=1e-11 * float(L.abs().max()))
+    Linv = torch.linalg.solve_triangular(L, torch.eye(N, dtype=F64), upper=False)
+    np.testing.assert_allclose(eng.linv().cpu().numpy(), Linv.numpy(), rtol=0, atol=1e-10 * float(Linv.abs().max()))
+    np.testing.assert_allclose(eng.alpha[:N].cpu().numpy(), alpha.numpy(), rtol=0, atol=1e-9 * float(alpha.abs().max()))
+    assert float(eng.alpha[N:].abs().sum()) == 0.0          # padding stays exactly zero
+    loss = float(O.neg_mll(X, y, kind, ls, s, nz, mean_x))
+    assert float(eng.loss) == pytest.approx(loss, rel=1e-10)
+    g = O.neg_mll_analytic_grads(X, y, kind, ls, s, torch.tensor(nz, dtype=F64), mean_x)
+    gref = torch.cat([g["lengthscale"], g["outputscale"].reshape(1), g["noise"].reshape(1)]).numpy()
+    got = eng.gradients().cpu().numpy()
+    np.testing.assert_allclose(got, gref, rtol=1e-8, atol=1e-11 * np.abs(gref).max())
+    Kinv = torch.cholesky_inverse(L)
+    np.testing.assert_allclose(eng.W[:N, :N].cpu().numpy(), Kinv.numpy(), rtol=0, atol=1e-9 * float(Kinv.abs().max()))
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("N,D,M", [(5, 1, 1), (200, 8, 1000), (384, 6, 129), (500, 3, 4097)])
+def test_predict_parity_with_oracle(dev, kind, N, D, M):
+    X, y, Xs, ls, s, w, b = _problem(N, D, M, seed=3 * N + kind)
+    nz = 1e-3
+    eng = _engine(dev, X, y, kind, ls, s, nz, w, b)
+    mref, vref = O.predict(X, y, kind, ls, s, nz, X @ w + b, Xs, Xs @ w + b)
+    mean, std = eng.predict(Xs.to(dev), prior_mean=(Xs @ w + b).to(dev))
+    np.testing.assert_allclose(mean.cpu().numpy(), mref.numpy(), rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(std.cpu().numpy(), vref.sqrt().numpy(), rtol=1e-8)
+    # latent (noise-free) variance and the dense cross-kernel entry point
+    _, std_lat = eng.predict(Xs.to(dev), prior_mean=(Xs @ w + b).to(dev), noisy=False)
+    np.testing.assert_allclose((std_lat ** 2).cpu().numpy(), (vref - nz).clamp_min(1e-10).numpy(), rtol=1e-6, atol=1e-11)
+    Ks = O.kernel_matrix(Xs, X, kind, ls, s)
+    np.testing.assert_allclose(eng.cross_kernel(Xs.to(dev)).cpu().numpy(), Ks.numpy(), rtol=1e-12, atol=1e-15)
+    # chunking must not change a single bit (no cross-chunk reduction)
+    mean2, std2 = eng.predict(Xs.to(dev), prior_mean=(Xs @ w + b).to(dev), chunk=128)
+    assert torch.equal(mean, mean2) and torch.equal(std, std2)
+
+
+def test_trmm_sumsq_entry_point(dev):
+    """The dominant kernel alone, through its own C-ABI entry."""
+    N, D, M = 640, 5, 384
+    X, y, Xs, ls, s, w, b = _problem(N, D, M, seed=11)
+    eng = _engine(dev, X, y, O.KIND_MATERN52, ls, s, 1e-2, w, b)
+    lib = nv.lib()
+    Ks = torch.zeros(M, eng.Np, dtype=F64, device=dev)
+    Ks[:, :N] = torch.randn(M, N, dtype=F64, device=dev)
+    qpart = torch.empty(eng.nb, M, dtype=F64, device=dev)
+    nv.check(lib.gpx_trmm_sumsq(nv.ptr(eng.S), eng.Np, nv.ptr(Ks), M, nv.ptr(qpart), nv.stream_ptr()), "trmm")
+    V = eng.linv().cpu() @ Ks[:, :N].cpu().T
+    np.testing.assert_allclose(qpart.sum(0).cpu().numpy(), (V * V).sum(0).numpy(), rtol=1e-11)
+
+
+def test_failed_cholesky_reports_info_and_jitter_path(dev):
+    from gperks_b200.engine import ExactGPEngine, NotPSDError
+    X = torch.rand(40, 2, dtype=F64)
+    eng = ExactGPEngine(X.to(dev), O.KIND_RBF)
+    theta = torch.tensor([1.0, 1.0, 1.0, -0.5], dtype=F64, device=dev)      # K - 0.5 I is indefinite
+    with warnings.catch_warnings(record=True) as rec:
+        warnings.simplefilter("always")
+        with pytest.raises(NotPSDError):
+            eng.factorize(theta, torch.zeros(40, dtype=F64, device=dev))
+    assert len(rec) == 3, "one NumericalWarning per jitter level (1e-8, 1e-7, 1e-6), as psd_safe_cholesky"
+    # LAPACK-style info (1-based index of the first non-positive pivot) without the retry loop
+    eng.factorize(theta, torch.zeros(40, dtype=F64, device=dev), check=False)
+    info = int(eng.info.item())
+    Kref = O.kernel_matrix(X, X, O.KIND_RBF, torch.ones(2, dtype=F64), 1.0) - 0.5 * torch.eye(40, dtype=F64)
+    _, ref_info = torch.linalg.cholesky_ex(Kref)
+    assert info == int(ref_info) and info > 0
+
+
+# ----------------------------------------------------------------------------------------------------
+# public API: notebook goldens + oracle parity through GPExperiment / GPEmulator
+# ----------------------------------------------------------------------------------------------------
+def _emulator_from_golden(g, name):
+    from gperks_b200.gp.data.dataset import Dataset
+    from gperks_b200.gp.experiment import GPExperiment
+    from gperks_b200.gp.mean import LinearMean
+    from gperks_b200.kernels import MaternKernel, RBFKernel, ScaleKernel
+    from gperks_b200.likelihoods import GaussianLikelihood
+    from gperks_b200.means import LinearMean as GpLinearMean
+    from gperks_b200.train.emulator import GPEmulator
+    from gperks_b200.utils.metrics import MeanSquaredError, R2Score
+    d = g["data"]
+    Xtr = np.array(d["X_train"])
+    if Xtr.ndim == 1:
+        Xtr = Xtr[:, None]
+    Xte = np.array(d["X_test"])
+    if Xte.ndim == 1:
+        Xte = Xte[:, None]
+    ds = Dataset(Xtr, np.array(d["y_train"]), X_test=Xte, y_test=np.array(d["y_test"]))
+    D = Xtr.shape[1]
+    kernel = ScaleKernel(RBFKernel(ard_num_dims=D) if g["kernel"] == "rbf" else MaternKernel(ard_num_dims=D))
+    mean = GpLinearMean(D) if (g["mean_degree"] == 1 and name != "example_9") else LinearMean(g["mean_degree"], D)
+    exp = GPExperiment(ds, GaussianLikelihood(), mean, kernel, n_restarts=1, seed=8,
+                       metrics=[MeanSquaredError(), R2Score()])
+    em = GPEmulator(exp, "cuda:0")
+    m = em.model
+    t = lambda v: torch.as_tensor(v, dtype=F64)  # noqa: E731
+    if "raw" in g:
+        r = g["raw"]
+        m.likelihood.initialize(raw_noise=t([r["raw_noise"]]))
+        m.initialize(**{"covar_module.raw_outputscale": t(r["raw_outputscale"]),
+                        "covar_module.base_kernel.raw_lengthscale": t(r["raw_lengthscale"]),
+                        "mean_module.weights": t(r["weights"]), "mean_module.bias": t([r["bias"]])})
+    else:
+        a = g["actual"]
+        m.likelihood.noise = a["noise"]
+        m.covar_module.outputscale = a["outputscale"]
+        m.covar_module.base_kernel.lengthscale = t(a["lengthscale"])
+        m.initialize(**{"mean_module.weights": t(a["weights"]), "mean_module.bias": t([a["bias"]])})
+    return em, ds
+
+
+def test_notebook_golden_example_2(dev, goldens):
+    g = goldens["example_2"]
+    em, ds = _emulator_from_golden(g, "example_2")
+    mean, std, covar = em.predict(ds.X_test, with_covar=True)
+    p = g["printed"]
+    assert O.mse(mean, ds.y_test) == pytest.approx(p["MSE"], abs=5e-4)
+    assert O.r2score(mean, ds.y_test) == pytest.approx(p["R2"], abs=5e-4)
+    assert O.chi_squared(mean, std, ds.y_test) == pytest.approx(p["chi2"], rel=2e-4)
+    assert O.mahalanobis(mean, covar, ds.y_test) == pytest.approx(p["mahalanobis"], rel=2e-4)
+    assert O.ise(mean, std, ds.y_test) == pytest.approx(p["CI"], abs=1e-12)
+    # training loss at the same parameters == the notebook's epoch-100 log line
+    from gperks_b200.mlls import ExactMarginalLogLikelihood
+    em.model.train()
+    mll = ExactMarginalLogLikelihood(em.model.likelihood, em.model)
+    loss = -mll(em.model(em.scaled_data.X_train), em.scaled_data.y_train)
+    assert float(loss) == pytest.approx(p["train_loss"], abs=5e-5)
+
+
+def test_notebook_golden_example_9_and_1(dev, goldens):
+    g = goldens["example_9"]
+    em, ds = _emulator_from_golden(g, "example_9")
+    mean, std = em.predict(ds.X_test)
+    assert O.mse(mean, ds.y_test) == pytest.approx(g["printed"]["MSE"], abs=5e-4)
+    assert O.r2score(mean, ds.y_test) == pytest.approx(g["printed"]["R2"], abs=5e-4)
+    assert O.ise(mean, std, ds.y_test) == pytest.approx(g["printed"]["ISE"], abs=1e-12)
+    g = goldens["example_1"]
+    em, ds = _emulator_from_golden(g, "example_1")
+    mean, std = em.predict(ds.X_test[:, 0])            # 1-D inputs may be passed flat (examples/example_1.py)
+    assert O.mse(mean, ds.y_test) == pytest.approx(g["printed"]["MSE"], rel=1e-3)
+    assert O.r2score(mean, ds.y_test) == pytest.approx(g["printed"]["R2"], rel=1e-3)
+
+
+@pytest.mark.parametrize("name", ["example_2", "example_9", "example_1"])
+def test_emulator_matches_oracle_emulator(dev, goldens, name):
+    """Same inputs and hyper-parameters through GPEmulator (CUDA) and OracleEmulator (CPU): rel 1e-6 bar."""
+    g = goldens[name]
+    em, ds = _emulator_from_golden(g, name)
+    m = em.model
+    kind = O.KIND_RBF if g["kernel"] == "rbf" else O.KIND_MATERN52
+    orc = O.OracleEmulator(ds.X_train, ds.y_train, kind=kind,
+                           lengthscale=m.covar_module.base_kernel.lengthscale.detach(),
+                           outputscale=m.covar_module.outputscale.detach(), noise=m.likelihood.noise.detach(),
+                           weights=m.mean_module.weights.detach(), bias=m.mean_module.bias.detach(),
+                           degree=g["mean_degree"])
+    rng = np.random.default_rng(0)
+    Xq = ds.X_train.min(0) + rng.random((777, ds.X_train.shape[1])) * (ds.X_train.max(0) - ds.X_train.min(0))
+    mean, std, covar = em.predict(Xq[:60], with_covar=True)
+    om, os_, oc = orc.predict(Xq[:60], with_covar=True)
+    np.testing.assert_allclose(mean, om, rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(std, os_, rtol=1e-6)
+    np.testing.assert_allclose(covar, oc, rtol=1e-5, atol=1e-9 * np.abs(oc).max())
+    mean, std = em.predict(Xq)
+    om, os_ = orc.predict(Xq)
+    np.testing.assert_allclose(mean, om, rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(std, os_, rtol=1e-6)
+    # empty input and sampling moments
+    e_mean, e_std = em.predict(np.empty((0, ds.X_train.shape[1])))
+    assert e_mean.shape == (0,) and e_std.shape == (0,)
+    torch.manual_seed(0)
+    draws = em.sample(Xq[:8], n_draws=20000)
+    assert draws.shape == (20000, 8)
+    m8, s8, c8 = orc.predict(Xq[:8], with_covar=True)
+    np.testing.assert_allclose(draws.mean(0), m8, atol=5 * s8.max() / np.sqrt(20000) + 1e-9)
+    np.testing.assert_allclose(draws.std(0), s8, rtol=0.05)
+
+
+def test_adam_training_follows_oracle_autograd(dev, goldens):
+    """Five Adam steps through GPEmulator._train_step vs the same steps with torch autograd through the
+    oracle's float64 Cholesky: pins the analytic CUDA gradients, the softplus chain and the mean gradient."""
+    g = goldens["example_2"]
+    em, ds = _emulator_from_golden(g, "example_2")
+    from gperks_b200.mlls import ExactMarginalLogLikelihood
+    m = em.model
+    em.criterion = ExactMarginalLogLikelihood(m.likelihood, m)
+    opt = torch.optim.Adam(m.parameters(), lr=0.05)
+    # oracle-side copies of the raw parameters
+    raw = {k: v.detach().clone().requires_grad_(True) for k, v in m.named_parameters()}
+    oopt = torch.optim.Adam([raw[k] for k, _ in m.named_parameters()], lr=0.05)
+    X, y = em.scaled_data.X_train, em.scaled_data.y_train
+
+    def oracle_loss():
+        ls = O.softplus(raw["covar_module.base_kernel.raw_lengthscale"]).reshape(-1)
+        s = O.softplus(raw["covar_module.raw_outputscale"])
+        nz = O.softplus(raw["likelihood.noise_covar.raw_noise"]).reshape(()) + 1e-4
+        mean_x = (X @ raw["mean_module.weights"]).squeeze(-1) + raw["mean_module.bias"]
+        return O.neg_mll(X, y, O.KIND_RBF, ls, s, nz, mean_x)
+
+    for step in range(5):
+        loss = em._train_step(X, y, opt)
+        oopt.zero_grad()
+        ol = oracle_loss()
+        ol.backward()
+        oopt.step()
+        assert loss == pytest.approx(float(ol), rel=1e-9), f"step {step}"
+    for k, p in m.named_parameters():
+        np.testing.assert_allclose(p.detach().numpy(), raw[k].detach().numpy(), rtol=1e-7, atol=1e-9, err_msg=k)
+
+
+def test_full_train_api_runs_and_improves(dev, tmp_path):
+    from gperks_b200.gp.data.dataset import Dataset
+    from gperks_b200.gp.experiment import GPExperiment
+    from gperks_b200.gp.mean import LinearMean
+    from gperks_b200.kernels import RBFKernel, ScaleKernel
+    from gperks_b200.likelihoods import GaussianLikelihood
+    from gperks_b200.train.early_stop import GLEarlyStoppingCriterion
+    from gperks_b200.train.emulator import GPEmulator
+    from gperks_b200.train.snapshot import EveryEpochSnapshottingCriterion
+    from gperks_b200.utils.metrics import IndependentStandardError, MeanSquaredError, R2Score
+    from gperks_b200.utils.test_functions import currin_exp
+    ds = Dataset.build_from_function(currin_exp, 2, 40, 10, 25, "lhs", 8)
+    exp = GPExperiment(ds, GaussianLikelihood(), LinearMean(1, 2), ScaleKernel(RBFKernel(ard_num_dims=2)),
+                       n_restarts=2, seed=8, metrics=[MeanSquaredError(), R2Score(), IndependentStandardError()])
+    em = GPEmulator(exp, "cuda:0")
+    opt = torch.optim.Adam(exp.model.parameters(), lr=0.1)
+    snap = EveryEpochSnapshottingCriterion((tmp_path / "restart_{restart}").as_posix(), "epoch_{epoch}.pth")
+    best_model, stats = em.train(opt, GLEarlyStoppingCriterion(60, alpha=0.5, patience=8), snap)
+    assert (tmp_path / "best_model.pth").exists() and (tmp_path / "best_train_stats.json").exists()
+    assert stats.train_loss[stats.best_epoch - 1] < stats.train_loss[0]
+    assert len(stats.val_loss) == len(stats.train_loss)
+    assert set(em.best_val_metrics_score) == {"MeanSquaredError", "R2Score", "IndependentStandardError"}
+    mean, std = em.predict(ds.X_test)
+    assert O.r2score(mean, ds.y_test) > 0.8
+    # the snapshot reloads into a fresh emulator and reproduces the predictions bit for bit
+    exp2 = GPExperiment(ds, GaussianLikelihood(), LinearMean(1, 2), ScaleKernel(RBFKernel(ard_num_dims=2)), seed=8)
+    em2 = GPEmulator(exp2, "cuda:0")
+    em2.load_state((tmp_path / "best_model.pth").as_posix())
+    mean2, std2 = em2.predict(ds.X_test)
+    assert np.array_equal(mean, mean2) and np.array_equal(std, std2)
+    # train_auto (L-BFGS-B) lowers the loss further or equal
+    res = em2.train_auto((tmp_path / "auto").as_posix())
+    assert (tmp_path / "auto" / "best_model.pth").exists()
+    assert np.isfinite(res.fun) and res.fun <= stats.train_loss[0]
+
+
+# ----------------------------------------------------------------------------------------------------
+# BASELINE.json full size: size-independent properties (the oracle is too slow here)
+# ----------------------------------------------------------------------------------------------------
+def test_full_size_properties_n8192(dev):
+    N, D, M = 8192, 8, 4096
+    X, y, Xs, ls, s, w, b = _problem(N, D, M, seed=5)
+    nz = 1e-2
+    eng = _engine(dev, X, y, O.KIND_MATERN52, ls, s, nz, w, b)
+    assert int(eng.info.item()) == 0
+    # (1) L L^T reproduces K_hat on random probes:  ||L (L^T v) - K_hat v|| / ||K_hat v||
+    lib = nv.lib()
+    Kh = torch.empty_like(eng.K)
+    nv.check(lib.gpx_kmat_sym(nv.ptr(eng.X), N, D, nv.ptr(eng.theta), O.KIND_MATERN52, nv.ptr(Kh), eng.Np,
+                              nv.stream_ptr()), "kmat")
+    Kfull = torch.tril(Kh) + torch.tril(Kh, -1).T
+    v = torch.randn(N, 4, dtype=F64, device=dev)
+    L = eng.chol()
+    assert float((L @ (L.T @ v) - Kfull @ v).norm() / (Kfull @ v).norm()) < 1e-13
+    # (2) L^-1 L = I on probes, and alpha solves K_hat alpha = r
+    assert float((eng.linv() @ (L @ v) - v).norm() / v.norm()) < 1e-11
+    assert float((Kfull @ eng.alpha[:N] - eng.r[:N]).norm() / eng.r[:N].norm()) < 1e-10
+    # (3) interpolation property: at the training inputs the latent mean is K alpha and the latent variance
+    #     is s - k^T K_hat^-1 k  => compare against cuBLAS on a slice of training points
+    idx = torch.arange(0, N, 16, device=dev)
+    pm = (X @ w + b).to(dev)[idx]
+    mean, std = eng.predict(eng.X[idx], prior_mean=pm)
+    Kc = Kfull[idx] - nz * torch.eye(N, dtype=F64, device=dev)[idx]
+    np.testing.assert_allclose(mean.cpu().numpy(), (pm + Kc @ eng.alpha[:N]).cpu().numpy(), rtol=1e-9, atol=1e-10)
+    V = eng.linv() @ Kc.T
+    var = (s.to(dev) + nz - (V * V).sum(0)).clamp_min(1e-10)
+    np.testing.assert_allclose(std.cpu().numpy(), var.sqrt().cpu().numpy(), rtol=1e-8)
+    assert float(std.min()) >= math.sqrt(nz) * (1 - 1e-9)       # noisy variance >= noise
+    # (4) linearity of the posterior mean in y:  mean(y1 + y2) - prior = (mean(y1)-prior) + (mean(y2)-prior)
+    Xq = Xs.to(dev)
+    zero = torch.zeros(M, dtype=F64, device=dev)
+    y2 = torch.randn(N, dtype=F64, device=dev)
+    r1 = eng.r[:N].clone()
+    m1, s1 = eng.predict(Xq, prior_mean=zero)
+    eng.factorize(eng.theta_in.clone(), y2)
+    m2, s2 = eng.predict(Xq, prior_mean=zero)
+    eng.factorize(eng.theta_in.clone(), r1 + y2)
+    m12, s12 = eng.predict(Xq, prior_mean=zero)
+    np.testing.assert_allclose(m12.cpu().numpy(), (m1 + m2).cpu().numpy(), rtol=1e-9, atol=1e-9)
+    assert torch.equal(s1, s2) and torch.equal(s1, s12)         # the variance does not depend on y
+    # (5) determinism / chunk invariance at full size
+    m12b, s12b = eng.predict(Xq, prior_mean=zero, chunk=1024)
+    assert torch.equal(m12, m12b) and torch.equal(s12, s12b)
