@@ -319,7 +319,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": int(M * DIM * 8), "d2h_bytes_per_step": int(M * 16),
                 "steps": e2e_steps, "api": "GPEmulator.predict(numpy)", "max_abs_diff_vs_device_arm": parity},
         "gpu_launches": int(args.steps * n_chunks * 3),
-        "roofline": {"kernel": "trmm_sumsq_kernel (variance contraction L^-1 K*^T, FP64 DMMA)", "bound": "tensor",
+        "roofline": {"kernel": "trmm_sumsq_tma_kernel (variance contraction L^-1 K*^T: TMA + mbarrier ring, FP64 DMMA)", "bound": "tensor",
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
                      "peak_source": "gpx_peak_dmma probe measured in this run (FP64 DMMA.8x8x4 issue peak; MEASURED_PEAKS.json "
                                     "has no FP64 figure; cuBLAS DGEMM 8192^3 measured 35.5 TF/s on this pool, see profiles/)",

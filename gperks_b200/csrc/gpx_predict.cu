@@ -10,6 +10,8 @@
 //                            epilogue into qpart[i_blk][m]
 //   3. predict_finalize      deterministic sums over the partials, prior mean, clamp, sqrt, unscale
 #include "gpx_common.cuh"
+#include "gpx_tma.cuh"
+#include <stdlib.h>
 
 namespace gpx {
 
@@ -53,6 +55,169 @@ trmm_sumsq_kernel(const double* __restrict__ S, int Np, const double* __restrict
     __syncthreads();
     if (threadIdx.x < TILE)
         qpart[(long)ib * Mc + (long)mb * TILE + threadIdx.x] = red[threadIdx.x] + red[TILE + threadIdx.x];
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// TMA version of the variance contraction (default).  Same tile / warp layout and DMMA inner loop as
+// trmm_sumsq_kernel, but operand tiles arrive by cp.async.bulk.tensor (one elected producer thread, 128-byte
+// swizzled 128 x 16 boxes) through a 6-stage full/empty mbarrier ring, so the 8 MMA warps issue nothing but
+// LDS.128 + DMMA and never meet at a CTA-wide barrier inside the k loop.
+//
+// Rasterisation: row blocks are walked in bands of T_BAND (heaviest band first); inside a band consecutive
+// CTAs share the K* panel (same mb) and differ in ib, so a resident wave touches ~T_BAND L^-1 panels and
+// ~148/T_BAND K* panels instead of 1 and 148: each K* panel is fetched from HBM once per band, not once
+// per row block.
+// ------------------------------------------------------------------------------------------------
+constexpr int T_STAGES = 6;
+constexpr int T_TILE_BYTES = TILE * G_BK * 8;            // 16 KB: 128 rows x 128 B
+constexpr int T_STAGE_BYTES = 2 * T_TILE_BYTES;
+constexpr int T_CONSUMERS = 256;
+constexpr int T_THREADS = T_CONSUMERS;      // no dedicated producer warp: thread 0 refills the ring 2 tiles behind
+constexpr int T_BAND = 8;
+constexpr size_t T_SMEM_BYTES = 1024 + size_t(T_STAGES) * T_STAGE_BYTES + 2 * TILE * 8 + 2 * T_STAGES * 8;
+
+__global__ void __launch_bounds__(T_THREADS, 1)
+trmm_sumsq_tma_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmK, int Np, int Mc,
+                      double* __restrict__ qpart) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    double* red = reinterpret_cast<double*>(base + size_t(T_STAGES) * T_STAGE_BYTES);       // [2][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(red + 2 * TILE);                           // full[S], empty[S]
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + T_STAGES);
+    const uint32_t tile0 = smem_u32(base);
+
+    const int n_mb = Mc / TILE, nb = Np / TILE;
+    // band-major rasterisation (see above)
+    int id = blockIdx.x;
+    int ib, mb;
+    {
+        const int per_full_band = T_BAND * n_mb;
+        int band = id / per_full_band;
+        int hi = nb - band * T_BAND;                 // row blocks [hi - width, hi)
+        int width = hi < T_BAND ? hi : T_BAND;
+        int rem = id - band * per_full_band;
+        mb = rem / width;
+        ib = hi - 1 - (rem - mb * width);
+    }
+    const int nk = (ib + 1) * (TILE / G_BK);
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < T_STAGES; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, T_CONSUMERS / 32);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    // prologue: thread 0 fills every stage of the ring
+    if (tid == 0) {
+        tma_prefetch_desc(&tmS);
+        tma_prefetch_desc(&tmK);
+        const int npro = nk < T_STAGES ? nk : T_STAGES;
+        for (int kt = 0; kt < npro; ++kt) {
+            mbar_arrive_expect_tx(full0 + 8 * kt, T_STAGE_BYTES);
+            const uint32_t dst = tile0 + kt * T_STAGE_BYTES;
+            tma_load_2d(dst, &tmS, kt * G_BK, ib * TILE, full0 + 8 * kt);
+            tma_load_2d(dst + T_TILE_BYTES, &tmK, kt * G_BK, mb * TILE, full0 + 8 * kt);
+        }
+    }
+
+    // ===== 8 MMA warps =====
+    const int lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 2, wn = warp & 3;
+    const int lr = lane >> 2, lc = lane & 3;
+    const int off0 = ((2 * lc) ^ lr) * 16, off1 = off0 ^ 16;      // 128B-swizzled 16-byte chunk positions
+    double acc[8][4][2];
+#pragma unroll
+    for (int s = 0; s < 8; ++s)
+#pragma unroll
+        for (int n = 0; n < 4; ++n) { acc[s][n][0] = 0.0; acc[s][n][1] = 0.0; }
+
+    for (int kt = 0; kt < nk; ++kt) {
+        const int s_ = kt % T_STAGES, round = kt / T_STAGES;
+        if (tid == 0) {
+            // refill the stage that every warp released two iterations ago with k-tile kt + S - 2
+            const int kl = kt + T_STAGES - 2;
+            if (kt >= 2 && kl < nk) {
+                const int sl = kl % T_STAGES;
+                mbar_wait(empty0 + 8 * sl, ((kl / T_STAGES) - 1) & 1);
+                mbar_arrive_expect_tx(full0 + 8 * sl, T_STAGE_BYTES);
+                const uint32_t dst = tile0 + sl * T_STAGE_BYTES;
+                tma_load_2d(dst, &tmS, kl * G_BK, ib * TILE, full0 + 8 * sl);
+                tma_load_2d(dst + T_TILE_BYTES, &tmK, kl * G_BK, mb * TILE, full0 + 8 * sl);
+            }
+        }
+        __syncwarp();
+        mbar_wait(full0 + 8 * s_, round & 1);
+        const unsigned char* at = base + s_ * T_STAGE_BYTES + (wm * 64 + lr) * 128;
+        const unsigned char* bt = base + s_ * T_STAGE_BYTES + T_TILE_BYTES + (wn * 32 + lr) * 128;
+        double bf[4][4];
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+            double2 v0 = *reinterpret_cast<const double2*>(bt + n * 1024 + off0);
+            double2 v1 = *reinterpret_cast<const double2*>(bt + n * 1024 + off1);
+            bf[n][0] = v0.x; bf[n][1] = v0.y; bf[n][2] = v1.x; bf[n][3] = v1.y;
+        }
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            double2 a0 = *reinterpret_cast<const double2*>(at + s * 1024 + off0);
+            double2 a1 = *reinterpret_cast<const double2*>(at + s * 1024 + off1);
+            double af[4] = {a0.x, a0.y, a1.x, a1.y};
+#pragma unroll
+            for (int st = 0; st < 4; ++st)
+#pragma unroll
+                for (int n = 0; n < 4; ++n) dmma884(acc[s][n][0], acc[s][n][1], af[st], bf[n][st]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0 + 8 * s_);
+    }
+
+    // epilogue: column sums of squares over the 128 rows of the tile
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+        double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            c0 = fma(acc[s][n][0], acc[s][n][0], c0);
+            c1 = fma(acc[s][n][1], acc[s][n][1], c1);
+        }
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+            c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+            c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+        }
+        if (lr == 0) {
+            red[wm * TILE + wn * 32 + n * 8 + 2 * lc] = c0;
+            red[wm * TILE + wn * 32 + n * 8 + 2 * lc + 1] = c1;
+        }
+    }
+    named_bar_sync(1, T_CONSUMERS);
+    if (tid < TILE) qpart[(long)ib * Mc + (long)mb * TILE + tid] = red[tid] + red[TILE + tid];
+}
+
+static int use_tma_impl() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("GPX_TRMM_IMPL");
+        v = (e && e[0] == 'c') ? 0 : 1;          // GPX_TRMM_IMPL=cpasync selects the LDGSTS version
+    }
+    return v;
+}
+
+static int launch_trmm(const double* S, int Np, const double* Ks, int Mc, double* qpart, cudaStream_t st) {
+    if (!use_tma_impl()) {
+        trmm_sumsq_kernel<<<(Np / TILE) * (Mc / TILE), G_THREADS, G_SMEM_BYTES, st>>>(S, Np, Ks, Mc, qpart);
+        return 0;
+    }
+    CUtensorMap tmS, tmK;
+    int rc = encode_f64_rowmajor(&tmS, S, Np, Np, Np, TILE);
+    if (rc) return rc;
+    rc = encode_f64_rowmajor(&tmK, Ks, Mc, Np, Np, TILE);
+    if (rc) return rc;
+    trmm_sumsq_tma_kernel<<<(Np / TILE) * (Mc / TILE), T_THREADS, T_SMEM_BYTES, st>>>(tmS, tmK, Np, Mc, qpart);
+    return 0;
 }
 
 // One thread per test point of the chunk.
@@ -118,7 +283,8 @@ size_t predict_workspace_bytes(int Np, int Mc) {
 // The variance TRMM alone (bench / tests): qpart[ib][m] = sum_{i in row block ib} (L^-1 K*^T)[i][m]^2
 int trmm_sumsq(const double* S, int Np, const double* Ks, int Mc, double* qpart, cudaStream_t st) {
     set_pred_attrs();
-    trmm_sumsq_kernel<<<(Np / TILE) * (Mc / TILE), G_THREADS, G_SMEM_BYTES, st>>>(S, Np, Ks, Mc, qpart);
+    int rc = launch_trmm(S, Np, Ks, Mc, qpart, st);
+    if (rc) return rc;
     GPX_CHECK_LAUNCH();
     return 0;
 }
@@ -144,7 +310,8 @@ int predict_meanvar(const double* Xs, long M, const double* X, int N, int D, con
         const double* xs = Xs + m0 * D;
         int rc = kmat_cross(xs, mv, X, N, D, theta, xa, xr, kind, alpha, Ks, Np, mean_part, mc, st);
         if (rc) return rc;
-        trmm_sumsq_kernel<<<nb * (mc / TILE), G_THREADS, G_SMEM_BYTES, st>>>(S, Np, Ks, mc, qpart);
+        rc = launch_trmm(S, Np, Ks, mc, qpart, st);
+        if (rc) return rc;
         predict_finalize_kernel<<<(int)((mv + 255) / 256), 256, 0, st>>>(
             xs, mv, D, xa, xr, theta, mean_part, qpart, nb, mc, prior_mean ? prior_mean + m0 : nullptr, feat_idx,
             n_feat, degree, weights, bias, y_mu, y_sigma, min_var, out_mean + m0, out_std + m0);
@@ -158,6 +325,7 @@ static void set_pred_attrs() {
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && g_pred_attr_dev[dev]) return;
     cudaFuncSetAttribute(trmm_sumsq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES);
+    cudaFuncSetAttribute(trmm_sumsq_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T_SMEM_BYTES);
     if (dev >= 0 && dev < 64) g_pred_attr_dev[dev] = true;
 }
 
