@@ -15,6 +15,8 @@ int solve_alpha(const double*, const double*, int, const double*, double*, doubl
 int mll_value(const double*, const double*, int, int, const double*, double*, cudaStream_t);
 size_t predict_workspace_bytes(int, int);
 int trmm_sumsq(const double*, int, const double*, int, double*, cudaStream_t);
+int implausibility(const double*, const double*, long, int, const double*, const double*, int, double*, double*,
+                   cudaStream_t);
 int predict_meanvar(const double*, long, const double*, int, int, const double*, const double*, const double*, int,
                     const double*, int, const double*, const double*, const int*, int, int, const double*,
                     const double*, double, double, double, double*, double*, void*, size_t, int, cudaStream_t);
@@ -141,6 +143,13 @@ int gpx_predict_meanvar(const double* Xs, long M, const double* X, int N, int D,
     return predict_meanvar(Xs, M, X, N, D, theta, xa, xr, kind, S, Np, alpha, prior_mean, feat_idx, n_feat, degree,
                            weights, bias, y_mu, y_sigma, min_var, out_mean, out_std, workspace, workspace_bytes, Mc,
                            ST(stream));
+}
+
+int gpx_implausibility(const double* mean, const double* std_, long M, int E, const double* z, const double* v,
+                       int maxno, double* I, double* PV, void* stream) {
+    if (!mean || !std_ || !z || !v || !I || !PV) return -1;
+    if (M < 0 || E < 1) return -3;
+    return implausibility(mean, std_, M, E, z, v, maxno, I, PV, ST(stream));
 }
 
 double gpx_peak_dmma(int blocks, int iters, double* sink, void* stream) {

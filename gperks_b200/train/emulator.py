@@ -291,31 +291,48 @@ class GPEmulator(Trainable):
             return PolyMeanSpec(feat[:0].to(dev), degree, torch.zeros(0, dtype=F64, device=dev), b)
         return PolyMeanSpec(feat.to(dev).contiguous(), degree, w, b)
 
+    def predict_device(self, x_dev: torch.Tensor):
+        """Device-resident predict: raw (unscaled) inputs ``x_dev`` [M, D] already in HBM -> (mean, std) device
+        tensors, un-standardised when the output scaler is the (linear) StandardScaler.  This is the call the
+        GPU-side consumers (history matching, GSA, the benchmark's device arm) use; ``predict`` wraps it with
+        the pinned H2D / D2H staging.  Returns ``(mean, std, linear_out)``."""
+        cdev = self._compute_device()
+        scx, scy = self.scaled_data.scx, self.scaled_data.scy
+        with torch.no_grad(), torch.cuda.device(cdev):
+            eng = self.model._factorized_engine()
+            M = x_dev.shape[0]
+            xa = torch.as_tensor(numpy.asarray(scx.a, dtype=numpy.float64).reshape(-1), device=cdev)
+            xr = torch.as_tensor((numpy.asarray(scx.b, dtype=numpy.float64)
+                                  - numpy.asarray(scx.a, dtype=numpy.float64)).reshape(-1), device=cdev)
+            poly = self._poly_spec(cdev)
+            prior = None
+            if poly is None:   # arbitrary user mean: evaluate it with torch on the scaled inputs
+                prior = self.model.mean_module((x_dev - xa) / xr).to(cdev, F64)
+            linear_out = type(scy).__name__ == "StandardScaler"
+            mean_d, std_d = eng.predict(
+                x_dev, xa=xa, xr=xr, prior_mean=prior, poly=poly,
+                y_mu=float(scy.mu) if linear_out else 0.0, y_sigma=float(scy.sigma) if linear_out else 1.0,
+                chunk=eng.pick_chunk(M, DEFAULT_PREDICT_CHUNK_BYTES) if M > 0 else None)
+        return mean_d, std_d, linear_out
+
     def predict(self, X_new, with_covar: bool = False):
         """(y_mean, y_std[, y_covar]) as numpy float64 -- GPErks/train/emulator.py:348-383.
 
-        ``y_std`` is the *noisy* predictive std (likelihood noise included) as in the reference.  Points are
-        streamed through the GPU in chunks (pinned staging, H2D / compute / D2H on the same stream)."""
+        ``y_std`` is the *noisy* predictive std (likelihood noise included) as in the reference.  Inputs go
+        through pinned host memory, are un-scaled inside the kernels, streamed through the GPU in chunks, and the
+        un-standardised results come back through pinned memory."""
         self.model.eval()
         self.model.likelihood.eval()
         X_new = self._as_2d(X_new)
         cdev = self._compute_device()
         scx, scy = self.scaled_data.scx, self.scaled_data.scy
+        M = X_new.shape[0]
         with torch.no_grad(), torch.cuda.device(cdev):
-            eng = self.model._factorized_engine()
-            M = X_new.shape[0]
-            xa = torch.as_tensor(numpy.asarray(scx.a, dtype=numpy.float64).reshape(-1), device=cdev)
-            xr = torch.as_tensor((numpy.asarray(scx.b, dtype=numpy.float64) - numpy.asarray(scx.a, dtype=numpy.float64)).reshape(-1), device=cdev)
-            poly = self._poly_spec(cdev)
-            prior = None
-            x_dev = torch.from_numpy(X_new).pin_memory().to(cdev, non_blocking=True) if M > 0 else torch.empty(0, eng.D, dtype=F64, device=cdev)
-            if poly is None:   # arbitrary user mean: evaluate it with torch on the scaled inputs
-                prior = self.model.mean_module((x_dev - xa) / xr).to(cdev, F64)
-            linear_out = hasattr(scy, "mu") and type(scy).__name__ == "StandardScaler"
-            mean_d, std_d = eng.predict(
-                x_dev, xa=xa, xr=xr, prior_mean=prior, poly=poly,
-                y_mu=float(scy.mu) if linear_out else 0.0, y_sigma=float(scy.sigma) if linear_out else 1.0,
-                chunk=eng.pick_chunk(M, DEFAULT_PREDICT_CHUNK_BYTES) if M > 0 else None)
+            if M > 0:
+                x_dev = torch.from_numpy(X_new).pin_memory().to(cdev, non_blocking=True)
+            else:
+                x_dev = torch.empty(0, self.scaled_data.input_size, dtype=F64, device=cdev)
+            mean_d, std_d, linear_out = self.predict_device(x_dev)
             out = torch.empty(2, M, dtype=F64).pin_memory() if M > 0 else torch.empty(2, 0, dtype=F64)
             out[0].copy_(mean_d, non_blocking=True)
             out[1].copy_(std_d, non_blocking=True)
@@ -325,28 +342,44 @@ class GPEmulator(Trainable):
                 y_mean, y_std = scy.inverse_transform(y_mean, ystd_=y_std)
             if not with_covar:
                 return y_mean, y_std
-            x_scaled = ((x_dev - xa) / xr)
-            covar = self.model.likelihood(self.model(x_scaled)).covariance_matrix.cpu().numpy()
+            xa = torch.as_tensor(numpy.asarray(scx.a, dtype=numpy.float64).reshape(-1), device=cdev)
+            xr = torch.as_tensor((numpy.asarray(scx.b, dtype=numpy.float64)
+                                  - numpy.asarray(scx.a, dtype=numpy.float64)).reshape(-1), device=cdev)
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                covar = self.model.likelihood(self.model((x_dev - xa) / xr)).covariance_matrix.cpu().numpy()
         # un-standardise the covariance the way the reference does (sign * (sigma_y * sqrt|C|)^2)
         sign = numpy.sign(covar)
         _, as_std = scy.inverse_transform(y_mean, ystd_=numpy.sqrt(numpy.abs(covar.reshape(-1))))
         y_covar = sign * numpy.power(as_std.reshape(len(y_std), len(y_std)), 2)
         return y_mean, y_std, y_covar
 
-    def sample(self, X_new: numpy.ndarray, n_draws: int = DEFAULT_GSA_N_DRAWS):
-        """(n_draws, M) joint posterior-predictive draws -- GPErks/train/emulator.py:385-401."""
+    def sample(self, X_new: numpy.ndarray, n_draws: int = DEFAULT_GSA_N_DRAWS, chunk: Optional[int] = None):
+        """(n_draws, M) posterior-predictive draws -- GPErks/train/emulator.py:385-401.
+
+        ``chunk=None`` reproduces the reference: ONE joint draw over all M points (dense M x M covariance and its
+        Cholesky root on the GPU; the reference switches to a rank-100 Lanczos root above M=800).  With ``chunk``
+        the draw is joint within consecutive blocks of ``chunk`` points and independent across blocks, which is the
+        only way to sample 1e6+ point designs."""
         self.model.eval()
         self.model.likelihood.eval()
         X_new = self._as_2d(X_new)
         cdev = self._compute_device()
         scx, scy = self.scaled_data.scx, self.scaled_data.scy
+        M = X_new.shape[0]
+        step = M if chunk is None else int(chunk)
+        draws = numpy.empty((n_draws, M), dtype=numpy.float64)
+        y_std = numpy.empty(M, dtype=numpy.float64)
         import warnings
         with torch.no_grad(), torch.cuda.device(cdev), warnings.catch_warnings():
             warnings.simplefilter("ignore")
-            x_scaled = torch.from_numpy(scx.transform(X_new)).to(cdev, F64)
-            predictions = self.model.likelihood(self.model(x_scaled))
-            y_std = numpy.sqrt(predictions.variance.cpu().numpy())
-            draws = predictions.sample(sample_shape=torch.Size([n_draws])).cpu().numpy()
+            for lo in range(0, M, max(step, 1)):
+                hi = min(M, lo + step)
+                x_scaled = torch.from_numpy(scx.transform(X_new[lo:hi])).to(cdev, F64)
+                predictions = self.model.likelihood(self.model(x_scaled))
+                y_std[lo:hi] = numpy.sqrt(predictions.variance.cpu().numpy())
+                draws[:, lo:hi] = predictions.sample(sample_shape=torch.Size([n_draws])).cpu().numpy()
         for i in range(n_draws):
             draws[i] = scy.inverse_transform(draws[i], ystd_=y_std)[0]
         return draws

@@ -85,6 +85,12 @@ int gpx_predict_meanvar(const double* Xs, long M, const double* X, int N, int D,
                         double min_var, double* out_mean, double* out_std, void* workspace,
                         size_t workspace_bytes, int Mc, void* stream);
 
+/* History-matching epilogue over E emulators: I[m] = maxno-th largest_e sqrt((mean[e][m]-z[e])^2/(std[e][m]^2+v[e])),
+ * PV[m] = maxno-th largest_e std[e][m]^2/v[e]; inputs emulator-major [E][M]; 1 <= maxno <= min(E, 8).
+ * replaces: the per-point loop with two np.sort in Wave.compute_impl, GPErks/perks/history_matching.py:57-62. */
+int gpx_implausibility(const double* mean, const double* std_, long M, int E, const double* z, const double* v,
+                       int maxno, double* I, double* PV, void* stream);
+
 /* Microbenchmarks for the roofline denominators: enqueue `iters` dependent-chain-free DMMA.8x8x4
  * (or DFMA) per warp on `blocks` CTAs of 256 threads; returns the FLOP count of the launch. */
 double gpx_peak_dmma(int blocks, int iters, double* sink, void* stream);

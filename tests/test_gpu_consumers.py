@@ -1,0 +1,142 @@
+"""GPU tests of the consumers that sit on the hot path: history matching, Sobol' GSA,
+K-fold cross validation, Inference / Diagnostics -- against the reference's formulas restated in numpy, the
+notebook goldens and analytic Sobol' indices."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import gp_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda:0")
+
+
+def _fit(f, d, n_train, kernel="matern", seed=8, n_test=None, l_bounds=None, u_bounds=None, auto=True, degree=1):
+    from gperks_b200.gp.data.dataset import Dataset
+    from gperks_b200.gp.experiment import GPExperiment
+    from gperks_b200.gp.mean import LinearMean
+    from gperks_b200.kernels import MaternKernel, RBFKernel, ScaleKernel
+    from gperks_b200.likelihoods import GaussianLikelihood
+    from gperks_b200.train.emulator import GPEmulator
+    from gperks_b200.utils.metrics import IndependentStandardError, MeanSquaredError, R2Score
+    ds = Dataset.build_from_function(f, d, n_train, None, n_test, "lhs", seed, l_bounds=l_bounds, u_bounds=u_bounds)
+    base = MaternKernel(ard_num_dims=d) if kernel == "matern" else RBFKernel(ard_num_dims=d)
+    exp = GPExperiment(ds, GaussianLikelihood(), LinearMean(degree, d), ScaleKernel(base), n_restarts=1, seed=seed,
+                       metrics=[MeanSquaredError(), R2Score(), IndependentStandardError()])
+    em = GPEmulator(exp, "cuda:0")
+    if auto:
+        em.train_auto(snap_dir="/tmp/gperks_b200_test_snap")
+    return em, ds
+
+
+def test_history_matching_matches_reference_loop(dev):
+    from gperks_b200.perks.history_matching import Wave
+    from gperks_b200.utils.test_functions import branin_rescaled, currin_exp, lim_poly
+    emulators = [_fit(f, 2, 40, seed=s)[0] for f, s in ((currin_exp, 8), (lim_poly, 9), (branin_rescaled, 10))]
+    rng = np.random.default_rng(0)
+    X = rng.random((5003, 2))
+    z, v = [5.0, 8.0, -0.2], [0.5, 1.0, 0.01]
+    for maxno in (1, 2, 3):
+        W = Wave(emulator=emulators, Itrain=np.array([[0, 1], [0, 1]]), cutoff=3.0, maxno=maxno, mean=z, var=v)
+        I, PV = W.compute_impl(X, block_points=2048)
+        # the reference's arithmetic (history_matching.py:46-62), on the same predictions
+        M = np.zeros((X.shape[0], 3))
+        V = np.zeros((X.shape[0], 3))
+        for j, em in enumerate(emulators):
+            mean, std = em.predict(X)
+            M[:, j], V[:, j] = mean, np.power(std, 2)
+        Iref = np.array([np.sort(np.sqrt(np.power(M[i] - np.array(z), 2) / (V[i] + np.array(v))))[-maxno] for i in range(X.shape[0])])
+        PVref = np.array([np.sort(V[i] / np.array(v))[-maxno] for i in range(X.shape[0])])
+        assert np.array_equal(I, Iref) and np.array_equal(PV, PVref)      # byte-identical
+    W = Wave(emulator=emulators, Itrain=np.array([[0.0, 1.0], [0.0, 1.0]]), cutoff=3.0, maxno=1, mean=z, var=v)
+    W.find_regions(X)
+    assert len(W.nimp_idx) + len(W.imp_idx) == X.shape[0]
+    assert np.array_equal(W.reconstruct_tests(), X)
+    if 10 < len(W.nimp_idx) < 4000:
+        n0 = len(W.nimp_idx)
+        np.random.seed(0)
+        W.augment_nimp(n0 + 50)
+        assert W.NIMP.shape[0] == n0 + 50 and len(W.I) == X.shape[0] + 50
+        assert (W.I[-50:] < W.cutoff).all()
+
+
+def test_sobol_gsa_against_analytic_indices(dev):
+    from functools import partial
+    from gperks_b200.perks.gsa import SobolGSA
+    from gperks_b200.utils.test_functions_gsa import SobolGstar, SobolGstar_theoretical_Si
+    d = 4
+    a, delta, alpha = [0.0, 1.0, 4.5, 99.0], [0.1, 0.3, 0.5, 0.7], [2.0] * d
+    f = partial(SobolGstar, a=a, delta=delta, alpha=alpha)
+    em, ds = _fit(f, d, 300, l_bounds=[0.0] * d, u_bounds=[1.0] * d)
+    ST_th, S1_th, _ = SobolGstar_theoretical_Si(a, delta, alpha)
+    gsa = SobolGSA(ds, n=2 ** 15, seed=8)
+    gsa.estimate_Sobol_indices_with_emulator_mean(em)          # 196608 predictions + sums on the device
+    assert gsa.S1.shape == (1, d) and gsa.ST.shape == (1, d)
+    np.testing.assert_allclose(gsa.S1[0], S1_th["Si"].values, atol=0.08)
+    np.testing.assert_allclose(gsa.ST[0], ST_th["STi"].values, atol=0.08)
+    # the device pipeline equals scipy's estimator applied to the same predictions
+    _, _, X = gsa.saltelli_design()
+    mean, _ = em.predict(X)
+    from scipy.stats import sobol_indices
+    n = gsa.n
+    f_AB = np.moveaxis(mean[2 * n:].reshape((-1, n, d)), -1, 0)
+    ref = sobol_indices(func={"f_A": mean[:n].reshape(1, -1), "f_B": mean[n:2 * n].reshape(1, -1), "f_AB": f_AB}, n=n)
+    np.testing.assert_allclose(gsa.S1[0], np.ravel(ref.first_order), rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(gsa.ST[0], np.ravel(ref.total_order), rtol=1e-9, atol=1e-12)
+    # reference-style path: joint posterior draws at n(d+2) points
+    small = SobolGSA(ds, n=64, seed=8)
+    small.estimate_Sobol_indices_with_emulator(em, n_draws=40)
+    assert small.S1.shape == (40, d) and small.ST.shape == (40, d)
+    assert np.argmax(np.median(small.ST, axis=0)) == 0            # X1 dominates (a_1 = 0)
+    small.estimate_Sobol_indices_with_emulator(em, n_draws=10, chunk=100)
+    assert small.ST.shape == (10, d)
+    small.correct_Sobol_indices()
+    small.assemble_dataframe()
+    assert set(small.df.columns) == {"Parameter", "Index", "Value"}
+
+
+def test_inference_and_diagnostics_reproduce_notebook(dev, goldens):
+    from test_gpu_parity import _emulator_from_golden
+    from gperks_b200.perks.diagnostics import Diagnostics
+    from gperks_b200.perks.inference import Inference
+    g = goldens["example_2"]
+    em, ds = _emulator_from_golden(g, "example_2")
+    inf = Inference(em)
+    inf.summary(printtoconsole=False)
+    assert float(inf.scores_dct["MeanSquaredError"]) == pytest.approx(g["printed"]["MSE"], abs=5e-4)
+    assert float(inf.scores_dct["R2Score"]) == pytest.approx(g["printed"]["R2"], abs=5e-4)
+    diag = Diagnostics(em)
+    assert diag.chi_squared()[0] == pytest.approx(g["printed"]["chi2"], rel=2e-4)
+    md, md_mean, _ = diag.mahalanobis_distance()
+    assert float(md) == pytest.approx(g["printed"]["mahalanobis"], rel=2e-4) and md_mean == 25
+    torch.manual_seed(0)
+    ci, ci_mean, ci_std = diag.credible_interval()
+    assert ci == pytest.approx(g["printed"]["CI"], abs=1e-12) and 0.5 < ci_mean <= 1.0
+    for kind in ("correlated", "uncorrelated", "pivoted"):
+        assert diag.errors(kind).shape == (25,)
+
+
+def test_kfold_cross_validation(dev, tmp_path):
+    from gperks_b200.perks.cross_validation import KFoldCrossValidation
+    from gperks_b200.train.early_stop import NoEarlyStoppingCriterion
+    from gperks_b200.train.snapshot import NeverSaveSnapshottingCriterion
+    from gperks_b200.utils.test_functions import currin_exp
+    em, ds = _fit(currin_exp, 2, 45, auto=False)
+    exp = em.experiment
+    opt = torch.optim.Adam(exp.model.parameters(), lr=0.1)
+    snap = NeverSaveSnapshottingCriterion((tmp_path / "split_{split}" / "restart_{restart}").as_posix(), "epoch_{epoch}.pth")
+    cv = KFoldCrossValidation(exp, ["cuda:0"], n_splits=3, max_workers=1)
+    models, stats = cv.train(opt, NoEarlyStoppingCriterion(30), snap, leftout_is_val=True)
+    assert set(models) == {0, 1, 2} and all(len(stats[s].train_loss) == 30 for s in stats)
+    assert len(cv.best_test_scores_structured_dct["R2Score"]) == 3
+    assert cv.best_split == int(np.argmax(cv.best_test_scores_structured_dct["R2Score"]))
+    mean, std = cv.emulator.predict(ds.X_train[:5])
+    assert mean.shape == (5,) and (std > 0).all()
+    for s in range(3):
+        assert (tmp_path / f"split_{s}" / "best_model.pth").exists()

@@ -182,7 +182,7 @@ def test_notebook_golden_example_2(dev, goldens):
     em.model.train()
     mll = ExactMarginalLogLikelihood(em.model.likelihood, em.model)
     loss = -mll(em.model(em.scaled_data.X_train), em.scaled_data.y_train)
-    assert float(loss) == pytest.approx(p["train_loss"], abs=5e-5)
+    assert float(loss.detach()) == pytest.approx(p["train_loss"], abs=5e-5)
 
 
 def test_notebook_golden_example_9_and_1(dev, goldens):
