@@ -11,6 +11,7 @@
 //                 upper off-diagonal blocks = mirror (L^-T), so rows of S serve as "columns" of L^-1.
 //   DT (nb x 128 x 128): transposed diagonal blocks of L^-1 (upper triangular, zero below).
 #include "gpx_common.cuh"
+#include <stdlib.h>
 
 namespace gpx {
 
@@ -110,6 +111,194 @@ potrf_diag_kernel(double* __restrict__ K, int Np, int blk, int N, double* __rest
 }
 
 // ------------------------------------------------------------------------------------------------
+// Diagonal block, version 2 (default): blocked right-looking Cholesky with 8-wide panels, the triangular
+// inverse carried along as the forward substitution L X = I, and every rank-8 update (matrix and
+// right-hand side) on DMMA.8x8x4.  One CTA, 8 warps, the 128 x 128 block resident in shared memory:
+//   lower triangle  : A -> L
+//   strict upper    : B = I - sum L X (transposed) -> X^T, i.e. X[i][c] (i > c) lives at a[c][i]
+// Per panel p: (1) one thread factors the 8x8 diagonal block in registers (rsqrt-based, fully unrolled) and
+// inverts it; (2) 128 threads finish the panel rows L_ip = A_ip T^T while 128 threads finish the inverse's
+// block row X_pj = T B_pj; (3) 8 warps apply A_ij -= L_ip L_jp^T and B_ij -= L_ip X_pj with two DMMAs per
+// 8x8 block.  ~3 CTA barriers per panel instead of 2 per column.
+// ------------------------------------------------------------------------------------------------
+constexpr int D2_THREADS = 256;
+
+__global__ void __launch_bounds__(D2_THREADS, 1)
+potrf_diag2_kernel(double* __restrict__ K, int Np, int blk, int N, double* __restrict__ S, double* __restrict__ DT,
+                   double* __restrict__ logdet_blk, int* __restrict__ info) {
+    extern __shared__ double a[];            // [128][DG_LD]
+    double* rinv = a + TILE * DG_LD;         // [128] 1/L_jj
+    double* dg = rinv + TILE;                // [128] L_jj
+    double* Tb = dg + TILE;                  // [8][8] inverse of the current 8x8 diagonal block (lower)
+    __shared__ int bad_pivot;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int lr = lane >> 2, lc = lane & 3;
+    const long off = (long)blk * TILE;
+    double* Ab = K + off * Np + off;
+    if (tid == 0) bad_pivot = 0;
+    for (int e = tid; e < TILE * TILE; e += D2_THREADS) {
+        int r = e >> 7, c = e & 127;
+        double v = Ab[(long)r * Np + c];
+        a[r * DG_LD + c] = (c <= r) ? v : 0.0;     // B starts as the identity: zero strict upper part
+    }
+    __syncthreads();
+    for (int p = 0; p < TILE / 8; ++p) {
+        const int c0 = 8 * p;
+        // ---- (1) 8x8 diagonal block: Cholesky + inverse in the registers of one thread
+        if (tid == 0) {
+            double d[8][8], t[8][8], ri[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) d[r][c] = (c <= r) ? a[(c0 + r) * DG_LD + c0 + c] : 0.0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const double piv = d[j][j];
+                if (!(piv > 0.0) && bad_pivot == 0) bad_pivot = c0 + j + 1;
+                const double inv = rsqrt(piv);
+                ri[j] = inv;
+                d[j][j] = piv * inv;
+#pragma unroll
+                for (int r = j + 1; r < 8; ++r) d[r][j] *= inv;
+#pragma unroll
+                for (int c = j + 1; c < 8; ++c)
+#pragma unroll
+                    for (int r = c; r < 8; ++r) d[r][c] = fma(-d[r][j], d[c][j], d[r][c]);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                t[j][j] = ri[j];
+#pragma unroll
+                for (int i = j + 1; i < 8; ++i) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int k = j; k < i; ++k) s = fma(d[i][k], t[k][j], s);
+                    t[i][j] = -s * ri[i];
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                rinv[c0 + r] = ri[r];
+                dg[c0 + r] = d[r][r];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    if (c <= r) a[(c0 + r) * DG_LD + c0 + c] = d[r][c];
+                    Tb[r * 8 + c] = (c <= r) ? t[r][c] : 0.0;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- (2) panel rows (threads 0..127) and the inverse's block row (threads 128..255)
+        if (tid < TILE) {
+            const int i = tid;
+            if (i >= c0 + 8) {
+                double v[8], o[8];
+                double* row = a + i * DG_LD + c0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] = row[k];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int k = 0; k <= c; ++k) s = fma(v[k], Tb[c * 8 + k], s);
+                    o[c] = s;
+                }
+#pragma unroll
+                for (int c = 0; c < 8; ++c) row[c] = o[c];
+            }
+        } else {
+            const int c = tid - TILE;
+            if (c < c0 + 8) {
+                double b[8], x[8];
+                double* row = a + c * DG_LD + c0;      // transposed storage: B[p][c][r] at a[c][c0 + r]
+                const int cc = c - c0;                  // >= 0 inside the diagonal block
+#pragma unroll
+                for (int r = 0; r < 8; ++r) b[r] = (cc >= 0) ? ((r == cc) ? 1.0 : 0.0) : row[r];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int k = 0; k <= r; ++k) s = fma(Tb[r * 8 + k], b[k], s);
+                    x[r] = s;
+                }
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+                    if (cc < 0 || r > cc) row[r] = x[r];
+            }
+        }
+        __syncthreads();
+        // ---- (3) rank-8 updates on DMMA: matrix blocks (bi >= bj > p) and right-hand-side blocks (bi > p >= bj)
+        const int nrem = TILE / 8 - 1 - p;
+        const int n_mat = nrem * (nrem + 1) / 2;
+        const int total = n_mat + nrem * (p + 1);
+        for (int t = warp; t < total; t += D2_THREADS / 32) {
+            int bi, bj;
+            const bool rhs = t >= n_mat;
+            if (!rhs) {
+                int q = (int)((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
+                while (q * (q + 1) / 2 > t) --q;
+                while ((q + 1) * (q + 2) / 2 <= t) ++q;
+                bi = p + 1 + q;
+                bj = p + 1 + (t - q * (q + 1) / 2);
+            } else {
+                const int u = t - n_mat;
+                bi = p + 1 + u / (p + 1);
+                bj = u % (p + 1);
+            }
+            const double* ar = a + (8 * bi + lr) * DG_LD + c0 + lc;
+            double b0, b1;
+            if (rhs && bj == p) {
+                // X_pp = T: its storage overlaps L_pp (diagonal + lower part), so read the dense copy
+                b0 = Tb[lc * 8 + lr];
+                b1 = Tb[(lc + 4) * 8 + lr];
+            } else {
+                const double* br = a + (8 * bj + lr) * DG_LD + c0 + lc;
+                b0 = br[0];
+                b1 = br[4];
+            }
+            double c0v = 0.0, c1v = 0.0;
+            dmma884(c0v, c1v, ar[0], b0);
+            dmma884(c0v, c1v, ar[4], b1);
+            if (!rhs) {
+                double2* ptr = reinterpret_cast<double2*>(a + (8 * bi + lr) * DG_LD + 8 * bj + 2 * lc);
+                double2 v = *ptr;
+                v.x -= c0v; v.y -= c1v;
+                *ptr = v;
+            } else {
+                a[(8 * bj + 2 * lc) * DG_LD + 8 * bi + lr] -= c0v;
+                a[(8 * bj + 2 * lc + 1) * DG_LD + 8 * bi + lr] -= c1v;
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0 && bad_pivot != 0 && *info == 0) *info = (int)off + bad_pivot;
+    // ---- write back: L (lower, zero above), D = L^-1 into S (zero above), D^T into DT
+    double* Sb = S + off * Np + off;
+    double* DTb = DT + (long)blk * TILE * TILE;
+    for (int e = tid; e < TILE * TILE; e += D2_THREADS) {
+        int i = e >> 7, c = e & 127;
+        double l = (c <= i) ? a[i * DG_LD + c] : 0.0;
+        double x = (c < i) ? a[c * DG_LD + i] : ((c == i) ? rinv[i] : 0.0);
+        Ab[(long)i * Np + c] = l;
+        Sb[(long)i * Np + c] = x;
+    }
+    for (int e = tid; e < TILE * TILE; e += D2_THREADS) {
+        int c = e >> 7, i = e & 127;   // DT[c][i] = D[i][c]
+        double x = (c < i) ? a[c * DG_LD + i] : ((c == i) ? rinv[i] : 0.0);
+        DTb[c * TILE + i] = x;
+    }
+    if (tid < 32) {
+        double t = 0.0;
+        for (int j = tid; j < TILE; j += 32)
+            if (off + j < N) t += log(dg[j]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (tid == 0) logdet_blk[blk] = t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Panel: L[i][p] = A[i][p] * D_p^T   for row tiles i > p.   grid.x = nb - p - 1
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(G_THREADS, 1) potrf_panel_kernel(double* __restrict__ K, int Np, int p,
@@ -126,11 +315,14 @@ __global__ void __launch_bounds__(G_THREADS, 1) potrf_panel_kernel(double* __res
     });
 }
 
-// Trailing update: A[i][j] -= L[i][p] L[j][p]^T for p < j <= i.  grid = (n, n), n = nb - p - 1.
-__global__ void __launch_bounds__(G_THREADS, 1) potrf_trailing_kernel(double* __restrict__ K, int Np, int p) {
-    if (blockIdx.x > blockIdx.y) return;
+// Trailing update: A[i][j] -= L[i][p] L[j][p]^T for tiles tj = j0 + bx <= ti = i0 + by.
+//   next block column only : (j0, i0) = (p+1, p+1), grid (1, n)      -- on the critical path
+//   the rest               : (j0, i0) = (p+2, p+2), grid (n-1, n-1)  -- overlapped with the next diag/panel
+__global__ void __launch_bounds__(G_THREADS, 1) potrf_trailing_kernel(double* __restrict__ K, int Np, int p, int j0,
+                                                                      int i0) {
+    const int ti = i0 + blockIdx.y, tj = j0 + blockIdx.x;
+    if (tj > ti) return;
     extern __shared__ double smem[];
-    const int ti = p + 1 + blockIdx.y, tj = p + 1 + blockIdx.x;
     Operand A = make_operand(K + (long)ti * TILE * Np + (long)p * TILE, Np);
     Operand B = make_operand(K + (long)tj * TILE * Np + (long)p * TILE, Np);
     double acc[8][4][2];
@@ -285,23 +477,84 @@ static void set_gemm_attrs() {
     cudaFuncSetAttribute(lauum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES);
     const int dg = (TILE * DG_LD + 2 * TILE + 2) * 8;
     cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dg);
+    cudaFuncSetAttribute(potrf_diag2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (TILE * DG_LD + 2 * TILE + 64) * 8);
     if (dev >= 0 && dev < 64) g_attr_set[dev] = true;
 }
 
+static int use_diag_v1() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("GPX_DIAG_IMPL"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v;
+}
+
+// Helper stream + events for the look-ahead (per device, created on first use; all work is ordered
+// after the caller's stream and joined back into it before potrf returns control of the data).
+struct LookAhead {
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_main[2] = {nullptr, nullptr};
+    cudaEvent_t ev_side[2] = {nullptr, nullptr};
+};
+static LookAhead g_la[64];
+
+static LookAhead* lookahead_for_current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return nullptr;
+    LookAhead* la = &g_la[dev];
+    if (la->side == nullptr) {
+        if (cudaStreamCreateWithFlags(&la->side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        for (int i = 0; i < 2; ++i) {
+            cudaEventCreateWithFlags(&la->ev_main[i], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&la->ev_side[i], cudaEventDisableTiming);
+        }
+    }
+    return la;
+}
+
+static int use_lookahead() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("GPX_POTRF_LOOKAHEAD"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v;
+}
+
 // K (lower tiles valid) -> L in place; diagonal-block inverses into S / DT; per-block log-dets; info.
+// Right-looking with a one-panel look-ahead: after panel p, the next block column is updated on the caller's
+// stream (critical path: diag p+1, panel p+1), while the rest of the trailing matrix is updated on a helper
+// stream.
 int potrf(double* K, int Np, int N, double* S, double* DT, double* logdet_blk, int* info, cudaStream_t st) {
     set_gemm_attrs();
     const int nb = Np / TILE;
     const int dg = (TILE * DG_LD + 2 * TILE + 2) * 8;
+    const int dg2 = (TILE * DG_LD + 2 * TILE + 64) * 8;
+    LookAhead* la = use_lookahead() ? lookahead_for_current_device() : nullptr;
     cudaMemsetAsync(info, 0, sizeof(int), st);
+    bool side_pending = false;
     for (int p = 0; p < nb; ++p) {
-        potrf_diag_kernel<<<1, DG_THREADS, dg, st>>>(K, Np, p, N, S, DT, logdet_blk, info);
+        if (use_diag_v1())
+            potrf_diag_kernel<<<1, DG_THREADS, dg, st>>>(K, Np, p, N, S, DT, logdet_blk, info);
+        else
+            potrf_diag2_kernel<<<1, D2_THREADS, dg2, st>>>(K, Np, p, N, S, DT, logdet_blk, info);
         const int n = nb - p - 1;
-        if (n > 0) {
-            potrf_panel_kernel<<<n, G_THREADS, G_SMEM_BYTES, st>>>(K, Np, p, S);
-            potrf_trailing_kernel<<<dim3(n, n), G_THREADS, G_SMEM_BYTES, st>>>(K, Np, p);
+        if (n <= 0) break;
+        potrf_panel_kernel<<<n, G_THREADS, G_SMEM_BYTES, st>>>(K, Np, p, S);
+        if (la == nullptr) {
+            potrf_trailing_kernel<<<dim3(n, n), G_THREADS, G_SMEM_BYTES, st>>>(K, Np, p, p + 1, p + 1);
+            continue;
+        }
+        // block column p+1 was also touched by the helper stream's update p-1: wait for it first
+        if (side_pending) cudaStreamWaitEvent(st, la->ev_side[(p - 1) & 1], 0);
+        potrf_trailing_kernel<<<dim3(1, n), G_THREADS, G_SMEM_BYTES, st>>>(K, Np, p, p + 1, p + 1);
+        if (n > 1) {
+            cudaEventRecord(la->ev_main[p & 1], st);
+            cudaStreamWaitEvent(la->side, la->ev_main[p & 1], 0);
+            potrf_trailing_kernel<<<dim3(n - 1, n - 1), G_THREADS, G_SMEM_BYTES, la->side>>>(K, Np, p, p + 2, p + 2);
+            cudaEventRecord(la->ev_side[p & 1], la->side);
+            side_pending = true;
+        } else {
+            side_pending = false;
         }
     }
+    if (la != nullptr && side_pending) cudaStreamWaitEvent(st, la->ev_side[(nb - 3) & 1], 0);
     GPX_CHECK_LAUNCH();
     return 0;
 }
