@@ -15,6 +15,14 @@ int solve_alpha(const double*, const double*, int, const double*, double*, doubl
 int mll_value(const double*, const double*, int, int, const double*, double*, cudaStream_t);
 size_t predict_workspace_bytes(int, int);
 int trmm_sumsq(const double*, int, const double*, int, double*, cudaStream_t);
+int split_tf32_matrix(const double*, long, float*, float*, int, cudaStream_t);
+int trmm_sumsq_tf32(const float*, const float*, int, const float*, const float*, int, double*, int, cudaStream_t);
+int tf32_row_tiles(int);
+size_t predict_tf32_workspace_bytes(int, int);
+int predict_meanvar_tf32(const double*, long, const double*, int, int, const double*, const double*, const double*, int,
+                         const float*, const float*, int, const double*, const double*, const int*, int, int,
+                         const double*, const double*, double, double, double, double*, double*, void*, size_t, int,
+                         int, cudaStream_t);
 int implausibility(const double*, const double*, long, int, const double*, const double*, int, double*, double*,
                    cudaStream_t);
 int predict_meanvar(const double*, long, const double*, int, int, const double*, const double*, const double*, int,
@@ -143,6 +151,41 @@ int gpx_predict_meanvar(const double* Xs, long M, const double* X, int N, int D,
     return predict_meanvar(Xs, M, X, N, D, theta, xa, xr, kind, S, Np, alpha, prior_mean, feat_idx, n_feat, degree,
                            weights, bias, y_mu, y_sigma, min_var, out_mean, out_std, workspace, workspace_bytes, Mc,
                            ST(stream));
+}
+
+int gpx_split_tf32(const double* src, long n, float* hi, float* lo, int ld, void* stream) {
+    if (!src || !hi || !lo) return -1;
+    if (n < 0 || ld < 0) return -2;
+    return split_tf32_matrix(src, n, hi, lo, ld, ST(stream));
+}
+
+int gpx_tf32_row_tiles(int Np) { return tf32_row_tiles(Np); }
+
+int gpx_trmm_sumsq_tf32(const float* Shi, const float* Slo, int Np, const float* Khi, const float* Klo, int Mc,
+                        double* qpart, int kchunk, void* stream) {
+    if (!Shi || !Slo || !Khi || !Klo || !qpart) return -1;
+    if (Np % TILE || Mc % TILE || Np <= 0 || Mc <= 0) return -3;
+    if (kchunk > 0 && kchunk % 32) return -8;
+    return trmm_sumsq_tf32(Shi, Slo, Np, Khi, Klo, Mc, qpart, kchunk, ST(stream));
+}
+
+size_t gpx_predict_tf32_workspace_bytes(int Np, int Mc) { return predict_tf32_workspace_bytes(Np, Mc); }
+
+int gpx_predict_meanvar_tf32(const double* Xs, long M, const double* X, int N, int D, const double* theta,
+                             const double* xa, const double* xr, int kind, const float* Shi, const float* Slo, int Np,
+                             const double* alpha, const double* prior_mean, const int* feat_idx, int n_feat,
+                             int degree, const double* weights, const double* bias, double y_mu, double y_sigma,
+                             double min_var, double* out_mean, double* out_std, void* workspace,
+                             size_t workspace_bytes, int Mc, int kchunk, void* stream) {
+    if (kchunk > 0 && kchunk % 32) return -27;
+    if (!Xs || !X || !theta || !Shi || !Slo || !alpha || !out_mean || !out_std || !workspace) return -1;
+    if (M < 0) return -2;
+    if (M == 0) return 0;
+    if ((xa == nullptr) != (xr == nullptr)) return -7;
+    if (!prior_mean && weights && n_feat > 0 && (!feat_idx || degree < 1)) return -14;
+    return predict_meanvar_tf32(Xs, M, X, N, D, theta, xa, xr, kind, Shi, Slo, Np, alpha, prior_mean, feat_idx, n_feat,
+                                degree, weights, bias, y_mu, y_sigma, min_var, out_mean, out_std, workspace,
+                                workspace_bytes, Mc, kchunk, ST(stream));
 }
 
 int gpx_implausibility(const double* mean, const double* std_, long M, int E, const double* z, const double* v,

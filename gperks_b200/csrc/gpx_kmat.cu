@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(P_THREADS)
 kmat_cross_kernel(const double* __restrict__ Xs, long m_valid, const double* __restrict__ X, int N, int D,
                   const double* __restrict__ theta, const double* __restrict__ xa, const double* __restrict__ xr,
                   const double* __restrict__ alpha, double* __restrict__ Ks, int Np, double* __restrict__ mean_part,
-                  int Mc) {
+                  int Mc, float* __restrict__ Khi, float* __restrict__ Klo) {
     const int jb = blockIdx.x, mb = blockIdx.y;
     extern __shared__ double sm[];
     double* sa = sm;                    // test points (rows m)
@@ -128,7 +128,18 @@ kmat_cross_kernel(const double* __restrict__ Xs, long m_valid, const double* __r
         for (int b = 0; b < 8; ++b) {
             const long j = (long)jb * TILE + tx + 16 * b;
             double v = (j < N) ? kernel_value<KIND>(r2[a][b], s) : 0.0;
-            Ks[m * Np + j] = v;
+            if (Khi != nullptr) {       // TF32 mode: 3xTF32 operand split (hi = tf32(x), lo = tf32(x - hi))
+                uint32_t h, l;
+                float fh, fl;
+                asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(h) : "f"((float)v));
+                fh = __uint_as_float(h);
+                asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(l) : "f"((float)(v - (double)fh)));
+                fl = __uint_as_float(l);
+                Khi[m * Np + j] = fh;
+                Klo[m * Np + j] = fl;
+            } else {
+                Ks[m * Np + j] = v;
+            }
             part = fma(v, al[b], part);
         }
         // reduce over the 16 tx lanes (a half-warp holds one row)
@@ -269,11 +280,11 @@ static int launch_kmat_sym(const double* X, int N, int D, const double* theta, d
 template <int KIND>
 static int launch_kmat_cross(const double* Xs, long m_valid, const double* X, int N, int D, const double* theta,
                              const double* xa, const double* xr, const double* alpha, double* Ks, int Np,
-                             double* mean_part, int Mc, cudaStream_t st) {
+                             double* mean_part, int Mc, float* Khi, float* Klo, cudaStream_t st) {
     const size_t smem = size_t(2) * MAXD * P_LD * 8 + 2 * TILE * 8;
     cudaFuncSetAttribute(kmat_cross_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kmat_cross_kernel<KIND><<<dim3(Np / TILE, Mc / TILE), P_THREADS, smem, st>>>(Xs, m_valid, X, N, D, theta, xa, xr,
-                                                                                 alpha, Ks, Np, mean_part, Mc);
+                                                                                 alpha, Ks, Np, mean_part, Mc, Khi, Klo);
     GPX_CHECK_LAUNCH();
     return 0;
 }
@@ -309,7 +320,16 @@ int kmat_sym(const double* X, int N, int D, const double* theta, int kind, doubl
 int kmat_cross(const double* Xs, long m_valid, const double* X, int N, int D, const double* theta, const double* xa,
                const double* xr, int kind, const double* alpha, double* Ks, int Np, double* mean_part, int Mc,
                cudaStream_t st) {
-#define C_(KD) launch_kmat_cross<KD>(Xs, m_valid, X, N, D, theta, xa, xr, alpha, Ks, Np, mean_part, Mc, st)
+#define C_(KD) launch_kmat_cross<KD>(Xs, m_valid, X, N, D, theta, xa, xr, alpha, Ks, Np, mean_part, Mc, nullptr, nullptr, st)
+    GPX_DISPATCH_KIND(kind, C_)
+#undef C_
+}
+
+// TF32 mode: K* written as (hi, lo) float pairs for the 3xTF32 tensor-core contraction; mean partials stay FP64
+int kmat_cross_split(const double* Xs, long m_valid, const double* X, int N, int D, const double* theta,
+                     const double* xa, const double* xr, int kind, const double* alpha, float* Khi, float* Klo, int Np,
+                     double* mean_part, int Mc, cudaStream_t st) {
+#define C_(KD) launch_kmat_cross<KD>(Xs, m_valid, X, N, D, theta, xa, xr, alpha, nullptr, Np, mean_part, Mc, Khi, Klo, st)
     GPX_DISPATCH_KIND(kind, C_)
 #undef C_
 }

@@ -232,7 +232,7 @@ __global__ void predict_finalize_kernel(const double* __restrict__ Xs, long m_va
                                         const double* __restrict__ prior_mean, const int* __restrict__ feat_idx,
                                         int n_feat, int degree, const double* __restrict__ weights,
                                         const double* __restrict__ bias, double y_mu, double y_sigma, double min_var,
-                                        double* __restrict__ out_mean, double* __restrict__ out_std) {
+                                        double* __restrict__ out_mean, double* __restrict__ out_std, int nq) {
     const long m = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= m_valid) return;
     double mean = 0.0;
@@ -256,10 +256,8 @@ __global__ void predict_finalize_kernel(const double* __restrict__ Xs, long m_va
         if (bias != nullptr) mean += bias[0];
     }
     double km = 0.0, q = 0.0;
-    for (int b = 0; b < nb; ++b) {
-        km += mean_part[(long)b * Mc + m];
-        q += qpart[(long)b * Mc + m];
-    }
+    for (int b = 0; b < nb; ++b) km += mean_part[(long)b * Mc + m];
+    for (int b = 0; b < nq; ++b) q += qpart[(long)b * Mc + m];
     mean += km;
     double var = theta[D] + theta[D + 1] - q;
     var = fmax(var, min_var);
@@ -314,7 +312,52 @@ int predict_meanvar(const double* Xs, long M, const double* X, int N, int D, con
         if (rc) return rc;
         predict_finalize_kernel<<<(int)((mv + 255) / 256), 256, 0, st>>>(
             xs, mv, D, xa, xr, theta, mean_part, qpart, nb, mc, prior_mean ? prior_mean + m0 : nullptr, feat_idx,
-            n_feat, degree, weights, bias, y_mu, y_sigma, min_var, out_mean + m0, out_std + m0);
+            n_feat, degree, weights, bias, y_mu, y_sigma, min_var, out_mean + m0, out_std + m0, nb);
+    }
+    GPX_CHECK_LAUNCH();
+    return 0;
+}
+
+// ---- TF32 mode (tcgen05, 3xTF32) ------------------------------------------------------------------------
+int kmat_cross_split(const double* Xs, long m_valid, const double* X, int N, int D, const double* theta,
+                     const double* xa, const double* xr, int kind, const double* alpha, float* Khi, float* Klo, int Np,
+                     double* mean_part, int Mc, cudaStream_t st);
+int trmm_sumsq_tf32(const float* Shi, const float* Slo, int Np, const float* Khi, const float* Klo, int Mc,
+                    double* qpart, int kchunk, cudaStream_t st);
+int tf32_row_tiles(int Np);
+
+size_t predict_tf32_workspace_bytes(int Np, int Mc) {
+    const size_t nb = Np / TILE;
+    return (size_t)Mc * Np * 8 + (nb + tf32_row_tiles(Np)) * (size_t)Mc * 8;
+}
+
+int predict_meanvar_tf32(const double* Xs, long M, const double* X, int N, int D, const double* theta, const double* xa,
+                         const double* xr, int kind, const float* Shi, const float* Slo, int Np, const double* alpha,
+                         const double* prior_mean, const int* feat_idx, int n_feat, int degree, const double* weights,
+                         const double* bias, double y_mu, double y_sigma, double min_var, double* out_mean,
+                         double* out_std, void* workspace, size_t workspace_bytes, int Mc, int kchunk,
+                         cudaStream_t st) {
+    if (Mc <= 0 || Mc % TILE != 0) return -25;
+    if (Np % TILE != 0 || Np < N) return -11;
+    if (D > MAXD || D < 1) return -5;
+    if (workspace_bytes < predict_tf32_workspace_bytes(Np, Mc)) return -23;
+    const int nb = Np / TILE, nt = tf32_row_tiles(Np);
+    float* Khi = reinterpret_cast<float*>(workspace);
+    float* Klo = Khi + (size_t)Mc * Np;
+    double* mean_part = reinterpret_cast<double*>(Klo + (size_t)Mc * Np);
+    double* qpart = mean_part + (size_t)nb * Mc;
+    for (long m0 = 0; m0 < M; m0 += Mc) {
+        const long mv = (M - m0 < Mc) ? (M - m0) : Mc;
+        const int mc = round_up((int)mv, TILE);
+        const double* xs = Xs + m0 * D;
+        int rc = kmat_cross_split(xs, mv, X, N, D, theta, xa, xr, kind, alpha, Khi, Klo, Np, mean_part, mc, st);
+        if (rc) return rc;
+        rc = trmm_sumsq_tf32(Shi, Slo, Np, Khi, Klo, mc, qpart, kchunk, st);
+        if (rc) return rc;
+        // mean partials come in nb row blocks, variance partials in nt 256-row tiles
+        predict_finalize_kernel<<<(int)((mv + 255) / 256), 256, 0, st>>>(
+            xs, mv, D, xa, xr, theta, mean_part, qpart, nb, mc, prior_mean ? prior_mean + m0 : nullptr, feat_idx,
+            n_feat, degree, weights, bias, y_mu, y_sigma, min_var, out_mean + m0, out_std + m0, nt);
     }
     GPX_CHECK_LAUNCH();
     return 0;

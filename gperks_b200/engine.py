@@ -84,6 +84,9 @@ class ExactGPEngine:
         self.jitter_used = 0.0
         self._ws: Optional[torch.Tensor] = None
         self.n_factorizations = 0
+        self.has_split = False
+        self.S_hi: Optional[torch.Tensor] = None      # TF32 mode: (hi, lo) float split of L^-1
+        self.S_lo: Optional[torch.Tensor] = None
 
     # ------------------------------------------------------------------------------------------
     def _launch(self, name: str, *args) -> None:
@@ -129,6 +132,7 @@ class ExactGPEngine:
             self._launch("gpx_mll_value", p(self.r), p(self.alpha), self.Np, self.N, p(self.logdet_blk),
                          p(self.out), st)
         self.has_kinv = False
+        self.has_split = False
         self.factor_key = key
         self.factored = True
         self.n_factorizations += 1
@@ -176,6 +180,7 @@ class ExactGPEngine:
     def predict(self, Xs: torch.Tensor, *, xa: Optional[torch.Tensor] = None, xr: Optional[torch.Tensor] = None,
                 prior_mean: Optional[torch.Tensor] = None, poly: Optional[PolyMeanSpec] = None,
                 y_mu: float = 0.0, y_sigma: float = 1.0, min_var: float = 1e-10, noisy: bool = True,
+                precision: str = "fp64", tf32_kchunk: int = 128,
                 out_mean: Optional[torch.Tensor] = None, out_std: Optional[torch.Tensor] = None,
                 chunk: Optional[int] = None):
         """Posterior mean and noisy std for device-resident points Xs [M, D] using the cached factors.
@@ -197,7 +202,14 @@ class ExactGPEngine:
         if M == 0:
             return out_mean, out_std
         Mc = int(chunk) if chunk else self.pick_chunk(M)
-        ws_bytes = int(self.lib.gpx_predict_workspace_bytes(self.Np, Mc))
+        if precision not in ("fp64", "tf32x3"):
+            raise ValueError("precision must be 'fp64' or 'tf32x3'")
+        tf32 = precision == "tf32x3"
+        if tf32:
+            self._ensure_split()
+            ws_bytes = int(self.lib.gpx_predict_tf32_workspace_bytes(self.Np, Mc))
+        else:
+            ws_bytes = int(self.lib.gpx_predict_workspace_bytes(self.Np, Mc))
         ws = self._workspace(ws_bytes)
         p = nv.ptr
         feat = wts = bias = None
@@ -209,11 +221,29 @@ class ExactGPEngine:
             n_feat, degree = int(feat.shape[0]), int(poly.degree)
         with torch.cuda.device(self.device):
             theta = self.theta if noisy else self.theta_latent
-            self._launch("gpx_predict_meanvar", p(Xs), M, p(self.X), self.N, self.D, p(theta), p(xa), p(xr),
-                         self.kind, p(self.S), self.Np, p(self.alpha), p(prior_mean), p(feat), n_feat, degree,
-                         p(wts), p(bias), float(y_mu), float(y_sigma), float(min_var), p(out_mean), p(out_std),
-                         p(ws), ws_bytes, Mc, nv.stream_ptr())
+            if tf32:
+                self._launch("gpx_predict_meanvar_tf32", p(Xs), M, p(self.X), self.N, self.D, p(theta), p(xa), p(xr),
+                             self.kind, p(self.S_hi), p(self.S_lo), self.Np, p(self.alpha), p(prior_mean), p(feat),
+                             n_feat, degree, p(wts), p(bias), float(y_mu), float(y_sigma), float(min_var),
+                             p(out_mean), p(out_std), p(ws), ws_bytes, Mc, int(tf32_kchunk), nv.stream_ptr())
+            else:
+                self._launch("gpx_predict_meanvar", p(Xs), M, p(self.X), self.N, self.D, p(theta), p(xa), p(xr),
+                             self.kind, p(self.S), self.Np, p(self.alpha), p(prior_mean), p(feat), n_feat, degree,
+                             p(wts), p(bias), float(y_mu), float(y_sigma), float(min_var), p(out_mean), p(out_std),
+                             p(ws), ws_bytes, Mc, nv.stream_ptr())
         return out_mean, out_std
+
+    def _ensure_split(self) -> None:
+        """(hi, lo) TF32 split of L^-1 for the tensor-core variance path; refreshed after every factorisation."""
+        if self.has_split:
+            return
+        if self.S_hi is None:
+            self.S_hi = torch.empty(self.Np, self.Np, dtype=torch.float32, device=self.device)
+            self.S_lo = torch.empty(self.Np, self.Np, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._launch("gpx_split_tf32", nv.ptr(self.S), self.Np * self.Np, nv.ptr(self.S_hi), nv.ptr(self.S_lo),
+                         self.Np, nv.stream_ptr())
+        self.has_split = True
 
     # ------------------------------------------------------------------------------------------
     def cross_kernel(self, Xs: torch.Tensor, xa=None, xr=None) -> torch.Tensor:

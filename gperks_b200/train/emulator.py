@@ -291,7 +291,7 @@ class GPEmulator(Trainable):
             return PolyMeanSpec(feat[:0].to(dev), degree, torch.zeros(0, dtype=F64, device=dev), b)
         return PolyMeanSpec(feat.to(dev).contiguous(), degree, w, b)
 
-    def predict_device(self, x_dev: torch.Tensor):
+    def predict_device(self, x_dev: torch.Tensor, precision: str = "fp64", tf32_kchunk: int = 128):
         """Device-resident predict: raw (unscaled) inputs ``x_dev`` [M, D] already in HBM -> (mean, std) device
         tensors, un-standardised when the output scaler is the (linear) StandardScaler.  This is the call the
         GPU-side consumers (history matching, GSA, the benchmark's device arm) use; ``predict`` wraps it with
@@ -312,11 +312,16 @@ class GPEmulator(Trainable):
             mean_d, std_d = eng.predict(
                 x_dev, xa=xa, xr=xr, prior_mean=prior, poly=poly,
                 y_mu=float(scy.mu) if linear_out else 0.0, y_sigma=float(scy.sigma) if linear_out else 1.0,
-                chunk=eng.pick_chunk(M, DEFAULT_PREDICT_CHUNK_BYTES) if M > 0 else None)
+                chunk=eng.pick_chunk(M, DEFAULT_PREDICT_CHUNK_BYTES) if M > 0 else None,
+                precision=precision, tf32_kchunk=tf32_kchunk)
         return mean_d, std_d, linear_out
 
-    def predict(self, X_new, with_covar: bool = False):
+    def predict(self, X_new, with_covar: bool = False, precision: str = "fp64", tf32_kchunk: int = 128):
         """(y_mean, y_std[, y_covar]) as numpy float64 -- GPErks/train/emulator.py:348-383.
+
+        ``precision="fp64"`` (default) is the float64 path (rel <= 1e-6 vs the float64 reference);
+        ``precision="tf32x3"`` runs the variance contraction on the tcgen05 tensor cores as a 3xTF32 split product
+        (rel <= 1e-3 on ``y_std``; ``y_mean`` is unchanged, bit for bit).
 
         ``y_std`` is the *noisy* predictive std (likelihood noise included) as in the reference.  Inputs go
         through pinned host memory, are un-scaled inside the kernels, streamed through the GPU in chunks, and the
@@ -332,7 +337,7 @@ class GPEmulator(Trainable):
                 x_dev = torch.from_numpy(X_new).pin_memory().to(cdev, non_blocking=True)
             else:
                 x_dev = torch.empty(0, self.scaled_data.input_size, dtype=F64, device=cdev)
-            mean_d, std_d, linear_out = self.predict_device(x_dev)
+            mean_d, std_d, linear_out = self.predict_device(x_dev, precision=precision, tf32_kchunk=tf32_kchunk)
             out = torch.empty(2, M, dtype=F64).pin_memory() if M > 0 else torch.empty(2, 0, dtype=F64)
             out[0].copy_(mean_d, non_blocking=True)
             out[1].copy_(std_d, non_blocking=True)

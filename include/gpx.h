@@ -85,6 +85,28 @@ int gpx_predict_meanvar(const double* Xs, long M, const double* X, int N, int D,
                         double min_var, double* out_mean, double* out_std, void* workspace,
                         size_t workspace_bytes, int Mc, void* stream);
 
+/* ---- TF32 mode of the predictive variance (north_star tolerance: rel 1e-3): 3xTF32 on tcgen05 / TMEM ----
+ * gpx_split_tf32: (hi, lo) float split of n FP64 values, x ~= hi + lo, both exactly representable in TF32
+
+ * (run once per factorisation on S = L^-1; ld = Np makes it zero the mirrored L^-T blocks above the diagonal, ld = 0
+ * splits a flat array).  gpx_trmm_sumsq_tf32: qpart[it][m] = sum over the 256 rows of tile
+ * `it` of (K* L^-T)[m][i]^2, it < gpx_tf32_row_tiles(Np).  gpx_predict_meanvar_tf32: as gpx_predict_meanvar with
+ * the variance contraction on the tensor cores; kernel matrix and posterior mean remain FP64.
+ * kchunk: K elements accumulated in TMEM between round-to-nearest flushes (multiple of 32, <= 0 -> 128): the tensor
+ * core's FP32 accumulation truncates, so the error of std grows ~linearly with kchunk (2.6e-4 at 128, N=8192).
+ * replaces: the same call sites as gpx_predict_meanvar (GPErks/train/emulator.py:348-363). */
+int gpx_split_tf32(const double* src, long n, float* hi, float* lo, int ld, void* stream);
+int gpx_tf32_row_tiles(int Np);
+int gpx_trmm_sumsq_tf32(const float* Shi, const float* Slo, int Np, const float* Khi, const float* Klo, int Mc,
+                        double* qpart, int kchunk, void* stream);
+size_t gpx_predict_tf32_workspace_bytes(int Np, int Mc);
+int gpx_predict_meanvar_tf32(const double* Xs, long M, const double* X, int N, int D, const double* theta,
+                             const double* xa, const double* xr, int kind, const float* Shi, const float* Slo, int Np,
+                             const double* alpha, const double* prior_mean, const int* feat_idx, int n_feat,
+                             int degree, const double* weights, const double* bias, double y_mu, double y_sigma,
+                             double min_var, double* out_mean, double* out_std, void* workspace,
+                             size_t workspace_bytes, int Mc, int kchunk, void* stream);
+
 /* History-matching epilogue over E emulators: I[m] = maxno-th largest_e sqrt((mean[e][m]-z[e])^2/(std[e][m]^2+v[e])),
  * PV[m] = maxno-th largest_e std[e][m]^2/v[e]; inputs emulator-major [E][M]; 1 <= maxno <= min(E, 8).
  * replaces: the per-point loop with two np.sort in Wave.compute_impl, GPErks/perks/history_matching.py:57-62. */

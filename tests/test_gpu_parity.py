@@ -260,7 +260,7 @@ def test_adam_training_follows_oracle_autograd(dev, goldens):
         ol = oracle_loss()
         ol.backward()
         oopt.step()
-        assert loss == pytest.approx(float(ol), rel=1e-9), f"step {step}"
+        assert loss == pytest.approx(float(ol.detach()), rel=1e-9), f"step {step}"
     for k, p in m.named_parameters():
         np.testing.assert_allclose(p.detach().numpy(), raw[k].detach().numpy(), rtol=1e-7, atol=1e-9, err_msg=k)
 
@@ -348,3 +348,69 @@ def test_full_size_properties_n8192(dev):
     # (5) determinism / chunk invariance at full size
     m12b, s12b = eng.predict(Xq, prior_mean=zero, chunk=1024)
     assert torch.equal(m12, m12b) and torch.equal(s12, s12b)
+
+
+# ----------------------------------------------------------------------------------------------------
+# TF32 mode (tcgen05 3xTF32 variance contraction): north_star tolerance rel 1e-3 vs the float64 path
+# ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,D,M,kind", [(300, 3, 1000, O.KIND_RBF), (2048, 6, 8192, O.KIND_MATERN52),
+                                        (1000, 5, 777, O.KIND_MATERN32)])
+def test_tf32_mode_within_tolerance(dev, N, D, M, kind):
+    X, y, Xs, ls, s, w, b = _problem(N, D, M, seed=N)
+    nz = 1e-2
+    eng = _engine(dev, X, y, kind, ls, s, nz, w, b)
+    pm = (Xs @ w + b).to(dev)
+    m64, s64 = eng.predict(Xs.to(dev), prior_mean=pm)
+    m32, s32 = eng.predict(Xs.to(dev), prior_mean=pm, precision="tf32x3")
+    assert torch.equal(m64, m32)                                     # the mean path stays FP64
+    rel = ((s32 - s64).abs() / s64)
+    assert float(rel.max()) < 1e-3, float(rel.max())                 # TF32-mode tolerance (north_star)
+    # against the CPU oracle as well (small case only)
+    if N <= 1000:
+        _, vref = O.predict(X, y, kind, ls, s, nz, X @ w + b, Xs, Xs @ w + b)
+        np.testing.assert_allclose(s32.cpu().numpy(), vref.sqrt().numpy(), rtol=1e-3)
+    # shorter accumulation chunks are more accurate (the tensor core truncates its FP32 accumulation)
+    _, s32b = eng.predict(Xs.to(dev), prior_mean=pm, precision="tf32x3", tf32_kchunk=32)
+    assert float(((s32b - s64).abs() / s64).max()) < 3e-4
+    # refactorising refreshes the split factor
+    eng.factorize(eng.theta_in.clone() * 1.0, eng.r[:N].clone() * 2.0)
+    _, s32c = eng.predict(Xs.to(dev), prior_mean=pm, precision="tf32x3")
+    assert float(((s32c - s64).abs() / s64).max()) < 1e-3           # the variance does not depend on y
+
+
+def test_tcgen05_kernel_exact_on_integers(dev):
+    """Small-integer operands are exact in TF32 and in the FP32 accumulator: the tensor-core kernel must then be
+    bit-exact, which pins the TMA swizzle / UMMA descriptors / TMEM epilogue layout."""
+    lib = nv.lib()
+    for Np, Mc in [(256, 128), (384, 256), (1024, 128)]:
+        g = torch.Generator(device="cpu").manual_seed(Np)
+        Khi = torch.randint(-3, 4, (Mc, Np), generator=g).float().to(dev)
+        Shi = torch.tril(torch.randint(-2, 3, (Np, Np), generator=g).float()).to(dev)
+        Klo = (torch.randint(-3, 4, (Mc, Np), generator=g).float() * 2.0 ** -12).to(dev)
+        Slo = (torch.tril(torch.randint(-2, 3, (Np, Np), generator=g).float()) * 2.0 ** -12).to(dev)
+        zK, zS = torch.zeros_like(Khi), torch.zeros_like(Shi)
+        nt = lib.gpx_tf32_row_tiles(Np)
+        for (kl, sl, exact) in ((zK, zS, True), (Klo, Slo, False)):
+            q = torch.empty(nt, Mc, dtype=F64, device=dev)
+            for kchunk in (32, 128, 4096):
+                nv.check(lib.gpx_trmm_sumsq_tf32(nv.ptr(Shi), nv.ptr(sl), Np, nv.ptr(Khi), nv.ptr(kl), Mc, nv.ptr(q), kchunk,
+                                                 nv.stream_ptr()), "tf32")
+                V = (Khi.double() + kl.double()) @ (Shi.double() + sl.double()).T
+                Vpad = torch.zeros(Mc, nt * 256, dtype=F64, device=dev)
+                Vpad[:, :Np] = V
+                ref = (Vpad.reshape(Mc, nt, 256) ** 2).sum(-1).T
+                if exact:
+                    assert torch.equal(q, ref)
+                else:
+                    np.testing.assert_allclose(q.cpu().numpy(), ref.cpu().numpy(), rtol=5e-6)
+
+
+def test_emulator_predict_tf32_precision(dev, goldens):
+    g = goldens["example_2"]
+    em, ds = _emulator_from_golden(g, "example_2")
+    rng = np.random.default_rng(1)
+    Xq = rng.random((3000, 2))
+    m64, s64 = em.predict(Xq)
+    m32, s32 = em.predict(Xq, precision="tf32x3")
+    assert np.array_equal(m64, m32)
+    np.testing.assert_allclose(s32, s64, rtol=1e-3)
