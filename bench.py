@@ -35,6 +35,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 N_TRAIN, DIM = 8192, 8
+NCU_TRAFFIC_BYTES = 13.546e9   # dram read+write per launch, profiles/r01_ncu_trmm_tma.txt (N=8192, chunk 32768)
 KIND_NAME = "matern52"
 NOISE = 1e-2
 
@@ -184,6 +185,9 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=32768, help="points of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mll-evals", type=int, default=3)
+    ap.add_argument("--no-tf32", action="store_true", help="skip the TF32-mode (tcgen05) arm")
+    ap.add_argument("--ncu-traffic", type=float, default=None,
+                    help="dram bytes per launch of the dominant kernel from an ncu --set full capture (profiles/)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -212,7 +216,7 @@ def main():
     torch.cuda.synchronize()
     theta, resid = eng.theta_in.clone(), eng.r[:eng.N].clone()
     mll_ms = []
-    for i in range(args.mll_evals + 1):
+    for i in range(args.mll_evals + 1 if args.mll_evals > 0 else 0):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         eng.factorize(theta, resid)
@@ -309,6 +313,73 @@ def main():
     e2e_value = world * M * e2e_steps / float(t.item())
     parity = float(np.max(np.abs(y_mean - out_mean.cpu().numpy())))     # the two arms must agree bit for bit
 
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel (one chunk of Mc points) from the
+    # committed `ncu --set full` capture (profiles/r01_ncu_trmm_tma.txt); only valid for the default chunk size
+    TRAFFIC = args.ncu_traffic if args.ncu_traffic is not None else (NCU_TRAFFIC_BYTES if Mc == 32768 and eng.N == 8192 else None)
+
+    # ---- TF32 mode (tcgen05 3xTF32 variance contraction), reported beside the FP64 headline
+    tf32 = None
+    if not args.no_tf32:
+        s64 = out_std.clone()
+        tmean = torch.empty_like(out_mean)
+        tstd = torch.empty_like(out_std)
+
+        def tf32_step():
+            eng.predict(x_dev, xa=xa, xr=xr, poly=poly, y_mu=float(scy.mu), y_sigma=float(scy.sigma), out_mean=tmean,
+                        out_std=tstd, chunk=Mc, precision="tf32x3")
+        for _ in range(3):
+            tf32_step()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(args.steps):
+            tf32_step()
+        b.record()
+        barrier()
+        t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        tf32_ms = float(t.item())
+        rel = ((tstd - s64).abs() / s64)
+        # the tensor-core kernel alone, and the cuBLAS TF32 GEMM rate measured here as its denominator
+        Khi = ws.view(torch.float32)[: Mc * eng.Np]
+        Klo = ws.view(torch.float32)[Mc * eng.Np: 2 * Mc * eng.Np]
+        nt = int(lib.gpx_tf32_row_tiles(eng.Np))
+        qp = torch.empty(nt * Mc, dtype=torch.float64, device=dev)
+        tk = []
+        for i in range(4):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            nv.check(lib.gpx_trmm_sumsq_tf32(nv.ptr(eng.S_hi), nv.ptr(eng.S_lo), eng.Np, Khi.data_ptr(), Klo.data_ptr(), Mc,
+                                             nv.ptr(qp), 128, st), "tf32 trmm")
+            b.record()
+            torch.cuda.synchronize()
+            if i > 0:
+                tk.append(a.elapsed_time(b))
+        tk = sum(tk) / len(tk)
+        a32 = torch.randn(8192, 8192, device=dev)
+        b32 = torch.randn(8192, 8192, device=dev)
+        torch.backends.cuda.matmul.allow_tf32 = True
+        tg = []
+        for i in range(4):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            torch.matmul(a32, b32)
+            b.record()
+            torch.cuda.synchronize()
+            if i > 0:
+                tg.append(a.elapsed_time(b))
+        torch.backends.cuda.matmul.allow_tf32 = False
+        tf32_peak = 2 * 8192 ** 3 / (min(tg) / 1e3) / 1e12
+        raw = 3.0 * float(eng.N) ** 2 * Mc / (tk / 1e3) / 1e12
+        tf32 = {"value": world * M * args.steps / (tf32_ms / 1e3), "unit": "points/s", "ms_per_step": tf32_ms / args.steps,
+                "max_rel_err_std_vs_fp64": float(rel.max()), "median_rel_err_std_vs_fp64": float(rel.median()),
+                "mean_bitwise_equal_to_fp64": bool(torch.equal(tmean, out_mean)), "tolerance": 1e-3, "kchunk": 128,
+                "roofline": {"kernel": "trmm_sumsq_tf32_kernel (tcgen05.mma kind::tf32, 3 MMAs per product, TMEM accumulators)",
+                             "bound": "tensor", "achieved": raw, "peak": tf32_peak, "unit": "TFLOP/s (TF32, raw = 3 x useful)",
+                             "frac": raw / tf32_peak, "useful_tflops": raw / 3.0, "kernel_ms": tk,
+                             "peak_source": "cuBLAS TF32 GEMM 8192^3 (torch.matmul, allow_tf32) measured in this run"}}
+
     line = {
         "metric": "predict points/sec (mean+var) N=8192 D=8", "value": value, "unit": "points/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
@@ -320,12 +391,14 @@ def main():
                 "steps": e2e_steps, "api": "GPEmulator.predict(numpy)", "max_abs_diff_vs_device_arm": parity},
         "gpu_launches": int(args.steps * n_chunks * 3),
         "roofline": {"kernel": "trmm_sumsq_tma_kernel (variance contraction L^-1 K*^T: TMA + mbarrier ring, FP64 DMMA)", "bound": "tensor",
-                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": TRAFFIC,
                      "peak_source": "gpx_peak_dmma probe measured in this run (FP64 DMMA.8x8x4 issue peak; MEASURED_PEAKS.json "
                                     "has no FP64 figure; cuBLAS DGEMM 8192^3 measured 35.5 TF/s on this pool, see profiles/)",
                      "algorithmic_flops_per_launch": flops_per_launch, "kernel_ms": k_ms, "kernel_share_of_step": kernel_share},
-        "mll_grad": {"evals_per_s": 1e3 / (sum(mll_ms) / len(mll_ms)), "ms_per_eval": sum(mll_ms) / len(mll_ms),
-                     "n_train": eng.N, "what": "K_hat build + Cholesky + L^-1 + alpha + -mll + K_hat^-1 + gradient reduce"},
+        "mll_grad": ({"evals_per_s": 1e3 / (sum(mll_ms) / len(mll_ms)), "ms_per_eval": sum(mll_ms) / len(mll_ms),
+                      "n_train": eng.N, "what": "K_hat build + Cholesky + L^-1 + alpha + -mll + K_hat^-1 + gradient reduce"}
+                     if mll_ms else None),
+        "tf32_mode": tf32,
         "clocks": clocks.summary(),
     }
     if rank == 0 and not args.no_cpu_baseline and world == 1:
