@@ -324,22 +324,31 @@ def main():
         tmean = torch.empty_like(out_mean)
         tstd = torch.empty_like(out_std)
 
-        def tf32_step():
-            eng.predict(x_dev, xa=xa, xr=xr, poly=poly, y_mu=float(scy.mu), y_sigma=float(scy.sigma), out_mean=tmean,
-                        out_std=tstd, chunk=Mc, precision="tf32x3")
-        for _ in range(3):
-            tf32_step()
-        barrier()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(args.steps):
-            tf32_step()
-        b.record()
-        barrier()
-        t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        tf32_ms = float(t.item())
+        def tf32_arm(precision):
+            def tf32_step():
+                eng.predict(x_dev, xa=xa, xr=xr, poly=poly, y_mu=float(scy.mu), y_sigma=float(scy.sigma),
+                            out_mean=tmean, out_std=tstd, chunk=Mc, precision=precision)
+            for _ in range(3):
+                tf32_step()
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(args.steps):
+                tf32_step()
+            b.record()
+            barrier()
+            t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            rel_s = ((tstd - s64).abs() / s64)
+            rel_m = (tmean - out_mean).abs().max() / out_mean.abs().max()
+            return {"value": world * M * args.steps / (ms / 1e3), "unit": "points/s", "ms_per_step": ms / args.steps,
+                    "max_rel_err_std_vs_fp64": float(rel_s.max()), "median_rel_err_std_vs_fp64": float(rel_s.median()),
+                    "max_err_mean_vs_fp64_rel_to_scale": float(rel_m)}
+        fast = tf32_arm("tf32x3_fast")
+        exact = tf32_arm("tf32x3")
+        tf32_ms = exact["ms_per_step"] * args.steps
         rel = ((tstd - s64).abs() / s64)
         # the tensor-core kernel alone, and the cuBLAS TF32 GEMM rate measured here as its denominator
         Khi = ws.view(torch.float32)[: Mc * eng.Np]
@@ -372,9 +381,8 @@ def main():
         torch.backends.cuda.matmul.allow_tf32 = False
         tf32_peak = 2 * 8192 ** 3 / (min(tg) / 1e3) / 1e12
         raw = 3.0 * float(eng.N) ** 2 * Mc / (tk / 1e3) / 1e12
-        tf32 = {"value": world * M * args.steps / (tf32_ms / 1e3), "unit": "points/s", "ms_per_step": tf32_ms / args.steps,
-                "max_rel_err_std_vs_fp64": float(rel.max()), "median_rel_err_std_vs_fp64": float(rel.median()),
-                "mean_bitwise_equal_to_fp64": bool(torch.equal(tmean, out_mean)), "tolerance": 1e-3, "kchunk": 128,
+        tf32 = {"tf32x3": exact, "tf32x3_fast": fast, "tolerance": 1e-3, "kchunk": 128,
+                "note": "tf32x3: K* evaluated in FP64 (mean bit-identical to fp64); tf32x3_fast: K* evaluated in FP32",
                 "roofline": {"kernel": "trmm_sumsq_tf32_kernel (tcgen05.mma kind::tf32, 3 MMAs per product, TMEM accumulators)",
                              "bound": "tensor", "achieved": raw, "peak": tf32_peak, "unit": "TFLOP/s (TF32, raw = 3 x useful)",
                              "frac": raw / tf32_peak, "useful_tflops": raw / 3.0, "kernel_ms": tk,

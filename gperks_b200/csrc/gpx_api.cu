@@ -177,7 +177,7 @@ int gpx_predict_meanvar_tf32(const double* Xs, long M, const double* X, int N, i
                              int degree, const double* weights, const double* bias, double y_mu, double y_sigma,
                              double min_var, double* out_mean, double* out_std, void* workspace,
                              size_t workspace_bytes, int Mc, int kchunk, void* stream) {
-    if (kchunk > 0 && kchunk % 32) return -27;
+    if (kchunk % 32) return -27;
     if (!Xs || !X || !theta || !Shi || !Slo || !alpha || !out_mean || !out_std || !workspace) return -1;
     if (M < 0) return -2;
     if (M == 0) return 0;

@@ -154,6 +154,113 @@ kmat_cross_kernel(const double* __restrict__ Xs, long m_valid, const double* __r
 }
 
 // ------------------------------------------------------------------------------------------------
+// TF32-mode cross kernel: K* evaluated in FP32 (coordinates are scaled in FP64, rounded once) and written as the
+// (hi, lo) TF32 operand pair of the 3xTF32 contraction; the posterior-mean partials accumulate in FP64.
+// Relative error of an entry ~3e-7 -- far inside the mode's 1e-3 tolerance -- at ~1/5 of the FP64 builder's cost.
+__device__ __forceinline__ void stage_coords_f32(float* sm, const double* __restrict__ X, long row0, long n_valid, int D,
+                                                 const double* __restrict__ theta, const double* __restrict__ xa,
+                                                 const double* __restrict__ xr) {
+    for (int e = threadIdx.x; e < TILE * D; e += P_THREADS) {
+        int r = e / D, d = e - r * D;
+        double v = 0.0;
+        if (row0 + r < n_valid) {
+            v = X[(row0 + r) * (long)D + d];
+            if (xa != nullptr) v = (v - xa[d]) / xr[d];
+            v *= theta[d];
+        }
+        sm[d * P_LD + r] = (float)v;
+    }
+}
+
+template <int KIND>
+__device__ __forceinline__ float kernel_value_f32(float r2, float s) {
+    if (KIND == RBF) return s * expf(-0.5f * r2);
+    const float r = sqrtf(fmaxf(r2, 1e-30f));
+    if (KIND == MATERN12) return s * expf(-r);
+    if (KIND == MATERN32) {
+        const float c = 1.7320508075688772f;
+        return s * (1.0f + c * r) * expf(-c * r);
+    }
+    const float c = 2.23606797749979f;
+    return s * (1.0f + c * r + (5.0f / 3.0f) * r2) * expf(-c * r);
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(P_THREADS, 2)
+kmat_cross_f32_kernel(const double* __restrict__ Xs, long m_valid, const double* __restrict__ X, int N, int D,
+                      const double* __restrict__ theta, const double* __restrict__ xa, const double* __restrict__ xr,
+                      const double* __restrict__ alpha, float* __restrict__ Khi, float* __restrict__ Klo, int Np,
+                      double* __restrict__ mean_part, int Mc) {
+    const int jb = blockIdx.x, mb = blockIdx.y;
+    extern __shared__ double smd[];
+    float* sa = reinterpret_cast<float*>(smd);     // test points  [d][129]
+    float* sb = sa + MAXD * P_LD;                   // train points [d][129]
+    double* sal = reinterpret_cast<double*>(sb + MAXD * P_LD + 2);   // alpha tile [128] (8-byte aligned: 2*32*129+2 floats)
+    double* smean = sal + TILE;
+    stage_coords_f32(sa, Xs, (long)mb * TILE, m_valid, D, theta, xa, xr);
+    stage_coords_f32(sb, X, (long)jb * TILE, N, D, theta, nullptr, nullptr);
+    if (threadIdx.x < TILE) sal[threadIdx.x] = alpha[jb * TILE + threadIdx.x];
+    __syncthreads();
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    float r2[8][8];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) r2[a][b] = 0.f;
+    for (int d = 0; d < D; ++d) {
+        float xa_[8], xb_[8];
+#pragma unroll
+        for (int a = 0; a < 8; ++a) xa_[a] = sa[d * P_LD + ty + 16 * a];
+#pragma unroll
+        for (int b = 0; b < 8; ++b) xb_[b] = sb[d * P_LD + tx + 16 * b];
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                const float df = xa_[a] - xb_[b];
+                r2[a][b] = fmaf(df, df, r2[a][b]);
+            }
+    }
+    const float s = (float)theta[D];
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        const long m = (long)mb * TILE + ty + 16 * a;
+        double part = 0.0;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const long j = (long)jb * TILE + tx + 16 * b;
+            const float v = (j < N) ? kernel_value_f32<KIND>(r2[a][b], s) : 0.f;
+            uint32_t h, l;
+            asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(h) : "f"(v));
+            const float fh = __uint_as_float(h);
+            asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(l) : "f"(v - fh));
+            Khi[m * Np + j] = fh;
+            Klo[m * Np + j] = __uint_as_float(l);
+            part = fma((double)v, sal[tx + 16 * b], part);
+        }
+        part += __shfl_xor_sync(0xffffffffu, part, 1);
+        part += __shfl_xor_sync(0xffffffffu, part, 2);
+        part += __shfl_xor_sync(0xffffffffu, part, 4);
+        part += __shfl_xor_sync(0xffffffffu, part, 8);
+        if (tx == 0) smean[ty + 16 * a] = part;
+    }
+    __syncthreads();
+    if (threadIdx.x < TILE) mean_part[(long)jb * Mc + (long)mb * TILE + threadIdx.x] = smean[threadIdx.x];
+}
+
+template <int KIND>
+static int launch_kmat_cross_f32(const double* Xs, long m_valid, const double* X, int N, int D, const double* theta,
+                                 const double* xa, const double* xr, const double* alpha, float* Khi, float* Klo,
+                                 int Np, double* mean_part, int Mc, cudaStream_t st) {
+    const size_t smem = (size_t(2) * MAXD * P_LD + 2) * 4 + 2 * TILE * 8;
+    cudaFuncSetAttribute(kmat_cross_f32_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kmat_cross_f32_kernel<KIND><<<dim3(Np / TILE, Mc / TILE), P_THREADS, smem, st>>>(Xs, m_valid, X, N, D, theta, xa, xr,
+                                                                                     alpha, Khi, Klo, Np, mean_part, Mc);
+    GPX_CHECK_LAUNCH();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Gradient reduction.  grid = lower tiles (bj <= bi).  partial[(bi*nb + bj)*(D+2) + p]:
 //   p <  D : sum W_ij g(r_ij) dz_ijd^2     (weight 2 for off-diagonal tiles)
 //   p == D : sum W_ij k_ij / s
@@ -325,10 +432,16 @@ int kmat_cross(const double* Xs, long m_valid, const double* X, int N, int D, co
 #undef C_
 }
 
-// TF32 mode: K* written as (hi, lo) float pairs for the 3xTF32 tensor-core contraction; mean partials stay FP64
+// TF32 mode: K* written as (hi, lo) float pairs for the 3xTF32 tensor-core contraction.
+//   fp32_eval = 1 (default of the mode): kernel evaluated in FP32;  0: evaluated in FP64, then split
 int kmat_cross_split(const double* Xs, long m_valid, const double* X, int N, int D, const double* theta,
                      const double* xa, const double* xr, int kind, const double* alpha, float* Khi, float* Klo, int Np,
-                     double* mean_part, int Mc, cudaStream_t st) {
+                     double* mean_part, int Mc, int fp32_eval, cudaStream_t st) {
+    if (fp32_eval) {
+#define C_(KD) launch_kmat_cross_f32<KD>(Xs, m_valid, X, N, D, theta, xa, xr, alpha, Khi, Klo, Np, mean_part, Mc, st)
+        GPX_DISPATCH_KIND(kind, C_)
+#undef C_
+    }
 #define C_(KD) launch_kmat_cross<KD>(Xs, m_valid, X, N, D, theta, xa, xr, alpha, nullptr, Np, mean_part, Mc, Khi, Klo, st)
     GPX_DISPATCH_KIND(kind, C_)
 #undef C_

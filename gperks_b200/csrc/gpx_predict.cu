@@ -321,7 +321,7 @@ int predict_meanvar(const double* Xs, long M, const double* X, int N, int D, con
 // ---- TF32 mode (tcgen05, 3xTF32) ------------------------------------------------------------------------
 int kmat_cross_split(const double* Xs, long m_valid, const double* X, int N, int D, const double* theta,
                      const double* xa, const double* xr, int kind, const double* alpha, float* Khi, float* Klo, int Np,
-                     double* mean_part, int Mc, cudaStream_t st);
+                     double* mean_part, int Mc, int fp32_eval, cudaStream_t st);
 int trmm_sumsq_tf32(const float* Shi, const float* Slo, int Np, const float* Khi, const float* Klo, int Mc,
                     double* qpart, int kchunk, cudaStream_t st);
 int tf32_row_tiles(int Np);
@@ -342,6 +342,10 @@ int predict_meanvar_tf32(const double* Xs, long M, const double* X, int N, int D
     if (D > MAXD || D < 1) return -5;
     if (workspace_bytes < predict_tf32_workspace_bytes(Np, Mc)) return -23;
     const int nb = Np / TILE, nt = tf32_row_tiles(Np);
+    // kchunk < 0: kernel values evaluated in FP64 then split (posterior mean bit-identical to the FP64 path);
+    // kchunk >= 0: evaluated in FP32 (default of the mode, ~5x cheaper builder)
+    const int fp32_eval = kchunk >= 0;
+    const int kc = kchunk < 0 ? -kchunk : kchunk;
     float* Khi = reinterpret_cast<float*>(workspace);
     float* Klo = Khi + (size_t)Mc * Np;
     double* mean_part = reinterpret_cast<double*>(Klo + (size_t)Mc * Np);
@@ -350,9 +354,9 @@ int predict_meanvar_tf32(const double* Xs, long M, const double* X, int N, int D
         const long mv = (M - m0 < Mc) ? (M - m0) : Mc;
         const int mc = round_up((int)mv, TILE);
         const double* xs = Xs + m0 * D;
-        int rc = kmat_cross_split(xs, mv, X, N, D, theta, xa, xr, kind, alpha, Khi, Klo, Np, mean_part, mc, st);
+        int rc = kmat_cross_split(xs, mv, X, N, D, theta, xa, xr, kind, alpha, Khi, Klo, Np, mean_part, mc, fp32_eval, st);
         if (rc) return rc;
-        rc = trmm_sumsq_tf32(Shi, Slo, Np, Khi, Klo, mc, qpart, kchunk, st);
+        rc = trmm_sumsq_tf32(Shi, Slo, Np, Khi, Klo, mc, qpart, kc, st);
         if (rc) return rc;
         // mean partials come in nb row blocks, variance partials in nt 256-row tiles
         predict_finalize_kernel<<<(int)((mv + 255) / 256), 256, 0, st>>>(

@@ -202,9 +202,14 @@ class ExactGPEngine:
         if M == 0:
             return out_mean, out_std
         Mc = int(chunk) if chunk else self.pick_chunk(M)
-        if precision not in ("fp64", "tf32x3"):
-            raise ValueError("precision must be 'fp64' or 'tf32x3'")
-        tf32 = precision == "tf32x3"
+        if precision not in ("fp64", "tf32x3", "tf32x3_fast"):
+            raise ValueError("precision must be 'fp64', 'tf32x3' or 'tf32x3_fast'")
+        # tf32x3: K* evaluated in FP64 then split (posterior mean bit-identical to fp64; variance on tcgen05);
+        # tf32x3_fast: K* evaluated in FP32 as well (mean moves by ~1e-4 of its scale for noise-like targets)
+        tf32 = precision != "fp64"
+        kchunk = abs(int(tf32_kchunk)) or 128
+        if precision == "tf32x3":
+            kchunk = -kchunk
         if tf32:
             self._ensure_split()
             ws_bytes = int(self.lib.gpx_predict_tf32_workspace_bytes(self.Np, Mc))
@@ -225,7 +230,7 @@ class ExactGPEngine:
                 self._launch("gpx_predict_meanvar_tf32", p(Xs), M, p(self.X), self.N, self.D, p(theta), p(xa), p(xr),
                              self.kind, p(self.S_hi), p(self.S_lo), self.Np, p(self.alpha), p(prior_mean), p(feat),
                              n_feat, degree, p(wts), p(bias), float(y_mu), float(y_sigma), float(min_var),
-                             p(out_mean), p(out_std), p(ws), ws_bytes, Mc, int(tf32_kchunk), nv.stream_ptr())
+                             p(out_mean), p(out_std), p(ws), ws_bytes, Mc, kchunk, nv.stream_ptr())
             else:
                 self._launch("gpx_predict_meanvar", p(Xs), M, p(self.X), self.N, self.D, p(theta), p(xa), p(xr),
                              self.kind, p(self.S), self.Np, p(self.alpha), p(prior_mean), p(feat), n_feat, degree,

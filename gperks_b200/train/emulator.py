@@ -321,7 +321,8 @@ class GPEmulator(Trainable):
 
         ``precision="fp64"`` (default) is the float64 path (rel <= 1e-6 vs the float64 reference);
         ``precision="tf32x3"`` runs the variance contraction on the tcgen05 tensor cores as a 3xTF32 split product
-        (rel <= 1e-3 on ``y_std``; ``y_mean`` is unchanged, bit for bit).
+        (rel <= 1e-3 on ``y_std``; ``y_mean`` is unchanged, bit for bit); ``"tf32x3_fast"`` additionally evaluates
+        the cross-kernel in FP32 (``y_mean`` then moves by up to ~1e-4 of its scale for noise-like targets).
 
         ``y_std`` is the *noisy* predictive std (likelihood noise included) as in the reference.  Inputs go
         through pinned host memory, are un-scaled inside the kernels, streamed through the GPU in chunks, and the

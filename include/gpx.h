@@ -94,6 +94,8 @@ int gpx_predict_meanvar(const double* Xs, long M, const double* X, int N, int D,
  * the variance contraction on the tensor cores; kernel matrix and posterior mean remain FP64.
  * kchunk: K elements accumulated in TMEM between round-to-nearest flushes (multiple of 32, <= 0 -> 128): the tensor
  * core's FP32 accumulation truncates, so the error of std grows ~linearly with kchunk (2.6e-4 at 128, N=8192).
+ * gpx_predict_meanvar_tf32 only: kchunk >= 0 evaluates K* in FP32 (entries ~3e-7 relative); kchunk < 0 evaluates it in
+ * FP64 before the split (posterior mean bit-identical to gpx_predict_meanvar) and uses |kchunk|.
  * replaces: the same call sites as gpx_predict_meanvar (GPErks/train/emulator.py:348-363). */
 int gpx_split_tf32(const double* src, long n, float* hi, float* lo, int ld, void* stream);
 int gpx_tf32_row_tiles(int Np);

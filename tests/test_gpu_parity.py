@@ -362,13 +362,18 @@ def test_tf32_mode_within_tolerance(dev, N, D, M, kind):
     pm = (Xs @ w + b).to(dev)
     m64, s64 = eng.predict(Xs.to(dev), prior_mean=pm)
     m32, s32 = eng.predict(Xs.to(dev), prior_mean=pm, precision="tf32x3")
-    assert torch.equal(m64, m32)                                     # the mean path stays FP64
+    assert torch.equal(m64, m32)              # tf32x3: K* evaluated in FP64 => the mean is bit-identical to fp64
     rel = ((s32 - s64).abs() / s64)
     assert float(rel.max()) < 1e-3, float(rel.max())                 # TF32-mode tolerance (north_star)
     # against the CPU oracle as well (small case only)
     if N <= 1000:
         _, vref = O.predict(X, y, kind, ls, s, nz, X @ w + b, Xs, Xs @ w + b)
         np.testing.assert_allclose(s32.cpu().numpy(), vref.sqrt().numpy(), rtol=1e-3)
+    # tf32x3_fast: K* evaluated in FP32 too (entries ~3e-7 relative); targets here are pure noise, the worst case for
+    # cancellation in K* alpha, and the mean still stays within 1e-3 of its scale
+    m32f, s32f = eng.predict(Xs.to(dev), prior_mean=pm, precision="tf32x3_fast")
+    assert float((m32f - m64).abs().max()) < 1e-3 * float(m64.abs().max())
+    assert float(((s32f - s64).abs() / s64).max()) < 1e-3
     # shorter accumulation chunks are more accurate (the tensor core truncates its FP32 accumulation)
     _, s32b = eng.predict(Xs.to(dev), prior_mean=pm, precision="tf32x3", tf32_kchunk=32)
     assert float(((s32b - s64).abs() / s64).max()) < 3e-4
@@ -414,3 +419,6 @@ def test_emulator_predict_tf32_precision(dev, goldens):
     m32, s32 = em.predict(Xq, precision="tf32x3")
     assert np.array_equal(m64, m32)
     np.testing.assert_allclose(s32, s64, rtol=1e-3)
+    m32f, s32f = em.predict(Xq, precision="tf32x3_fast")
+    np.testing.assert_allclose(m32f, m64, rtol=1e-3, atol=1e-4 * np.abs(m64).max())
+    np.testing.assert_allclose(s32f, s64, rtol=1e-3)
