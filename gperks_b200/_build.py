@@ -27,7 +27,7 @@ def nvcc_path() -> str:
 
 def build(force: bool = False, verbose: bool = False) -> Path:
     srcs = [CSRC / s for s in SOURCES]
-    deps = srcs + [CSRC / "gpx_common.cuh", CSRC / "gpx_tma.cuh", PKG.parent / "include" / "gpx.h"]
+    deps = srcs + [CSRC / "gpx_common.cuh", CSRC / "gpx_tma.cuh", CSRC / "gpx_gemm_tma.cuh", PKG.parent / "include" / "gpx.h"]
     if LIB.exists() and not force:
         return LIB
     LIBDIR.mkdir(parents=True, exist_ok=True)

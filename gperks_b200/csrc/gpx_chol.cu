@@ -11,6 +11,7 @@
 //                 upper off-diagonal blocks = mirror (L^-T), so rows of S serve as "columns" of L^-1.
 //   DT (nb x 128 x 128): transposed diagonal blocks of L^-1 (upper triangular, zero below).
 #include "gpx_common.cuh"
+#include "gpx_gemm_tma.cuh"
 #include <stdlib.h>
 
 namespace gpx {
@@ -414,6 +415,107 @@ lauum_kernel(const double* __restrict__ S, const double* __restrict__ DT, double
 }
 
 // ------------------------------------------------------------------------------------------------
+// TMA editions of the dense stages (default; GPX_CHOL_IMPL=cpasync selects the LDGSTS kernels above).
+// Tensor maps: tmK = K[Np][Np], tmS = S[Np][Np], tmW = W[Np][Np], tmD = DT viewed as [nb*128][128].
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GT_THREADS, 1)
+potrf_panel_tma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmS,
+                       double* __restrict__ K, int Np, int p) {
+    extern __shared__ unsigned char smem_raw[];
+    const int ti = p + 1 + blockIdx.x;
+    TOperand A = t_operand(&tmK, ti * TILE, p * TILE);
+    TOperand B = t_operand(&tmS, p * TILE, p * TILE);
+    double acc[8][4][2];
+    gemm_nt_tma_mainloop(acc, A, B, 0, TILE, smem_raw);
+    // every thread must be past its last read of the A tile (== this output tile) before anyone overwrites it:
+    // the reads went through the async proxy into smem and were all consumed above, so a CTA barrier suffices
+    __syncthreads();
+    double* Ct = K + (long)ti * TILE * Np + (long)p * TILE;
+    gemm_foreach_pair(acc, [&](int row, int col, double v0, double v1) {
+        *reinterpret_cast<double2*>(Ct + (long)row * Np + col) = make_double2(v0, v1);
+    });
+}
+
+__global__ void __launch_bounds__(GT_THREADS, 1)
+potrf_trailing_tma_kernel(const __grid_constant__ CUtensorMap tmK, double* __restrict__ K, int Np, int p, int j0, int i0) {
+    const int ti = i0 + blockIdx.y, tj = j0 + blockIdx.x;
+    if (tj > ti) return;
+    extern __shared__ unsigned char smem_raw[];
+    TOperand A = t_operand(&tmK, ti * TILE, p * TILE);
+    TOperand B = t_operand(&tmK, tj * TILE, p * TILE);
+    double acc[8][4][2];
+    gemm_nt_tma_mainloop(acc, A, B, 0, TILE, smem_raw);
+    double* Ct = K + (long)ti * TILE * Np + (long)tj * TILE;
+    gemm_foreach_pair(acc, [&](int row, int col, double v0, double v1) {
+        double2* ptr = reinterpret_cast<double2*>(Ct + (long)row * Np + col);
+        double2 c = *ptr;
+        c.x -= v0; c.y -= v1;
+        *ptr = c;
+    });
+}
+
+__global__ void __launch_bounds__(GT_THREADS, 1)
+trtri_step1_tma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmS,
+                       const __grid_constant__ CUtensorMap tmD, double* __restrict__ W, int Np, int nb, int h) {
+    const int tj = blockIdx.x, ti = blockIdx.y, q = blockIdx.z;
+    const int left = 2 * h * q, right = left + h;
+    if (right + ti >= nb) return;
+    extern __shared__ unsigned char smem_raw[];
+    TOperand A = t_operand(&tmK, (right + ti) * TILE, left * TILE);
+    TOperand B = t_operand_alt(&tmS, (left + tj) * TILE, left * TILE, &tmD, (left + tj) * TILE, tj * TILE, (tj + 1) * TILE);
+    double acc[8][4][2];
+    gemm_nt_tma_mainloop(acc, A, B, tj * TILE, h * TILE, smem_raw);
+    double* Wt = W + ((long)(left + tj) * TILE) * Np + (long)(right + ti) * TILE;   // W[j][i]
+    gemm_foreach_pair(acc, [&](int row, int col, double v0, double v1) {
+        Wt[(long)col * Np + row] = v0;
+        Wt[(long)(col + 1) * Np + row] = v1;
+    });
+}
+
+__global__ void __launch_bounds__(GT_THREADS, 1)
+trtri_step2_tma_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmW,
+                       double* __restrict__ S, int Np, int nb, int h) {
+    const int tj = blockIdx.x, ti = blockIdx.y, q = blockIdx.z;
+    const int left = 2 * h * q, right = left + h;
+    if (right + ti >= nb) return;
+    extern __shared__ unsigned char smem_raw[];
+    TOperand A = t_operand(&tmS, (right + ti) * TILE, right * TILE);
+    TOperand B = t_operand(&tmW, (left + tj) * TILE, right * TILE);
+    double acc[8][4][2];
+    gemm_nt_tma_mainloop(acc, A, B, 0, (ti + 1) * TILE, smem_raw);
+    double* Xt = S + ((long)(right + ti) * TILE) * Np + (long)(left + tj) * TILE;
+    double* Xm = S + ((long)(left + tj) * TILE) * Np + (long)(right + ti) * TILE;
+    gemm_foreach_pair(acc, [&](int row, int col, double v0, double v1) {
+        *reinterpret_cast<double2*>(Xt + (long)row * Np + col) = make_double2(-v0, -v1);
+        Xm[(long)col * Np + row] = -v0;
+        Xm[(long)(col + 1) * Np + row] = -v1;
+    });
+}
+
+__global__ void __launch_bounds__(GT_THREADS, 1)
+lauum_tma_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmD,
+                 double* __restrict__ Kinv, int Np) {
+    // heaviest (longest k range = smallest ti) tiles first
+    const int tj = blockIdx.x, ti = blockIdx.y;
+    if (tj > ti) return;
+    extern __shared__ unsigned char smem_raw[];
+    TOperand A = t_operand_alt(&tmS, ti * TILE, 0, &tmD, ti * TILE, ti * TILE, (ti + 1) * TILE);
+    TOperand B = (tj == ti) ? A : t_operand(&tmS, tj * TILE, 0);
+    double acc[8][4][2];
+    gemm_nt_tma_mainloop(acc, A, B, ti * TILE, Np, smem_raw);
+    double* Ct = Kinv + ((long)ti * TILE) * Np + (long)tj * TILE;
+    double* Cm = Kinv + ((long)tj * TILE) * Np + (long)ti * TILE;
+    const bool diag = (ti == tj);
+    gemm_foreach_pair(acc, [&](int row, int col, double v0, double v1) {
+        *reinterpret_cast<double2*>(Ct + (long)row * Np + col) = make_double2(v0, v1);
+        if (!diag) {
+            Cm[(long)col * Np + row] = v0;
+            Cm[(long)(col + 1) * Np + row] = v1;
+        }
+    });
+}
+
+// ------------------------------------------------------------------------------------------------
 // Triangular mat-vecs on S (one warp per row, 8 rows per CTA):
 //   mode 0:  u[i]     = sum_{k <= i} Linv[i][k] r[k]                      (rows of the lower part)
 //   mode 1:  alpha[i] = sum_{k >= i} Linv[k][i] u[k] = DT-block part + mirror part of row i
@@ -475,6 +577,11 @@ static void set_gemm_attrs() {
     cudaFuncSetAttribute(trtri_step1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES);
     cudaFuncSetAttribute(trtri_step2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES);
     cudaFuncSetAttribute(lauum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES);
+    cudaFuncSetAttribute(potrf_panel_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM_BYTES);
+    cudaFuncSetAttribute(potrf_trailing_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM_BYTES);
+    cudaFuncSetAttribute(trtri_step1_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM_BYTES);
+    cudaFuncSetAttribute(trtri_step2_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM_BYTES);
+    cudaFuncSetAttribute(lauum_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM_BYTES);
     const int dg = (TILE * DG_LD + 2 * TILE + 2) * 8;
     cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dg);
     cudaFuncSetAttribute(potrf_diag2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (TILE * DG_LD + 2 * TILE + 64) * 8);
@@ -511,6 +618,12 @@ static LookAhead* lookahead_for_current_device() {
     return la;
 }
 
+static int use_chol_tma() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("GPX_CHOL_IMPL"); v = (e && e[0] == 'c') ? 0 : 1; }
+    return v;
+}
+
 static int use_lookahead() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("GPX_POTRF_LOOKAHEAD"); v = (e && e[0] == '0') ? 0 : 1; }
@@ -528,6 +641,21 @@ int potrf(double* K, int Np, int N, double* S, double* DT, double* logdet_blk, i
     const int dg2 = (TILE * DG_LD + 2 * TILE + 64) * 8;
     LookAhead* la = use_lookahead() ? lookahead_for_current_device() : nullptr;
     cudaMemsetAsync(info, 0, sizeof(int), st);
+    const bool tma = use_chol_tma();
+    CUtensorMap tmK, tmS;
+    if (tma) {
+        int rc;
+        if ((rc = encode_f64_rowmajor(&tmK, K, Np, Np, Np, TILE))) return rc;
+        if ((rc = encode_f64_rowmajor(&tmS, S, Np, Np, Np, TILE))) return rc;
+    }
+    auto panel = [&](int n, int p) {
+        if (tma) potrf_panel_tma_kernel<<<n, GT_THREADS, GT_SMEM_BYTES, st>>>(tmK, tmS, K, Np, p);
+        else potrf_panel_kernel<<<n, G_THREADS, G_SMEM_BYTES, st>>>(K, Np, p, S);
+    };
+    auto trailing = [&](dim3 grid, int p, int j0, int i0, cudaStream_t s_) {
+        if (tma) potrf_trailing_tma_kernel<<<grid, GT_THREADS, GT_SMEM_BYTES, s_>>>(tmK, K, Np, p, j0, i0);
+        else potrf_trailing_kernel<<<grid, G_THREADS, G_SMEM_BYTES, s_>>>(K, Np, p, j0, i0);
+    };
     bool side_pending = false;
     for (int p = 0; p < nb; ++p) {
         if (use_diag_v1())
@@ -536,18 +664,18 @@ int potrf(double* K, int Np, int N, double* S, double* DT, double* logdet_blk, i
             potrf_diag2_kernel<<<1, D2_THREADS, dg2, st>>>(K, Np, p, N, S, DT, logdet_blk, info);
         const int n = nb - p - 1;
         if (n <= 0) break;
-        potrf_panel_kernel<<<n, G_THREADS, G_SMEM_BYTES, st>>>(K, Np, p, S);
+        panel(n, p);
         if (la == nullptr) {
-            potrf_trailing_kernel<<<dim3(n, n), G_THREADS, G_SMEM_BYTES, st>>>(K, Np, p, p + 1, p + 1);
+            trailing(dim3(n, n), p, p + 1, p + 1, st);
             continue;
         }
         // block column p+1 was also touched by the helper stream's update p-1: wait for it first
         if (side_pending) cudaStreamWaitEvent(st, la->ev_side[(p - 1) & 1], 0);
-        potrf_trailing_kernel<<<dim3(1, n), G_THREADS, G_SMEM_BYTES, st>>>(K, Np, p, p + 1, p + 1);
+        trailing(dim3(1, n), p, p + 1, p + 1, st);
         if (n > 1) {
             cudaEventRecord(la->ev_main[p & 1], st);
             cudaStreamWaitEvent(la->side, la->ev_main[p & 1], 0);
-            potrf_trailing_kernel<<<dim3(n - 1, n - 1), G_THREADS, G_SMEM_BYTES, la->side>>>(K, Np, p, p + 2, p + 2);
+            trailing(dim3(n - 1, n - 1), p, p + 2, p + 2, la->side);
             cudaEventRecord(la->ev_side[p & 1], la->side);
             side_pending = true;
         } else {
@@ -563,11 +691,25 @@ int potrf(double* K, int Np, int N, double* S, double* DT, double* logdet_blk, i
 int trtri(const double* L, double* S, const double* DT, double* W, int Np, cudaStream_t st) {
     set_gemm_attrs();
     const int nb = Np / TILE;
+    const bool tma = use_chol_tma();
+    CUtensorMap tmK, tmS, tmW, tmD;
+    if (tma) {
+        int rc;
+        if ((rc = encode_f64_rowmajor(&tmK, L, Np, Np, Np, TILE))) return rc;
+        if ((rc = encode_f64_rowmajor(&tmS, S, Np, Np, Np, TILE))) return rc;
+        if ((rc = encode_f64_rowmajor(&tmW, W, Np, Np, Np, TILE))) return rc;
+        if ((rc = encode_f64_rowmajor(&tmD, DT, (uint64_t)nb * TILE, TILE, TILE, TILE))) return rc;
+    }
     for (int h = 1; h < nb; h *= 2) {
         const int pairs = (nb + 2 * h - 1) / (2 * h);
         dim3 grid(h, h, pairs);
-        trtri_step1_kernel<<<grid, G_THREADS, G_SMEM_BYTES, st>>>(L, S, DT, W, Np, nb, h);
-        trtri_step2_kernel<<<grid, G_THREADS, G_SMEM_BYTES, st>>>(S, W, Np, nb, h);
+        if (tma) {
+            trtri_step1_tma_kernel<<<grid, GT_THREADS, GT_SMEM_BYTES, st>>>(tmK, tmS, tmD, W, Np, nb, h);
+            trtri_step2_tma_kernel<<<grid, GT_THREADS, GT_SMEM_BYTES, st>>>(tmS, tmW, S, Np, nb, h);
+        } else {
+            trtri_step1_kernel<<<grid, G_THREADS, G_SMEM_BYTES, st>>>(L, S, DT, W, Np, nb, h);
+            trtri_step2_kernel<<<grid, G_THREADS, G_SMEM_BYTES, st>>>(S, W, Np, nb, h);
+        }
     }
     GPX_CHECK_LAUNCH();
     return 0;
@@ -576,7 +718,15 @@ int trtri(const double* L, double* S, const double* DT, double* W, int Np, cudaS
 int lauum(const double* S, const double* DT, double* Kinv, int Np, cudaStream_t st) {
     set_gemm_attrs();
     const int nb = Np / TILE;
-    lauum_kernel<<<dim3(nb, nb), G_THREADS, G_SMEM_BYTES, st>>>(S, DT, Kinv, Np);
+    if (use_chol_tma()) {
+        CUtensorMap tmS, tmD;
+        int rc;
+        if ((rc = encode_f64_rowmajor(&tmS, S, Np, Np, Np, TILE))) return rc;
+        if ((rc = encode_f64_rowmajor(&tmD, DT, (uint64_t)nb * TILE, TILE, TILE, TILE))) return rc;
+        lauum_tma_kernel<<<dim3(nb, nb), GT_THREADS, GT_SMEM_BYTES, st>>>(tmS, tmD, Kinv, Np);
+    } else {
+        lauum_kernel<<<dim3(nb, nb), G_THREADS, G_SMEM_BYTES, st>>>(S, DT, Kinv, Np);
+    }
     GPX_CHECK_LAUNCH();
     return 0;
 }
