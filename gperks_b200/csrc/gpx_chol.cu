@@ -138,55 +138,66 @@ potrf_diag2_kernel(double* __restrict__ K, int Np, int blk, int N, double* __res
     const long off = (long)blk * TILE;
     double* Ab = K + off * Np + off;
     if (tid == 0) bad_pivot = 0;
-    for (int e = tid; e < TILE * TILE; e += D2_THREADS) {
-        int r = e >> 7, c = e & 127;
-        double v = Ab[(long)r * Np + c];
-        a[r * DG_LD + c] = (c <= r) ? v : 0.0;     // B starts as the identity: zero strict upper part
+    // 8192 double2 loads, 8 in flight per thread (one CTA has to pull 128 KB on its own)
+#pragma unroll 1
+    for (int e0 = tid; e0 < TILE * TILE / 2; e0 += 8 * D2_THREADS) {
+        double2 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int e = e0 + u * D2_THREADS, r = e >> 6, c = (e & 63) * 2;
+            v[u] = *reinterpret_cast<const double2*>(Ab + (long)r * Np + c);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int e = e0 + u * D2_THREADS, r = e >> 6, c = (e & 63) * 2;
+            // B starts as the identity: zero strict upper part
+            *reinterpret_cast<double2*>(a + r * DG_LD + c) = make_double2(c <= r ? v[u].x : 0.0, c + 1 <= r ? v[u].y : 0.0);
+        }
     }
     __syncthreads();
     for (int p = 0; p < TILE / 8; ++p) {
         const int c0 = 8 * p;
-        // ---- (1) 8x8 diagonal block: Cholesky + inverse in the registers of one thread
-        if (tid == 0) {
-            double d[8][8], t[8][8], ri[8];
-#pragma unroll
-            for (int r = 0; r < 8; ++r)
-#pragma unroll
-                for (int c = 0; c < 8; ++c) d[r][c] = (c <= r) ? a[(c0 + r) * DG_LD + c0 + c] : 0.0;
+        // ---- (1) 8x8 diagonal block on warp 0: lane (r = lane/4, q = lane%4) owns D[r][2q], D[r][2q+1]; one
+        //      pivot broadcast + rsqrt + three shuffles per column, then lanes 0..7 invert one column each
+        if (warp == 0) {
+            const unsigned full = 0xffffffffu;
+            double d0 = a[(c0 + lr) * DG_LD + c0 + 2 * lc];
+            double d1 = a[(c0 + lr) * DG_LD + c0 + 2 * lc + 1];
+            double inv_r = 0.0, sd_r = 0.0;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const double piv = d[j][j];
-                if (!(piv > 0.0) && bad_pivot == 0) bad_pivot = c0 + j + 1;
+                const int jq = j >> 1, je = j & 1;
+                const double sel = je ? d1 : d0;                        // this lane's entry of column j (if it has one)
+                const double piv = __shfl_sync(full, sel, j * 4 + jq);
+                if (!(piv > 0.0) && lane == 0 && bad_pivot == 0) bad_pivot = c0 + j + 1;
                 const double inv = rsqrt(piv);
-                ri[j] = inv;
-                d[j][j] = piv * inv;
-#pragma unroll
-                for (int r = j + 1; r < 8; ++r) d[r][j] *= inv;
-#pragma unroll
-                for (int c = j + 1; c < 8; ++c)
-#pragma unroll
-                    for (int r = c; r < 8; ++r) d[r][c] = fma(-d[r][j], d[c][j], d[r][c]);
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                t[j][j] = ri[j];
-#pragma unroll
-                for (int i = j + 1; i < 8; ++i) {
-                    double s = 0.0;
-#pragma unroll
-                    for (int k = j; k < i; ++k) s = fma(d[i][k], t[k][j], s);
-                    t[i][j] = -s * ri[i];
+                const double sd = piv * inv;
+                const double lrj = __shfl_sync(full, sel, lr * 4 + jq) * inv;              // L[r][j], r > j
+                const double lc0 = __shfl_sync(full, sel, (2 * lc) * 4 + jq) * inv;        // L[2q][j]
+                const double lc1 = __shfl_sync(full, sel, (2 * lc + 1) * 4 + jq) * inv;    // L[2q+1][j]
+                if (lc == jq && lr >= j) {
+                    const double v = (lr == j) ? sd : lrj;
+                    if (je) d1 = v; else d0 = v;
                 }
+                if (2 * lc > j && lr >= 2 * lc) d0 = fma(-lrj, lc0, d0);
+                if (2 * lc + 1 > j && lr >= 2 * lc + 1) d1 = fma(-lrj, lc1, d1);
+                if (lr == j) { inv_r = inv; sd_r = sd; }
             }
+            if (2 * lc <= lr) a[(c0 + lr) * DG_LD + c0 + 2 * lc] = d0;
+            if (2 * lc + 1 <= lr) a[(c0 + lr) * DG_LD + c0 + 2 * lc + 1] = d1;
+            if (lc == 0) { rinv[c0 + lr] = inv_r; dg[c0 + lr] = sd_r; }
+            __syncwarp();
+            if (lane < 8) {        // column `lane` of T = L_pp^-1 by forward substitution (entries above the diagonal come out 0)
+                double x[8];
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                rinv[c0 + r] = ri[r];
-                dg[c0 + r] = d[r][r];
+                for (int i = 0; i < 8; ++i) {
+                    double acc_ = (i == lane) ? 1.0 : 0.0;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    if (c <= r) a[(c0 + r) * DG_LD + c0 + c] = d[r][c];
-                    Tb[r * 8 + c] = (c <= r) ? t[r][c] : 0.0;
+                    for (int k = 0; k < i; ++k) acc_ = fma(-a[(c0 + i) * DG_LD + c0 + k], x[k], acc_);
+                    x[i] = acc_ * rinv[c0 + i];
                 }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) Tb[i * 8 + lane] = x[i];
             }
         }
         __syncthreads();
@@ -233,9 +244,8 @@ potrf_diag2_kernel(double* __restrict__ K, int Np, int blk, int N, double* __res
         const int nrem = TILE / 8 - 1 - p;
         const int n_mat = nrem * (nrem + 1) / 2;
         const int total = n_mat + nrem * (p + 1);
-        for (int t = warp; t < total; t += D2_THREADS / 32) {
-            int bi, bj;
-            const bool rhs = t >= n_mat;
+        auto decode = [&](int t, int& bi, int& bj, bool& rhs) {
+            rhs = t >= n_mat;
             if (!rhs) {
                 int q = (int)((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
                 while (q * (q + 1) / 2 > t) --q;
@@ -247,10 +257,9 @@ potrf_diag2_kernel(double* __restrict__ K, int Np, int blk, int N, double* __res
                 bi = p + 1 + u / (p + 1);
                 bj = u % (p + 1);
             }
-            const double* ar = a + (8 * bi + lr) * DG_LD + c0 + lc;
-            double b0, b1;
-            if (rhs && bj == p) {
-                // X_pp = T: its storage overlaps L_pp (diagonal + lower part), so read the dense copy
+        };
+        auto load_b = [&](int bj, bool rhs, double& b0, double& b1) {
+            if (rhs && bj == p) {   // X_pp = T: its storage overlaps L_pp (diagonal + lower part): read the dense copy
                 b0 = Tb[lc * 8 + lr];
                 b1 = Tb[(lc + 4) * 8 + lr];
             } else {
@@ -258,9 +267,8 @@ potrf_diag2_kernel(double* __restrict__ K, int Np, int blk, int N, double* __res
                 b0 = br[0];
                 b1 = br[4];
             }
-            double c0v = 0.0, c1v = 0.0;
-            dmma884(c0v, c1v, ar[0], b0);
-            dmma884(c0v, c1v, ar[4], b1);
+        };
+        auto store_c = [&](int bi, int bj, bool rhs, double c0v, double c1v) {
             if (!rhs) {
                 double2* ptr = reinterpret_cast<double2*>(a + (8 * bi + lr) * DG_LD + 8 * bj + 2 * lc);
                 double2 v = *ptr;
@@ -270,6 +278,31 @@ potrf_diag2_kernel(double* __restrict__ K, int Np, int blk, int N, double* __res
                 a[(8 * bj + 2 * lc) * DG_LD + 8 * bi + lr] -= c0v;
                 a[(8 * bj + 2 * lc + 1) * DG_LD + 8 * bi + lr] -= c1v;
             }
+        };
+        constexpr int NW = D2_THREADS / 32;
+        for (int t = warp; t < total; t += 2 * NW) {      // two independent blocks per iteration (latency overlap)
+            const int t2 = t + NW;
+            const bool two = t2 < total;
+            int bi, bj, bi2 = 0, bj2 = 0;
+            bool rhs, rhs2 = false;
+            decode(t, bi, bj, rhs);
+            if (two) decode(t2, bi2, bj2, rhs2);
+            const double* ar = a + (8 * bi + lr) * DG_LD + c0 + lc;
+            const double a0 = ar[0], a1 = ar[4];
+            double b0, b1, a20 = 0.0, a21 = 0.0, b20 = 0.0, b21 = 0.0;
+            load_b(bj, rhs, b0, b1);
+            if (two) {
+                const double* ar2 = a + (8 * bi2 + lr) * DG_LD + c0 + lc;
+                a20 = ar2[0]; a21 = ar2[4];
+                load_b(bj2, rhs2, b20, b21);
+            }
+            double c0v = 0.0, c1v = 0.0, d0v = 0.0, d1v = 0.0;
+            dmma884(c0v, c1v, a0, b0);
+            dmma884(d0v, d1v, a20, b20);
+            dmma884(c0v, c1v, a1, b1);
+            dmma884(d0v, d1v, a21, b21);
+            store_c(bi, bj, rhs, c0v, c1v);
+            if (two) store_c(bi2, bj2, rhs2, d0v, d1v);
         }
         __syncthreads();
     }
@@ -277,17 +310,24 @@ potrf_diag2_kernel(double* __restrict__ K, int Np, int blk, int N, double* __res
     // ---- write back: L (lower, zero above), D = L^-1 into S (zero above), D^T into DT
     double* Sb = S + off * Np + off;
     double* DTb = DT + (long)blk * TILE * TILE;
-    for (int e = tid; e < TILE * TILE; e += D2_THREADS) {
-        int i = e >> 7, c = e & 127;
-        double l = (c <= i) ? a[i * DG_LD + c] : 0.0;
-        double x = (c < i) ? a[c * DG_LD + i] : ((c == i) ? rinv[i] : 0.0);
-        Ab[(long)i * Np + c] = l;
-        Sb[(long)i * Np + c] = x;
+    auto xval = [&](int i, int c) -> double {        // X[i][c] = (L^-1)[i][c]
+        return (c < i) ? a[c * DG_LD + i] : ((c == i) ? rinv[i] : 0.0);
+    };
+#pragma unroll 4
+    for (int e = tid; e < TILE * TILE / 2; e += D2_THREADS) {
+        const int i = e >> 6, c = (e & 63) * 2;
+        const double2 lv = *reinterpret_cast<const double2*>(a + i * DG_LD + c);
+        *reinterpret_cast<double2*>(Ab + (long)i * Np + c) = make_double2(c <= i ? lv.x : 0.0, c + 1 <= i ? lv.y : 0.0);
+        *reinterpret_cast<double2*>(Sb + (long)i * Np + c) = make_double2(xval(i, c), xval(i, c + 1));
     }
-    for (int e = tid; e < TILE * TILE; e += D2_THREADS) {
-        int c = e >> 7, i = e & 127;   // DT[c][i] = D[i][c]
-        double x = (c < i) ? a[c * DG_LD + i] : ((c == i) ? rinv[i] : 0.0);
-        DTb[c * TILE + i] = x;
+#pragma unroll 4
+    for (int e = tid; e < TILE * TILE / 2; e += D2_THREADS) {
+        const int c = e >> 6, i = (e & 63) * 2;      // DT[c][i] = X[i][c]: contiguous in the transposed storage
+        double2 xv = make_double2(0.0, 0.0);
+        if (i > c) xv = *reinterpret_cast<const double2*>(a + c * DG_LD + i);
+        else if (i == c) xv = make_double2(rinv[c], a[c * DG_LD + c + 1]);
+        else if (i + 1 == c) xv = make_double2(0.0, rinv[c]);
+        *reinterpret_cast<double2*>(DTb + c * TILE + i) = xv;
     }
     if (tid < 32) {
         double t = 0.0;
