@@ -97,8 +97,12 @@ __global__ void __launch_bounds__(P_THREADS) kmat_sym_kernel(const double* __res
 // Cross kernel for one chunk of test points.  grid = (Np/128 j-tiles, Mc/128 m-tiles).
 //   Ks[m][j]  (ld = Np)            m in [0, Mc), chunk-local
 //   mean_part[jb][m]  (ld = Mc)    partial  sum_{j in tile jb} Ks[m][j] * alpha[j]
+// The 8 x 8 micro-tile is walked one row (8 entries) at a time in a ROLLED loop: fully unrolling the 64
+// double-precision sqrt/exp evaluations produced ~80 KB of code and the kernel stalled on instruction fetch
+// (ncu: "no_instruction" was the top stall, FP64 pipe 18 % busy); one row keeps the body inside the I-cache and
+// the register count low enough for several resident CTAs.
 template <int KIND>
-__global__ void __launch_bounds__(P_THREADS)
+__global__ void __launch_bounds__(P_THREADS, 2)
 kmat_cross_kernel(const double* __restrict__ Xs, long m_valid, const double* __restrict__ X, int N, int D,
                   const double* __restrict__ theta, const double* __restrict__ xa, const double* __restrict__ xr,
                   const double* __restrict__ alpha, double* __restrict__ Ks, int Np, double* __restrict__ mean_part,
@@ -114,20 +118,30 @@ kmat_cross_kernel(const double* __restrict__ Xs, long m_valid, const double* __r
     if (threadIdx.x < TILE) sal[threadIdx.x] = alpha[jb * TILE + threadIdx.x];   // alpha is zero-padded to Np
     __syncthreads();
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    double r2[8][8];
-    tile_r2(r2, sa, sb, D, ty, tx);
     const double s = theta[D];
     double al[8];
 #pragma unroll
     for (int b = 0; b < 8; ++b) al[b] = sal[tx + 16 * b];
-#pragma unroll
+#pragma unroll 1
     for (int a = 0; a < 8; ++a) {
-        const long m = (long)mb * TILE + ty + 16 * a;
+        const int row = ty + 16 * a;
+        double r2[8];
+#pragma unroll
+        for (int b = 0; b < 8; ++b) r2[b] = 0.0;
+        for (int d = 0; d < D; ++d) {
+            const double xa_ = sa[d * P_LD + row];
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                const double df = xa_ - sb[d * P_LD + tx + 16 * b];
+                r2[b] = fma(df, df, r2[b]);
+            }
+        }
+        const long m = (long)mb * TILE + row;
         double part = 0.0;
 #pragma unroll
         for (int b = 0; b < 8; ++b) {
             const long j = (long)jb * TILE + tx + 16 * b;
-            double v = (j < N) ? kernel_value<KIND>(r2[a][b], s) : 0.0;
+            double v = (j < N) ? kernel_value<KIND>(r2[b], s) : 0.0;
             if (Khi != nullptr) {       // TF32 mode: 3xTF32 operand split (hi = tf32(x), lo = tf32(x - hi))
                 uint32_t h, l;
                 float fh, fl;
@@ -147,7 +161,7 @@ kmat_cross_kernel(const double* __restrict__ Xs, long m_valid, const double* __r
         part += __shfl_xor_sync(0xffffffffu, part, 2);
         part += __shfl_xor_sync(0xffffffffu, part, 4);
         part += __shfl_xor_sync(0xffffffffu, part, 8);
-        if (tx == 0) smean[ty + 16 * a] = part;
+        if (tx == 0) smean[row] = part;
     }
     __syncthreads();
     if (threadIdx.x < TILE) mean_part[(long)jb * Mc + (long)mb * TILE + threadIdx.x] = smean[threadIdx.x];
