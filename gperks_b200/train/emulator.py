@@ -48,6 +48,7 @@ from .trainable import Trainable
 
 log = get_logger()
 F64 = torch.float64
+PREDICT_STAGE_POINTS = 262144      # points per pinned staging slot of GPEmulator.predict
 
 
 def _default_snapshotting() -> SnapshottingCriterion:
@@ -75,6 +76,11 @@ class GPEmulator(Trainable):
         self.criterion = None
         self.best_train_metrics_score: Dict[str, float] = {}
         self.best_val_metrics_score: Dict[str, float] = {}
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state.pop("_stage", None)          # pinned buffers / streams / events do not pickle
+        return state
 
     # ------------------------------------------------------------------------------------------
     # training
@@ -269,6 +275,24 @@ class GPEmulator(Trainable):
     # ------------------------------------------------------------------------------------------
     # prediction
     # ------------------------------------------------------------------------------------------
+    def _staging(self, cdev, blk: int, D: int):
+        """Two pinned host slots + two device slots for ``predict`` (allocated once, grown on demand): pinned
+        allocation costs ~10 ms per 32 MB, far too much to pay per call."""
+        st = getattr(self, "_stage", None)
+        if st is None or st["device"] != cdev or st["blk"] < blk or st["D"] != D:
+            st = {
+                "device": cdev, "blk": blk, "D": D, "stream": torch.cuda.Stream(device=cdev),
+                "xin": [torch.empty(blk * D, dtype=F64).pin_memory() for _ in range(2)],
+                "out": [torch.empty(2, blk, dtype=F64).pin_memory() for _ in range(2)],
+                "xdev": [torch.empty(blk * D, dtype=F64, device=cdev) for _ in range(2)],
+                "odev": [torch.empty(2, blk, dtype=F64, device=cdev) for _ in range(2)],
+                "ev_h2d": [torch.cuda.Event() for _ in range(2)],
+                "ev_done": [torch.cuda.Event() for _ in range(2)],
+                "ev_d2h": [torch.cuda.Event() for _ in range(2)],
+            }
+            self._stage = st
+        return st
+
     def _as_2d(self, X_new) -> numpy.ndarray:
         X_new = numpy.asarray(X_new, dtype=numpy.float64)
         if X_new.ndim == 1:
@@ -291,7 +315,8 @@ class GPEmulator(Trainable):
             return PolyMeanSpec(feat[:0].to(dev), degree, torch.zeros(0, dtype=F64, device=dev), b)
         return PolyMeanSpec(feat.to(dev).contiguous(), degree, w, b)
 
-    def predict_device(self, x_dev: torch.Tensor, precision: str = "fp64", tf32_kchunk: int = 128):
+    def predict_device(self, x_dev: torch.Tensor, precision: str = "fp64", tf32_kchunk: int = 128,
+                       out_mean: Optional[torch.Tensor] = None, out_std: Optional[torch.Tensor] = None):
         """Device-resident predict: raw (unscaled) inputs ``x_dev`` [M, D] already in HBM -> (mean, std) device
         tensors, un-standardised when the output scaler is the (linear) StandardScaler.  This is the call the
         GPU-side consumers (history matching, GSA, the benchmark's device arm) use; ``predict`` wraps it with
@@ -313,7 +338,7 @@ class GPEmulator(Trainable):
                 x_dev, xa=xa, xr=xr, prior_mean=prior, poly=poly,
                 y_mu=float(scy.mu) if linear_out else 0.0, y_sigma=float(scy.sigma) if linear_out else 1.0,
                 chunk=eng.pick_chunk(M, DEFAULT_PREDICT_CHUNK_BYTES) if M > 0 else None,
-                precision=precision, tf32_kchunk=tf32_kchunk)
+                precision=precision, tf32_kchunk=tf32_kchunk, out_mean=out_mean, out_std=out_std)
         return mean_d, std_d, linear_out
 
     def predict(self, X_new, with_covar: bool = False, precision: str = "fp64", tf32_kchunk: int = 128):
@@ -333,28 +358,57 @@ class GPEmulator(Trainable):
         cdev = self._compute_device()
         scx, scy = self.scaled_data.scx, self.scaled_data.scy
         M = X_new.shape[0]
+        D = self.scaled_data.input_size
+        y_mean = numpy.empty(M, dtype=numpy.float64)
+        y_std = numpy.empty(M, dtype=numpy.float64)
         with torch.no_grad(), torch.cuda.device(cdev):
-            if M > 0:
-                x_dev = torch.from_numpy(X_new).pin_memory().to(cdev, non_blocking=True)
-            else:
-                x_dev = torch.empty(0, self.scaled_data.input_size, dtype=F64, device=cdev)
-            mean_d, std_d, linear_out = self.predict_device(x_dev, precision=precision, tf32_kchunk=tf32_kchunk)
-            out = torch.empty(2, M, dtype=F64).pin_memory() if M > 0 else torch.empty(2, 0, dtype=F64)
-            out[0].copy_(mean_d, non_blocking=True)
-            out[1].copy_(std_d, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            y_mean, y_std = out[0].numpy().copy(), out[1].numpy().copy()
+            # Blocks of points stream through two pinned staging slots: the H2D copy of block b+1 and the D2H copy
+            # of block b-1 run on a copy stream while block b is being computed.
+            blk = max(1, min(M, PREDICT_STAGE_POINTS))
+            st = self._staging(cdev, blk, D)
+            comp = torch.cuda.current_stream()
+            copy = st["stream"]
+            linear_out = True
+            pending = {}
+
+            def flush(slot):
+                lo_, hi_ = pending.pop(slot)
+                st["ev_d2h"][slot].synchronize()
+                m_ = hi_ - lo_
+                y_mean[lo_:hi_] = st["out"][slot][0, :m_].numpy()
+                y_std[lo_:hi_] = st["out"][slot][1, :m_].numpy()
+
+            for b, lo in enumerate(range(0, M, blk)):
+                i = b % 2
+                hi = min(M, lo + blk)
+                m = hi - lo
+                if i in pending:
+                    flush(i)
+                st["xin"][i][: m * D].copy_(torch.from_numpy(X_new[lo:hi]).reshape(-1))
+                with torch.cuda.stream(copy):
+                    st["xdev"][i][: m * D].copy_(st["xin"][i][: m * D], non_blocking=True)
+                    st["ev_h2d"][i].record(copy)
+                comp.wait_event(st["ev_h2d"][i])
+                _, _, linear_out = self.predict_device(st["xdev"][i][: m * D].view(m, D), precision=precision,
+                                                       tf32_kchunk=tf32_kchunk, out_mean=st["odev"][i][0, :m],
+                                                       out_std=st["odev"][i][1, :m])
+                st["ev_done"][i].record(comp)
+                with torch.cuda.stream(copy):
+                    copy.wait_event(st["ev_done"][i])
+                    st["out"][i][:, :m].copy_(st["odev"][i][:, :m], non_blocking=True)
+                    st["ev_d2h"][i].record(copy)
+                pending[i] = (lo, hi)
+            for slot in sorted(pending, key=lambda k: pending[k][0]):
+                flush(slot)
             if not linear_out:
                 y_mean, y_std = scy.inverse_transform(y_mean, ystd_=y_std)
             if not with_covar:
                 return y_mean, y_std
-            xa = torch.as_tensor(numpy.asarray(scx.a, dtype=numpy.float64).reshape(-1), device=cdev)
-            xr = torch.as_tensor((numpy.asarray(scx.b, dtype=numpy.float64)
-                                  - numpy.asarray(scx.a, dtype=numpy.float64)).reshape(-1), device=cdev)
+            x_scaled = torch.from_numpy(scx.transform(X_new)).to(cdev, F64)
             import warnings
             with warnings.catch_warnings():
                 warnings.simplefilter("ignore")
-                covar = self.model.likelihood(self.model((x_dev - xa) / xr)).covariance_matrix.cpu().numpy()
+                covar = self.model.likelihood(self.model(x_scaled)).covariance_matrix.cpu().numpy()
         # un-standardise the covariance the way the reference does (sign * (sigma_y * sqrt|C|)^2)
         sign = numpy.sign(covar)
         _, as_std = scy.inverse_transform(y_mean, ystd_=numpy.sqrt(numpy.abs(covar.reshape(-1))))
