@@ -360,7 +360,7 @@ def main():
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             nv.check(lib.gpx_trmm_sumsq_tf32(nv.ptr(eng.S_hi), nv.ptr(eng.S_lo), eng.Np, Khi.data_ptr(), Klo.data_ptr(), Mc,
-                                             nv.ptr(qp), 128, st), "tf32 trmm")
+                                             nv.ptr(qp), 32, st), "tf32 trmm")
             b.record()
             torch.cuda.synchronize()
             if i > 0:
@@ -381,7 +381,7 @@ def main():
         torch.backends.cuda.matmul.allow_tf32 = False
         tf32_peak = 2 * 8192 ** 3 / (min(tg) / 1e3) / 1e12
         raw = 3.0 * float(eng.N) ** 2 * Mc / (tk / 1e3) / 1e12
-        tf32 = {"tf32x3": exact, "tf32x3_fast": fast, "tolerance": 1e-3, "kchunk": 128,
+        tf32 = {"tf32x3": exact, "tf32x3_fast": fast, "tolerance": 1e-3, "kchunk": 32,
                 "note": "tf32x3: K* evaluated in FP64 (mean bit-identical to fp64); tf32x3_fast: K* evaluated in FP32",
                 "roofline": {"kernel": "trmm_sumsq_tf32_kernel (tcgen05.mma kind::tf32, 3 MMAs per product, TMEM accumulators)",
                              "bound": "tensor", "achieved": raw, "peak": tf32_peak, "unit": "TFLOP/s (TF32, raw = 3 x useful)",

@@ -164,7 +164,7 @@ int gpx_tf32_row_tiles(int Np) { return tf32_row_tiles(Np); }
 int gpx_trmm_sumsq_tf32(const float* Shi, const float* Slo, int Np, const float* Khi, const float* Klo, int Mc,
                         double* qpart, int kchunk, void* stream) {
     if (!Shi || !Slo || !Khi || !Klo || !qpart) return -1;
-    if (Np % TILE || Mc % TILE || Np <= 0 || Mc <= 0) return -3;
+    if (Np % TILE || Mc % (2 * TILE) || Np <= 0 || Mc <= 0) return -3;
     if (kchunk > 0 && kchunk % 32) return -8;
     return trmm_sumsq_tf32(Shi, Slo, Np, Khi, Klo, Mc, qpart, kchunk, ST(stream));
 }

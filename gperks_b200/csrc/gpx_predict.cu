@@ -337,7 +337,7 @@ int predict_meanvar_tf32(const double* Xs, long M, const double* X, int N, int D
                          const double* bias, double y_mu, double y_sigma, double min_var, double* out_mean,
                          double* out_std, void* workspace, size_t workspace_bytes, int Mc, int kchunk,
                          cudaStream_t st) {
-    if (Mc <= 0 || Mc % TILE != 0) return -25;
+    if (Mc <= 0 || Mc % (2 * TILE) != 0) return -25;      // CTA pairs of the tcgen05 kernel cover 256 points
     if (Np % TILE != 0 || Np < N) return -11;
     if (D > MAXD || D < 1) return -5;
     if (workspace_bytes < predict_tf32_workspace_bytes(Np, Mc)) return -23;
@@ -352,7 +352,7 @@ int predict_meanvar_tf32(const double* Xs, long M, const double* X, int N, int D
     double* qpart = mean_part + (size_t)nb * Mc;
     for (long m0 = 0; m0 < M; m0 += Mc) {
         const long mv = (M - m0 < Mc) ? (M - m0) : Mc;
-        const int mc = round_up((int)mv, TILE);
+        const int mc = round_up((int)mv, 2 * TILE);
         const double* xs = Xs + m0 * D;
         int rc = kmat_cross_split(xs, mv, X, N, D, theta, xa, xr, kind, alpha, Khi, Klo, Np, mean_part, mc, fp32_eval, st);
         if (rc) return rc;

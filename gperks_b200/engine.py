@@ -180,7 +180,7 @@ class ExactGPEngine:
     def predict(self, Xs: torch.Tensor, *, xa: Optional[torch.Tensor] = None, xr: Optional[torch.Tensor] = None,
                 prior_mean: Optional[torch.Tensor] = None, poly: Optional[PolyMeanSpec] = None,
                 y_mu: float = 0.0, y_sigma: float = 1.0, min_var: float = 1e-10, noisy: bool = True,
-                precision: str = "fp64", tf32_kchunk: int = 128,
+                precision: str = "fp64", tf32_kchunk: int = 32,
                 out_mean: Optional[torch.Tensor] = None, out_std: Optional[torch.Tensor] = None,
                 chunk: Optional[int] = None):
         """Posterior mean and noisy std for device-resident points Xs [M, D] using the cached factors.
@@ -207,11 +207,12 @@ class ExactGPEngine:
         # tf32x3: K* evaluated in FP64 then split (posterior mean bit-identical to fp64; variance on tcgen05);
         # tf32x3_fast: K* evaluated in FP32 as well (mean moves by ~1e-4 of its scale for noise-like targets)
         tf32 = precision != "fp64"
-        kchunk = abs(int(tf32_kchunk)) or 128
+        kchunk = abs(int(tf32_kchunk)) or 32
         if precision == "tf32x3":
             kchunk = -kchunk
         if tf32:
             self._ensure_split()
+            Mc = (Mc + 255) // 256 * 256         # the tcgen05 kernel works on pairs of 128-point tiles
             ws_bytes = int(self.lib.gpx_predict_tf32_workspace_bytes(self.Np, Mc))
         else:
             ws_bytes = int(self.lib.gpx_predict_workspace_bytes(self.Np, Mc))

@@ -315,7 +315,7 @@ class GPEmulator(Trainable):
             return PolyMeanSpec(feat[:0].to(dev), degree, torch.zeros(0, dtype=F64, device=dev), b)
         return PolyMeanSpec(feat.to(dev).contiguous(), degree, w, b)
 
-    def predict_device(self, x_dev: torch.Tensor, precision: str = "fp64", tf32_kchunk: int = 128,
+    def predict_device(self, x_dev: torch.Tensor, precision: str = "fp64", tf32_kchunk: int = 32,
                        out_mean: Optional[torch.Tensor] = None, out_std: Optional[torch.Tensor] = None):
         """Device-resident predict: raw (unscaled) inputs ``x_dev`` [M, D] already in HBM -> (mean, std) device
         tensors, un-standardised when the output scaler is the (linear) StandardScaler.  This is the call the
@@ -341,7 +341,7 @@ class GPEmulator(Trainable):
                 precision=precision, tf32_kchunk=tf32_kchunk, out_mean=out_mean, out_std=out_std)
         return mean_d, std_d, linear_out
 
-    def predict(self, X_new, with_covar: bool = False, precision: str = "fp64", tf32_kchunk: int = 128):
+    def predict(self, X_new, with_covar: bool = False, precision: str = "fp64", tf32_kchunk: int = 32):
         """(y_mean, y_std[, y_covar]) as numpy float64 -- GPErks/train/emulator.py:348-383.
 
         ``precision="fp64"`` (default) is the float64 path (rel <= 1e-6 vs the float64 reference);

@@ -90,10 +90,13 @@ int gpx_predict_meanvar(const double* Xs, long M, const double* X, int N, int D,
 
  * (run once per factorisation on S = L^-1; ld = Np makes it zero the mirrored L^-T blocks above the diagonal, ld = 0
  * splits a flat array).  gpx_trmm_sumsq_tf32: qpart[it][m] = sum over the 256 rows of tile
- * `it` of (K* L^-T)[m][i]^2, it < gpx_tf32_row_tiles(Np).  gpx_predict_meanvar_tf32: as gpx_predict_meanvar with
+ * `it` of (K* L^-T)[m][i]^2, it < gpx_tf32_row_tiles(Np); Mc must be a multiple of 256 (CTA pairs share an L^-1 tile
+ * through TMA multicast).  gpx_predict_meanvar_tf32: as gpx_predict_meanvar with
  * the variance contraction on the tensor cores; kernel matrix and posterior mean remain FP64.
- * kchunk: K elements accumulated in TMEM between round-to-nearest flushes (multiple of 32, <= 0 -> 128): the tensor
- * core's FP32 accumulation truncates, so the error of std grows ~linearly with kchunk (2.6e-4 at 128, N=8192).
+ * kchunk: K elements accumulated in one TMEM accumulator before it is drained (round-to-nearest) into the running
+ * total (multiple of 32, <= 0 -> 32): the tensor core's FP32 accumulation truncates, so the error of std grows
+ * ~linearly with kchunk (7.5e-5 at 32, 2.6e-4 at 128, 5.5e-3 unchunked; N=8192).  Two accumulators ping-pong, so the
+ * drain overlaps the next chunk's MMAs and short chunks cost nothing.
  * gpx_predict_meanvar_tf32 only: kchunk >= 0 evaluates K* in FP32 (entries ~3e-7 relative); kchunk < 0 evaluates it in
  * FP64 before the split (posterior mean bit-identical to gpx_predict_meanvar) and uses |kchunk|.
  * replaces: the same call sites as gpx_predict_meanvar (GPErks/train/emulator.py:348-363). */

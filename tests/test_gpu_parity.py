@@ -374,9 +374,10 @@ def test_tf32_mode_within_tolerance(dev, N, D, M, kind):
     m32f, s32f = eng.predict(Xs.to(dev), prior_mean=pm, precision="tf32x3_fast")
     assert float((m32f - m64).abs().max()) < 1e-3 * float(m64.abs().max())
     assert float(((s32f - s64).abs() / s64).max()) < 1e-3
-    # shorter accumulation chunks are more accurate (the tensor core truncates its FP32 accumulation)
-    _, s32b = eng.predict(Xs.to(dev), prior_mean=pm, precision="tf32x3", tf32_kchunk=32)
-    assert float(((s32b - s64).abs() / s64).max()) < 3e-4
+    assert float(rel.max()) < 3e-4                                   # observed with the default 32-wide chunks
+    # longer accumulation chunks are less accurate (the tensor core truncates its FP32 accumulation) but still pass
+    _, s32b = eng.predict(Xs.to(dev), prior_mean=pm, precision="tf32x3", tf32_kchunk=256)
+    assert float(((s32b - s64).abs() / s64).max()) < 1e-3
     # refactorising refreshes the split factor
     eng.factorize(eng.theta_in.clone() * 1.0, eng.r[:N].clone() * 2.0)
     _, s32c = eng.predict(Xs.to(dev), prior_mean=pm, precision="tf32x3")
@@ -387,7 +388,7 @@ def test_tcgen05_kernel_exact_on_integers(dev):
     """Small-integer operands are exact in TF32 and in the FP32 accumulator: the tensor-core kernel must then be
     bit-exact, which pins the TMA swizzle / UMMA descriptors / TMEM epilogue layout."""
     lib = nv.lib()
-    for Np, Mc in [(256, 128), (384, 256), (1024, 128)]:
+    for Np, Mc in [(256, 256), (384, 512), (1024, 256)]:
         g = torch.Generator(device="cpu").manual_seed(Np)
         Khi = torch.randint(-3, 4, (Mc, Np), generator=g).float().to(dev)
         Shi = torch.tril(torch.randint(-2, 3, (Np, Np), generator=g).float()).to(dev)

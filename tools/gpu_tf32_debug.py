@@ -28,7 +28,7 @@ def ref(Khi, Klo, Shi, Slo):
     return torch.stack(out)
 
 torch.manual_seed(0)
-for Np, Mc in [(256, 128), (512, 256), (1024, 128)]:
+for Np, Mc in [(256, 256), (512, 512), (1024, 256)]:
     z = lambda *s: torch.zeros(*s, dtype=F32, device=dev)
     # test 1: K = ones, S = I
     K1 = torch.ones(Mc, Np, dtype=F32, device=dev); S1 = torch.eye(Np, dtype=F32, device=dev)
