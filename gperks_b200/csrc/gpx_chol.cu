@@ -137,6 +137,12 @@ potrf_diag2_kernel(double* __restrict__ K, int Np, int blk, int N, double* __res
     const int lr = lane >> 2, lc = lane & 3;
     const long off = (long)blk * TILE;
     double* Ab = K + off * Np + off;
+#ifdef GPX_DIAG_TIMING
+    long long t_mark = clock64(), t_acc[6] = {0, 0, 0, 0, 0, 0};
+#define GPX_TICK(i) do { long long n_ = clock64(); t_acc[i] += n_ - t_mark; t_mark = n_; } while (0)
+#else
+#define GPX_TICK(i)
+#endif
     if (tid == 0) bad_pivot = 0;
     // 8192 double2 loads, 8 in flight per thread (one CTA has to pull 128 KB on its own)
 #pragma unroll 1
@@ -155,6 +161,7 @@ potrf_diag2_kernel(double* __restrict__ K, int Np, int blk, int N, double* __res
         }
     }
     __syncthreads();
+    GPX_TICK(0);
     for (int p = 0; p < TILE / 8; ++p) {
         const int c0 = 8 * p;
         // ---- (1) 8x8 diagonal block on warp 0: lane (r = lane/4, q = lane%4) owns D[r][2q], D[r][2q+1]; one
@@ -201,6 +208,7 @@ potrf_diag2_kernel(double* __restrict__ K, int Np, int blk, int N, double* __res
             }
         }
         __syncthreads();
+        GPX_TICK(1);
         // ---- (2) panel rows (threads 0..127) and the inverse's block row (threads 128..255)
         if (tid < TILE) {
             const int i = tid;
@@ -240,71 +248,60 @@ potrf_diag2_kernel(double* __restrict__ K, int Np, int blk, int N, double* __res
             }
         }
         __syncthreads();
-        // ---- (3) rank-8 updates on DMMA: matrix blocks (bi >= bj > p) and right-hand-side blocks (bi > p >= bj)
-        const int nrem = TILE / 8 - 1 - p;
-        const int n_mat = nrem * (nrem + 1) / 2;
-        const int total = n_mat + nrem * (p + 1);
-        auto decode = [&](int t, int& bi, int& bj, bool& rhs) {
-            rhs = t >= n_mat;
-            if (!rhs) {
-                int q = (int)((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
-                while (q * (q + 1) / 2 > t) --q;
-                while ((q + 1) * (q + 2) / 2 <= t) ++q;
-                bi = p + 1 + q;
-                bj = p + 1 + (t - q * (q + 1) / 2);
-            } else {
-                const int u = t - n_mat;
-                bi = p + 1 + u / (p + 1);
-                bj = u % (p + 1);
-            }
-        };
-        auto load_b = [&](int bj, bool rhs, double& b0, double& b1) {
-            if (rhs && bj == p) {   // X_pp = T: its storage overlaps L_pp (diagonal + lower part): read the dense copy
-                b0 = Tb[lc * 8 + lr];
-                b1 = Tb[(lc + 4) * 8 + lr];
-            } else {
-                const double* br = a + (8 * bj + lr) * DG_LD + c0 + lc;
-                b0 = br[0];
-                b1 = br[4];
-            }
-        };
-        auto store_c = [&](int bi, int bj, bool rhs, double c0v, double c1v) {
-            if (!rhs) {
-                double2* ptr = reinterpret_cast<double2*>(a + (8 * bi + lr) * DG_LD + 8 * bj + 2 * lc);
-                double2 v = *ptr;
-                v.x -= c0v; v.y -= c1v;
-                *ptr = v;
-            } else {
-                a[(8 * bj + 2 * lc) * DG_LD + 8 * bi + lr] -= c0v;
-                a[(8 * bj + 2 * lc + 1) * DG_LD + 8 * bi + lr] -= c1v;
-            }
-        };
-        constexpr int NW = D2_THREADS / 32;
-        for (int t = warp; t < total; t += 2 * NW) {      // two independent blocks per iteration (latency overlap)
-            const int t2 = t + NW;
-            const bool two = t2 < total;
-            int bi, bj, bi2 = 0, bj2 = 0;
-            bool rhs, rhs2 = false;
-            decode(t, bi, bj, rhs);
-            if (two) decode(t2, bi2, bj2, rhs2);
+        GPX_TICK(2);
+        // ---- (3) rank-8 updates on DMMA.  Each warp owns whole block rows bi > p (A fragment loaded once) and
+        //      walks bj = 0..bi four blocks at a time: bj <= p are right-hand-side blocks (B_ij -= L_ip X_pj, stored
+        //      transposed), bj > p matrix blocks (A_ij -= L_ip L_jp^T).  No index decoding, 4-way ILP.
+        for (int bi = p + 1 + warp; bi < TILE / 8; bi += D2_THREADS / 32) {
             const double* ar = a + (8 * bi + lr) * DG_LD + c0 + lc;
-            const double a0 = ar[0], a1 = ar[4];
-            double b0, b1, a20 = 0.0, a21 = 0.0, b20 = 0.0, b21 = 0.0;
-            load_b(bj, rhs, b0, b1);
-            if (two) {
-                const double* ar2 = a + (8 * bi2 + lr) * DG_LD + c0 + lc;
-                a20 = ar2[0]; a21 = ar2[4];
-                load_b(bj2, rhs2, b20, b21);
+            const double a0 = -ar[0], a1 = -ar[4];        // C - L L^T == (-L) L^T + C: accumulate in place
+            // phase A: every B fragment and every C block of the block row.  The panel columns are not written in
+            // this step and the blocks are disjoint, so ALL loads are issued before any DMMA / store (separate
+            // load -> modify -> store sequences per block would serialise on possible shared-memory aliasing).
+            double b0[16], b1[16], cv0[16], cv1[16];
+#pragma unroll
+            for (int bj = 0; bj < 16; ++bj) {
+                b0[bj] = 0.0; b1[bj] = 0.0; cv0[bj] = 0.0; cv1[bj] = 0.0;
+                if (bj <= bi) {
+                    if (bj == p) {      // X_pp = T: its storage overlaps L_pp, read the dense copy
+                        b0[bj] = Tb[lc * 8 + lr];
+                        b1[bj] = Tb[(lc + 4) * 8 + lr];
+                    } else {
+                        const double* br = a + (8 * bj + lr) * DG_LD + c0 + lc;
+                        b0[bj] = br[0];
+                        b1[bj] = br[4];
+                    }
+                    if (bj > p) {
+                        const double2 v = *reinterpret_cast<const double2*>(a + (8 * bi + lr) * DG_LD + 8 * bj + 2 * lc);
+                        cv0[bj] = v.x; cv1[bj] = v.y;
+                    } else {
+                        cv0[bj] = a[(8 * bj + 2 * lc) * DG_LD + 8 * bi + lr];
+                        cv1[bj] = a[(8 * bj + 2 * lc + 1) * DG_LD + 8 * bi + lr];
+                    }
+                }
             }
-            double c0v = 0.0, c1v = 0.0, d0v = 0.0, d1v = 0.0;
-            dmma884(c0v, c1v, a0, b0);
-            dmma884(d0v, d1v, a20, b20);
-            dmma884(c0v, c1v, a1, b1);
-            dmma884(d0v, d1v, a21, b21);
-            store_c(bi, bj, rhs, c0v, c1v);
-            if (two) store_c(bi2, bj2, rhs2, d0v, d1v);
+            // phase B: up to 16 independent 2-deep DMMA chains, accumulating onto the loaded blocks
+#pragma unroll
+            for (int bj = 0; bj < 16; ++bj)
+                if (bj <= bi) dmma884(cv0[bj], cv1[bj], a0, b0[bj]);
+#pragma unroll
+            for (int bj = 0; bj < 16; ++bj)
+                if (bj <= bi) dmma884(cv0[bj], cv1[bj], a1, b1[bj]);
+            // phase C: stores only
+#pragma unroll
+            for (int bj = 0; bj < 16; ++bj) {
+                if (bj <= bi) {
+                    if (bj > p) {
+                        *reinterpret_cast<double2*>(a + (8 * bi + lr) * DG_LD + 8 * bj + 2 * lc) = make_double2(cv0[bj], cv1[bj]);
+                    } else {
+                        a[(8 * bj + 2 * lc) * DG_LD + 8 * bi + lr] = cv0[bj];
+                        a[(8 * bj + 2 * lc + 1) * DG_LD + 8 * bi + lr] = cv1[bj];
+                    }
+                }
+            }
         }
         __syncthreads();
+        GPX_TICK(3);
     }
     if (tid == 0 && bad_pivot != 0 && *info == 0) *info = (int)off + bad_pivot;
     // ---- write back: L (lower, zero above), D = L^-1 into S (zero above), D^T into DT
@@ -329,6 +326,11 @@ potrf_diag2_kernel(double* __restrict__ K, int Np, int blk, int N, double* __res
         else if (i + 1 == c) xv = make_double2(0.0, rinv[c]);
         *reinterpret_cast<double2*>(DTb + c * TILE + i) = xv;
     }
+    __syncthreads();
+    GPX_TICK(4);
+#ifdef GPX_DIAG_TIMING
+    if (tid == 0) for (int i = 0; i < 5; ++i) logdet_blk[8 + i] = (double)t_acc[i];     // timing build only
+#endif
     if (tid < 32) {
         double t = 0.0;
         for (int j = tid; j < TILE; j += 32)

@@ -1,0 +1,55 @@
+// Phase timing of potrf_diag2_kernel (clock64 stamps compiled in with -DGPX_DIAG_TIMING). Not part of the product.
+#define GPX_DIAG_TIMING 1
+#include "../gperks_b200/csrc/gpx_chol.cu"
+#include <cstdio>
+#include <vector>
+#include <cmath>
+int main() {
+    using namespace gpx;
+    const int Np = 128;
+    std::vector<double> A(Np * Np);
+    for (int i = 0; i < Np; ++i) for (int j = 0; j < Np; ++j) A[i * Np + j] = std::exp(-0.5 * (i - j) * (i - j) / 400.0) + (i == j ? 0.01 : 0.0);
+    double *K, *S, *DT, *ld; int* info;
+    cudaMalloc(&K, Np * Np * 8); cudaMalloc(&S, Np * Np * 8); cudaMalloc(&DT, Np * Np * 8); cudaMalloc(&ld, 64 * 8); cudaMalloc(&info, 4);
+    cudaMemset(info, 0, 4); cudaMemset(ld, 0, 64 * 8);
+    const int smem = (TILE * DG_LD + 2 * TILE + 64) * 8;
+    cudaFuncSetAttribute(potrf_diag2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    for (int rep = 0; rep < 3; ++rep) {
+        cudaMemcpy(K, A.data(), Np * Np * 8, cudaMemcpyHostToDevice); cudaMemset(ld, 0, 64 * 8);
+        potrf_diag2_kernel<<<1, D2_THREADS, smem>>>(K, Np, 0, Np, S, DT, ld, info);
+        cudaError_t e = cudaDeviceSynchronize();
+        double h[32]; cudaMemcpy(h, ld, 32 * 8, cudaMemcpyDeviceToHost);
+        int hi; cudaMemcpy(&hi, info, 4, cudaMemcpyDeviceToHost);
+        printf("rep %d err=%d info=%d  cycles: load=%.0f step1=%.0f step2=%.0f step3=%.0f writeback=%.0f  logdet=%.6f\n", rep, (int)e, hi,
+               h[8], h[9], h[10], h[11], h[12], h[0]);
+        printf("   warp0 step3 phases: loads=%.0f dmma=%.0f rmw=%.0f over %.0f block rows\n", h[20], h[21], h[22], h[23]);
+    }
+    return 0;
+}
+
+// ---- DMMA latency probe: one warp, dependent chain vs 4 independent chains
+__global__ void dmma_latency_kernel(double* out) {
+    double c0 = 0, c1 = 0, d0[4] = {0, 0, 0, 0}, d1[4] = {0, 0, 0, 0};
+    double a = 1.0 + threadIdx.x * 1e-3, b = 1.0 - threadIdx.x * 1e-3;
+    long long t0 = clock64();
+#pragma unroll 1
+    for (int i = 0; i < 256; ++i) gpx::dmma884(c0, c1, a, b);
+    long long t1 = clock64();
+#pragma unroll 1
+    for (int i = 0; i < 64; ++i) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) gpx::dmma884(d0[u], d1[u], a, b);
+    }
+    long long t2 = clock64();
+    if (threadIdx.x == 0) { out[0] = (double)(t1 - t0) / 256.0; out[1] = (double)(t2 - t1) / 256.0; }
+    out[2 + threadIdx.x] = c0 + c1 + d0[0] + d0[1] + d0[2] + d0[3] + d1[0] + d1[1] + d1[2] + d1[3];
+}
+struct LatencyProbe {
+    LatencyProbe() {
+        double* o; cudaMalloc(&o, 64 * 8);
+        dmma_latency_kernel<<<1, 32>>>(o);
+        cudaDeviceSynchronize();
+        double h[2]; cudaMemcpy(h, o, 16, cudaMemcpyDeviceToHost);
+        printf("DMMA.8x8x4 single warp: dependent chain %.1f cycles/op, 4 independent chains %.1f cycles/op\n", h[0], h[1]);
+    }
+} g_probe;
