@@ -138,7 +138,7 @@ potrf_diag2_kernel(double* __restrict__ K, int Np, int blk, int N, double* __res
     const long off = (long)blk * TILE;
     double* Ab = K + off * Np + off;
 #ifdef GPX_DIAG_TIMING
-    long long t_mark = clock64(), t_acc[6] = {0, 0, 0, 0, 0, 0};
+    long long t_mark = clock64(), t_acc[6] = {0, 0, 0, 0, 0, 0}, t_ph[4] = {0, 0, 0, 0};
 #define GPX_TICK(i) do { long long n_ = clock64(); t_acc[i] += n_ - t_mark; t_mark = n_; } while (0)
 #else
 #define GPX_TICK(i)
@@ -255,6 +255,9 @@ potrf_diag2_kernel(double* __restrict__ K, int Np, int blk, int N, double* __res
         for (int bi = p + 1 + warp; bi < TILE / 8; bi += D2_THREADS / 32) {
             const double* ar = a + (8 * bi + lr) * DG_LD + c0 + lc;
             const double a0 = -ar[0], a1 = -ar[4];        // C - L L^T == (-L) L^T + C: accumulate in place
+#ifdef GPX_DIAG_TIMING
+            long long q0 = clock64();
+#endif
             // phase A: every B fragment and every C block of the block row.  The panel columns are not written in
             // this step and the blocks are disjoint, so ALL loads are issued before any DMMA / store (separate
             // load -> modify -> store sequences per block would serialise on possible shared-memory aliasing).
@@ -280,6 +283,9 @@ potrf_diag2_kernel(double* __restrict__ K, int Np, int blk, int N, double* __res
                     }
                 }
             }
+#ifdef GPX_DIAG_TIMING
+            long long q1 = clock64();
+#endif
             // phase B: up to 16 independent 2-deep DMMA chains, accumulating onto the loaded blocks
 #pragma unroll
             for (int bj = 0; bj < 16; ++bj)
@@ -287,6 +293,9 @@ potrf_diag2_kernel(double* __restrict__ K, int Np, int blk, int N, double* __res
 #pragma unroll
             for (int bj = 0; bj < 16; ++bj)
                 if (bj <= bi) dmma884(cv0[bj], cv1[bj], a1, b1[bj]);
+#ifdef GPX_DIAG_TIMING
+            long long q2 = clock64();
+#endif
             // phase C: stores only
 #pragma unroll
             for (int bj = 0; bj < 16; ++bj) {
@@ -299,6 +308,9 @@ potrf_diag2_kernel(double* __restrict__ K, int Np, int blk, int N, double* __res
                     }
                 }
             }
+#ifdef GPX_DIAG_TIMING
+            { long long q3 = clock64(); t_ph[0] += q1 - q0; t_ph[1] += q2 - q1; t_ph[2] += q3 - q2; t_ph[3] += 1; }
+#endif
         }
         __syncthreads();
         GPX_TICK(3);
@@ -329,7 +341,10 @@ potrf_diag2_kernel(double* __restrict__ K, int Np, int blk, int N, double* __res
     __syncthreads();
     GPX_TICK(4);
 #ifdef GPX_DIAG_TIMING
-    if (tid == 0) for (int i = 0; i < 5; ++i) logdet_blk[8 + i] = (double)t_acc[i];     // timing build only
+    if (tid == 0) {     // timing build only
+        for (int i = 0; i < 5; ++i) logdet_blk[8 + i] = (double)t_acc[i];
+        for (int i = 0; i < 4; ++i) logdet_blk[20 + i] = (double)t_ph[i];
+    }
 #endif
     if (tid < 32) {
         double t = 0.0;
