@@ -156,7 +156,7 @@ class Wave:
         return X[np.argsort(I)[:n_points]]
 
     def copy(self):
-        W = Wave(emulator=self.emulator, Itrain=self.Itrain, cutoff=self.cutoff, maxno=self.maxno, mean=self.mean,
+        W = type(self)(emulator=self.emulator, Itrain=self.Itrain, cutoff=self.cutoff, maxno=self.maxno, mean=self.mean,
                  var=self.var)
         W.I, W.PV = np.copy(self.I), np.copy(self.PV)
         W.NIMP, W.IMP = np.copy(self.NIMP), np.copy(self.IMP)
