@@ -99,6 +99,7 @@ class PosteriorDistribution:
 
     def __init__(self, model, x: torch.Tensor, noisy: bool = False):
         self.model = model
+        self._x_orig = x                 # identity of the caller's tensor keys the per-epoch prediction cache
         self.x = x if x.dim() > 1 else x.unsqueeze(-1)
         self.noisy = noisy
         self._mv = None
@@ -112,11 +113,12 @@ class PosteriorDistribution:
     def _mean_var_device(self):
         if self._mv is None:
             with torch.no_grad():
-                eng = self.model._factorized_engine()
-                xd = self.x.detach().to(eng.device, F64).contiguous()
-                prior = self.model.mean_module(xd).detach().to(eng.device, F64)
-                mean, std = eng.predict(xd, prior_mean=prior, noisy=self.noisy)
-                self._mv = (mean, std * std)
+                def compute(eng):
+                    xd = self.x.detach().to(eng.device, F64).contiguous()
+                    prior = self.model.mean_module(self.x.detach()).detach().to(eng.device, F64)
+                    mean, std = eng.predict(xd, prior_mean=prior, noisy=self.noisy)
+                    return (mean, std * std)
+                self._mv = self.model._cached_prediction(self._x_orig, self.noisy, compute)
         return self._mv
 
     def _cov_device(self) -> torch.Tensor:
@@ -157,7 +159,7 @@ class PosteriorDistribution:
         return self.covariance_matrix
 
     def with_noise(self, likelihood) -> "PosteriorDistribution":
-        return PosteriorDistribution(self.model, self.x, noisy=True)
+        return PosteriorDistribution(self.model, self._x_orig, noisy=True)
 
     def confidence_region(self):
         s2 = self.stddev * 2.0

@@ -38,6 +38,7 @@ class ExactGP(Module):
         state = self.__dict__.copy()
         state["_engine"] = None
         state["_factor_theta"] = None
+        state["_pred_cache"] = None
         return state
 
     def _apply(self, fn, recurse=True):
@@ -79,9 +80,10 @@ class ExactGP(Module):
         return make_theta(base.lengthscale_vector(D), s, self.likelihood.noise, device)
 
     def _resid(self, device) -> torch.Tensor:
+        # evaluated where the (tiny) mean parameters live, then moved once: avoids a host->device hop per parameter
         X = self.train_inputs[0]
         y = self.train_targets
-        return y.to(device, F64).reshape(-1) - self.mean_module(X.to(device, F64)).to(device, F64).reshape(-1)
+        return (y.reshape(-1).to(F64) - self.mean_module(X).reshape(-1).to(F64)).to(device)
 
     def _factorized_engine(self) -> ExactGPEngine:
         """Engine whose cached factors match the current hyper-parameters (refactorises if stale)."""
@@ -91,7 +93,20 @@ class ExactGP(Module):
             resid = self._resid(eng.device)
         if not eng.matches(theta, resid):
             eng.factorize(theta, resid)
+            self._pred_cache = None
         return eng
+
+    def _cached_prediction(self, x: torch.Tensor, noisy: bool, compute):
+        """Per-epoch metrics call ``likelihood(model(X))`` once per metric on the same inputs: keep the last
+        (mean, variance) keyed on the input tensor, its version and the factorisation they were computed from."""
+        eng = self._factorized_engine()
+        key = (id(x), x._version, tuple(x.shape), noisy, eng.n_factorizations)
+        cache = getattr(self, "_pred_cache", None)
+        if cache is not None and cache[0] == key:
+            return cache[1]
+        value = compute(eng)
+        self._pred_cache = (key, value)
+        return value
 
     # -- gpytorch calling convention ------------------------------------------------------------
     def __call__(self, *args, **kwargs):
