@@ -5,6 +5,7 @@ posterior predictive distribution.  Call sites: GPErks/gp/model.py:7-21, GPErks/
 from __future__ import annotations
 
 import warnings
+import weakref
 from typing import Optional
 
 import torch
@@ -100,12 +101,13 @@ class ExactGP(Module):
         """Per-epoch metrics call ``likelihood(model(X))`` once per metric on the same inputs: keep the last
         (mean, variance) keyed on the input tensor, its version and the factorisation they were computed from."""
         eng = self._factorized_engine()
-        key = (id(x), x._version, tuple(x.shape), noisy, eng.n_factorizations)
+        key = (x._version, tuple(x.shape), noisy, eng.n_factorizations)
         cache = getattr(self, "_pred_cache", None)
-        if cache is not None and cache[0] == key:
-            return cache[1]
+        # the weak reference guards against a new tensor re-using the id of a collected one
+        if cache is not None and cache[0] == key and cache[1]() is x:
+            return cache[2]
         value = compute(eng)
-        self._pred_cache = (key, value)
+        self._pred_cache = (key, weakref.ref(x), value)
         return value
 
     # -- gpytorch calling convention ------------------------------------------------------------
