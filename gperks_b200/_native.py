@@ -35,6 +35,8 @@ _SIGS = {
     "gpx_predict_meanvar": (C.c_int, [_P, C.c_long, _P, C.c_int, C.c_int, _P, _P, _P, C.c_int, _P, C.c_int, _P, _P,
                                       _P, C.c_int, C.c_int, _P, _P, C.c_double, C.c_double, C.c_double, _P, _P, _P,
                                       C.c_size_t, C.c_int, _P]),
+    "gpx_trmm_store": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P]),
+    "gpx_syrk_sub": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
     "gpx_split_tf32": (C.c_int, [_P, C.c_long, _P, _P, C.c_int, _P]),
     "gpx_tf32_row_tiles": (C.c_int, [C.c_int]),
     "gpx_trmm_sumsq_tf32": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, _P, C.c_int, _P]),

@@ -15,6 +15,8 @@ int solve_alpha(const double*, const double*, int, const double*, double*, doubl
 int mll_value(const double*, const double*, int, int, const double*, double*, cudaStream_t);
 size_t predict_workspace_bytes(int, int);
 int trmm_sumsq(const double*, int, const double*, int, double*, cudaStream_t);
+int trmm_store(const double*, int, const double*, int, double*, cudaStream_t);
+int syrk_sub(const double*, int, int, double*, cudaStream_t);
 int split_tf32_matrix(const double*, long, float*, float*, int, cudaStream_t);
 int trmm_sumsq_tf32(const float*, const float*, int, const float*, const float*, int, double*, int, cudaStream_t);
 int tf32_row_tiles(int);
@@ -151,6 +153,18 @@ int gpx_predict_meanvar(const double* Xs, long M, const double* X, int N, int D,
     return predict_meanvar(Xs, M, X, N, D, theta, xa, xr, kind, S, Np, alpha, prior_mean, feat_idx, n_feat, degree,
                            weights, bias, y_mu, y_sigma, min_var, out_mean, out_std, workspace, workspace_bytes, Mc,
                            ST(stream));
+}
+
+int gpx_trmm_store(const double* S, int Np, const double* Ks, int Mp, double* Vt, void* stream) {
+    if (!S || !Ks || !Vt) return -1;
+    if (Np % TILE || Mp % TILE || Np <= 0 || Mp <= 0) return -2;
+    return trmm_store(S, Np, Ks, Mp, Vt, ST(stream));
+}
+
+int gpx_syrk_sub(const double* Vt, int Mp, int Np, double* C, void* stream) {
+    if (!Vt || !C) return -1;
+    if (Np % TILE || Mp % TILE || Np <= 0 || Mp <= 0) return -2;
+    return syrk_sub(Vt, Mp, Np, C, ST(stream));
 }
 
 int gpx_split_tf32(const double* src, long n, float* hi, float* lo, int ld, void* stream) {

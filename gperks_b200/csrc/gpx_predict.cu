@@ -11,6 +11,7 @@
 //   3. predict_finalize      deterministic sums over the partials, prior mean, clamp, sqrt, unscale
 #include "gpx_common.cuh"
 #include "gpx_tma.cuh"
+#include "gpx_gemm_tma.cuh"
 #include <stdlib.h>
 
 namespace gpx {
@@ -314,6 +315,72 @@ int predict_meanvar(const double* Xs, long M, const double* X, int N, int D, con
             xs, mv, D, xa, xr, theta, mean_part, qpart, nb, mc, prior_mean ? prior_mean + m0 : nullptr, feat_idx,
             n_feat, degree, weights, bias, y_mu, y_sigma, min_var, out_mean + m0, out_std + m0, nb);
     }
+    GPX_CHECK_LAUNCH();
+    return 0;
+}
+
+// ---- dense predictive covariance (with_covar / sample / validation loss; test-set sized M) ---------------------
+// Vt[m][i] = sum_{k <= i} Ks[m][k] * Linv[i][k]   (= (L^-1 K*^T)^T, rows = test points), tiles (mb, ib)
+__global__ void __launch_bounds__(GT_THREADS, 1)
+trmm_store_tma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmS,
+                      double* __restrict__ Vt, int Np) {
+    extern __shared__ unsigned char smem_raw[];
+    const int ib = blockIdx.x, mb = blockIdx.y;
+    TOperand A = t_operand(&tmK, mb * TILE, 0);
+    TOperand B = t_operand(&tmS, ib * TILE, 0);
+    double acc[8][4][2];
+    gemm_nt_tma_mainloop(acc, A, B, 0, (ib + 1) * TILE, smem_raw);
+    double* Ct = Vt + ((long)mb * TILE) * Np + (long)ib * TILE;
+    gemm_foreach_pair(acc, [&](int row, int col, double v0, double v1) {
+        *reinterpret_cast<double2*>(Ct + (long)row * Np + col) = make_double2(v0, v1);
+    });
+}
+
+// C[m1][m2] -= sum_k Vt[m1][k] * Vt[m2][k]   (C = K** on entry, Mp x Mp), all tiles
+__global__ void __launch_bounds__(GT_THREADS, 1)
+syrk_sub_tma_kernel(const __grid_constant__ CUtensorMap tmV, double* __restrict__ C, int Mp, int Np) {
+    extern __shared__ unsigned char smem_raw[];
+    const int t2 = blockIdx.x, t1 = blockIdx.y;
+    TOperand A = t_operand(&tmV, t1 * TILE, 0);
+    TOperand B = t_operand(&tmV, t2 * TILE, 0);
+    double acc[8][4][2];
+    gemm_nt_tma_mainloop(acc, A, B, 0, Np, smem_raw);
+    double* Ct = C + ((long)t1 * TILE) * Mp + (long)t2 * TILE;
+    gemm_foreach_pair(acc, [&](int row, int col, double v0, double v1) {
+        double2* ptr = reinterpret_cast<double2*>(Ct + (long)row * Mp + col);
+        double2 c = *ptr;
+        c.x -= v0; c.y -= v1;
+        *ptr = c;
+    });
+}
+
+static bool g_cov_attr[64] = {false};
+static void set_cov_attrs() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && g_cov_attr[dev]) return;
+    cudaFuncSetAttribute(trmm_store_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM_BYTES);
+    cudaFuncSetAttribute(syrk_sub_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM_BYTES);
+    if (dev >= 0 && dev < 64) g_cov_attr[dev] = true;
+}
+
+int trmm_store(const double* S, int Np, const double* Ks, int Mp, double* Vt, cudaStream_t st) {
+    set_cov_attrs();
+    CUtensorMap tmK, tmS;
+    int rc;
+    if ((rc = encode_f64_rowmajor(&tmK, Ks, Mp, Np, Np, TILE))) return rc;
+    if ((rc = encode_f64_rowmajor(&tmS, S, Np, Np, Np, TILE))) return rc;
+    trmm_store_tma_kernel<<<dim3(Np / TILE, Mp / TILE), GT_THREADS, GT_SMEM_BYTES, st>>>(tmK, tmS, Vt, Np);
+    GPX_CHECK_LAUNCH();
+    return 0;
+}
+
+int syrk_sub(const double* Vt, int Mp, int Np, double* C, cudaStream_t st) {
+    set_cov_attrs();
+    CUtensorMap tmV;
+    int rc;
+    if ((rc = encode_f64_rowmajor(&tmV, Vt, Mp, Np, Np, TILE))) return rc;
+    syrk_sub_tma_kernel<<<dim3(Mp / TILE, Mp / TILE), GT_THREADS, GT_SMEM_BYTES, st>>>(tmV, C, Mp, Np);
     GPX_CHECK_LAUNCH();
     return 0;
 }

@@ -4,7 +4,8 @@
   evaluated until the marginal log-likelihood consumes it on the GPU.
 * ``PosteriorDistribution`` -- eval-mode predictive distribution; ``.mean`` / ``.variance`` run the fused
   predict kernels, ``.covariance_matrix`` / ``.sample`` / ``.log_prob`` form the dense M x M covariance
-  (test-set sized M only; plain cuBLAS/cuSOLVER through torch, not a hot path).
+  (test-set sized M) with the TRMM-store / SYRK kernels and factor it with the blocked CUDA Cholesky
+  (``engine.DenseCholesky``); only the final ``L @ z`` of a draw is a plain library GEMM.
 
 They stand in for gpytorch.distributions.MultivariateNormal as used at GPErks/gp/model.py:21 and
 GPErks/train/emulator.py:336-346, 356-360, 392-394."""
@@ -19,18 +20,13 @@ F64 = torch.float64
 
 
 def _psd_safe_cholesky(A: torch.Tensor) -> torch.Tensor:
-    L, info = torch.linalg.cholesky_ex(A)
-    if not bool(info.any()):
-        return L
-    eye = torch.eye(A.shape[-1], dtype=A.dtype, device=A.device)
-    for i in range(3):
-        jitter = 1e-8 * 10 ** i
-        L, info = torch.linalg.cholesky_ex(A + jitter * eye)
-        if not bool(info.any()):
-            warnings.warn(f"A not p.d., added jitter of {jitter:.1e} to the diagonal", RuntimeWarning)
-            return L
-    from .engine import NotPSDError
-    raise NotPSDError("Matrix not positive definite after repeatedly adding jitter up to 1.0e-06.")
+    """Lower Cholesky factor of a dense covariance through the blocked CUDA factorisation (jitter retries as
+    gpytorch's psd_safe_cholesky)."""
+    from . import _native as nv
+    from .engine import DenseCholesky
+    nv.require_cuda()
+    dev = A.device if A.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    return DenseCholesky(A.detach().to(dev, F64).contiguous()).L.to(A.device)
 
 
 class MultivariateNormal:
@@ -104,6 +100,7 @@ class PosteriorDistribution:
         self.noisy = noisy
         self._mv = None
         self._cov = None
+        self._cov_mean = None
 
     # -- helpers --------------------------------------------------------------------------------
     def _out(self, t: torch.Tensor) -> torch.Tensor:
@@ -125,14 +122,10 @@ class PosteriorDistribution:
         if self._cov is None:
             with torch.no_grad():
                 eng = self.model._factorized_engine()
-                xd = self.x.detach().to(eng.device, F64).contiguous()
-                Ks = eng.cross_kernel(xd)                                   # [M, N]
-                V = eng.linv() @ Ks.T                                       # [N, M]  (library GEMM, small M)
-                Kss = self.model.covar_module.dense(xd, xd).to(eng.device, F64)
-                cov = Kss - V.T @ V
-                if self.noisy:
-                    cov = cov + eng.theta[eng.D + 1] * torch.eye(cov.shape[0], dtype=F64, device=eng.device)
-                self._cov = 0.5 * (cov + cov.T)
+                prior = self.model.mean_module(self.x.detach()).detach()
+                mean, cov = eng.predict_covar(self.x, prior, noisy=self.noisy)
+                self._cov = cov
+                self._cov_mean = mean
         return self._cov
 
     # -- gpytorch API ---------------------------------------------------------------------------
@@ -179,11 +172,12 @@ class PosteriorDistribution:
             return self.rsample(sample_shape)
 
     def log_prob(self, value: torch.Tensor) -> torch.Tensor:
-        mean = self._mean_var_device()[0]
+        from .engine import DenseCholesky
         cov = self._cov_device()
+        mean = self._cov_mean
         diff = value.detach().to(mean.device, F64).reshape(-1) - mean
-        L = _psd_safe_cholesky(cov)
-        z = torch.linalg.solve_triangular(L, diff.unsqueeze(-1), upper=False).squeeze(-1)
+        chol = DenseCholesky(cov, need_inverse=True)
+        z = chol.solve_lower(diff)
         M = mean.shape[0]
-        lp = -0.5 * (z @ z) - torch.log(torch.diagonal(L)).sum() - 0.5 * M * 1.8378770664093453
+        lp = -0.5 * (z @ z) - chol.logdet_half - 0.5 * M * 1.8378770664093453
         return self._out(lp)

@@ -267,12 +267,101 @@ class ExactGPEngine:
                          nv.stream_ptr())
         return Ks[:M, : self.N]
 
+    def predict_covar(self, Xs: torch.Tensor, prior_mean: torch.Tensor, noisy: bool = True):
+        """Posterior mean and the dense M x M predictive covariance for scaled device inputs Xs (test-set sized M):
+        K** - (L^-1 K*^T)^T (L^-1 K*^T) [+ noise I], every product on the DMMA/TMA tile engine."""
+        if not self.factored:
+            raise RuntimeError("predict_covar() before factorize()")
+        if Xs.dim() == 1:
+            Xs = Xs.unsqueeze(-1)
+        Xs = Xs.detach().to(self.device, F64).contiguous()
+        M = Xs.shape[0]
+        Mp, Np, nb = nv.padded(M), self.Np, self.nb
+        dev, p = self.device, nv.ptr
+        Ks = torch.empty(Mp, Np, dtype=F64, device=dev)
+        mpart = torch.empty(nb, Mp, dtype=F64, device=dev)
+        Vt = torch.empty(Mp, Np, dtype=F64, device=dev)
+        Kss = torch.empty(Mp, Mp, dtype=F64, device=dev)
+        mpart2 = torch.empty(Mp // nv.TILE, Mp, dtype=F64, device=dev)
+        zeros = torch.zeros(Mp, dtype=F64, device=dev)
+        with torch.cuda.device(dev):
+            st = nv.stream_ptr()
+            self._launch("gpx_kmat_cross", p(Xs), M, p(self.X), self.N, self.D, p(self.theta), None, None, self.kind,
+                         p(self.alpha), p(Ks), Np, p(mpart), Mp, st)
+            self._launch("gpx_trmm_store", p(self.S), Np, p(Ks), Mp, p(Vt), st)
+            self._launch("gpx_kmat_cross", p(Xs), M, p(Xs), M, self.D, p(self.theta_latent), None, None, self.kind,
+                         p(zeros), p(Kss), Mp, p(mpart2), Mp, st)
+            self._launch("gpx_syrk_sub", p(Vt), Mp, Np, p(Kss), st)
+        mean = prior_mean.detach().to(dev, F64).reshape(-1) + mpart[:, :M].sum(0)
+        cov = Kss[:M, :M]
+        cov = 0.5 * (cov + cov.T)
+        if noisy:
+            cov = cov + self.theta[self.D + 1] * torch.eye(M, dtype=F64, device=dev)
+        return mean, cov
+
     def linv(self) -> torch.Tensor:
         """Dense lower-triangular L^-1 [N, N] (copy; for the small-M covariance paths and tests)."""
         return torch.tril(self.S[: self.N, : self.N])
 
     def chol(self) -> torch.Tensor:
         return torch.tril(self.K[: self.N, : self.N])
+
+
+class DenseCholesky:
+    """Cholesky factor / inverse / log-determinant of a small dense SPD matrix (predictive covariances) through the
+    same blocked kernels as the training factorisation, with gpytorch's jitter retry schedule."""
+
+    def __init__(self, A: torch.Tensor, need_inverse: bool = False):
+        nv.require_cuda()
+        lib = nv.lib()
+        dev = A.device
+        M = A.shape[0]
+        Mp = nv.padded(M)
+        nb = Mp // nv.TILE
+        self.M, self.Mp = M, Mp
+        p = nv.ptr
+        S = torch.empty(Mp, Mp, dtype=F64, device=dev)
+        DT = torch.empty(nb, nv.TILE, nv.TILE, dtype=F64, device=dev)
+        logdet_blk = torch.zeros(nb, dtype=F64, device=dev)
+        info = torch.zeros(1, dtype=torch.int32, device=dev)
+        jitter = 0.0
+        with torch.cuda.device(dev):
+            for attempt in range(4):
+                K = torch.eye(Mp, dtype=F64, device=dev)
+                K[:M, :M] = A
+                if attempt > 0:
+                    jitter = 1e-8 * 10 ** (attempt - 1)
+                    warnings.warn(f"A not p.d., added jitter of {jitter:.1e} to the diagonal", NumericalWarning)
+                    K[:M, :M].diagonal().add_(jitter)
+                nv.check(lib.gpx_potrf(p(K), Mp, M, p(S), p(DT), p(logdet_blk), p(info), nv.stream_ptr()), "gpx_potrf")
+                if int(info.item()) == 0:
+                    break
+                if attempt == 3:
+                    raise NotPSDError(f"Matrix not positive definite after repeatedly adding jitter up to {jitter:.1e}.")
+            if need_inverse:
+                W = torch.empty(Mp, Mp, dtype=F64, device=dev)
+                nv.check(lib.gpx_trtri(p(K), p(S), p(DT), p(W), Mp, nv.stream_ptr()), "gpx_trtri")
+        self.K, self.S, self.DT = K, S, DT
+        self.logdet_half = logdet_blk.sum()          # sum log L_ii
+        self.has_inverse = need_inverse
+
+    @property
+    def L(self) -> torch.Tensor:
+        return torch.tril(self.K[: self.M, : self.M])
+
+    def solve_lower(self, b: torch.Tensor) -> torch.Tensor:
+        """L^-1 b through the explicit triangular inverse (one mat-vec kernel)."""
+        assert self.has_inverse
+        lib = nv.lib()
+        dev = self.K.device
+        r = torch.zeros(self.Mp, dtype=F64, device=dev)
+        r[: self.M] = b.reshape(-1)
+        u = torch.empty(self.Mp, dtype=F64, device=dev)
+        a = torch.empty(self.Mp, dtype=F64, device=dev)
+        with torch.cuda.device(dev):
+            nv.check(lib.gpx_solve_alpha(nv.ptr(self.S), nv.ptr(self.DT), self.Mp, nv.ptr(r), nv.ptr(u), nv.ptr(a),
+                                         nv.stream_ptr()), "gpx_solve_alpha")
+        return u[: self.M]
 
 
 def make_theta(lengthscale: torch.Tensor, outputscale: torch.Tensor, noise: torch.Tensor,

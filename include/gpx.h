@@ -85,6 +85,13 @@ int gpx_predict_meanvar(const double* Xs, long M, const double* X, int N, int D,
                         double min_var, double* out_mean, double* out_std, void* workspace,
                         size_t workspace_bytes, int Mc, void* stream);
 
+/* Dense predictive covariance for test-set sized M (with_covar, sample, validation loss):
+ * gpx_trmm_store: Vt[m][i] = (K* L^-T)[m][i] for Ks[Mp][Np] -> Vt[Mp][Np];
+ * gpx_syrk_sub:   C[Mp][Mp] -= Vt Vt^T  (C holds K** on entry, the predictive covariance on exit).
+ * replaces: predictions.covariance_matrix / .sample / the eval-mode mll, GPErks/train/emulator.py:331-333,359-360,394. */
+int gpx_trmm_store(const double* S, int Np, const double* Ks, int Mp, double* Vt, void* stream);
+int gpx_syrk_sub(const double* Vt, int Mp, int Np, double* C, void* stream);
+
 /* ---- TF32 mode of the predictive variance (north_star tolerance: rel 1e-3): 3xTF32 on tcgen05 / TMEM ----
  * gpx_split_tf32: (hi, lo) float split of n FP64 values, x ~= hi + lo, both exactly representable in TF32
 

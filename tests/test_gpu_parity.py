@@ -423,3 +423,26 @@ def test_emulator_predict_tf32_precision(dev, goldens):
     m32f, s32f = em.predict(Xq, precision="tf32x3_fast")
     np.testing.assert_allclose(m32f, m64, rtol=1e-3, atol=1e-4 * np.abs(m64).max())
     np.testing.assert_allclose(s32f, s64, rtol=1e-3)
+
+
+def test_validation_loss_and_covariance_kernels_match_oracle(dev):
+    """Eval-mode mll(model(X_val), y_val) = posterior-predictive log density / M_val (GPEmulator._val_step), the dense
+    predictive covariance and its Cholesky all run on the CUDA tile engine: compare with the oracle."""
+    from gperks_b200.engine import DenseCholesky
+    N, D, M = 300, 4, 150
+    X, y, Xs, ls, s, w, b = _problem(N, D, M, seed=21)
+    nz = 5e-3
+    eng = _engine(dev, X, y, O.KIND_MATERN52, ls, s, nz, w, b)
+    prior = (Xs @ w + b)
+    mean, cov = eng.predict_covar(Xs.to(dev), prior.to(dev), noisy=True)
+    mref, vref, cref = O.predict(X, y, O.KIND_MATERN52, ls, s, nz, X @ w + b, Xs, prior, with_covar=True)
+    np.testing.assert_allclose(mean.cpu().numpy(), mref.numpy(), rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(cov.cpu().numpy(), cref.numpy(), rtol=0, atol=1e-10 * float(cref.abs().max()))
+    chol = DenseCholesky(cov, need_inverse=True)
+    Lref = torch.linalg.cholesky(cref)
+    np.testing.assert_allclose(chol.L.cpu().numpy(), Lref.numpy(), rtol=0, atol=1e-10 * float(Lref.abs().max()))
+    yv = torch.randn(M, dtype=F64, generator=torch.Generator().manual_seed(3))
+    z = chol.solve_lower((yv.to(dev) - mean))
+    lp = -0.5 * float(z @ z) - float(chol.logdet_half) - 0.5 * M * math.log(2 * math.pi)
+    ref = torch.distributions.MultivariateNormal(mref, scale_tril=Lref).log_prob(yv)
+    assert lp == pytest.approx(float(ref), rel=1e-9)
