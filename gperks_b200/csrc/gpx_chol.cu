@@ -357,6 +357,223 @@ potrf_diag2_kernel(double* __restrict__ K, int Np, int blk, int N, double* __res
 }
 
 // ------------------------------------------------------------------------------------------------
+// Diagonal block, version 3 (default): the whole 128 x 128 problem lives in REGISTERS.
+// v2's rank-8 updates were bound by shared-memory traffic (every 8x8 block was read-modify-written in smem once
+// per panel: 12 wavefronts for 2 DMMAs).  Here the 16 x 16 grid of 8x8 blocks is distributed once: warp w owns
+// block rows w and 15-w (17 lower-triangular blocks, perfectly balanced) of BOTH the matrix (A -> L) and the
+// right-hand side of L X = I (B -> X = L^-1), each block held as a DMMA C fragment (2 doubles per lane).
+// Per 8-wide panel p only the panel itself goes through shared memory:
+//   (1) the owner of block (p,p) factors it with warp shuffles, publishes L_pp and T = L_pp^-1;
+//   (2) owners of column-p blocks form L_ip = A_ip T^T and owners of row-p X blocks form X_pj = T B_pj on DMMA
+//       (C-fragment -> operand-fragment conversion by shuffles) and publish them;
+//   (3) every warp updates its own blocks: A_ij -= L_ip L_jp^T, B_ij -= L_ip X_pj (2 DMMAs per block, operands from
+//       the published panel, accumulators never leave the registers).
+// The published panel is double-buffered by panel parity, so only two CTA barriers per panel are needed.
+// ------------------------------------------------------------------------------------------------
+constexpr int D3_THREADS = 256;
+constexpr int D3_BS = 96;                 // doubles per published 8x8 block: rows padded to 12 (conflict-free fragments)
+constexpr int D3_BUF = 33 * D3_BS;        // 16 L blocks + 16 X blocks + T
+constexpr int D3_SMEM = (2 * D3_BUF + 2 * TILE) * 8;
+
+__device__ __forceinline__ void d3_slot(int s, int w, int& bi, int& bj) {
+    if (s <= w) { bi = w; bj = s; } else { bi = 15 - w; bj = s - w - 1; }
+}
+
+// C-fragment (lane (lr,lc) holds M[lr][2lc], M[lr][2lc+1]) -> A-operand fragment (M[lr][lc], M[lr][lc+4])
+__device__ __forceinline__ void d3_c_to_a(double v0, double v1, int lr, int lc, double& a0, double& a1) {
+    const unsigned full = 0xffffffffu;
+    const int src0 = lr * 4 + (lc >> 1), src1 = src0 + 2;
+    const double p0 = __shfl_sync(full, v0, src0), p1 = __shfl_sync(full, v1, src0);
+    const double q0 = __shfl_sync(full, v0, src1), q1 = __shfl_sync(full, v1, src1);
+    a0 = (lc & 1) ? p1 : p0;
+    a1 = (lc & 1) ? q1 : q0;
+}
+// C-fragment -> B-operand fragment of the same matrix used as B[k][n] = M[k][n]: lane (k=lc, n=lr) needs M[lc][lr], M[lc+4][lr]
+__device__ __forceinline__ void d3_c_to_b(double v0, double v1, int lr, int lc, double& b0, double& b1) {
+    const unsigned full = 0xffffffffu;
+    const int src0 = lc * 4 + (lr >> 1), src1 = (lc + 4) * 4 + (lr >> 1);
+    const double p0 = __shfl_sync(full, v0, src0), p1 = __shfl_sync(full, v1, src0);
+    const double q0 = __shfl_sync(full, v0, src1), q1 = __shfl_sync(full, v1, src1);
+    b0 = (lr & 1) ? p1 : p0;
+    b1 = (lr & 1) ? q1 : q0;
+}
+
+__global__ void __launch_bounds__(D3_THREADS, 1)
+potrf_diag3_kernel(double* __restrict__ K, int Np, int blk, int N, double* __restrict__ S, double* __restrict__ DT,
+                   double* __restrict__ logdet_blk, int* __restrict__ info) {
+    extern __shared__ double sm3[];
+    double* rinv = sm3 + 2 * D3_BUF;          // [128]
+    double* dg = rinv + TILE;                 // [128]
+    __shared__ int bad_pivot;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int lr = lane >> 2, lc = lane & 3;
+    const unsigned full = 0xffffffffu;
+    const long off = (long)blk * TILE;
+    double* Ab = K + off * Np + off;
+    if (tid == 0) bad_pivot = 0;
+
+    // ---- distribute: 17 blocks of the matrix per warp as C fragments; the right-hand side starts as the identity
+    double cl0[17], cl1[17], cx0[17], cx1[17];
+#pragma unroll
+    for (int s = 0; s < 17; ++s) {
+        int bi, bj;
+        d3_slot(s, w, bi, bj);
+        const double2 v = *reinterpret_cast<const double2*>(Ab + (long)(8 * bi + lr) * Np + 8 * bj + 2 * lc);
+        cl0[s] = v.x; cl1[s] = v.y;
+        cx0[s] = 0.0; cx1[s] = 0.0;
+    }
+    __syncthreads();
+
+    for (int p = 0; p < 16; ++p) {
+        double* buf = sm3 + (p & 1) * D3_BUF;
+        double* Lc = buf;                      // published column p of L: block bi at Lc + bi*D3_BS, [8][12]
+        double* Xr = buf + 16 * D3_BS;         // published row p of X   : block bj at Xr + bj*D3_BS, stored [k][n]
+        double* Tb = buf + 32 * D3_BS;         // T = L_pp^-1, [8][12], zeros above the diagonal
+        const int wp = (p <= 7) ? p : 15 - p;  // owner warp of block row p
+        const int sp = (p <= 7) ? p : 16;      // its slot of the diagonal block (p,p)
+        // ---- (1) diagonal 8x8 block
+        if (w == wp) {
+            double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+            for (int s = 0; s < 17; ++s) if (s == sp) { d0 = cl0[s]; d1 = cl1[s]; }
+            double inv_r = 0.0, sd_r = 0.0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int jq = j >> 1, je = j & 1;
+                const double sel = je ? d1 : d0;
+                const double piv = __shfl_sync(full, sel, j * 4 + jq);
+                if (!(piv > 0.0) && lane == 0 && bad_pivot == 0) bad_pivot = 8 * p + j + 1;
+                const double inv = rsqrt(piv);
+                const double sd = piv * inv;
+                const double lrj = __shfl_sync(full, sel, lr * 4 + jq) * inv;
+                const double lc0 = __shfl_sync(full, sel, (2 * lc) * 4 + jq) * inv;
+                const double lc1 = __shfl_sync(full, sel, (2 * lc + 1) * 4 + jq) * inv;
+                if (lc == jq && lr >= j) {
+                    const double v = (lr == j) ? sd : lrj;
+                    if (je) d1 = v; else d0 = v;
+                }
+                if (2 * lc > j && lr >= 2 * lc) d0 = fma(-lrj, lc0, d0);
+                if (2 * lc + 1 > j && lr >= 2 * lc + 1) d1 = fma(-lrj, lc1, d1);
+                if (lr == j) { inv_r = inv; sd_r = sd; }
+            }
+            if (2 * lc > lr) d0 = 0.0;                 // keep L_pp clean above the diagonal
+            if (2 * lc + 1 > lr) d1 = 0.0;
+#pragma unroll
+            for (int s = 0; s < 17; ++s) if (s == sp) { cl0[s] = d0; cl1[s] = d1; }
+            *reinterpret_cast<double2*>(Lc + p * D3_BS + lr * 12 + 2 * lc) = make_double2(d0, d1);
+            if (lc == 0) { rinv[8 * p + lr] = inv_r; dg[8 * p + lr] = sd_r; }
+            __syncwarp();
+            if (lane < 8) {        // column `lane` of T by forward substitution
+                const double* Lb = Lc + p * D3_BS;
+                double x[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    double acc_ = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+                    for (int k = 0; k < i; ++k) acc_ = fma(-Lb[i * 12 + k], x[k], acc_);
+                    x[i] = acc_ * rinv[8 * p + i];
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) Tb[i * 12 + lane] = x[i];
+            }
+            __syncwarp();
+            // X_pp = T: the owner's right-hand-side diagonal block, also published as row-p block p ([k][n] = T[k][n])
+            const double2 t = *reinterpret_cast<const double2*>(Tb + lr * 12 + 2 * lc);
+#pragma unroll
+            for (int s = 0; s < 17; ++s) if (s == sp) { cx0[s] = t.x; cx1[s] = t.y; }
+            *reinterpret_cast<double2*>(Xr + p * D3_BS + lr * 12 + 2 * lc) = t;
+        }
+        __syncthreads();
+        // ---- (2) column-p blocks of L (bi > p) and row-p blocks of X (bj < p) on DMMA
+        {
+            const double tb0 = Tb[lr * 12 + lc], tb1 = Tb[lr * 12 + lc + 4];     // T as A operand, and T^T as B operand
+#pragma unroll
+            for (int s = 0; s < 17; ++s) {
+                int bi, bj;
+                d3_slot(s, w, bi, bj);
+                if (bj == p && bi > p) {          // L_ip = A_ip T^T : A = A_ip (from registers), B[k][n] = T[n][k]
+                    double a0, a1;
+                    d3_c_to_a(cl0[s], cl1[s], lr, lc, a0, a1);
+                    double r0 = 0.0, r1 = 0.0;
+                    dmma884(r0, r1, a0, tb0);
+                    dmma884(r0, r1, a1, tb1);
+                    cl0[s] = r0; cl1[s] = r1;
+                    *reinterpret_cast<double2*>(Lc + bi * D3_BS + lr * 12 + 2 * lc) = make_double2(r0, r1);
+                }
+                if (bi == p && bj < p) {          // X_pj = T B_pj : A = T, B[k][n] = B_pj[k][n] (from registers)
+                    double b0, b1;
+                    d3_c_to_b(cx0[s], cx1[s], lr, lc, b0, b1);
+                    double r0 = 0.0, r1 = 0.0;
+                    dmma884(r0, r1, tb0, b0);
+                    dmma884(r0, r1, tb1, b1);
+                    cx0[s] = r0; cx1[s] = r1;
+                    *reinterpret_cast<double2*>(Xr + bj * D3_BS + lr * 12 + 2 * lc) = make_double2(r0, r1);
+                }
+            }
+        }
+        __syncthreads();
+        // ---- (3) register-resident rank-8 updates of this warp's two block rows
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int bi = half ? 15 - w : w;
+            if (bi > p) {
+                const double a0 = -Lc[bi * D3_BS + lr * 12 + lc], a1 = -Lc[bi * D3_BS + lr * 12 + lc + 4];
+#pragma unroll
+                for (int s = 0; s < 17; ++s) {
+                    int sbi, bj;
+                    d3_slot(s, w, sbi, bj);
+                    if (sbi == bi) {
+                        if (bj > p) {             // A_ij -= L_ip L_jp^T : B[k][n] = L_jp[n][k]
+                            const double b0 = Lc[bj * D3_BS + lr * 12 + lc], b1 = Lc[bj * D3_BS + lr * 12 + lc + 4];
+                            dmma884(cl0[s], cl1[s], a0, b0);
+                            dmma884(cl0[s], cl1[s], a1, b1);
+                        } else {                  // B_ij -= L_ip X_pj : B[k][n] = X_pj[k][n]
+                            const double b0 = Xr[bj * D3_BS + lc * 12 + lr], b1 = Xr[bj * D3_BS + (lc + 4) * 12 + lr];
+                            dmma884(cx0[s], cx1[s], a0, b0);
+                            dmma884(cx0[s], cx1[s], a1, b1);
+                        }
+                    }
+                }
+            }
+        }
+        // no barrier: the next panel publishes into the other buffer, and every block a warp needs next is its own
+    }
+    __syncthreads();
+    if (tid == 0 && bad_pivot != 0 && *info == 0) *info = (int)off + bad_pivot;
+    // ---- write back from the registers: L -> K (lower blocks), X -> S (lower blocks), X^T -> DT
+    double* Sb = S + off * Np + off;
+    double* DTb = DT + (long)blk * TILE * TILE;
+#pragma unroll
+    for (int s = 0; s < 17; ++s) {
+        int bi, bj;
+        d3_slot(s, w, bi, bj);
+        const long r = 8 * bi + lr, c = 8 * bj + 2 * lc;
+        *reinterpret_cast<double2*>(Ab + r * Np + c) = make_double2(cl0[s], cl1[s]);
+        *reinterpret_cast<double2*>(Sb + r * Np + c) = make_double2(cx0[s], cx1[s]);
+        DTb[c * TILE + r] = cx0[s];
+        DTb[(c + 1) * TILE + r] = cx1[s];
+    }
+    // zero the blocks above the diagonal of S and below the diagonal of DT (diagonal blocks are already clean)
+    for (int e = tid; e < 120 * 32; e += D3_THREADS) {
+        const int b = e >> 5, q = e & 31;               // b-th strictly-upper block, q-th double2 of it
+        int bi = 0, rem = b;
+        while (rem >= 15 - bi) { rem -= 15 - bi; ++bi; }
+        const int bj = bi + 1 + rem;                    // bj > bi
+        const int rr = q >> 2, cc = (q & 3) * 2;
+        *reinterpret_cast<double2*>(Sb + (long)(8 * bi + rr) * Np + 8 * bj + cc) = make_double2(0.0, 0.0);
+        *reinterpret_cast<double2*>(DTb + (8 * bj + rr) * TILE + 8 * bi + cc) = make_double2(0.0, 0.0);
+    }
+    if (tid < 32) {
+        double t = 0.0;
+        for (int j = tid; j < TILE; j += 32)
+            if (off + j < N) t += log(dg[j]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (tid == 0) logdet_blk[blk] = t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Panel: L[i][p] = A[i][p] * D_p^T   for row tiles i > p.   grid.x = nb - p - 1
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(G_THREADS, 1) potrf_panel_kernel(double* __restrict__ K, int Np, int p,
@@ -642,14 +859,16 @@ static void set_gemm_attrs() {
     const int dg = (TILE * DG_LD + 2 * TILE + 2) * 8;
     cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dg);
     cudaFuncSetAttribute(potrf_diag2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (TILE * DG_LD + 2 * TILE + 64) * 8);
+    cudaFuncSetAttribute(potrf_diag3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D3_SMEM);
     if (dev >= 0 && dev < 64) g_attr_set[dev] = true;
 }
 
-static int use_diag_v1() {
+static int diag_impl() {       // GPX_DIAG_IMPL = 1 | 2 | 3 (default 3)
     static int v = -1;
-    if (v < 0) { const char* e = getenv("GPX_DIAG_IMPL"); v = (e && e[0] == '1') ? 1 : 0; }
+    if (v < 0) { const char* e = getenv("GPX_DIAG_IMPL"); v = (e && e[0] >= '1' && e[0] <= '3') ? e[0] - '0' : 3; }
     return v;
 }
+static int use_diag_v1() { return diag_impl() == 1; }
 
 // Helper stream + events for the look-ahead (per device, created on first use; all work is ordered
 // after the caller's stream and joined back into it before potrf returns control of the data).
@@ -717,8 +936,10 @@ int potrf(double* K, int Np, int N, double* S, double* DT, double* logdet_blk, i
     for (int p = 0; p < nb; ++p) {
         if (use_diag_v1())
             potrf_diag_kernel<<<1, DG_THREADS, dg, st>>>(K, Np, p, N, S, DT, logdet_blk, info);
-        else
+        else if (diag_impl() == 2)
             potrf_diag2_kernel<<<1, D2_THREADS, dg2, st>>>(K, Np, p, N, S, DT, logdet_blk, info);
+        else
+            potrf_diag3_kernel<<<1, D3_THREADS, D3_SMEM, st>>>(K, Np, p, N, S, DT, logdet_blk, info);
         const int n = nb - p - 1;
         if (n <= 0) break;
         panel(n, p);
