@@ -446,3 +446,76 @@ def test_validation_loss_and_covariance_kernels_match_oracle(dev):
     lp = -0.5 * float(z @ z) - float(chol.logdet_half) - 0.5 * M * math.log(2 * math.pi)
     ref = torch.distributions.MultivariateNormal(mref, scale_tril=Lref).log_prob(yv)
     assert lp == pytest.approx(float(ref), rel=1e-9)
+
+
+@pytest.mark.parametrize("variant", ["zero_mean_shared_ls", "constant_mean_bare_kernel", "fixed_noise_quadratic_mean"])
+def test_api_variants_match_oracle(dev, variant):
+    """Less common module combinations through the public API: shared (non-ARD) lengthscale, kernels without a
+    ScaleKernel wrapper, Zero/Constant means, fixed-noise mode -- loss, gradients (vs oracle autograd) and predict."""
+    from gperks_b200.gp.data.dataset import Dataset
+    from gperks_b200.gp.experiment import GPExperiment
+    from gperks_b200.gp.mean import LinearMean
+    from gperks_b200.kernels import MaternKernel, RBFKernel, ScaleKernel
+    from gperks_b200.likelihoods import GaussianLikelihood
+    from gperks_b200.means import ConstantMean, ZeroMean
+    from gperks_b200.mlls import ExactMarginalLogLikelihood
+    from gperks_b200.train.emulator import GPEmulator
+    rng = np.random.default_rng(7)
+    N, D = 90, 3
+    Xn = rng.random((N, D))
+    yn = np.sin(4 * Xn[:, 0]) + Xn[:, 1] * Xn[:, 2] + 0.05 * rng.standard_normal(N)
+    learn_noise = True
+    if variant == "zero_mean_shared_ls":
+        mean, kern, kind, degree = ZeroMean(), ScaleKernel(RBFKernel()), O.KIND_RBF, 0
+    elif variant == "constant_mean_bare_kernel":
+        mean, kern, kind, degree = ConstantMean(), MaternKernel(nu=1.5, ard_num_dims=D), O.KIND_MATERN32, 0
+    else:
+        mean, kern, kind, degree = LinearMean(2, D), ScaleKernel(MaternKernel(nu=0.5, ard_num_dims=D)), O.KIND_MATERN12, 2
+        learn_noise = False
+    exp = GPExperiment(Dataset(Xn, yn), GaussianLikelihood(), mean, kern, n_restarts=1, seed=3, learn_noise=learn_noise)
+    em = GPEmulator(exp, "cuda:0")
+    m = em.model
+    torch.manual_seed(1)
+    with torch.no_grad():
+        for p_ in m.parameters():
+            if p_.requires_grad:
+                p_.add_(0.3 * torch.randn_like(p_))
+    m.train()
+    mll = ExactMarginalLogLikelihood(m.likelihood, m)
+    loss = -mll(m(em.scaled_data.X_train), em.scaled_data.y_train)
+    loss.backward()
+    # oracle with the same constrained values, autograd through its float64 Cholesky
+    X, y = em.scaled_data.X_train, em.scaled_data.y_train
+    raw = {k: v.detach().clone().requires_grad_(v.requires_grad) for k, v in m.named_parameters()}
+    s_, base = m.covar_module.scale_and_base()
+    raw_ls = raw["covar_module.base_kernel.raw_lengthscale" if isinstance(m.covar_module, ScaleKernel) else "covar_module.raw_lengthscale"]
+    ls = O.softplus(raw_ls).reshape(-1)
+    if ls.numel() == 1:
+        ls = ls.expand(D)
+    s = O.softplus(raw["covar_module.raw_outputscale"]) if isinstance(m.covar_module, ScaleKernel) else torch.ones((), dtype=F64)
+    lb = float(m.likelihood.noise_covar.raw_noise_constraint.lower_bound)
+    nz = O.softplus(raw["likelihood.noise_covar.raw_noise"]).reshape(()) + lb
+    if variant == "zero_mean_shared_ls":
+        mean_x = torch.zeros(N, dtype=F64)
+        mean_fn = lambda Z: torch.zeros(Z.shape[0], dtype=F64)  # noqa: E731
+    elif variant == "constant_mean_bare_kernel":
+        mean_x = raw["mean_module.raw_constant"].expand(N)
+        mean_fn = lambda Z: raw["mean_module.raw_constant"].detach().expand(Z.shape[0])  # noqa: E731
+    else:
+        mean_x = O.mean_fn(X, raw["mean_module.weights"], raw["mean_module.bias"], degree=2)
+        mean_fn = lambda Z: O.mean_fn(Z, raw["mean_module.weights"].detach(), raw["mean_module.bias"].detach(), degree=2)  # noqa: E731
+    ol = O.neg_mll(X, y, kind, ls, s, nz, mean_x)
+    ol.backward()
+    assert float(loss.detach()) == pytest.approx(float(ol.detach()), rel=1e-10)
+    for k, p_ in m.named_parameters():
+        if p_.requires_grad:
+            np.testing.assert_allclose(p_.grad.numpy(), raw[k].grad.numpy(), rtol=1e-7, atol=1e-11, err_msg=k)
+        else:
+            assert p_.grad is None
+    Xq = rng.random((500, D))
+    mean_p, std_p = em.predict(Xq)
+    Xqs = torch.from_numpy(em.scaled_data.scx.transform(Xq))
+    mref, vref = O.predict(X, y, kind, ls.detach(), s.detach(), nz.detach(), mean_x.detach(), Xqs, mean_fn(Xqs))
+    scy = em.scaled_data.scy
+    np.testing.assert_allclose(mean_p, scy.sigma * mref.numpy() + scy.mu, rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(std_p, scy.sigma * vref.sqrt().numpy(), rtol=1e-8)
