@@ -147,6 +147,44 @@ def cpu_oracle_predict_rate(X, y, Xs, hyper, sample_pts, chunk=4096):
     return sample_pts / t_pred, t_pred, t_fac, torch.get_num_threads()
 
 
+def torch_gpu_predict_rate(X, y, Xs, hyper, dev, sample_pts, chunk=4096):
+    """"Baseline B" of SURVEY.md section 8d: the same exact-GP math written with plain torch ops on the same B200
+    (cuSOLVER potrf, cuBLAS trsm/gemm in FP64, unfused pointwise kernels) -- what a GPErks user gets from
+    device="cuda" with stock libraries.  Uses the oracle's formulas on device tensors; reported, never shipped."""
+    from oracle import gp_oracle as O
+    em = O.OracleEmulator(X, y, kind=O.KIND_MATERN52, lengthscale=hyper["lengthscale"], outputscale=hyper["outputscale"],
+                          noise=hyper["noise"], weights=hyper["weights"], bias=hyper["bias"], degree=1)
+    Xd, yd = em.X.to(dev), em.y.to(dev)
+    ls, s, nz, w, b = em.ls.to(dev), em.s.to(dev), em.noise.to(dev), em.w.to(dev), em.b.to(dev)
+    K = torch.empty(Xd.shape[0], Xd.shape[0], dtype=torch.float64, device=dev)
+    for lo in range(0, Xd.shape[0], 2048):
+        K[lo:lo + 2048] = O.kernel_from_r2(O.sq_dist(Xd[lo:lo + 2048], Xd, ls, "gpytorch"), em.kind, s)
+    K.diagonal().add_(nz)
+    L = torch.linalg.cholesky(K)
+    del K
+    alpha = torch.cholesky_solve((yd - (Xd @ w + b)).reshape(-1, 1), L).reshape(-1)
+    Xq = torch.from_numpy(em.scx.transform(Xs[:sample_pts])).to(dev)
+
+    def run():
+        for lo in range(0, sample_pts, chunk):
+            xs = Xq[lo:lo + chunk]
+            Ks = O.kernel_from_r2(O.sq_dist(xs, Xd, ls, "gpytorch"), em.kind, s)
+            mean = xs @ w + b + Ks @ alpha
+            V = torch.linalg.solve_triangular(L, Ks.T, upper=False)
+            var = (s - (V * V).sum(0) + nz).clamp_min(1e-10)
+            _ = em.scy.sigma * mean + em.scy.mu, em.scy.sigma * var.sqrt()
+    run()
+    torch.cuda.synchronize()
+    a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    run()
+    e.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(e)
+    return {"value": sample_pts / ms * 1e3, "unit": "points/s", "what": "plain torch float64 on the same B200 "
+            "(cuSOLVER/cuBLAS trsm + unfused pointwise kernels), device-resident", "sample": f"{sample_pts} points, chunks of {chunk}"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -415,6 +453,8 @@ def main():
         line["cpu_baseline"] = {"value": r, "unit": "points/s", "cores": threads, "kind": "port",
                                 "sample": f"first {min(args.cpu_sample, M)} X* points, chunks of 4096, {t_pred:.1f} s "
                                           f"(factorisation {t_fac:.1f} s excluded)"}
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        line["torch_gpu_baseline"] = torch_gpu_predict_rate(X, y, Xs, hyper, dev, min(32768, M))
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
