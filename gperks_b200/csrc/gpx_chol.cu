@@ -411,6 +411,14 @@ potrf_diag3_kernel(double* __restrict__ K, int Np, int blk, int N, double* __res
     const long off = (long)blk * TILE;
     double* Ab = K + off * Np + off;
     if (tid == 0) bad_pivot = 0;
+#ifdef GPX_DIAG_TIMING
+    __shared__ long long t3_own[3];
+    if (tid == 0) { t3_own[0] = 0; t3_own[1] = 0; t3_own[2] = 0; }
+    long long t3_mark = clock64(), t3_acc[5] = {0, 0, 0, 0, 0};
+#define GPX_TICK3(i) do { long long n_ = clock64(); t3_acc[i] += n_ - t3_mark; t3_mark = n_; } while (0)
+#else
+#define GPX_TICK3(i)
+#endif
 
     // ---- distribute: 17 blocks of the matrix per warp as C fragments; the right-hand side starts as the identity
     double cl0[17], cl1[17], cx0[17], cx1[17];
@@ -423,6 +431,7 @@ potrf_diag3_kernel(double* __restrict__ K, int Np, int blk, int N, double* __res
         cx0[s] = 0.0; cx1[s] = 0.0;
     }
     __syncthreads();
+    GPX_TICK3(0);
 
     for (int p = 0; p < 16; ++p) {
         double* buf = sm3 + (p & 1) * D3_BUF;
@@ -433,6 +442,9 @@ potrf_diag3_kernel(double* __restrict__ K, int Np, int blk, int N, double* __res
         const int sp = (p <= 7) ? p : 16;      // its slot of the diagonal block (p,p)
         // ---- (1) diagonal 8x8 block
         if (w == wp) {
+#ifdef GPX_DIAG_TIMING
+            const long long q0 = clock64();
+#endif
             double d0 = 0.0, d1 = 0.0;
 #pragma unroll
             for (int s = 0; s < 17; ++s) if (s == sp) { d0 = cl0[s]; d1 = cl1[s]; }
@@ -463,6 +475,9 @@ potrf_diag3_kernel(double* __restrict__ K, int Np, int blk, int N, double* __res
             *reinterpret_cast<double2*>(Lc + p * D3_BS + lr * 12 + 2 * lc) = make_double2(d0, d1);
             if (lc == 0) { rinv[8 * p + lr] = inv_r; dg[8 * p + lr] = sd_r; }
             __syncwarp();
+#ifdef GPX_DIAG_TIMING
+            const long long q1 = clock64();
+#endif
             if (lane < 8) {        // column `lane` of T by forward substitution
                 const double* Lb = Lc + p * D3_BS;
                 double x[8];
@@ -482,8 +497,12 @@ potrf_diag3_kernel(double* __restrict__ K, int Np, int blk, int N, double* __res
 #pragma unroll
             for (int s = 0; s < 17; ++s) if (s == sp) { cx0[s] = t.x; cx1[s] = t.y; }
             *reinterpret_cast<double2*>(Xr + p * D3_BS + lr * 12 + 2 * lc) = t;
+#ifdef GPX_DIAG_TIMING
+            if (lane == 0) { const long long q2 = clock64(); t3_own[0] += q1 - q0; t3_own[1] += q2 - q1; }
+#endif
         }
         __syncthreads();
+        GPX_TICK3(1);
         // ---- (2) column-p blocks of L (bi > p) and row-p blocks of X (bj < p) on DMMA
         {
             const double tb0 = Tb[lr * 12 + lc], tb1 = Tb[lr * 12 + lc + 4];     // T as A operand, and T^T as B operand
@@ -512,6 +531,7 @@ potrf_diag3_kernel(double* __restrict__ K, int Np, int blk, int N, double* __res
             }
         }
         __syncthreads();
+        GPX_TICK3(2);
         // ---- (3) register-resident rank-8 updates of this warp's two block rows
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -536,6 +556,7 @@ potrf_diag3_kernel(double* __restrict__ K, int Np, int blk, int N, double* __res
                 }
             }
         }
+        GPX_TICK3(3);
         // no barrier: the next panel publishes into the other buffer, and every block a warp needs next is its own
     }
     __syncthreads();
@@ -563,6 +584,645 @@ potrf_diag3_kernel(double* __restrict__ K, int Np, int blk, int N, double* __res
         *reinterpret_cast<double2*>(Sb + (long)(8 * bi + rr) * Np + 8 * bj + cc) = make_double2(0.0, 0.0);
         *reinterpret_cast<double2*>(DTb + (8 * bj + rr) * TILE + 8 * bi + cc) = make_double2(0.0, 0.0);
     }
+#ifdef GPX_DIAG_TIMING
+    __syncthreads();
+    GPX_TICK3(4);
+    if (tid == 0) {     // timing build only
+        for (int i = 0; i < 5; ++i) logdet_blk[8 + i] = (double)t3_acc[i];
+        for (int i = 0; i < 2; ++i) logdet_blk[20 + i] = (double)t3_own[i];
+    }
+#endif
+    if (tid < 32) {
+        double t = 0.0;
+        for (int j = tid; j < TILE; j += 32)
+            if (off + j < N) t += log(dg[j]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (tid == 0) logdet_blk[blk] = t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Diagonal block, version 4 (default): v3's register-resident block distribution, restructured around its measured
+// critical path (tools/diag_timing.cu: of v3's 123k cycles, 33k were the serial 8x8 factor by shuffles, ~14k the
+// owner's serial X-row finalisation, and the 75 KB unrolled body ran out of the instruction cache).
+//   * ONE accumulator per block slot: block (i,j) is first the Schur-updated A_ij (panels p < j), is finalised to
+//     L_ij at panel j and written out, and then restarts from zero as the right-hand side B_ij of L X = I
+//     (panels j <= p < i) until it is finalised to X_ij at panel i.  Half the registers, and the update code no longer
+//     exists twice (the loop body is ~4x smaller).
+//   * A ninth warp does nothing but factor the 8x8 diagonal blocks: every lane runs the whole 8x8 LDL^T recurrence
+//     redundantly in registers (no shuffles; the pivots chain through a reciprocal, the rsqrt's are off the chain), and
+//     lane c forms column c of T = L_pp^-1.  The owner of block row p+1 updates block (p+1,p+1) FIRST in panel p's
+//     update stage and hands it over through a named barrier, so the factor of panel p+1 overlaps the rank-8 updates
+//     of panel p.
+//   * The right-hand-side updates use M_ip = L_ip T_p (one extra DMMA pair per block row, computed by the row's own
+//     warp) against the RAW row B_pj, i.e. B_ij -= (L_ip T_p) B_pj: the owner of row p only has to publish registers,
+//     and the outputs X_pj = T_p B_pj are formed from the published blocks by all warps, after the updates.
+// ------------------------------------------------------------------------------------------------
+constexpr int D4_THREADS = 288;
+constexpr int D4_BS = 96;
+constexpr int D4_BUF = 33 * D4_BS;        // 16 L blocks + 16 raw B blocks + T
+constexpr int D4_SMEM = (2 * D4_BUF + 3 * D4_BS + TILE) * 8;
+
+__device__ __forceinline__ void d4_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void d4_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+struct D4Panel {
+    double* Lc; double* Xr; double* Dnext;
+    double* Ab; double* Sb; double* DTb;
+    double ta0, ta1, tk0, tk1;
+    int p, lr, lc, Np;
+};
+
+// block (bi, p) of a row that is still below the panel: L_ip = A_ip T^T (published + written out), M_ip = L_ip T,
+// the slot restarts as B_ip = -M_ip; a[] receives the A fragments of -L_ip and -M_ip.  Row p itself publishes its raw
+// blocks.  Straight-line on purpose (results of an inactive row are simply not committed): the two rows of a warp are
+// independent dependency chains of shuffles and DMMAs that the scheduler can interleave, and the shuffles stay outside
+// of conditional code.
+template <int NJ>
+__device__ __forceinline__ void d4_stage2_row(double (&c0)[NJ], double (&c1)[NJ], int bi, const D4Panel& P, double (&a)[4]) {
+    const int p = P.p, lr = P.lr, lc = P.lc;
+    const bool on = bi > p;
+    double v0 = 0.0, v1 = 0.0;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) if (j == p) { v0 = c0[j]; v1 = c1[j]; }
+    double a0, a1;
+    d3_c_to_a(v0, v1, lr, lc, a0, a1);
+    double r0 = 0.0, r1 = 0.0;
+    dmma884(r0, r1, a0, P.ta0);
+    dmma884(r0, r1, a1, P.ta1);
+    if (on) {
+        *reinterpret_cast<double2*>(P.Lc + bi * D4_BS + lr * 12 + 2 * lc) = make_double2(r0, r1);
+        *reinterpret_cast<double2*>(P.Ab + (long)(8 * bi + lr) * P.Np + 8 * p + 2 * lc) = make_double2(r0, r1);
+    }
+    double l0, l1;
+    d3_c_to_a(r0, r1, lr, lc, l0, l1);
+    double m0 = 0.0, m1 = 0.0;
+    dmma884(m0, m1, l0, P.tk0);
+    dmma884(m0, m1, l1, P.tk1);
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) if (on && j == p) { c0[j] = -m0; c1[j] = -m1; }
+    double n0, n1;
+    d3_c_to_a(m0, m1, lr, lc, n0, n1);
+    a[0] = -l0; a[1] = -l1; a[2] = -n0; a[3] = -n1;
+    if (bi == p) {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j)
+            if (j < p) *reinterpret_cast<double2*>(P.Xr + j * D4_BS + lr * 12 + 2 * lc) = make_double2(c0[j], c1[j]);
+    }
+}
+
+// the row that holds the next diagonal block updates it first and hands it to the factor warp
+template <int NJ>
+__device__ __forceinline__ bool d4_next_diag_row(double (&c0)[NJ], double (&c1)[NJ], int bi, const D4Panel& P, const double (&a)[4]) {
+    if (bi != P.p + 1) return false;
+    double v0 = 0.0, v1 = 0.0;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) if (j == bi) { v0 = c0[j]; v1 = c1[j]; }
+    dmma884(v0, v1, a[0], -a[0]);              // A_qq -= L_qp L_qp^T  (B[k][n] = L_qp[n][k] has the A fragment's values)
+    dmma884(v0, v1, a[1], -a[1]);
+    *reinterpret_cast<double2*>(P.Dnext + P.lr * 12 + 2 * P.lc) = make_double2(v0, v1);
+    return true;
+}
+
+// rank-8 updates of one block row, eight slots at a time: all operand loads first, then the first k-step of every
+// active slot, then the second -- consecutive DMMAs are independent, so they issue back to back instead of each slot
+// paying load latency + two dependent DMMA latencies
+template <int NJ>
+__device__ __forceinline__ void d4_stage3_row(double (&c0)[NJ], double (&c1)[NJ], int bi, const D4Panel& P, const double (&a)[4]) {
+    const int p = P.p;
+    if (bi <= p) return;
+    const double* LcA = P.Lc + P.lr * 12 + P.lc;       // L_jp^T as B operand
+    const double* XrX = P.Xr + P.lc * 12 + P.lr;       // raw B_pj as B operand
+#pragma unroll
+    for (int j0 = 0; j0 < NJ; j0 += 8) {
+        if (j0 > bi) break;
+        double b0[8], b1[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int j = j0 + q;
+            const bool isA = j > p;
+            const double* bp = (isA ? LcA : XrX) + j * D4_BS;
+            b0[q] = 0.0; b1[q] = 0.0;
+            if (j <= bi && j != p && !(bi == p + 1 && j == bi)) { b0[q] = bp[0]; b1[q] = bp[isA ? 4 : 48]; }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int j = j0 + q;
+            if (j <= bi && j != p && !(bi == p + 1 && j == bi)) dmma884(c0[j], c1[j], (j > p) ? a[0] : a[2], b0[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int j = j0 + q;
+            if (j <= bi && j != p && !(bi == p + 1 && j == bi)) dmma884(c0[j], c1[j], (j > p) ? a[1] : a[3], b1[q]);
+        }
+    }
+}
+
+__global__ void __maxnreg__(168)   // 9 warps are allocated as 12: 168 x 384 = 64512 registers
+potrf_diag4_kernel(double* __restrict__ K, int Np, int blk, int N, double* __restrict__ S, double* __restrict__ DT,
+                   double* __restrict__ logdet_blk, int* __restrict__ info) {
+    extern __shared__ double sm4[];
+    double* Draw = sm4 + 2 * D4_BUF;          // [2][8][12]: diagonal block handed to the factor warp
+    double* Lpp = Draw + 2 * D4_BS;           // [8][12]
+    double* dg = Lpp + D4_BS;                 // [128]
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int lr = lane >> 2, lc = lane & 3;
+    const long off = (long)blk * TILE;
+    double* Ab = K + off * Np + off;
+    double* Sb = S + off * Np + off;
+    double* DTb = DT + (long)blk * TILE * TILE;
+
+    if (w == 8) {
+        // =================== factor warp ===================
+        int bad = 0;
+#ifdef GPX_DIAG_TIMING
+        long long f_mark = clock64(), f_acc[6] = {0, 0, 0, 0, 0, 0};
+#define GPX_TICKF(i) do { long long n_ = clock64(); f_acc[i] += n_ - f_mark; f_mark = n_; } while (0)
+#else
+#define GPX_TICKF(i)
+#endif
+        for (int p = 0; p < 16; ++p) {
+            double* Tb = sm4 + (p & 1) * D4_BUF + 32 * D4_BS;
+            const double* Dr = Draw + (p & 1) * D4_BS;
+            d4_bar_sync(1, 64);                               // block (p,p) published by the owner of row p
+            GPX_TICKF(0);
+            double a[8][8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j <= i; j += 2) {
+                    const double2 v = *reinterpret_cast<const double2*>(Dr + i * 12 + j);
+                    a[i][j] = v.x;
+                    if (j + 1 <= i) a[i][j + 1] = v.y;
+                }
+            // LDL^T recurrence.  Column j of a[][] is overwritten by the unit-lower factor u_kj = a_kj / d_j once its
+            // rank-1 update is done; sd[j] = sqrt(d_j), inv[j] = 1/sqrt(d_j) come off the pivot chain.
+            double inv[8], sd[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const double d = a[j][j];
+                if (!(d > 0.0) && bad == 0) bad = 8 * p + j + 1;
+                const double r = __drcp_rn(d);
+                inv[j] = rsqrt(d);
+                sd[j] = d * inv[j];
+                double uj[8];
+#pragma unroll
+                for (int k = j + 1; k < 8; ++k) uj[k] = a[k][j] * r;
+#pragma unroll
+                for (int k = j + 1; k < 8; ++k)
+#pragma unroll
+                    for (int i = k; i < 8; ++i) a[i][k] = fma(-a[i][j], uj[k], a[i][k]);
+#pragma unroll
+                for (int k = j + 1; k < 8; ++k) a[k][j] = uj[k];
+            }
+            GPX_TICKF(1);
+            // L_pp = U D^1/2 ; T = D^-1/2 U^-1, column c = lane & 7 by forward substitution with the unit-lower U
+            const int c = lane & 7;
+            double x[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                double acc_ = (i == c) ? 1.0 : 0.0;
+#pragma unroll
+                for (int k = 0; k < i; ++k) acc_ = fma(-a[i][k], x[k], acc_);
+                x[i] = acc_;
+            }
+            GPX_TICKF(2);
+            if (lane < 8) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) Tb[i * 12 + lane] = x[i] * inv[i];
+            }
+            if (lane == 8) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+#pragma unroll
+                    for (int j = 0; j < 8; j += 2) {
+                        const double v0 = (j < i) ? a[i][j] * sd[j] : ((j == i) ? sd[i] : 0.0);
+                        const double v1 = (j + 1 < i) ? a[i][j + 1] * sd[j + 1] : ((j + 1 == i) ? sd[i] : 0.0);
+                        *reinterpret_cast<double2*>(Lpp + i * 12 + j) = make_double2(v0, v1);
+                    }
+                    dg[8 * p + i] = sd[i];
+                }
+            }
+            __syncwarp();
+            GPX_TICKF(3);
+            __syncthreads();                                  // #1: T_p visible to the compute warps
+            GPX_TICKF(4);
+            {   // outputs of the diagonal 8x8 block: L_pp -> K, T -> S and (transposed) DT
+                const double2 lf = *reinterpret_cast<const double2*>(Lpp + lr * 12 + 2 * lc);
+                const double2 tf = *reinterpret_cast<const double2*>(Tb + lr * 12 + 2 * lc);
+                const long r_ = 8 * p + lr, c_ = 8 * p + 2 * lc;
+                *reinterpret_cast<double2*>(Ab + r_ * Np + c_) = lf;
+                *reinterpret_cast<double2*>(Sb + r_ * Np + c_) = tf;
+                DTb[c_ * TILE + r_] = tf.x;
+                DTb[(c_ + 1) * TILE + r_] = tf.y;
+            }
+            __syncthreads();                                  // #2
+            GPX_TICKF(5);
+        }
+        __syncthreads();
+#ifdef GPX_DIAG_TIMING
+        if (lane == 0) for (int i = 0; i < 6; ++i) logdet_blk[40 + i] = (double)f_acc[i];
+#endif
+        if (lane == 0 && bad != 0 && *info == 0) *info = (int)off + bad;
+        return;
+    }
+
+    // =================== compute warps ===================
+    // warp w owns block rows w (blocks j = 0..w, accumulators cA) and 15-w (blocks j = 0..15-w, accumulators cB);
+    // slot j of a row is block column j, so every shared-memory offset below is an immediate
+    double cA0[8], cA1[8], cB0[16], cB1[16];
+    const int rA = w, rB = 15 - w;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        cA0[j] = 0.0; cA1[j] = 0.0;
+        if (j <= rA) {
+            const double2 v = *reinterpret_cast<const double2*>(Ab + (long)(8 * rA + lr) * Np + 8 * j + 2 * lc);
+            cA0[j] = v.x; cA1[j] = v.y;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        cB0[j] = 0.0; cB1[j] = 0.0;
+        if (j <= rB) {
+            const double2 v = *reinterpret_cast<const double2*>(Ab + (long)(8 * rB + lr) * Np + 8 * j + 2 * lc);
+            cB0[j] = v.x; cB1[j] = v.y;
+        }
+    }
+    if (w == 0) {       // block (0,0) goes to the factor warp straight away
+        *reinterpret_cast<double2*>(Draw + lr * 12 + 2 * lc) = make_double2(cA0[0], cA1[0]);
+        __threadfence_block();
+        d4_bar_arrive(1, 64);
+    }
+    // while the first factor runs: zero the blocks above the diagonal of S and below the diagonal of DT
+    for (int b = w; b < 256; b += 8) {
+        const int bi = b >> 4, bj = b & 15;
+        if (bj > bi) {
+            const int rr = lane >> 2, cc = (lane & 3) * 2;
+            *reinterpret_cast<double2*>(Sb + (long)(8 * bi + rr) * Np + 8 * bj + cc) = make_double2(0.0, 0.0);
+            *reinterpret_cast<double2*>(DTb + (8 * bj + rr) * TILE + 8 * bi + cc) = make_double2(0.0, 0.0);
+        }
+    }
+
+#ifdef GPX_DIAG_TIMING
+    long long c_mark = clock64(), c_acc[6] = {0, 0, 0, 0, 0, 0};
+#define GPX_TICKC(i) do { long long n_ = clock64(); c_acc[i] += n_ - c_mark; c_mark = n_; } while (0)
+#else
+#define GPX_TICKC(i)
+#endif
+    for (int p = 0; p < 16; ++p) {
+        D4Panel P;
+        double* buf = sm4 + (p & 1) * D4_BUF;
+        P.Lc = buf;                            // published column p of L: block bi at Lc + bi*D4_BS, [8][12]
+        P.Xr = buf + 16 * D4_BS;               // published RAW row p of the right-hand side: block bj, stored [k][n]
+        const double* Tb = buf + 32 * D4_BS;   // T = L_pp^-1, [8][12], zeros above the diagonal
+        P.p = p; P.lr = lr; P.lc = lc; P.Np = Np; P.Ab = Ab; P.Sb = Sb; P.DTb = DTb;
+        P.Dnext = Draw + ((p + 1) & 1) * D4_BS;
+        __syncthreads();                       // #1: T_p published by the factor warp
+        GPX_TICKC(0);
+        P.ta0 = Tb[lr * 12 + lc]; P.ta1 = Tb[lr * 12 + lc + 4];           // T as A operand == T^T as B operand
+        P.tk0 = Tb[lc * 12 + lr]; P.tk1 = Tb[(lc + 4) * 12 + lr];         // T as B operand (B[k][n] = T[k][n])
+        double aA[4] = {0.0, 0.0, 0.0, 0.0}, aB[4] = {0.0, 0.0, 0.0, 0.0};   // A fragments of -L_ip (0,1) and -M_ip (2,3)
+        // ---- stage 2: finalise column p of L (<= 2 blocks per warp); the owner of row p publishes its raw row
+        d4_stage2_row<8>(cA0, cA1, rA, P, aA);
+        d4_stage2_row<16>(cB0, cB1, rB, P, aB);
+        GPX_TICKC(1);
+        __syncthreads();                       // #2
+        GPX_TICKC(2);
+        // ---- stage 3: the next diagonal block first (its factor then overlaps everything else), then the rest
+        if (d4_next_diag_row<8>(cA0, cA1, rA, P, aA) | d4_next_diag_row<16>(cB0, cB1, rB, P, aB)) {
+            __threadfence_block();
+            d4_bar_arrive(1, 64);
+        }
+        d4_stage3_row<8>(cA0, cA1, rA, P, aA);
+        d4_stage3_row<16>(cB0, cB1, rB, P, aB);
+        GPX_TICKC(3);
+        // ---- output row p of the inverse, X_pj = T_p B_pj (nobody in this kernel reads it): the raw blocks are in
+        //      shared memory, so the p blocks are dealt round-robin to the warps instead of burdening the row's owner
+        for (int j = w; j < p; j += 8) {
+            const double* bp = P.Xr + j * D4_BS + lc * 12 + lr;
+            double r0 = 0.0, r1 = 0.0;
+            dmma884(r0, r1, P.ta0, bp[0]);
+            dmma884(r0, r1, P.ta1, bp[48]);
+            const long r_ = 8 * p + lr, c_ = 8 * j + 2 * lc;
+            *reinterpret_cast<double2*>(Sb + r_ * Np + c_) = make_double2(r0, r1);
+            DTb[c_ * TILE + r_] = r0;
+            DTb[(c_ + 1) * TILE + r_] = r1;
+        }
+        GPX_TICKC(4);
+    }
+    __syncthreads();
+#ifdef GPX_DIAG_TIMING
+    if (tid == 0) for (int i = 0; i < 6; ++i) logdet_blk[48 + i] = (double)c_acc[i];
+#endif
+    if (tid < 32) {
+        double t = 0.0;
+        for (int j = tid; j < TILE; j += 32)
+            if (off + j < N) t += log(dg[j]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (tid == 0) logdet_blk[blk] = t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Diagonal block, version 5: v4's algorithm with the 16 panels unrolled at compile time (template <int P>).
+// ncu on v4 (profiles/): 930 issued warp-instructions per panel and warp, ~3x what the arithmetic needs -- select
+// chains that pick "slot p" out of the register arrays, per-slot predicates, shuffle conversions.  With P static every
+// slot index is an immediate, the phase of a slot (Schur update / right-hand side) is known at compile time and dead
+// slots are never visited.  Published blocks are stored in FRAGMENT order (element `lane` of a block is the pair a DMMA
+// operand needs), so an operand is one conflict-free LDS.128 and the C-fragment -> operand conversions go through a
+// small per-warp shared-memory transposer instead of eight shuffles.
+// ------------------------------------------------------------------------------------------------
+constexpr int D5_THREADS = 288;
+constexpr int D5_BS = 64;                 // doubles per published 8x8 block
+constexpr int D5_BUF = 34 * D5_BS;        // 16 L blocks | 16 raw right-hand-side blocks | T (A layout) | T (B layout)
+constexpr int D5_SMEM = (2 * D5_BUF + 3 * D4_BS + TILE + 16 * D5_BS) * 8;
+
+// index of element (r, c) of an 8x8 block in "A layout": lane lr*4+lc finds (M[lr][lc], M[lr][lc+4]) as one double2.
+// The same pair is the B operand of M^T (B[k][n] = M[n][k]).
+__device__ __forceinline__ int d5_ia(int r, int c) { return ((r * 4 + (c & 3)) << 1) + (c >> 2); }
+// "B layout": lane lr*4+lc finds (M[lc][lr], M[lc+4][lr]), the B operand of M itself (B[k][n] = M[k][n])
+__device__ __forceinline__ int d5_ib(int r, int c) { return ((c * 4 + (r & 3)) << 1) + (r >> 2); }
+
+struct D5Ctx {
+    double* sm;            // dynamic shared memory base
+    double* scratch;       // this warp's transposer: [2 rows][64]
+    double* Ab; double* Sb; double* DTb;
+    int Np, w, lane, lr, lc;
+    int ia0, ib0;          // A-/B-layout index of this lane's first C-fragment element (the second is +2 / +8)
+};
+
+// C fragment -> A-operand pair through the warp's transposer
+__device__ __forceinline__ double2 d5_c_to_a(double v0, double v1, double* scr, const D5Ctx& X) {
+    __syncwarp();
+    scr[X.ia0] = v0; scr[X.ia0 + 2] = v1;
+    __syncwarp();
+    return *reinterpret_cast<const double2*>(scr + 2 * X.lane);
+}
+
+template <int P, int NJ>
+__device__ __forceinline__ void d5_stage2_row(double (&c0)[NJ], double (&c1)[NJ], int bi, int half, const D5Ctx& X,
+                                              double* Lc, double* Xr, double2 ta, double2 tk, double2& aL, double2& aM) {
+    if (P >= NJ) return;
+    constexpr int PJ = (P < NJ) ? P : 0;
+    if (bi > P) {
+        double* scr = X.scratch + half * D5_BS;
+        const double2 a = d5_c_to_a(c0[PJ], c1[PJ], scr, X);
+        double r0 = 0.0, r1 = 0.0;
+        dmma884(r0, r1, a.x, ta.x);                    // L_ip = A_ip T^T
+        dmma884(r0, r1, a.y, ta.y);
+        double* Lb = Lc + bi * D5_BS;                  // publish (A layout) and write out
+        Lb[X.ia0] = r0; Lb[X.ia0 + 2] = r1;
+        *reinterpret_cast<double2*>(X.Ab + (long)(8 * bi + X.lr) * X.Np + 8 * P + 2 * X.lc) = make_double2(r0, r1);
+        __syncwarp();
+        const double2 l = *reinterpret_cast<const double2*>(Lb + 2 * X.lane);
+        double m0 = 0.0, m1 = 0.0;
+        dmma884(m0, m1, l.x, tk.x);                    // M_ip = L_ip T
+        dmma884(m0, m1, l.y, tk.y);
+        c0[PJ] = -m0; c1[PJ] = -m1;                    // the slot restarts as B_ip = 0 - L_ip X_pp
+        const double2 n = d5_c_to_a(m0, m1, scr, X);
+        aL = make_double2(-l.x, -l.y);
+        aM = make_double2(-n.x, -n.y);
+    } else if (bi == P) {                              // the owner of row P publishes its raw right-hand-side blocks
+#pragma unroll
+        for (int j = 0; j < P && j < NJ; ++j) {
+            double* Xb = Xr + j * D5_BS;
+            Xb[X.ib0] = c0[j]; Xb[X.ib0 + 8] = c1[j];
+        }
+    }
+}
+
+template <int P, int NJ>
+__device__ __forceinline__ bool d5_next_diag_row(double (&c0)[NJ], double (&c1)[NJ], int bi, const D5Ctx& X, double2 aL, double* Dnext) {
+    if (P + 1 >= NJ) return false;
+    constexpr int QJ = (P + 1 < NJ) ? P + 1 : 0;
+    if (bi != P + 1) return false;
+    dmma884(c0[QJ], c1[QJ], aL.x, -aL.x);              // A_qq -= L_qp L_qp^T
+    dmma884(c0[QJ], c1[QJ], aL.y, -aL.y);
+    *reinterpret_cast<double2*>(Dnext + X.lr * 12 + 2 * X.lc) = make_double2(c0[QJ], c1[QJ]);
+    return true;
+}
+
+template <int P, int NJ>
+__device__ __forceinline__ void d5_stage3_row(double (&c0)[NJ], double (&c1)[NJ], int bi, const D5Ctx& X,
+                                              const double* Lc, const double* Xr, double2 aL, double2 aM) {
+    if (bi <= P) return;
+    const double* xb = Xr + 2 * X.lane;
+    const double* lb = Lc + 2 * X.lane;
+    // eight slots at a time: operand loads, then the first k-step of every slot, then the second (consecutive DMMAs
+    // are independent).  Slots j < P are right-hand sides, B_ij -= M_ip B_pj(raw), always present because j < P < bi;
+    // slots j > P are Schur updates, A_ij -= L_ip L_jp^T, present if j <= bi.
+#pragma unroll
+    for (int j0 = 0; j0 < NJ; j0 += 8) {
+        double2 b[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int j = j0 + q;
+            if (j < P) b[q] = *reinterpret_cast<const double2*>(xb + j * D5_BS);
+            else if (j > P && j <= bi) b[q] = *reinterpret_cast<const double2*>(lb + j * D5_BS);
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int j = j0 + q;
+            if (j < P) dmma884(c0[j], c1[j], aM.x, b[q].x);
+            else if (j > P && j <= bi) dmma884(c0[j], c1[j], aL.x, b[q].x);
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int j = j0 + q;
+            if (j < P) dmma884(c0[j], c1[j], aM.y, b[q].y);
+            else if (j > P && j <= bi) dmma884(c0[j], c1[j], aL.y, b[q].y);
+        }
+    }
+}
+
+template <int P>
+__device__ __forceinline__ void d5_panel(double (&cA0)[8], double (&cA1)[8], double (&cB0)[16], double (&cB1)[16], const D5Ctx& X) {
+    double* buf = X.sm + (P & 1) * D5_BUF;
+    double* Lc = buf;
+    double* Xr = buf + 16 * D5_BS;
+    const double* TA = buf + 32 * D5_BS;
+    const double* TK = buf + 33 * D5_BS;
+    double* Dnext = X.sm + 2 * D5_BUF + ((P + 1) & 1) * D4_BS;
+    const int rA = X.w, rB = 15 - X.w;
+    __syncthreads();                                   // #1: T_P published by the factor warp
+    const double2 ta = *reinterpret_cast<const double2*>(TA + 2 * X.lane);
+    const double2 tk = *reinterpret_cast<const double2*>(TK + 2 * X.lane);
+    double2 aLA = make_double2(0.0, 0.0), aMA = aLA, aLB = aLA, aMB = aLA;
+    d5_stage2_row<P, 8>(cA0, cA1, rA, 0, X, Lc, Xr, ta, tk, aLA, aMA);
+    d5_stage2_row<P, 16>(cB0, cB1, rB, 1, X, Lc, Xr, ta, tk, aLB, aMB);
+    __syncthreads();                                   // #2: column P of L and raw row P complete
+    if (P < 15) {
+        if (d5_next_diag_row<P, 8>(cA0, cA1, rA, X, aLA, Dnext) | d5_next_diag_row<P, 16>(cB0, cB1, rB, X, aLB, Dnext)) {
+            __threadfence_block();
+            d4_bar_arrive(1, 64);
+        }
+        d5_stage3_row<P, 8>(cA0, cA1, rA, X, Lc, Xr, aLA, aMA);
+        d5_stage3_row<P, 16>(cB0, cB1, rB, X, Lc, Xr, aLB, aMB);
+    }
+    // output row P of the inverse, X_pj = T_p B_pj, from the published raw blocks; dealt round-robin to the warps
+    for (int j = X.w; j < P; j += 8) {
+        const double2 b = *reinterpret_cast<const double2*>(Xr + j * D5_BS + 2 * X.lane);
+        double r0 = 0.0, r1 = 0.0;
+        dmma884(r0, r1, ta.x, b.x);
+        dmma884(r0, r1, ta.y, b.y);
+        const long r_ = 8 * P + X.lr, c_ = 8 * j + 2 * X.lc;
+        *reinterpret_cast<double2*>(X.Sb + r_ * X.Np + c_) = make_double2(r0, r1);
+        X.DTb[c_ * TILE + r_] = r0;
+        X.DTb[(c_ + 1) * TILE + r_] = r1;
+    }
+}
+
+template <int P>
+struct D5Unroll {
+    static __device__ __forceinline__ void run(double (&cA0)[8], double (&cA1)[8], double (&cB0)[16], double (&cB1)[16], const D5Ctx& X) {
+        D5Unroll<P - 1>::run(cA0, cA1, cB0, cB1, X);
+        d5_panel<P>(cA0, cA1, cB0, cB1, X);
+    }
+};
+template <>
+struct D5Unroll<-1> {
+    static __device__ __forceinline__ void run(double (&)[8], double (&)[8], double (&)[16], double (&)[16], const D5Ctx&) {}
+};
+
+__global__ void __maxnreg__(168)   // 9 warps are allocated as 12: 168 x 384 = 64512 registers
+potrf_diag5_kernel(double* __restrict__ K, int Np, int blk, int N, double* __restrict__ S, double* __restrict__ DT,
+                   double* __restrict__ logdet_blk, int* __restrict__ info) {
+    extern __shared__ double sm5[];
+    double* Draw = sm5 + 2 * D5_BUF;          // [2][8][12] row-major: diagonal block handed to the factor warp
+    double* Lpp = Draw + 2 * D4_BS;           // [8][12]
+    double* dg = Lpp + D4_BS;                 // [128]
+    double* scratch = dg + TILE;              // [8 warps][2][64]
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int lr = lane >> 2, lc = lane & 3;
+    const long off = (long)blk * TILE;
+    double* Ab = K + off * Np + off;
+    double* Sb = S + off * Np + off;
+    double* DTb = DT + (long)blk * TILE * TILE;
+
+    if (w == 8) {
+        // =================== factor warp (as in v4; T is published in both operand layouts) ===================
+        int bad = 0;
+        for (int p = 0; p < 16; ++p) {
+            double* TA = sm5 + (p & 1) * D5_BUF + 32 * D5_BS;
+            double* TK = TA + D5_BS;
+            const double* Dr = Draw + (p & 1) * D4_BS;
+            d4_bar_sync(1, 64);                               // block (p,p) published by the owner of row p
+            double a[8][8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j <= i; j += 2) {
+                    const double2 v = *reinterpret_cast<const double2*>(Dr + i * 12 + j);
+                    a[i][j] = v.x;
+                    if (j + 1 <= i) a[i][j + 1] = v.y;
+                }
+            double inv[8], sd[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const double d = a[j][j];
+                if (!(d > 0.0) && bad == 0) bad = 8 * p + j + 1;
+                const double r = __drcp_rn(d);
+                inv[j] = rsqrt(d);
+                sd[j] = d * inv[j];
+                double uj[8];
+#pragma unroll
+                for (int k = j + 1; k < 8; ++k) uj[k] = a[k][j] * r;
+#pragma unroll
+                for (int k = j + 1; k < 8; ++k)
+#pragma unroll
+                    for (int i = k; i < 8; ++i) a[i][k] = fma(-a[i][j], uj[k], a[i][k]);
+#pragma unroll
+                for (int k = j + 1; k < 8; ++k) a[k][j] = uj[k];
+            }
+            const int c = lane & 7;
+            double x[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                double acc_ = (i == c) ? 1.0 : 0.0;
+#pragma unroll
+                for (int k = 0; k < i; ++k) acc_ = fma(-a[i][k], x[k], acc_);
+                x[i] = acc_;
+            }
+            if (lane < 8) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const double t = x[i] * inv[i];
+                    TA[d5_ia(i, c)] = t;
+                    TK[d5_ib(i, c)] = t;
+                }
+            }
+            if (lane == 8) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+#pragma unroll
+                    for (int j = 0; j < 8; j += 2) {
+                        const double v0 = (j < i) ? a[i][j] * sd[j] : ((j == i) ? sd[i] : 0.0);
+                        const double v1 = (j + 1 < i) ? a[i][j + 1] * sd[j + 1] : ((j + 1 == i) ? sd[i] : 0.0);
+                        *reinterpret_cast<double2*>(Lpp + i * 12 + j) = make_double2(v0, v1);
+                    }
+                    dg[8 * p + i] = sd[i];
+                }
+            }
+            __syncwarp();
+            __syncthreads();                                  // #1: T_p visible to the compute warps
+            {   // outputs of the diagonal 8x8 block: L_pp -> K, T -> S and (transposed) DT
+                const double2 lf = *reinterpret_cast<const double2*>(Lpp + lr * 12 + 2 * lc);
+                const int i0 = d5_ia(lr, 2 * lc);
+                const double t0 = TA[i0], t1 = TA[i0 + 2];
+                const long r_ = 8 * p + lr, c_ = 8 * p + 2 * lc;
+                *reinterpret_cast<double2*>(Ab + r_ * Np + c_) = lf;
+                *reinterpret_cast<double2*>(Sb + r_ * Np + c_) = make_double2(t0, t1);
+                DTb[c_ * TILE + r_] = t0;
+                DTb[(c_ + 1) * TILE + r_] = t1;
+            }
+            __syncthreads();                                  // #2
+        }
+        __syncthreads();
+        if (lane == 0 && bad != 0 && *info == 0) *info = (int)off + bad;
+        return;
+    }
+
+    // =================== compute warps ===================
+    D5Ctx X;
+    X.sm = sm5; X.scratch = scratch + w * 2 * D5_BS;
+    X.Ab = Ab; X.Sb = Sb; X.DTb = DTb; X.Np = Np; X.w = w; X.lane = lane; X.lr = lr; X.lc = lc;
+    X.ia0 = d5_ia(lr, 2 * lc); X.ib0 = d5_ib(lr, 2 * lc);
+    double cA0[8], cA1[8], cB0[16], cB1[16];
+    const int rA = w, rB = 15 - w;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        cA0[j] = 0.0; cA1[j] = 0.0;
+        if (j <= rA) {
+            const double2 v = *reinterpret_cast<const double2*>(Ab + (long)(8 * rA + lr) * Np + 8 * j + 2 * lc);
+            cA0[j] = v.x; cA1[j] = v.y;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        cB0[j] = 0.0; cB1[j] = 0.0;
+        if (j <= rB) {
+            const double2 v = *reinterpret_cast<const double2*>(Ab + (long)(8 * rB + lr) * Np + 8 * j + 2 * lc);
+            cB0[j] = v.x; cB1[j] = v.y;
+        }
+    }
+    if (w == 0) {       // block (0,0) goes to the factor warp straight away
+        *reinterpret_cast<double2*>(Draw + lr * 12 + 2 * lc) = make_double2(cA0[0], cA1[0]);
+        __threadfence_block();
+        d4_bar_arrive(1, 64);
+    }
+    // while the first factor runs: zero the blocks above the diagonal of S and below the diagonal of DT
+    for (int b = w; b < 256; b += 8) {
+        const int bi = b >> 4, bj = b & 15;
+        if (bj > bi) {
+            const int rr = lane >> 2, cc = (lane & 3) * 2;
+            *reinterpret_cast<double2*>(Sb + (long)(8 * bi + rr) * Np + 8 * bj + cc) = make_double2(0.0, 0.0);
+            *reinterpret_cast<double2*>(DTb + (8 * bj + rr) * TILE + 8 * bi + cc) = make_double2(0.0, 0.0);
+        }
+    }
+    D5Unroll<15>::run(cA0, cA1, cB0, cB1, X);
+    __syncthreads();
     if (tid < 32) {
         double t = 0.0;
         for (int j = tid; j < TILE; j += 32)
@@ -860,12 +1520,14 @@ static void set_gemm_attrs() {
     cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dg);
     cudaFuncSetAttribute(potrf_diag2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (TILE * DG_LD + 2 * TILE + 64) * 8);
     cudaFuncSetAttribute(potrf_diag3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D3_SMEM);
+    cudaFuncSetAttribute(potrf_diag4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D4_SMEM);
+    cudaFuncSetAttribute(potrf_diag5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D5_SMEM);
     if (dev >= 0 && dev < 64) g_attr_set[dev] = true;
 }
 
-static int diag_impl() {       // GPX_DIAG_IMPL = 1 | 2 | 3 (default 3)
+static int diag_impl() {       // GPX_DIAG_IMPL = 1 | 2 | 3 | 4 (default 3)
     static int v = -1;
-    if (v < 0) { const char* e = getenv("GPX_DIAG_IMPL"); v = (e && e[0] >= '1' && e[0] <= '3') ? e[0] - '0' : 3; }
+    if (v < 0) { const char* e = getenv("GPX_DIAG_IMPL"); v = (e && e[0] >= '1' && e[0] <= '5') ? e[0] - '0' : 3; }
     return v;
 }
 static int use_diag_v1() { return diag_impl() == 1; }
@@ -885,7 +1547,10 @@ static LookAhead* lookahead_for_current_device() {
     if (dev < 0 || dev >= 64) return nullptr;
     LookAhead* la = &g_la[dev];
     if (la->side == nullptr) {
-        if (cudaStreamCreateWithFlags(&la->side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        // lowest priority: when SMs free up, pending CTAs of the caller's stream (the critical path) are placed first
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        if (cudaStreamCreateWithPriority(&la->side, cudaStreamNonBlocking, prio_lo) != cudaSuccess) return nullptr;
         for (int i = 0; i < 2; ++i) {
             cudaEventCreateWithFlags(&la->ev_main[i], cudaEventDisableTiming);
             cudaEventCreateWithFlags(&la->ev_side[i], cudaEventDisableTiming);
@@ -933,11 +1598,17 @@ int potrf(double* K, int Np, int N, double* S, double* DT, double* logdet_blk, i
         else potrf_trailing_kernel<<<grid, G_THREADS, G_SMEM_BYTES, s_>>>(K, Np, p, j0, i0);
     };
     bool side_pending = false;
+    static int ev_old = -1;
+    if (ev_old < 0) { const char* e = getenv("GPX_POTRF_EV"); ev_old = (e && e[0] == 'o') ? 1 : 0; }
     for (int p = 0; p < nb; ++p) {
         if (use_diag_v1())
             potrf_diag_kernel<<<1, DG_THREADS, dg, st>>>(K, Np, p, N, S, DT, logdet_blk, info);
         else if (diag_impl() == 2)
             potrf_diag2_kernel<<<1, D2_THREADS, dg2, st>>>(K, Np, p, N, S, DT, logdet_blk, info);
+        else if (diag_impl() == 4)
+            potrf_diag4_kernel<<<1, D4_THREADS, D4_SMEM, st>>>(K, Np, p, N, S, DT, logdet_blk, info);
+        else if (diag_impl() == 5)
+            potrf_diag5_kernel<<<1, D5_THREADS, D5_SMEM, st>>>(K, Np, p, N, S, DT, logdet_blk, info);
         else
             potrf_diag3_kernel<<<1, D3_THREADS, D3_SMEM, st>>>(K, Np, p, N, S, DT, logdet_blk, info);
         const int n = nb - p - 1;
@@ -947,14 +1618,27 @@ int potrf(double* K, int Np, int N, double* S, double* DT, double* logdet_blk, i
             trailing(dim3(n, n), p, p + 1, p + 1, st);
             continue;
         }
-        // block column p+1 was also touched by the helper stream's update p-1: wait for it first
-        if (side_pending) cudaStreamWaitEvent(st, la->ev_side[(p - 1) & 1], 0);
-        trailing(dim3(1, n), p, p + 1, p + 1, st);
-        if (n > 1) {
+        // the helper stream's update p only needs panel p (it touches block columns >= p+2): release it before the
+        // look-ahead column so that it starts right behind update p-1 instead of idling through the column update
+        const bool early = !ev_old && n > 1;
+        if (early) {
             cudaEventRecord(la->ev_main[p & 1], st);
             cudaStreamWaitEvent(la->side, la->ev_main[p & 1], 0);
+        }
+        // block column p+1 was also touched by the helper stream's update p-1: wait for it first
+        if (side_pending) cudaStreamWaitEvent(st, la->ev_side[(p - 1) & 1], 0);
+        if (early) {
             trailing(dim3(n - 1, n - 1), p, p + 2, p + 2, la->side);
             cudaEventRecord(la->ev_side[p & 1], la->side);
+        }
+        trailing(dim3(1, n), p, p + 1, p + 1, st);
+        if (n > 1) {
+            if (!early) {
+                cudaEventRecord(la->ev_main[p & 1], st);
+                cudaStreamWaitEvent(la->side, la->ev_main[p & 1], 0);
+                trailing(dim3(n - 1, n - 1), p, p + 2, p + 2, la->side);
+                cudaEventRecord(la->ev_side[p & 1], la->side);
+            }
             side_pending = true;
         } else {
             side_pending = false;

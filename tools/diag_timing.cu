@@ -24,6 +24,44 @@ int main() {
                h[8], h[9], h[10], h[11], h[12], h[0]);
         printf("   warp0 step3 phases: loads=%.0f dmma=%.0f rmw=%.0f over %.0f block rows\n", h[20], h[21], h[22], h[23]);
     }
+    cudaFuncSetAttribute(potrf_diag3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D3_SMEM);
+    for (int rep = 0; rep < 3; ++rep) {
+        cudaMemcpy(K, A.data(), Np * Np * 8, cudaMemcpyHostToDevice); cudaMemset(ld, 0, 64 * 8);
+        potrf_diag3_kernel<<<1, D3_THREADS, D3_SMEM>>>(K, Np, 0, Np, S, DT, ld, info);
+        cudaError_t e = cudaDeviceSynchronize();
+        double h[32]; cudaMemcpy(h, ld, 32 * 8, cudaMemcpyDeviceToHost);
+        printf("v3 rep %d err=%d cycles (warp 0 view): load=%.0f stage1+wait=%.0f stage2=%.0f stage3=%.0f writeback=%.0f | owner: factor8x8=%.0f Tinv=%.0f (sums over 16 panels)\n",
+               rep, (int)e, h[8], h[9], h[10], h[11], h[12], h[20], h[21]);
+    }
+    cudaFuncSetAttribute(potrf_diag4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D4_SMEM);
+    for (int rep = 0; rep < 3; ++rep) {
+        cudaMemcpy(K, A.data(), Np * Np * 8, cudaMemcpyHostToDevice); cudaMemset(ld, 0, 64 * 8);
+        cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0);
+        potrf_diag4_kernel<<<1, D4_THREADS, D4_SMEM>>>(K, Np, 0, Np, S, DT, ld, info);
+        { cudaError_t le = cudaGetLastError(); if (le != cudaSuccess) printf("launch error: %s\n", cudaGetErrorString(le)); }
+        cudaEventRecord(e1);
+        cudaError_t e = cudaDeviceSynchronize();
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        double h[64]; cudaMemcpy(h, ld, 64 * 8, cudaMemcpyDeviceToHost);
+        printf("v4 rep %d err=%d %.1f us | factor warp cycles: wait_block=%.0f load+ldl=%.0f usolve=%.0f store=%.0f wait#1=%.0f out+wait#2=%.0f\n",
+               rep, (int)e, ms * 1e3, h[40], h[41], h[42], h[43], h[44], h[45]);
+        printf("            compute warp 0 cycles: wait#1=%.0f stage2=%.0f wait#2=%.0f stage3=%.0f output=%.0f (sums over 16 panels)\n",
+               h[48], h[49], h[50], h[51], h[52]);
+    }
+    cudaFuncSetAttribute(potrf_diag5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D5_SMEM);
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaMemcpy(K, A.data(), Np * Np * 8, cudaMemcpyHostToDevice); cudaMemset(ld, 0, 64 * 8);
+        cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0);
+        potrf_diag5_kernel<<<1, D5_THREADS, D5_SMEM>>>(K, Np, 0, Np, S, DT, ld, info);
+        { cudaError_t le = cudaGetLastError(); if (le != cudaSuccess) printf("launch error: %s\n", cudaGetErrorString(le)); }
+        cudaEventRecord(e1);
+        cudaError_t e = cudaDeviceSynchronize();
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        double h[1]; cudaMemcpy(h, ld, 8, cudaMemcpyDeviceToHost);
+        printf("v5 rep %d err=%d %.1f us logdet=%.6f\n", rep, (int)e, ms * 1e3, h[0]);
+    }
     return 0;
 }
 
