@@ -934,7 +934,7 @@ potrf_diag4_kernel(double* __restrict__ K, int Np, int blk, int N, double* __res
 // operand needs), so an operand is one conflict-free LDS.128 and the C-fragment -> operand conversions go through a
 // small per-warp shared-memory transposer instead of eight shuffles.
 // ------------------------------------------------------------------------------------------------
-constexpr int D5_THREADS = 288;
+constexpr int D5_THREADS = 384;           // 12 warps: warp 0 factors alone on its scheduler, 8 compute warps on the other three
 constexpr int D5_BS = 64;                 // doubles per published 8x8 block
 constexpr int D5_BUF = 34 * D5_BS;        // 16 L blocks | 16 raw right-hand-side blocks | T (A layout) | T (B layout)
 constexpr int D5_SMEM = (2 * D5_BUF + 3 * D4_BS + TILE + 16 * D5_BS) * 8;
@@ -945,13 +945,41 @@ __device__ __forceinline__ int d5_ia(int r, int c) { return ((r * 4 + (c & 3)) <
 // "B layout": lane lr*4+lc finds (M[lc][lr], M[lc+4][lr]), the B operand of M itself (B[k][n] = M[k][n])
 __device__ __forceinline__ int d5_ib(int r, int c) { return ((c * 4 + (r & 3)) << 1) + (r >> 2); }
 
+// Reciprocal and reciprocal square root of a positive, normal double without the library's special-case branches: the
+// hardware seed (MUFU.RCP64H / RSQ64H, ~2^-20) followed by one third-order step (error e^3) and, for the rsqrt (off the
+// pivot chain), a final Newton step.  Branch-free, so the whole 8x8 recurrence is one basic block whose independent
+// chains the scheduler interleaves.  Non-positive pivots are reported through `info` before these are used.
+__device__ __forceinline__ double d5_rcp(double d) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    const double e = fma(-d, r, 1.0);
+    const double e2 = fma(e, e, e);
+    return fma(e2, r, r);
+}
+__device__ __forceinline__ double d5_rsqrt(double d) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    const double e = fma(-(d * y), y, 1.0);                 // 1 - d y^2
+    y = fma(y * e, fma(0.375, e, 0.5), y);                  // y (1 + e/2 + 3 e^2/8)
+    const double e2 = fma(-(d * y), y, 1.0);
+    return fma(0.5 * y, e2, y);
+}
+
 struct D5Ctx {
     double* sm;            // dynamic shared memory base
     double* scratch;       // this warp's transposer: [2 rows][64]
     double* Ab; double* Sb; double* DTb;
     int Np, w, lane, lr, lc;
     int ia0, ib0;          // A-/B-layout index of this lane's first C-fragment element (the second is +2 / +8)
+#ifdef GPX_DIAG_TIMING
+    long long* tstat;      // shared: [0] = mark, [1..] = accumulated cycles per phase (thread 0 only)
+#endif
 };
+#ifdef GPX_DIAG_TIMING
+#define GPX_TICK5(X, i) do { if ((X).w == 0 && (X).lane == 0) { long long n_ = clock64(); (X).tstat[1 + (i)] += n_ - (X).tstat[0]; (X).tstat[0] = n_; } } while (0)
+#else
+#define GPX_TICK5(X, i)
+#endif
 
 // C fragment -> A-operand pair through the warp's transposer
 __device__ __forceinline__ double2 d5_c_to_a(double v0, double v1, double* scr, const D5Ctx& X) {
@@ -961,35 +989,14 @@ __device__ __forceinline__ double2 d5_c_to_a(double v0, double v1, double* scr, 
     return *reinterpret_cast<const double2*>(scr + 2 * X.lane);
 }
 
+// the owner of row P publishes its raw right-hand-side blocks (B layout)
 template <int P, int NJ>
-__device__ __forceinline__ void d5_stage2_row(double (&c0)[NJ], double (&c1)[NJ], int bi, int half, const D5Ctx& X,
-                                              double* Lc, double* Xr, double2 ta, double2 tk, double2& aL, double2& aM) {
-    if (P >= NJ) return;
-    constexpr int PJ = (P < NJ) ? P : 0;
-    if (bi > P) {
-        double* scr = X.scratch + half * D5_BS;
-        const double2 a = d5_c_to_a(c0[PJ], c1[PJ], scr, X);
-        double r0 = 0.0, r1 = 0.0;
-        dmma884(r0, r1, a.x, ta.x);                    // L_ip = A_ip T^T
-        dmma884(r0, r1, a.y, ta.y);
-        double* Lb = Lc + bi * D5_BS;                  // publish (A layout) and write out
-        Lb[X.ia0] = r0; Lb[X.ia0 + 2] = r1;
-        *reinterpret_cast<double2*>(X.Ab + (long)(8 * bi + X.lr) * X.Np + 8 * P + 2 * X.lc) = make_double2(r0, r1);
-        __syncwarp();
-        const double2 l = *reinterpret_cast<const double2*>(Lb + 2 * X.lane);
-        double m0 = 0.0, m1 = 0.0;
-        dmma884(m0, m1, l.x, tk.x);                    // M_ip = L_ip T
-        dmma884(m0, m1, l.y, tk.y);
-        c0[PJ] = -m0; c1[PJ] = -m1;                    // the slot restarts as B_ip = 0 - L_ip X_pp
-        const double2 n = d5_c_to_a(m0, m1, scr, X);
-        aL = make_double2(-l.x, -l.y);
-        aM = make_double2(-n.x, -n.y);
-    } else if (bi == P) {                              // the owner of row P publishes its raw right-hand-side blocks
+__device__ __forceinline__ void d5_publish_row(const double (&c0)[NJ], const double (&c1)[NJ], int bi, const D5Ctx& X, double* Xr) {
+    if (bi != P) return;
 #pragma unroll
-        for (int j = 0; j < P && j < NJ; ++j) {
-            double* Xb = Xr + j * D5_BS;
-            Xb[X.ib0] = c0[j]; Xb[X.ib0 + 8] = c1[j];
-        }
+    for (int j = 0; j < P && j < NJ; ++j) {
+        double* Xb = Xr + j * D5_BS;
+        Xb[X.ib0] = c0[j]; Xb[X.ib0 + 8] = c1[j];
     }
 }
 
@@ -1046,20 +1053,75 @@ __device__ __forceinline__ void d5_panel(double (&cA0)[8], double (&cA1)[8], dou
     const double* TK = buf + 33 * D5_BS;
     double* Dnext = X.sm + 2 * D5_BUF + ((P + 1) & 1) * D4_BS;
     const int rA = X.w, rB = 15 - X.w;
+    constexpr bool HAS_A = (P < 7);                    // block row w <= 7 can only be below panel P if P < 7
+    constexpr int PA = HAS_A ? P : 0;
+    const bool onA = HAS_A && rA > P, onB = rB > P;
+    double* scrA = X.scratch;
+    double* scrB = X.scratch + D5_BS;
+    double* LbA = Lc + rA * D5_BS;
+    double* LbB = Lc + rB * D5_BS;
     __syncthreads();                                   // #1: T_P published by the factor warp
+    GPX_TICK5(X, 0);
     const double2 ta = *reinterpret_cast<const double2*>(TA + 2 * X.lane);
     const double2 tk = *reinterpret_cast<const double2*>(TK + 2 * X.lane);
-    double2 aLA = make_double2(0.0, 0.0), aMA = aLA, aLB = aLA, aMB = aLA;
-    d5_stage2_row<P, 8>(cA0, cA1, rA, 0, X, Lc, Xr, ta, tk, aLA, aMA);
-    d5_stage2_row<P, 16>(cB0, cB1, rB, 1, X, Lc, Xr, ta, tk, aLB, aMB);
-    __syncthreads();                                   // #2: column P of L and raw row P complete
-    if (P < 15) {
-        if (d5_next_diag_row<P, 8>(cA0, cA1, rA, X, aLA, Dnext) | d5_next_diag_row<P, 16>(cB0, cB1, rB, X, aLB, Dnext)) {
-            __threadfence_block();
-            d4_bar_arrive(1, 64);
+    double2 lA = make_double2(0.0, 0.0), lB = lA;
+    // ---- stage 2a: L_ip = A_ip T^T for this warp's (<= 2) blocks of column P.  Both rows run as one straight-line
+    //      sequence (an absent row computes on garbage and commits nothing), so their transposer round trips and
+    //      DMMA pairs overlap.
+    if (onA | onB) {
+        if (HAS_A && onA) { scrA[X.ia0] = cA0[PA]; scrA[X.ia0 + 2] = cA1[PA]; }
+        if (onB) { scrB[X.ia0] = cB0[P]; scrB[X.ia0 + 2] = cB1[P]; }
+        __syncwarp();
+        double2 aA = make_double2(0.0, 0.0);
+        if (HAS_A) aA = *reinterpret_cast<const double2*>(scrA + 2 * X.lane);
+        const double2 aB = *reinterpret_cast<const double2*>(scrB + 2 * X.lane);
+        double rA0 = 0.0, rA1 = 0.0, rB0 = 0.0, rB1 = 0.0;
+        if (HAS_A) dmma884(rA0, rA1, aA.x, ta.x);
+        dmma884(rB0, rB1, aB.x, ta.x);
+        if (HAS_A) dmma884(rA0, rA1, aA.y, ta.y);
+        dmma884(rB0, rB1, aB.y, ta.y);
+        if (HAS_A && onA) {
+            LbA[X.ia0] = rA0; LbA[X.ia0 + 2] = rA1;
+            *reinterpret_cast<double2*>(X.Ab + (long)(8 * rA + X.lr) * X.Np + 8 * P + 2 * X.lc) = make_double2(rA0, rA1);
         }
-        d5_stage3_row<P, 8>(cA0, cA1, rA, X, Lc, Xr, aLA, aMA);
+        if (onB) {
+            LbB[X.ia0] = rB0; LbB[X.ia0 + 2] = rB1;
+            *reinterpret_cast<double2*>(X.Ab + (long)(8 * rB + X.lr) * X.Np + 8 * P + 2 * X.lc) = make_double2(rB0, rB1);
+        }
+        __syncwarp();
+        if (HAS_A && onA) lA = *reinterpret_cast<const double2*>(LbA + 2 * X.lane);
+        if (onB) lB = *reinterpret_cast<const double2*>(LbB + 2 * X.lane);
+    }
+    d5_publish_row<P, 8>(cA0, cA1, rA, X, Xr);
+    d5_publish_row<P, 16>(cB0, cB1, rB, X, Xr);
+    GPX_TICK5(X, 1);
+    __syncthreads();                                   // #2: column P of L and raw row P complete
+    GPX_TICK5(X, 2);
+    if (P < 15) {
+        const double2 aLA = make_double2(-lA.x, -lA.y), aLB = make_double2(-lB.x, -lB.y);
+        // ---- the next diagonal block first: its factor then overlaps everything below
+        if (d5_next_diag_row<P, 8>(cA0, cA1, rA, X, aLA, Dnext) | d5_next_diag_row<P, 16>(cB0, cB1, rB, X, aLB, Dnext))
+            d4_bar_arrive(1, 64);
+        GPX_TICK5(X, 3);
+        // ---- stage 2b: M_ip = L_ip T; the slot restarts as B_ip = 0 - L_ip X_pp; A fragments of -M_ip
+        double2 aMA = make_double2(0.0, 0.0), aMB = aMA;
+        if (onA | onB) {
+            double mA0 = 0.0, mA1 = 0.0, mB0 = 0.0, mB1 = 0.0;
+            if (HAS_A) dmma884(mA0, mA1, lA.x, tk.x);
+            dmma884(mB0, mB1, lB.x, tk.x);
+            if (HAS_A) dmma884(mA0, mA1, lA.y, tk.y);
+            dmma884(mB0, mB1, lB.y, tk.y);
+            if (HAS_A && onA) { cA0[PA] = -mA0; cA1[PA] = -mA1; scrA[X.ia0] = mA0; scrA[X.ia0 + 2] = mA1; }
+            if (onB) { cB0[P] = -mB0; cB1[P] = -mB1; scrB[X.ia0] = mB0; scrB[X.ia0 + 2] = mB1; }
+            __syncwarp();
+            if (HAS_A) { const double2 n = *reinterpret_cast<const double2*>(scrA + 2 * X.lane); aMA = make_double2(-n.x, -n.y); }
+            { const double2 n = *reinterpret_cast<const double2*>(scrB + 2 * X.lane); aMB = make_double2(-n.x, -n.y); }
+            __syncwarp();
+        }
+        // ---- stage 3: rank-8 updates of this warp's two block rows
+        if (HAS_A) d5_stage3_row<P, 8>(cA0, cA1, rA, X, Lc, Xr, aLA, aMA);
         d5_stage3_row<P, 16>(cB0, cB1, rB, X, Lc, Xr, aLB, aMB);
+        GPX_TICK5(X, 4);
     }
     // output row P of the inverse, X_pj = T_p B_pj, from the published raw blocks; dealt round-robin to the warps
     for (int j = X.w; j < P; j += 8) {
@@ -1072,6 +1134,7 @@ __device__ __forceinline__ void d5_panel(double (&cA0)[8], double (&cA1)[8], dou
         X.DTb[c_ * TILE + r_] = r0;
         X.DTb[(c_ + 1) * TILE + r_] = r1;
     }
+    GPX_TICK5(X, 5);
 }
 
 template <int P>
@@ -1094,21 +1157,34 @@ potrf_diag5_kernel(double* __restrict__ K, int Np, int blk, int N, double* __res
     double* Lpp = Draw + 2 * D4_BS;           // [8][12]
     double* dg = Lpp + D4_BS;                 // [128]
     double* scratch = dg + TILE;              // [8 warps][2][64]
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    // The factor warp's ~250 dependent FP64 instructions per panel share the FP64 pipe of their scheduler with the
+    // DMMAs of whatever else runs there (measured: 2150 instead of ~600 cycles next to two compute warps), so hardware
+    // warp 0 factors alone on scheduler 0 and the compute warps live on schedulers 1-3 (warps 4, 8, 11 exit).
+    const int tid = threadIdx.x, lane = tid & 31, hw = tid >> 5;
+    if (hw == 4 || hw == 8 || hw == 11) return;
+    const int w = (hw == 0) ? 8 : hw - 1 - (hw > 4) - (hw > 8);     // 8 = factor warp, 0..7 = compute warps
     const int lr = lane >> 2, lc = lane & 3;
     const long off = (long)blk * TILE;
     double* Ab = K + off * Np + off;
     double* Sb = S + off * Np + off;
     double* DTb = DT + (long)blk * TILE * TILE;
 
+#ifdef GPX_DIAG_TIMING
+    __shared__ long long t5_stat[8];
+    if (tid == 32) { for (int i = 0; i < 8; ++i) t5_stat[i] = 0; t5_stat[0] = clock64(); }
+#endif
     if (w == 8) {
         // =================== factor warp (as in v4; T is published in both operand layouts) ===================
         int bad = 0;
+#ifdef GPX_DIAG_TIMING
+        long long f_mark = clock64(), f_acc[6] = {0, 0, 0, 0, 0, 0};
+#endif
         for (int p = 0; p < 16; ++p) {
             double* TA = sm5 + (p & 1) * D5_BUF + 32 * D5_BS;
             double* TK = TA + D5_BS;
             const double* Dr = Draw + (p & 1) * D4_BS;
             d4_bar_sync(1, 64);                               // block (p,p) published by the owner of row p
+            GPX_TICKF(0);
             double a[8][8];
 #pragma unroll
             for (int i = 0; i < 8; ++i)
@@ -1123,8 +1199,8 @@ potrf_diag5_kernel(double* __restrict__ K, int Np, int blk, int N, double* __res
             for (int j = 0; j < 8; ++j) {
                 const double d = a[j][j];
                 if (!(d > 0.0) && bad == 0) bad = 8 * p + j + 1;
-                const double r = __drcp_rn(d);
-                inv[j] = rsqrt(d);
+                const double r = d5_rcp(d);
+                inv[j] = d5_rsqrt(d);
                 sd[j] = d * inv[j];
                 double uj[8];
 #pragma unroll
@@ -1136,6 +1212,7 @@ potrf_diag5_kernel(double* __restrict__ K, int Np, int blk, int N, double* __res
 #pragma unroll
                 for (int k = j + 1; k < 8; ++k) a[k][j] = uj[k];
             }
+            GPX_TICKF(1);
             const int c = lane & 7;
             double x[8];
 #pragma unroll
@@ -1166,7 +1243,9 @@ potrf_diag5_kernel(double* __restrict__ K, int Np, int blk, int N, double* __res
                 }
             }
             __syncwarp();
+            GPX_TICKF(3);
             __syncthreads();                                  // #1: T_p visible to the compute warps
+            GPX_TICKF(4);
             {   // outputs of the diagonal 8x8 block: L_pp -> K, T -> S and (transposed) DT
                 const double2 lf = *reinterpret_cast<const double2*>(Lpp + lr * 12 + 2 * lc);
                 const int i0 = d5_ia(lr, 2 * lc);
@@ -1178,9 +1257,19 @@ potrf_diag5_kernel(double* __restrict__ K, int Np, int blk, int N, double* __res
                 DTb[(c_ + 1) * TILE + r_] = t1;
             }
             __syncthreads();                                  // #2
+            GPX_TICKF(5);
         }
-        __syncthreads();
+#ifdef GPX_DIAG_TIMING
+        if (lane == 0) for (int i = 0; i < 6; ++i) logdet_blk[40 + i] = (double)f_acc[i];
+#endif
         if (lane == 0 && bad != 0 && *info == 0) *info = (int)off + bad;
+        __syncwarp();
+        double t = 0.0;
+        for (int j = lane; j < TILE; j += 32)
+            if (off + j < N) t += log(dg[j]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0) logdet_blk[blk] = t;
         return;
     }
 
@@ -1189,6 +1278,9 @@ potrf_diag5_kernel(double* __restrict__ K, int Np, int blk, int N, double* __res
     X.sm = sm5; X.scratch = scratch + w * 2 * D5_BS;
     X.Ab = Ab; X.Sb = Sb; X.DTb = DTb; X.Np = Np; X.w = w; X.lane = lane; X.lr = lr; X.lc = lc;
     X.ia0 = d5_ia(lr, 2 * lc); X.ib0 = d5_ib(lr, 2 * lc);
+#ifdef GPX_DIAG_TIMING
+    X.tstat = t5_stat;
+#endif
     double cA0[8], cA1[8], cB0[16], cB1[16];
     const int rA = w, rB = 15 - w;
 #pragma unroll
@@ -1209,8 +1301,7 @@ potrf_diag5_kernel(double* __restrict__ K, int Np, int blk, int N, double* __res
     }
     if (w == 0) {       // block (0,0) goes to the factor warp straight away
         *reinterpret_cast<double2*>(Draw + lr * 12 + 2 * lc) = make_double2(cA0[0], cA1[0]);
-        __threadfence_block();
-        d4_bar_arrive(1, 64);
+        d4_bar_arrive(1, 64);        // bar.arrive/bar.sync order the shared-memory hand-over (PTX producer/consumer idiom)
     }
     // while the first factor runs: zero the blocks above the diagonal of S and below the diagonal of DT
     for (int b = w; b < 256; b += 8) {
@@ -1222,15 +1313,9 @@ potrf_diag5_kernel(double* __restrict__ K, int Np, int blk, int N, double* __res
         }
     }
     D5Unroll<15>::run(cA0, cA1, cB0, cB1, X);
-    __syncthreads();
-    if (tid < 32) {
-        double t = 0.0;
-        for (int j = tid; j < TILE; j += 32)
-            if (off + j < N) t += log(dg[j]);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        if (tid == 0) logdet_blk[blk] = t;
-    }
+#ifdef GPX_DIAG_TIMING
+    if (w == 0 && lane == 0) for (int i = 0; i < 6; ++i) logdet_blk[48 + i] = (double)t5_stat[1 + i];
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1377,14 +1462,17 @@ potrf_trailing_tma_kernel(const __grid_constant__ CUtensorMap tmK, double* __res
     extern __shared__ unsigned char smem_raw[];
     TOperand A = t_operand(&tmK, ti * TILE, p * TILE);
     TOperand B = t_operand(&tmK, tj * TILE, p * TILE);
-    double acc[8][4][2];
-    gemm_nt_tma_mainloop(acc, A, B, 0, TILE, smem_raw);
+    // the accumulators start as the C tile (its loads overlap the TMA prologue) and the loop accumulates -A B^T, so the
+    // epilogue is a plain store instead of an exposed load-subtract-store pass
     double* Ct = K + (long)ti * TILE * Np + (long)tj * TILE;
+    double acc[8][4][2];
+    gemm_foreach_pair_ref(acc, [&](int row, int col, double& v0, double& v1) {
+        const double2 c = *reinterpret_cast<const double2*>(Ct + (long)row * Np + col);
+        v0 = c.x; v1 = c.y;
+    });
+    gemm_nt_tma_mainloop<false, true>(acc, A, B, 0, TILE, smem_raw);
     gemm_foreach_pair(acc, [&](int row, int col, double v0, double v1) {
-        double2* ptr = reinterpret_cast<double2*>(Ct + (long)row * Np + col);
-        double2 c = *ptr;
-        c.x -= v0; c.y -= v1;
-        *ptr = c;
+        *reinterpret_cast<double2*>(Ct + (long)row * Np + col) = make_double2(v0, v1);
     });
 }
 
@@ -1525,9 +1613,9 @@ static void set_gemm_attrs() {
     if (dev >= 0 && dev < 64) g_attr_set[dev] = true;
 }
 
-static int diag_impl() {       // GPX_DIAG_IMPL = 1 | 2 | 3 | 4 (default 3)
+static int diag_impl() {       // GPX_DIAG_IMPL = 1 | 2 | 3 | 4 | 5 (default 5)
     static int v = -1;
-    if (v < 0) { const char* e = getenv("GPX_DIAG_IMPL"); v = (e && e[0] >= '1' && e[0] <= '5') ? e[0] - '0' : 3; }
+    if (v < 0) { const char* e = getenv("GPX_DIAG_IMPL"); v = (e && e[0] >= '1' && e[0] <= '5') ? e[0] - '0' : 5; }
     return v;
 }
 static int use_diag_v1() { return diag_impl() == 1; }
@@ -1599,7 +1687,7 @@ int potrf(double* K, int Np, int N, double* S, double* DT, double* logdet_blk, i
     };
     bool side_pending = false;
     static int ev_old = -1;
-    if (ev_old < 0) { const char* e = getenv("GPX_POTRF_EV"); ev_old = (e && e[0] == 'o') ? 1 : 0; }
+    if (ev_old < 0) { const char* e = getenv("GPX_POTRF_EV"); ev_old = (e && e[0] == 'n') ? 0 : 1; }   // "new" = release the helper stream before the look-ahead column (measured slower)
     for (int p = 0; p < nb; ++p) {
         if (use_diag_v1())
             potrf_diag_kernel<<<1, DG_THREADS, dg, st>>>(K, Np, p, N, S, DT, logdet_blk, info);

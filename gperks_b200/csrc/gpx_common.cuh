@@ -199,6 +199,18 @@ __device__ __forceinline__ void gemm_foreach_pair(double (&acc)[8][4][2], F f) {
         for (int n = 0; n < 4; ++n) f(wm * 64 + s * 8 + lr, wn * 32 + n * 8 + 2 * lc, acc[s][n][0], acc[s][n][1]);
 }
 
+// same traversal with writable accumulators (used to preload C so that acc = C - A B^T needs no read-modify-write epilogue)
+template <typename F>
+__device__ __forceinline__ void gemm_foreach_pair_ref(double (&acc)[8][4][2], F f) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wm = warp >> 2, wn = warp & 3;
+    const int lr = lane >> 2, lc = lane & 3;
+#pragma unroll
+    for (int s = 0; s < 8; ++s)
+#pragma unroll
+        for (int n = 0; n < 4; ++n) f(wm * 64 + s * 8 + lr, wn * 32 + n * 8 + 2 * lc, acc[s][n][0], acc[s][n][1]);
+}
+
 #define GPX_CHECK_LAUNCH()                                  \
     do {                                                    \
         cudaError_t e__ = cudaGetLastError();               \

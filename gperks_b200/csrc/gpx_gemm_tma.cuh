@@ -40,6 +40,9 @@ __device__ __forceinline__ void t_issue(const TOperand& o, int k, uint32_t dst, 
 }
 
 // `smem_raw`: dynamic shared memory of GT_SMEM_BYTES.  Must be called by all GT_THREADS threads, once per CTA.
+// INIT_ZERO = false keeps the caller's accumulators (e.g. a preloaded C tile); NEG_A accumulates -A B^T (the
+// negation is an operand modifier of the DMMA, not an instruction).
+template <bool INIT_ZERO = true, bool NEG_A = false>
 __device__ __forceinline__ void gemm_nt_tma_mainloop(double (&acc)[8][4][2], const TOperand& A, const TOperand& B,
                                                      int k_begin, int k_end, unsigned char* smem_raw) {
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -69,10 +72,12 @@ __device__ __forceinline__ void gemm_nt_tma_mainloop(double (&acc)[8][4][2], con
     const int wm = warp >> 2, wn = warp & 3;
     const int lr = lane >> 2, lc = lane & 3;
     const int off0 = ((2 * lc) ^ lr) * 16, off1 = off0 ^ 16;      // 128B-swizzled 16-byte chunk positions
+    if (INIT_ZERO) {
 #pragma unroll
-    for (int s = 0; s < 8; ++s)
+        for (int s = 0; s < 8; ++s)
 #pragma unroll
-        for (int n = 0; n < 4; ++n) { acc[s][n][0] = 0.0; acc[s][n][1] = 0.0; }
+            for (int n = 0; n < 4; ++n) { acc[s][n][0] = 0.0; acc[s][n][1] = 0.0; }
+    }
 
     for (int kt = 0; kt < nk; ++kt) {
         const int s_ = kt % GT_STAGES, round = kt / GT_STAGES;
@@ -103,6 +108,7 @@ __device__ __forceinline__ void gemm_nt_tma_mainloop(double (&acc)[8][4][2], con
             double2 a0 = *reinterpret_cast<const double2*>(at + s * 1024 + off0);
             double2 a1 = *reinterpret_cast<const double2*>(at + s * 1024 + off1);
             double af[4] = {a0.x, a0.y, a1.x, a1.y};
+            if (NEG_A) { af[0] = -af[0]; af[1] = -af[1]; af[2] = -af[2]; af[3] = -af[3]; }
 #pragma unroll
             for (int st = 0; st < 4; ++st)
 #pragma unroll
