@@ -1456,7 +1456,9 @@ potrf_panel_tma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_con
 }
 
 __global__ void __launch_bounds__(GT_THREADS, 1)
-potrf_trailing_tma_kernel(const __grid_constant__ CUtensorMap tmK, double* __restrict__ K, int Np, int p, int j0, int i0) {
+potrf_trailing_tma_kernel(const __grid_constant__ CUtensorMap tmK, double* __restrict__ K, int Np, int p, int j0, int i0,
+                          int kpanels) {
+    // C[ti][tj] -= L[ti][p .. p+kpanels) L[tj][p .. p+kpanels)^T
     const int ti = i0 + blockIdx.y, tj = j0 + blockIdx.x;
     if (tj > ti) return;
     extern __shared__ unsigned char smem_raw[];
@@ -1470,7 +1472,7 @@ potrf_trailing_tma_kernel(const __grid_constant__ CUtensorMap tmK, double* __res
         const double2 c = *reinterpret_cast<const double2*>(Ct + (long)row * Np + col);
         v0 = c.x; v1 = c.y;
     });
-    gemm_nt_tma_mainloop<false, true>(acc, A, B, 0, TILE, smem_raw);
+    gemm_nt_tma_mainloop<false, true>(acc, A, B, 0, kpanels * TILE, smem_raw);
     gemm_foreach_pair(acc, [&](int row, int col, double v0, double v1) {
         *reinterpret_cast<double2*>(Ct + (long)row * Np + col) = make_double2(v0, v1);
     });
@@ -1624,6 +1626,8 @@ static int use_diag_v1() { return diag_impl() == 1; }
 // after the caller's stream and joined back into it before potrf returns control of the data).
 struct LookAhead {
     cudaStream_t side = nullptr;
+    cudaStream_t chain = nullptr;          // highest-priority stream for the critical path (GPX_POTRF_PRIO=1)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_main[2] = {nullptr, nullptr};
     cudaEvent_t ev_side[2] = {nullptr, nullptr};
 };
@@ -1639,6 +1643,9 @@ static LookAhead* lookahead_for_current_device() {
         int prio_lo = 0, prio_hi = 0;
         cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
         if (cudaStreamCreateWithPriority(&la->side, cudaStreamNonBlocking, prio_lo) != cudaSuccess) return nullptr;
+        if (cudaStreamCreateWithPriority(&la->chain, cudaStreamNonBlocking, prio_hi) != cudaSuccess) return nullptr;
+        cudaEventCreateWithFlags(&la->ev_fork, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&la->ev_join, cudaEventDisableTiming);
         for (int i = 0; i < 2; ++i) {
             cudaEventCreateWithFlags(&la->ev_main[i], cudaEventDisableTiming);
             cudaEventCreateWithFlags(&la->ev_side[i], cudaEventDisableTiming);
@@ -1663,13 +1670,21 @@ static int use_lookahead() {
 // Right-looking with a one-panel look-ahead: after panel p, the next block column is updated on the caller's
 // stream (critical path: diag p+1, panel p+1), while the rest of the trailing matrix is updated on a helper
 // stream.
-int potrf(double* K, int Np, int N, double* S, double* DT, double* logdet_blk, int* info, cudaStream_t st) {
+int potrf(double* K, int Np, int N, double* S, double* DT, double* logdet_blk, int* info, cudaStream_t st_caller) {
     set_gemm_attrs();
+    cudaStream_t st = st_caller;
     const int nb = Np / TILE;
     const int dg = (TILE * DG_LD + 2 * TILE + 2) * 8;
     const int dg2 = (TILE * DG_LD + 2 * TILE + 64) * 8;
     LookAhead* la = use_lookahead() ? lookahead_for_current_device() : nullptr;
     cudaMemsetAsync(info, 0, sizeof(int), st);
+    static int prio = -1;
+    if (prio < 0) { const char* e = getenv("GPX_POTRF_PRIO"); prio = (e && e[0] == '0') ? 0 : 1; }
+    if (la != nullptr && prio) {           // run the critical path on the high-priority stream, forked from the caller's
+        cudaEventRecord(la->ev_fork, st_caller);
+        cudaStreamWaitEvent(la->chain, la->ev_fork, 0);
+        st = la->chain;
+    }
     const bool tma = use_chol_tma();
     CUtensorMap tmK, tmS;
     if (tma) {
@@ -1682,13 +1697,10 @@ int potrf(double* K, int Np, int N, double* S, double* DT, double* logdet_blk, i
         else potrf_panel_kernel<<<n, G_THREADS, G_SMEM_BYTES, st>>>(K, Np, p, S);
     };
     auto trailing = [&](dim3 grid, int p, int j0, int i0, cudaStream_t s_) {
-        if (tma) potrf_trailing_tma_kernel<<<grid, GT_THREADS, GT_SMEM_BYTES, s_>>>(tmK, K, Np, p, j0, i0);
+        if (tma) potrf_trailing_tma_kernel<<<grid, GT_THREADS, GT_SMEM_BYTES, s_>>>(tmK, K, Np, p, j0, i0, 1);
         else potrf_trailing_kernel<<<grid, G_THREADS, G_SMEM_BYTES, s_>>>(K, Np, p, j0, i0);
     };
-    bool side_pending = false;
-    static int ev_old = -1;
-    if (ev_old < 0) { const char* e = getenv("GPX_POTRF_EV"); ev_old = (e && e[0] == 'n') ? 0 : 1; }   // "new" = release the helper stream before the look-ahead column (measured slower)
-    for (int p = 0; p < nb; ++p) {
+    auto diag = [&](int p) {
         if (use_diag_v1())
             potrf_diag_kernel<<<1, DG_THREADS, dg, st>>>(K, Np, p, N, S, DT, logdet_blk, info);
         else if (diag_impl() == 2)
@@ -1699,6 +1711,61 @@ int potrf(double* K, int Np, int N, double* S, double* DT, double* logdet_blk, i
             potrf_diag5_kernel<<<1, D5_THREADS, D5_SMEM, st>>>(K, Np, p, N, S, DT, logdet_blk, info);
         else
             potrf_diag3_kernel<<<1, D3_THREADS, D3_SMEM, st>>>(K, Np, p, N, S, DT, logdet_blk, info);
+    };
+    static int ob_env = -1, sw_env = -1;
+    if (ob_env < 0) { const char* e = getenv("GPX_POTRF_OB"); ob_env = (e && e[0] >= '1' && e[0] <= '8') ? e[0] - '0' : 0; }
+    if (sw_env < 0) { const char* e = getenv("GPX_POTRF_SWITCH"); sw_env = e ? atoi(e) : 32; }
+    const int OB = ob_env ? ob_env : (nb >= 96 ? 4 : 2);
+    int p_start = 0;
+    if (tma && la != nullptr && st != st_caller && OB >= 2 && nb > sw_env) {
+        // Two-level schedule.  Panels are still 128 wide (diag + panel on the critical path), but the bulk of the
+        // trailing matrix is updated once per OUTER block of OB panels with K = OB*128, which halves (OB = 2) the
+        // prologue/epilogue share of every output tile.  Inside an outer block the panels only update the block's own
+        // columns; afterwards the next outer block's columns are updated on the critical-path stream (look-ahead) and
+        // everything to the right of them on the low-priority helper stream.  Only while the trailing matrix is large
+        // enough to be throughput-bound: the last `sw_env` block columns are chain-bound and go through the one-panel
+        // look-ahead loop below, whose critical path per panel is shorter.
+        bool pending = false;
+        int q_idx = 0;
+        for (int q = 0; q < nb && nb - q > sw_env; q += OB, ++q_idx) {
+            const int qe = (q + OB < nb) ? q + OB : nb;
+            for (int p = q; p < qe; ++p) {
+                diag(p);
+                const int n = nb - p - 1;
+                if (n <= 0) break;
+                potrf_panel_tma_kernel<<<n, GT_THREADS, GT_SMEM_BYTES, st>>>(tmK, tmS, K, Np, p);
+                if (p + 1 < qe)      // the outer block's remaining columns, K = 128
+                    potrf_trailing_tma_kernel<<<dim3(qe - p - 1, n), GT_THREADS, GT_SMEM_BYTES, st>>>(tmK, K, Np, p, p + 1, p + 1, 1);
+            }
+            if (qe >= nb) { p_start = nb; break; }
+            const int kp = qe - q;
+            const int la_cols = (qe + OB < nb) ? OB : nb - qe;          // look-ahead: the next outer block's columns
+            const int rest = nb - qe - la_cols;                          // helper stream: everything right of them
+            if (rest > 0) {          // the helper only needs this outer block's panels
+                cudaEventRecord(la->ev_main[q_idx & 1], st);
+                cudaStreamWaitEvent(la->side, la->ev_main[q_idx & 1], 0);
+            }
+            // the look-ahead columns were last written by the helper's previous outer update
+            if (pending) cudaStreamWaitEvent(st, la->ev_side[(q_idx - 1) & 1], 0);
+            if (rest > 0) {
+                potrf_trailing_tma_kernel<<<dim3(rest, rest), GT_THREADS, GT_SMEM_BYTES, la->side>>>(tmK, K, Np, q, qe + la_cols,
+                                                                                                 qe + la_cols, kp);
+                cudaEventRecord(la->ev_side[q_idx & 1], la->side);
+                pending = true;
+            } else {
+                pending = false;
+            }
+            potrf_trailing_tma_kernel<<<dim3(la_cols, nb - qe), GT_THREADS, GT_SMEM_BYTES, st>>>(tmK, K, Np, q, qe, qe, kp);
+            p_start = qe;
+        }
+        // hand over to the one-panel loop with the whole trailing matrix up to date
+        if (pending) cudaStreamWaitEvent(st, la->ev_side[(q_idx - 1) & 1], 0);
+    }
+    bool side_pending = false;
+    static int ev_old = -1;
+    if (ev_old < 0) { const char* e = getenv("GPX_POTRF_EV"); ev_old = e ? (e[0] == 'o') : !prio; }    // releasing the helper stream before the look-ahead column only pays with the priority stream
+    for (int p = p_start; p < nb; ++p) {
+        diag(p);
         const int n = nb - p - 1;
         if (n <= 0) break;
         panel(n, p);
@@ -1732,7 +1799,11 @@ int potrf(double* K, int Np, int N, double* S, double* DT, double* logdet_blk, i
             side_pending = false;
         }
     }
-    if (la != nullptr && side_pending) cudaStreamWaitEvent(st, la->ev_side[(nb - 3) & 1], 0);
+    if (la != nullptr && side_pending) cudaStreamWaitEvent(st, la->ev_side[(nb - 3) & 1], 0);   // last helper launch: p = nb-3
+    if (st != st_caller) {
+        cudaEventRecord(la->ev_join, st);
+        cudaStreamWaitEvent(st_caller, la->ev_join, 0);
+    }
     GPX_CHECK_LAUNCH();
     return 0;
 }
