@@ -1478,6 +1478,48 @@ potrf_trailing_tma_kernel(const __grid_constant__ CUtensorMap tmK, double* __res
     });
 }
 
+// Narrow-tile editions of the two kernels on potrf's critical path (tile = ROWS x 128, ROWS = WM*S*8 in {64, 32}):
+// grid.x = (#block rows) * (128 / ROWS).  tmKr is K with a ROWS-row box for the A operand.
+template <int WM, int S, int NB>
+__global__ void __launch_bounds__(GT_THREADS, 1)
+potrf_panel_narrow_kernel(const __grid_constant__ CUtensorMap tmKr, const __grid_constant__ CUtensorMap tmS,
+                          double* __restrict__ K, int Np, int p) {
+    constexpr int ROWS = WM * S * 8, PER = TILE / ROWS;
+    extern __shared__ unsigned char smem_raw[];
+    const int row0 = (p + 1 + blockIdx.x / PER) * TILE + (blockIdx.x % PER) * ROWS;
+    TOperand A = t_operand(&tmKr, row0, p * TILE);
+    TOperand B = t_operand(&tmS, p * TILE, p * TILE);
+    double acc[S][NB][2];
+    gemm_nt_tma_mainloop_t<WM, S, NB>(acc, A, B, 0, TILE, smem_raw);
+    __syncthreads();        // the A tile is this CTA's output: all reads (through smem) are done before it is overwritten
+    double* Ct = K + (long)row0 * Np + (long)p * TILE;
+    gemm_foreach_pair_t<WM, S, NB>(acc, [&](int row, int col, double& v0, double& v1) {
+        *reinterpret_cast<double2*>(Ct + (long)row * Np + col) = make_double2(v0, v1);
+    });
+}
+
+// look-ahead column: C[rows][p+1] -= L[rows][p] L[p+1][p]^T for block rows >= p+1
+template <int WM, int S, int NB>
+__global__ void __launch_bounds__(GT_THREADS, 1)
+potrf_column_narrow_kernel(const __grid_constant__ CUtensorMap tmKr, const __grid_constant__ CUtensorMap tmK,
+                           double* __restrict__ K, int Np, int p) {
+    constexpr int ROWS = WM * S * 8, PER = TILE / ROWS;
+    extern __shared__ unsigned char smem_raw[];
+    const int row0 = (p + 1 + blockIdx.x / PER) * TILE + (blockIdx.x % PER) * ROWS;
+    TOperand A = t_operand(&tmKr, row0, p * TILE);
+    TOperand B = t_operand(&tmK, (p + 1) * TILE, p * TILE);
+    double* Ct = K + (long)row0 * Np + (long)(p + 1) * TILE;
+    double acc[S][NB][2];
+    gemm_foreach_pair_t<WM, S, NB>(acc, [&](int row, int col, double& v0, double& v1) {
+        const double2 c = *reinterpret_cast<const double2*>(Ct + (long)row * Np + col);
+        v0 = c.x; v1 = c.y;
+    });
+    gemm_nt_tma_mainloop_t<WM, S, NB, false, true>(acc, A, B, 0, TILE, smem_raw);
+    gemm_foreach_pair_t<WM, S, NB>(acc, [&](int row, int col, double& v0, double& v1) {
+        *reinterpret_cast<double2*>(Ct + (long)row * Np + col) = make_double2(v0, v1);
+    });
+}
+
 __global__ void __launch_bounds__(GT_THREADS, 1)
 trtri_step1_tma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmS,
                        const __grid_constant__ CUtensorMap tmD, double* __restrict__ W, int Np, int nb, int h) {
@@ -1612,6 +1654,10 @@ static void set_gemm_attrs() {
     cudaFuncSetAttribute(potrf_diag3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D3_SMEM);
     cudaFuncSetAttribute(potrf_diag4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D4_SMEM);
     cudaFuncSetAttribute(potrf_diag5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D5_SMEM);
+    cudaFuncSetAttribute(potrf_panel_narrow_kernel<2, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM_BYTES);
+    cudaFuncSetAttribute(potrf_panel_narrow_kernel<1, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM_BYTES);
+    cudaFuncSetAttribute(potrf_column_narrow_kernel<2, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM_BYTES);
+    cudaFuncSetAttribute(potrf_column_narrow_kernel<1, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM_BYTES);
     if (dev >= 0 && dev < 64) g_attr_set[dev] = true;
 }
 
@@ -1686,15 +1732,28 @@ int potrf(double* K, int Np, int N, double* S, double* DT, double* logdet_blk, i
         st = la->chain;
     }
     const bool tma = use_chol_tma();
-    CUtensorMap tmK, tmS;
+    CUtensorMap tmK, tmS, tmK64, tmK32;
     if (tma) {
         int rc;
         if ((rc = encode_f64_rowmajor(&tmK, K, Np, Np, Np, TILE))) return rc;
         if ((rc = encode_f64_rowmajor(&tmS, S, Np, Np, Np, TILE))) return rc;
+        if ((rc = encode_f64_rowmajor(&tmK64, K, Np, Np, Np, 64))) return rc;
+        if ((rc = encode_f64_rowmajor(&tmK32, K, Np, Np, Np, 32))) return rc;
     }
+    // panel / look-ahead column over n block rows: with few rows, narrower tiles put the same work on more SMs
+    static int narrow = -1;
+    if (narrow < 0) { const char* e = getenv("GPX_POTRF_NARROW"); narrow = (e && e[0] == '0') ? 0 : 1; }
     auto panel = [&](int n, int p) {
-        if (tma) potrf_panel_tma_kernel<<<n, GT_THREADS, GT_SMEM_BYTES, st>>>(tmK, tmS, K, Np, p);
-        else potrf_panel_kernel<<<n, G_THREADS, G_SMEM_BYTES, st>>>(K, Np, p, S);
+        if (!tma) potrf_panel_kernel<<<n, G_THREADS, G_SMEM_BYTES, st>>>(K, Np, p, S);
+        else if (narrow && 4 * n <= 148) potrf_panel_narrow_kernel<1, 4, 2><<<4 * n, GT_THREADS, GT_SMEM_BYTES, st>>>(tmK32, tmS, K, Np, p);
+        else if (narrow && 2 * n <= 148) potrf_panel_narrow_kernel<2, 4, 4><<<2 * n, GT_THREADS, GT_SMEM_BYTES, st>>>(tmK64, tmS, K, Np, p);
+        else potrf_panel_tma_kernel<<<n, GT_THREADS, GT_SMEM_BYTES, st>>>(tmK, tmS, K, Np, p);
+    };
+    auto column = [&](int n, int p) {          // block rows p+1 .. p+n of block column p+1
+        if (tma && narrow && 4 * n <= 148) potrf_column_narrow_kernel<1, 4, 2><<<4 * n, GT_THREADS, GT_SMEM_BYTES, st>>>(tmK32, tmK, K, Np, p);
+        else if (tma && narrow && 2 * n <= 148) potrf_column_narrow_kernel<2, 4, 4><<<2 * n, GT_THREADS, GT_SMEM_BYTES, st>>>(tmK64, tmK, K, Np, p);
+        else if (tma) potrf_trailing_tma_kernel<<<dim3(1, n), GT_THREADS, GT_SMEM_BYTES, st>>>(tmK, K, Np, p, p + 1, p + 1, 1);
+        else potrf_trailing_kernel<<<dim3(1, n), G_THREADS, G_SMEM_BYTES, st>>>(K, Np, p, p + 1, p + 1);
     };
     auto trailing = [&](dim3 grid, int p, int j0, int i0, cudaStream_t s_) {
         if (tma) potrf_trailing_tma_kernel<<<grid, GT_THREADS, GT_SMEM_BYTES, s_>>>(tmK, K, Np, p, j0, i0, 1);
@@ -1733,7 +1792,7 @@ int potrf(double* K, int Np, int N, double* S, double* DT, double* logdet_blk, i
                 diag(p);
                 const int n = nb - p - 1;
                 if (n <= 0) break;
-                potrf_panel_tma_kernel<<<n, GT_THREADS, GT_SMEM_BYTES, st>>>(tmK, tmS, K, Np, p);
+                panel(n, p);
                 if (p + 1 < qe)      // the outer block's remaining columns, K = 128
                     potrf_trailing_tma_kernel<<<dim3(qe - p - 1, n), GT_THREADS, GT_SMEM_BYTES, st>>>(tmK, K, Np, p, p + 1, p + 1, 1);
             }
@@ -1786,7 +1845,7 @@ int potrf(double* K, int Np, int N, double* S, double* DT, double* logdet_blk, i
             trailing(dim3(n - 1, n - 1), p, p + 2, p + 2, la->side);
             cudaEventRecord(la->ev_side[p & 1], la->side);
         }
-        trailing(dim3(1, n), p, p + 1, p + 1, st);
+        column(n, p);
         if (n > 1) {
             if (!early) {
                 cudaEventRecord(la->ev_main[p & 1], st);
