@@ -1774,7 +1774,7 @@ int potrf(double* K, int Np, int N, double* S, double* DT, double* logdet_blk, i
     static int ob_env = -1, sw_env = -1;
     if (ob_env < 0) { const char* e = getenv("GPX_POTRF_OB"); ob_env = (e && e[0] >= '1' && e[0] <= '8') ? e[0] - '0' : 0; }
     if (sw_env < 0) { const char* e = getenv("GPX_POTRF_SWITCH"); sw_env = e ? atoi(e) : 32; }
-    const int OB = ob_env ? ob_env : (nb >= 96 ? 4 : 2);
+    const int OB = ob_env ? ob_env : (nb >= 96 ? 4 : 3);
     int p_start = 0;
     if (tma && la != nullptr && st != st_caller && OB >= 2 && nb > sw_env) {
         // Two-level schedule.  Panels are still 128 wide (diag + panel on the critical path), but the bulk of the
