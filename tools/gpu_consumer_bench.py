@@ -72,7 +72,8 @@ print(json.dumps(out["config1"]), flush=True)
 
 # ---- config 4 shape: 8 emulators N=2048 D=6, implausibility over M points (bounded sample of the 5e7 grid)
 ems = [emulator(6, 2048, "matern", seed=8 + i)[0] for i in range(8)]
-M = 4_000_000
+import os
+M = int(os.environ.get("GPX_C4_M", 4_000_000))      # BASELINE config 4 is 5e7; default is a bounded sample
 X4 = np.random.default_rng(1).random((M, 6))
 W = Wave(emulator=ems, Itrain=np.array([[0.0, 1.0]] * 6), cutoff=3.0, maxno=1, mean=[1.0] * 8, var=[0.05] * 8)
 W.compute_impl(X4[:200_000])
