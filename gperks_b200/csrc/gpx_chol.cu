@@ -1523,7 +1523,8 @@ potrf_column_narrow_kernel(const __grid_constant__ CUtensorMap tmKr, const __gri
 __global__ void __launch_bounds__(GT_THREADS, 1)
 trtri_step1_tma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmS,
                        const __grid_constant__ CUtensorMap tmD, double* __restrict__ W, int Np, int nb, int h) {
-    const int tj = blockIdx.x, ti = blockIdx.y, q = blockIdx.z;
+    // grid (pairs, h, h): the k range shrinks with tj, so tj is the slowest index -- heaviest tiles are dispatched first
+    const int q = blockIdx.x, ti = blockIdx.y, tj = blockIdx.z;
     const int left = 2 * h * q, right = left + h;
     if (right + ti >= nb) return;
     extern __shared__ unsigned char smem_raw[];
@@ -1541,7 +1542,8 @@ trtri_step1_tma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_con
 __global__ void __launch_bounds__(GT_THREADS, 1)
 trtri_step2_tma_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmW,
                        double* __restrict__ S, int Np, int nb, int h) {
-    const int tj = blockIdx.x, ti = blockIdx.y, q = blockIdx.z;
+    // grid (pairs, h, h): the k range grows with ti, so the largest ti goes first
+    const int q = blockIdx.x, tj = blockIdx.y, ti = h - 1 - (int)blockIdx.z;
     const int left = 2 * h * q, right = left + h;
     if (right + ti >= nb) return;
     extern __shared__ unsigned char smem_raw[];
@@ -1884,8 +1886,9 @@ int trtri(const double* L, double* S, const double* DT, double* W, int Np, cudaS
         const int pairs = (nb + 2 * h - 1) / (2 * h);
         dim3 grid(h, h, pairs);
         if (tma) {
-            trtri_step1_tma_kernel<<<grid, GT_THREADS, GT_SMEM_BYTES, st>>>(tmK, tmS, tmD, W, Np, nb, h);
-            trtri_step2_tma_kernel<<<grid, GT_THREADS, GT_SMEM_BYTES, st>>>(tmS, tmW, S, Np, nb, h);
+            dim3 grid_hf(pairs, h, h);      // heaviest-first dispatch order
+            trtri_step1_tma_kernel<<<grid_hf, GT_THREADS, GT_SMEM_BYTES, st>>>(tmK, tmS, tmD, W, Np, nb, h);
+            trtri_step2_tma_kernel<<<grid_hf, GT_THREADS, GT_SMEM_BYTES, st>>>(tmS, tmW, S, Np, nb, h);
         } else {
             trtri_step1_kernel<<<grid, G_THREADS, G_SMEM_BYTES, st>>>(L, S, DT, W, Np, nb, h);
             trtri_step2_kernel<<<grid, G_THREADS, G_SMEM_BYTES, st>>>(S, W, Np, nb, h);
