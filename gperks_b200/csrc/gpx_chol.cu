@@ -17,349 +17,10 @@
 namespace gpx {
 
 // ------------------------------------------------------------------------------------------------
-// Diagonal block: Cholesky of a 128 x 128 SPD block + its triangular inverse, one CTA, 512 threads.
-// Thread t: row/column r = t/4, k-partition h = t%4 (dot products split 4 ways, shuffle-combined).
-// ------------------------------------------------------------------------------------------------
-constexpr int DG_THREADS = 512;
-constexpr int DG_LD = 132;   // 8 (mod 32) words per row: conflict-free 8-row x 4-k half-warp reads
-
-__global__ void __launch_bounds__(DG_THREADS, 1)
-potrf_diag_kernel(double* __restrict__ K, int Np, int blk, int N, double* __restrict__ S, double* __restrict__ DT,
-                  double* __restrict__ logdet_blk, int* __restrict__ info) {
-    extern __shared__ double a[];            // [128][DG_LD]  lower: L ; strictly upper: X^T (inverse)
-    double* rinv = a + TILE * DG_LD;         // [128] 1/L_jj
-    double* piv = rinv + TILE;               // [1]
-    double* lsum = piv + 2;                  // [128] log L_jj
-    const int tid = threadIdx.x;
-    const long off = (long)blk * TILE;
-    double* Ab = K + off * Np + off;
-    for (int e = tid; e < TILE * TILE; e += DG_THREADS) {
-        int r = e >> 7, c = e & 127;
-        a[r * DG_LD + c] = Ab[(long)r * Np + c];
-    }
-    __syncthreads();
-    const int r = tid >> 2, h = tid & 3;
-    // ---- left-looking Cholesky, column by column
-    for (int j = 0; j < TILE; ++j) {
-        double s = 0.0;
-        if (r >= j) {
-            const double* ar = a + r * DG_LD;
-            const double* aj = a + j * DG_LD;
-            for (int k = h; k < j; k += 4) s = fma(ar[k], aj[k], s);
-        }
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        double v = 0.0;
-        if (r >= j) v = a[r * DG_LD + j] - s;
-        if (r == j && h == 0) piv[0] = v;
-        __syncthreads();
-        const double d = piv[0];
-        if (tid == 0) {
-            if (!(d > 0.0) && *info == 0) *info = (int)off + j + 1;   // LAPACK: first non-positive pivot
-        }
-        const double sd = sqrt(d);
-        if (h == 0 && r >= j) {
-            if (r == j) { a[r * DG_LD + j] = sd; rinv[j] = 1.0 / sd; lsum[j] = log(sd); }
-            else a[r * DG_LD + j] = v / sd;
-        }
-        __syncthreads();
-    }
-    // ---- triangular inverse X = L^-1 by forward substitution, one column c per 4-thread group.
-    // X[i][c] (i > c) is stored transposed in the strictly-upper part: a[c][i]; X[c][c] = rinv[c].
-    {
-        const int c = r;
-        double* xc = a + c * DG_LD;
-        const double rc = rinv[c];
-        const int cmin = (tid >> 5) * 8;   // smallest column of this warp: warp-uniform trip count
-        for (int i = cmin + 1; i < TILE; ++i) {
-            const bool active = i > c;
-            const double* li = a + i * DG_LD;
-            double s = 0.0;
-            if (active) {
-                if (h == 0) s = li[c] * rc;
-                for (int k = c + 1 + h; k < i; k += 4) s = fma(li[k], xc[k], s);
-            }
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            if (active && h == 0) xc[i] = -s * rinv[i];
-            __syncwarp();
-        }
-    }
-    __syncthreads();
-    // ---- write back: L (lower, zero above), D = L^-1 into S (zero above), D^T into DT
-    double* Sb = S + off * Np + off;
-    double* DTb = DT + (long)blk * TILE * TILE;
-    for (int e = tid; e < TILE * TILE; e += DG_THREADS) {
-        int i = e >> 7, c = e & 127;
-        double l = (c <= i) ? a[i * DG_LD + c] : 0.0;
-        double x = (c < i) ? a[c * DG_LD + i] : ((c == i) ? rinv[i] : 0.0);
-        Ab[(long)i * Np + c] = l;
-        Sb[(long)i * Np + c] = x;
-    }
-    for (int e = tid; e < TILE * TILE; e += DG_THREADS) {
-        int c = e >> 7, i = e & 127;   // DT[c][i] = D[i][c]
-        double x = (c < i) ? a[c * DG_LD + i] : ((c == i) ? rinv[i] : 0.0);
-        DTb[c * TILE + i] = x;
-    }
-    if (tid < 32) {
-        double t = 0.0;
-        for (int j = tid; j < TILE; j += 32)
-            if (off + j < N) t += lsum[j];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        if (tid == 0) logdet_blk[blk] = t;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Diagonal block, version 2 (default): blocked right-looking Cholesky with 8-wide panels, the triangular
-// inverse carried along as the forward substitution L X = I, and every rank-8 update (matrix and
-// right-hand side) on DMMA.8x8x4.  One CTA, 8 warps, the 128 x 128 block resident in shared memory:
-//   lower triangle  : A -> L
-//   strict upper    : B = I - sum L X (transposed) -> X^T, i.e. X[i][c] (i > c) lives at a[c][i]
-// Per panel p: (1) one thread factors the 8x8 diagonal block in registers (rsqrt-based, fully unrolled) and
-// inverts it; (2) 128 threads finish the panel rows L_ip = A_ip T^T while 128 threads finish the inverse's
-// block row X_pj = T B_pj; (3) 8 warps apply A_ij -= L_ip L_jp^T and B_ij -= L_ip X_pj with two DMMAs per
-// 8x8 block.  ~3 CTA barriers per panel instead of 2 per column.
-// ------------------------------------------------------------------------------------------------
-constexpr int D2_THREADS = 256;
-
-__global__ void __launch_bounds__(D2_THREADS, 1)
-potrf_diag2_kernel(double* __restrict__ K, int Np, int blk, int N, double* __restrict__ S, double* __restrict__ DT,
-                   double* __restrict__ logdet_blk, int* __restrict__ info) {
-    extern __shared__ double a[];            // [128][DG_LD]
-    double* rinv = a + TILE * DG_LD;         // [128] 1/L_jj
-    double* dg = rinv + TILE;                // [128] L_jj
-    double* Tb = dg + TILE;                  // [8][8] inverse of the current 8x8 diagonal block (lower)
-    __shared__ int bad_pivot;
-    const int tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
-    const int lr = lane >> 2, lc = lane & 3;
-    const long off = (long)blk * TILE;
-    double* Ab = K + off * Np + off;
-#ifdef GPX_DIAG_TIMING
-    long long t_mark = clock64(), t_acc[6] = {0, 0, 0, 0, 0, 0}, t_ph[4] = {0, 0, 0, 0};
-#define GPX_TICK(i) do { long long n_ = clock64(); t_acc[i] += n_ - t_mark; t_mark = n_; } while (0)
-#else
-#define GPX_TICK(i)
-#endif
-    if (tid == 0) bad_pivot = 0;
-    // 8192 double2 loads, 8 in flight per thread (one CTA has to pull 128 KB on its own)
-#pragma unroll 1
-    for (int e0 = tid; e0 < TILE * TILE / 2; e0 += 8 * D2_THREADS) {
-        double2 v[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int e = e0 + u * D2_THREADS, r = e >> 6, c = (e & 63) * 2;
-            v[u] = *reinterpret_cast<const double2*>(Ab + (long)r * Np + c);
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int e = e0 + u * D2_THREADS, r = e >> 6, c = (e & 63) * 2;
-            // B starts as the identity: zero strict upper part
-            *reinterpret_cast<double2*>(a + r * DG_LD + c) = make_double2(c <= r ? v[u].x : 0.0, c + 1 <= r ? v[u].y : 0.0);
-        }
-    }
-    __syncthreads();
-    GPX_TICK(0);
-    for (int p = 0; p < TILE / 8; ++p) {
-        const int c0 = 8 * p;
-        // ---- (1) 8x8 diagonal block on warp 0: lane (r = lane/4, q = lane%4) owns D[r][2q], D[r][2q+1]; one
-        //      pivot broadcast + rsqrt + three shuffles per column, then lanes 0..7 invert one column each
-        if (warp == 0) {
-            const unsigned full = 0xffffffffu;
-            double d0 = a[(c0 + lr) * DG_LD + c0 + 2 * lc];
-            double d1 = a[(c0 + lr) * DG_LD + c0 + 2 * lc + 1];
-            double inv_r = 0.0, sd_r = 0.0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int jq = j >> 1, je = j & 1;
-                const double sel = je ? d1 : d0;                        // this lane's entry of column j (if it has one)
-                const double piv = __shfl_sync(full, sel, j * 4 + jq);
-                if (!(piv > 0.0) && lane == 0 && bad_pivot == 0) bad_pivot = c0 + j + 1;
-                const double inv = rsqrt(piv);
-                const double sd = piv * inv;
-                const double lrj = __shfl_sync(full, sel, lr * 4 + jq) * inv;              // L[r][j], r > j
-                const double lc0 = __shfl_sync(full, sel, (2 * lc) * 4 + jq) * inv;        // L[2q][j]
-                const double lc1 = __shfl_sync(full, sel, (2 * lc + 1) * 4 + jq) * inv;    // L[2q+1][j]
-                if (lc == jq && lr >= j) {
-                    const double v = (lr == j) ? sd : lrj;
-                    if (je) d1 = v; else d0 = v;
-                }
-                if (2 * lc > j && lr >= 2 * lc) d0 = fma(-lrj, lc0, d0);
-                if (2 * lc + 1 > j && lr >= 2 * lc + 1) d1 = fma(-lrj, lc1, d1);
-                if (lr == j) { inv_r = inv; sd_r = sd; }
-            }
-            if (2 * lc <= lr) a[(c0 + lr) * DG_LD + c0 + 2 * lc] = d0;
-            if (2 * lc + 1 <= lr) a[(c0 + lr) * DG_LD + c0 + 2 * lc + 1] = d1;
-            if (lc == 0) { rinv[c0 + lr] = inv_r; dg[c0 + lr] = sd_r; }
-            __syncwarp();
-            if (lane < 8) {        // column `lane` of T = L_pp^-1 by forward substitution (entries above the diagonal come out 0)
-                double x[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    double acc_ = (i == lane) ? 1.0 : 0.0;
-#pragma unroll
-                    for (int k = 0; k < i; ++k) acc_ = fma(-a[(c0 + i) * DG_LD + c0 + k], x[k], acc_);
-                    x[i] = acc_ * rinv[c0 + i];
-                }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) Tb[i * 8 + lane] = x[i];
-            }
-        }
-        __syncthreads();
-        GPX_TICK(1);
-        // ---- (2) panel rows (threads 0..127) and the inverse's block row (threads 128..255)
-        if (tid < TILE) {
-            const int i = tid;
-            if (i >= c0 + 8) {
-                double v[8], o[8];
-                double* row = a + i * DG_LD + c0;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) v[k] = row[k];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    double s = 0.0;
-#pragma unroll
-                    for (int k = 0; k <= c; ++k) s = fma(v[k], Tb[c * 8 + k], s);
-                    o[c] = s;
-                }
-#pragma unroll
-                for (int c = 0; c < 8; ++c) row[c] = o[c];
-            }
-        } else {
-            const int c = tid - TILE;
-            if (c < c0 + 8) {
-                double b[8], x[8];
-                double* row = a + c * DG_LD + c0;      // transposed storage: B[p][c][r] at a[c][c0 + r]
-                const int cc = c - c0;                  // >= 0 inside the diagonal block
-#pragma unroll
-                for (int r = 0; r < 8; ++r) b[r] = (cc >= 0) ? ((r == cc) ? 1.0 : 0.0) : row[r];
-#pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    double s = 0.0;
-#pragma unroll
-                    for (int k = 0; k <= r; ++k) s = fma(Tb[r * 8 + k], b[k], s);
-                    x[r] = s;
-                }
-#pragma unroll
-                for (int r = 0; r < 8; ++r)
-                    if (cc < 0 || r > cc) row[r] = x[r];
-            }
-        }
-        __syncthreads();
-        GPX_TICK(2);
-        // ---- (3) rank-8 updates on DMMA.  Each warp owns whole block rows bi > p (A fragment loaded once) and
-        //      walks bj = 0..bi four blocks at a time: bj <= p are right-hand-side blocks (B_ij -= L_ip X_pj, stored
-        //      transposed), bj > p matrix blocks (A_ij -= L_ip L_jp^T).  No index decoding, 4-way ILP.
-        for (int bi = p + 1 + warp; bi < TILE / 8; bi += D2_THREADS / 32) {
-            const double* ar = a + (8 * bi + lr) * DG_LD + c0 + lc;
-            const double a0 = -ar[0], a1 = -ar[4];        // C - L L^T == (-L) L^T + C: accumulate in place
-#ifdef GPX_DIAG_TIMING
-            long long q0 = clock64();
-#endif
-            // phase A: every B fragment and every C block of the block row.  The panel columns are not written in
-            // this step and the blocks are disjoint, so ALL loads are issued before any DMMA / store (separate
-            // load -> modify -> store sequences per block would serialise on possible shared-memory aliasing).
-            double b0[16], b1[16], cv0[16], cv1[16];
-#pragma unroll
-            for (int bj = 0; bj < 16; ++bj) {
-                b0[bj] = 0.0; b1[bj] = 0.0; cv0[bj] = 0.0; cv1[bj] = 0.0;
-                if (bj <= bi) {
-                    if (bj == p) {      // X_pp = T: its storage overlaps L_pp, read the dense copy
-                        b0[bj] = Tb[lc * 8 + lr];
-                        b1[bj] = Tb[(lc + 4) * 8 + lr];
-                    } else {
-                        const double* br = a + (8 * bj + lr) * DG_LD + c0 + lc;
-                        b0[bj] = br[0];
-                        b1[bj] = br[4];
-                    }
-                    if (bj > p) {
-                        const double2 v = *reinterpret_cast<const double2*>(a + (8 * bi + lr) * DG_LD + 8 * bj + 2 * lc);
-                        cv0[bj] = v.x; cv1[bj] = v.y;
-                    } else {
-                        cv0[bj] = a[(8 * bj + 2 * lc) * DG_LD + 8 * bi + lr];
-                        cv1[bj] = a[(8 * bj + 2 * lc + 1) * DG_LD + 8 * bi + lr];
-                    }
-                }
-            }
-#ifdef GPX_DIAG_TIMING
-            long long q1 = clock64();
-#endif
-            // phase B: up to 16 independent 2-deep DMMA chains, accumulating onto the loaded blocks
-#pragma unroll
-            for (int bj = 0; bj < 16; ++bj)
-                if (bj <= bi) dmma884(cv0[bj], cv1[bj], a0, b0[bj]);
-#pragma unroll
-            for (int bj = 0; bj < 16; ++bj)
-                if (bj <= bi) dmma884(cv0[bj], cv1[bj], a1, b1[bj]);
-#ifdef GPX_DIAG_TIMING
-            long long q2 = clock64();
-#endif
-            // phase C: stores only
-#pragma unroll
-            for (int bj = 0; bj < 16; ++bj) {
-                if (bj <= bi) {
-                    if (bj > p) {
-                        *reinterpret_cast<double2*>(a + (8 * bi + lr) * DG_LD + 8 * bj + 2 * lc) = make_double2(cv0[bj], cv1[bj]);
-                    } else {
-                        a[(8 * bj + 2 * lc) * DG_LD + 8 * bi + lr] = cv0[bj];
-                        a[(8 * bj + 2 * lc + 1) * DG_LD + 8 * bi + lr] = cv1[bj];
-                    }
-                }
-            }
-#ifdef GPX_DIAG_TIMING
-            { long long q3 = clock64(); t_ph[0] += q1 - q0; t_ph[1] += q2 - q1; t_ph[2] += q3 - q2; t_ph[3] += 1; }
-#endif
-        }
-        __syncthreads();
-        GPX_TICK(3);
-    }
-    if (tid == 0 && bad_pivot != 0 && *info == 0) *info = (int)off + bad_pivot;
-    // ---- write back: L (lower, zero above), D = L^-1 into S (zero above), D^T into DT
-    double* Sb = S + off * Np + off;
-    double* DTb = DT + (long)blk * TILE * TILE;
-    auto xval = [&](int i, int c) -> double {        // X[i][c] = (L^-1)[i][c]
-        return (c < i) ? a[c * DG_LD + i] : ((c == i) ? rinv[i] : 0.0);
-    };
-#pragma unroll 4
-    for (int e = tid; e < TILE * TILE / 2; e += D2_THREADS) {
-        const int i = e >> 6, c = (e & 63) * 2;
-        const double2 lv = *reinterpret_cast<const double2*>(a + i * DG_LD + c);
-        *reinterpret_cast<double2*>(Ab + (long)i * Np + c) = make_double2(c <= i ? lv.x : 0.0, c + 1 <= i ? lv.y : 0.0);
-        *reinterpret_cast<double2*>(Sb + (long)i * Np + c) = make_double2(xval(i, c), xval(i, c + 1));
-    }
-#pragma unroll 4
-    for (int e = tid; e < TILE * TILE / 2; e += D2_THREADS) {
-        const int c = e >> 6, i = (e & 63) * 2;      // DT[c][i] = X[i][c]: contiguous in the transposed storage
-        double2 xv = make_double2(0.0, 0.0);
-        if (i > c) xv = *reinterpret_cast<const double2*>(a + c * DG_LD + i);
-        else if (i == c) xv = make_double2(rinv[c], a[c * DG_LD + c + 1]);
-        else if (i + 1 == c) xv = make_double2(0.0, rinv[c]);
-        *reinterpret_cast<double2*>(DTb + c * TILE + i) = xv;
-    }
-    __syncthreads();
-    GPX_TICK(4);
-#ifdef GPX_DIAG_TIMING
-    if (tid == 0) {     // timing build only
-        for (int i = 0; i < 5; ++i) logdet_blk[8 + i] = (double)t_acc[i];
-        for (int i = 0; i < 4; ++i) logdet_blk[20 + i] = (double)t_ph[i];
-    }
-#endif
-    if (tid < 32) {
-        double t = 0.0;
-        for (int j = tid; j < TILE; j += 32)
-            if (off + j < N) t += log(dg[j]);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        if (tid == 0) logdet_blk[blk] = t;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Diagonal block, version 3 (default): the whole 128 x 128 problem lives in REGISTERS.
-// v2's rank-8 updates were bound by shared-memory traffic (every 8x8 block was read-modify-written in smem once
-// per panel: 12 wavefronts for 2 DMMAs).  Here the 16 x 16 grid of 8x8 blocks is distributed once: warp w owns
+// Diagonal block, version 3 (GPX_DIAG_IMPL=3, kept as the A/B reference of v5): the whole 128 x 128 problem lives in
+// REGISTERS.  Its predecessors (v1: column by column in shared memory, 186 us; v2: 8-wide sub-panels in shared memory
+// with DMMA updates, 83 us, bound by shared-memory traffic -- 12 wavefronts per 2 DMMAs) are in the history only.
+// Here the 16 x 16 grid of 8x8 blocks is distributed once: warp w owns
 // block rows w and 15-w (17 lower-triangular blocks, perfectly balanced) of BOTH the matrix (A -> L) and the
 // right-hand side of L X = I (B -> X = L^-1), each block held as a DMMA C fragment (2 doubles per lane).
 // Per 8-wide panel p only the panel itself goes through shared memory:
@@ -603,341 +264,35 @@ potrf_diag3_kernel(double* __restrict__ K, int Np, int blk, int N, double* __res
 }
 
 // ------------------------------------------------------------------------------------------------
-// Diagonal block, version 4 (default): v3's register-resident block distribution, restructured around its measured
-// critical path (tools/diag_timing.cu: of v3's 123k cycles, 33k were the serial 8x8 factor by shuffles, ~14k the
-// owner's serial X-row finalisation, and the 75 KB unrolled body ran out of the instruction cache).
+// Diagonal block, version 5 (default): v3's register-resident block distribution, restructured around its measured
+// critical path (tools/diag_timing.cu: of v3's 123k cycles, 33k were the serial 8x8 factors done with shuffles and ~14k the
+// owner's serial X-row finalisation; the 75 KB unrolled loop body missed the instruction cache).
 //   * ONE accumulator per block slot: block (i,j) is first the Schur-updated A_ij (panels p < j), is finalised to
-//     L_ij at panel j and written out, and then restarts from zero as the right-hand side B_ij of L X = I
-//     (panels j <= p < i) until it is finalised to X_ij at panel i.  Half the registers, and the update code no longer
-//     exists twice (the loop body is ~4x smaller).
-//   * A ninth warp does nothing but factor the 8x8 diagonal blocks: every lane runs the whole 8x8 LDL^T recurrence
-//     redundantly in registers (no shuffles; the pivots chain through a reciprocal, the rsqrt's are off the chain), and
-//     lane c forms column c of T = L_pp^-1.  The owner of block row p+1 updates block (p+1,p+1) FIRST in panel p's
-//     update stage and hands it over through a named barrier, so the factor of panel p+1 overlaps the rank-8 updates
-//     of panel p.
+//     L_ij at panel j and written out, and then restarts as the right-hand side B_ij of L X = I (panels j <= p < i)
+//     until it is finalised to X_ij at panel i.
+//   * A dedicated factor warp does nothing but factor the 8x8 diagonal blocks: every lane runs the whole 8x8 LDL^T
+//     recurrence redundantly in registers (no shuffles; the pivots chain through a branch-free reciprocal, the rsqrt's
+//     are off the chain), and lane c forms column c of T = L_pp^-1.  The owner of block row p+1 updates block (p+1,p+1)
+//     FIRST in panel p's update stage and hands it over through a named barrier, so the factor of panel p+1 overlaps
+//     the rank-8 updates of panel p.
 //   * The right-hand-side updates use M_ip = L_ip T_p (one extra DMMA pair per block row, computed by the row's own
 //     warp) against the RAW row B_pj, i.e. B_ij -= (L_ip T_p) B_pj: the owner of row p only has to publish registers,
 //     and the outputs X_pj = T_p B_pj are formed from the published blocks by all warps, after the updates.
+//   * The 16 panels are unrolled at compile time (template <int P>): a rolled version issued 930 warp-instructions per
+//     panel and warp (ncu, profiles/r01_ncu_potrf_diag.txt), ~3x what the arithmetic needs -- select chains that pick
+//     "slot p" out of the register arrays, per-slot predicates.  With P static every slot index is an immediate, the
+//     phase of a slot is known at compile time and dead slots are never visited (260 instructions).
+//   * Published blocks are stored in FRAGMENT order (element `lane` of a block is the pair a DMMA operand needs), so an
+//     operand is one conflict-free LDS.128 and the C-fragment -> operand conversions go through a small per-warp
+//     shared-memory transposer instead of eight shuffles.
 // ------------------------------------------------------------------------------------------------
-constexpr int D4_THREADS = 288;
-constexpr int D4_BS = 96;
-constexpr int D4_BUF = 33 * D4_BS;        // 16 L blocks + 16 raw B blocks + T
-constexpr int D4_SMEM = (2 * D4_BUF + 3 * D4_BS + TILE) * 8;
-
-__device__ __forceinline__ void d4_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ void d4_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-
-struct D4Panel {
-    double* Lc; double* Xr; double* Dnext;
-    double* Ab; double* Sb; double* DTb;
-    double ta0, ta1, tk0, tk1;
-    int p, lr, lc, Np;
-};
-
-// block (bi, p) of a row that is still below the panel: L_ip = A_ip T^T (published + written out), M_ip = L_ip T,
-// the slot restarts as B_ip = -M_ip; a[] receives the A fragments of -L_ip and -M_ip.  Row p itself publishes its raw
-// blocks.  Straight-line on purpose (results of an inactive row are simply not committed): the two rows of a warp are
-// independent dependency chains of shuffles and DMMAs that the scheduler can interleave, and the shuffles stay outside
-// of conditional code.
-template <int NJ>
-__device__ __forceinline__ void d4_stage2_row(double (&c0)[NJ], double (&c1)[NJ], int bi, const D4Panel& P, double (&a)[4]) {
-    const int p = P.p, lr = P.lr, lc = P.lc;
-    const bool on = bi > p;
-    double v0 = 0.0, v1 = 0.0;
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) if (j == p) { v0 = c0[j]; v1 = c1[j]; }
-    double a0, a1;
-    d3_c_to_a(v0, v1, lr, lc, a0, a1);
-    double r0 = 0.0, r1 = 0.0;
-    dmma884(r0, r1, a0, P.ta0);
-    dmma884(r0, r1, a1, P.ta1);
-    if (on) {
-        *reinterpret_cast<double2*>(P.Lc + bi * D4_BS + lr * 12 + 2 * lc) = make_double2(r0, r1);
-        *reinterpret_cast<double2*>(P.Ab + (long)(8 * bi + lr) * P.Np + 8 * p + 2 * lc) = make_double2(r0, r1);
-    }
-    double l0, l1;
-    d3_c_to_a(r0, r1, lr, lc, l0, l1);
-    double m0 = 0.0, m1 = 0.0;
-    dmma884(m0, m1, l0, P.tk0);
-    dmma884(m0, m1, l1, P.tk1);
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) if (on && j == p) { c0[j] = -m0; c1[j] = -m1; }
-    double n0, n1;
-    d3_c_to_a(m0, m1, lr, lc, n0, n1);
-    a[0] = -l0; a[1] = -l1; a[2] = -n0; a[3] = -n1;
-    if (bi == p) {
-#pragma unroll
-        for (int j = 0; j < NJ; ++j)
-            if (j < p) *reinterpret_cast<double2*>(P.Xr + j * D4_BS + lr * 12 + 2 * lc) = make_double2(c0[j], c1[j]);
-    }
-}
-
-// the row that holds the next diagonal block updates it first and hands it to the factor warp
-template <int NJ>
-__device__ __forceinline__ bool d4_next_diag_row(double (&c0)[NJ], double (&c1)[NJ], int bi, const D4Panel& P, const double (&a)[4]) {
-    if (bi != P.p + 1) return false;
-    double v0 = 0.0, v1 = 0.0;
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) if (j == bi) { v0 = c0[j]; v1 = c1[j]; }
-    dmma884(v0, v1, a[0], -a[0]);              // A_qq -= L_qp L_qp^T  (B[k][n] = L_qp[n][k] has the A fragment's values)
-    dmma884(v0, v1, a[1], -a[1]);
-    *reinterpret_cast<double2*>(P.Dnext + P.lr * 12 + 2 * P.lc) = make_double2(v0, v1);
-    return true;
-}
-
-// rank-8 updates of one block row, eight slots at a time: all operand loads first, then the first k-step of every
-// active slot, then the second -- consecutive DMMAs are independent, so they issue back to back instead of each slot
-// paying load latency + two dependent DMMA latencies
-template <int NJ>
-__device__ __forceinline__ void d4_stage3_row(double (&c0)[NJ], double (&c1)[NJ], int bi, const D4Panel& P, const double (&a)[4]) {
-    const int p = P.p;
-    if (bi <= p) return;
-    const double* LcA = P.Lc + P.lr * 12 + P.lc;       // L_jp^T as B operand
-    const double* XrX = P.Xr + P.lc * 12 + P.lr;       // raw B_pj as B operand
-#pragma unroll
-    for (int j0 = 0; j0 < NJ; j0 += 8) {
-        if (j0 > bi) break;
-        double b0[8], b1[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int j = j0 + q;
-            const bool isA = j > p;
-            const double* bp = (isA ? LcA : XrX) + j * D4_BS;
-            b0[q] = 0.0; b1[q] = 0.0;
-            if (j <= bi && j != p && !(bi == p + 1 && j == bi)) { b0[q] = bp[0]; b1[q] = bp[isA ? 4 : 48]; }
-        }
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int j = j0 + q;
-            if (j <= bi && j != p && !(bi == p + 1 && j == bi)) dmma884(c0[j], c1[j], (j > p) ? a[0] : a[2], b0[q]);
-        }
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int j = j0 + q;
-            if (j <= bi && j != p && !(bi == p + 1 && j == bi)) dmma884(c0[j], c1[j], (j > p) ? a[1] : a[3], b1[q]);
-        }
-    }
-}
-
-__global__ void __maxnreg__(168)   // 9 warps are allocated as 12: 168 x 384 = 64512 registers
-potrf_diag4_kernel(double* __restrict__ K, int Np, int blk, int N, double* __restrict__ S, double* __restrict__ DT,
-                   double* __restrict__ logdet_blk, int* __restrict__ info) {
-    extern __shared__ double sm4[];
-    double* Draw = sm4 + 2 * D4_BUF;          // [2][8][12]: diagonal block handed to the factor warp
-    double* Lpp = Draw + 2 * D4_BS;           // [8][12]
-    double* dg = Lpp + D4_BS;                 // [128]
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const int lr = lane >> 2, lc = lane & 3;
-    const long off = (long)blk * TILE;
-    double* Ab = K + off * Np + off;
-    double* Sb = S + off * Np + off;
-    double* DTb = DT + (long)blk * TILE * TILE;
-
-    if (w == 8) {
-        // =================== factor warp ===================
-        int bad = 0;
-#ifdef GPX_DIAG_TIMING
-        long long f_mark = clock64(), f_acc[6] = {0, 0, 0, 0, 0, 0};
-#define GPX_TICKF(i) do { long long n_ = clock64(); f_acc[i] += n_ - f_mark; f_mark = n_; } while (0)
-#else
-#define GPX_TICKF(i)
-#endif
-        for (int p = 0; p < 16; ++p) {
-            double* Tb = sm4 + (p & 1) * D4_BUF + 32 * D4_BS;
-            const double* Dr = Draw + (p & 1) * D4_BS;
-            d4_bar_sync(1, 64);                               // block (p,p) published by the owner of row p
-            GPX_TICKF(0);
-            double a[8][8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-#pragma unroll
-                for (int j = 0; j <= i; j += 2) {
-                    const double2 v = *reinterpret_cast<const double2*>(Dr + i * 12 + j);
-                    a[i][j] = v.x;
-                    if (j + 1 <= i) a[i][j + 1] = v.y;
-                }
-            // LDL^T recurrence.  Column j of a[][] is overwritten by the unit-lower factor u_kj = a_kj / d_j once its
-            // rank-1 update is done; sd[j] = sqrt(d_j), inv[j] = 1/sqrt(d_j) come off the pivot chain.
-            double inv[8], sd[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const double d = a[j][j];
-                if (!(d > 0.0) && bad == 0) bad = 8 * p + j + 1;
-                const double r = __drcp_rn(d);
-                inv[j] = rsqrt(d);
-                sd[j] = d * inv[j];
-                double uj[8];
-#pragma unroll
-                for (int k = j + 1; k < 8; ++k) uj[k] = a[k][j] * r;
-#pragma unroll
-                for (int k = j + 1; k < 8; ++k)
-#pragma unroll
-                    for (int i = k; i < 8; ++i) a[i][k] = fma(-a[i][j], uj[k], a[i][k]);
-#pragma unroll
-                for (int k = j + 1; k < 8; ++k) a[k][j] = uj[k];
-            }
-            GPX_TICKF(1);
-            // L_pp = U D^1/2 ; T = D^-1/2 U^-1, column c = lane & 7 by forward substitution with the unit-lower U
-            const int c = lane & 7;
-            double x[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                double acc_ = (i == c) ? 1.0 : 0.0;
-#pragma unroll
-                for (int k = 0; k < i; ++k) acc_ = fma(-a[i][k], x[k], acc_);
-                x[i] = acc_;
-            }
-            GPX_TICKF(2);
-            if (lane < 8) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) Tb[i * 12 + lane] = x[i] * inv[i];
-            }
-            if (lane == 8) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-#pragma unroll
-                    for (int j = 0; j < 8; j += 2) {
-                        const double v0 = (j < i) ? a[i][j] * sd[j] : ((j == i) ? sd[i] : 0.0);
-                        const double v1 = (j + 1 < i) ? a[i][j + 1] * sd[j + 1] : ((j + 1 == i) ? sd[i] : 0.0);
-                        *reinterpret_cast<double2*>(Lpp + i * 12 + j) = make_double2(v0, v1);
-                    }
-                    dg[8 * p + i] = sd[i];
-                }
-            }
-            __syncwarp();
-            GPX_TICKF(3);
-            __syncthreads();                                  // #1: T_p visible to the compute warps
-            GPX_TICKF(4);
-            {   // outputs of the diagonal 8x8 block: L_pp -> K, T -> S and (transposed) DT
-                const double2 lf = *reinterpret_cast<const double2*>(Lpp + lr * 12 + 2 * lc);
-                const double2 tf = *reinterpret_cast<const double2*>(Tb + lr * 12 + 2 * lc);
-                const long r_ = 8 * p + lr, c_ = 8 * p + 2 * lc;
-                *reinterpret_cast<double2*>(Ab + r_ * Np + c_) = lf;
-                *reinterpret_cast<double2*>(Sb + r_ * Np + c_) = tf;
-                DTb[c_ * TILE + r_] = tf.x;
-                DTb[(c_ + 1) * TILE + r_] = tf.y;
-            }
-            __syncthreads();                                  // #2
-            GPX_TICKF(5);
-        }
-        __syncthreads();
-#ifdef GPX_DIAG_TIMING
-        if (lane == 0) for (int i = 0; i < 6; ++i) logdet_blk[40 + i] = (double)f_acc[i];
-#endif
-        if (lane == 0 && bad != 0 && *info == 0) *info = (int)off + bad;
-        return;
-    }
-
-    // =================== compute warps ===================
-    // warp w owns block rows w (blocks j = 0..w, accumulators cA) and 15-w (blocks j = 0..15-w, accumulators cB);
-    // slot j of a row is block column j, so every shared-memory offset below is an immediate
-    double cA0[8], cA1[8], cB0[16], cB1[16];
-    const int rA = w, rB = 15 - w;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        cA0[j] = 0.0; cA1[j] = 0.0;
-        if (j <= rA) {
-            const double2 v = *reinterpret_cast<const double2*>(Ab + (long)(8 * rA + lr) * Np + 8 * j + 2 * lc);
-            cA0[j] = v.x; cA1[j] = v.y;
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        cB0[j] = 0.0; cB1[j] = 0.0;
-        if (j <= rB) {
-            const double2 v = *reinterpret_cast<const double2*>(Ab + (long)(8 * rB + lr) * Np + 8 * j + 2 * lc);
-            cB0[j] = v.x; cB1[j] = v.y;
-        }
-    }
-    if (w == 0) {       // block (0,0) goes to the factor warp straight away
-        *reinterpret_cast<double2*>(Draw + lr * 12 + 2 * lc) = make_double2(cA0[0], cA1[0]);
-        __threadfence_block();
-        d4_bar_arrive(1, 64);
-    }
-    // while the first factor runs: zero the blocks above the diagonal of S and below the diagonal of DT
-    for (int b = w; b < 256; b += 8) {
-        const int bi = b >> 4, bj = b & 15;
-        if (bj > bi) {
-            const int rr = lane >> 2, cc = (lane & 3) * 2;
-            *reinterpret_cast<double2*>(Sb + (long)(8 * bi + rr) * Np + 8 * bj + cc) = make_double2(0.0, 0.0);
-            *reinterpret_cast<double2*>(DTb + (8 * bj + rr) * TILE + 8 * bi + cc) = make_double2(0.0, 0.0);
-        }
-    }
-
-#ifdef GPX_DIAG_TIMING
-    long long c_mark = clock64(), c_acc[6] = {0, 0, 0, 0, 0, 0};
-#define GPX_TICKC(i) do { long long n_ = clock64(); c_acc[i] += n_ - c_mark; c_mark = n_; } while (0)
-#else
-#define GPX_TICKC(i)
-#endif
-    for (int p = 0; p < 16; ++p) {
-        D4Panel P;
-        double* buf = sm4 + (p & 1) * D4_BUF;
-        P.Lc = buf;                            // published column p of L: block bi at Lc + bi*D4_BS, [8][12]
-        P.Xr = buf + 16 * D4_BS;               // published RAW row p of the right-hand side: block bj, stored [k][n]
-        const double* Tb = buf + 32 * D4_BS;   // T = L_pp^-1, [8][12], zeros above the diagonal
-        P.p = p; P.lr = lr; P.lc = lc; P.Np = Np; P.Ab = Ab; P.Sb = Sb; P.DTb = DTb;
-        P.Dnext = Draw + ((p + 1) & 1) * D4_BS;
-        __syncthreads();                       // #1: T_p published by the factor warp
-        GPX_TICKC(0);
-        P.ta0 = Tb[lr * 12 + lc]; P.ta1 = Tb[lr * 12 + lc + 4];           // T as A operand == T^T as B operand
-        P.tk0 = Tb[lc * 12 + lr]; P.tk1 = Tb[(lc + 4) * 12 + lr];         // T as B operand (B[k][n] = T[k][n])
-        double aA[4] = {0.0, 0.0, 0.0, 0.0}, aB[4] = {0.0, 0.0, 0.0, 0.0};   // A fragments of -L_ip (0,1) and -M_ip (2,3)
-        // ---- stage 2: finalise column p of L (<= 2 blocks per warp); the owner of row p publishes its raw row
-        d4_stage2_row<8>(cA0, cA1, rA, P, aA);
-        d4_stage2_row<16>(cB0, cB1, rB, P, aB);
-        GPX_TICKC(1);
-        __syncthreads();                       // #2
-        GPX_TICKC(2);
-        // ---- stage 3: the next diagonal block first (its factor then overlaps everything else), then the rest
-        if (d4_next_diag_row<8>(cA0, cA1, rA, P, aA) | d4_next_diag_row<16>(cB0, cB1, rB, P, aB)) {
-            __threadfence_block();
-            d4_bar_arrive(1, 64);
-        }
-        d4_stage3_row<8>(cA0, cA1, rA, P, aA);
-        d4_stage3_row<16>(cB0, cB1, rB, P, aB);
-        GPX_TICKC(3);
-        // ---- output row p of the inverse, X_pj = T_p B_pj (nobody in this kernel reads it): the raw blocks are in
-        //      shared memory, so the p blocks are dealt round-robin to the warps instead of burdening the row's owner
-        for (int j = w; j < p; j += 8) {
-            const double* bp = P.Xr + j * D4_BS + lc * 12 + lr;
-            double r0 = 0.0, r1 = 0.0;
-            dmma884(r0, r1, P.ta0, bp[0]);
-            dmma884(r0, r1, P.ta1, bp[48]);
-            const long r_ = 8 * p + lr, c_ = 8 * j + 2 * lc;
-            *reinterpret_cast<double2*>(Sb + r_ * Np + c_) = make_double2(r0, r1);
-            DTb[c_ * TILE + r_] = r0;
-            DTb[(c_ + 1) * TILE + r_] = r1;
-        }
-        GPX_TICKC(4);
-    }
-    __syncthreads();
-#ifdef GPX_DIAG_TIMING
-    if (tid == 0) for (int i = 0; i < 6; ++i) logdet_blk[48 + i] = (double)c_acc[i];
-#endif
-    if (tid < 32) {
-        double t = 0.0;
-        for (int j = tid; j < TILE; j += 32)
-            if (off + j < N) t += log(dg[j]);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        if (tid == 0) logdet_blk[blk] = t;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Diagonal block, version 5: v4's algorithm with the 16 panels unrolled at compile time (template <int P>).
-// ncu on v4 (profiles/): 930 issued warp-instructions per panel and warp, ~3x what the arithmetic needs -- select
-// chains that pick "slot p" out of the register arrays, per-slot predicates, shuffle conversions.  With P static every
-// slot index is an immediate, the phase of a slot (Schur update / right-hand side) is known at compile time and dead
-// slots are never visited.  Published blocks are stored in FRAGMENT order (element `lane` of a block is the pair a DMMA
-// operand needs), so an operand is one conflict-free LDS.128 and the C-fragment -> operand conversions go through a
-// small per-warp shared-memory transposer instead of eight shuffles.
-// ------------------------------------------------------------------------------------------------
+constexpr int D5_DS = 96;                 // doubles per row-major 8x8 block with rows padded to 12 (factor warp's in/out)
+__device__ __forceinline__ void d5_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void d5_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 constexpr int D5_THREADS = 384;           // 12 warps: warp 0 factors alone on its scheduler, 8 compute warps on the other three
 constexpr int D5_BS = 64;                 // doubles per published 8x8 block
 constexpr int D5_BUF = 34 * D5_BS;        // 16 L blocks | 16 raw right-hand-side blocks | T (A layout) | T (B layout)
-constexpr int D5_SMEM = (2 * D5_BUF + 3 * D4_BS + TILE + 16 * D5_BS) * 8;
+constexpr int D5_SMEM = (2 * D5_BUF + 3 * D5_DS + TILE + 16 * D5_BS) * 8;
 
 // index of element (r, c) of an 8x8 block in "A layout": lane lr*4+lc finds (M[lr][lc], M[lr][lc+4]) as one double2.
 // The same pair is the B operand of M^T (B[k][n] = M[n][k]).
@@ -1051,7 +406,7 @@ __device__ __forceinline__ void d5_panel(double (&cA0)[8], double (&cA1)[8], dou
     double* Xr = buf + 16 * D5_BS;
     const double* TA = buf + 32 * D5_BS;
     const double* TK = buf + 33 * D5_BS;
-    double* Dnext = X.sm + 2 * D5_BUF + ((P + 1) & 1) * D4_BS;
+    double* Dnext = X.sm + 2 * D5_BUF + ((P + 1) & 1) * D5_DS;
     const int rA = X.w, rB = 15 - X.w;
     constexpr bool HAS_A = (P < 7);                    // block row w <= 7 can only be below panel P if P < 7
     constexpr int PA = HAS_A ? P : 0;
@@ -1101,7 +456,7 @@ __device__ __forceinline__ void d5_panel(double (&cA0)[8], double (&cA1)[8], dou
         const double2 aLA = make_double2(-lA.x, -lA.y), aLB = make_double2(-lB.x, -lB.y);
         // ---- the next diagonal block first: its factor then overlaps everything below
         if (d5_next_diag_row<P, 8>(cA0, cA1, rA, X, aLA, Dnext) | d5_next_diag_row<P, 16>(cB0, cB1, rB, X, aLB, Dnext))
-            d4_bar_arrive(1, 64);
+            d5_bar_arrive(1, 64);
         GPX_TICK5(X, 3);
         // ---- stage 2b: M_ip = L_ip T; the slot restarts as B_ip = 0 - L_ip X_pp; A fragments of -M_ip
         double2 aMA = make_double2(0.0, 0.0), aMB = aMA;
@@ -1154,8 +509,8 @@ potrf_diag5_kernel(double* __restrict__ K, int Np, int blk, int N, double* __res
                    double* __restrict__ logdet_blk, int* __restrict__ info) {
     extern __shared__ double sm5[];
     double* Draw = sm5 + 2 * D5_BUF;          // [2][8][12] row-major: diagonal block handed to the factor warp
-    double* Lpp = Draw + 2 * D4_BS;           // [8][12]
-    double* dg = Lpp + D4_BS;                 // [128]
+    double* Lpp = Draw + 2 * D5_DS;           // [8][12]
+    double* dg = Lpp + D5_DS;                 // [128]
     double* scratch = dg + TILE;              // [8 warps][2][64]
     // The factor warp's ~250 dependent FP64 instructions per panel share the FP64 pipe of their scheduler with the
     // DMMAs of whatever else runs there (measured: 2150 instead of ~600 cycles next to two compute warps), so hardware
@@ -1170,11 +525,16 @@ potrf_diag5_kernel(double* __restrict__ K, int Np, int blk, int N, double* __res
     double* DTb = DT + (long)blk * TILE * TILE;
 
 #ifdef GPX_DIAG_TIMING
+#define GPX_TICKF(i) do { long long n_ = clock64(); f_acc[i] += n_ - f_mark; f_mark = n_; } while (0)
+#else
+#define GPX_TICKF(i)
+#endif
+#ifdef GPX_DIAG_TIMING
     __shared__ long long t5_stat[8];
     if (tid == 32) { for (int i = 0; i < 8; ++i) t5_stat[i] = 0; t5_stat[0] = clock64(); }
 #endif
     if (w == 8) {
-        // =================== factor warp (as in v4; T is published in both operand layouts) ===================
+        // =================== factor warp (T is published in both operand layouts) ===================
         int bad = 0;
 #ifdef GPX_DIAG_TIMING
         long long f_mark = clock64(), f_acc[6] = {0, 0, 0, 0, 0, 0};
@@ -1182,8 +542,8 @@ potrf_diag5_kernel(double* __restrict__ K, int Np, int blk, int N, double* __res
         for (int p = 0; p < 16; ++p) {
             double* TA = sm5 + (p & 1) * D5_BUF + 32 * D5_BS;
             double* TK = TA + D5_BS;
-            const double* Dr = Draw + (p & 1) * D4_BS;
-            d4_bar_sync(1, 64);                               // block (p,p) published by the owner of row p
+            const double* Dr = Draw + (p & 1) * D5_DS;
+            d5_bar_sync(1, 64);                               // block (p,p) published by the owner of row p
             GPX_TICKF(0);
             double a[8][8];
 #pragma unroll
@@ -1301,7 +661,7 @@ potrf_diag5_kernel(double* __restrict__ K, int Np, int blk, int N, double* __res
     }
     if (w == 0) {       // block (0,0) goes to the factor warp straight away
         *reinterpret_cast<double2*>(Draw + lr * 12 + 2 * lc) = make_double2(cA0[0], cA1[0]);
-        d4_bar_arrive(1, 64);        // bar.arrive/bar.sync order the shared-memory hand-over (PTX producer/consumer idiom)
+        d5_bar_arrive(1, 64);        // bar.arrive/bar.sync order the shared-memory hand-over (PTX producer/consumer idiom)
     }
     // while the first factor runs: zero the blocks above the diagonal of S and below the diagonal of DT
     for (int b = w; b < 256; b += 8) {
@@ -1650,11 +1010,7 @@ static void set_gemm_attrs() {
     cudaFuncSetAttribute(trtri_step1_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM_BYTES);
     cudaFuncSetAttribute(trtri_step2_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM_BYTES);
     cudaFuncSetAttribute(lauum_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM_BYTES);
-    const int dg = (TILE * DG_LD + 2 * TILE + 2) * 8;
-    cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dg);
-    cudaFuncSetAttribute(potrf_diag2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (TILE * DG_LD + 2 * TILE + 64) * 8);
     cudaFuncSetAttribute(potrf_diag3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D3_SMEM);
-    cudaFuncSetAttribute(potrf_diag4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D4_SMEM);
     cudaFuncSetAttribute(potrf_diag5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D5_SMEM);
     cudaFuncSetAttribute(potrf_panel_narrow_kernel<2, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM_BYTES);
     cudaFuncSetAttribute(potrf_panel_narrow_kernel<1, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM_BYTES);
@@ -1663,12 +1019,11 @@ static void set_gemm_attrs() {
     if (dev >= 0 && dev < 64) g_attr_set[dev] = true;
 }
 
-static int diag_impl() {       // GPX_DIAG_IMPL = 1 | 2 | 3 | 4 | 5 (default 5)
+static int diag_impl() {       // GPX_DIAG_IMPL = 3 | 5 (default 5)
     static int v = -1;
-    if (v < 0) { const char* e = getenv("GPX_DIAG_IMPL"); v = (e && e[0] >= '1' && e[0] <= '5') ? e[0] - '0' : 5; }
+    if (v < 0) { const char* e = getenv("GPX_DIAG_IMPL"); v = (e && e[0] == '3') ? 3 : 5; }
     return v;
 }
-static int use_diag_v1() { return diag_impl() == 1; }
 
 // Helper stream + events for the look-ahead (per device, created on first use; all work is ordered
 // after the caller's stream and joined back into it before potrf returns control of the data).
@@ -1722,8 +1077,6 @@ int potrf(double* K, int Np, int N, double* S, double* DT, double* logdet_blk, i
     set_gemm_attrs();
     cudaStream_t st = st_caller;
     const int nb = Np / TILE;
-    const int dg = (TILE * DG_LD + 2 * TILE + 2) * 8;
-    const int dg2 = (TILE * DG_LD + 2 * TILE + 64) * 8;
     LookAhead* la = use_lookahead() ? lookahead_for_current_device() : nullptr;
     cudaMemsetAsync(info, 0, sizeof(int), st);
     static int prio = -1;
@@ -1762,16 +1115,10 @@ int potrf(double* K, int Np, int N, double* S, double* DT, double* logdet_blk, i
         else potrf_trailing_kernel<<<grid, G_THREADS, G_SMEM_BYTES, s_>>>(K, Np, p, j0, i0);
     };
     auto diag = [&](int p) {
-        if (use_diag_v1())
-            potrf_diag_kernel<<<1, DG_THREADS, dg, st>>>(K, Np, p, N, S, DT, logdet_blk, info);
-        else if (diag_impl() == 2)
-            potrf_diag2_kernel<<<1, D2_THREADS, dg2, st>>>(K, Np, p, N, S, DT, logdet_blk, info);
-        else if (diag_impl() == 4)
-            potrf_diag4_kernel<<<1, D4_THREADS, D4_SMEM, st>>>(K, Np, p, N, S, DT, logdet_blk, info);
-        else if (diag_impl() == 5)
-            potrf_diag5_kernel<<<1, D5_THREADS, D5_SMEM, st>>>(K, Np, p, N, S, DT, logdet_blk, info);
-        else
+        if (diag_impl() == 3)
             potrf_diag3_kernel<<<1, D3_THREADS, D3_SMEM, st>>>(K, Np, p, N, S, DT, logdet_blk, info);
+        else
+            potrf_diag5_kernel<<<1, D5_THREADS, D5_SMEM, st>>>(K, Np, p, N, S, DT, logdet_blk, info);
     };
     static int ob_env = -1, sw_env = -1;
     if (ob_env < 0) { const char* e = getenv("GPX_POTRF_OB"); ob_env = (e && e[0] >= '1' && e[0] <= '8') ? e[0] - '0' : 0; }

@@ -1,4 +1,6 @@
-// Phase timing of potrf_diag2_kernel (clock64 stamps compiled in with -DGPX_DIAG_TIMING). Not part of the product.
+// Phase timing of the diagonal-block kernels (clock64 stamps compiled in with -DGPX_DIAG_TIMING) + a DMMA latency
+// probe.  Not part of the product.  Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -lcuda
+//                                          -o build/diag_timing tools/diag_timing.cu
 #define GPX_DIAG_TIMING 1
 #include "../gperks_b200/csrc/gpx_chol.cu"
 #include <cstdio>
@@ -12,18 +14,6 @@ int main() {
     double *K, *S, *DT, *ld; int* info;
     cudaMalloc(&K, Np * Np * 8); cudaMalloc(&S, Np * Np * 8); cudaMalloc(&DT, Np * Np * 8); cudaMalloc(&ld, 64 * 8); cudaMalloc(&info, 4);
     cudaMemset(info, 0, 4); cudaMemset(ld, 0, 64 * 8);
-    const int smem = (TILE * DG_LD + 2 * TILE + 64) * 8;
-    cudaFuncSetAttribute(potrf_diag2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    for (int rep = 0; rep < 3; ++rep) {
-        cudaMemcpy(K, A.data(), Np * Np * 8, cudaMemcpyHostToDevice); cudaMemset(ld, 0, 64 * 8);
-        potrf_diag2_kernel<<<1, D2_THREADS, smem>>>(K, Np, 0, Np, S, DT, ld, info);
-        cudaError_t e = cudaDeviceSynchronize();
-        double h[32]; cudaMemcpy(h, ld, 32 * 8, cudaMemcpyDeviceToHost);
-        int hi; cudaMemcpy(&hi, info, 4, cudaMemcpyDeviceToHost);
-        printf("rep %d err=%d info=%d  cycles: load=%.0f step1=%.0f step2=%.0f step3=%.0f writeback=%.0f  logdet=%.6f\n", rep, (int)e, hi,
-               h[8], h[9], h[10], h[11], h[12], h[0]);
-        printf("   warp0 step3 phases: loads=%.0f dmma=%.0f rmw=%.0f over %.0f block rows\n", h[20], h[21], h[22], h[23]);
-    }
     cudaFuncSetAttribute(potrf_diag3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D3_SMEM);
     for (int rep = 0; rep < 3; ++rep) {
         cudaMemcpy(K, A.data(), Np * Np * 8, cudaMemcpyHostToDevice); cudaMemset(ld, 0, 64 * 8);
@@ -32,22 +22,6 @@ int main() {
         double h[32]; cudaMemcpy(h, ld, 32 * 8, cudaMemcpyDeviceToHost);
         printf("v3 rep %d err=%d cycles (warp 0 view): load=%.0f stage1+wait=%.0f stage2=%.0f stage3=%.0f writeback=%.0f | owner: factor8x8=%.0f Tinv=%.0f (sums over 16 panels)\n",
                rep, (int)e, h[8], h[9], h[10], h[11], h[12], h[20], h[21]);
-    }
-    cudaFuncSetAttribute(potrf_diag4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D4_SMEM);
-    for (int rep = 0; rep < 3; ++rep) {
-        cudaMemcpy(K, A.data(), Np * Np * 8, cudaMemcpyHostToDevice); cudaMemset(ld, 0, 64 * 8);
-        cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-        cudaEventRecord(e0);
-        potrf_diag4_kernel<<<1, D4_THREADS, D4_SMEM>>>(K, Np, 0, Np, S, DT, ld, info);
-        { cudaError_t le = cudaGetLastError(); if (le != cudaSuccess) printf("launch error: %s\n", cudaGetErrorString(le)); }
-        cudaEventRecord(e1);
-        cudaError_t e = cudaDeviceSynchronize();
-        float ms; cudaEventElapsedTime(&ms, e0, e1);
-        double h[64]; cudaMemcpy(h, ld, 64 * 8, cudaMemcpyDeviceToHost);
-        printf("v4 rep %d err=%d %.1f us | factor warp cycles: wait_block=%.0f load+ldl=%.0f usolve=%.0f store=%.0f wait#1=%.0f out+wait#2=%.0f\n",
-               rep, (int)e, ms * 1e3, h[40], h[41], h[42], h[43], h[44], h[45]);
-        printf("            compute warp 0 cycles: wait#1=%.0f stage2=%.0f wait#2=%.0f stage3=%.0f output=%.0f (sums over 16 panels)\n",
-               h[48], h[49], h[50], h[51], h[52]);
     }
     cudaFuncSetAttribute(potrf_diag5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D5_SMEM);
     for (int rep = 0; rep < 4; ++rep) {
