@@ -13,6 +13,7 @@
 #include "gpx_common.cuh"
 #include "gpx_gemm_tma.cuh"
 #include <stdlib.h>
+#include <mutex>
 
 namespace gpx {
 
@@ -1028,6 +1029,7 @@ static int diag_impl() {       // GPX_DIAG_IMPL = 3 | 5 (default 5)
 // Helper stream + events for the look-ahead (per device, created on first use; all work is ordered
 // after the caller's stream and joined back into it before potrf returns control of the data).
 struct LookAhead {
+    std::mutex enqueue;                    // the helper streams/events are shared per device: one potrf enqueues at a time
     cudaStream_t side = nullptr;
     cudaStream_t chain = nullptr;          // highest-priority stream for the critical path (GPX_POTRF_PRIO=1)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -1078,6 +1080,10 @@ int potrf(double* K, int Np, int N, double* S, double* DT, double* logdet_blk, i
     cudaStream_t st = st_caller;
     const int nb = Np / TILE;
     LookAhead* la = use_lookahead() ? lookahead_for_current_device() : nullptr;
+    // Every event record/wait pair below is resolved at enqueue time, so holding the lock while enqueuing is enough to
+    // keep concurrent callers (other host threads, other streams) from interleaving their fork/join sequences.
+    std::unique_lock<std::mutex> enqueue_lock;
+    if (la != nullptr) enqueue_lock = std::unique_lock<std::mutex>(la->enqueue);
     cudaMemsetAsync(info, 0, sizeof(int), st);
     static int prio = -1;
     if (prio < 0) { const char* e = getenv("GPX_POTRF_PRIO"); prio = (e && e[0] == '0') ? 0 : 1; }

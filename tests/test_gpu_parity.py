@@ -124,6 +124,56 @@ def test_failed_cholesky_reports_info_and_jitter_path(dev):
     assert info == int(ref_info) and info > 0
 
 
+def _spd(n, dev, seed):
+    g = torch.Generator().manual_seed(seed)
+    X = torch.rand(n, 6, dtype=F64, generator=g).to(dev)
+    ls = torch.linspace(0.4, 0.9, 6, dtype=F64, device=dev)
+    K = torch.empty(n, n, dtype=F64, device=dev)
+    for lo in range(0, n, 2048):
+        K[lo:lo + 2048] = O.kernel_from_r2(O.sq_dist(X[lo:lo + 2048], X, ls), O.KIND_MATERN52, 1.0)
+    K.diagonal().add_(1e-2)
+    return K
+
+
+def _potrf_cabi(K, dev):
+    """gpx_potrf on a padded copy of K (identity padding, as the engine lays it out); returns (L, info)."""
+    lib = nv.lib()
+    n = K.shape[0]
+    Np = nv.padded(n)
+    A = torch.eye(Np, dtype=F64, device=dev)
+    A[:n, :n] = K
+    S = torch.zeros(Np, Np, dtype=F64, device=dev)
+    DT = torch.zeros(Np // 128, 128, 128, dtype=F64, device=dev)
+    logdet = torch.zeros(Np // 128, dtype=F64, device=dev)
+    info = torch.zeros(1, dtype=torch.int32, device=dev)
+    nv.check(lib.gpx_potrf(nv.ptr(A), Np, n, nv.ptr(S), nv.ptr(DT), nv.ptr(logdet), nv.ptr(info), nv.stream_ptr()), "potrf")
+    torch.cuda.synchronize()
+    return torch.tril(A[:n, :n]), int(info.item()), float(logdet.sum())
+
+
+@pytest.mark.parametrize("n", [129, 1000, 4200, 5000, 12500])
+def test_potrf_schedules_match_cusolver(dev, n):
+    """The Cholesky through its own C-ABI entry at sizes that exercise every schedule: one-panel look-ahead with 32- and
+    64-row panel/column tiles (nb <= 32), the two-level K=384 outer updates (33 <= nb < 96) and K=512 (nb >= 96)."""
+    K = _spd(n, dev, seed=n)
+    L, info, logdet = _potrf_cabi(K, dev)
+    Lref = torch.linalg.cholesky(K)
+    assert info == 0
+    assert float((L - Lref).abs().max() / Lref.abs().max()) < 1e-11
+    np.testing.assert_allclose(logdet, float(torch.log(torch.diagonal(Lref)).sum()), rtol=1e-11)
+
+
+@pytest.mark.parametrize("n,bad", [(300, 5), (300, 200), (4500, 130), (4500, 4100)])
+def test_potrf_info_is_first_bad_pivot(dev, n, bad):
+    """LAPACK convention: info = order of the first leading minor that is not positive definite, wherever it falls
+    (first/late 8x8 sub-block of a diagonal block, early two-level part, chain-bound tail)."""
+    K = _spd(n, dev, seed=n + bad)
+    K[bad, bad] = -1.0
+    _, info, _ = _potrf_cabi(K, dev)
+    _, ref_info = torch.linalg.cholesky_ex(K)
+    assert info == int(ref_info) == bad + 1
+
+
 # ----------------------------------------------------------------------------------------------------
 # public API: notebook goldens + oracle parity through GPExperiment / GPEmulator
 # ----------------------------------------------------------------------------------------------------
