@@ -163,6 +163,17 @@ def test_potrf_schedules_match_cusolver(dev, n):
     np.testing.assert_allclose(logdet, float(torch.log(torch.diagonal(Lref)).sum()), rtol=1e-11)
 
 
+def test_potrf_is_bitwise_reproducible(dev):
+    """No atomics, fixed reduction orders, and every cross-warp / cross-stream hand-over ordered by a barrier or an
+    event: repeated factorizations of one matrix must agree bit for bit (a race would show up here first)."""
+    for n in (700, 4500):
+        K = _spd(n, dev, seed=3)
+        L0, _, ld0 = _potrf_cabi(K, dev)
+        for _ in range(12):
+            L, info, ld = _potrf_cabi(K, dev)
+            assert info == 0 and ld == ld0 and torch.equal(L, L0)
+
+
 @pytest.mark.parametrize("n,bad", [(300, 5), (300, 200), (4500, 130), (4500, 4100)])
 def test_potrf_info_is_first_bad_pivot(dev, n, bad):
     """LAPACK convention: info = order of the first leading minor that is not positive definite, wherever it falls
