@@ -53,7 +53,12 @@ class KFoldCrossValidation(Trainable):
         self.emulator: Optional[GPEmulator] = None
 
     def train(self, optimizer, early_stopping_criterion: Optional[EarlyStoppingCriterion] = None,
-              snapshotting_criterion: Optional[SnapshottingCriterion] = None, leftout_is_val: bool = False):
+              snapshotting_criterion: Optional[SnapshottingCriterion] = None, leftout_is_val: bool = False, *,
+              parallel_restarts: bool = False):
+        """``parallel_restarts`` (extension): deal the n_splits x n_restarts independent fits, not just
+        the folds, over ``devices`` -- e.g. 5 folds x 8 restarts = 40 jobs on 8 GPUs in 5 waves instead of 5 GPUs each
+        running 8 restarts in a row.  Every (fold, restart) job starts from the raw hyper-parameter draw it would get
+        in the sequential run and uses a fresh optimizer (see ``GPEmulator.train``)."""
         if early_stopping_criterion is None:
             early_stopping_criterion = NoEarlyStoppingCriterion(DEFAULT_TRAIN_MAX_EPOCH)
         if snapshotting_criterion is None:
@@ -63,6 +68,8 @@ class KFoldCrossValidation(Trainable):
         self.leftout_is_val = leftout_is_val
         X, y = self.experiment.dataset.X_train, self.experiment.dataset.y_train
         opt_spec = (optimizer.__class__, dict(optimizer.defaults))
+        if parallel_restarts:
+            return self._train_fold_restart_jobs(opt_spec, early_stopping_criterion, snapshotting_criterion, X, y)
         tasks = {
             i: (opt_spec, early_stopping_criterion, snapshotting_criterion, i, device, X[tr], y[tr], X[lo], y[lo], tr, lo)
             for i, (device, (tr, lo)) in enumerate(zip(cycle(self.devices), self.split_generator.split(X)))
@@ -72,7 +79,9 @@ class KFoldCrossValidation(Trainable):
                 self._train_split, tasks, self.max_workers).items():
             models[split] = {k: torch.as_tensor(v) for k, v in best_model.items()}
             stats[split], scores[split], idx[split] = best_stats, test_scores, split_idx
+        return self._finish(models, stats, scores, idx)
 
+    def _finish(self, models, stats, scores, idx):
         names = [get_metric_name(m) for m in self.experiment.metrics]
         self.best_test_scores_structured_dct = {n: [float(np.asarray(scores[s][n]).item()) for s in range(self.n_splits)]
                                                 for n in names}
@@ -106,21 +115,60 @@ class KFoldCrossValidation(Trainable):
         emulator.model.load_state_dict(best_state)
         return emulator
 
-    def _train_split(self, opt_spec, early_stopping_criterion, snapshotting_criterion, i, device, X_train, y_train,
-                     X_leftout, y_leftout, idx_train, idx_leftout):
-        log.info(f"Running K-fold split {i}...")
+    def _train_fold_restart_jobs(self, opt_spec, early_stopping_criterion, snapshotting_criterion, X, y):
+        splits = list(self.split_generator.split(X))
+        n_restarts = self.experiment.n_restarts
+        devices = cycle(self.devices)
+        tasks = {(i, r): (opt_spec, early_stopping_criterion, snapshotting_criterion, i, r, next(devices),
+                          X[tr], y[tr], X[lo], y[lo])
+                 for i, (tr, lo) in enumerate(splits) for r in range(1, n_restarts + 1)}
+        results = execute_task_in_parallel(self._train_split_restart, tasks, self.max_workers)
+        models, stats, scores, idx = {}, {}, {}, {}
+        for i, (tr, lo) in enumerate(splits):
+            # best restart of the fold, its snapshot and its test scores: same selection as GPEmulator.train
+            emulator = GPEmulator(self._fold_experiment(self._fold_dataset(X[tr], y[tr], X[lo], y[lo])),
+                                  self.devices[i % len(self.devices)])
+            snpc = self._split_snapshotting(snapshotting_criterion, i)
+            best_model, best_stats = emulator._select_best_restart(
+                [results[(i, r)][0] for r in range(1, n_restarts + 1)],
+                [results[(i, r)][1] for r in range(1, n_restarts + 1)], snpc)
+            inference = Inference(emulator)
+            inference.summary(printtoconsole=False)
+            models[i] = {k: torch.as_tensor(v) for k, v in best_model.items()}
+            stats[i], scores[i], idx[i] = best_stats, inference.scores_dct, [tr, lo]
+        return self._finish(models, stats, scores, idx)
+
+    def _train_split_restart(self, opt_spec, early_stopping_criterion, snapshotting_criterion, i, restart, device,
+                             X_train, y_train, X_leftout, y_leftout):
+        from ..train.emulator import train_restart_job
+        log.info(f"Running K-fold split {i}, restart {restart}...")
+        experiment = self._fold_experiment(self._fold_dataset(X_train, y_train, X_leftout, y_leftout))
+        # the random stream right after the fold's experiment is built is where the sequential run starts drawing
+        return train_restart_job(experiment, None, device, restart, torch.get_rng_state(), opt_spec,
+                                 early_stopping_criterion, self._split_snapshotting(snapshotting_criterion, i))
+
+    def _fold_dataset(self, X_train, y_train, X_leftout, y_leftout) -> Dataset:
         ds = self.experiment.dataset
         if self.leftout_is_val:
             X_val, y_val = X_leftout, y_leftout
         else:
             X_val, y_val = ds.X_val, ds.y_val
-        dataset = Dataset(X_train, y_train, X_val=X_val, y_val=y_val, X_test=X_leftout, y_test=y_leftout,
-                          x_labels=ds.x_labels, y_label=ds.y_label)
-        experiment = self._fold_experiment(dataset)
+        return Dataset(X_train, y_train, X_val=X_val, y_val=y_val, X_test=X_leftout, y_test=y_leftout,
+                       x_labels=ds.x_labels, y_label=ds.y_label)
+
+    @staticmethod
+    def _split_snapshotting(snapshotting_criterion, i):
+        snpc = deepcopy(snapshotting_criterion)
+        snpc.snapshot_dir = snpc.snapshot_dir.replace("{restart}", "{{restart}}").format(split=i)
+        return snpc
+
+    def _train_split(self, opt_spec, early_stopping_criterion, snapshotting_criterion, i, device, X_train, y_train,
+                     X_leftout, y_leftout, idx_train, idx_leftout):
+        log.info(f"Running K-fold split {i}...")
+        experiment = self._fold_experiment(self._fold_dataset(X_train, y_train, X_leftout, y_leftout))
         opt_cls, opt_defaults = opt_spec
         optimizer = opt_cls(experiment.model.parameters(), **opt_defaults)
-        esc, snpc = deepcopy(early_stopping_criterion), deepcopy(snapshotting_criterion)
-        snpc.snapshot_dir = snpc.snapshot_dir.replace("{restart}", "{{restart}}").format(split=i)
+        esc, snpc = deepcopy(early_stopping_criterion), self._split_snapshotting(snapshotting_criterion, i)
         emulator = GPEmulator(experiment, device)
         best_model, best_stats = emulator.train(optimizer, early_stopping_criterion=esc, snapshotting_criterion=snpc)
         log.info(f"Run K-fold split {i}.")

@@ -95,7 +95,14 @@ class GPEmulator(Trainable):
 
     def train(self, optimizer,
               early_stopping_criterion: Optional[EarlyStoppingCriterion] = None,
-              snapshotting_criterion: Optional[SnapshottingCriterion] = None):
+              snapshotting_criterion: Optional[SnapshottingCriterion] = None, *,
+              devices: Optional[List[str]] = None, max_workers: Optional[int] = None):
+        """``devices`` (extension): restarts are independent fits, so with a device list they are
+        dealt round-robin onto those GPUs and run in spawned workers, one fit per GPU at a time, instead of one after
+        the other.  Each restart starts from the same raw hyper-parameter draw as in the sequential run (the random
+        stream is replayed), but gets a fresh optimizer (``optimizer.__class__(params, **optimizer.defaults)``, as the
+        reference's K-fold does per split) -- the sequential loop carries the optimizer's moment estimates from one
+        restart into the next, so restarts >= 2 follow slightly different trajectories in the two modes."""
         if early_stopping_criterion is None:
             early_stopping_criterion = NoEarlyStoppingCriterion(DEFAULT_TRAIN_MAX_EPOCH)
         if snapshotting_criterion is None:
@@ -109,15 +116,37 @@ class GPEmulator(Trainable):
 
             all_stats: List[TrainStats] = []
             best_epochs: List[int] = []
-            for restart in range(1, self.experiment.n_restarts + 1):
-                log.info(f"Running restart {restart}...")
-                self.restart_idx = restart
-                stats, best_epoch = self._train_once(X_train, y_train, optimizer, X_val, y_val,
-                                                     early_stopping_criterion, snapshotting_criterion)
-                all_stats.append(stats)
-                best_epochs.append(best_epoch)
-                log.info(f"Run restart {restart}.")
+            if devices:
+                all_stats, best_epochs = self._train_restarts_on_devices(optimizer, early_stopping_criterion,
+                                                                         snapshotting_criterion, list(devices), max_workers)
+            else:
+                for restart in range(1, self.experiment.n_restarts + 1):
+                    log.info(f"Running restart {restart}...")
+                    self.restart_idx = restart
+                    stats, best_epoch = self._train_once(X_train, y_train, optimizer, X_val, y_val,
+                                                         early_stopping_criterion, snapshotting_criterion)
+                    all_stats.append(stats)
+                    best_epochs.append(best_epoch)
+                    log.info(f"Run restart {restart}.")
         log.info("Trained emulator.")
+        return self._select_best_restart(all_stats, best_epochs, snapshotting_criterion)
+
+    def _train_restarts_on_devices(self, optimizer, early_stopping_criterion, snapshotting_criterion,
+                                   devices: List[str], max_workers: Optional[int]):
+        from ..utils.concurrency import execute_task_in_parallel
+        n = self.experiment.n_restarts
+        rng_state = torch.get_rng_state()
+        opt_spec = (optimizer.__class__, dict(optimizer.defaults))
+        tasks = {r: (self.experiment, self.init_state, devices[(r - 1) % len(devices)], r, rng_state, opt_spec,
+                     early_stopping_criterion, snapshotting_criterion) for r in range(1, n + 1)}
+        results = execute_task_in_parallel(train_restart_job, tasks, max_workers or len(devices))
+        torch.set_rng_state(rng_state)          # (in-process jobs moved it) leave the caller's random stream where the
+        for _ in range(n):                      # sequential loop would
+            self._draw_restart_init()
+        return [results[r][0] for r in range(1, n + 1)], [results[r][1] for r in range(1, n + 1)]
+
+    def _select_best_restart(self, all_stats: List[TrainStats], best_epochs: List[int],
+                             snapshotting_criterion: SnapshottingCriterion):
 
         # best restart: validation loss at each restart's best epoch if available, else training loss
         key = "val_loss" if self.scaled_data.with_val else "train_loss"
@@ -144,14 +173,21 @@ class GPEmulator(Trainable):
     def _reinit_hyperparameters(self):
         """Raw (pre-softplus) values ~ U(log 0.1, log 10) for lengthscales, outputscale and noise; the mean
         parameters keep their initial state (GPErks/train/emulator.py:230-244)."""
+        raw_ls, raw_os, raw_noise = self._draw_restart_init()
+        self.model.initialize(**{
+            "covar_module.base_kernel.raw_lengthscale": raw_ls,
+            "covar_module.raw_outputscale": raw_os,
+        })
+        if raw_noise is not None:
+            self.model.likelihood.initialize(raw_noise=raw_noise)
+
+    def _draw_restart_init(self):
+        """One restart's draws from the global torch generator, in the reference's order (lengthscales, outputscale,
+        noise); also used to replay the stream when restarts run out of order in worker processes."""
         lo, hi = numpy.log(1e-1), numpy.log(1e1)
         draw = lambda n: (hi - lo) * torch.rand(n) + lo  # noqa: E731  (default dtype: same stream as the reference)
-        self.model.initialize(**{
-            "covar_module.base_kernel.raw_lengthscale": draw(self.scaled_data.input_size),
-            "covar_module.raw_outputscale": draw(1),
-        })
-        if self.learn_noise:
-            self.model.likelihood.initialize(raw_noise=draw(1))
+        raw_ls, raw_os = draw(self.scaled_data.input_size), draw(1)
+        return raw_ls, raw_os, (draw(1) if self.learn_noise else None)
 
     def _train_once(self, X_train, y_train, optimizer, X_val, y_val,
                     early_stopping_criterion: EarlyStoppingCriterion,
@@ -460,6 +496,29 @@ class GPEmulator(Trainable):
         log.info("Loading model from hyperparameters state dictionary...")
         self.model.load_state_dict(torch.load(model_path, map_location=torch.device("cpu")))
         log.info("Loaded model.")
+
+
+def train_restart_job(experiment: GPExperiment, init_state, device: str, restart: int, rng_state, opt_spec,
+                      early_stopping_criterion, snapshotting_criterion):
+    """One restart as a self-contained job (runs in a spawned worker, one GPU): rebuilds the emulator on ``device``,
+    replays the random stream up to this restart's draw and trains it.  Returns ``(TrainStats, best_epoch)``; the
+    snapshots it wrote are picked up by the parent through the shared snapshot directory."""
+    torch.set_rng_state(rng_state)
+    emulator = GPEmulator(experiment, device)
+    if init_state is not None:
+        emulator.init_state = init_state
+    for _ in range(restart - 1):
+        emulator._draw_restart_init()
+    opt_cls, opt_defaults = opt_spec
+    optimizer = opt_cls(emulator.model.parameters(), **opt_defaults)
+    emulator.restart_idx = restart
+    sd = emulator.scaled_data
+    log.info(f"Running restart {restart} on {device}...")
+    with torch.cuda.device(emulator._compute_device()):
+        stats, best_epoch = emulator._train_once(sd.X_train, sd.y_train, optimizer, sd.X_val, sd.y_val,
+                                                 deepcopy(early_stopping_criterion), deepcopy(snapshotting_criterion))
+    log.info(f"Run restart {restart}.")
+    return stats, best_epoch
 
 
 def _relink(target: str, link: str):

@@ -1,6 +1,8 @@
 """GPU tests of the consumers that sit on the hot path: history matching, Sobol' GSA,
 K-fold cross validation, Inference / Diagnostics -- against the reference's formulas restated in numpy, the
 notebook goldens and analytic Sobol' indices."""
+import json
+
 import numpy as np
 import pytest
 import torch
@@ -140,3 +142,64 @@ def test_kfold_cross_validation(dev, tmp_path):
     assert mean.shape == (5,) and (std > 0).all()
     for s in range(3):
         assert (tmp_path / f"split_{s}" / "best_model.pth").exists()
+
+
+def _restart_experiment(n_restarts, seed=8):
+    from gperks_b200.gp.data.dataset import Dataset
+    from gperks_b200.gp.experiment import GPExperiment
+    from gperks_b200.gp.mean import LinearMean
+    from gperks_b200.kernels import MaternKernel, ScaleKernel
+    from gperks_b200.likelihoods import GaussianLikelihood
+    from gperks_b200.utils.metrics import MeanSquaredError, R2Score
+    from gperks_b200.utils.test_functions import currin_exp
+    ds = Dataset.build_from_function(currin_exp, 2, 40, None, 15, "lhs", seed)
+    torch.manual_seed(seed)     # LinearMean draws its initial weights when it is constructed, before GPExperiment seeds
+    exp = GPExperiment(ds, GaussianLikelihood(), LinearMean(1, 2), ScaleKernel(MaternKernel(ard_num_dims=2)),
+                       n_restarts=n_restarts, seed=seed, metrics=[MeanSquaredError(), R2Score()])
+    return exp, ds
+
+
+def test_restarts_as_device_jobs_replay_the_sequential_draws(dev, tmp_path):
+    """`train(devices=[...])` runs every restart as a self-contained job.  Restart r must start from the raw
+    hyper-parameters the sequential loop draws for it; restart 1 (fresh optimizer in both modes) must reproduce the
+    sequential trajectory exactly, and the selection / snapshot links must work from the jobs' files."""
+    from gperks_b200.train.early_stop import NoEarlyStoppingCriterion
+    from gperks_b200.train.emulator import GPEmulator
+    from gperks_b200.train.snapshot import NeverSaveSnapshottingCriterion
+    runs = {}
+    for mode in ("sequential", "jobs"):
+        exp, ds = _restart_experiment(3)
+        em = GPEmulator(exp, "cuda:0")
+        opt = torch.optim.Adam(exp.model.parameters(), lr=0.1)
+        root = tmp_path / mode
+        snap = NeverSaveSnapshottingCriterion((root / "restart_{restart}").as_posix(), "epoch_{epoch}.pth")
+        kw = {"devices": ["cuda:0"], "max_workers": 1} if mode == "jobs" else {}
+        best_model, best_stats = em.train(opt, NoEarlyStoppingCriterion(25), snap, **kw)
+        stats = [json.loads((root / f"restart_{r}" / "train_stats.json").read_text()) for r in (1, 2, 3)]
+        runs[mode] = (stats, best_stats, em.predict(ds.X_test), torch.rand(1).item())
+        assert (root / "best_model.pth").exists() and (root / "best_train_stats.json").exists()
+    seq, job = runs["sequential"], runs["jobs"]
+    np.testing.assert_allclose(seq[0][0]["train_loss"], job[0][0]["train_loss"], rtol=1e-10)      # restart 1: identical
+    for r in (1, 2):            # later restarts: same starting point, optimizer moments not carried over
+        assert seq[0][r]["train_loss"][0] == pytest.approx(job[0][r]["train_loss"][0], rel=1e-10)
+    assert seq[3] == job[3], "the caller's random stream must end where the sequential loop leaves it"
+    assert len(job[1].train_loss) == 25 and np.isfinite(job[2][0]).all()
+
+
+def test_kfold_with_fold_restart_jobs(dev, tmp_path):
+    from gperks_b200.perks.cross_validation import KFoldCrossValidation
+    from gperks_b200.train.early_stop import NoEarlyStoppingCriterion
+    from gperks_b200.train.snapshot import NeverSaveSnapshottingCriterion
+    exp, ds = _restart_experiment(2)
+    opt = torch.optim.Adam(exp.model.parameters(), lr=0.1)
+    snap = NeverSaveSnapshottingCriterion((tmp_path / "split_{split}" / "restart_{restart}").as_posix(), "epoch_{epoch}.pth")
+    cv = KFoldCrossValidation(exp, ["cuda:0"], n_splits=3, max_workers=1)
+    models, stats = cv.train(opt, NoEarlyStoppingCriterion(20), snap, parallel_restarts=True)
+    assert set(models) == {0, 1, 2} and all(len(stats[s].train_loss) == 20 for s in stats)
+    for s in range(3):
+        for r in (1, 2):
+            assert (tmp_path / f"split_{s}" / f"restart_{r}" / "train_stats.json").exists()
+        assert (tmp_path / f"split_{s}" / "best_model.pth").exists()
+    assert min(cv.best_test_scores_structured_dct["R2Score"]) > 0.8
+    mean, std = cv.emulator.predict(ds.X_train[:4])
+    assert mean.shape == (4,) and (std > 0).all()
