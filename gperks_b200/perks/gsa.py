@@ -69,21 +69,40 @@ class SobolGSA:
         self.ST = np.atleast_2d(indices.total_order)
         self.S1 = np.atleast_2d(indices.first_order)
 
-    def estimate_Sobol_indices_with_emulator_mean(self, emulator, block_points: int = 4_000_000):
-        """Saltelli-2010 indices of the emulator's posterior mean; predictions and sums stay on the device."""
+    def estimate_Sobol_indices_with_emulator_mean(self, emulator, block_points: int = 4_000_000, group=None):
+        """Saltelli-2010 indices of the emulator's posterior mean; predictions and sums stay on the device.
+        With an initialised ``torch.distributed`` process group (one process per GPU, the same emulator and seed on every
+        rank) the design rows are split contiguously over the ranks and only the 8 B/point means are all-gathered; the
+        sums are then formed redundantly on every rank, so the result does not depend on the number of GPUs."""
+        import torch.distributed as dist
+        from ..parallel import shard_bounds
         _, _, X = self.saltelli_design()
         n, d = self.n, self.d
         dev = emulator._compute_device()
+        sharded = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        world, rank = (dist.get_world_size(group), dist.get_rank(group)) if sharded else (1, 0)
+        row_lo, row_hi = shard_bounds(X.shape[0], world, rank)
         with torch.no_grad(), torch.cuda.device(dev):
             f = torch.empty(X.shape[0], dtype=torch.float64, device=dev)
-            for lo in range(0, X.shape[0], block_points):
-                hi = min(X.shape[0], lo + block_points)
+            for lo in range(row_lo, row_hi, block_points):
+                hi = min(row_hi, lo + block_points)
                 x_dev = torch.from_numpy(np.ascontiguousarray(X[lo:hi])).pin_memory().to(dev, non_blocking=True)
                 emulator.model.eval()
                 mu, _, linear = emulator.predict_device(x_dev)
                 if not linear:
                     raise NotImplementedError("device-side GSA needs the (linear) StandardScaler on the outputs")
                 f[lo:hi] = mu
+            if sharded:
+                bounds = [shard_bounds(X.shape[0], world, r) for r in range(world)]
+                width = max(h - l for l, h in bounds)
+                local = torch.zeros(width, dtype=torch.float64, device=dev)
+                local[: row_hi - row_lo] = f[row_lo:row_hi]
+                if dist.get_backend(group) != "nccl":
+                    local = local.cpu()
+                parts = [torch.empty_like(local) for _ in range(world)]
+                dist.all_gather(parts, local, group=group)
+                for (l, h), part in zip(bounds, parts):
+                    f[l:h] = part[: h - l].to(dev)
             f_A, f_B = f[:n], f[n:2 * n]
             f_AB = f[2 * n:].reshape(n, d)                       # row j, column p: A_j with coordinate p from B_j
             mean = torch.cat([f_A, f_B]).mean()

@@ -77,6 +77,14 @@ class Wave:
                 PV[lo:hi] = PVd.cpu().numpy()
         return I, PV
 
+    def compute_impl_sharded(self, X, group=None, block_points: int = 4_000_000):
+        """``compute_impl`` over all ranks of an initialised ``torch.distributed`` group (one process per GPU, every rank
+        holding the same emulators and the same X): rank r scores a contiguous slice of the points with all emulators
+        resident on its own GPU, so the per-point maximum over emulators stays local, and only (I, PV) -- 16 B/point --
+        are exchanged.  Bitwise identical to the single-GPU result.  """
+        from ..parallel import sharded_predict
+        return sharded_predict(lambda x: self.compute_impl(x, block_points), X, group=group)
+
     def find_regions(self, X):
         n_samples = X.shape[0]
         I, PV = self.compute_impl(X)
