@@ -945,6 +945,83 @@ lauum_tma_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------------
+// Narrow-tile editions of the inverse kernels (output strip = ROWS x 128, ROWS = WM*S*8 in {64, 32}).  At small and
+// medium N a recursion level of trtri, or all of lauum, has fewer 128x128 tiles than the GPU has SMs and its duration
+// is that of the tile with the longest k range; ROWS-row strips spread the same work over 2-4x more CTAs.
+// blockIdx.y = tile row * (128/ROWS) + strip.  Operand maps with an `r` suffix have a ROWS-row box.
+// ------------------------------------------------------------------------------------------------
+template <int WM, int S_, int NB>
+__global__ void __launch_bounds__(GT_THREADS, 1)
+trtri_step1_narrow_kernel(const __grid_constant__ CUtensorMap tmKr, const __grid_constant__ CUtensorMap tmS,
+                          const __grid_constant__ CUtensorMap tmD, double* __restrict__ W, int Np, int nb, int h) {
+    constexpr int ROWS = WM * S_ * 8, PER = TILE / ROWS;
+    const int q = blockIdx.x, ti = blockIdx.y / PER, sub = blockIdx.y % PER, tj = blockIdx.z;
+    const int left = 2 * h * q, right = left + h;
+    if (right + ti >= nb) return;
+    extern __shared__ unsigned char smem_raw[];
+    const int arow = (right + ti) * TILE + sub * ROWS;
+    TOperand A = t_operand(&tmKr, arow, left * TILE);
+    TOperand B = t_operand_alt(&tmS, (left + tj) * TILE, left * TILE, &tmD, (left + tj) * TILE, tj * TILE, (tj + 1) * TILE);
+    double acc[S_][NB][2];
+    gemm_nt_tma_mainloop_t<WM, S_, NB>(acc, A, B, tj * TILE, h * TILE, smem_raw);
+    double* Wt = W + ((long)(left + tj) * TILE) * Np + arow;                 // W[j][i]
+    gemm_foreach_pair_t<WM, S_, NB>(acc, [&](int row, int col, double& v0, double& v1) {
+        Wt[(long)col * Np + row] = v0;
+        Wt[(long)(col + 1) * Np + row] = v1;
+    });
+}
+
+template <int WM, int S_, int NB>
+__global__ void __launch_bounds__(GT_THREADS, 1)
+trtri_step2_narrow_kernel(const __grid_constant__ CUtensorMap tmSr, const __grid_constant__ CUtensorMap tmW,
+                          double* __restrict__ S, int Np, int nb, int h) {
+    constexpr int ROWS = WM * S_ * 8, PER = TILE / ROWS;
+    const int q = blockIdx.x, tj = blockIdx.y / PER, sub = blockIdx.y % PER, ti = h - 1 - (int)blockIdx.z;
+    const int left = 2 * h * q, right = left + h;
+    if (right + ti >= nb) return;
+    extern __shared__ unsigned char smem_raw[];
+    const int arow = (right + ti) * TILE + sub * ROWS;
+    TOperand A = t_operand(&tmSr, arow, right * TILE);
+    TOperand B = t_operand(&tmW, (left + tj) * TILE, right * TILE);
+    double acc[S_][NB][2];
+    gemm_nt_tma_mainloop_t<WM, S_, NB>(acc, A, B, 0, (ti + 1) * TILE, smem_raw);
+    double* Xt = S + (long)arow * Np + (long)(left + tj) * TILE;
+    double* Xm = S + ((long)(left + tj) * TILE) * Np + arow;
+    gemm_foreach_pair_t<WM, S_, NB>(acc, [&](int row, int col, double& v0, double& v1) {
+        *reinterpret_cast<double2*>(Xt + (long)row * Np + col) = make_double2(-v0, -v1);
+        Xm[(long)col * Np + row] = -v0;
+        Xm[(long)(col + 1) * Np + row] = -v1;
+    });
+}
+
+template <int WM, int S_, int NB>
+__global__ void __launch_bounds__(GT_THREADS, 1)
+lauum_narrow_kernel(const __grid_constant__ CUtensorMap tmSr, const __grid_constant__ CUtensorMap tmDr,
+                    const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmD,
+                    double* __restrict__ Kinv, int Np) {
+    constexpr int ROWS = WM * S_ * 8, PER = TILE / ROWS;
+    const int tj = blockIdx.x, ti = blockIdx.y / PER, sub = blockIdx.y % PER;     // small ti (long k range) first
+    if (tj > ti) return;
+    extern __shared__ unsigned char smem_raw[];
+    const int arow = ti * TILE + sub * ROWS;
+    TOperand A = t_operand_alt(&tmSr, arow, 0, &tmDr, arow, ti * TILE, (ti + 1) * TILE);
+    TOperand B = (tj == ti) ? t_operand_alt(&tmS, tj * TILE, 0, &tmD, tj * TILE, tj * TILE, (tj + 1) * TILE)
+                            : t_operand(&tmS, tj * TILE, 0);
+    double acc[S_][NB][2];
+    gemm_nt_tma_mainloop_t<WM, S_, NB>(acc, A, B, ti * TILE, Np, smem_raw);
+    double* Ct = Kinv + (long)arow * Np + (long)tj * TILE;
+    double* Cm = Kinv + ((long)tj * TILE) * Np + arow;
+    const bool diag = (ti == tj);
+    gemm_foreach_pair_t<WM, S_, NB>(acc, [&](int row, int col, double& v0, double& v1) {
+        *reinterpret_cast<double2*>(Ct + (long)row * Np + col) = make_double2(v0, v1);
+        if (!diag) {
+            Cm[(long)col * Np + row] = v0;
+            Cm[(long)(col + 1) * Np + row] = v1;
+        }
+    });
+}
+
+// ------------------------------------------------------------------------------------------------
 // Triangular mat-vecs on S (one warp per row, 8 rows per CTA):
 //   mode 0:  u[i]     = sum_{k <= i} Linv[i][k] r[k]                      (rows of the lower part)
 //   mode 1:  alpha[i] = sum_{k >= i} Linv[k][i] u[k] = DT-block part + mirror part of row i
@@ -1017,6 +1094,12 @@ static void set_gemm_attrs() {
     cudaFuncSetAttribute(potrf_panel_narrow_kernel<1, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM_BYTES);
     cudaFuncSetAttribute(potrf_column_narrow_kernel<2, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM_BYTES);
     cudaFuncSetAttribute(potrf_column_narrow_kernel<1, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM_BYTES);
+    cudaFuncSetAttribute(trtri_step1_narrow_kernel<2, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM_BYTES);
+    cudaFuncSetAttribute(trtri_step1_narrow_kernel<1, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM_BYTES);
+    cudaFuncSetAttribute(trtri_step2_narrow_kernel<2, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM_BYTES);
+    cudaFuncSetAttribute(trtri_step2_narrow_kernel<1, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM_BYTES);
+    cudaFuncSetAttribute(lauum_narrow_kernel<2, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM_BYTES);
+    cudaFuncSetAttribute(lauum_narrow_kernel<1, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM_BYTES);
     if (dev >= 0 && dev < 64) g_attr_set[dev] = true;
 }
 
@@ -1223,22 +1306,42 @@ int potrf(double* K, int Np, int N, double* S, double* DT, double* logdet_blk, i
 }
 
 // Completes S (diagonal blocks already hold D_b) to the full mirrored inverse. W = Np x Np scratch.
+static int inverse_narrow_tiles() {       // GPX_INV_NARROW=0: 128-row tiles only
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("GPX_INV_NARROW"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v;
+}
+
 int trtri(const double* L, double* S, const double* DT, double* W, int Np, cudaStream_t st) {
     set_gemm_attrs();
     const int nb = Np / TILE;
     const bool tma = use_chol_tma();
-    CUtensorMap tmK, tmS, tmW, tmD;
+    CUtensorMap tmK, tmS, tmW, tmD, tmK64, tmK32, tmS64, tmS32;
     if (tma) {
         int rc;
         if ((rc = encode_f64_rowmajor(&tmK, L, Np, Np, Np, TILE))) return rc;
         if ((rc = encode_f64_rowmajor(&tmS, S, Np, Np, Np, TILE))) return rc;
         if ((rc = encode_f64_rowmajor(&tmW, W, Np, Np, Np, TILE))) return rc;
         if ((rc = encode_f64_rowmajor(&tmD, DT, (uint64_t)nb * TILE, TILE, TILE, TILE))) return rc;
+        if ((rc = encode_f64_rowmajor(&tmK64, L, Np, Np, Np, 64))) return rc;
+        if ((rc = encode_f64_rowmajor(&tmK32, L, Np, Np, Np, 32))) return rc;
+        if ((rc = encode_f64_rowmajor(&tmS64, S, Np, Np, Np, 64))) return rc;
+        if ((rc = encode_f64_rowmajor(&tmS32, S, Np, Np, Np, 32))) return rc;
     }
+    const int narrow = inverse_narrow_tiles();
     for (int h = 1; h < nb; h *= 2) {
         const int pairs = (nb + 2 * h - 1) / (2 * h);
         dim3 grid(h, h, pairs);
-        if (tma) {
+        const int tiles = pairs * h * h;
+        if (tma && narrow && tiles <= 300) {             // 32-row strips
+            dim3 g(pairs, 4 * h, h);
+            trtri_step1_narrow_kernel<1, 4, 2><<<g, GT_THREADS, GT_SMEM_BYTES, st>>>(tmK32, tmS, tmD, W, Np, nb, h);
+            trtri_step2_narrow_kernel<1, 4, 2><<<g, GT_THREADS, GT_SMEM_BYTES, st>>>(tmS32, tmW, S, Np, nb, h);
+        } else if (tma && narrow && tiles <= 600) {      // 64-row strips
+            dim3 g(pairs, 2 * h, h);
+            trtri_step1_narrow_kernel<2, 4, 4><<<g, GT_THREADS, GT_SMEM_BYTES, st>>>(tmK64, tmS, tmD, W, Np, nb, h);
+            trtri_step2_narrow_kernel<2, 4, 4><<<g, GT_THREADS, GT_SMEM_BYTES, st>>>(tmS64, tmW, S, Np, nb, h);
+        } else if (tma) {
             dim3 grid_hf(pairs, h, h);      // heaviest-first dispatch order
             trtri_step1_tma_kernel<<<grid_hf, GT_THREADS, GT_SMEM_BYTES, st>>>(tmK, tmS, tmD, W, Np, nb, h);
             trtri_step2_tma_kernel<<<grid_hf, GT_THREADS, GT_SMEM_BYTES, st>>>(tmS, tmW, S, Np, nb, h);
@@ -1259,7 +1362,19 @@ int lauum(const double* S, const double* DT, double* Kinv, int Np, cudaStream_t 
         int rc;
         if ((rc = encode_f64_rowmajor(&tmS, S, Np, Np, Np, TILE))) return rc;
         if ((rc = encode_f64_rowmajor(&tmD, DT, (uint64_t)nb * TILE, TILE, TILE, TILE))) return rc;
-        lauum_tma_kernel<<<dim3(nb, nb), GT_THREADS, GT_SMEM_BYTES, st>>>(tmS, tmD, Kinv, Np);
+        const int tiles = nb * (nb + 1) / 2;
+        if (inverse_narrow_tiles() && tiles <= 1200) {
+            const int rows = tiles <= 300 ? 32 : 64;
+            CUtensorMap tmSr, tmDr;
+            if ((rc = encode_f64_rowmajor(&tmSr, S, Np, Np, Np, rows))) return rc;
+            if ((rc = encode_f64_rowmajor(&tmDr, DT, (uint64_t)nb * TILE, TILE, TILE, rows))) return rc;
+            if (rows == 32)
+                lauum_narrow_kernel<1, 4, 2><<<dim3(nb, 4 * nb), GT_THREADS, GT_SMEM_BYTES, st>>>(tmSr, tmDr, tmS, tmD, Kinv, Np);
+            else
+                lauum_narrow_kernel<2, 4, 4><<<dim3(nb, 2 * nb), GT_THREADS, GT_SMEM_BYTES, st>>>(tmSr, tmDr, tmS, tmD, Kinv, Np);
+        } else {
+            lauum_tma_kernel<<<dim3(nb, nb), GT_THREADS, GT_SMEM_BYTES, st>>>(tmS, tmD, Kinv, Np);
+        }
     } else {
         lauum_kernel<<<dim3(nb, nb), G_THREADS, G_SMEM_BYTES, st>>>(S, DT, Kinv, Np);
     }
