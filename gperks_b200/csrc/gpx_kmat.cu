@@ -59,10 +59,12 @@ __device__ __forceinline__ void tile_r2(double (&r2)[8][8], const double* sa, co
 }
 
 // ------------------------------------------------------------------------------------------------
+// One row (8 entries) of the micro-tile at a time, in a ROLLED loop, like kmat_cross below: 64 unrolled FP64 sqrt/exp
+// evaluations do not fit the instruction cache (this kernel ran at half the entry rate of kmat_cross before).
 template <int KIND>
-__global__ void __launch_bounds__(P_THREADS) kmat_sym_kernel(const double* __restrict__ X, int N, int D,
-                                                             const double* __restrict__ theta, double* __restrict__ K,
-                                                             int Np) {
+__global__ void __launch_bounds__(P_THREADS, 2) kmat_sym_kernel(const double* __restrict__ X, int N, int D,
+                                                                const double* __restrict__ theta, double* __restrict__ K,
+                                                                int Np) {
     const int bi = blockIdx.y, bj = blockIdx.x;
     if (bj > bi) return;
     extern __shared__ double sm[];
@@ -72,18 +74,28 @@ __global__ void __launch_bounds__(P_THREADS) kmat_sym_kernel(const double* __res
     stage_coords(sb, X, (long)bj * TILE, N, D, theta, nullptr, nullptr);
     __syncthreads();
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    double r2[8][8];
-    tile_r2(r2, sa, sb, D, ty, tx);
     const double s = theta[D], noise = theta[D + 1];
-#pragma unroll
+#pragma unroll 1
     for (int a = 0; a < 8; ++a) {
-        const long i = (long)bi * TILE + ty + 16 * a;
+        const int row = ty + 16 * a;
+        double r2[8];
+#pragma unroll
+        for (int b = 0; b < 8; ++b) r2[b] = 0.0;
+        for (int d = 0; d < D; ++d) {
+            const double xa_ = sa[d * P_LD + row];
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                const double df = xa_ - sb[d * P_LD + tx + 16 * b];
+                r2[b] = fma(df, df, r2[b]);
+            }
+        }
+        const long i = (long)bi * TILE + row;
 #pragma unroll
         for (int b = 0; b < 8; ++b) {
             const long j = (long)bj * TILE + tx + 16 * b;
             double v;
             if (i < N && j < N) {
-                v = kernel_value<KIND>(r2[a][b], s);
+                v = kernel_value<KIND>(r2[b], s);
                 if (i == j) v += noise;
             } else {
                 v = (i == j) ? 1.0 : 0.0;
@@ -302,44 +314,56 @@ mll_grad_tile_kernel(const double* __restrict__ X, int N, int D, const double* _
     __syncthreads();
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const double s = theta[D];
-    // pass 1: r2 -> weights  wg = W*g,  and the outputscale / noise sums
-    double wg[8][8];
-    tile_r2(wg, sa, sb, D, ty, tx);
+    const double tile_w = (bi == bj) ? 1.0 : 2.0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // One row (8 entries) of the micro-tile at a time in a ROLLED loop (instruction-cache footprint, see kmat_cross):
+    // r2 -> weight wg = W*g and the outputscale / noise sums, then the per-dimension sums  sum wg * dz_d^2  into this
+    // thread's column of sacc[d][thread] (shared memory: D is a run-time value, a register array could not be indexed).
+    double* sacc = sred + 8 * (MAXD + 2);      // [D][256]
+    for (int d = 0; d < D; ++d) sacc[d * P_THREADS + threadIdx.x] = 0.0;
     double acc_s = 0.0, acc_n = 0.0;
-#pragma unroll
+#pragma unroll 1
     for (int a = 0; a < 8; ++a) {
-        const long i = (long)bi * TILE + ty + 16 * a;
-        const double ai = sali[ty + 16 * a];
+        const int row = ty + 16 * a;
+        double r2[8];
+#pragma unroll
+        for (int b = 0; b < 8; ++b) r2[b] = 0.0;
+        for (int d = 0; d < D; ++d) {
+            const double xa_ = sa[d * P_LD + row];
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                const double df = xa_ - sb[d * P_LD + tx + 16 * b];
+                r2[b] = fma(df, df, r2[b]);
+            }
+        }
+        const long i = (long)bi * TILE + row;
+        const double ai = sali[row];
+        double wg[8];
 #pragma unroll
         for (int b = 0; b < 8; ++b) {
             const long j = (long)bj * TILE + tx + 16 * b;
             double w = 0.0, g = 0.0, k = 0.0;
             if (i < N && j < N) {
                 w = Kinv[i * Np + j] - ai * salj[tx + 16 * b];
-                k = kernel_value_grad<KIND>(wg[a][b], s, g);
+                k = kernel_value_grad<KIND>(r2[b], s, g);
             }
             acc_s = fma(w, k, acc_s);
             if (i == j) acc_n += w;
-            wg[a][b] = w * g;
+            wg[b] = w * g;
         }
-    }
-    const double tile_w = (bi == bj) ? 1.0 : 2.0;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // pass 2: per-dimension sums  sum wg * dz_d^2
-    for (int d = 0; d < D; ++d) {
-        double xa_[8], xb_[8];
-#pragma unroll
-        for (int a = 0; a < 8; ++a) xa_[a] = sa[d * P_LD + ty + 16 * a];
-#pragma unroll
-        for (int b = 0; b < 8; ++b) xb_[b] = sb[d * P_LD + tx + 16 * b];
-        double acc = 0.0;
-#pragma unroll
-        for (int a = 0; a < 8; ++a)
+        for (int d = 0; d < D; ++d) {
+            const double xa_ = sa[d * P_LD + row];
+            double acc = sacc[d * P_THREADS + threadIdx.x];
 #pragma unroll
             for (int b = 0; b < 8; ++b) {
-                double df = xa_[a] - xb_[b];
-                acc = fma(wg[a][b], df * df, acc);
+                const double df = xa_ - sb[d * P_LD + tx + 16 * b];
+                acc = fma(wg[b], df * df, acc);
             }
+            sacc[d * P_THREADS + threadIdx.x] = acc;
+        }
+    }
+    for (int d = 0; d < D; ++d) {
+        double acc = sacc[d * P_THREADS + threadIdx.x];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         if (lane == 0) sred[warp * (MAXD + 2) + d] = acc;
@@ -414,7 +438,7 @@ template <int KIND>
 static int launch_mll_grad(const double* X, int N, int D, const double* theta, const double* Kinv, int Np,
                            const double* alpha, double* partial, double* grad, cudaStream_t st) {
     const int nb = Np / TILE;
-    const size_t smem = size_t(2) * MAXD * P_LD * 8 + 2 * TILE * 8 + 8 * (MAXD + 2) * 8;
+    const size_t smem = size_t(2) * MAXD * P_LD * 8 + 2 * TILE * 8 + 8 * (MAXD + 2) * 8 + size_t(D) * P_THREADS * 8;
     cudaFuncSetAttribute(mll_grad_tile_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     mll_grad_tile_kernel<KIND><<<dim3(nb, nb), P_THREADS, smem, st>>>(X, N, D, theta, Kinv, Np, alpha, partial);
     GPX_CHECK_LAUNCH();
