@@ -219,8 +219,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--points", type=int, default=1_000_000, help="predict points per GPU per step")
-    ap.add_argument("--ref-points", type=int, default=32768, help="points per step of the CPU reference arm")
-    ap.add_argument("--cpu-sample", type=int, default=32768, help="points of the cpu_baseline sample")
+    ap.add_argument("--ref-points", type=int, default=65536, help="points per step of the CPU reference arm")
+    ap.add_argument("--cpu-sample", type=int, default=98304, help="points of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mll-evals", type=int, default=3)
     ap.add_argument("--no-tf32", action="store_true", help="skip the TF32-mode (tcgen05) arm")
