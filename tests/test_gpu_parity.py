@@ -72,6 +72,34 @@ def test_stagewise_parity_with_oracle(dev, kind, N, D):
     np.testing.assert_allclose(eng.W[:N, :N].cpu().numpy(), Kinv.numpy(), rtol=0, atol=1e-9 * float(Kinv.abs().max()))
 
 
+@pytest.mark.parametrize("N,D,kind", [(1500, 5, O.KIND_MATERN32), (2048, 6, O.KIND_MATERN52), (4200, 7, O.KIND_RBF)])
+def test_mid_size_mll_and_gradients_against_oracle_on_device(dev, N, D, kind):
+    """Sizes where the schedule choices differ from both the small cases above and N=8192: 32- and 64-row strip editions
+    of the panel/column/trtri/lauum kernels, 12-33 block columns, the first two-level outer step (nb = 33).  The oracle's
+    formulas are evaluated with torch on the same device (checker only)."""
+    X, y, _, ls, s, w, b = _problem(N, D, 8, seed=N)
+    nz = 1e-2
+    eng = _engine(dev, X, y, kind, ls, s, nz, w, b)
+    Xd, lsd, sd = X.to(dev), ls.to(dev), s.to(dev)
+    resid = (y - (X @ w + b)).to(dev)
+    K = O.kernel_from_r2(O.sq_dist(Xd, Xd, lsd), kind, sd)
+    K.diagonal().add_(nz)
+    L = torch.linalg.cholesky(K)
+    alpha = torch.cholesky_solve(resid.reshape(-1, 1), L).reshape(-1)
+    loss = (0.5 * resid @ alpha + torch.log(torch.diagonal(L)).sum() + 0.5 * N * np.log(2 * np.pi)) / N
+    assert float(eng.loss) == pytest.approx(float(loss), rel=1e-10)
+    np.testing.assert_allclose(eng.alpha[:N].cpu().numpy(), alpha.cpu().numpy(), rtol=0, atol=1e-8 * float(alpha.abs().max()))
+    Linv = torch.linalg.solve_triangular(L, torch.eye(N, dtype=F64, device=dev), upper=False)
+    assert float((eng.linv() - Linv).abs().max() / Linv.abs().max()) < 1e-9
+    got = eng.gradients().cpu()
+    Kinv = torch.cholesky_inverse(L)
+    assert float((eng.W[:N, :N] - Kinv).abs().max() / Kinv.abs().max()) < 1e-8
+    del Kinv, Linv, K, L
+    g = O.neg_mll_analytic_grads(X, y, kind, ls, s, torch.tensor(nz, dtype=F64), X @ w + b)       # CPU oracle, a few seconds
+    gref = torch.cat([g["lengthscale"], g["outputscale"].reshape(1), g["noise"].reshape(1)])
+    np.testing.assert_allclose(got.numpy(), gref.numpy(), rtol=1e-7, atol=1e-10 * float(gref.abs().max()))
+
+
 @pytest.mark.parametrize("kind", KINDS)
 @pytest.mark.parametrize("N,D,M", [(5, 1, 1), (200, 8, 1000), (384, 6, 129), (500, 3, 4097)])
 def test_predict_parity_with_oracle(dev, kind, N, D, M):
