@@ -104,7 +104,7 @@ class ExactGPEngine:
             self.theta.copy_(theta.detach().reshape(-1))
             self.theta_in.copy_(self.theta)
             self.theta_latent.copy_(self.theta)
-            self.theta_latent[self.D + 1] = 0.0
+            self.theta_latent[self.D + 1:].zero_()      # device-side (a Python scalar assignment is a host copy: not capturable)
             self.r[: self.N].copy_(resid.detach().reshape(-1))
             p = nv.ptr
             jitter = 0.0

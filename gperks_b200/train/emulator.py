@@ -96,13 +96,20 @@ class GPEmulator(Trainable):
     def train(self, optimizer,
               early_stopping_criterion: Optional[EarlyStoppingCriterion] = None,
               snapshotting_criterion: Optional[SnapshottingCriterion] = None, *,
-              devices: Optional[List[str]] = None, max_workers: Optional[int] = None):
+              devices: Optional[List[str]] = None, max_workers: Optional[int] = None,
+              batched_restarts: bool = False):
         """``devices`` (extension): restarts are independent fits, so with a device list they are
         dealt round-robin onto those GPUs and run in spawned workers, one fit per GPU at a time, instead of one after
         the other.  Each restart starts from the same raw hyper-parameter draw as in the sequential run (the random
         stream is replayed), but gets a fresh optimizer (``optimizer.__class__(params, **optimizer.defaults)``, as the
         reference's K-fold does per split) -- the sequential loop carries the optimizer's moment estimates from one
-        restart into the next, so restarts >= 2 follow slightly different trajectories in the two modes."""
+        restart into the next, so restarts >= 2 follow slightly different trajectories in the two modes.
+
+        ``batched_restarts`` (extension): train all restarts at the same time on this emulator's
+        GPU -- one CUDA graph per restart replayed on its own stream, one optimizer over all replicas' parameters, one
+        host read per epoch (``gperks_b200/train/batched.py``).  For small training sets, where an epoch is bound by
+        the host; same per-restart semantics as ``devices``.  Falls back to the sequential loop when it cannot help
+        (a single restart, N > 2048)."""
         if early_stopping_criterion is None:
             early_stopping_criterion = NoEarlyStoppingCriterion(DEFAULT_TRAIN_MAX_EPOCH)
         if snapshotting_criterion is None:
@@ -116,7 +123,16 @@ class GPEmulator(Trainable):
 
             all_stats: List[TrainStats] = []
             best_epochs: List[int] = []
-            if devices:
+            batched_off = None
+            if batched_restarts and not devices:
+                from .batched import train_restarts_batched, unsupported_reason
+                batched_off = unsupported_reason(self)
+                if batched_off is not None:
+                    log.info(f"batched_restarts ignored: {batched_off}")
+            if batched_restarts and not devices and batched_off is None:
+                all_stats, best_epochs = train_restarts_batched(self, optimizer, early_stopping_criterion,
+                                                                snapshotting_criterion)
+            elif devices:
                 all_stats, best_epochs = self._train_restarts_on_devices(optimizer, early_stopping_criterion,
                                                                          snapshotting_criterion, list(devices), max_workers)
             else:

@@ -203,3 +203,41 @@ def test_kfold_with_fold_restart_jobs(dev, tmp_path):
     assert min(cv.best_test_scores_structured_dct["R2Score"]) > 0.8
     mean, std = cv.emulator.predict(ds.X_train[:4])
     assert mean.shape == (4,) and (std > 0).all()
+
+
+@pytest.mark.parametrize("with_val", [False, True])
+def test_batched_restarts_match_restart_jobs(dev, tmp_path, with_val):
+    """All restarts trained at once (CUDA graph per restart, one optimizer over every replica) must follow, restart by
+    restart, the trajectory of the same restart run on its own (`devices` mode: same draw, fresh optimizer state)."""
+    from gperks_b200.train.early_stop import GLEarlyStoppingCriterion, NoEarlyStoppingCriterion
+    from gperks_b200.train.emulator import GPEmulator
+    from gperks_b200.train.snapshot import EveryEpochSnapshottingCriterion
+    runs = {}
+    for mode in ("jobs", "batched"):
+        exp, ds = _restart_experiment(4)
+        if with_val:
+            from gperks_b200.gp.data.dataset import Dataset
+            from gperks_b200.gp.experiment import GPExperiment
+            d2 = Dataset(ds.X_train, ds.y_train, X_val=ds.X_test, y_val=ds.y_test, X_test=ds.X_test, y_test=ds.y_test)
+            torch.manual_seed(8)
+            exp = GPExperiment(d2, exp.likelihood, exp.mean_module, exp.covar_module, n_restarts=4, seed=8, metrics=exp.metrics)
+        em = GPEmulator(exp, "cuda:0")
+        opt = torch.optim.Adam(exp.model.parameters(), lr=0.1)
+        root = tmp_path / mode
+        snap = EveryEpochSnapshottingCriterion((root / "restart_{restart}").as_posix(), "epoch_{epoch}.pth")
+        esc = GLEarlyStoppingCriterion(40, alpha=0.5, patience=3) if with_val else NoEarlyStoppingCriterion(30)
+        kw = {"devices": ["cuda:0"], "max_workers": 1} if mode == "jobs" else {"batched_restarts": True}
+        best_model, best_stats = em.train(opt, esc, snap, **kw)
+        stats = [json.loads((root / f"restart_{r}" / "train_stats.json").read_text()) for r in (1, 2, 3, 4)]
+        runs[mode] = (stats, best_stats, em.predict(ds.X_test), {k: v.clone() for k, v in best_model.items()})
+        assert (root / "best_model.pth").exists()
+    for a, b in zip(runs["jobs"][0], runs["batched"][0]):
+        assert len(a["train_loss"]) == len(b["train_loss"]) and a["best_epoch"] == b["best_epoch"]
+        np.testing.assert_allclose(a["train_loss"], b["train_loss"], rtol=1e-8, atol=1e-10)
+        for name in a["train_metrics_score"]:
+            np.testing.assert_allclose(a["train_metrics_score"][name], b["train_metrics_score"][name], rtol=1e-7, atol=1e-9)
+        if with_val:
+            np.testing.assert_allclose(a["val_loss"], b["val_loss"], rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(runs["jobs"][2][0], runs["batched"][2][0], rtol=1e-7)
+    for k, v in runs["jobs"][3].items():
+        np.testing.assert_allclose(v.numpy(), runs["batched"][3][k].numpy(), rtol=1e-7, atol=1e-10)
