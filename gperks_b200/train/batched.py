@@ -35,6 +35,7 @@ from .train_stats import TrainStats
 log = get_logger()
 F64 = torch.float64
 MAX_BATCHED_N = 2048          # beyond this a restart keeps the GPU busy on its own
+_FORCE_GENERIC = False        # tests: evaluate replica by replica even when the stacked fast path applies
 
 
 class _BatchedNegMLL(torch.autograd.Function):
@@ -159,6 +160,102 @@ class _Runner:
         self._last = (list(rows), theta.clone(), resid.clone())
 
 
+class _StackedParams:
+    """The parameters of all replicas as ONE leaf tensor per parameter name ([R, ...]), with every replica's own
+    ``nn.Parameter`` re-pointed at its row (shared storage), so that (theta, resid) of all replicas come from a handful
+    of vectorised torch ops and the optimizer steps five tensors instead of 5 R.  Understands the standard GPErks
+    model: [ScaleKernel(] RBF/Matern kernel [)], Gaussian likelihood, and the polynomial means of this package;
+    anything else makes ``build`` return None and the trainer evaluates replica by replica."""
+
+    @staticmethod
+    def build(replicas, X_train, y_train, X_val, device):
+        from ..gp.mean import LinearMean as PolyLinearMean
+        from ..means import ConstantMean, LinearMean, ZeroMean
+        m0 = replicas[0]
+        mm = m0.mean_module
+        if not isinstance(mm, (PolyLinearMean, LinearMean, ConstantMean, ZeroMean)):
+            return None
+        names = [n for n, _ in m0.named_parameters()]
+        known = {"mean_module.weights", "mean_module.bias", "mean_module.raw_constant"}
+        ls_name = [n for n in names if n.endswith("raw_lengthscale")]
+        os_name = [n for n in names if n.endswith("raw_outputscale")]
+        nz_name = [n for n in names if n.endswith("raw_noise")]
+        if len(ls_name) != 1 or len(nz_name) != 1 or len(os_name) > 1:
+            return None
+        if any(n not in known and n not in ls_name + os_name + nz_name for n in names):
+            return None
+        cov = m0.covar_module
+        base = cov.base_kernel if hasattr(cov, "base_kernel") else cov
+        if bool(os_name) != hasattr(cov, "base_kernel"):
+            return None
+        self = _StackedParams()
+        self.R, self.device = len(replicas), device
+        self.leaves = {}
+        for n in names:
+            ps = [dict(m.named_parameters())[n] for m in replicas]
+            st = torch.stack([p.detach() for p in ps]).clone().requires_grad_(ps[0].requires_grad)
+            for r, p_ in enumerate(ps):
+                p_.data = st.data[r]                   # the replica's parameter now IS row r of the stacked tensor
+            self.leaves[n] = st
+        self.ls_name, self.nz_name = ls_name[0], nz_name[0]
+        self.os_name = os_name[0] if os_name else None
+        self.ls_c = base._modules.get("raw_lengthscale_constraint")
+        self.os_c = cov._modules.get("raw_outputscale_constraint") if os_name else None
+        self.nz_c = m0.likelihood.noise_covar._modules.get("raw_noise_constraint")
+        self.D = X_train.shape[1] if X_train.dim() > 1 else 1
+        X2 = X_train if X_train.dim() > 1 else X_train.unsqueeze(-1)
+        self.y = y_train.reshape(-1).to(F64)
+        self.mean_kind = ("poly" if isinstance(mm, PolyLinearMean) else "linear" if isinstance(mm, LinearMean)
+                          else "const" if isinstance(mm, ConstantMean) else "zero")
+        feats = (lambda x: mm._poly.transform(x)) if self.mean_kind == "poly" else (lambda x: x)
+        self.phi_train = feats(X2).detach() if self.mean_kind in ("poly", "linear") else None
+        self.n_train = X2.shape[0]
+        self.phi_val = self.n_val = None
+        if X_val is not None:
+            Xv = X_val if X_val.dim() > 1 else X_val.unsqueeze(-1)
+            self.n_val = Xv.shape[0]
+            self.phi_val = feats(Xv).detach() if self.mean_kind in ("poly", "linear") else None
+        self.has_bias = "mean_module.bias" in self.leaves
+        return self
+
+    def parameters(self):
+        return list(self.leaves.values())
+
+    @staticmethod
+    def _tr(c, raw):
+        return raw if c is None else c.transform(raw)
+
+    def theta(self, idx: torch.Tensor) -> torch.Tensor:
+        k = idx.numel()
+        ls = self._tr(self.ls_c, self.leaves[self.ls_name].index_select(0, idx)).reshape(k, -1)
+        if ls.shape[1] == 1 and self.D > 1:
+            ls = ls.expand(k, self.D)
+        nz = self._tr(self.nz_c, self.leaves[self.nz_name].index_select(0, idx)).reshape(k, 1)
+        if self.os_name is not None:
+            os_ = self._tr(self.os_c, self.leaves[self.os_name].index_select(0, idx)).reshape(k, 1)
+        else:
+            os_ = torch.ones(k, 1, dtype=ls.dtype, device=ls.device)
+        return torch.cat([1.0 / ls, os_, nz], dim=1).to(self.device, F64)
+
+    def _mean(self, idx: torch.Tensor, phi, n: int) -> torch.Tensor:
+        k = idx.numel()
+        if self.mean_kind in ("poly", "linear"):
+            W = self.leaves["mean_module.weights"].index_select(0, idx)              # [k, P, 1]
+            res = phi.matmul(W.to(phi.device, phi.dtype)).squeeze(-1)                  # [k, n]
+            if self.has_bias:
+                res = res + self.leaves["mean_module.bias"].index_select(0, idx).to(phi.device, phi.dtype)
+            return res
+        if self.mean_kind == "const":
+            return self.leaves["mean_module.raw_constant"].index_select(0, idx).reshape(k, 1).expand(k, n)
+        return torch.zeros(k, n, dtype=F64)
+
+    def resid(self, idx: torch.Tensor) -> torch.Tensor:
+        return (self.y.unsqueeze(0) - self._mean(idx, self.phi_train, self.n_train).to(F64)).to(self.device)
+
+    def val_prior(self, idx: torch.Tensor) -> torch.Tensor:
+        return self._mean(idx, self.phi_val, self.n_val).to(F64).to(self.device)
+
+
 def unsupported_reason(emulator) -> Optional[str]:
     sd = emulator.scaled_data
     if emulator.experiment.n_restarts < 2:
@@ -195,12 +292,18 @@ def train_restarts_batched(emulator, optimizer, early_stopping_criterion, snapsh
         stats.append(st)
         escs.append(esc)
         snpcs.append(snpc)
-    opt = optimizer.__class__([p for m in replicas for p in m.parameters()], **optimizer.defaults)
+    stacked = None if _FORCE_GENERIC else _StackedParams.build(replicas, X_train, y_train, X_val if with_val else None, dev)
+    params = stacked.parameters() if stacked is not None else [p for m in replicas for p in m.parameters()]
+    opt = optimizer.__class__(params, **optimizer.defaults)
+    frozen = {}            # row -> {name: value} of replicas that stopped (stacked mode: their rows still see the optimizer)
 
     with torch.cuda.device(dev):
         runner = _Runner(X_train, replicas[0].covar_module.kind, R, y_train, X_val if with_val else None, dev)
         for r, m in enumerate(replicas):
             m._engine = runner.engines[r]
+            # the validation loss goes through the replica's own posterior: it must use the factors of the batched
+            # evaluation as they are, not re-derive (theta, resid) and compare them bit by bit
+            m._factorized_engine = (lambda e=runner.engines[r]: e)
         y_cpu = y_train.detach().cpu()
         yv_cpu = y_val.detach().cpu() if with_val else None
         active = list(range(R))
@@ -210,6 +313,13 @@ def train_restarts_batched(emulator, optimizer, early_stopping_criterion, snapsh
 
         def evaluate(rows):
             """-mll of the replicas in ``rows`` at their current parameters, differentiable; refreshes the predictions."""
+            if stacked is not None:
+                idx = torch.as_tensor(rows)
+                thetas, resids = stacked.theta(idx), stacked.resid(idx)
+                if with_val:
+                    with torch.no_grad():
+                        runner.val_prior.index_copy_(0, idx.to(dev), stacked.val_prior(idx))
+                return _BatchedNegMLL.apply(runner, list(rows), thetas, resids)
             thetas = torch.stack([replicas[r]._theta(dev) for r in rows])
             resids = torch.stack([replicas[r]._resid(dev) for r in rows])
             if with_val:
@@ -225,6 +335,11 @@ def train_restarts_batched(emulator, optimizer, early_stopping_criterion, snapsh
             opt.zero_grad(set_to_none=True)
             loss.sum().backward()
             opt.step()
+            if frozen:          # a stopped replica keeps the state its criterion left it in
+                with torch.no_grad():
+                    for r_, saved in frozen.items():
+                        for n_, v_ in saved.items():
+                            stacked.leaves[n_].data[r_].copy_(v_)
             msgs = {}
             for k, r in enumerate(rows):
                 st = stats[r]
@@ -270,6 +385,8 @@ def train_restarts_batched(emulator, optimizer, early_stopping_criterion, snapsh
                     best_epochs[r] = best_epoch
                     st.save_to_file(posix_path(snpcs[r].snapshot_dir.format(restart=r + 1), "train_stats.json"))
                     snpcs[r].keep_snapshots_until(r + 1, best_epoch)
+                    if stacked is not None:
+                        frozen[r] = {n_: v_.data[r].clone() for n_, v_ in stacked.leaves.items()}
                 else:
                     still.append(r)
             if still and len(still) != len(rows):

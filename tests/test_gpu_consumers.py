@@ -212,8 +212,10 @@ def test_batched_restarts_match_restart_jobs(dev, tmp_path, with_val):
     from gperks_b200.train.early_stop import GLEarlyStoppingCriterion, NoEarlyStoppingCriterion
     from gperks_b200.train.emulator import GPEmulator
     from gperks_b200.train.snapshot import EveryEpochSnapshottingCriterion
+    import gperks_b200.train.batched as batched_mod
     runs = {}
-    for mode in ("jobs", "batched"):
+    for mode in ("jobs", "batched", "batched_generic"):
+        batched_mod._FORCE_GENERIC = mode == "batched_generic"
         exp, ds = _restart_experiment(4)
         if with_val:
             from gperks_b200.gp.data.dataset import Dataset
@@ -231,13 +233,15 @@ def test_batched_restarts_match_restart_jobs(dev, tmp_path, with_val):
         stats = [json.loads((root / f"restart_{r}" / "train_stats.json").read_text()) for r in (1, 2, 3, 4)]
         runs[mode] = (stats, best_stats, em.predict(ds.X_test), {k: v.clone() for k, v in best_model.items()})
         assert (root / "best_model.pth").exists()
-    for a, b in zip(runs["jobs"][0], runs["batched"][0]):
-        assert len(a["train_loss"]) == len(b["train_loss"]) and a["best_epoch"] == b["best_epoch"]
-        np.testing.assert_allclose(a["train_loss"], b["train_loss"], rtol=1e-8, atol=1e-10)
-        for name in a["train_metrics_score"]:
-            np.testing.assert_allclose(a["train_metrics_score"][name], b["train_metrics_score"][name], rtol=1e-7, atol=1e-9)
-        if with_val:
-            np.testing.assert_allclose(a["val_loss"], b["val_loss"], rtol=1e-7, atol=1e-9)
-    np.testing.assert_allclose(runs["jobs"][2][0], runs["batched"][2][0], rtol=1e-7)
-    for k, v in runs["jobs"][3].items():
-        np.testing.assert_allclose(v.numpy(), runs["batched"][3][k].numpy(), rtol=1e-7, atol=1e-10)
+    batched_mod._FORCE_GENERIC = False
+    for other in ("batched", "batched_generic"):
+        for a, b in zip(runs["jobs"][0], runs[other][0]):
+            assert len(a["train_loss"]) == len(b["train_loss"]) and a["best_epoch"] == b["best_epoch"]
+            np.testing.assert_allclose(a["train_loss"], b["train_loss"], rtol=1e-8, atol=1e-10)
+            for name in a["train_metrics_score"]:
+                np.testing.assert_allclose(a["train_metrics_score"][name], b["train_metrics_score"][name], rtol=1e-7, atol=1e-9)
+            if with_val:
+                np.testing.assert_allclose(a["val_loss"], b["val_loss"], rtol=1e-7, atol=1e-9)
+        np.testing.assert_allclose(runs["jobs"][2][0], runs[other][2][0], rtol=1e-7)
+        for k, v in runs["jobs"][3].items():
+            np.testing.assert_allclose(v.numpy(), runs[other][3][k].numpy(), rtol=1e-7, atol=1e-10)
