@@ -258,8 +258,6 @@ class _StackedParams:
 
 def unsupported_reason(emulator) -> Optional[str]:
     sd = emulator.scaled_data
-    if emulator.experiment.n_restarts < 2:
-        return "a single restart"
     if sd.X_train.shape[0] > MAX_BATCHED_N:
         return f"more than {MAX_BATCHED_N} training points"
     return None

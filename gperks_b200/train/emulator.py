@@ -108,8 +108,8 @@ class GPEmulator(Trainable):
         ``batched_restarts`` (extension): train all restarts at the same time on this emulator's
         GPU -- one CUDA graph per restart replayed on its own stream, one optimizer over all replicas' parameters, one
         host read per epoch (``gperks_b200/train/batched.py``).  For small training sets, where an epoch is bound by
-        the host; same per-restart semantics as ``devices``.  Falls back to the sequential loop when it cannot help
-        (a single restart, N > 2048)."""
+        the host (also worthwhile for a single restart: ~2x per epoch); same per-restart semantics as ``devices``.  Falls
+        back to the sequential loop for N > 2048, where a fit keeps the GPU busy on its own."""
         if early_stopping_criterion is None:
             early_stopping_criterion = NoEarlyStoppingCriterion(DEFAULT_TRAIN_MAX_EPOCH)
         if snapshotting_criterion is None:

@@ -30,7 +30,7 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 f = partial(SobolGstar, a=[0, 1, 4.5, 9, 99, 99, 99, 99], delta=np.linspace(0.1, 0.9, d), alpha=[1.0] * d)
 ds = Dataset.build_from_function(f, d, n, None, 64, "lhs", 8)
 out = {"N": n, "D": d, "epochs": 100}
-for R in (3, 8):
+for R in (1, 3, 8):
     for mode in ("sequential", "batched"):
         torch.manual_seed(8)
         exp = GPExperiment(ds, GaussianLikelihood(), LinearMean(1, d), ScaleKernel(RBFKernel(ard_num_dims=d)), n_restarts=R, seed=8,
