@@ -289,3 +289,74 @@ def test_metrics_shims():
     assert float(R2Score()(p, t)) == pytest.approx(O.r2score(p.numpy(), t.numpy()))
     assert float(IndependentStandardError()(p, torch.tensor([0.1, 1.0, 0.4]), t)) == pytest.approx(2 / 3)
     assert get_metric_name(R2Score()) == "R2Score"
+
+
+@pytest.mark.parametrize("mean", ["poly2", "gp_linear", "constant", "zero"])
+@pytest.mark.parametrize("scaled", [True, False])
+def test_stacked_restart_parameters_match_per_replica_evaluation(mean, scaled):
+    """The batched trainer's vectorised (theta, resid) over all replicas -- values and gradients -- against each replica's
+    own ``_theta`` / ``_resid``; and that a replica's parameters are views of its row of the stacked tensors."""
+    from copy import deepcopy
+    from gperks_b200.models import ExactGP
+    from gperks_b200.train.batched import _StackedParams
+    torch.manual_seed(3)
+    D, N, R = 3, 17, 4
+    X, y = torch.rand(N, D, dtype=torch.float64), torch.randn(N, dtype=torch.float64)
+    Xv = torch.rand(5, D, dtype=torch.float64)
+    mm = {"poly2": lambda: LinearMean(2, D), "gp_linear": lambda: GpLinearMean(D), "constant": ConstantMean, "zero": ZeroMean}[mean]()
+    base = MaternKernel(nu=1.5, ard_num_dims=D)
+
+    class Model(ExactGP):
+        def __init__(self):
+            super().__init__(X, y, GaussianLikelihood())
+            self.mean_module = mm
+            self.covar_module = ScaleKernel(base) if scaled else base
+
+        def forward(self, x):
+            from gperks_b200.distributions import MultivariateNormal
+            return MultivariateNormal(self.mean_module(x), self.covar_module(x))
+
+    m0 = Model()
+    replicas = []
+    for r in range(R):
+        m = deepcopy(m0)
+        with torch.no_grad():
+            for p in m.parameters():
+                p.add_(0.3 * torch.randn_like(p))
+        replicas.append(m)
+    dev = torch.device("cpu")
+    ref_theta = torch.stack([m._theta(dev) for m in replicas])
+    ref_resid = torch.stack([m._resid(dev) for m in replicas])
+    wt, wr = torch.randn_like(ref_theta), torch.randn_like(ref_resid)
+    ((ref_theta * wt).sum() + (ref_resid * wr).sum()).backward()
+    ref_grads = [{n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None} for m in replicas]
+    ref_vprior = torch.stack([m.mean_module(Xv).reshape(-1) for m in replicas]).detach()
+
+    st = _StackedParams.build(replicas, X, y, Xv, dev)
+    assert st is not None
+    idx = torch.arange(R)
+    theta, resid = st.theta(idx), st.resid(idx)
+    np.testing.assert_allclose(theta.detach().numpy(), ref_theta.detach().numpy(), rtol=1e-15, atol=0)
+    np.testing.assert_allclose(resid.detach().numpy(), ref_resid.detach().numpy(), rtol=0, atol=1e-14)
+    np.testing.assert_allclose(st.val_prior(idx).detach().numpy(), ref_vprior.numpy(), rtol=0, atol=1e-14)
+    ((theta * wt).sum() + (resid * wr).sum()).backward()
+    for r in range(R):
+        for n, g in ref_grads[r].items():
+            np.testing.assert_allclose(st.leaves[n].grad[r].numpy(), g.numpy(), rtol=1e-12, atol=1e-14)
+    # subset of rows, and shared storage between a replica's parameter and its row
+    sub = torch.tensor([2, 0])
+    np.testing.assert_allclose(st.theta(sub).detach().numpy(), ref_theta.detach().numpy()[[2, 0]], rtol=1e-15)
+    with torch.no_grad():
+        for leaf in st.parameters():
+            leaf.add_(1.0)
+    for r, m in enumerate(replicas):
+        for n, p in m.named_parameters():
+            assert torch.equal(p.detach(), st.leaves[n].detach()[r])
+
+
+def test_settings_shim_accepts_gpytorch_idioms():
+    from gperks_b200 import settings
+    with torch.no_grad(), settings.fast_pred_var(), settings.max_cholesky_size(4000), settings.cholesky_jitter(1e-6):
+        pass
+    with settings.fast_computations(covar_root_decomposition=False, log_prob=False, solves=False):
+        assert settings.fast_pred_var.on() and not settings.fast_pred_var.off()
