@@ -367,7 +367,7 @@ __device__ __forceinline__ bool d5_next_diag_row(double (&c0)[NJ], double (&c1)[
     return true;
 }
 
-template <int P, int NJ>
+template <int P, int NJ, bool INV>
 __device__ __forceinline__ void d5_stage3_row(double (&c0)[NJ], double (&c1)[NJ], int bi, const D5Ctx& X,
                                               const double* Lc, const double* Xr, double2 aL, double2 aM) {
     if (bi <= P) return;
@@ -382,25 +382,28 @@ __device__ __forceinline__ void d5_stage3_row(double (&c0)[NJ], double (&c1)[NJ]
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             const int j = j0 + q;
-            if (j < P) b[q] = *reinterpret_cast<const double2*>(xb + j * D5_BS);
+            if (INV && j < P) b[q] = *reinterpret_cast<const double2*>(xb + j * D5_BS);
             else if (j > P && j <= bi) b[q] = *reinterpret_cast<const double2*>(lb + j * D5_BS);
         }
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             const int j = j0 + q;
-            if (j < P) dmma884(c0[j], c1[j], aM.x, b[q].x);
+            if (INV && j < P) dmma884(c0[j], c1[j], aM.x, b[q].x);
             else if (j > P && j <= bi) dmma884(c0[j], c1[j], aL.x, b[q].x);
         }
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             const int j = j0 + q;
-            if (j < P) dmma884(c0[j], c1[j], aM.y, b[q].y);
+            if (INV && j < P) dmma884(c0[j], c1[j], aM.y, b[q].y);
             else if (j > P && j <= bi) dmma884(c0[j], c1[j], aL.y, b[q].y);
         }
     }
 }
 
-template <int P>
+// index of block (i, j), j <= i, in the packed lower-triangular block list that the Cholesky-only edition exports
+__device__ __forceinline__ int d5_tri(int i, int j) { return i * (i + 1) / 2 + j; }
+
+template <int P, bool INV>
 __device__ __forceinline__ void d5_panel(double (&cA0)[8], double (&cA1)[8], double (&cB0)[16], double (&cB1)[16], const D5Ctx& X) {
     double* buf = X.sm + (P & 1) * D5_BUF;
     double* Lc = buf;
@@ -447,9 +450,15 @@ __device__ __forceinline__ void d5_panel(double (&cA0)[8], double (&cA1)[8], dou
         __syncwarp();
         if (HAS_A && onA) lA = *reinterpret_cast<const double2*>(LbA + 2 * X.lane);
         if (onB) lB = *reinterpret_cast<const double2*>(LbB + 2 * X.lane);
+        if (!INV) {     // export the finished blocks in operand layout for the blocked TRSM panel (scratch = this block's DT)
+            if (HAS_A && onA) *reinterpret_cast<double2*>(X.DTb + d5_tri(rA, P) * D5_BS + 2 * X.lane) = lA;
+            if (onB) *reinterpret_cast<double2*>(X.DTb + d5_tri(rB, P) * D5_BS + 2 * X.lane) = lB;
+        }
     }
-    d5_publish_row<P, 8>(cA0, cA1, rA, X, Xr);
-    d5_publish_row<P, 16>(cB0, cB1, rB, X, Xr);
+    if (INV) {
+        d5_publish_row<P, 8>(cA0, cA1, rA, X, Xr);
+        d5_publish_row<P, 16>(cB0, cB1, rB, X, Xr);
+    }
     GPX_TICK5(X, 1);
     __syncthreads();                                   // #2: column P of L and raw row P complete
     GPX_TICK5(X, 2);
@@ -461,7 +470,7 @@ __device__ __forceinline__ void d5_panel(double (&cA0)[8], double (&cA1)[8], dou
         GPX_TICK5(X, 3);
         // ---- stage 2b: M_ip = L_ip T; the slot restarts as B_ip = 0 - L_ip X_pp; A fragments of -M_ip
         double2 aMA = make_double2(0.0, 0.0), aMB = aMA;
-        if (onA | onB) {
+        if (INV && (onA | onB)) {
             double mA0 = 0.0, mA1 = 0.0, mB0 = 0.0, mB1 = 0.0;
             if (HAS_A) dmma884(mA0, mA1, lA.x, tk.x);
             dmma884(mB0, mB1, lB.x, tk.x);
@@ -475,12 +484,12 @@ __device__ __forceinline__ void d5_panel(double (&cA0)[8], double (&cA1)[8], dou
             __syncwarp();
         }
         // ---- stage 3: rank-8 updates of this warp's two block rows
-        if (HAS_A) d5_stage3_row<P, 8>(cA0, cA1, rA, X, Lc, Xr, aLA, aMA);
-        d5_stage3_row<P, 16>(cB0, cB1, rB, X, Lc, Xr, aLB, aMB);
+        if (HAS_A) d5_stage3_row<P, 8, INV>(cA0, cA1, rA, X, Lc, Xr, aLA, aMA);
+        d5_stage3_row<P, 16, INV>(cB0, cB1, rB, X, Lc, Xr, aLB, aMB);
         GPX_TICK5(X, 4);
     }
     // output row P of the inverse, X_pj = T_p B_pj, from the published raw blocks; dealt round-robin to the warps
-    for (int j = X.w; j < P; j += 8) {
+    for (int j = X.w; INV && j < P; j += 8) {
         const double2 b = *reinterpret_cast<const double2*>(Xr + j * D5_BS + 2 * X.lane);
         double r0 = 0.0, r1 = 0.0;
         dmma884(r0, r1, ta.x, b.x);
@@ -493,18 +502,23 @@ __device__ __forceinline__ void d5_panel(double (&cA0)[8], double (&cA1)[8], dou
     GPX_TICK5(X, 5);
 }
 
-template <int P>
+template <int P, bool INV>
 struct D5Unroll {
     static __device__ __forceinline__ void run(double (&cA0)[8], double (&cA1)[8], double (&cB0)[16], double (&cB1)[16], const D5Ctx& X) {
-        D5Unroll<P - 1>::run(cA0, cA1, cB0, cB1, X);
-        d5_panel<P>(cA0, cA1, cB0, cB1, X);
+        D5Unroll<P - 1, INV>::run(cA0, cA1, cB0, cB1, X);
+        d5_panel<P, INV>(cA0, cA1, cB0, cB1, X);
     }
 };
-template <>
-struct D5Unroll<-1> {
+template <bool INV>
+struct D5Unroll<-1, INV> {
     static __device__ __forceinline__ void run(double (&)[8], double (&)[8], double (&)[16], double (&)[16], const D5Ctx&) {}
 };
 
+// INV = true : L_pp -> K, X_pp = L_pp^-1 -> S and (transposed) DT.
+// INV = false: Cholesky only (the right-hand-side half of the rank-8 updates disappears): L_pp -> K, and the 8x8 blocks
+//              of L_pp plus the sixteen diagonal 8x8 inverses T_j in DMMA-operand layout -> this block's DT storage,
+//              used as scratch by trsm_strips_kernel (blocked TRSM panel; it also forms S / DT at the end of potrf).
+template <bool INV>
 __global__ void __maxnreg__(168)   // 9 warps are allocated as 12: 168 x 384 = 64512 registers
 potrf_diag5_kernel(double* __restrict__ K, int Np, int blk, int N, double* __restrict__ S, double* __restrict__ DT,
                    double* __restrict__ logdet_blk, int* __restrict__ info) {
@@ -613,9 +627,15 @@ potrf_diag5_kernel(double* __restrict__ K, int Np, int blk, int N, double* __res
                 const double t0 = TA[i0], t1 = TA[i0 + 2];
                 const long r_ = 8 * p + lr, c_ = 8 * p + 2 * lc;
                 *reinterpret_cast<double2*>(Ab + r_ * Np + c_) = lf;
-                *reinterpret_cast<double2*>(Sb + r_ * Np + c_) = make_double2(t0, t1);
-                DTb[c_ * TILE + r_] = t0;
-                DTb[(c_ + 1) * TILE + r_] = t1;
+                if (INV) {
+                    *reinterpret_cast<double2*>(Sb + r_ * Np + c_) = make_double2(t0, t1);
+                    DTb[c_ * TILE + r_] = t0;
+                    DTb[(c_ + 1) * TILE + r_] = t1;
+                } else {    // scratch: L_pp block and T_p in operand (A) layout
+                    const double2 la = make_double2(Lpp[lr * 12 + lc], Lpp[lr * 12 + lc + 4]);
+                    *reinterpret_cast<double2*>(DTb + d5_tri(p, p) * D5_BS + 2 * lane) = la;
+                    *reinterpret_cast<double2*>(DTb + (136 + p) * D5_BS + 2 * lane) = *reinterpret_cast<const double2*>(TA + 2 * lane);
+                }
             }
             __syncthreads();                                  // #2
             GPX_TICKF(5);
@@ -665,7 +685,7 @@ potrf_diag5_kernel(double* __restrict__ K, int Np, int blk, int N, double* __res
         d5_bar_arrive(1, 64);        // bar.arrive/bar.sync order the shared-memory hand-over (PTX producer/consumer idiom)
     }
     // while the first factor runs: zero the blocks above the diagonal of S and below the diagonal of DT
-    for (int b = w; b < 256; b += 8) {
+    for (int b = w; INV && b < 256; b += 8) {
         const int bi = b >> 4, bj = b & 15;
         if (bj > bi) {
             const int rr = lane >> 2, cc = (lane & 3) * 2;
@@ -673,7 +693,7 @@ potrf_diag5_kernel(double* __restrict__ K, int Np, int blk, int N, double* __res
             *reinterpret_cast<double2*>(DTb + (8 * bj + rr) * TILE + 8 * bi + cc) = make_double2(0.0, 0.0);
         }
     }
-    D5Unroll<15>::run(cA0, cA1, cB0, cB1, X);
+    D5Unroll<15, INV>::run(cA0, cA1, cB0, cB1, X);
 #ifdef GPX_DIAG_TIMING
     if (w == 0 && lane == 0) for (int i = 0; i < 6; ++i) logdet_blk[48 + i] = (double)t5_stat[1 + i];
 #endif
@@ -838,6 +858,96 @@ potrf_trailing_tma_kernel(const __grid_constant__ CUtensorMap tmK, double* __res
         *reinterpret_cast<double2*>(Ct + (long)row * Np + col) = make_double2(v0, v1);
     });
 }
+
+// ------------------------------------------------------------------------------------------------
+// Blocked TRSM against one factored diagonal block:  Y L_pp^T = A,  8 rows per warp, 8x8 blocks, using the sixteen
+// diagonal 8x8 inverses T_j the Cholesky-only diagonal kernel exported (with L_pp's blocks, in DMMA-operand layout,
+// into that block's DT storage):
+//     for kk = 0..15:  Y_kk = A_kk T_kk^T ;  A_j -= Y_kk L(j,kk)^T  for j > kk        (right-looking, in registers)
+// MODE 0 (panel, NW = 4 warps = 32 rows per CTA): A = K[rows][p*128 ..], overwritten by L[rows][p] = A L_pp^-T.
+//        Replaces the GEMM with the explicit 128x128 inverse: half the flops, no wait for that inverse, ~5 us.
+// MODE 1 (inverse, NW = 16 warps = the 128 rows of one block, one CTA per block, run once at the end of potrf):
+//        A = I, so Y = L_pp^-T = DT block; S block = Y^T; also clears the scratch.  All 64 blocks in one launch instead
+//        of 64 serial in-kernel inversions on the critical path.
+// ------------------------------------------------------------------------------------------------
+constexpr int TS_SCRATCH = (136 + 16) * D5_BS;      // doubles exported per diagonal block
+
+template <int NW, int MODE>
+__global__ void __launch_bounds__(NW * 32)
+trsm_strips_kernel(double* __restrict__ K, int Np, int p, double* __restrict__ S, double* __restrict__ DT) {
+    extern __shared__ double ts_sm[];
+    double* Ls = ts_sm;                              // [136][64] blocks of L_pp (A layout)
+    double* Ts = ts_sm + 136 * D5_BS;                // [16][64]  T_j (A layout)
+    double* scr = Ts + 16 * D5_BS + (threadIdx.x >> 5) * D5_BS;      // this warp's C-fragment -> A-operand transposer
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int lr = lane >> 2, lc = lane & 3;
+    const int blk = (MODE == 0) ? p : (int)blockIdx.x;
+    double* DTb = DT + (long)blk * TILE * TILE;
+    for (int e = threadIdx.x; e < TS_SCRATCH / 2; e += NW * 32)
+        reinterpret_cast<double2*>(ts_sm)[e] = reinterpret_cast<const double2*>(DTb)[e];
+    __syncthreads();
+    const int ia0 = d5_ia(lr, 2 * lc);
+    double a0[16], a1[16];
+    long row0 = 0;
+    if (MODE == 0) {
+        constexpr int PER = TILE / (NW * 8);
+        row0 = (long)(p + 1 + blockIdx.x / PER) * TILE + (blockIdx.x % PER) * (NW * 8) + w * 8;
+        const double* Ar = K + (row0 + lr) * Np + (long)p * TILE + 2 * lc;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const double2 v = *reinterpret_cast<const double2*>(Ar + 8 * j);
+            a0[j] = v.x; a1[j] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            a0[j] = (j == w && lr == 2 * lc) ? 1.0 : 0.0;
+            a1[j] = (j == w && lr == 2 * lc + 1) ? 1.0 : 0.0;
+        }
+    }
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+        double r0 = 0.0, r1 = 0.0;
+        double2 xf = make_double2(0.0, 0.0);
+        const bool live = (MODE == 0) || (kk >= w);          // identity input: Y_kk = 0 for kk < w
+        if (live) {
+            __syncwarp();
+            scr[ia0] = a0[kk]; scr[ia0 + 2] = a1[kk];
+            __syncwarp();
+            const double2 xa = *reinterpret_cast<const double2*>(scr + 2 * lane);
+            const double2 t = *reinterpret_cast<const double2*>(Ts + kk * D5_BS + 2 * lane);
+            dmma884(r0, r1, xa.x, t.x);                       // Y_kk = A_kk T_kk^T
+            dmma884(r0, r1, xa.y, t.y);
+            __syncwarp();
+            scr[ia0] = r0; scr[ia0 + 2] = r1;
+            __syncwarp();
+            xf = *reinterpret_cast<const double2*>(scr + 2 * lane);
+        }
+        if (MODE == 0) {
+            *reinterpret_cast<double2*>(K + (row0 + lr) * Np + (long)p * TILE + 8 * kk + 2 * lc) = make_double2(r0, r1);
+        } else {        // row 8w+lr of Y: DT block directly, S block transposed (zeros where kk < w)
+            const long off = (long)blk * TILE;
+            const int r_ = 8 * w + lr, c_ = 8 * kk + 2 * lc;
+            a0[kk] = r0; a1[kk] = r1;                         // keep: DT is also the scratch other warps still read
+            S[(off + c_) * Np + off + r_] = r0;
+            S[(off + c_ + 1) * Np + off + r_] = r1;
+        }
+        if (live) {
+#pragma unroll
+            for (int j = kk + 1; j < 16; ++j) {
+                const double2 l = *reinterpret_cast<const double2*>(Ls + (j * (j + 1) / 2 + kk) * D5_BS + 2 * lane);
+                dmma884(a0[j], a1[j], -xf.x, l.x);            // A_j -= Y_kk L(j,kk)^T
+                dmma884(a0[j], a1[j], -xf.y, l.y);
+            }
+        }
+    }
+    if (MODE == 1) {        // every warp is done with the scratch (it was copied to shared memory before the barrier above)
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk)
+            *reinterpret_cast<double2*>(DTb + (8 * w + lr) * TILE + 8 * kk + 2 * lc) = make_double2(a0[kk], a1[kk]);
+    }
+}
+constexpr int TS_SMEM = (TS_SCRATCH + 16 * D5_BS) * 8;
 
 // Narrow-tile editions of the two kernels on potrf's critical path (tile = ROWS x 128, ROWS = WM*S*8 in {64, 32}):
 // grid.x = (#block rows) * (128 / ROWS).  tmKr is K with a ROWS-row box for the A operand.
@@ -1089,7 +1199,10 @@ static void set_gemm_attrs() {
     cudaFuncSetAttribute(trtri_step2_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM_BYTES);
     cudaFuncSetAttribute(lauum_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM_BYTES);
     cudaFuncSetAttribute(potrf_diag3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D3_SMEM);
-    cudaFuncSetAttribute(potrf_diag5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D5_SMEM);
+    cudaFuncSetAttribute(potrf_diag5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, D5_SMEM);
+    cudaFuncSetAttribute(potrf_diag5_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, D5_SMEM);
+    cudaFuncSetAttribute(trsm_strips_kernel<4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM);
+    cudaFuncSetAttribute(trsm_strips_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM);
     cudaFuncSetAttribute(potrf_panel_narrow_kernel<2, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM_BYTES);
     cudaFuncSetAttribute(potrf_panel_narrow_kernel<1, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM_BYTES);
     cudaFuncSetAttribute(potrf_column_narrow_kernel<2, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM_BYTES);
@@ -1187,8 +1300,14 @@ int potrf(double* K, int Np, int N, double* S, double* DT, double* logdet_blk, i
     // panel / look-ahead column over n block rows: with few rows, narrower tiles put the same work on more SMs
     static int narrow = -1;
     if (narrow < 0) { const char* e = getenv("GPX_POTRF_NARROW"); narrow = (e && e[0] == '0') ? 0 : 1; }
+    // GPX_POTRF_PANEL=gemm: panel = GEMM with the explicit inverse of the diagonal block (computed inside the diagonal
+    // kernel); default: Cholesky-only diagonal kernel + blocked TRSM panel + one batched inversion launch at the end
+    static int panel_trsm = -1;
+    if (panel_trsm < 0) { const char* e = getenv("GPX_POTRF_PANEL"); panel_trsm = (e && e[0] == 'g') ? 0 : 1; }
+    const bool trsm_mode = tma && panel_trsm && diag_impl() == 5;
     auto panel = [&](int n, int p) {
-        if (!tma) potrf_panel_kernel<<<n, G_THREADS, G_SMEM_BYTES, st>>>(K, Np, p, S);
+        if (trsm_mode) trsm_strips_kernel<4, 0><<<4 * n, 128, TS_SMEM, st>>>(K, Np, p, S, DT);
+        else if (!tma) potrf_panel_kernel<<<n, G_THREADS, G_SMEM_BYTES, st>>>(K, Np, p, S);
         else if (narrow && 4 * n <= 148) potrf_panel_narrow_kernel<1, 4, 2><<<4 * n, GT_THREADS, GT_SMEM_BYTES, st>>>(tmK32, tmS, K, Np, p);
         else if (narrow && 2 * n <= 148) potrf_panel_narrow_kernel<2, 4, 4><<<2 * n, GT_THREADS, GT_SMEM_BYTES, st>>>(tmK64, tmS, K, Np, p);
         else potrf_panel_tma_kernel<<<n, GT_THREADS, GT_SMEM_BYTES, st>>>(tmK, tmS, K, Np, p);
@@ -1206,8 +1325,10 @@ int potrf(double* K, int Np, int N, double* S, double* DT, double* logdet_blk, i
     auto diag = [&](int p) {
         if (diag_impl() == 3)
             potrf_diag3_kernel<<<1, D3_THREADS, D3_SMEM, st>>>(K, Np, p, N, S, DT, logdet_blk, info);
+        else if (trsm_mode)
+            potrf_diag5_kernel<false><<<1, D5_THREADS, D5_SMEM, st>>>(K, Np, p, N, S, DT, logdet_blk, info);
         else
-            potrf_diag5_kernel<<<1, D5_THREADS, D5_SMEM, st>>>(K, Np, p, N, S, DT, logdet_blk, info);
+            potrf_diag5_kernel<true><<<1, D5_THREADS, D5_SMEM, st>>>(K, Np, p, N, S, DT, logdet_blk, info);
     };
     static int ob_env = -1, sw_env = -1;
     if (ob_env < 0) { const char* e = getenv("GPX_POTRF_OB"); ob_env = (e && e[0] >= '1' && e[0] <= '8') ? e[0] - '0' : 0; }
@@ -1296,6 +1417,8 @@ int potrf(double* K, int Np, int N, double* S, double* DT, double* logdet_blk, i
             side_pending = false;
         }
     }
+    if (trsm_mode)      // S / DT diagonal blocks for all block columns at once, from the exported 8x8 blocks
+        trsm_strips_kernel<16, 1><<<nb, 512, TS_SMEM, st>>>(K, Np, 0, S, DT);
     if (la != nullptr && side_pending) cudaStreamWaitEvent(st, la->ev_side[(nb - 3) & 1], 0);   // last helper launch: p = nb-3
     if (st != st_caller) {
         cudaEventRecord(la->ev_join, st);

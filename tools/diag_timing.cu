@@ -23,12 +23,12 @@ int main() {
         printf("v3 rep %d err=%d cycles (warp 0 view): load=%.0f stage1+wait=%.0f stage2=%.0f stage3=%.0f writeback=%.0f | owner: factor8x8=%.0f Tinv=%.0f (sums over 16 panels)\n",
                rep, (int)e, h[8], h[9], h[10], h[11], h[12], h[20], h[21]);
     }
-    cudaFuncSetAttribute(potrf_diag5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D5_SMEM);
+    cudaFuncSetAttribute(potrf_diag5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, D5_SMEM);
     for (int rep = 0; rep < 4; ++rep) {
         cudaMemcpy(K, A.data(), Np * Np * 8, cudaMemcpyHostToDevice); cudaMemset(ld, 0, 64 * 8);
         cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
         cudaEventRecord(e0);
-        potrf_diag5_kernel<<<1, D5_THREADS, D5_SMEM>>>(K, Np, 0, Np, S, DT, ld, info);
+        potrf_diag5_kernel<true><<<1, D5_THREADS, D5_SMEM>>>(K, Np, 0, Np, S, DT, ld, info);
         { cudaError_t le = cudaGetLastError(); if (le != cudaSuccess) printf("launch error: %s\n", cudaGetErrorString(le)); }
         cudaEventRecord(e1);
         cudaError_t e = cudaDeviceSynchronize();
