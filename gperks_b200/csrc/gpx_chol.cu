@@ -883,9 +883,11 @@ trsm_strips_kernel(double* __restrict__ K, int Np, int p, double* __restrict__ S
     const int lr = lane >> 2, lc = lane & 3;
     const int blk = (MODE == 0) ? p : (int)blockIdx.x;
     double* DTb = DT + (long)blk * TILE * TILE;
+    // 78 KB of operand blocks: asynchronous 16-byte copies, all in flight at once (a load/store loop through registers
+    // serialised on the L2 latency and took longer than the solve itself)
     for (int e = threadIdx.x; e < TS_SCRATCH / 2; e += NW * 32)
-        reinterpret_cast<double2*>(ts_sm)[e] = reinterpret_cast<const double2*>(DTb)[e];
-    __syncthreads();
+        cp_async16(ts_sm + 2 * e, DTb + 2 * e);
+    cp_async_commit();
     const int ia0 = d5_ia(lr, 2 * lc);
     double a0[16], a1[16];
     long row0 = 0;
@@ -905,6 +907,8 @@ trsm_strips_kernel(double* __restrict__ K, int Np, int p, double* __restrict__ S
             a1[j] = (j == w && lr == 2 * lc + 1) ? 1.0 : 0.0;
         }
     }
+    cp_async_wait<0>();      // the strip's own rows were loaded meanwhile
+    __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < 16; ++kk) {
         double r0 = 0.0, r1 = 0.0;
