@@ -41,7 +41,7 @@ int gpx_kmat_cross(const double* Xs, long m_valid, const double* X, int N, int D
                    double* mean_part, int Mc, void* stream);
 
 /* In-place blocked Cholesky of K (lower) -> L; writes the inverted diagonal blocks into S and DT,
- * per-block sum(log L_ii) into logdet_blk[Np/128], and info (LAPACK convention: 0, or the 1-based order of
+ * per-block sum(log L_ii) into logdet_blk[Np/128], and info (DT is also used as scratch while the call runs; LAPACK convention: 0, or the 1-based order of
  * the first leading minor that is not positive definite; the factor is then undefined).
  * Stream semantics: all work is ordered after `stream` and joined back into it before the call returns, but it
  * runs on two per-device helper streams (a high-priority one for the panel chain, a low-priority one for the
