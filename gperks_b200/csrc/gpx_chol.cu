@@ -1211,6 +1211,7 @@ static void set_gemm_attrs() {
     cudaFuncSetAttribute(potrf_panel_narrow_kernel<1, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM_BYTES);
     cudaFuncSetAttribute(potrf_column_narrow_kernel<2, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM_BYTES);
     cudaFuncSetAttribute(potrf_column_narrow_kernel<1, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM_BYTES);
+    cudaFuncSetAttribute(potrf_column_narrow_kernel<1, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM_BYTES);
     cudaFuncSetAttribute(trtri_step1_narrow_kernel<2, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM_BYTES);
     cudaFuncSetAttribute(trtri_step1_narrow_kernel<1, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM_BYTES);
     cudaFuncSetAttribute(trtri_step2_narrow_kernel<2, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM_BYTES);
@@ -1293,13 +1294,14 @@ int potrf(double* K, int Np, int N, double* S, double* DT, double* logdet_blk, i
         st = la->chain;
     }
     const bool tma = use_chol_tma();
-    CUtensorMap tmK, tmS, tmK64, tmK32;
+    CUtensorMap tmK, tmS, tmK64, tmK32, tmK16;
     if (tma) {
         int rc;
         if ((rc = encode_f64_rowmajor(&tmK, K, Np, Np, Np, TILE))) return rc;
         if ((rc = encode_f64_rowmajor(&tmS, S, Np, Np, Np, TILE))) return rc;
         if ((rc = encode_f64_rowmajor(&tmK64, K, Np, Np, Np, 64))) return rc;
         if ((rc = encode_f64_rowmajor(&tmK32, K, Np, Np, Np, 32))) return rc;
+        if ((rc = encode_f64_rowmajor(&tmK16, K, Np, Np, Np, 16))) return rc;
     }
     // panel / look-ahead column over n block rows: with few rows, narrower tiles put the same work on more SMs
     static int narrow = -1;
@@ -1317,7 +1319,8 @@ int potrf(double* K, int Np, int N, double* S, double* DT, double* logdet_blk, i
         else potrf_panel_tma_kernel<<<n, GT_THREADS, GT_SMEM_BYTES, st>>>(tmK, tmS, K, Np, p);
     };
     auto column = [&](int n, int p) {          // block rows p+1 .. p+n of block column p+1
-        if (tma && narrow && 4 * n <= 148) potrf_column_narrow_kernel<1, 4, 2><<<4 * n, GT_THREADS, GT_SMEM_BYTES, st>>>(tmK32, tmK, K, Np, p);
+        if (tma && narrow && 8 * n <= 148) potrf_column_narrow_kernel<1, 2, 2><<<8 * n, GT_THREADS, GT_SMEM_BYTES, st>>>(tmK16, tmK, K, Np, p);
+        else if (tma && narrow && 4 * n <= 148) potrf_column_narrow_kernel<1, 4, 2><<<4 * n, GT_THREADS, GT_SMEM_BYTES, st>>>(tmK32, tmK, K, Np, p);
         else if (tma && narrow && 2 * n <= 148) potrf_column_narrow_kernel<2, 4, 4><<<2 * n, GT_THREADS, GT_SMEM_BYTES, st>>>(tmK64, tmK, K, Np, p);
         else if (tma) potrf_trailing_tma_kernel<<<dim3(1, n), GT_THREADS, GT_SMEM_BYTES, st>>>(tmK, K, Np, p, p + 1, p + 1, 1);
         else potrf_trailing_kernel<<<dim3(1, n), G_THREADS, G_SMEM_BYTES, st>>>(K, Np, p, p + 1, p + 1);
