@@ -602,9 +602,14 @@ potrf_diag5_kernel(double* __restrict__ K, int Np, int blk, int N, double* __res
                 for (int i = 0; i < 8; ++i) {
                     const double t = x[i] * inv[i];
                     TA[d5_ia(i, c)] = t;
-                    TK[d5_ib(i, c)] = t;
+                    if (INV) TK[d5_ib(i, c)] = t;            // T as a B operand is only needed for M = L T
                 }
             }
+            __syncwarp();
+            GPX_TICKF(3);
+            __syncthreads();                                  // #1: T_p visible to the compute warps
+            GPX_TICKF(4);
+            // L_pp itself is only needed for the outputs below: formed after the barrier, off the critical path
             if (lane == 8) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -618,9 +623,6 @@ potrf_diag5_kernel(double* __restrict__ K, int Np, int blk, int N, double* __res
                 }
             }
             __syncwarp();
-            GPX_TICKF(3);
-            __syncthreads();                                  // #1: T_p visible to the compute warps
-            GPX_TICKF(4);
             {   // outputs of the diagonal 8x8 block: L_pp -> K, T -> S and (transposed) DT
                 const double2 lf = *reinterpret_cast<const double2*>(Lpp + lr * 12 + 2 * lc);
                 const int i0 = d5_ia(lr, 2 * lc);
