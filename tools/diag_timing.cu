@@ -38,6 +38,21 @@ int main() {
                h[40], h[41], h[43], h[44], h[45]);
         printf("            compute warp 0: wait#1=%.0f stage2=%.0f wait#2=%.0f nextdiag=%.0f stage3=%.0f output=%.0f\n", h[48], h[49], h[50], h[51], h[52], h[53]);
     }
+    cudaFuncSetAttribute(potrf_diag5_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, D5_SMEM);
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaMemcpy(K, A.data(), Np * Np * 8, cudaMemcpyHostToDevice); cudaMemset(ld, 0, 64 * 8);
+        cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0);
+        potrf_diag5_kernel<false><<<1, D5_THREADS, D5_SMEM>>>(K, Np, 0, Np, S, DT, ld, info);
+        { cudaError_t le = cudaGetLastError(); if (le != cudaSuccess) printf("launch error: %s\n", cudaGetErrorString(le)); }
+        cudaEventRecord(e1);
+        cudaError_t e = cudaDeviceSynchronize();
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        double h[64]; cudaMemcpy(h, ld, 64 * 8, cudaMemcpyDeviceToHost);
+        printf("v5 Cholesky-only rep %d err=%d %.1f us logdet=%.6f | factor warp: wait_block=%.0f load+ldl=%.0f T+store=%.0f wait#1=%.0f out+wait#2=%.0f\n", rep, (int)e, ms * 1e3, h[0],
+               h[40], h[41], h[43], h[44], h[45]);
+        printf("            compute warp 0: wait#1=%.0f stage2=%.0f wait#2=%.0f nextdiag=%.0f stage3=%.0f output=%.0f\n", h[48], h[49], h[50], h[51], h[52], h[53]);
+    }
     return 0;
 }
 
