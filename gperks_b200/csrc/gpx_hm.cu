@@ -11,43 +11,77 @@
 namespace gpx {
 
 constexpr int HM_KMAX = 8;
+constexpr int HM_UNROLL = 4;       // emulators whose (mean, std) loads are issued before any of them is consumed
 
-__global__ void implausibility_kernel(const double* __restrict__ mean, const double* __restrict__ std_, long M, int E,
-                                      const double* __restrict__ z, const double* __restrict__ v, int maxno,
-                                      double* __restrict__ I, double* __restrict__ PV) {
+// Insert (a, b) into the descending lists of the MAXNO largest values seen so far.
+template <int MAXNO>
+__device__ __forceinline__ void hm_insert(double (&topI)[MAXNO], double (&topP)[MAXNO], double a, double b) {
+#pragma unroll
+    for (int k = 0; k < MAXNO; ++k) {
+        const double ti = topI[k], tp = topP[k];
+        const bool ci = a > ti, cp = b > tp;
+        topI[k] = ci ? a : ti;  a = ci ? ti : a;
+        topP[k] = cp ? b : tp;  b = cp ? tp : b;
+    }
+}
+
+// Explicit round-to-nearest intrinsics: nvcc must not contract sd*sd + v into an FMA, numpy does not.
+__device__ __forceinline__ void hm_terms(double mu, double sd, double ze, double ve, double& a, double& b) {
+    const double var = __dmul_rn(sd, sd);
+    const double d = __dsub_rn(mu, ze);
+    a = __dsqrt_rn(__ddiv_rn(__dmul_rn(d, d), __dadd_rn(var, ve)));
+    b = __ddiv_rn(var, ve);
+}
+
+// One thread per point; the maxno-th largest is kept in MAXNO registers per list (compile-time MAXNO: the edition with a
+// run-time bound on 8-entry lists needed 151 registers, ran one block per SM with one load in flight per thread and
+// reached 0.68 TB/s, profiles/r01_ncu_hbm_stages.txt).
+template <int MAXNO>
+__global__ void __launch_bounds__(256, (MAXNO <= 4 ? 4 : 3))
+implausibility_kernel(const double* __restrict__ mean, const double* __restrict__ std_, long M, int E,
+                      const double* __restrict__ z, const double* __restrict__ v, double* __restrict__ I, double* __restrict__ PV) {
     const long m = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= M) return;
-    double topI[HM_KMAX], topP[HM_KMAX];      // descending: top[0] largest ... top[maxno-1] = answer
+    double topI[MAXNO], topP[MAXNO];          // descending: top[0] largest ... top[MAXNO-1] = answer
 #pragma unroll
-    for (int k = 0; k < HM_KMAX; ++k) { topI[k] = -INFINITY; topP[k] = -INFINITY; }
-    for (int e = 0; e < E; ++e) {
-        const double mu = mean[(long)e * M + m];
-        const double sd = std_[(long)e * M + m];
-        const double var = sd * sd;
-        const double d = mu - z[e];
-        double a = sqrt((d * d) / (var + v[e]));
-        double b = var / v[e];
+    for (int k = 0; k < MAXNO; ++k) { topI[k] = -INFINITY; topP[k] = -INFINITY; }
+    const double* pm = mean + m;
+    const double* ps = std_ + m;
+    int e = 0;
+    for (; e + HM_UNROLL <= E; e += HM_UNROLL) {
+        double mu[HM_UNROLL], sd[HM_UNROLL];
 #pragma unroll
-        for (int k = 0; k < HM_KMAX; ++k) {
-            if (k < maxno) {
-                if (a > topI[k]) { double t = topI[k]; topI[k] = a; a = t; }
-                if (b > topP[k]) { double t = topP[k]; topP[k] = b; b = t; }
-            }
+        for (int u = 0; u < HM_UNROLL; ++u) {
+            mu[u] = __ldcs(pm + (long)(e + u) * M);       // streamed once: evict-first
+            sd[u] = __ldcs(ps + (long)(e + u) * M);
+        }
+#pragma unroll
+        for (int u = 0; u < HM_UNROLL; ++u) {
+            double a, b;
+            hm_terms(mu[u], sd[u], __ldg(z + e + u), __ldg(v + e + u), a, b);
+            hm_insert<MAXNO>(topI, topP, a, b);
         }
     }
-    double ri = topI[0], rp = topP[0];
-#pragma unroll
-    for (int k = 1; k < HM_KMAX; ++k)
-        if (k == maxno - 1) { ri = topI[k]; rp = topP[k]; }
-    I[m] = ri;
-    PV[m] = rp;
+    for (; e < E; ++e) {
+        double a, b;
+        hm_terms(__ldcs(pm + (long)e * M), __ldcs(ps + (long)e * M), __ldg(z + e), __ldg(v + e), a, b);
+        hm_insert<MAXNO>(topI, topP, a, b);
+    }
+    __stcs(I + m, topI[MAXNO - 1]);
+    __stcs(PV + m, topP[MAXNO - 1]);
 }
 
 int implausibility(const double* mean, const double* std_, long M, int E, const double* z, const double* v, int maxno,
                    double* I, double* PV, cudaStream_t st) {
     if (maxno < 1 || maxno > HM_KMAX || maxno > E) return -7;
     if (M == 0) return 0;
-    implausibility_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(mean, std_, M, E, z, v, maxno, I, PV);
+    const unsigned grid = (unsigned)((M + 255) / 256);
+#define GPX_HM_CASE(K) case K: implausibility_kernel<K><<<grid, 256, 0, st>>>(mean, std_, M, E, z, v, I, PV); break;
+    switch (maxno) {
+        GPX_HM_CASE(1) GPX_HM_CASE(2) GPX_HM_CASE(3) GPX_HM_CASE(4)
+        GPX_HM_CASE(5) GPX_HM_CASE(6) GPX_HM_CASE(7) GPX_HM_CASE(8)
+    }
+#undef GPX_HM_CASE
     GPX_CHECK_LAUNCH();
     return 0;
 }
