@@ -1142,22 +1142,35 @@ lauum_narrow_kernel(const __grid_constant__ CUtensorMap tmSr, const __grid_const
 //   mode 0:  u[i]     = sum_{k <= i} Linv[i][k] r[k]                      (rows of the lower part)
 //   mode 1:  alpha[i] = sum_{k >= i} Linv[k][i] u[k] = DT-block part + mirror part of row i
 // ------------------------------------------------------------------------------------------------
-__global__ void trmv_kernel(const double* __restrict__ S, const double* __restrict__ DT, int Np,
-                            const double* __restrict__ x, double* __restrict__ y, int mode) {
+// 16-byte loads (rows and segment starts are multiples of 128 doubles), four of them in flight per lane and two
+// accumulators: the 8-byte edition stalled on its loads at 50 % occupancy (ncu: 4.2 TB/s, profiles/r01_ncu_hbm_stages.txt).
+__device__ __forceinline__ void trmv_dot2(const double* __restrict__ a, const double* __restrict__ x, int k0, int k1,
+                                          int lane, double& s0, double& s1) {
+#pragma unroll 4
+    for (int k = k0 + 2 * lane; k < k1; k += 64) {
+        const double2 av = __ldcs(reinterpret_cast<const double2*>(a + k));
+        const double2 xv = *reinterpret_cast<const double2*>(x + k);
+        s0 = fma(av.x, xv.x, s0);
+        s1 = fma(av.y, xv.y, s1);
+    }
+}
+
+__global__ void __launch_bounds__(256) trmv_kernel(const double* __restrict__ S, const double* __restrict__ DT, int Np,
+                                                   const double* __restrict__ x, double* __restrict__ y, int mode) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int i = blockIdx.x * 8 + warp;
     if (i >= Np) return;
     const int b = i / TILE;
     const double* row = S + (long)i * Np;
-    double s = 0.0;
+    double s0 = 0.0, s1 = 0.0;
     if (mode == 0) {
-        const int kend = (b + 1) * TILE;    // masked zeros above the diagonal inside the block
-        for (int k = lane; k < kend; k += 32) s = fma(row[k], x[k], s);
+        trmv_dot2(row, x, 0, (b + 1) * TILE, lane, s0, s1);    // masked zeros above the diagonal inside the block
     } else {
         const double* drow = DT + (long)b * TILE * TILE + (long)(i - b * TILE) * TILE;
-        for (int k = lane; k < TILE; k += 32) s = fma(drow[k], x[b * TILE + k], s);
-        for (int k = (b + 1) * TILE + lane; k < Np; k += 32) s = fma(row[k], x[k], s);
+        trmv_dot2(drow, x + b * TILE, 0, TILE, lane, s0, s1);
+        trmv_dot2(row, x, (b + 1) * TILE, Np, lane, s0, s1);
     }
+    double s = s0 + s1;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) y[i] = s;

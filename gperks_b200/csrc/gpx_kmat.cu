@@ -292,7 +292,7 @@ static int launch_kmat_cross_f32(const double* Xs, long m_valid, const double* X
 //   p == D : sum W_ij k_ij / s
 //   p == D+1 : sum_i W_ii
 template <int KIND>
-__global__ void __launch_bounds__(P_THREADS)
+__global__ void __launch_bounds__(P_THREADS, 3)
 mll_grad_tile_kernel(const double* __restrict__ X, int N, int D, const double* __restrict__ theta,
                      const double* __restrict__ Kinv, int Np, const double* __restrict__ alpha,
                      double* __restrict__ partial) {
@@ -322,9 +322,23 @@ mll_grad_tile_kernel(const double* __restrict__ X, int N, int D, const double* _
     double* sacc = sred + 8 * (MAXD + 2);      // [D][256]
     for (int d = 0; d < D; ++d) sacc[d * P_THREADS + threadIdx.x] = 0.0;
     double acc_s = 0.0, acc_n = 0.0;
+    // K_hat^-1 entries of the NEXT row are requested before this row's distances and sqrt/exp are evaluated (the tile is
+    // full: Np is padded, so the loads need no bounds check); without it every row waited on its own eight loads
+    // (ncu: long-scoreboard 3.8 warps per issue, 0.63 TB/s).
+    const double* wbase = Kinv + ((long)bi * TILE + ty) * Np + (long)bj * TILE + tx;
+    double wnext[8];
+#pragma unroll
+    for (int b = 0; b < 8; ++b) wnext[b] = __ldcs(wbase + 16 * b);
 #pragma unroll 1
     for (int a = 0; a < 8; ++a) {
         const int row = ty + 16 * a;
+        double wcur[8];
+#pragma unroll
+        for (int b = 0; b < 8; ++b) wcur[b] = wnext[b];
+        if (a < 7) {
+#pragma unroll
+            for (int b = 0; b < 8; ++b) wnext[b] = __ldcs(wbase + (long)(16 * (a + 1)) * Np + 16 * b);
+        }
         double r2[8];
 #pragma unroll
         for (int b = 0; b < 8; ++b) r2[b] = 0.0;
@@ -344,7 +358,7 @@ mll_grad_tile_kernel(const double* __restrict__ X, int N, int D, const double* _
             const long j = (long)bj * TILE + tx + 16 * b;
             double w = 0.0, g = 0.0, k = 0.0;
             if (i < N && j < N) {
-                w = Kinv[i * Np + j] - ai * salj[tx + 16 * b];
+                w = wcur[b] - ai * salj[tx + 16 * b];
                 k = kernel_value_grad<KIND>(r2[b], s, g);
             }
             acc_s = fma(w, k, acc_s);

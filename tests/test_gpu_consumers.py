@@ -68,6 +68,33 @@ def test_history_matching_matches_reference_loop(dev):
         assert (W.I[-50:] < W.cutoff).all()
 
 
+@pytest.mark.parametrize("E,maxno", [(1, 1), (3, 2), (4, 1), (5, 5), (8, 1), (8, 3), (8, 8), (11, 2), (13, 7)])
+def test_implausibility_c_abi_is_byte_identical_to_numpy(dev, E, maxno):
+    """gpx_implausibility for every code path of the kernel (blocks of four emulators + remainder, every list length),
+    against the reference's arithmetic (GPErks/perks/history_matching.py:46-62) written with numpy."""
+    from gperks_b200 import _native as nv
+    rng = np.random.default_rng(100 * E + maxno)
+    M = 3001
+    means = rng.standard_normal((E, M))
+    stds = rng.random((E, M)) + 0.05
+    stds[:, ::97] = 0.0                                # exact zeros in the variance
+    means[0, ::101] = means[E - 1, ::101]              # ties
+    z = rng.standard_normal(E)
+    v = rng.random(E) + 0.01
+    d_m, d_s = torch.as_tensor(means, device=dev), torch.as_tensor(stds, device=dev)
+    d_z, d_v = torch.as_tensor(z, device=dev), torch.as_tensor(v, device=dev)
+    Id = torch.empty(M, dtype=torch.float64, device=dev)
+    PVd = torch.empty(M, dtype=torch.float64, device=dev)
+    nv.check(nv.lib().gpx_implausibility(nv.ptr(d_m), nv.ptr(d_s), M, E, nv.ptr(d_z), nv.ptr(d_v), maxno, nv.ptr(Id), nv.ptr(PVd),
+                                         nv.stream_ptr()), "gpx_implausibility")
+    V = np.power(stds, 2)
+    Iref = np.sort(np.sqrt(np.power(means - z[:, None], 2) / (V + v[:, None])), axis=0)[-maxno]
+    PVref = np.sort(V / v[:, None], axis=0)[-maxno]
+    assert np.array_equal(Id.cpu().numpy(), Iref) and np.array_equal(PVd.cpu().numpy(), PVref)
+    assert nv.lib().gpx_implausibility(nv.ptr(d_m), nv.ptr(d_s), M, E, nv.ptr(d_z), nv.ptr(d_v), E + 1, nv.ptr(Id), nv.ptr(PVd),
+                                       nv.stream_ptr()) < 0
+
+
 def test_sobol_gsa_against_analytic_indices(dev):
     from functools import partial
     from gperks_b200.perks.gsa import SobolGSA
