@@ -10,7 +10,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIBDIR = PKG / "lib"
 LIB = LIBDIR / "libgpx.so"
-SOURCES = ["gpx_api.cu", "gpx_kmat.cu", "gpx_chol.cu", "gpx_predict.cu", "gpx_hm.cu", "gpx_tf32.cu"]
+SOURCES = ["gpx_api.cu", "gpx_kmat.cu", "gpx_chol.cu", "gpx_predict.cu", "gpx_hm.cu", "gpx_tf32.cu", "gpx_i8.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
@@ -27,7 +27,7 @@ def nvcc_path() -> str:
 
 def build(force: bool = False, verbose: bool = False) -> Path:
     srcs = [CSRC / s for s in SOURCES]
-    deps = srcs + [CSRC / "gpx_common.cuh", CSRC / "gpx_tma.cuh", CSRC / "gpx_gemm_tma.cuh", PKG.parent / "include" / "gpx.h"]
+    deps = srcs + [CSRC / "gpx_common.cuh", CSRC / "gpx_tma.cuh", CSRC / "gpx_gemm_tma.cuh", CSRC / "gpx_tc.cuh", PKG.parent / "include" / "gpx.h"]
     if LIB.exists() and not force:
         return LIB
     LIBDIR.mkdir(parents=True, exist_ok=True)

@@ -44,6 +44,13 @@ _SIGS = {
     "gpx_predict_meanvar_tf32": (C.c_int, [_P, C.c_long, _P, C.c_int, C.c_int, _P, _P, _P, C.c_int, _P, _P, C.c_int, _P,
                                            _P, _P, C.c_int, C.c_int, _P, _P, C.c_double, C.c_double, C.c_double, _P,
                                            _P, _P, C.c_size_t, C.c_int, C.c_int, _P]),
+    "gpx_slice_i8": (C.c_int, [_P, C.c_int, C.c_int, C.c_long, _P, C.c_long, C.c_int, C.c_int, _P, _P, _P]),
+    "gpx_i8_row_tiles": (C.c_int, [C.c_int]),
+    "gpx_trmm_sumsq_i8": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.c_int, _P, _P, _P]),
+    "gpx_predict_i8_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "gpx_predict_meanvar_i8": (C.c_int, [_P, C.c_long, _P, C.c_int, C.c_int, _P, _P, _P, C.c_int, _P, _P, C.c_int, C.c_int,
+                                         _P, _P, _P, C.c_int, C.c_int, _P, _P, C.c_double, C.c_double, C.c_double, _P,
+                                         _P, _P, C.c_size_t, C.c_int, _P]),
     "gpx_implausibility": (C.c_int, [_P, _P, C.c_long, C.c_int, _P, _P, C.c_int, _P, _P, _P]),
     "gpx_peak_dmma": (C.c_double, [C.c_int, C.c_int, _P, _P]),
     "gpx_peak_dfma": (C.c_double, [C.c_int, C.c_int, _P, _P]),

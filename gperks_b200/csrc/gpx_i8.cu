@@ -1,0 +1,359 @@
+// "Sliced-integer mode" of the predictive variance: the FP64 contraction V = K* L^-T evaluated EXACTLY-ROUNDED on the
+// 5th-generation tensor cores' integer path (tcgen05.mma kind::i8, exact int32 accumulators in TMEM).
+//
+// Each operand is scaled by a power of two (L^-1: one per row; K*: one for the whole matrix, k <= outputscale) and cut
+// into S signed 7-bit slices by repeated round-to-nearest
+//       x * scale = sum_{j<S} I_j 2^{-7(j+1)} + rho,      |I_j| <= 64,  |rho| <= 2^{-7S-1},
+// so that            V[m][i] = (1 / scale_i scale_K) sum_{g<S} 2^{-7(g+2)} sum_{a+b=g} <I_a(L^-1 row i), I_b(K* row m)>
+// up to the dropped products a+b >= S.  Every inner product is an integer GEMM whose int32 accumulation is exact
+// (|sum| <= 64*64*K*S < 2^31 for K <= 32768); the S diagonals are combined in FP64 in the epilogue.  With S = 5 the
+// predictive std agrees with the FP64 path to ~5e-8 relative (N = 8192, noise 1e-2; 5e-7 at noise 1e-4), S = 6 to ~5e-9
+// -- inside the 1e-6 bar of the FP64 mode, at the integer tensor-core rate instead of the DMMA rate
+// (the variance contraction is the N^2 FLOP/point term that bounds predict).
+//
+// Tile: 128 test points (MMA M = TMEM lanes) x 64 rows of L^-1 (per slice), S accumulators of 64 TMEM columns, one per
+// diagonal g.  The S slices of the L^-1 tile are STACKED along MMA N in shared memory, so for the K* slice a one
+// instruction with N = 64 (S - a) (cut at 256) multiplies it with the L^-1 slices b = 0 .. S-1-a and lands in the
+// accumulators g = a .. S-1, which are contiguous in TMEM: S = 5 needs 6 MMAs per 32-deep k step instead of 15, and the
+// K* slices are read from shared memory 6 times instead of 15.  The accumulators are zeroed once through tcgen05.st so
+// every MMA accumulates.  K runs over the training index in BKB-byte slices (SWIZZLE_64B: three stages of 60-72 KB).
+// Warp roles as in gpx_tf32.cu: warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer, warps 2..9 epilogue.
+#include "gpx_common.cuh"
+#include "gpx_tma.cuh"
+#include "gpx_tc.cuh"
+#include <stdlib.h>
+
+namespace gpx {
+
+constexpr int I_M = 128;        // test points per tile
+constexpr int I_N = 64;         // L^-1 rows per tile (and per slice in the stacked B operand)
+constexpr int I_BITS = 7;
+constexpr int I_THREADS = 320;
+constexpr int I_BAND = 8;       // m tiles that share L^-1 tiles through L2
+constexpr int I_TMEM_COLS = 512;
+constexpr int I_SMAX = 6;
+
+template <int S, int BKB>
+struct I8Cfg {
+    static constexpr int STAGES = (BKB == 64) ? 3 : 1;
+    static constexpr int A_BYTES = I_M * BKB;
+    static constexpr int B_BYTES = I_N * BKB;
+    static constexpr int STAGE_BYTES = S * (A_BYTES + B_BYTES);
+    // tiles | full[STAGES] empty[STAGES] acc_full | tmem slot | inverse scales [64] | partial sums [2][128]
+    static constexpr size_t SMEM_BYTES = 1024 + size_t(STAGES) * STAGE_BYTES + (2 * STAGES + 2) * 8 + I_N * 8 + 2 * I_M * 8;
+};
+
+// power-of-two scale that brings |x| <= amax into [-1/2, 1/2]:  returns e with amax < 2^e, scale = 2^-(e+1)
+__device__ __forceinline__ int scale_exponent(double amax) {
+    if (!(amax > 0.0)) return 0;
+    int e;
+    frexp(amax, &e);            // amax = f 2^e, f in [1/2, 1)
+    return e;
+}
+
+// ---- FP64 -> S int8 slices -------------------------------------------------------------------------------
+// One CTA per row.  planes[j][row][col] (row pitch = cols bytes, plane pitch = plane_rows * cols bytes).
+// tri != 0: `src` is the mirrored inverse S (L^-1 below, L^-T above the diagonal blocks): entries right of the diagonal
+// are sliced as zero and the row's own maximum sets its scale, whose inverse is stored in inv_scale[row].
+// tri == 0: one scale for the whole matrix from *amax_ptr (K* <= outputscale).
+template <int S>
+__global__ void __launch_bounds__(256) slice_i8_kernel(const double* __restrict__ src, int cols, long ld_src,
+                                                       int8_t* __restrict__ planes, long plane_rows, int tri,
+                                                       double* __restrict__ inv_scale, const double* __restrict__ amax_ptr) {
+    const int row = blockIdx.x;
+    const double* x = src + (long)row * ld_src;
+    const int kmax = tri ? row + 1 : cols;          // entries [0, kmax) are live
+    __shared__ double red[8];
+    __shared__ int s_e;
+    if (tri) {
+        double a = 0.0;
+        for (int c = threadIdx.x; c < kmax; c += 256) a = fmax(a, fabs(x[c]));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a = fmax(a, __shfl_xor_sync(0xffffffffu, a, o));
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < 8; ++w) a = fmax(a, red[w]);
+            s_e = scale_exponent(a);
+            inv_scale[row] = ldexp(1.0, s_e + 1);
+        }
+        __syncthreads();
+    } else {
+        if (threadIdx.x == 0) s_e = scale_exponent(*amax_ptr);
+        __syncthreads();
+    }
+    const double scale = ldexp(1.0, -(s_e + 1) + I_BITS);       // first slice: rint(x * scale * 2^7)
+    const long pitch = plane_rows * (long)cols;
+    int8_t* out = planes + (long)row * cols;
+    const int cend = tri ? min(cols, round_up(row + 1, TILE)) : cols;     // the MMA tiles never read beyond the row's 128-block
+    for (int c0 = threadIdx.x * 8; c0 < cend; c0 += 256 * 8) {
+        if (c0 >= kmax) {
+#pragma unroll
+            for (int j = 0; j < S; ++j) *reinterpret_cast<uint2*>(out + j * pitch + c0) = make_uint2(0u, 0u);
+            continue;
+        }
+        double r[8];
+#pragma unroll
+        for (int u = 0; u < 8; u += 2) {
+            const double2 v = *reinterpret_cast<const double2*>(x + c0 + u);
+            r[u] = (c0 + u < kmax) ? v.x * scale : 0.0;
+            r[u + 1] = (c0 + u + 1 < kmax) ? v.y * scale : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < S; ++j) {
+            uint32_t lo = 0, hi = 0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const double q = rint(r[u]);
+                r[u] = (r[u] - q) * 128.0;                       // exact: |r - q| <= 1/2
+                const uint32_t b = (uint32_t)(__double2int_rn(q) & 0xff);
+                if (u < 4) lo |= b << (8 * u); else hi |= b << (8 * (u - 4));
+            }
+            *reinterpret_cast<uint2*>(out + j * pitch + c0) = make_uint2(lo, hi);
+        }
+    }
+}
+
+// ---- descriptors --------------------------------------------------------------------------------------------
+template <int BKB>
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr) {
+    // cute::UMMA::SmemDescriptor, K-major, rows of BKB bytes: 8-row groups 8*BKB bytes apart (SBO), LBO unused (=1),
+    // version 1, layout_type 2 = SWIZZLE_128B / 4 = SWIZZLE_64B
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)((8 * BKB) >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)(BKB == 128 ? 2 : 4) << 61);
+}
+// cute::UMMA::InstrDescriptor: D = S32 (2 at bit 4), A = B = signed int8 (1 at bits 7 and 10), both K-major
+__device__ __forceinline__ uint32_t i8_idesc(int n) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(I_M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// ---- the kernel ---------------------------------------------------------------------------------------------
+// grid.x = (Np/64) * (Mc/128) tiles; qpart[it][m] (ld = Mc) = sum over the 64 rows of tile `it` of V[m][i]^2.
+// tmA: K* planes as one [S*Mc][Np] byte matrix (box BKB x 128); tmB: L^-1 planes as [S*Np][Np] (box BKB x 64).
+template <int S, int BKB>
+__global__ void __launch_bounds__(I_THREADS, 1)
+trmm_sumsq_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int Np, int Mc,
+                     const double* __restrict__ inv_scale, const double* __restrict__ amax_ptr, double* __restrict__ qpart) {
+    using C = I8Cfg<S, BKB>;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + size_t(C::STAGES) * C::STAGE_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 1);
+    double* sinv = reinterpret_cast<double*>(bars + 2 * C::STAGES + 2);      // [64]
+    double* red = sinv + I_N;                                                 // [2][128]
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + C::STAGES), acc_full = smem_u32(bars + 2 * C::STAGES);
+    const uint32_t tile0 = smem_u32(base);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    // bands of I_BAND m tiles; inside a band the row tiles run heaviest (largest k extent) first
+    const int n_mb = Mc / I_M, n_it = Np / I_N;
+    int it, mb;
+    {
+        const int per_band = I_BAND * n_it;
+        const int band = (int)blockIdx.x / per_band;
+        const int left = n_mb - band * I_BAND;
+        const int width = left < I_BAND ? left : I_BAND;
+        const int rem = (int)blockIdx.x - band * per_band;
+        it = n_it - 1 - rem / width;
+        mb = band * I_BAND + rem % width;
+    }
+    const int kend = round_up((it + 1) * I_N, BKB);       // entries right of the diagonal are zero slices
+    const int nk = kend / BKB;
+
+    if (tid == 0) {
+        for (int s = 0; s < C::STAGES; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, 1);
+        }
+        mbar_init(acc_full, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "n"(I_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    if (tid < I_N) {
+        // V = (sum_g acc_g 2^{-7g}) * 2^{-14} / (scale_i * scale_K):  all powers of two, exact
+        const int ek = scale_exponent(*amax_ptr);
+        sinv[tid] = inv_scale[it * I_N + tid] * ldexp(1.0, ek + 1 - 2 * I_BITS);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = *tmem_slot;
+
+    if (warp >= 2) {    // zero the S accumulators: this warp's lane quadrant, alternate 32-column blocks per half
+        const int quad = warp & 3, half = (warp - 2) >> 2;
+        uint32_t z[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) z[j] = 0u;
+#pragma unroll
+        for (int g = 0; g < S; ++g)
+            tmem_st_32x32b_x32(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * I_N + half * 32), z);
+        tmem_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB);
+            for (int kt = 0; kt < nk; ++kt) {
+                const int s = kt % C::STAGES, round = kt / C::STAGES;
+                if (round > 0) mbar_wait(empty0 + 8 * s, (round - 1) & 1);
+                mbar_arrive_expect_tx(full0 + 8 * s, C::STAGE_BYTES);
+                const uint32_t dst = tile0 + s * C::STAGE_BYTES;
+                const int k0 = kt * BKB;
+#pragma unroll
+                for (int j = 0; j < S; ++j) tma_load_2d(dst + j * C::A_BYTES, &tmA, k0, j * Mc + mb * I_M, full0 + 8 * s);
+#pragma unroll
+                for (int j = 0; j < S; ++j)
+                    tma_load_2d(dst + S * C::A_BYTES + j * C::B_BYTES, &tmB, k0, j * Np + it * I_N, full0 + 8 * s);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            for (int kt = 0; kt < nk; ++kt) {
+                const int s = kt % C::STAGES, round = kt / C::STAGES;
+                mbar_wait(full0 + 8 * s, round & 1);
+                tc_fence_after();
+                const uint32_t st = tile0 + s * C::STAGE_BYTES;
+#pragma unroll
+                for (int kk = 0; kk < BKB / 32; ++kk) {
+                    const uint64_t adv = (uint64_t)((kk * 32) >> 4);     // 32 int8 along K inside the swizzle atom
+#pragma unroll
+                    for (int a = 0; a < S; ++a) {
+                        const uint64_t da = umma_desc_kmajor<BKB>(st + a * C::A_BYTES) + adv;
+                        const int ncols = (S - a) * I_N;                  // L^-1 slices 0 .. S-1-a -> diagonals a .. S-1
+#pragma unroll
+                        for (int c0 = 0; c0 < ncols; c0 += 256) {
+                            const int w = (ncols - c0) < 256 ? (ncols - c0) : 256;
+                            const uint64_t db = umma_desc_kmajor<BKB>(st + S * C::A_BYTES + (c0 / I_N) * C::B_BYTES) + adv;
+                            umma_i8(tmem_d + (uint32_t)(a * I_N + c0), da, db, i8_idesc(w), 1u);
+                        }
+                    }
+                }
+                umma_commit(empty0 + 8 * s);
+            }
+            umma_commit(acc_full);
+        }
+    } else {
+        // ===== epilogue warps 2..9: TMEM lane quadrant = warp % 4, columns [32 half, 32 half + 32) of every diagonal =====
+        const int quad = warp & 3, half = (warp - 2) >> 2;
+        const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        double t[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) t[j] = 0.0;
+#pragma unroll
+        for (int g = S - 1; g >= 0; --g) {          // smallest diagonal first
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(tmem_d + lane_base + (uint32_t)(g * I_N + half * 32), v);
+            tmem_wait_ld();
+            const double wg = 1.0 / (double)(1ull << (I_BITS * g));
+#pragma unroll
+            for (int j = 0; j < 32; ++j) t[j] = fma((double)(int)v[j], wg, t[j]);
+        }
+        double ssum = 0.0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const double x = t[j] * sinv[half * 32 + j];
+            ssum = fma(x, x, ssum);
+        }
+        red[half * I_M + quad * 32 + lane] = ssum;
+        named_bar_sync(1, 256);
+        if (half == 0) {
+            const int m = mb * I_M + quad * 32 + lane;
+            qpart[(long)it * Mc + m] = red[quad * 32 + lane] + red[I_M + quad * 32 + lane];
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "n"(I_TMEM_COLS) : "memory");
+    }
+}
+
+// ---- host -------------------------------------------------------------------------------------------------
+static int encode_u8_rowmajor(CUtensorMap* tm, const int8_t* base, uint64_t rows, uint64_t cols, uint32_t box_cols,
+                              uint32_t box_rows) {
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) return -900;
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {cols};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<int8_t*>(base), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -901 - (int)r;
+}
+
+static int i8_bkb() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("GPX_I8_BKB"); v = (e && atoi(e) == 128) ? 128 : 64; }   // GPX_I8_BKB=128: one-stage A/B edition
+    return v;
+}
+
+int i8_row_tiles(int Np) { return Np / I_N; }
+
+// planes <- slices of src [rows][cols] (ld_src); tri: mirrored inverse with per-row scales -> inv_scale[rows]
+int slice_i8_matrix(const double* src, int rows, int cols, long ld_src, int8_t* planes, long plane_rows, int nslices, int tri,
+                    double* inv_scale, const double* amax_ptr, cudaStream_t st) {
+    if (cols % 8 || nslices < 5 || nslices > I_SMAX) return -2;
+    if (rows <= 0) return 0;
+    if (nslices == 5) slice_i8_kernel<5><<<rows, 256, 0, st>>>(src, cols, ld_src, planes, plane_rows, tri, inv_scale, amax_ptr);
+    else slice_i8_kernel<6><<<rows, 256, 0, st>>>(src, cols, ld_src, planes, plane_rows, tri, inv_scale, amax_ptr);
+    GPX_CHECK_LAUNCH();
+    return 0;
+}
+
+template <int S, int BKB>
+static int launch_i8(const int8_t* Ls, const double* inv_scale, int Np, const int8_t* Kp, int Mc, const double* amax_ptr,
+                     double* qpart, cudaStream_t st) {
+    using C = I8Cfg<S, BKB>;
+    static bool attr[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!(dev >= 0 && dev < 64 && attr[dev])) {
+        cudaFuncSetAttribute(trmm_sumsq_i8_kernel<S, BKB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+        if (dev >= 0 && dev < 64) attr[dev] = true;
+    }
+    CUtensorMap tmA, tmB;
+    int rc;
+    if ((rc = encode_u8_rowmajor(&tmA, Kp, (uint64_t)S * Mc, Np, BKB, I_M))) return rc;
+    if ((rc = encode_u8_rowmajor(&tmB, Ls, (uint64_t)S * Np, Np, BKB, I_N))) return rc;
+    const int tiles = (Np / I_N) * (Mc / I_M);
+    trmm_sumsq_i8_kernel<S, BKB><<<tiles, I_THREADS, C::SMEM_BYTES, st>>>(tmA, tmB, Np, Mc, inv_scale, amax_ptr, qpart);
+    GPX_CHECK_LAUNCH();
+    return 0;
+}
+
+// qpart[it][m], it < Np/64.  Ls: S planes [Np][Np] of the sliced inverse, Kp: S planes [Mc][Np] of the sliced K* chunk.
+int trmm_sumsq_i8(const int8_t* Ls, const double* inv_scale, int Np, const int8_t* Kp, int Mc, int nslices,
+                  const double* amax_ptr, double* qpart, cudaStream_t st) {
+    if (Mc % I_M || Np % TILE) return -6;
+    if (Np > 32768) return -7;              // int32 accumulators: 64*64*K*S < 2^31
+    const bool wide = i8_bkb() == 128;
+    if (nslices == 5) return wide ? launch_i8<5, 128>(Ls, inv_scale, Np, Kp, Mc, amax_ptr, qpart, st)
+                                  : launch_i8<5, 64>(Ls, inv_scale, Np, Kp, Mc, amax_ptr, qpart, st);
+    if (nslices == 6) return wide ? launch_i8<6, 128>(Ls, inv_scale, Np, Kp, Mc, amax_ptr, qpart, st)
+                                  : launch_i8<6, 64>(Ls, inv_scale, Np, Kp, Mc, amax_ptr, qpart, st);
+    return -8;
+}
+
+}  // namespace gpx

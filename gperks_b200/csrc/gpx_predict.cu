@@ -434,6 +434,54 @@ int predict_meanvar_tf32(const double* Xs, long M, const double* X, int N, int D
     return 0;
 }
 
+// ---- sliced-integer mode (tcgen05 kind::i8, gpx_i8.cu) -------------------------------------------------------
+int slice_i8_matrix(const double* src, int rows, int cols, long ld_src, int8_t* planes, long plane_rows, int nslices, int tri,
+                    double* inv_scale, const double* amax_ptr, cudaStream_t st);
+int trmm_sumsq_i8(const int8_t* Ls, const double* inv_scale, int Np, const int8_t* Kp, int Mc, int nslices,
+                  const double* amax_ptr, double* qpart, cudaStream_t st);
+int i8_row_tiles(int Np);
+
+size_t predict_i8_workspace_bytes(int Np, int Mc, int nslices) {
+    const size_t nb = Np / TILE;
+    return (size_t)Mc * Np * 8 + (size_t)nslices * Mc * Np + (nb + i8_row_tiles(Np)) * (size_t)Mc * 8;
+}
+
+// As predict_meanvar; the variance contraction runs on the integer tensor cores from `nslices` 7-bit slices of L^-1
+// (Ls, inv_scale: gpx_slice_i8 of S, once per factorisation) and of each K* chunk (sliced here).  K* itself, the
+// posterior mean and the final reduction are the FP64 path's kernels, so the mean is bit-identical to predict_meanvar.
+int predict_meanvar_i8(const double* Xs, long M, const double* X, int N, int D, const double* theta, const double* xa,
+                       const double* xr, int kind, const int8_t* Ls, const double* inv_scale, int nslices, int Np,
+                       const double* alpha, const double* prior_mean, const int* feat_idx, int n_feat, int degree,
+                       const double* weights, const double* bias, double y_mu, double y_sigma, double min_var,
+                       double* out_mean, double* out_std, void* workspace, size_t workspace_bytes, int Mc, cudaStream_t st) {
+    if (Mc <= 0 || Mc % TILE != 0) return -25;
+    if (Np % TILE != 0 || Np < N) return -11;
+    if (D > MAXD || D < 1) return -5;
+    if (workspace_bytes < predict_i8_workspace_bytes(Np, Mc, nslices)) return -23;
+    const int nb = Np / TILE, nt = i8_row_tiles(Np);
+    double* Ks = reinterpret_cast<double*>(workspace);
+    int8_t* Kp = reinterpret_cast<int8_t*>(Ks + (size_t)Mc * Np);
+    double* mean_part = reinterpret_cast<double*>(Kp + (size_t)nslices * Mc * Np);
+    double* qpart = mean_part + (size_t)nb * Mc;
+    const double* amax = theta + D;          // K* <= outputscale for every kernel family here
+    for (long m0 = 0; m0 < M; m0 += Mc) {
+        const long mv = (M - m0 < Mc) ? (M - m0) : Mc;
+        const int mc = round_up((int)mv, TILE);
+        const double* xs = Xs + m0 * D;
+        int rc = kmat_cross(xs, mv, X, N, D, theta, xa, xr, kind, alpha, Ks, Np, mean_part, mc, st);
+        if (rc) return rc;
+        rc = slice_i8_matrix(Ks, mc, Np, Np, Kp, mc, nslices, 0, nullptr, amax, st);
+        if (rc) return rc;
+        rc = trmm_sumsq_i8(Ls, inv_scale, Np, Kp, mc, nslices, amax, qpart, st);
+        if (rc) return rc;
+        predict_finalize_kernel<<<(int)((mv + 255) / 256), 256, 0, st>>>(
+            xs, mv, D, xa, xr, theta, mean_part, qpart, nb, mc, prior_mean ? prior_mean + m0 : nullptr, feat_idx,
+            n_feat, degree, weights, bias, y_mu, y_sigma, min_var, out_mean + m0, out_std + m0, nt);
+    }
+    GPX_CHECK_LAUNCH();
+    return 0;
+}
+
 static void set_pred_attrs() {
     int dev = 0;
     cudaGetDevice(&dev);

@@ -87,6 +87,9 @@ class ExactGPEngine:
         self.has_split = False
         self.S_hi: Optional[torch.Tensor] = None      # TF32 mode: (hi, lo) float split of L^-1
         self.S_lo: Optional[torch.Tensor] = None
+        self.i8_slices = 0                            # sliced-integer mode: number of int8 slices of L^-1 held (0 = none)
+        self.S_i8: Optional[torch.Tensor] = None      # [slices, Np, Np] int8 planes of L^-1
+        self.S_i8_inv_scale: Optional[torch.Tensor] = None   # [Np] inverse power-of-two row scales
 
     # ------------------------------------------------------------------------------------------
     def _launch(self, name: str, *args) -> None:
@@ -133,6 +136,7 @@ class ExactGPEngine:
                          p(self.out), st)
         self.has_kinv = False
         self.has_split = False
+        self.i8_slices = 0
         self.factor_key = key
         self.factored = True
         self.n_factorizations += 1
@@ -202,11 +206,16 @@ class ExactGPEngine:
         if M == 0:
             return out_mean, out_std
         Mc = int(chunk) if chunk else self.pick_chunk(M)
-        if precision not in ("fp64", "tf32x3", "tf32x3_fast"):
-            raise ValueError("precision must be 'fp64', 'tf32x3' or 'tf32x3_fast'")
+        if precision not in ("fp64", "tf32x3", "tf32x3_fast", "int8x5", "int8x6"):
+            raise ValueError("precision must be 'fp64', 'int8x5', 'int8x6', 'tf32x3' or 'tf32x3_fast'")
+        # int8x5 / int8x6: the FP64 contraction from 5 / 6 signed 7-bit slices per operand on the integer tensor cores
+        # (exact int32 accumulation): std within ~5e-8 / 5e-9 of fp64, mean bit-identical (gpx_i8.cu)
+        i8 = int(precision[-1]) if precision.startswith("int8") else 0
+        if i8 and self.Np > 32768:
+            raise ValueError("the sliced-integer mode holds its sums in int32: N <= 32768")
         # tf32x3: K* evaluated in FP64 then split (posterior mean bit-identical to fp64; variance on tcgen05);
         # tf32x3_fast: K* evaluated in FP32 as well (mean moves by ~1e-4 of its scale for noise-like targets)
-        tf32 = precision != "fp64"
+        tf32 = precision.startswith("tf32")
         kchunk = abs(int(tf32_kchunk)) or 32
         if precision == "tf32x3":
             kchunk = -kchunk
@@ -214,6 +223,9 @@ class ExactGPEngine:
             self._ensure_split()
             Mc = (Mc + 255) // 256 * 256         # the tcgen05 kernel works on pairs of 128-point tiles
             ws_bytes = int(self.lib.gpx_predict_tf32_workspace_bytes(self.Np, Mc))
+        elif i8:
+            self._ensure_i8(i8)
+            ws_bytes = int(self.lib.gpx_predict_i8_workspace_bytes(self.Np, Mc, i8))
         else:
             ws_bytes = int(self.lib.gpx_predict_workspace_bytes(self.Np, Mc))
         ws = self._workspace(ws_bytes)
@@ -232,6 +244,11 @@ class ExactGPEngine:
                              self.kind, p(self.S_hi), p(self.S_lo), self.Np, p(self.alpha), p(prior_mean), p(feat),
                              n_feat, degree, p(wts), p(bias), float(y_mu), float(y_sigma), float(min_var),
                              p(out_mean), p(out_std), p(ws), ws_bytes, Mc, kchunk, nv.stream_ptr())
+            elif i8:
+                self._launch("gpx_predict_meanvar_i8", p(Xs), M, p(self.X), self.N, self.D, p(theta), p(xa), p(xr),
+                             self.kind, p(self.S_i8), p(self.S_i8_inv_scale), i8, self.Np, p(self.alpha), p(prior_mean),
+                             p(feat), n_feat, degree, p(wts), p(bias), float(y_mu), float(y_sigma), float(min_var),
+                             p(out_mean), p(out_std), p(ws), ws_bytes, Mc, nv.stream_ptr())
             else:
                 self._launch("gpx_predict_meanvar", p(Xs), M, p(self.X), self.N, self.D, p(theta), p(xa), p(xr),
                              self.kind, p(self.S), self.Np, p(self.alpha), p(prior_mean), p(feat), n_feat, degree,
@@ -250,6 +267,18 @@ class ExactGPEngine:
             self._launch("gpx_split_tf32", nv.ptr(self.S), self.Np * self.Np, nv.ptr(self.S_hi), nv.ptr(self.S_lo),
                          self.Np, nv.stream_ptr())
         self.has_split = True
+
+    def _ensure_i8(self, slices: int) -> None:
+        """int8 slices and row scales of L^-1 for the sliced-integer variance path; refreshed after every factorisation."""
+        if self.i8_slices == slices:
+            return
+        if self.S_i8 is None or self.S_i8.shape[0] != slices:
+            self.S_i8 = torch.empty(slices, self.Np, self.Np, dtype=torch.int8, device=self.device)
+            self.S_i8_inv_scale = torch.empty(self.Np, dtype=F64, device=self.device)
+        with torch.cuda.device(self.device):
+            self._launch("gpx_slice_i8", nv.ptr(self.S), self.Np, self.Np, self.Np, nv.ptr(self.S_i8), self.Np, slices, 1,
+                         nv.ptr(self.S_i8_inv_scale), None, nv.stream_ptr())
+        self.i8_slices = slices
 
     # ------------------------------------------------------------------------------------------
     def cross_kernel(self, Xs: torch.Tensor, xa=None, xr=None) -> torch.Tensor:

@@ -124,6 +124,33 @@ int gpx_predict_meanvar_tf32(const double* Xs, long M, const double* X, int N, i
                              double min_var, double* out_mean, double* out_std, void* workspace,
                              size_t workspace_bytes, int Mc, int kchunk, void* stream);
 
+/* ---- sliced-integer mode of the predictive variance: FP64-grade results from the integer tensor cores -------------
+ * (tcgen05 kind::i8, exact int32 accumulation in TMEM; gperks_b200/csrc/gpx_i8.cu).  Operands are scaled by powers of
+ * two and cut into nslices (5 or 6) signed 7-bit slices; the products of slices a+b < nslices are integer GEMMs, combined
+ * in FP64.  std agrees with gpx_predict_meanvar to ~5e-8 relative with 5 slices (5e-7 at noise 1e-4) and ~5e-9 with 6, i.e.
+ * inside the 1e-6 bar of the FP64 mode; the posterior mean is bit-identical (K* and the mean stay on the FP64 kernels).
+ * gpx_slice_i8: planes[j][row][col] (int8, row pitch = cols, plane pitch = plane_rows*cols) <- slices of src[rows][cols]
+ *   (leading dimension ld_src).  tri != 0: src is the mirrored inverse S of gpx_trtri; entries right of the diagonal are
+ *   sliced as zero (columns beyond the row's 128-block are left untouched: never read) and every row gets its own scale,
+ *   inv_scale[row] = 1/scale.  tri == 0: one scale for the whole matrix from the device scalar *amax_ptr >= max|src|
+ *   (K* <= outputscale).  Run once per factorisation on S and once per chunk on K*.
+ * gpx_trmm_sumsq_i8: qpart[it][m] = sum over the 64 rows of tile `it` of (K* L^-T)[m][i]^2, it < gpx_i8_row_tiles(Np);
+ *   Mc multiple of 128, Np <= 32768 (int32 accumulators).
+ * gpx_predict_meanvar_i8: as gpx_predict_meanvar with the variance contraction on the integer tensor cores.
+ * replaces: the same call sites as gpx_predict_meanvar (GPErks/train/emulator.py:348-363). */
+int gpx_slice_i8(const double* src, int rows, int cols, long ld_src, signed char* planes, long plane_rows, int nslices,
+                 int tri, double* inv_scale, const double* amax_ptr, void* stream);
+int gpx_i8_row_tiles(int Np);
+int gpx_trmm_sumsq_i8(const signed char* Ls, const double* inv_scale, int Np, const signed char* Kp, int Mc, int nslices,
+                      const double* amax_ptr, double* qpart, void* stream);
+size_t gpx_predict_i8_workspace_bytes(int Np, int Mc, int nslices);
+int gpx_predict_meanvar_i8(const double* Xs, long M, const double* X, int N, int D, const double* theta, const double* xa,
+                           const double* xr, int kind, const signed char* Ls, const double* inv_scale, int nslices, int Np,
+                           const double* alpha, const double* prior_mean, const int* feat_idx, int n_feat, int degree,
+                           const double* weights, const double* bias, double y_mu, double y_sigma, double min_var,
+                           double* out_mean, double* out_std, void* workspace, size_t workspace_bytes, int Mc,
+                           void* stream);
+
 /* History-matching epilogue over E emulators: I[m] = maxno-th largest_e sqrt((mean[e][m]-z[e])^2/(std[e][m]^2+v[e])),
  * PV[m] = maxno-th largest_e std[e][m]^2/v[e]; inputs emulator-major [E][M]; 1 <= maxno <= min(E, 8).
  * replaces: the per-point loop with two np.sort in Wave.compute_impl, GPErks/perks/history_matching.py:57-62. */
