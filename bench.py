@@ -224,6 +224,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mll-evals", type=int, default=3)
     ap.add_argument("--no-tf32", action="store_true", help="skip the TF32-mode (tcgen05) arm")
+    ap.add_argument("--no-int8", action="store_true", help="skip the sliced-integer (tcgen05 kind::i8) arm")
     ap.add_argument("--ncu-traffic", type=float, default=None,
                     help="dram bytes per launch of the dominant kernel from an ncu --set full capture (profiles/)")
     args = ap.parse_args()
@@ -426,6 +427,89 @@ def main():
                              "frac": raw / tf32_peak, "useful_tflops": raw / 3.0, "kernel_ms": tk,
                              "peak_source": "cuBLAS TF32 GEMM 8192^3 (torch.matmul, allow_tf32) measured in this run"}}
 
+    # ---- sliced-integer mode (tcgen05 kind::i8, exact int32 accumulation; std inside the FP64 bar of 1e-6), beside the headline
+    int8 = None
+    if not args.no_int8:
+        s64 = out_std.clone()
+        imean = torch.empty_like(out_mean)
+        istd = torch.empty_like(out_std)
+        int8 = {"tolerance": 1e-6, "note": "FP64 contraction from S signed 7-bit slices per operand on the integer tensor cores; "
+                                           "K* and the posterior mean stay on the FP64 kernels (mean bit-identical)"}
+        try:
+            ai = torch.randint(-64, 64, (8192, 8192), device=dev, dtype=torch.int8)
+            bi = torch.randint(-64, 64, (8192, 8192), device=dev, dtype=torch.int8)
+            tg = []
+            for i in range(4):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                torch._int_mm(ai, bi)
+                b.record()
+                torch.cuda.synchronize()
+                if i > 0:
+                    tg.append(a.elapsed_time(b))
+            i8_peak = 2 * 8192 ** 3 / (min(tg) / 1e3) / 1e12
+            del ai, bi
+        except Exception as exc:          # noqa: BLE001 -- the probe is optional; the mode itself never falls back
+            i8_peak = None
+            int8["peak_probe_error"] = repr(exc)[:200]
+        for S_ in (5, 6):
+            prec = f"int8x{S_}"
+
+            def i8_step():
+                eng.predict(x_dev, xa=xa, xr=xr, poly=poly, y_mu=float(scy.mu), y_sigma=float(scy.sigma),
+                            out_mean=imean, out_std=istd, chunk=Mc, precision=prec)
+            for _ in range(3):
+                i8_step()
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(args.steps):
+                i8_step()
+            b.record()
+            barrier()
+            t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            rel_s = ((istd - s64).abs() / s64)
+            entry = {"value": world * M * args.steps / (ms / 1e3), "unit": "points/s", "ms_per_step": ms / args.steps,
+                     "max_rel_err_std_vs_fp64": float(rel_s.max()), "median_rel_err_std_vs_fp64": float(rel_s.median()),
+                     "mean_bit_identical_to_fp64": bool(torch.equal(imean, out_mean))}
+            # end to end through GPEmulator.predict(numpy)
+            em.predict(Xs[: min(M, 200_000)], precision=prec)
+            barrier()
+            t0 = time.perf_counter()
+            ym8, ys8 = em.predict(Xs, precision=prec)
+            barrier()
+            t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            entry["e2e"] = {"value": world * M / float(t.item()), "unit": "points/s", "api": f"GPEmulator.predict(numpy, precision='{prec}')",
+                            "max_rel_err_std_vs_fp64_e2e": float(np.max(np.abs(ys8 - y_std) / y_std))}
+            # the integer tensor-core kernel alone on the slices left in the workspace by the last chunk
+            ws8 = eng._workspace(int(lib.gpx_predict_i8_workspace_bytes(eng.Np, Mc, S_)))
+            Kp_ptr = ws8.data_ptr() + Mc * eng.Np * 8
+            nt8 = int(lib.gpx_i8_row_tiles(eng.Np))
+            qp8 = torch.empty(nt8 * Mc, dtype=torch.float64, device=dev)
+            tk = []
+            for i in range(4):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                nv.check(lib.gpx_trmm_sumsq_i8(nv.ptr(eng.S_i8), nv.ptr(eng.S_i8_inv_scale), eng.Np, Kp_ptr, Mc, S_,
+                                               nv.ptr(eng.theta) + 8 * DIM, nv.ptr(qp8), st), "i8 trmm")
+                b.record()
+                torch.cuda.synchronize()
+                if i > 0:
+                    tk.append(a.elapsed_time(b))
+            tk = sum(tk) / len(tk)
+            raw = (S_ * (S_ + 1) / 2) * float(eng.N) ** 2 * Mc / (tk / 1e3) / 1e12
+            entry["roofline"] = {"kernel": f"trmm_sumsq_i8_kernel<{S_}> (tcgen05.mma kind::i8, {S_ * (S_ + 1) // 2} slice products, int32 TMEM accumulators)",
+                                 "bound": "tensor", "achieved": raw, "peak": i8_peak, "unit": "TOP/s (int8, raw)",
+                                 "frac": (raw / i8_peak) if i8_peak else None, "fp64_equivalent_tflops": float(eng.N) ** 2 * Mc / (tk / 1e3) / 1e12,
+                                 "kernel_ms": tk, "kernel_share_of_step": tk * (M / Mc) / (ms / args.steps),
+                                 "peak_source": "cuBLASLt int8 GEMM 8192^3 (torch._int_mm) measured in this run"}
+            int8[prec] = entry
+
     line = {
         "metric": "predict points/sec (mean+var) N=8192 D=8", "value": value, "unit": "points/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
@@ -445,6 +529,7 @@ def main():
                       "n_train": eng.N, "what": "K_hat build + Cholesky + L^-1 + alpha + -mll + K_hat^-1 + gradient reduce"}
                      if mll_ms else None),
         "tf32_mode": tf32,
+        "int8_mode": int8,
         "clocks": clocks.summary(),
     }
     if rank == 0 and not args.no_cpu_baseline and world == 1:

@@ -514,6 +514,103 @@ def test_emulator_predict_tf32_precision(dev, goldens):
     np.testing.assert_allclose(s32f, s64, rtol=1e-3)
 
 
+# ----------------------------------------------------------------------------------------------------
+# Sliced-integer mode (tcgen05 kind::i8, exact int32 accumulation): inside the FP64 bar, rel 1e-6 on std
+# ----------------------------------------------------------------------------------------------------
+def test_i8_kernel_exact_on_integer_slices(dev):
+    """The integer contraction is exact: qpart must equal, bit for bit up to the FP64 combination of the diagonals, the same
+    slices multiplied in float64 -- pins the TMA swizzle, the stacked-slice UMMA descriptors and the TMEM epilogue."""
+    lib = nv.lib()
+    for S, Np, Mc in [(5, 128, 128), (5, 256, 256), (6, 384, 128), (5, 1024, 384), (6, 1152, 256)]:
+        g = torch.Generator(device="cpu").manual_seed(Np + S)
+        Ls = torch.randint(-64, 65, (S, Np, Np), generator=g, dtype=torch.int64).to(torch.int8)
+        Ls = torch.tril(Ls).contiguous().to(dev)
+        Kp = torch.randint(-64, 65, (S, Mc, Np), generator=g, dtype=torch.int64).to(torch.int8).to(dev)
+        e = torch.randint(-3, 4, (Np,), generator=g)
+        inv_scale = torch.ldexp(torch.ones(Np, dtype=F64), e.to(torch.int32)).to(dev)
+        amax = torch.tensor([1.3], dtype=F64, device=dev)           # frexp exponent 1 -> 1/scale_K = 4
+        nt = lib.gpx_i8_row_tiles(Np)
+        q = torch.full((nt, Mc), -1.0, dtype=F64, device=dev)
+        nv.check(lib.gpx_trmm_sumsq_i8(nv.ptr(Ls), nv.ptr(inv_scale), Np, nv.ptr(Kp), Mc, S, nv.ptr(amax), nv.ptr(q),
+                                       nv.stream_ptr()), "i8")
+        V = torch.zeros(Np, Mc, dtype=F64, device=dev)
+        for a in range(S):
+            for b in range(S - a):
+                V += (Ls[b].double() @ Kp[a].double().T) * 2.0 ** (-7 * (a + b + 2))
+        V = V * inv_scale.view(-1, 1) * 4.0
+        ref = (V * V).view(nt, 64, Mc).sum(1)
+        np.testing.assert_allclose(q.cpu().numpy(), ref.cpu().numpy(), rtol=1e-13, atol=0)
+
+
+def test_i8_slices_reconstruct_the_operand(dev):
+    lib = nv.lib()
+    g = torch.Generator(device="cpu").manual_seed(3)
+    rows, cols = 300, 384
+    A = (torch.randn(rows, cols, generator=g, dtype=F64) * torch.logspace(-3, 1, rows, dtype=F64).view(-1, 1)).to(dev)
+    for S in (5, 6):
+        w = torch.tensor([2.0 ** (-7 * (j + 1)) for j in range(S)], dtype=F64, device=dev).view(S, 1, 1)
+        # one scale for the matrix
+        amax = A.abs().max().reshape(1).contiguous()
+        planes = torch.empty(S, rows, cols, dtype=torch.int8, device=dev)
+        nv.check(lib.gpx_slice_i8(nv.ptr(A), rows, cols, cols, nv.ptr(planes), rows, S, 0, None, nv.ptr(amax), nv.stream_ptr()), "slice")
+        assert int(planes.abs().max()) <= 64
+        import math
+        inv = 2.0 ** (math.frexp(float(amax))[1] + 1)
+        rec = (planes.double() * w).sum(0) * inv
+        assert float((rec - A).abs().max()) <= inv * 2.0 ** (-7 * S - 1) * (1 + 1e-12)
+        # per-row scales, entries right of the diagonal treated as zero (square input)
+        B = A[:, :rows].contiguous() if rows <= cols else A
+        Bp = torch.zeros(384, 384, dtype=F64, device=dev)
+        Bp[:rows, :rows] = B
+        planes = torch.zeros(S, 384, 384, dtype=torch.int8, device=dev)
+        inv_scale = torch.empty(384, dtype=F64, device=dev)
+        nv.check(lib.gpx_slice_i8(nv.ptr(Bp), 384, 384, 384, nv.ptr(planes), 384, S, 1, nv.ptr(inv_scale), None, nv.stream_ptr()), "slice")
+        assert int(planes.abs().max()) <= 64
+        rec = (planes.double() * w).sum(0) * inv_scale.view(-1, 1)
+        low = torch.tril(Bp)
+        assert float(torch.triu(rec, 1).abs().max()) == 0.0
+        err = (rec - low).abs().max(dim=1).values
+        assert bool((err <= inv_scale * 2.0 ** (-7 * S - 1) * (1 + 1e-12)).all())
+        rowmax = low.abs().max(dim=1).values
+        ok = rowmax > 0
+        assert bool((rowmax[ok] * 2 <= inv_scale[ok]).all()) and bool((inv_scale[ok] <= rowmax[ok] * 4).all())
+
+
+@pytest.mark.parametrize("N,D,M,kind,nz", [(20, 2, 25, O.KIND_RBF, 1e-2), (300, 3, 1000, O.KIND_RBF, 1e-2),
+                                           (1000, 5, 777, O.KIND_MATERN32, 1e-2), (200, 8, 500, O.KIND_MATERN12, 1e-4),
+                                           (2048, 6, 8192, O.KIND_MATERN52, 1e-2), (2048, 6, 4096, O.KIND_MATERN52, 1e-4)])
+def test_int8_mode_within_fp64_tolerance(dev, N, D, M, kind, nz):
+    X, y, Xs, ls, s, w, b = _problem(N, D, M, seed=N)
+    eng = _engine(dev, X, y, kind, ls, s, nz, w, b)
+    pm = (Xs @ w + b).to(dev)
+    m64, s64 = eng.predict(Xs.to(dev), prior_mean=pm)
+    for prec, tol in (("int8x5", 1e-6), ("int8x6", 1e-7)):
+        mi, si = eng.predict(Xs.to(dev), prior_mean=pm, precision=prec)
+        assert torch.equal(m64, mi)               # K* and the mean stay on the FP64 kernels
+        rel = float(((si - s64).abs() / s64).max())
+        assert rel < tol, (prec, rel)
+        mi2, si2 = eng.predict(Xs.to(dev), prior_mean=pm, precision=prec, chunk=256)
+        assert torch.equal(si, si2)               # chunking never changes a bit
+    if N <= 1000:
+        _, vref = O.predict(X, y, kind, ls, s, nz, X @ w + b, Xs, Xs @ w + b)
+        np.testing.assert_allclose(si.cpu().numpy(), vref.sqrt().numpy(), rtol=1e-6)     # the FP64 bar of north_star
+    # refactorising refreshes the slices
+    eng.factorize(eng.theta_in.clone() * 1.0, eng.r[:N].clone() * 2.0)
+    _, s5 = eng.predict(Xs.to(dev), prior_mean=pm, precision="int8x5")
+    assert float(((s5 - s64).abs() / s64).max()) < 1e-6
+
+
+def test_emulator_predict_int8_precision(dev, goldens):
+    g = goldens["example_2"]
+    em, ds = _emulator_from_golden(g, "example_2")
+    rng = np.random.default_rng(1)
+    Xq = rng.random((3000, 2))
+    m64, s64 = em.predict(Xq)
+    m8, s8 = em.predict(Xq, precision="int8x5")
+    assert np.array_equal(m64, m8)
+    np.testing.assert_allclose(s8, s64, rtol=1e-6)
+
+
 def test_validation_loss_and_covariance_kernels_match_oracle(dev):
     """Eval-mode mll(model(X_val), y_val) = posterior-predictive log density / M_val (GPEmulator._val_step), the dense
     predictive covariance and its Cholesky all run on the CUDA tile engine: compare with the oracle."""
