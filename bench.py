@@ -35,6 +35,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 N_TRAIN, DIM = 8192, 8
+NCU_TRAFFIC_I8_BYTES = {"int8x6": 11.952e9}      # dram read+write per launch of trmm_sumsq_i8_kernel<6>, profiles/r01_ncu_i8.txt (N=8192, chunk 32768)
 NCU_TRAFFIC_BYTES = 13.546e9   # dram read+write per launch, profiles/r01_ncu_trmm_tma.txt (N=8192, chunk 32768)
 KIND_NAME = "matern52"
 NOISE = 1e-2
@@ -225,6 +226,8 @@ def main():
     ap.add_argument("--mll-evals", type=int, default=3)
     ap.add_argument("--no-tf32", action="store_true", help="skip the TF32-mode (tcgen05) arm")
     ap.add_argument("--no-int8", action="store_true", help="skip the sliced-integer (tcgen05 kind::i8) arm")
+    ap.add_argument("--precision", default="auto",
+                    help="precision of the headline arms: auto (GPEmulator.predict's default: int8x6 for this workload), fp64, int8x5, int8x6")
     ap.add_argument("--ncu-traffic", type=float, default=None,
                     help="dram bytes per launch of the dominant kernel from an ncu --set full capture (profiles/)")
     args = ap.parse_args()
@@ -275,12 +278,13 @@ def main():
     out_std = torch.empty(M, dtype=torch.float64, device=dev)
     Mc = eng.pick_chunk(M)
     n_chunks = math.ceil(M / Mc)
+    PREC = em.resolve_precision(args.precision)        # what GPEmulator.predict(X) runs by default for this emulator
     gathered = [torch.empty(2, M, dtype=torch.float64, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
     local_out = torch.empty(2, M, dtype=torch.float64, device=dev)
 
     def step():
         eng.predict(x_dev, xa=xa, xr=xr, poly=poly, y_mu=float(scy.mu), y_sigma=float(scy.sigma),
-                    out_mean=out_mean, out_std=out_std, chunk=Mc)
+                    out_mean=out_mean, out_std=out_std, chunk=Mc, precision=PREC)
         if world > 1:       # the path's only exchange: gather the 16 B/point results on rank 0
             local_out[0].copy_(out_mean)
             local_out[1].copy_(out_std)
@@ -308,7 +312,30 @@ def main():
     elapsed_ms = float(t.item())
     value = world * M * args.steps / (elapsed_ms / 1e3)
 
-    # ---- dominant kernel alone (roofline): the variance TRMM on one full chunk, CUDA events on its stream
+    # ---- the FP64 DMMA arm (precision="fp64"): the reference point every other mode's error is measured against
+    f_mean = torch.empty(M, dtype=torch.float64, device=dev)
+    f_std = torch.empty(M, dtype=torch.float64, device=dev)
+
+    def f64_step():
+        eng.predict(x_dev, xa=xa, xr=xr, poly=poly, y_mu=float(scy.mu), y_sigma=float(scy.sigma),
+                    out_mean=f_mean, out_std=f_std, chunk=Mc, precision="fp64")
+    f64_step()
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.steps):
+        f64_step()
+    b.record()
+    barrier()
+    t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    f64_ms = float(t.item())
+    f64_value = world * M * args.steps / (f64_ms / 1e3)
+    headline_err_std = float(((out_std - f_std).abs() / f_std).max())
+    headline_err_mean = float((out_mean - f_mean).abs().max() / f_mean.abs().max())
+
+    # ---- the FP64 variance TRMM alone on one full chunk, CUDA events on its stream
     ws = eng._workspace(int(lib.gpx_predict_workspace_bytes(eng.Np, Mc)))
     Ks_ptr = ws.data_ptr()
     qpart = torch.empty(eng.nb * Mc, dtype=torch.float64, device=dev)
@@ -335,15 +362,15 @@ def main():
         torch.cuda.synchronize()
         peak_ms.append(a.elapsed_time(b))
     peak = peak_flops / (min(peak_ms) / 1e3) / 1e12
-    kernel_share = k_ms * (M / Mc) / (elapsed_ms / args.steps)      # TRMM work is linear in the points
+    kernel_share = k_ms * (M / Mc) / (f64_ms / args.steps)      # TRMM work is linear in the points
 
     # ---- end-to-end arm: GPEmulator.predict on host numpy buffers (pinned H2D + D2H inside)
     e2e_steps = max(1, min(args.steps, 2))
-    em.predict(Xs[: min(M, 200_000)])       # warm the pinned allocator
+    em.predict(Xs[: min(M, 200_000)], precision=args.precision)       # warm the pinned allocator
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        y_mean, y_std = em.predict(Xs)
+        y_mean, y_std = em.predict(Xs, precision=args.precision)
     barrier()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -359,7 +386,7 @@ def main():
     # ---- TF32 mode (tcgen05 3xTF32 variance contraction), reported beside the FP64 headline
     tf32 = None
     if not args.no_tf32:
-        s64 = out_std.clone()
+        s64 = f_std
         tmean = torch.empty_like(out_mean)
         tstd = torch.empty_like(out_std)
 
@@ -381,7 +408,7 @@ def main():
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
             rel_s = ((tstd - s64).abs() / s64)
-            rel_m = (tmean - out_mean).abs().max() / out_mean.abs().max()
+            rel_m = (tmean - f_mean).abs().max() / f_mean.abs().max()
             return {"value": world * M * args.steps / (ms / 1e3), "unit": "points/s", "ms_per_step": ms / args.steps,
                     "max_rel_err_std_vs_fp64": float(rel_s.max()), "median_rel_err_std_vs_fp64": float(rel_s.median()),
                     "max_err_mean_vs_fp64_rel_to_scale": float(rel_m)}
@@ -429,10 +456,11 @@ def main():
 
     # ---- sliced-integer mode (tcgen05 kind::i8, exact int32 accumulation; std inside the FP64 bar of 1e-6), beside the headline
     int8 = None
-    if not args.no_int8:
-        s64 = out_std.clone()
+    if not args.no_int8 or PREC.startswith("int8"):
+        s64 = f_std
         imean = torch.empty_like(out_mean)
         istd = torch.empty_like(out_std)
+        f_std_host = f_std.cpu().numpy()
         int8 = {"tolerance": 1e-6, "note": "FP64 contraction from S signed 7-bit slices per operand on the integer tensor cores; "
                                            "K* and the posterior mean stay on the FP64 kernels (mean bit-identical)"}
         try:
@@ -474,7 +502,7 @@ def main():
             rel_s = ((istd - s64).abs() / s64)
             entry = {"value": world * M * args.steps / (ms / 1e3), "unit": "points/s", "ms_per_step": ms / args.steps,
                      "max_rel_err_std_vs_fp64": float(rel_s.max()), "median_rel_err_std_vs_fp64": float(rel_s.median()),
-                     "mean_bit_identical_to_fp64": bool(torch.equal(imean, out_mean))}
+                     "mean_bit_identical_to_fp64": bool(torch.equal(imean, f_mean))}
             # end to end through GPEmulator.predict(numpy)
             em.predict(Xs[: min(M, 200_000)], precision=prec)
             barrier()
@@ -485,7 +513,7 @@ def main():
             if world > 1:
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             entry["e2e"] = {"value": world * M / float(t.item()), "unit": "points/s", "api": f"GPEmulator.predict(numpy, precision='{prec}')",
-                            "max_rel_err_std_vs_fp64_e2e": float(np.max(np.abs(ys8 - y_std) / y_std))}
+                            "max_rel_err_std_vs_fp64_e2e": float(np.max(np.abs(ys8 - f_std_host) / f_std_host))}
             # the integer tensor-core kernel alone on the slices left in the workspace by the last chunk
             ws8 = eng._workspace(int(lib.gpx_predict_i8_workspace_bytes(eng.Np, Mc, S_)))
             Kp_ptr = ws8.data_ptr() + Mc * eng.Np * 8
@@ -510,21 +538,43 @@ def main():
                                  "peak_source": "cuBLASLt int8 GEMM 8192^3 (torch._int_mm) measured in this run"}
             int8[prec] = entry
 
-    line = {
-        "metric": "predict points/sec (mean+var) N=8192 D=8", "value": value, "unit": "points/s", "n_gpus": world,
-        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "configs[1]: Matern-5/2 ARD emulator, N_train=8192 D=8, predict mean+noisy std",
-                   "points_per_gpu_per_step": M, "chunk_points": Mc, "parallelism": f"x*-shard x{world}, L^-1/alpha replicated",
-                   "l2": "working set per chunk (K* 2 GiB + L^-1 0.5 GB) exceeds the 126 MB L2; no flush needed"},
-        "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": int(M * DIM * 8), "d2h_bytes_per_step": int(M * 16),
-                "steps": e2e_steps, "api": "GPEmulator.predict(numpy)", "max_abs_diff_vs_device_arm": parity},
-        "gpu_launches": int(args.steps * n_chunks * 3),
-        "roofline": {"kernel": "trmm_sumsq_tma_kernel (variance contraction L^-1 K*^T: TMA + mbarrier ring, FP64 DMMA)", "bound": "tensor",
+    fp64_roofline = {"kernel": "trmm_sumsq_tma_kernel (variance contraction L^-1 K*^T: TMA + mbarrier ring, FP64 DMMA)", "bound": "tensor",
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": TRAFFIC,
                      "peak_source": "gpx_peak_dmma probe measured in this run (FP64 DMMA.8x8x4 issue peak; MEASURED_PEAKS.json "
                                     "has no FP64 figure; cuBLAS DGEMM 8192^3 measured 35.5 TF/s on this pool, see profiles/)",
-                     "algorithmic_flops_per_launch": flops_per_launch, "kernel_ms": k_ms, "kernel_share_of_step": kernel_share},
+                     "algorithmic_flops_per_launch": flops_per_launch, "kernel_ms": k_ms, "kernel_share_of_step": kernel_share}
+    if PREC.startswith("int8") and int8 is not None and PREC in int8:
+        # headline = the sliced-integer path: its dominant kernel is the integer tensor-core contraction.  `achieved` counts the
+        # int8 operations the kernel actually issues (S(S+1)/2 slice products of the algorithmic N^2/2 multiply-adds per
+        # point); the FP64-equivalent rate (algorithmic N^2 FLOP per point / time) is given beside it.
+        roofline = dict(int8[PREC]["roofline"])
+        roofline["traffic"] = args.ncu_traffic if args.ncu_traffic is not None else (
+            NCU_TRAFFIC_I8_BYTES.get(PREC) if Mc == 32768 and eng.N == 8192 else None)
+        roofline["algorithmic_flops_per_launch"] = flops_per_launch
+        roofline["nominal_int8_peak_tops"] = 4500.0
+        roofline["kernel_share_of_step"] = roofline["kernel_ms"] * (M / Mc) / (elapsed_ms / args.steps)
+        dtype = f"i8 slices ({PREC[-1]} x 7 bit, exact i32 accumulation on tcgen05, FP64 combination): f64-equivalent, see accuracy"
+        launches_per_chunk = 4       # kmat_cross, slice_i8, trmm_sumsq_i8, predict_finalize
+    else:
+        roofline, dtype, launches_per_chunk = fp64_roofline, "f64", 3
+    line = {
+        "metric": "predict points/sec (mean+var) N=8192 D=8", "value": value, "unit": "points/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+        "config": {"workload": "configs[1]: Matern-5/2 ARD emulator, N_train=8192 D=8, predict mean+noisy std",
+                   "points_per_gpu_per_step": M, "chunk_points": Mc, "parallelism": f"x*-shard x{world}, L^-1/alpha replicated",
+                   "precision": PREC, "precision_requested": args.precision,
+                   "l2": "working set per chunk (K* 2 GiB + its slices + L^-1) exceeds the 126 MB L2; no flush needed"},
+        "accuracy": {"max_rel_err_std_vs_fp64_dmma_path": headline_err_std, "max_err_mean_vs_fp64_dmma_path_rel_to_scale": headline_err_mean,
+                     "tolerance": 1e-6, "points": int(M),
+                     "note": "every point of the timed step compared with the precision='fp64' (DMMA) arm of the same run; "
+                             "the FP64 arm itself is within 3e-12 / 5e-13 of cuSOLVER/cuBLAS FP64 math (tests)"},
+        "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": int(M * DIM * 8), "d2h_bytes_per_step": int(M * 16),
+                "steps": e2e_steps, "api": "GPEmulator.predict(numpy)  [default precision='auto']", "max_abs_diff_vs_device_arm": parity},
+        "gpu_launches": int(args.steps * n_chunks * launches_per_chunk),
+        "roofline": roofline,
+        "fp64_dmma_mode": {"value": f64_value, "unit": "points/s", "ms_per_step": f64_ms / args.steps, "roofline": fp64_roofline,
+                           "note": "precision='fp64': the same predict with the variance contraction on the FP64 tensor path (DMMA)"},
         "mll_grad": ({"evals_per_s": 1e3 / (sum(mll_ms) / len(mll_ms)), "ms_per_eval": sum(mll_ms) / len(mll_ms),
                       "n_train": eng.N, "what": "K_hat build + Cholesky + L^-1 + alpha + -mll + K_hat^-1 + gradient reduce"}
                      if mll_ms else None),

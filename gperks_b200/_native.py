@@ -46,6 +46,8 @@ _SIGS = {
                                            _P, _P, C.c_size_t, C.c_int, C.c_int, _P]),
     "gpx_slice_i8": (C.c_int, [_P, C.c_int, C.c_int, C.c_long, _P, C.c_long, C.c_int, C.c_int, _P, _P, _P]),
     "gpx_i8_row_tiles": (C.c_int, [C.c_int]),
+    "gpx_kmat_cross_i8": (C.c_int, [_P, C.c_long, _P, C.c_int, C.c_int, _P, _P, _P, C.c_int, _P, _P, C.c_long, C.c_int, C.c_int,
+                                    _P, C.c_int, _P]),
     "gpx_trmm_sumsq_i8": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.c_int, _P, _P, _P]),
     "gpx_predict_i8_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "gpx_predict_meanvar_i8": (C.c_int, [_P, C.c_long, _P, C.c_int, C.c_int, _P, _P, _P, C.c_int, _P, _P, C.c_int, C.c_int,

@@ -44,3 +44,14 @@ DEFAULT_TMP_OUTFILE_DIR = Path(os.getcwd(), "tmp").as_posix()
 
 # B200 path
 DEFAULT_PREDICT_CHUNK_BYTES = 2 << 30      # HBM budget for one K* chunk in GPEmulator.predict
+
+# precision="auto" in GPEmulator.predict / predict_device: the sliced-integer variance path (tcgen05 kind::i8, six 7-bit
+# slices, exact int32 accumulation; measured std error vs the FP64 DMMA path <= 7e-8 at outputscale/noise = 1.3e4) is used
+# when its int32 sums cannot overflow, the problem is large enough for the tensor-core tiles to pay, and the
+# cancellation in  var = s + noise - ||L^-1 k*||^2  (amplification ~ outputscale / noise) leaves the error inside 1e-6;
+# otherwise the FP64 DMMA path.
+AUTO_I8_SLICES = 6
+AUTO_I8_MIN_N = 1024
+AUTO_I8_MAX_N = 32768
+AUTO_I8_MAX_SCALE_TO_NOISE = 1.0e5
+

@@ -22,6 +22,8 @@ int trmm_sumsq_tf32(const float*, const float*, int, const float*, const float*,
 int tf32_row_tiles(int);
 size_t predict_tf32_workspace_bytes(int, int);
 int slice_i8_matrix(const double*, int, int, long, int8_t*, long, int, int, double*, const double*, cudaStream_t);
+int kmat_cross_i8(const double*, long, const double*, int, int, const double*, const double*, const double*, int, const double*,
+                  int8_t*, long, int, int, double*, int, cudaStream_t);
 int trmm_sumsq_i8(const int8_t*, const double*, int, const int8_t*, int, int, const double*, double*, cudaStream_t);
 int i8_row_tiles(int);
 size_t predict_i8_workspace_bytes(int, int, int);
@@ -221,6 +223,18 @@ int gpx_slice_i8(const double* src, int rows, int cols, long ld_src, signed char
 }
 
 int gpx_i8_row_tiles(int Np) { return i8_row_tiles(Np); }
+
+int gpx_kmat_cross_i8(const double* Xs, long m_valid, const double* X, int N, int D, const double* theta, const double* xa,
+                      const double* xr, int kind, const double* alpha, signed char* planes, long plane_rows, int nslices,
+                      int Np, double* mean_part, int Mc, void* stream) {
+    if (!Xs || !X || !theta || !alpha || !planes || !mean_part) return -1;
+    if (D < 1 || D > MAXD) return -5;
+    if (Np % TILE || Mc % TILE || Np < N || Mc <= 0 || plane_rows < Mc) return -3;
+    if (nslices < 5 || nslices > 6) return -13;
+    if ((xa == nullptr) != (xr == nullptr)) return -7;
+    return kmat_cross_i8(Xs, m_valid, X, N, D, theta, xa, xr, kind, alpha, reinterpret_cast<int8_t*>(planes), plane_rows,
+                         nslices, Np, mean_part, Mc, ST(stream));
+}
 
 int gpx_trmm_sumsq_i8(const signed char* Ls, const double* inv_scale, int Np, const signed char* Kp, int Mc, int nslices,
                       const double* amax_ptr, double* qpart, void* stream) {

@@ -138,10 +138,17 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64
 // ---- the kernel ---------------------------------------------------------------------------------------------
 // grid.x = (Np/64) * (Mc/128) tiles; qpart[it][m] (ld = Mc) = sum over the 64 rows of tile `it` of V[m][i]^2.
 // tmA: K* planes as one [S*Mc][Np] byte matrix (box BKB x 128); tmB: L^-1 planes as [S*Np][Np] (box BKB x 64).
-template <int S, int BKB>
+//
+// MC = true (default): CTAs run as clusters of two on the SAME 128 test points and on two neighbouring row tiles
+// (it = 2p, 2p+1).  Each CTA fetches half (64 points) of every K* slice tile and TMA-multicasts it into both CTAs, so the
+// L2 serves the K* bytes -- two thirds of a stage -- once per pair: 60 -> 40 KB of L2 reads per CTA and stage (S = 5).
+// Both CTAs run the k extent of the odd tile (one extra stage of zero slices for the even one); a stage is refilled
+// only when both tensor cores have retired it (tcgen05.commit multicast onto both `empty` barriers, count 2).
+template <int S, int BKB, bool MC>
 __global__ void __launch_bounds__(I_THREADS, 1)
 trmm_sumsq_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int Np, int Mc,
-                     const double* __restrict__ inv_scale, const double* __restrict__ amax_ptr, double* __restrict__ qpart) {
+                     const __grid_constant__ CUtensorMap tmAh, const double* __restrict__ inv_scale,
+                     const double* __restrict__ amax_ptr, double* __restrict__ qpart) {
     using C = I8Cfg<S, BKB>;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -154,24 +161,28 @@ trmm_sumsq_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     // bands of I_BAND m tiles; inside a band the row tiles run heaviest (largest k extent) first
-    const int n_mb = Mc / I_M, n_it = Np / I_N;
+    const uint32_t crank = MC ? cluster_ctarank() : 0u;
+    const int n_mb = Mc / I_M, n_it = MC ? Np / (2 * I_N) : Np / I_N;      // MC: n_it counts PAIRS of row tiles
     int it, mb;
     {
+        const int id = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
         const int per_band = I_BAND * n_it;
-        const int band = (int)blockIdx.x / per_band;
+        const int band = id / per_band;
         const int left = n_mb - band * I_BAND;
         const int width = left < I_BAND ? left : I_BAND;
-        const int rem = (int)blockIdx.x - band * per_band;
+        const int rem = id - band * per_band;
         it = n_it - 1 - rem / width;
         mb = band * I_BAND + rem % width;
     }
-    const int kend = round_up((it + 1) * I_N, BKB);       // entries right of the diagonal are zero slices
+    // entries right of the diagonal are zero slices up to the end of the row's 128-block, so a pair runs the odd tile's extent
+    const int kend = MC ? (it + 1) * 2 * I_N : round_up((it + 1) * I_N, BKB);
+    if (MC) it = 2 * it + (int)crank;
     const int nk = kend / BKB;
 
     if (tid == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
             mbar_init(full0 + 8 * s, 1);
-            mbar_init(empty0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, MC ? 2 : 1);
         }
         mbar_init(acc_full, 1);
         mbar_fence_init();
@@ -188,6 +199,7 @@ trmm_sumsq_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
     tc_fence_before();
     __syncthreads();
+    if (MC) cluster_sync_all();        // the peer's barriers must be initialised before anything is multicast at them
     tc_fence_after();
     const uint32_t tmem_d = *tmem_slot;
 
@@ -215,8 +227,15 @@ trmm_sumsq_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 mbar_arrive_expect_tx(full0 + 8 * s, C::STAGE_BYTES);
                 const uint32_t dst = tile0 + s * C::STAGE_BYTES;
                 const int k0 = kt * BKB;
+                if (MC) {   // my 64 points of every K* slice tile, delivered to both CTAs of the pair
 #pragma unroll
-                for (int j = 0; j < S; ++j) tma_load_2d(dst + j * C::A_BYTES, &tmA, k0, j * Mc + mb * I_M, full0 + 8 * s);
+                    for (int j = 0; j < S; ++j)
+                        tma_load_2d_multicast(dst + j * C::A_BYTES + crank * (C::A_BYTES / 2), &tmAh, k0,
+                                              j * Mc + mb * I_M + (int)crank * (I_M / 2), full0 + 8 * s, 3);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < S; ++j) tma_load_2d(dst + j * C::A_BYTES, &tmA, k0, j * Mc + mb * I_M, full0 + 8 * s);
+                }
 #pragma unroll
                 for (int j = 0; j < S; ++j)
                     tma_load_2d(dst + S * C::A_BYTES + j * C::B_BYTES, &tmB, k0, j * Np + it * I_N, full0 + 8 * s);
@@ -245,7 +264,8 @@ trmm_sumsq_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                         }
                     }
                 }
-                umma_commit(empty0 + 8 * s);
+                if (MC) umma_commit_multicast(empty0 + 8 * s, 3);     // both producers wait for both tensor cores
+                else umma_commit(empty0 + 8 * s);
             }
             umma_commit(acc_full);
         }
@@ -282,6 +302,7 @@ trmm_sumsq_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         tc_fence_before();
     }
     __syncthreads();
+    if (MC) cluster_sync_all();        // nobody leaves while the peer may still multicast into / arrive on this CTA
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "n"(I_TMEM_COLS) : "memory");
@@ -322,7 +343,13 @@ int slice_i8_matrix(const double* src, int rows, int cols, long ld_src, int8_t* 
     return 0;
 }
 
-template <int S, int BKB>
+static int i8_multicast() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("GPX_I8_IMPL"); v = (e && e[0] == '1') ? 0 : 1; }   // GPX_I8_IMPL=1cta: no pairing
+    return v;
+}
+
+template <int S, int BKB, bool MC>
 static int launch_i8(const int8_t* Ls, const double* inv_scale, int Np, const int8_t* Kp, int Mc, const double* amax_ptr,
                      double* qpart, cudaStream_t st) {
     using C = I8Cfg<S, BKB>;
@@ -330,15 +357,33 @@ static int launch_i8(const int8_t* Ls, const double* inv_scale, int Np, const in
     int dev = 0;
     cudaGetDevice(&dev);
     if (!(dev >= 0 && dev < 64 && attr[dev])) {
-        cudaFuncSetAttribute(trmm_sumsq_i8_kernel<S, BKB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+        cudaFuncSetAttribute(trmm_sumsq_i8_kernel<S, BKB, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
         if (dev >= 0 && dev < 64) attr[dev] = true;
     }
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmAh, tmB;
     int rc;
     if ((rc = encode_u8_rowmajor(&tmA, Kp, (uint64_t)S * Mc, Np, BKB, I_M))) return rc;
+    if ((rc = encode_u8_rowmajor(&tmAh, Kp, (uint64_t)S * Mc, Np, BKB, I_M / 2))) return rc;
     if ((rc = encode_u8_rowmajor(&tmB, Ls, (uint64_t)S * Np, Np, BKB, I_N))) return rc;
     const int tiles = (Np / I_N) * (Mc / I_M);
-    trmm_sumsq_i8_kernel<S, BKB><<<tiles, I_THREADS, C::SMEM_BYTES, st>>>(tmA, tmB, Np, Mc, inv_scale, amax_ptr, qpart);
+    if (!MC) {
+        trmm_sumsq_i8_kernel<S, BKB, false><<<tiles, I_THREADS, C::SMEM_BYTES, st>>>(tmA, tmB, Np, Mc, tmAh, inv_scale, amax_ptr, qpart);
+    } else {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(tiles);
+        cfg.blockDim = dim3(I_THREADS);
+        cfg.dynamicSmemBytes = C::SMEM_BYTES;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, trmm_sumsq_i8_kernel<S, BKB, true>, tmA, tmB, Np, Mc, tmAh, inv_scale, amax_ptr, qpart);
+        if (e != cudaSuccess) return -1000 - (int)e;
+    }
     GPX_CHECK_LAUNCH();
     return 0;
 }
@@ -349,10 +394,13 @@ int trmm_sumsq_i8(const int8_t* Ls, const double* inv_scale, int Np, const int8_
     if (Mc % I_M || Np % TILE) return -6;
     if (Np > 32768) return -7;              // int32 accumulators: 64*64*K*S < 2^31
     const bool wide = i8_bkb() == 128;
-    if (nslices == 5) return wide ? launch_i8<5, 128>(Ls, inv_scale, Np, Kp, Mc, amax_ptr, qpart, st)
-                                  : launch_i8<5, 64>(Ls, inv_scale, Np, Kp, Mc, amax_ptr, qpart, st);
-    if (nslices == 6) return wide ? launch_i8<6, 128>(Ls, inv_scale, Np, Kp, Mc, amax_ptr, qpart, st)
-                                  : launch_i8<6, 64>(Ls, inv_scale, Np, Kp, Mc, amax_ptr, qpart, st);
+    const bool mc = !wide && i8_multicast();
+    if (nslices == 5) return wide ? launch_i8<5, 128, false>(Ls, inv_scale, Np, Kp, Mc, amax_ptr, qpart, st)
+                           : mc   ? launch_i8<5, 64, true>(Ls, inv_scale, Np, Kp, Mc, amax_ptr, qpart, st)
+                                  : launch_i8<5, 64, false>(Ls, inv_scale, Np, Kp, Mc, amax_ptr, qpart, st);
+    if (nslices == 6) return wide ? launch_i8<6, 128, false>(Ls, inv_scale, Np, Kp, Mc, amax_ptr, qpart, st)
+                           : mc   ? launch_i8<6, 64, true>(Ls, inv_scale, Np, Kp, Mc, amax_ptr, qpart, st)
+                                  : launch_i8<6, 64, false>(Ls, inv_scale, Np, Kp, Mc, amax_ptr, qpart, st);
     return -8;
 }
 

@@ -180,6 +180,105 @@ kmat_cross_kernel(const double* __restrict__ Xs, long m_valid, const double* __r
 }
 
 // ------------------------------------------------------------------------------------------------
+// Sliced-integer mode (gpx_i8.cu): K* evaluated in FP64 exactly like kmat_cross_kernel -- same micro-tile, same order of
+// the fused K* alpha partial sums, so the posterior mean is bit-identical -- and written directly as S signed 7-bit
+// slices (int8 planes [S][plane_rows][Np]) of  v * 2^-(e+1),  outputscale = f 2^e  (k <= outputscale), instead of 8-byte
+// values that a second kernel would read back and slice.  A warp owns two rows of every 16-row step; its bytes are
+// staged through 256 B of shared memory per slice so that each lane stores 8 consecutive bytes (128 B per row and slice).
+template <int KIND, int S>
+__global__ void __launch_bounds__(P_THREADS, 2)
+kmat_cross_i8_kernel(const double* __restrict__ Xs, long m_valid, const double* __restrict__ X, int N, int D,
+                     const double* __restrict__ theta, const double* __restrict__ xa, const double* __restrict__ xr,
+                     const double* __restrict__ alpha, int8_t* __restrict__ planes, long plane_rows, int Np,
+                     double* __restrict__ mean_part, int Mc) {
+    const int jb = blockIdx.x, mb = blockIdx.y;
+    extern __shared__ double sm[];
+    double* sa = sm;                    // test points (rows m)
+    double* sb = sm + MAXD * P_LD;      // train points (cols j)
+    double* sal = sb + MAXD * P_LD;     // alpha tile [128]
+    double* smean = sal + TILE;         // [128]
+    unsigned char* stg = reinterpret_cast<unsigned char*>(smean + TILE) + (threadIdx.x >> 5) * (S * 256);   // [S][2][128] per warp
+    stage_coords(sa, Xs, (long)mb * TILE, m_valid, D, theta, xa, xr);
+    stage_coords(sb, X, (long)jb * TILE, N, D, theta, nullptr, nullptr);
+    if (threadIdx.x < TILE) sal[threadIdx.x] = alpha[jb * TILE + threadIdx.x];
+    __syncthreads();
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4, lane = threadIdx.x & 31;
+    const double s = theta[D];
+    int e = 0;
+    if (s > 0.0) frexp(s, &e);
+    const double scale = ldexp(1.0, 7 - (e + 1));            // first slice = rint(v * 2^-(e+1) * 2^7), |.| <= 64
+    const long pitch = plane_rows * (long)Np;
+    double al[8];
+#pragma unroll
+    for (int b = 0; b < 8; ++b) al[b] = sal[tx + 16 * b];
+#pragma unroll 1
+    for (int a = 0; a < 8; ++a) {
+        const int row = ty + 16 * a;
+        double r2[8];
+#pragma unroll
+        for (int b = 0; b < 8; ++b) r2[b] = 0.0;
+        for (int d = 0; d < D; ++d) {
+            const double xa_ = sa[d * P_LD + row];
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                const double df = xa_ - sb[d * P_LD + tx + 16 * b];
+                r2[b] = fma(df, df, r2[b]);
+            }
+        }
+        const long m = (long)mb * TILE + row;
+        double part = 0.0;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const long j = (long)jb * TILE + tx + 16 * b;
+            const double v = (j < N) ? kernel_value<KIND>(r2[b], s) : 0.0;
+            part = fma(v, al[b], part);
+            double r = v * scale;
+#pragma unroll
+            for (int q = 0; q < S; ++q) {
+                const double qi = rint(r);
+                r = (r - qi) * 128.0;                            // exact: |r - qi| <= 1/2
+                stg[q * 256 + (ty & 1) * 128 + tx + 16 * b] = (unsigned char)(__double2int_rn(qi) & 0xff);
+            }
+        }
+        part += __shfl_xor_sync(0xffffffffu, part, 1);
+        part += __shfl_xor_sync(0xffffffffu, part, 2);
+        part += __shfl_xor_sync(0xffffffffu, part, 4);
+        part += __shfl_xor_sync(0xffffffffu, part, 8);
+        if (tx == 0) smean[row] = part;
+        __syncwarp();
+        // lane -> 8 consecutive bytes of its own row (lane >> 4 == ty & 1): columns 8 (lane & 15) ..
+        int8_t* dst = planes + m * Np + (long)jb * TILE + (lane & 15) * 8;
+#pragma unroll
+        for (int q = 0; q < S; ++q)
+            *reinterpret_cast<uint2*>(dst + q * pitch) = *reinterpret_cast<const uint2*>(stg + q * 256 + lane * 8);
+        __syncwarp();
+    }
+    __syncthreads();
+    if (threadIdx.x < TILE) mean_part[(long)jb * Mc + (long)mb * TILE + threadIdx.x] = smean[threadIdx.x];
+}
+
+template <int KIND>
+static int launch_kmat_cross_i8(const double* Xs, long m_valid, const double* X, int N, int D, const double* theta,
+                                const double* xa, const double* xr, const double* alpha, int8_t* planes, long plane_rows,
+                                int nslices, int Np, double* mean_part, int Mc, cudaStream_t st) {
+    const size_t smem = size_t(2) * MAXD * P_LD * 8 + 2 * TILE * 8 + 8 * size_t(nslices) * 256;
+    const dim3 grid(Np / TILE, Mc / TILE);
+    if (nslices == 5) {
+        cudaFuncSetAttribute(kmat_cross_i8_kernel<KIND, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kmat_cross_i8_kernel<KIND, 5><<<grid, P_THREADS, smem, st>>>(Xs, m_valid, X, N, D, theta, xa, xr, alpha, planes,
+                                                                    plane_rows, Np, mean_part, Mc);
+    } else if (nslices == 6) {
+        cudaFuncSetAttribute(kmat_cross_i8_kernel<KIND, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kmat_cross_i8_kernel<KIND, 6><<<grid, P_THREADS, smem, st>>>(Xs, m_valid, X, N, D, theta, xa, xr, alpha, planes,
+                                                                    plane_rows, Np, mean_part, Mc);
+    } else {
+        return -8;
+    }
+    GPX_CHECK_LAUNCH();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // TF32-mode cross kernel: K* evaluated in FP32 (coordinates are scaled in FP64, rounded once) and written as the
 // (hi, lo) TF32 operand pair of the 3xTF32 contraction; the posterior-mean partials accumulate in FP64.
 // Relative error of an entry ~3e-7 -- far inside the mode's 1e-3 tolerance -- at ~1/5 of the FP64 builder's cost.
@@ -480,6 +579,15 @@ int kmat_cross(const double* Xs, long m_valid, const double* X, int N, int D, co
                const double* xr, int kind, const double* alpha, double* Ks, int Np, double* mean_part, int Mc,
                cudaStream_t st) {
 #define C_(KD) launch_kmat_cross<KD>(Xs, m_valid, X, N, D, theta, xa, xr, alpha, Ks, Np, mean_part, Mc, nullptr, nullptr, st)
+    GPX_DISPATCH_KIND(kind, C_)
+#undef C_
+}
+
+// Sliced-integer mode: K* written as `nslices` int8 planes [nslices][plane_rows][Np] (gpx_i8.cu).
+int kmat_cross_i8(const double* Xs, long m_valid, const double* X, int N, int D, const double* theta, const double* xa,
+                  const double* xr, int kind, const double* alpha, int8_t* planes, long plane_rows, int nslices, int Np,
+                  double* mean_part, int Mc, cudaStream_t st) {
+#define C_(KD) launch_kmat_cross_i8<KD>(Xs, m_valid, X, N, D, theta, xa, xr, alpha, planes, plane_rows, nslices, Np, mean_part, Mc, st)
     GPX_DISPATCH_KIND(kind, C_)
 #undef C_
 }

@@ -440,6 +440,15 @@ int slice_i8_matrix(const double* src, int rows, int cols, long ld_src, int8_t* 
 int trmm_sumsq_i8(const int8_t* Ls, const double* inv_scale, int Np, const int8_t* Kp, int Mc, int nslices,
                   const double* amax_ptr, double* qpart, cudaStream_t st);
 int i8_row_tiles(int Np);
+int kmat_cross_i8(const double* Xs, long m_valid, const double* X, int N, int D, const double* theta, const double* xa,
+                  const double* xr, int kind, const double* alpha, int8_t* planes, long plane_rows, int nslices, int Np,
+                  double* mean_part, int Mc, cudaStream_t st);
+
+static int i8_fused_builder() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("GPX_I8_BUILDER"); v = (e && e[0] == 's') ? 0 : 1; }   // GPX_I8_BUILDER=split: FP64 K* + slicing pass
+    return v;
+}
 
 size_t predict_i8_workspace_bytes(int Np, int Mc, int nslices) {
     const size_t nb = Np / TILE;
@@ -468,9 +477,14 @@ int predict_meanvar_i8(const double* Xs, long M, const double* X, int N, int D, 
         const long mv = (M - m0 < Mc) ? (M - m0) : Mc;
         const int mc = round_up((int)mv, TILE);
         const double* xs = Xs + m0 * D;
-        int rc = kmat_cross(xs, mv, X, N, D, theta, xa, xr, kind, alpha, Ks, Np, mean_part, mc, st);
-        if (rc) return rc;
-        rc = slice_i8_matrix(Ks, mc, Np, Np, Kp, mc, nslices, 0, nullptr, amax, st);
+        int rc;
+        if (i8_fused_builder()) {
+            rc = kmat_cross_i8(xs, mv, X, N, D, theta, xa, xr, kind, alpha, Kp, mc, nslices, Np, mean_part, mc, st);
+        } else {
+            rc = kmat_cross(xs, mv, X, N, D, theta, xa, xr, kind, alpha, Ks, Np, mean_part, mc, st);
+            if (rc) return rc;
+            rc = slice_i8_matrix(Ks, mc, Np, Np, Kp, mc, nslices, 0, nullptr, amax, st);
+        }
         if (rc) return rc;
         rc = trmm_sumsq_i8(Ls, inv_scale, Np, Kp, mc, nslices, amax, qpart, st);
         if (rc) return rc;

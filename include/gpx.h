@@ -141,6 +141,11 @@ int gpx_predict_meanvar_tf32(const double* Xs, long M, const double* X, int N, i
 int gpx_slice_i8(const double* src, int rows, int cols, long ld_src, signed char* planes, long plane_rows, int nslices,
                  int tri, double* inv_scale, const double* amax_ptr, void* stream);
 int gpx_i8_row_tiles(int Np);
+/* gpx_kmat_cross_i8: gpx_kmat_cross and gpx_slice_i8 (tri = 0, amax = outputscale) in one pass: the K* chunk is evaluated in
+ * FP64 and written only as its int8 slices (same bytes, same mean_part as the two calls). */
+int gpx_kmat_cross_i8(const double* Xs, long m_valid, const double* X, int N, int D, const double* theta, const double* xa,
+                      const double* xr, int kind, const double* alpha, signed char* planes, long plane_rows, int nslices,
+                      int Np, double* mean_part, int Mc, void* stream);
 int gpx_trmm_sumsq_i8(const signed char* Ls, const double* inv_scale, int Np, const signed char* Kp, int Mc, int nslices,
                       const double* amax_ptr, double* qpart, void* stream);
 size_t gpx_predict_i8_workspace_bytes(int Np, int Mc, int nslices);
