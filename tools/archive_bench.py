@@ -8,9 +8,10 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+sfx = sys.argv[2] if len(sys.argv) > 2 else "final"      # "int8": the run with the sliced-integer default as headline
 out, prof = ROOT / "gpurun_out", ROOT / "profiles"
 d = json.loads((out / "bench_final.json").read_text().strip().splitlines()[-1])
-(prof / f"{tag}_bench_1gpu_final.json").write_text(json.dumps(d, indent=1))
+(prof / f"{tag}_bench_1gpu_{sfx}.json").write_text(json.dumps(d, indent=1))
 print({k: d[k] for k in ("value", "ms_per_step", "gpu_launches")}, "e2e", d["e2e"]["value"], "frac", round(d["roofline"]["frac"], 4),
       "mll", d["mll_grad"], "cpu", d.get("cpu_baseline", {}).get("value"), "torch_gpu", d.get("torch_gpu_baseline", {}).get("value"))
 if d.get("tf32_mode"):
@@ -18,7 +19,7 @@ if d.get("tf32_mode"):
 ref = out / "bench_ref.json"
 if ref.exists():
     r = json.loads(ref.read_text().strip().splitlines()[-1])
-    (prof / f"{tag}_bench_reference_arm.json").write_text(json.dumps(r, indent=1))
+    (prof / (f"{tag}_bench_reference_arm.json" if sfx == "final" else f"{tag}_bench_reference_arm_{sfx}.json")).write_text(json.dumps(r, indent=1))
     print("reference arm", r["value"], r.get("cpu_baseline", {}).get("sample"))
 rows = list(csv.reader(l for l in open(out / "launches_final.csv") if not l.startswith("==")))
 hdr, agg = None, collections.OrderedDict()
@@ -36,7 +37,7 @@ for r_ in rows:
 tot = sum(t for _, t in agg.values())
 lines = ["# ncu launch list (gpu__time_duration.sum, --clock-control none), SHIPPED kernels (final)",
          "# command: python bench.py --steps 1 --warmup 3 --points 65536 --no-cpu-baseline --mll-evals 1",
-         "# covers: 3 factorisations (+gradients), FP64 predict (3 warm-up + 1 timed step + roofline probe), e2e predict, both TF32-mode arms",
+         "# covers: factorisations (+gradients), the headline predict arm (3 warm-up + 1 timed step), the FP64 DMMA arm + roofline probes, e2e predict, TF32- and int8-mode arms",
          "# per-launch times are cold-cache and serialised under ncu: compare SHARES",
          f"# total {tot / 1e3:.2f} ms over {sum(n for n, _ in agg.values())} launches", "kernel,launches,total_ms,share,mean_us"]
 for k, (n, t) in sorted(agg.items(), key=lambda x: -x[1][1]):
@@ -50,7 +51,12 @@ def mean(name):
 
 trmm, kc, fin = mean("trmm_sumsq_tma_kernel"), mean("kmat_cross_kernel<3>"), mean("predict_finalize_kernel")
 lines.append(f"# FP64 predict step (one 32768-point chunk) under ncu: trmm {trmm / 1e3:.2f} ms, kmat_cross {kc / 1e3:.2f} ms, "
-             f"finalize {fin / 1e3:.3f} ms -> TRMM share {trmm / (trmm + kc + fin):.3f} (bench.py live: {d['roofline']['kernel_share_of_step']:.3f})")
-(prof / f"{tag}_launches_shipped.csv").write_text("\n".join(lines) + "\n")
+             f"finalize {fin / 1e3:.3f} ms -> TRMM share {trmm / (trmm + kc + fin):.3f} (bench.py live: {d.get('fp64_dmma_mode', d)['roofline']['kernel_share_of_step']:.3f})")
+ti, ki = mean("trmm_sumsq_i8_kernel<6"), mean("kmat_cross_i8_kernel<3, 6>")
+if ti == ti:
+    lines.append(f"# int8x6 predict step (one 32768-point chunk) under ncu: trmm_i8 {ti / 1e3:.2f} ms, kmat_cross_i8 {ki / 1e3:.2f} ms, "
+                 f"finalize {fin / 1e3:.3f} ms -> integer-kernel share {ti / (ti + ki + fin):.3f}"
+                 + (f" (bench.py live: {d['roofline']['kernel_share_of_step']:.3f})" if "i8" in d["roofline"]["kernel"] else ""))
+(prof / (f"{tag}_launches_shipped.csv" if sfx == "final" else f"{tag}_launches_{sfx}.csv")).write_text("\n".join(lines) + "\n")
 print("\n".join(lines[5:26]))
 print(lines[-1])
