@@ -15,8 +15,8 @@
 // diagonal g.  The S slices of the L^-1 tile are STACKED along MMA N in shared memory, so for the K* slice a one
 // instruction with N = 64 (S - a) (cut at 256) multiplies it with the L^-1 slices b = 0 .. S-1-a and lands in the
 // accumulators g = a .. S-1, which are contiguous in TMEM: S = 5 needs 6 MMAs per 32-deep k step instead of 15, and the
-// K* slices are read from shared memory 6 times instead of 15.  The accumulators are zeroed once through tcgen05.st so
-// every MMA accumulates.  K runs over the training index in BKB-byte slices (SWIZZLE_64B: three stages of 60-72 KB).
+// K* slices are read from shared memory 6 times instead of 15.  The first k step of K* slice 0 covers all S accumulators
+// and overwrites them; every later MMA accumulates.  K runs over the training index in BKB-byte slices (SWIZZLE_64B: three stages of 60-72 KB).
 // Warp roles as in gpx_tf32.cu: warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer, warps 2..9 epilogue.
 #include "gpx_common.cuh"
 #include "gpx_tma.cuh"
@@ -203,20 +203,6 @@ trmm_sumsq_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     tc_fence_after();
     const uint32_t tmem_d = *tmem_slot;
 
-    if (warp >= 2) {    // zero the S accumulators: this warp's lane quadrant, alternate 32-column blocks per half
-        const int quad = warp & 3, half = (warp - 2) >> 2;
-        uint32_t z[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) z[j] = 0u;
-#pragma unroll
-        for (int g = 0; g < S; ++g)
-            tmem_st_32x32b_x32(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * I_N + half * 32), z);
-        tmem_wait_st();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
@@ -260,7 +246,8 @@ trmm_sumsq_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                         for (int c0 = 0; c0 < ncols; c0 += 256) {
                             const int w = (ncols - c0) < 256 ? (ncols - c0) : 256;
                             const uint64_t db = umma_desc_kmajor<BKB>(st + S * C::A_BYTES + (c0 / I_N) * C::B_BYTES) + adv;
-                            umma_i8(tmem_d + (uint32_t)(a * I_N + c0), da, db, i8_idesc(w), 1u);
+                            // the very first k step of K* slice 0 touches every accumulator once: it overwrites (no zero fill)
+                            umma_i8(tmem_d + (uint32_t)(a * I_N + c0), da, db, i8_idesc(w), (kt | kk | a) != 0 ? 1u : 0u);
                         }
                     }
                 }
