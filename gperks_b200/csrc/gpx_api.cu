@@ -22,6 +22,8 @@ int trmm_sumsq_tf32(const float*, const float*, int, const float*, const float*,
 int tf32_row_tiles(int);
 size_t predict_tf32_workspace_bytes(int, int);
 int slice_i8_matrix(const double*, int, int, long, int8_t*, long, int, int, double*, const double*, cudaStream_t);
+size_t lauum_i8_workspace_bytes(int, int);
+int lauum_i8(const double*, const double*, double*, int, int, void*, size_t, cudaStream_t);
 int kmat_cross_i8(const double*, long, const double*, int, int, const double*, const double*, const double*, int, const double*,
                   int8_t*, long, int, int, double*, int, cudaStream_t);
 int trmm_sumsq_i8(const int8_t*, const double*, int, const int8_t*, int, int, const double*, double*, cudaStream_t);
@@ -243,6 +245,15 @@ int gpx_trmm_sumsq_i8(const signed char* Ls, const double* inv_scale, int Np, co
     if (nslices < 5 || nslices > 6) return -6;
     return trmm_sumsq_i8(reinterpret_cast<const int8_t*>(Ls), inv_scale, Np, reinterpret_cast<const int8_t*>(Kp), Mc,
                          nslices, amax_ptr, qpart, ST(stream));
+}
+
+size_t gpx_lauum_i8_workspace_bytes(int Np, int nslices) { return lauum_i8_workspace_bytes(Np, nslices); }
+
+int gpx_lauum_i8(const double* S, const double* DT, double* Kinv, int Np, int nslices, void* workspace, size_t workspace_bytes,
+                 void* stream) {
+    if (!S || !DT || !Kinv || !workspace) return -1;
+    if (Np <= 0 || Np % TILE) return -4;
+    return lauum_i8(S, DT, Kinv, Np, nslices, workspace, workspace_bytes, ST(stream));
 }
 
 size_t gpx_predict_i8_workspace_bytes(int Np, int Mc, int nslices) { return predict_i8_workspace_bytes(Np, Mc, nslices); }

@@ -144,7 +144,13 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64
 // L2 serves the K* bytes -- two thirds of a stage -- once per pair: 60 -> 40 KB of L2 reads per CTA and stage (S = 5).
 // Both CTAs run the k extent of the odd tile (one extra stage of zero slices for the even one); a stage is refilled
 // only when both tensor cores have retired it (tcgen05.commit multicast onto both `empty` barriers, count 2).
-template <int S, int BKB, bool MC>
+//
+// SYRK = true: the same machinery forms K_hat^-1 = L^-T L^-1 for the gradient (lauum): both operands are tiles of ONE sliced
+// matrix -- the columns of L^-1 as rows (upper triangular, k >= i) -- the k range of tile row mb starts at its 128-block
+// instead of ending there, only tiles on or below the diagonal are formed (two 64-column tiles per pair, so a pair shares
+// its 128 rows and its k range), and the epilogue stores inv_scale_i inv_scale_j 2^-14 sum_g 2^-7g acc_g instead of
+// reducing its squares.  `Mc` is then the row count of the planes (Np) and `qpart` the output matrix W[Np][Np].
+template <int S, int BKB, bool MC, bool SYRK>
 __global__ void __launch_bounds__(I_THREADS, 1)
 trmm_sumsq_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int Np, int Mc,
                      const __grid_constant__ CUtensorMap tmAh, const double* __restrict__ inv_scale,
@@ -162,9 +168,25 @@ trmm_sumsq_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
     // bands of I_BAND m tiles; inside a band the row tiles run heaviest (largest k extent) first
     const uint32_t crank = MC ? cluster_ctarank() : 0u;
-    const int n_mb = Mc / I_M, n_it = MC ? Np / (2 * I_N) : Np / I_N;      // MC: n_it counts PAIRS of row tiles
-    int it, mb;
-    {
+    int it, mb, kstart, kend;
+    if constexpr (SYRK) {
+        // tile row mb owns the 64-column tiles it = 0 .. 2 mb + 1 (pairs p = 0 .. mb); rows are taken in ascending order: longest k first
+        const int id = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+        if (MC) {
+            mb = (int)((sqrt(8.0 * id + 1.0) - 1.0) * 0.5);
+            while ((mb + 1) * (mb + 2) / 2 <= id) ++mb;
+            while (mb * (mb + 1) / 2 > id) --mb;
+            it = 2 * (id - mb * (mb + 1) / 2) + (int)crank;
+        } else {
+            mb = (int)((sqrt(4.0 * id + 1.0) - 1.0) * 0.5);
+            while ((mb + 1) * (mb + 2) <= id) ++mb;
+            while (mb * (mb + 1) > id) --mb;
+            it = id - mb * (mb + 1);
+        }
+        kstart = mb * I_M;
+        kend = Np;
+    } else {
+        const int n_mb = Mc / I_M, n_it = MC ? Np / (2 * I_N) : Np / I_N;      // MC: n_it counts PAIRS of row tiles
         const int id = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
         const int per_band = I_BAND * n_it;
         const int band = id / per_band;
@@ -173,11 +195,12 @@ trmm_sumsq_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int rem = id - band * per_band;
         it = n_it - 1 - rem / width;
         mb = band * I_BAND + rem % width;
+        // entries right of the diagonal are zero slices up to the end of the row's 128-block, so a pair runs the odd tile's extent
+        kend = MC ? (it + 1) * 2 * I_N : round_up((it + 1) * I_N, BKB);
+        if (MC) it = 2 * it + (int)crank;
+        kstart = 0;
     }
-    // entries right of the diagonal are zero slices up to the end of the row's 128-block, so a pair runs the odd tile's extent
-    const int kend = MC ? (it + 1) * 2 * I_N : round_up((it + 1) * I_N, BKB);
-    if (MC) it = 2 * it + (int)crank;
-    const int nk = kend / BKB;
+    const int nk = (kend - kstart) / BKB;
 
     if (tid == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
@@ -194,7 +217,7 @@ trmm_sumsq_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
     if (tid < I_N) {
         // V = (sum_g acc_g 2^{-7g}) * 2^{-14} / (scale_i * scale_K):  all powers of two, exact
-        const int ek = scale_exponent(*amax_ptr);
+        const int ek = SYRK ? -1 : scale_exponent(*amax_ptr);        // SYRK: both operands carry per-row scales
         sinv[tid] = inv_scale[it * I_N + tid] * ldexp(1.0, ek + 1 - 2 * I_BITS);
     }
     tc_fence_before();
@@ -212,7 +235,7 @@ trmm_sumsq_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 if (round > 0) mbar_wait(empty0 + 8 * s, (round - 1) & 1);
                 mbar_arrive_expect_tx(full0 + 8 * s, C::STAGE_BYTES);
                 const uint32_t dst = tile0 + s * C::STAGE_BYTES;
-                const int k0 = kt * BKB;
+                const int k0 = kstart + kt * BKB;
                 if (MC) {   // my 64 points of every K* slice tile, delivered to both CTAs of the pair
 #pragma unroll
                     for (int j = 0; j < S; ++j)
@@ -274,17 +297,26 @@ trmm_sumsq_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
             for (int j = 0; j < 32; ++j) t[j] = fma((double)(int)v[j], wg, t[j]);
         }
-        double ssum = 0.0;
+        if constexpr (SYRK) {
+            const long row = (long)mb * I_M + quad * 32 + lane;
+            const double si = inv_scale[row];
+            double* dst = qpart + row * Np + (long)it * I_N + half * 32;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const double x = t[j] * sinv[half * 32 + j];
-            ssum = fma(x, x, ssum);
-        }
-        red[half * I_M + quad * 32 + lane] = ssum;
-        named_bar_sync(1, 256);
-        if (half == 0) {
-            const int m = mb * I_M + quad * 32 + lane;
-            qpart[(long)it * Mc + m] = red[quad * 32 + lane] + red[I_M + quad * 32 + lane];
+            for (int j = 0; j < 32; j += 2)
+                *reinterpret_cast<double2*>(dst + j) = make_double2(t[j] * sinv[half * 32 + j] * si, t[j + 1] * sinv[half * 32 + j + 1] * si);
+        } else {
+            double ssum = 0.0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const double x = t[j] * sinv[half * 32 + j];
+                ssum = fma(x, x, ssum);
+            }
+            red[half * I_M + quad * 32 + lane] = ssum;
+            named_bar_sync(1, 256);
+            if (half == 0) {
+                const int m = mb * I_M + quad * 32 + lane;
+                qpart[(long)it * Mc + m] = red[quad * 32 + lane] + red[I_M + quad * 32 + lane];
+            }
         }
         tc_fence_before();
     }
@@ -336,7 +368,7 @@ static int i8_multicast() {
     return v;
 }
 
-template <int S, int BKB, bool MC>
+template <int S, int BKB, bool MC, bool SYRK = false>
 static int launch_i8(const int8_t* Ls, const double* inv_scale, int Np, const int8_t* Kp, int Mc, const double* amax_ptr,
                      double* qpart, cudaStream_t st) {
     using C = I8Cfg<S, BKB>;
@@ -344,7 +376,7 @@ static int launch_i8(const int8_t* Ls, const double* inv_scale, int Np, const in
     int dev = 0;
     cudaGetDevice(&dev);
     if (!(dev >= 0 && dev < 64 && attr[dev])) {
-        cudaFuncSetAttribute(trmm_sumsq_i8_kernel<S, BKB, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+        cudaFuncSetAttribute(trmm_sumsq_i8_kernel<S, BKB, MC, SYRK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
         if (dev >= 0 && dev < 64) attr[dev] = true;
     }
     CUtensorMap tmA, tmAh, tmB;
@@ -352,9 +384,10 @@ static int launch_i8(const int8_t* Ls, const double* inv_scale, int Np, const in
     if ((rc = encode_u8_rowmajor(&tmA, Kp, (uint64_t)S * Mc, Np, BKB, I_M))) return rc;
     if ((rc = encode_u8_rowmajor(&tmAh, Kp, (uint64_t)S * Mc, Np, BKB, I_M / 2))) return rc;
     if ((rc = encode_u8_rowmajor(&tmB, Ls, (uint64_t)S * Np, Np, BKB, I_N))) return rc;
-    const int tiles = (Np / I_N) * (Mc / I_M);
+    const int nbt = Np / I_M;
+    const int tiles = SYRK ? nbt * (nbt + 1) : (Np / I_N) * (Mc / I_M);       // SYRK: 2 mb + 2 column tiles in tile row mb
     if (!MC) {
-        trmm_sumsq_i8_kernel<S, BKB, false><<<tiles, I_THREADS, C::SMEM_BYTES, st>>>(tmA, tmB, Np, Mc, tmAh, inv_scale, amax_ptr, qpart);
+        trmm_sumsq_i8_kernel<S, BKB, false, SYRK><<<tiles, I_THREADS, C::SMEM_BYTES, st>>>(tmA, tmB, Np, Mc, tmAh, inv_scale, amax_ptr, qpart);
     } else {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(tiles);
@@ -368,7 +401,7 @@ static int launch_i8(const int8_t* Ls, const double* inv_scale, int Np, const in
         at[0].val.clusterDim.z = 1;
         cfg.attrs = at;
         cfg.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, trmm_sumsq_i8_kernel<S, BKB, true>, tmA, tmB, Np, Mc, tmAh, inv_scale, amax_ptr, qpart);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, trmm_sumsq_i8_kernel<S, BKB, true, SYRK>, tmA, tmB, Np, Mc, tmAh, inv_scale, amax_ptr, qpart);
         if (e != cudaSuccess) return -1000 - (int)e;
     }
     GPX_CHECK_LAUNCH();
@@ -389,6 +422,75 @@ int trmm_sumsq_i8(const int8_t* Ls, const double* inv_scale, int Np, const int8_
                            : mc   ? launch_i8<6, 64, true>(Ls, inv_scale, Np, Kp, Mc, amax_ptr, qpart, st)
                                   : launch_i8<6, 64, false>(Ls, inv_scale, Np, Kp, Mc, amax_ptr, qpart, st);
     return -8;
+}
+
+// ---- K_hat^-1 = L^-T L^-1 on the integer tensor cores (lauum for the gradient) ----------------------------------------
+// Row i of the operand = column i of L^-1 over k >= i: the transposed diagonal block DT[b] inside the row's own 128-block,
+// the mirrored L^-T blocks of S right of it, zero left of the diagonal.  One CTA per row, a power-of-two scale per row.
+template <int S>
+__global__ void __launch_bounds__(256) slice_i8_linvT_kernel(const double* __restrict__ Smat, const double* __restrict__ DT, int Np,
+                                                             int8_t* __restrict__ planes, double* __restrict__ inv_scale) {
+    const int row = blockIdx.x, b = row / TILE;
+    const double* xs = Smat + (long)row * Np;
+    const double* xd = DT + (long)b * TILE * TILE + (long)(row - b * TILE) * TILE - (long)b * TILE;   // xd[k] valid inside block b
+    const int kblk_end = (b + 1) * TILE;
+    __shared__ double red[8];
+    __shared__ int s_e;
+    double a = 0.0;
+    for (int c = row + threadIdx.x; c < Np; c += 256) a = fmax(a, fabs(c < kblk_end ? xd[c] : xs[c]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a = fmax(a, __shfl_xor_sync(0xffffffffu, a, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) a = fmax(a, red[w]);
+        s_e = scale_exponent(a);
+        inv_scale[row] = ldexp(1.0, s_e + 1);
+    }
+    __syncthreads();
+    const double scale = ldexp(1.0, -(s_e + 1) + I_BITS);
+    const long pitch = (long)Np * Np;
+    int8_t* out = planes + (long)row * Np;
+    // columns left of the row's 128-block are never read (the k range of tile row b starts at b*128)
+    for (int c0 = b * TILE + threadIdx.x * 8; c0 < Np; c0 += 256 * 8) {
+        double r[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int c = c0 + u;
+            r[u] = (c < row) ? 0.0 : (c < kblk_end ? xd[c] : xs[c]) * scale;
+        }
+#pragma unroll
+        for (int j = 0; j < S; ++j) {
+            uint32_t lo = 0, hi = 0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const double q = rint(r[u]);
+                r[u] = (r[u] - q) * 128.0;
+                const uint32_t bb = (uint32_t)(__double2int_rn(q) & 0xff);
+                if (u < 4) lo |= bb << (8 * u); else hi |= bb << (8 * (u - 4));
+            }
+            *reinterpret_cast<uint2*>(out + j * pitch + c0) = make_uint2(lo, hi);
+        }
+    }
+}
+
+size_t lauum_i8_workspace_bytes(int Np, int nslices) { return (size_t)nslices * Np * Np + (size_t)Np * 8; }
+
+// W (lower 128-tiles, full inside the diagonal blocks) = L^-T L^-1 from the mirrored inverse S and the transposed diagonal blocks DT.
+int lauum_i8(const double* Smat, const double* DT, double* W, int Np, int nslices, void* workspace, size_t workspace_bytes,
+             cudaStream_t st) {
+    if (Np % TILE || Np > 32768) return -4;
+    if (nslices < 5 || nslices > I_SMAX) return -5;
+    if (workspace_bytes < lauum_i8_workspace_bytes(Np, nslices)) return -7;
+    double* inv_scale = reinterpret_cast<double*>(workspace);
+    int8_t* planes = reinterpret_cast<int8_t*>(inv_scale + Np);
+    if (nslices == 5) slice_i8_linvT_kernel<5><<<Np, 256, 0, st>>>(Smat, DT, Np, planes, inv_scale);
+    else slice_i8_linvT_kernel<6><<<Np, 256, 0, st>>>(Smat, DT, Np, planes, inv_scale);
+    const bool mc = i8_multicast();
+    if (nslices == 5) return mc ? launch_i8<5, 64, true, true>(planes, inv_scale, Np, planes, Np, nullptr, W, st)
+                                : launch_i8<5, 64, false, true>(planes, inv_scale, Np, planes, Np, nullptr, W, st);
+    return mc ? launch_i8<6, 64, true, true>(planes, inv_scale, Np, planes, Np, nullptr, W, st)
+              : launch_i8<6, 64, false, true>(planes, inv_scale, Np, planes, Np, nullptr, W, st);
 }
 
 }  // namespace gpx

@@ -14,6 +14,7 @@ This module replaces the arithmetic gpytorch performs behind GPErks' call sites
 """
 from __future__ import annotations
 
+import os
 import warnings
 from dataclasses import dataclass
 from typing import Optional, Sequence
@@ -21,6 +22,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _native as nv
+from .constants import AUTO_I8_MAX_N, AUTO_I8_MIN_N, AUTO_I8_SLICES
 
 F64 = torch.float64
 
@@ -88,6 +90,15 @@ class ExactGPEngine:
         self.S_hi: Optional[torch.Tensor] = None      # TF32 mode: (hi, lo) float split of L^-1
         self.S_lo: Optional[torch.Tensor] = None
         self.i8_slices = 0                            # sliced-integer mode: number of int8 slices of L^-1 held (0 = none)
+        # K_hat^-1 = L^-T L^-1 for the gradient: six-slice integer tensor-core product where its tiles pay and its int32 sums
+        # cannot overflow (entries within ~1e-10 of their row/column scale of the DMMA result), else the FP64 DMMA lauum;
+        # GPX_LAUUM=fp64 forces the latter
+        self.lauum_slices = (AUTO_I8_SLICES if (AUTO_I8_MIN_N <= self.N <= AUTO_I8_MAX_N
+                                                and os.environ.get("GPX_LAUUM", "") != "fp64") else 0)
+        self._lauum_ws: Optional[torch.Tensor] = None
+        if self.lauum_slices:       # allocated up front: gradients() may run inside a CUDA-graph capture
+            self._lauum_ws = torch.empty(int(self.lib.gpx_lauum_i8_workspace_bytes(self.Np, self.lauum_slices)),
+                                         dtype=torch.uint8, device=dev)
         self.S_i8: Optional[torch.Tensor] = None      # [slices, Np, Np] int8 planes of L^-1
         self.S_i8_inv_scale: Optional[torch.Tensor] = None   # [Np] inverse power-of-two row scales
 
@@ -158,7 +169,15 @@ class ExactGPEngine:
             st = nv.stream_ptr()
             p = nv.ptr
             if not self.has_kinv:
-                self._launch("gpx_lauum", p(self.S), p(self.DT), p(self.W), self.Np, st)
+                if self.lauum_slices:
+                    # K_hat^-1 on the integer tensor cores (lower 128-tiles only: what gpx_mll_grad reads)
+                    nbytes = int(self.lib.gpx_lauum_i8_workspace_bytes(self.Np, self.lauum_slices))
+                    if self._lauum_ws is None or self._lauum_ws.numel() < nbytes:
+                        self._lauum_ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+                    self._launch("gpx_lauum_i8", p(self.S), p(self.DT), p(self.W), self.Np, self.lauum_slices,
+                                 p(self._lauum_ws), nbytes, st)
+                else:
+                    self._launch("gpx_lauum", p(self.S), p(self.DT), p(self.W), self.Np, st)
                 self.has_kinv = True
             self._launch("gpx_mll_grad", p(self.X), self.N, self.D, p(self.theta), self.kind, p(self.W), self.Np,
                          p(self.alpha), p(self.partial), p(self.grad), st)

@@ -148,6 +148,15 @@ int gpx_kmat_cross_i8(const double* Xs, long m_valid, const double* X, int N, in
                       int Np, double* mean_part, int Mc, void* stream);
 int gpx_trmm_sumsq_i8(const signed char* Ls, const double* inv_scale, int Np, const signed char* Kp, int Mc, int nslices,
                       const double* amax_ptr, double* qpart, void* stream);
+/* gpx_lauum_i8: gpx_lauum on the integer tensor cores.  The columns of L^-1 (rows of L^-T: DT inside the diagonal blocks, the
+ * mirrored blocks of S beside them) are sliced with one power-of-two scale per column into the workspace, and
+ * Kinv = L^-T L^-1 is formed by the same kind::i8 kernel (store epilogue) for the 128-tiles on and below the diagonal -- the
+ * part gpx_mll_grad reads; tiles above the diagonal are NOT written.  Entries agree with gpx_lauum to ~1e-10 of the scale
+ * of their row and column (6 slices).  Np <= 32768.
+ * replaces: the K_hat^-1 of loss.backward(), GPErks/train/emulator.py:327. */
+size_t gpx_lauum_i8_workspace_bytes(int Np, int nslices);
+int gpx_lauum_i8(const double* S, const double* DT, double* Kinv, int Np, int nslices, void* workspace, size_t workspace_bytes,
+                 void* stream);
 size_t gpx_predict_i8_workspace_bytes(int Np, int Mc, int nslices);
 int gpx_predict_meanvar_i8(const double* Xs, long M, const double* X, int N, int D, const double* theta, const double* xa,
                            const double* xr, int kind, const signed char* Ls, const double* inv_scale, int nslices, int Np,

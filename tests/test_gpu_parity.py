@@ -93,7 +93,10 @@ def test_mid_size_mll_and_gradients_against_oracle_on_device(dev, N, D, kind):
     assert float((eng.linv() - Linv).abs().max() / Linv.abs().max()) < 1e-9
     got = eng.gradients().cpu()
     Kinv = torch.cholesky_inverse(L)
-    assert float((eng.W[:N, :N] - Kinv).abs().max() / Kinv.abs().max()) < 1e-8
+    # the integer-tensor-core lauum (default at these sizes) forms only the 128-tiles on and below the diagonal
+    blk = torch.arange(N, device=dev) // 128
+    low = (blk.view(-1, 1) >= blk.view(1, -1)) if eng.lauum_slices else torch.ones(N, N, dtype=torch.bool, device=dev)
+    assert float(((eng.W[:N, :N] - Kinv).abs() * low).max() / Kinv.abs().max()) < 1e-8
     del Kinv, Linv, K, L
     g = O.neg_mll_analytic_grads(X, y, kind, ls, s, torch.tensor(nz, dtype=F64), X @ w + b)       # CPU oracle, a few seconds
     gref = torch.cat([g["lengthscale"], g["outputscale"].reshape(1), g["noise"].reshape(1)])
@@ -625,6 +628,35 @@ def test_int8_mode_within_fp64_tolerance(dev, N, D, M, kind, nz):
     eng.factorize(eng.theta_in.clone() * 1.0, eng.r[:N].clone() * 2.0)
     _, s6 = eng.predict(Xs.to(dev), prior_mean=pm, precision="int8x6")
     assert float(((s6 - s64).abs() / s64).max()) < 2e-7
+
+
+@pytest.mark.parametrize("N,D,kind,nz", [(1100, 5, O.KIND_MATERN52, 1e-2), (2048, 6, O.KIND_RBF, 1e-4), (1300, 3, O.KIND_MATERN32, 1e-3)])
+def test_int8_lauum_matches_fp64_lauum(dev, N, D, kind, nz):
+    """K_hat^-1 = L^-T L^-1 on the integer tensor cores (the engine's default for 1024 <= N <= 32768) against the FP64 DMMA
+    lauum on the same factors: the lower 128-tiles that the gradient reduction reads, and the gradients themselves."""
+    lib = nv.lib()
+    X, y, Xs, ls, s, w, b = _problem(N, D, 10, seed=N)
+    eng = _engine(dev, X, y, kind, ls, s, nz, w, b)
+    assert eng.lauum_slices == 6
+    g8 = eng.gradients().clone()
+    W8 = eng.W.clone()
+    nv.check(lib.gpx_lauum(nv.ptr(eng.S), nv.ptr(eng.DT), nv.ptr(eng.W), eng.Np, nv.stream_ptr()), "lauum")
+    W64 = eng.W.clone()
+    eng.lauum_slices, eng.has_kinv = 0, True
+    g64 = eng.gradients().clone()
+    Np = eng.Np
+    blk = torch.arange(Np, device=dev) // 128
+    low = blk.view(-1, 1) >= blk.view(1, -1)               # 128-tiles on and below the diagonal
+    scale = W64.diagonal().abs().sqrt()
+    rel = ((W8 - W64).abs() / (scale.view(-1, 1) * scale.view(1, -1)))[low]
+    assert float(rel.max()) < 1e-9, float(rel.max())
+    np.testing.assert_allclose(g8.cpu().numpy(), g64.cpu().numpy(), rtol=1e-8, atol=1e-11 * float(g64.abs().max()))
+    # five slices through the C ABI
+    ws = torch.empty(int(lib.gpx_lauum_i8_workspace_bytes(Np, 5)), dtype=torch.uint8, device=dev)
+    W5 = torch.zeros_like(W64)
+    nv.check(lib.gpx_lauum_i8(nv.ptr(eng.S), nv.ptr(eng.DT), nv.ptr(W5), Np, 5, nv.ptr(ws), ws.numel(), nv.stream_ptr()), "lauum_i8")
+    rel5 = ((W5 - W64).abs() / (scale.view(-1, 1) * scale.view(1, -1)))[low]
+    assert float(rel5.max()) < 2e-7, float(rel5.max())
 
 
 def test_emulator_auto_precision(dev):

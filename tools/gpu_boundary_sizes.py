@@ -19,6 +19,7 @@ for N in sizes:
     ls = torch.tensor([0.5 * (1 + d / D) for d in range(D)], dtype=F64, device=dev)
     theta = torch.cat([1.0 / ls, torch.tensor([1.2, 1e-2], dtype=F64, device=dev)])
     eng = ExactGPEngine(X, 3)
+    eng.lauum_slices = 0          # this tool checks the FP64 lauum (full symmetric K^-1)
     eng.factorize(theta, y)
     eng.gradients()
     K = torch.empty(N, N, dtype=F64, device=dev)

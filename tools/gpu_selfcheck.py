@@ -89,6 +89,7 @@ def check(N, D, kind, M, noise=1e-2, seed=0, timing=True):
     mean_x = Xd @ w.to(dev) + b.to(dev)
     resid = yd - mean_x
     eng = ExactGPEngine(Xd, kind)
+    eng.lauum_slices = 0          # this tool checks the FP64 lauum (full symmetric K^-1)
     theta = torch.cat([1.0 / lsd, sd.reshape(1), nzd.reshape(1)])
     t0 = time.time()
     eng.factorize(theta, resid)
