@@ -11,7 +11,10 @@ A step = one pass of the predict hot path over M points per GPU (weak scaling: e
 shard; factors L^-1 and alpha are replicated; the only collective is the final gather of the 16 B/point
 results).  `value` = points all ranks processed / max-over-ranks device time with X* resident in HBM;
 `e2e` = the same through GPEmulator.predict with host numpy buffers (pinned H2D + D2H inside the timed
-region).  One JSON line on stdout (rank 0)."""
+region).  Both run at the precision GPEmulator.predict uses by default for this emulator (`--precision auto`: the
+FP64 variance contraction from six 7-bit integer slices on tcgen05 kind::i8, std within 1e-8 of the FP64 DMMA path,
+reported under `accuracy`); the FP64 DMMA path itself is timed beside it (`fp64_dmma_mode`, or `--precision fp64` to
+make it the headline), as are the TF32 mode and the five-slice edition.  One JSON line on stdout (rank 0)."""
 from __future__ import annotations
 
 import argparse
@@ -257,16 +260,24 @@ def main():
     eng = em.model._factorized_engine()
     torch.cuda.synchronize()
     theta, resid = eng.theta_in.clone(), eng.r[:eng.N].clone()
-    mll_ms = []
-    for i in range(args.mll_evals + 1 if args.mll_evals > 0 else 0):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        eng.factorize(theta, resid)
-        eng.gradients()
-        b.record()
-        torch.cuda.synchronize()
-        if i > 0:
-            mll_ms.append(a.elapsed_time(b))
+    def time_mll():
+        ms = []
+        for i in range(args.mll_evals + 1 if args.mll_evals > 0 else 0):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            eng.factorize(theta, resid)
+            eng.gradients()
+            b.record()
+            torch.cuda.synchronize()
+            if i > 0:
+                ms.append(a.elapsed_time(b))
+        return ms
+    mll_ms = time_mll()                      # the engine's default: K_hat^-1 on the integer tensor cores at this size
+    lauum_default = eng.lauum_slices
+    eng.lauum_slices = 0                     # all-FP64 edition (DMMA lauum) beside it
+    mll_ms_fp64 = time_mll() if lauum_default else mll_ms
+    eng.lauum_slices = lauum_default
+    eng.factorize(theta, resid)
 
     # ---- device-resident arm (`value`)
     scx, scy = em.scaled_data.scx, em.scaled_data.scy
@@ -576,7 +587,9 @@ def main():
         "fp64_dmma_mode": {"value": f64_value, "unit": "points/s", "ms_per_step": f64_ms / args.steps, "roofline": fp64_roofline,
                            "note": "precision='fp64': the same predict with the variance contraction on the FP64 tensor path (DMMA)"},
         "mll_grad": ({"evals_per_s": 1e3 / (sum(mll_ms) / len(mll_ms)), "ms_per_eval": sum(mll_ms) / len(mll_ms),
-                      "n_train": eng.N, "what": "K_hat build + Cholesky + L^-1 + alpha + -mll + K_hat^-1 + gradient reduce"}
+                      "n_train": eng.N, "what": "K_hat build + Cholesky + L^-1 + alpha + -mll + K_hat^-1 + gradient reduce",
+                      "k_inverse": (f"int8x{lauum_default} slices on tcgen05 kind::i8 (gpx_lauum_i8)" if lauum_default else "FP64 DMMA lauum"),
+                      "ms_per_eval_all_fp64": sum(mll_ms_fp64) / len(mll_ms_fp64)}
                      if mll_ms else None),
         "tf32_mode": tf32,
         "int8_mode": int8,
