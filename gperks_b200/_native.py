@@ -57,6 +57,7 @@ _SIGS = {
                                          _P, _P, C.c_size_t, C.c_int, _P]),
     "gpx_implausibility": (C.c_int, [_P, _P, C.c_long, C.c_int, _P, _P, C.c_int, _P, _P, _P]),
     "gpx_peak_dmma": (C.c_double, [C.c_int, C.c_int, _P, _P]),
+    "gpx_peak_i8mma": (C.c_double, [C.c_int, C.c_int, _P]),
     "gpx_peak_dfma": (C.c_double, [C.c_int, C.c_int, _P, _P]),
 }
 EXPORTS = tuple(_SIGS)

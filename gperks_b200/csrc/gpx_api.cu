@@ -22,6 +22,7 @@ int trmm_sumsq_tf32(const float*, const float*, int, const float*, const float*,
 int tf32_row_tiles(int);
 size_t predict_tf32_workspace_bytes(int, int);
 int slice_i8_matrix(const double*, int, int, long, int8_t*, long, int, int, double*, const double*, cudaStream_t);
+double peak_i8mma(int, int, cudaStream_t);
 size_t lauum_i8_workspace_bytes(int, int);
 int lauum_i8(const double*, const double*, double*, int, int, void*, size_t, cudaStream_t);
 int kmat_cross_i8(const double*, long, const double*, int, int, const double*, const double*, const double*, int, const double*,
@@ -288,6 +289,7 @@ double gpx_peak_dmma(int blocks, int iters, double* sink, void* stream) {
     // per warp per iter: 16 DMMA x (8*8*4 FMA) x 2 FLOP
     return (double)blocks * 8.0 * iters * 16.0 * 512.0;
 }
+double gpx_peak_i8mma(int blocks, int iters, void* stream) { return peak_i8mma(blocks, iters, ST(stream)); }
 double gpx_peak_dfma(int blocks, int iters, double* sink, void* stream) {
     peak_dfma_kernel<<<blocks, 256, 0, ST(stream)>>>(iters, sink);
     return (double)blocks * 256.0 * iters * 16.0 * 2.0;

@@ -493,4 +493,50 @@ int lauum_i8(const double* Smat, const double* DT, double* W, int Np, int nslice
               : launch_i8<6, 64, false, true>(planes, inv_scale, Np, planes, Np, nullptr, W, st);
 }
 
+// ---- roofline probe: the rate at which one SM retires kind::i8 MMAs from shared memory that is already resident ----
+// (no TMA, no epilogue): M = 128, N = 256, K = 32 per instruction into one 256-column accumulator.
+__global__ void __launch_bounds__(64, 1) peak_i8mma_kernel(int iters) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bar = reinterpret_cast<uint64_t*>(base + 24576);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+    for (int i = threadIdx.x; i < 24576 / 4; i += blockDim.x) {       // pseudo-random 7-bit slices: realistic operand toggling
+        uint32_t h = (uint32_t)i * 2654435761u + blockIdx.x * 40503u;
+        h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+        reinterpret_cast<uint32_t*>(base)[i] = h & 0x3f3f3f3fu;
+    }
+    if (threadIdx.x == 0) { mbar_init(smem_u32(bar), 1); mbar_fence_init(); }
+    if (threadIdx.x < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");     // generic-proxy stores above -> visible to the tensor core
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = *tmem_slot;
+    if (threadIdx.x == 0) {
+        const uint64_t da = umma_desc_kmajor<64>(smem_u32(base)), db = umma_desc_kmajor<64>(smem_u32(base) + 8192);
+        const uint32_t idesc = i8_idesc(256);
+        for (int it = 0; it < iters; ++it) {
+            umma_i8(tmem_d, da, db, idesc, it != 0);
+            umma_i8(tmem_d, da + 2, db + 2, idesc, 1u);
+        }
+        umma_commit(smem_u32(bar));
+        mbar_wait(smem_u32(bar), 0);
+        tc_fence_after();
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "n"(512) : "memory");
+    }
+}
+
+// returns the int8 operations issued (2 per multiply-add)
+double peak_i8mma(int blocks, int iters, cudaStream_t st) {
+    cudaFuncSetAttribute(peak_i8mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768);
+    peak_i8mma_kernel<<<blocks, 64, 32768, st>>>(iters);
+    return (double)blocks * iters * 2.0 * (128.0 * 256.0 * 32.0 * 2.0);
+}
+
 }  // namespace gpx

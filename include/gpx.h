@@ -174,6 +174,9 @@ int gpx_implausibility(const double* mean, const double* std_, long M, int E, co
 /* Microbenchmarks for the roofline denominators: enqueue `iters` dependent-chain-free DMMA.8x8x4
  * (or DFMA) per warp on `blocks` CTAs of 256 threads; returns the FLOP count of the launch. */
 double gpx_peak_dmma(int blocks, int iters, double* sink, void* stream);
+/* kind::i8 MMA issue rate from resident shared memory (M=128, N=256, K=32, one CTA per SM when blocks = #SMs): returns the int8
+ * operations issued; divide by the measured duration. */
+double gpx_peak_i8mma(int blocks, int iters, void* stream);
 double gpx_peak_dfma(int blocks, int iters, double* sink, void* stream);
 
 #ifdef __cplusplus
