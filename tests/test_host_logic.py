@@ -65,6 +65,31 @@ def test_product_path_fails_loudly_without_cuda():
         em.model.covar_module(torch.rand(3, 2)).to_dense()
 
 
+def test_auto_precision_is_resolved_from_host_values():
+    """precision="auto" (GPEmulator.predict's default) -> the sliced-integer path only where its int32 sums cannot overflow,
+    the tiles pay and outputscale/noise leaves the slicing error inside 1e-6; host-side values only, no CUDA call."""
+    from gperks_b200 import constants as K
+    rng = np.random.default_rng(0)
+
+    def emulator(n):
+        X = rng.random((n, 3))
+        exp = GPExperiment(Dataset(X, X.sum(1)), GaussianLikelihood(), LinearMean(1, 3), ScaleKernel(MaternKernel(ard_num_dims=3)),
+                           n_restarts=1, seed=8)
+        return GPEmulator(exp, "cpu")
+    small, big = emulator(K.AUTO_I8_MIN_N - 1), emulator(K.AUTO_I8_MIN_N)
+    assert small.resolve_precision("auto") == "fp64"
+    big.model.covar_module.outputscale = 1.0
+    big.model.likelihood.noise = 1e-2
+    assert big.resolve_precision("auto") == f"int8x{K.AUTO_I8_SLICES}"
+    big.model.likelihood.noise = 1e-3
+    big.model.covar_module.outputscale = 0.99e-3 * K.AUTO_I8_MAX_SCALE_TO_NOISE
+    assert big.resolve_precision("auto") == f"int8x{K.AUTO_I8_SLICES}"
+    big.model.covar_module.outputscale = 1.01e-3 * K.AUTO_I8_MAX_SCALE_TO_NOISE          # outputscale / noise above the limit
+    assert big.resolve_precision("auto") == "fp64"
+    for p in ("fp64", "int8x5", "int8x6", "tf32x3", "tf32x3_fast"):
+        assert big.resolve_precision(p) == p
+
+
 def test_product_never_imports_oracle():
     for path in (ROOT / "gperks_b200").rglob("*.py"):
         text = path.read_text()
