@@ -32,7 +32,19 @@ for rep in range(2):
     torch.cuda.synchronize()
     res["mll_grad_ms"] = a.elapsed_time(b)
 res["loss"] = float(eng.loss)
+res["k_inverse"] = f"int8x{eng.lauum_slices}" if eng.lauum_slices else "fp64 DMMA"
 res["mll_grad_tflops"] = N ** 3 / res["mll_grad_ms"] / 1e9
+if eng.lauum_slices:        # the all-FP64 edition beside it
+    keep, eng.lauum_slices = eng.lauum_slices, 0
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    eng.factorize(theta, y)
+    gr64 = eng.gradients().clone()
+    b.record()
+    torch.cuda.synchronize()
+    res["mll_grad_ms_all_fp64"] = a.elapsed_time(b)
+    res["grad_rel_diff_int8_vs_fp64_lauum"] = float((gr - gr64).abs().max() / gr64.abs().max())
+    eng.lauum_slices = keep
 # checker: cuSOLVER Cholesky of the same matrix, built in row blocks to bound memory
 K = torch.empty(N, N, dtype=F64, device=dev)
 for lo in range(0, N, 2048):
@@ -51,7 +63,7 @@ res["chol_rel_err"] = float((eng.chol() - L).abs().max() / L.abs().max())
 M = 65536
 Xs = torch.rand(M, D, dtype=F64, device=dev)
 pm = torch.zeros(M, dtype=F64, device=dev)
-for prec in ("fp64", "tf32x3"):
+for prec in ("fp64", "int8x6", "tf32x3"):
     eng.predict(Xs[:4096], prior_mean=pm[:4096], precision=prec)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
@@ -67,6 +79,6 @@ for prec in ("fp64", "tf32x3"):
         res["pred_std_rel_err"] = float(((std[:2048] - vref.sqrt()).abs() / vref.sqrt()).max())
         res["pred_mean_rel_err"] = float((mean[:2048] - Ks @ alpha).abs().max() / (Ks @ alpha).abs().max())
     else:
-        res["tf32_std_rel_err"] = float(((std - s64).abs() / s64).max())
+        res[f"{prec}_std_rel_err"] = float(((std - s64).abs() / s64).max())
 res["gpu_mem_GB"] = torch.cuda.max_memory_allocated() / 1e9
 print(json.dumps(res))
