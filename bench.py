@@ -277,6 +277,11 @@ def main():
     eng.lauum_slices = 0                     # all-FP64 edition (DMMA lauum) beside it
     mll_ms_fp64 = time_mll() if lauum_default else mll_ms
     eng.lauum_slices = lauum_default
+    mll_ms_i8_trtri = None
+    if getattr(eng, "_trtri_i8_capable", False):      # experimental, opt-in: the top merge levels of the inverse on the integer tensor cores too
+        eng.trtri_i8 = True
+        mll_ms_i8_trtri = time_mll()
+        eng.trtri_i8 = False
     eng.factorize(theta, resid)
 
     # ---- device-resident arm (`value`)
@@ -622,7 +627,10 @@ def main():
         "mll_grad": ({"evals_per_s": 1e3 / (sum(mll_ms) / len(mll_ms)), "ms_per_eval": sum(mll_ms) / len(mll_ms),
                       "n_train": eng.N, "what": "K_hat build + Cholesky + L^-1 + alpha + -mll + K_hat^-1 + gradient reduce",
                       "k_inverse": (f"int8x{lauum_default} slices on tcgen05 kind::i8 (gpx_lauum_i8)" if lauum_default else "FP64 DMMA lauum"),
-                      "ms_per_eval_all_fp64": sum(mll_ms_fp64) / len(mll_ms_fp64)}
+                      "ms_per_eval_all_fp64": sum(mll_ms_fp64) / len(mll_ms_fp64),
+                      "ms_per_eval_experimental_i8_trtri": (sum(mll_ms_i8_trtri) / len(mll_ms_i8_trtri)) if mll_ms_i8_trtri else None,
+                      "experimental_i8_trtri_note": "opt-in (GPX_TRTRI=i8): L^-1 accurate to ~1e-8 of its norm -- enough for loss and "
+                                                    "gradients, not for the predictive variance at small noise; not used by any other number here"}
                      if mll_ms else None),
         "tf32_mode": tf32,
         "int8_mode": int8,

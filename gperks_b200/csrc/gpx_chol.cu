@@ -1457,7 +1457,28 @@ static int inverse_narrow_tiles() {       // GPX_INV_NARROW=0: 128-row tiles onl
     return v;
 }
 
+// gpx_i8.cu: one merge level on the integer tensor cores
+int trtri_i8_merge(const double* L, double* Smat, const double* DT, double* W, int Np, int left, int h, int hr, void* workspace,
+                   cudaStream_t st);
+size_t trtri_i8_workspace_bytes(int Np, int nslices);
+constexpr int TRTRI_I8_MIN_H = 8;        // merge levels whose segments have >= 1024 rows run as sliced-integer GEMMs
+
+static int trtri_impl(const double* L, double* S, const double* DT, double* W, int Np, void* i8_ws, cudaStream_t st);
+
 int trtri(const double* L, double* S, const double* DT, double* W, int Np, cudaStream_t st) {
+    return trtri_impl(L, S, DT, W, Np, nullptr, st);
+}
+
+// As trtri; the top merge levels (segments of >= 1024 rows) run on the integer tensor cores from six 7-bit slices per operand
+// (entries of L^-1 then agree with the all-FP64 result to ~1e-11 of their row/column scales).
+int trtri_i8(const double* L, double* S, const double* DT, double* W, int Np, void* workspace, size_t workspace_bytes,
+             cudaStream_t st) {
+    if (Np > 32768) return -4;
+    if (workspace_bytes < trtri_i8_workspace_bytes(Np, 6)) return -7;
+    return trtri_impl(L, S, DT, W, Np, workspace, st);
+}
+
+static int trtri_impl(const double* L, double* S, const double* DT, double* W, int Np, void* i8_ws, cudaStream_t st) {
     set_gemm_attrs();
     const int nb = Np / TILE;
     const bool tma = use_chol_tma();
@@ -1478,7 +1499,15 @@ int trtri(const double* L, double* S, const double* DT, double* W, int Np, cudaS
         const int pairs = (nb + 2 * h - 1) / (2 * h);
         dim3 grid(h, h, pairs);
         const int tiles = pairs * h * h;
-        if (tma && narrow && tiles <= 300) {             // 32-row strips
+        if (i8_ws != nullptr && h >= TRTRI_I8_MIN_H) {
+            for (int q = 0; q < pairs; ++q) {
+                const int left = 2 * h * q, right = left + h;
+                if (right >= nb) continue;
+                const int hr = (nb - right) < h ? (nb - right) : h;
+                const int rc = trtri_i8_merge(L, S, DT, W, Np, left, h, hr, i8_ws, st);
+                if (rc) return rc;
+            }
+        } else if (tma && narrow && tiles <= 300) {             // 32-row strips
             dim3 g(pairs, 4 * h, h);
             trtri_step1_narrow_kernel<1, 4, 2><<<g, GT_THREADS, GT_SMEM_BYTES, st>>>(tmK32, tmS, tmD, W, Np, nb, h);
             trtri_step2_narrow_kernel<1, 4, 2><<<g, GT_THREADS, GT_SMEM_BYTES, st>>>(tmS32, tmW, S, Np, nb, h);

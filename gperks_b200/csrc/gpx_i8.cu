@@ -493,6 +493,261 @@ int lauum_i8(const double* Smat, const double* DT, double* W, int Np, int nslice
               : launch_i8<6, 64, false, true>(planes, inv_scale, Np, planes, Np, nullptr, W, st);
 }
 
+// ---- general sliced-integer NT product with a store epilogue (the merge steps of the recursive triangular inverse) ----
+//   C[c_row0 + i][c_col0 + j] = sign * sum_{k in range(i)} A[a_row0 + i][k] * B[b_row0 + j][k]      (+ the same value at C2[j][i])
+// A (MMA M side, 128-row tiles mi) and B (N side, 64-row tiles nj) are int8 slice planes [S][Np][Np] with per-row scales;
+// the k range of tile row mi is [k_base + 128 mi, k_end) (k_from = 1: operand rows that start at their own diagonal block)
+// or [k_base, k_base + 128 (mi + 1)) (k_from = 0: rows that end there).  Same pipeline as trmm_sumsq_i8_kernel<S, 64, true>:
+// clusters of two CTAs on neighbouring N tiles share the M-side tile through TMA multicast.
+struct I8Gemm {
+    int n_nj;                   // N tiles (even)
+    int a_row0, b_row0;
+    int k_base, k_end, k_from;
+    int c_row0, c_col0;
+    int m_row0, m_col0;         // mirror C2[m_row0 + j][m_col0 + i]; m_row0 < 0: none
+    double sign;
+};
+
+template <int S>
+__global__ void __launch_bounds__(I_THREADS, 1)
+gemm_i8_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmB, int Np,
+               const double* __restrict__ sa, const double* __restrict__ sb, double* __restrict__ Cout,
+               double* __restrict__ Cmir, const I8Gemm g) {
+    using C = I8Cfg<S, 64>;
+    constexpr int BKB = 64;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + size_t(C::STAGES) * C::STAGE_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 1);
+    double* sinv = reinterpret_cast<double*>(bars + 2 * C::STAGES + 2);      // [64]
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + C::STAGES), acc_full = smem_u32(bars + 2 * C::STAGES);
+    const uint32_t tile0 = smem_u32(base);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t crank = cluster_ctarank();
+    const int pairs = g.n_nj / 2;
+    const int cid = (int)(blockIdx.x >> 1);
+    const int mi = cid / pairs, nj = 2 * (cid - mi * pairs) + (int)crank;
+    const int kstart = g.k_from ? g.k_base + mi * I_M : g.k_base;
+    const int kend = g.k_from ? g.k_end : g.k_base + (mi + 1) * I_M;
+    const int nk = (kend - kstart) / BKB;
+    const int arow = g.a_row0 + mi * I_M, brow = g.b_row0 + nj * I_N;
+
+    if (tid == 0) {
+        for (int s = 0; s < C::STAGES; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, 2);
+        }
+        mbar_init(acc_full, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "n"(I_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    if (tid < I_N) sinv[tid] = sb[brow + tid] * ldexp(1.0, -2 * I_BITS);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_d = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            tma_prefetch_desc(&tmAh); tma_prefetch_desc(&tmB);
+            for (int kt = 0; kt < nk; ++kt) {
+                const int s = kt % C::STAGES, round = kt / C::STAGES;
+                if (round > 0) mbar_wait(empty0 + 8 * s, (round - 1) & 1);
+                mbar_arrive_expect_tx(full0 + 8 * s, C::STAGE_BYTES);
+                const uint32_t dst = tile0 + s * C::STAGE_BYTES;
+                const int k0 = kstart + kt * BKB;
+#pragma unroll
+                for (int j = 0; j < S; ++j)
+                    tma_load_2d_multicast(dst + j * C::A_BYTES + crank * (C::A_BYTES / 2), &tmAh, k0,
+                                          j * Np + arow + (int)crank * (I_M / 2), full0 + 8 * s, 3);
+#pragma unroll
+                for (int j = 0; j < S; ++j)
+                    tma_load_2d(dst + S * C::A_BYTES + j * C::B_BYTES, &tmB, k0, j * Np + brow, full0 + 8 * s);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            for (int kt = 0; kt < nk; ++kt) {
+                const int s = kt % C::STAGES, round = kt / C::STAGES;
+                mbar_wait(full0 + 8 * s, round & 1);
+                tc_fence_after();
+                const uint32_t st = tile0 + s * C::STAGE_BYTES;
+#pragma unroll
+                for (int kk = 0; kk < BKB / 32; ++kk) {
+                    const uint64_t adv = (uint64_t)((kk * 32) >> 4);
+#pragma unroll
+                    for (int a = 0; a < S; ++a) {
+                        const uint64_t da = umma_desc_kmajor<BKB>(st + a * C::A_BYTES) + adv;
+                        const int ncols = (S - a) * I_N;
+#pragma unroll
+                        for (int c0 = 0; c0 < ncols; c0 += 256) {
+                            const int w = (ncols - c0) < 256 ? (ncols - c0) : 256;
+                            const uint64_t db = umma_desc_kmajor<BKB>(st + S * C::A_BYTES + (c0 / I_N) * C::B_BYTES) + adv;
+                            umma_i8(tmem_d + (uint32_t)(a * I_N + c0), da, db, i8_idesc(w), (kt | kk | a) != 0 ? 1u : 0u);
+                        }
+                    }
+                }
+                umma_commit_multicast(empty0 + 8 * s, 3);
+            }
+            umma_commit(acc_full);
+        }
+    } else {
+        const int quad = warp & 3, half = (warp - 2) >> 2;
+        const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        double t[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) t[j] = 0.0;
+#pragma unroll
+        for (int gi = S - 1; gi >= 0; --gi) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(tmem_d + lane_base + (uint32_t)(gi * I_N + half * 32), v);
+            tmem_wait_ld();
+            const double wg = 1.0 / (double)(1ull << (I_BITS * gi));
+#pragma unroll
+            for (int j = 0; j < 32; ++j) t[j] = fma((double)(int)v[j], wg, t[j]);
+        }
+        const int r = quad * 32 + lane;
+        const double si = sa[arow + r] * g.sign;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) t[j] *= sinv[half * 32 + j] * si;
+        double* dst = Cout + (long)(g.c_row0 + mi * I_M + r) * Np + g.c_col0 + nj * I_N + half * 32;
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) *reinterpret_cast<double2*>(dst + j) = make_double2(t[j], t[j + 1]);
+        if (g.m_row0 >= 0) {       // transposed copy: consecutive lanes write consecutive doubles of one mirror row
+            double* mir = Cmir + (long)(g.m_row0 + nj * I_N + half * 32) * Np + g.m_col0 + mi * I_M + r;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mir[(long)j * Np] = t[j];
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "n"(I_TMEM_COLS) : "memory");
+    }
+}
+
+// Rows [r0, r0 + gridDim.x) of a row-major FP64 matrix -> int8 slices over the live columns [lo(r), hi(r)):
+//   lo(r) = lo_row ? r : c0,  hi(r) = hi_row ? r + 1 : c1;  the written range is the enclosing 128-aligned one, zero outside
+//   the live part.  DT != null: inside the row's own 128-block the value comes from DT[block][r % 128][c % 128].
+template <int S>
+__global__ void __launch_bounds__(256) slice_i8_rows_kernel(const double* __restrict__ src, long ld, const double* __restrict__ DT,
+                                                            int r0, int c0, int c1, int lo_row, int hi_row, int Np,
+                                                            int8_t* __restrict__ planes, double* __restrict__ inv_scale) {
+    const int row = r0 + blockIdx.x, b = row / TILE;
+    const double* xs = src + (long)row * ld;
+    const double* xd = DT ? DT + (long)b * TILE * TILE + (long)(row - b * TILE) * TILE - (long)b * TILE : nullptr;
+    const int lo = lo_row ? row : c0, hi = hi_row ? row + 1 : c1;
+    const int wlo = lo_row ? b * TILE : c0, whi = hi_row ? (b + 1) * TILE : c1;
+    const int blo = b * TILE, bhi = (b + 1) * TILE;
+    __shared__ double red[8];
+    __shared__ int s_e;
+    double a = 0.0;
+    for (int c = lo + threadIdx.x; c < hi; c += 256) a = fmax(a, fabs((xd && c >= blo && c < bhi) ? xd[c] : xs[c]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a = fmax(a, __shfl_xor_sync(0xffffffffu, a, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) a = fmax(a, red[w]);
+        s_e = scale_exponent(a);
+        inv_scale[row] = ldexp(1.0, s_e + 1);
+    }
+    __syncthreads();
+    const double scale = ldexp(1.0, -(s_e + 1) + I_BITS);
+    const long pitch = (long)Np * Np;
+    int8_t* out = planes + (long)row * Np;
+    for (int cc = wlo + threadIdx.x * 8; cc < whi; cc += 256 * 8) {
+        double r[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int c = cc + u;
+            r[u] = (c >= lo && c < hi) ? ((xd && c >= blo && c < bhi) ? xd[c] : xs[c]) * scale : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < S; ++j) {
+            uint32_t l32 = 0, h32 = 0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const double q = rint(r[u]);
+                r[u] = (r[u] - q) * 128.0;
+                const uint32_t bb = (uint32_t)(__double2int_rn(q) & 0xff);
+                if (u < 4) l32 |= bb << (8 * u); else h32 |= bb << (8 * (u - 4));
+            }
+            *reinterpret_cast<uint2*>(out + j * pitch + cc) = make_uint2(l32, h32);
+        }
+    }
+}
+
+size_t trtri_i8_workspace_bytes(int Np, int nslices) { return 2 * ((size_t)nslices * Np * Np + (size_t)Np * 8); }
+
+template <int S>
+static int launch_gemm_i8(const int8_t* PA, const int8_t* PB, int Np, const double* sa, const double* sb, double* Cout, double* Cmir,
+                          const I8Gemm& g, int n_mi, cudaStream_t st) {
+    using C = I8Cfg<S, 64>;
+    static bool attr[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!(dev >= 0 && dev < 64 && attr[dev])) {
+        cudaFuncSetAttribute(gemm_i8_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+        if (dev >= 0 && dev < 64) attr[dev] = true;
+    }
+    CUtensorMap tmAh, tmB;
+    int rc;
+    if ((rc = encode_u8_rowmajor(&tmAh, PA, (uint64_t)S * Np, Np, 64, I_M / 2))) return rc;
+    if ((rc = encode_u8_rowmajor(&tmB, PB, (uint64_t)S * Np, Np, 64, I_N))) return rc;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(n_mi * g.n_nj);
+    cfg.blockDim = dim3(I_THREADS);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_i8_kernel<S>, tmAh, tmB, Np, sa, sb, Cout, Cmir, g);
+    return e == cudaSuccess ? 0 : -1000 - (int)e;
+}
+
+// One merge level of the recursive inverse (gpx_chol.cu: trtri) for the pair of segments [left, left+h) | [right, right+hr) (in
+// 128-blocks) on the integer tensor cores:  T = L[right,left] A^-1 (stored transposed in W), X21 = -C^-1 T -> S (+ mirror).
+int trtri_i8_merge(const double* L, double* Smat, const double* DT, double* W, int Np, int left, int h, int hr, void* workspace,
+                   cudaStream_t st) {
+    constexpr int S = 6;
+    const size_t plane_bytes = (size_t)S * Np * Np;
+    double* sA = reinterpret_cast<double*>(workspace);
+    double* sB = sA + Np;
+    int8_t* PA = reinterpret_cast<int8_t*>(sB + Np);
+    int8_t* PB = PA + plane_bytes;
+    const int right = left + h;
+    const int l0 = left * TILE, r0 = right * TILE, r1 = (right + hr) * TILE;
+    // step 1: M side = columns of A^-1 as rows (left segment, k from the row to the end of the segment), N side = L[right, left]
+    slice_i8_rows_kernel<S><<<h * TILE, 256, 0, st>>>(Smat, Np, DT, l0, 0, r0, 1, 0, Np, PA, sA);
+    slice_i8_rows_kernel<S><<<hr * TILE, 256, 0, st>>>(L, Np, nullptr, r0, l0, r0, 0, 0, Np, PB, sB);
+    I8Gemm g1 = {2 * hr, l0, r0, l0, r0, 1, l0, r0, -1, 0, 1.0};
+    int rc = launch_gemm_i8<S>(PA, PB, Np, sA, sB, W, nullptr, g1, h, st);
+    if (rc) return rc;
+    // step 2: M side = rows of C^-1 (right segment, k from the segment start to the row), N side = T^T = W[left, right]
+    slice_i8_rows_kernel<S><<<hr * TILE, 256, 0, st>>>(Smat, Np, nullptr, r0, r0, 0, 0, 1, Np, PA, sA);
+    slice_i8_rows_kernel<S><<<h * TILE, 256, 0, st>>>(W, Np, nullptr, l0, r0, r1, 0, 0, Np, PB, sB);
+    I8Gemm g2 = {2 * h, r0, l0, r0, r1, 0, r0, l0, l0, r0, -1.0};
+    rc = launch_gemm_i8<S>(PA, PB, Np, sA, sB, Smat, Smat, g2, hr, st);
+    if (rc) return rc;
+    GPX_CHECK_LAUNCH();
+    return 0;
+}
+
 // ---- roofline probe: the rate at which one SM retires kind::i8 MMAs from shared memory that is already resident ----
 // (no TMA, no epilogue): M = 128, N = 256, K = 32 per instruction into one 256-column accumulator.
 __global__ void __launch_bounds__(64, 1) peak_i8mma_kernel(int iters) {

@@ -95,10 +95,18 @@ class ExactGPEngine:
         # GPX_LAUUM=fp64 forces the latter
         self.lauum_slices = (AUTO_I8_SLICES if (AUTO_I8_MIN_N <= self.N <= AUTO_I8_MAX_N
                                                 and os.environ.get("GPX_LAUUM", "") != "fp64") else 0)
+        # EXPERIMENTAL, opt-in (GPX_TRTRI=i8 or engine.trtri_i8 = True before factorize): the merge levels of the recursive inverse
+        # with segments of >= 1024 rows on the integer tensor cores as well.  L^-1 then carries ~1e-8 of its norm (six slices,
+        # errors compound over the levels) instead of ~1e-13 -- enough for the loss and its gradients, NOT for the predictive
+        # variance at small noise (amplification ~ outputscale / noise), so it is off by default.
+        self.trtri_i8 = bool(self.lauum_slices and self.Np >= 2048 and os.environ.get("GPX_TRTRI", "") == "i8")
+        self._trtri_i8_capable = bool(self.lauum_slices and self.Np >= 2048)
         self._lauum_ws: Optional[torch.Tensor] = None
-        if self.lauum_slices:       # allocated up front: gradients() may run inside a CUDA-graph capture
-            self._lauum_ws = torch.empty(int(self.lib.gpx_lauum_i8_workspace_bytes(self.Np, self.lauum_slices)),
-                                         dtype=torch.uint8, device=dev)
+        if self.lauum_slices:       # one workspace for both, allocated up front: gradients() may run inside a CUDA-graph capture
+            nbytes = int(self.lib.gpx_lauum_i8_workspace_bytes(self.Np, self.lauum_slices))
+            if self._trtri_i8_capable:
+                nbytes = max(nbytes, int(self.lib.gpx_trtri_i8_workspace_bytes(self.Np)))
+            self._lauum_ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         self.S_i8: Optional[torch.Tensor] = None      # [slices, Np, Np] int8 planes of L^-1
         self.S_i8_inv_scale: Optional[torch.Tensor] = None   # [Np] inverse power-of-two row scales
 
@@ -141,7 +149,11 @@ class ExactGPEngine:
                     raise NotPSDError(f"Matrix not positive definite after repeatedly adding jitter up to "
                                       f"{jitter:.1e} (first non-positive pivot at {info}).")
             self.jitter_used = jitter
-            self._launch("gpx_trtri", p(self.K), p(self.S), p(self.DT), p(self.W), self.Np, st)
+            if self.trtri_i8 and self._trtri_i8_capable:
+                self._launch("gpx_trtri_i8", p(self.K), p(self.S), p(self.DT), p(self.W), self.Np, p(self._lauum_ws),
+                             self._lauum_ws.numel(), st)
+            else:
+                self._launch("gpx_trtri", p(self.K), p(self.S), p(self.DT), p(self.W), self.Np, st)
             self._launch("gpx_solve_alpha", p(self.S), p(self.DT), self.Np, p(self.r), p(self.u), p(self.alpha), st)
             self._launch("gpx_mll_value", p(self.r), p(self.alpha), self.Np, self.N, p(self.logdet_blk),
                          p(self.out), st)
@@ -175,7 +187,7 @@ class ExactGPEngine:
                     if self._lauum_ws is None or self._lauum_ws.numel() < nbytes:
                         self._lauum_ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
                     self._launch("gpx_lauum_i8", p(self.S), p(self.DT), p(self.W), self.Np, self.lauum_slices,
-                                 p(self._lauum_ws), nbytes, st)
+                                 p(self._lauum_ws), self._lauum_ws.numel(), st)
                 else:
                     self._launch("gpx_lauum", p(self.S), p(self.DT), p(self.W), self.Np, st)
                 self.has_kinv = True

@@ -659,6 +659,35 @@ def test_int8_lauum_matches_fp64_lauum(dev, N, D, kind, nz):
     assert float(rel5.max()) < 2e-7, float(rel5.max())
 
 
+@pytest.mark.parametrize("N", [2048, 2300, 4200])
+def test_int8_trtri_opt_in_accuracy(dev, N):
+    """gpx_trtri_i8 (EXPERIMENTAL, opt-in: top merge levels as sliced-integer GEMMs) against gpx_trtri on the same Cholesky
+    factor.  Six slices and the compounding over the levels leave ~1e-8 of the norm of L^-1 -- the bound asserted here is what the
+    mode delivers (loss / gradients / mean are far inside 1e-6; the predictive variance is only as good as outputscale/noise
+    allows, which is why the mode is not the default)."""
+    X, y, Xs, ls, s, w, b = _problem(N, 6, 300, seed=N)
+    eng = _engine(dev, X, y, O.KIND_MATERN52, ls, s, 1e-2, w, b)
+    assert not eng.trtri_i8                          # off by default
+    S64, alpha64, loss64 = eng.S.clone(), eng.alpha.clone(), float(eng.loss)
+    g64 = eng.gradients().clone()
+    m64, s64 = eng.predict(Xs.to(dev), precision="fp64")
+    eng.trtri_i8 = True
+    eng.factorize(eng.theta_in.clone(), eng.r[:N].clone())
+    g8 = eng.gradients().clone()
+    m8, s8 = eng.predict(Xs.to(dev), precision="fp64")
+    Np = eng.Np
+    blk = torch.arange(Np, device=dev) // 128
+    offdiag = blk.view(-1, 1) != blk.view(1, -1)
+    assert float(((eng.S - S64).abs() * offdiag).max() / S64.abs().max()) < 1e-7       # L^-1 below, its mirror above the diagonal blocks
+    assert torch.equal(eng.S * (~offdiag), S64 * (~offdiag))                            # the diagonal blocks come from potrf, untouched
+    assert abs(float(eng.loss) - loss64) <= 1e-8 * abs(loss64)
+    np.testing.assert_allclose(eng.alpha[:N].cpu().numpy(), alpha64[:N].cpu().numpy(), rtol=0, atol=1e-7 * float(alpha64.abs().max()))
+    np.testing.assert_allclose(g8.cpu().numpy(), g64.cpu().numpy(), rtol=1e-6, atol=1e-9 * float(g64.abs().max()))
+    # pure-noise targets: K* alpha cancels heavily, the mean inherits ~1e-6 of its scale; std ~1e-6 at this noise level
+    np.testing.assert_allclose(m8.cpu().numpy(), m64.cpu().numpy(), rtol=0, atol=1e-5 * float(m64.abs().max()))
+    np.testing.assert_allclose(s8.cpu().numpy(), s64.cpu().numpy(), rtol=1e-4)
+
+
 def test_emulator_auto_precision(dev):
     """precision="auto" (the default of GPEmulator.predict) resolves from host-side values only and stays inside 1e-6."""
     from gperks_b200.gp.data.dataset import Dataset
