@@ -426,53 +426,10 @@ int trmm_sumsq_i8(const int8_t* Ls, const double* inv_scale, int Np, const int8_
 
 // ---- K_hat^-1 = L^-T L^-1 on the integer tensor cores (lauum for the gradient) ----------------------------------------
 // Row i of the operand = column i of L^-1 over k >= i: the transposed diagonal block DT[b] inside the row's own 128-block,
-// the mirrored L^-T blocks of S right of it, zero left of the diagonal.  One CTA per row, a power-of-two scale per row.
+// the mirrored L^-T blocks of S right of it, zero left of the diagonal (slice_i8_rows_kernel with lo = row, DT source).
 template <int S>
-__global__ void __launch_bounds__(256) slice_i8_linvT_kernel(const double* __restrict__ Smat, const double* __restrict__ DT, int Np,
-                                                             int8_t* __restrict__ planes, double* __restrict__ inv_scale) {
-    const int row = blockIdx.x, b = row / TILE;
-    const double* xs = Smat + (long)row * Np;
-    const double* xd = DT + (long)b * TILE * TILE + (long)(row - b * TILE) * TILE - (long)b * TILE;   // xd[k] valid inside block b
-    const int kblk_end = (b + 1) * TILE;
-    __shared__ double red[8];
-    __shared__ int s_e;
-    double a = 0.0;
-    for (int c = row + threadIdx.x; c < Np; c += 256) a = fmax(a, fabs(c < kblk_end ? xd[c] : xs[c]));
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) a = fmax(a, __shfl_xor_sync(0xffffffffu, a, o));
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int w = 1; w < 8; ++w) a = fmax(a, red[w]);
-        s_e = scale_exponent(a);
-        inv_scale[row] = ldexp(1.0, s_e + 1);
-    }
-    __syncthreads();
-    const double scale = ldexp(1.0, -(s_e + 1) + I_BITS);
-    const long pitch = (long)Np * Np;
-    int8_t* out = planes + (long)row * Np;
-    // columns left of the row's 128-block are never read (the k range of tile row b starts at b*128)
-    for (int c0 = b * TILE + threadIdx.x * 8; c0 < Np; c0 += 256 * 8) {
-        double r[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int c = c0 + u;
-            r[u] = (c < row) ? 0.0 : (c < kblk_end ? xd[c] : xs[c]) * scale;
-        }
-#pragma unroll
-        for (int j = 0; j < S; ++j) {
-            uint32_t lo = 0, hi = 0;
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const double q = rint(r[u]);
-                r[u] = (r[u] - q) * 128.0;
-                const uint32_t bb = (uint32_t)(__double2int_rn(q) & 0xff);
-                if (u < 4) lo |= bb << (8 * u); else hi |= bb << (8 * (u - 4));
-            }
-            *reinterpret_cast<uint2*>(out + j * pitch + c0) = make_uint2(lo, hi);
-        }
-    }
-}
+__global__ void slice_i8_rows_kernel(const double* __restrict__ src, long ld, const double* __restrict__ DT, int r0, int c0, int c1,
+                                     int lo_row, int hi_row, int Np, int8_t* __restrict__ planes, double* __restrict__ inv_scale);
 
 size_t lauum_i8_workspace_bytes(int Np, int nslices) { return (size_t)nslices * Np * Np + (size_t)Np * 8; }
 
@@ -484,8 +441,8 @@ int lauum_i8(const double* Smat, const double* DT, double* W, int Np, int nslice
     if (workspace_bytes < lauum_i8_workspace_bytes(Np, nslices)) return -7;
     double* inv_scale = reinterpret_cast<double*>(workspace);
     int8_t* planes = reinterpret_cast<int8_t*>(inv_scale + Np);
-    if (nslices == 5) slice_i8_linvT_kernel<5><<<Np, 256, 0, st>>>(Smat, DT, Np, planes, inv_scale);
-    else slice_i8_linvT_kernel<6><<<Np, 256, 0, st>>>(Smat, DT, Np, planes, inv_scale);
+    if (nslices == 5) slice_i8_rows_kernel<5><<<Np, 256, 0, st>>>(Smat, Np, DT, 0, 0, Np, 1, 0, Np, planes, inv_scale);
+    else slice_i8_rows_kernel<6><<<Np, 256, 0, st>>>(Smat, Np, DT, 0, 0, Np, 1, 0, Np, planes, inv_scale);
     const bool mc = i8_multicast();
     if (nslices == 5) return mc ? launch_i8<5, 64, true, true>(planes, inv_scale, Np, planes, Np, nullptr, W, st)
                                 : launch_i8<5, 64, false, true>(planes, inv_scale, Np, planes, Np, nullptr, W, st);

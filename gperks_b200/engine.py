@@ -104,7 +104,7 @@ class ExactGPEngine:
         self._lauum_ws: Optional[torch.Tensor] = None
         if self.lauum_slices:       # one workspace for both, allocated up front: gradients() may run inside a CUDA-graph capture
             nbytes = int(self.lib.gpx_lauum_i8_workspace_bytes(self.Np, self.lauum_slices))
-            if self._trtri_i8_capable:
+            if self.trtri_i8:
                 nbytes = max(nbytes, int(self.lib.gpx_trtri_i8_workspace_bytes(self.Np)))
             self._lauum_ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         self.S_i8: Optional[torch.Tensor] = None      # [slices, Np, Np] int8 planes of L^-1
@@ -150,6 +150,9 @@ class ExactGPEngine:
                                       f"{jitter:.1e} (first non-positive pivot at {info}).")
             self.jitter_used = jitter
             if self.trtri_i8 and self._trtri_i8_capable:
+                need = int(self.lib.gpx_trtri_i8_workspace_bytes(self.Np))
+                if self._lauum_ws is None or self._lauum_ws.numel() < need:      # switched on after construction
+                    self._lauum_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
                 self._launch("gpx_trtri_i8", p(self.K), p(self.S), p(self.DT), p(self.W), self.Np, p(self._lauum_ws),
                              self._lauum_ws.numel(), st)
             else:
