@@ -144,13 +144,7 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64
 // L2 serves the K* bytes -- two thirds of a stage -- once per pair: 60 -> 40 KB of L2 reads per CTA and stage (S = 5).
 // Both CTAs run the k extent of the odd tile (one extra stage of zero slices for the even one); a stage is refilled
 // only when both tensor cores have retired it (tcgen05.commit multicast onto both `empty` barriers, count 2).
-//
-// SYRK = true: the same machinery forms K_hat^-1 = L^-T L^-1 for the gradient (lauum): both operands are tiles of ONE sliced
-// matrix -- the columns of L^-1 as rows (upper triangular, k >= i) -- the k range of tile row mb starts at its 128-block
-// instead of ending there, only tiles on or below the diagonal are formed (two 64-column tiles per pair, so a pair shares
-// its 128 rows and its k range), and the epilogue stores inv_scale_i inv_scale_j 2^-14 sum_g 2^-7g acc_g instead of
-// reducing its squares.  `Mc` is then the row count of the planes (Np) and `qpart` the output matrix W[Np][Np].
-template <int S, int BKB, bool MC, bool SYRK>
+template <int S, int BKB, bool MC>
 __global__ void __launch_bounds__(I_THREADS, 1)
 trmm_sumsq_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int Np, int Mc,
                      const __grid_constant__ CUtensorMap tmAh, const double* __restrict__ inv_scale,
@@ -168,24 +162,8 @@ trmm_sumsq_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
     // bands of I_BAND m tiles; inside a band the row tiles run heaviest (largest k extent) first
     const uint32_t crank = MC ? cluster_ctarank() : 0u;
-    int it, mb, kstart, kend;
-    if constexpr (SYRK) {
-        // tile row mb owns the 64-column tiles it = 0 .. 2 mb + 1 (pairs p = 0 .. mb); rows are taken in ascending order: longest k first
-        const int id = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-        if (MC) {
-            mb = (int)((sqrt(8.0 * id + 1.0) - 1.0) * 0.5);
-            while ((mb + 1) * (mb + 2) / 2 <= id) ++mb;
-            while (mb * (mb + 1) / 2 > id) --mb;
-            it = 2 * (id - mb * (mb + 1) / 2) + (int)crank;
-        } else {
-            mb = (int)((sqrt(4.0 * id + 1.0) - 1.0) * 0.5);
-            while ((mb + 1) * (mb + 2) <= id) ++mb;
-            while (mb * (mb + 1) > id) --mb;
-            it = id - mb * (mb + 1);
-        }
-        kstart = mb * I_M;
-        kend = Np;
-    } else {
+    int it, mb, kend;
+    {
         const int n_mb = Mc / I_M, n_it = MC ? Np / (2 * I_N) : Np / I_N;      // MC: n_it counts PAIRS of row tiles
         const int id = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
         const int per_band = I_BAND * n_it;
@@ -198,8 +176,8 @@ trmm_sumsq_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         // entries right of the diagonal are zero slices up to the end of the row's 128-block, so a pair runs the odd tile's extent
         kend = MC ? (it + 1) * 2 * I_N : round_up((it + 1) * I_N, BKB);
         if (MC) it = 2 * it + (int)crank;
-        kstart = 0;
     }
+    const int kstart = 0;
     const int nk = (kend - kstart) / BKB;
 
     if (tid == 0) {
@@ -217,7 +195,7 @@ trmm_sumsq_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
     if (tid < I_N) {
         // V = (sum_g acc_g 2^{-7g}) * 2^{-14} / (scale_i * scale_K):  all powers of two, exact
-        const int ek = SYRK ? -1 : scale_exponent(*amax_ptr);        // SYRK: both operands carry per-row scales
+        const int ek = scale_exponent(*amax_ptr);
         sinv[tid] = inv_scale[it * I_N + tid] * ldexp(1.0, ek + 1 - 2 * I_BITS);
     }
     tc_fence_before();
@@ -297,26 +275,17 @@ trmm_sumsq_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
             for (int j = 0; j < 32; ++j) t[j] = fma((double)(int)v[j], wg, t[j]);
         }
-        if constexpr (SYRK) {
-            const long row = (long)mb * I_M + quad * 32 + lane;
-            const double si = inv_scale[row];
-            double* dst = qpart + row * Np + (long)it * I_N + half * 32;
+        double ssum = 0.0;
 #pragma unroll
-            for (int j = 0; j < 32; j += 2)
-                *reinterpret_cast<double2*>(dst + j) = make_double2(t[j] * sinv[half * 32 + j] * si, t[j + 1] * sinv[half * 32 + j + 1] * si);
-        } else {
-            double ssum = 0.0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const double x = t[j] * sinv[half * 32 + j];
-                ssum = fma(x, x, ssum);
-            }
-            red[half * I_M + quad * 32 + lane] = ssum;
-            named_bar_sync(1, 256);
-            if (half == 0) {
-                const int m = mb * I_M + quad * 32 + lane;
-                qpart[(long)it * Mc + m] = red[quad * 32 + lane] + red[I_M + quad * 32 + lane];
-            }
+        for (int j = 0; j < 32; ++j) {
+            const double x = t[j] * sinv[half * 32 + j];
+            ssum = fma(x, x, ssum);
+        }
+        red[half * I_M + quad * 32 + lane] = ssum;
+        named_bar_sync(1, 256);
+        if (half == 0) {
+            const int m = mb * I_M + quad * 32 + lane;
+            qpart[(long)it * Mc + m] = red[quad * 32 + lane] + red[I_M + quad * 32 + lane];
         }
         tc_fence_before();
     }
@@ -368,7 +337,7 @@ static int i8_multicast() {
     return v;
 }
 
-template <int S, int BKB, bool MC, bool SYRK = false>
+template <int S, int BKB, bool MC>
 static int launch_i8(const int8_t* Ls, const double* inv_scale, int Np, const int8_t* Kp, int Mc, const double* amax_ptr,
                      double* qpart, cudaStream_t st) {
     using C = I8Cfg<S, BKB>;
@@ -376,7 +345,7 @@ static int launch_i8(const int8_t* Ls, const double* inv_scale, int Np, const in
     int dev = 0;
     cudaGetDevice(&dev);
     if (!(dev >= 0 && dev < 64 && attr[dev])) {
-        cudaFuncSetAttribute(trmm_sumsq_i8_kernel<S, BKB, MC, SYRK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+        cudaFuncSetAttribute(trmm_sumsq_i8_kernel<S, BKB, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
         if (dev >= 0 && dev < 64) attr[dev] = true;
     }
     CUtensorMap tmA, tmAh, tmB;
@@ -384,10 +353,9 @@ static int launch_i8(const int8_t* Ls, const double* inv_scale, int Np, const in
     if ((rc = encode_u8_rowmajor(&tmA, Kp, (uint64_t)S * Mc, Np, BKB, I_M))) return rc;
     if ((rc = encode_u8_rowmajor(&tmAh, Kp, (uint64_t)S * Mc, Np, BKB, I_M / 2))) return rc;
     if ((rc = encode_u8_rowmajor(&tmB, Ls, (uint64_t)S * Np, Np, BKB, I_N))) return rc;
-    const int nbt = Np / I_M;
-    const int tiles = SYRK ? nbt * (nbt + 1) : (Np / I_N) * (Mc / I_M);       // SYRK: 2 mb + 2 column tiles in tile row mb
+    const int tiles = (Np / I_N) * (Mc / I_M);
     if (!MC) {
-        trmm_sumsq_i8_kernel<S, BKB, false, SYRK><<<tiles, I_THREADS, C::SMEM_BYTES, st>>>(tmA, tmB, Np, Mc, tmAh, inv_scale, amax_ptr, qpart);
+        trmm_sumsq_i8_kernel<S, BKB, false><<<tiles, I_THREADS, C::SMEM_BYTES, st>>>(tmA, tmB, Np, Mc, tmAh, inv_scale, amax_ptr, qpart);
     } else {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(tiles);
@@ -401,7 +369,7 @@ static int launch_i8(const int8_t* Ls, const double* inv_scale, int Np, const in
         at[0].val.clusterDim.z = 1;
         cfg.attrs = at;
         cfg.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, trmm_sumsq_i8_kernel<S, BKB, true, SYRK>, tmA, tmB, Np, Mc, tmAh, inv_scale, amax_ptr, qpart);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, trmm_sumsq_i8_kernel<S, BKB, true>, tmA, tmB, Np, Mc, tmAh, inv_scale, amax_ptr, qpart);
         if (e != cudaSuccess) return -1000 - (int)e;
     }
     GPX_CHECK_LAUNCH();
@@ -424,32 +392,6 @@ int trmm_sumsq_i8(const int8_t* Ls, const double* inv_scale, int Np, const int8_
     return -8;
 }
 
-// ---- K_hat^-1 = L^-T L^-1 on the integer tensor cores (lauum for the gradient) ----------------------------------------
-// Row i of the operand = column i of L^-1 over k >= i: the transposed diagonal block DT[b] inside the row's own 128-block,
-// the mirrored L^-T blocks of S right of it, zero left of the diagonal (slice_i8_rows_kernel with lo = row, DT source).
-template <int S>
-__global__ void slice_i8_rows_kernel(const double* __restrict__ src, long ld, const double* __restrict__ DT, int r0, int c0, int c1,
-                                     int lo_row, int hi_row, int Np, int8_t* __restrict__ planes, double* __restrict__ inv_scale);
-
-size_t lauum_i8_workspace_bytes(int Np, int nslices) { return (size_t)nslices * Np * Np + (size_t)Np * 8; }
-
-// W (lower 128-tiles, full inside the diagonal blocks) = L^-T L^-1 from the mirrored inverse S and the transposed diagonal blocks DT.
-int lauum_i8(const double* Smat, const double* DT, double* W, int Np, int nslices, void* workspace, size_t workspace_bytes,
-             cudaStream_t st) {
-    if (Np % TILE || Np > 32768) return -4;
-    if (nslices < 5 || nslices > I_SMAX) return -5;
-    if (workspace_bytes < lauum_i8_workspace_bytes(Np, nslices)) return -7;
-    double* inv_scale = reinterpret_cast<double*>(workspace);
-    int8_t* planes = reinterpret_cast<int8_t*>(inv_scale + Np);
-    if (nslices == 5) slice_i8_rows_kernel<5><<<Np, 256, 0, st>>>(Smat, Np, DT, 0, 0, Np, 1, 0, Np, planes, inv_scale);
-    else slice_i8_rows_kernel<6><<<Np, 256, 0, st>>>(Smat, Np, DT, 0, 0, Np, 1, 0, Np, planes, inv_scale);
-    const bool mc = i8_multicast();
-    if (nslices == 5) return mc ? launch_i8<5, 64, true, true>(planes, inv_scale, Np, planes, Np, nullptr, W, st)
-                                : launch_i8<5, 64, false, true>(planes, inv_scale, Np, planes, Np, nullptr, W, st);
-    return mc ? launch_i8<6, 64, true, true>(planes, inv_scale, Np, planes, Np, nullptr, W, st)
-              : launch_i8<6, 64, false, true>(planes, inv_scale, Np, planes, Np, nullptr, W, st);
-}
-
 // ---- general sliced-integer NT product with a store epilogue (the merge steps of the recursive triangular inverse) ----
 //   C[c_row0 + i][c_col0 + j] = sign * sum_{k in range(i)} A[a_row0 + i][k] * B[b_row0 + j][k]      (+ the same value at C2[j][i])
 // A (MMA M side, 128-row tiles mi) and B (N side, 64-row tiles nj) are int8 slice planes [S][Np][Np] with per-row scales;
@@ -462,6 +404,7 @@ struct I8Gemm {
     int k_base, k_end, k_from;
     int c_row0, c_col0;
     int m_row0, m_col0;         // mirror C2[m_row0 + j][m_col0 + i]; m_row0 < 0: none
+    int tri;                    // 1: only the N tiles of the first mi + 1 pairs exist (tiles on or below the block diagonal)
     double sign;
 };
 
@@ -484,6 +427,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     const int pairs = g.n_nj / 2;
     const int cid = (int)(blockIdx.x >> 1);
     const int mi = cid / pairs, nj = 2 * (cid - mi * pairs) + (int)crank;
+    if (g.tri && (nj >> 1) > mi) return;          // both CTAs of the pair leave together, before any barrier exists
     const int kstart = g.k_from ? g.k_base + mi * I_M : g.k_base;
     const int kend = g.k_from ? g.k_end : g.k_base + (mi + 1) * I_M;
     const int nk = (kend - kstart) / BKB;
@@ -677,6 +621,30 @@ static int launch_gemm_i8(const int8_t* PA, const int8_t* PB, int Np, const doub
     return e == cudaSuccess ? 0 : -1000 - (int)e;
 }
 
+// ---- K_hat^-1 = L^-T L^-1 on the integer tensor cores (lauum for the gradient) ----------------------------------------
+// Row i of the operand = column i of L^-1 over k >= i: the transposed diagonal block DT[b] inside the row's own 128-block,
+// the mirrored L^-T blocks of S right of it, zero left of the diagonal (slice_i8_rows_kernel with lo = row, DT source).
+// Both operands of the product are tiles of that one sliced matrix; the k range of tile row mi starts at its 128-block and
+// only the tiles on or below the block diagonal are formed (what gpx_mll_grad reads).
+size_t lauum_i8_workspace_bytes(int Np, int nslices) { return (size_t)nslices * Np * Np + (size_t)Np * 8; }
+
+int lauum_i8(const double* Smat, const double* DT, double* W, int Np, int nslices, void* workspace, size_t workspace_bytes,
+             cudaStream_t st) {
+    if (Np % TILE || Np > 32768) return -4;
+    if (nslices < 5 || nslices > I_SMAX) return -5;
+    if (workspace_bytes < lauum_i8_workspace_bytes(Np, nslices)) return -7;
+    double* inv_scale = reinterpret_cast<double*>(workspace);
+    int8_t* planes = reinterpret_cast<int8_t*>(inv_scale + Np);
+    const int nbt = Np / I_M;
+    const I8Gemm g = {2 * nbt, 0, 0, 0, Np, 1, 0, 0, -1, 0, 1, 1.0};
+    if (nslices == 5) {
+        slice_i8_rows_kernel<5><<<Np, 256, 0, st>>>(Smat, Np, DT, 0, 0, Np, 1, 0, Np, planes, inv_scale);
+        return launch_gemm_i8<5>(planes, planes, Np, inv_scale, inv_scale, W, nullptr, g, nbt, st);
+    }
+    slice_i8_rows_kernel<6><<<Np, 256, 0, st>>>(Smat, Np, DT, 0, 0, Np, 1, 0, Np, planes, inv_scale);
+    return launch_gemm_i8<6>(planes, planes, Np, inv_scale, inv_scale, W, nullptr, g, nbt, st);
+}
+
 // One merge level of the recursive inverse (gpx_chol.cu: trtri) for the pair of segments [left, left+h) | [right, right+hr) (in
 // 128-blocks) on the integer tensor cores:  T = L[right,left] A^-1 (stored transposed in W), X21 = -C^-1 T -> S (+ mirror).
 int trtri_i8_merge(const double* L, double* Smat, const double* DT, double* W, int Np, int left, int h, int hr, void* workspace,
@@ -692,13 +660,13 @@ int trtri_i8_merge(const double* L, double* Smat, const double* DT, double* W, i
     // step 1: M side = columns of A^-1 as rows (left segment, k from the row to the end of the segment), N side = L[right, left]
     slice_i8_rows_kernel<S><<<h * TILE, 256, 0, st>>>(Smat, Np, DT, l0, 0, r0, 1, 0, Np, PA, sA);
     slice_i8_rows_kernel<S><<<hr * TILE, 256, 0, st>>>(L, Np, nullptr, r0, l0, r0, 0, 0, Np, PB, sB);
-    I8Gemm g1 = {2 * hr, l0, r0, l0, r0, 1, l0, r0, -1, 0, 1.0};
+    I8Gemm g1 = {2 * hr, l0, r0, l0, r0, 1, l0, r0, -1, 0, 0, 1.0};
     int rc = launch_gemm_i8<S>(PA, PB, Np, sA, sB, W, nullptr, g1, h, st);
     if (rc) return rc;
     // step 2: M side = rows of C^-1 (right segment, k from the segment start to the row), N side = T^T = W[left, right]
     slice_i8_rows_kernel<S><<<hr * TILE, 256, 0, st>>>(Smat, Np, nullptr, r0, r0, 0, 0, 1, Np, PA, sA);
     slice_i8_rows_kernel<S><<<h * TILE, 256, 0, st>>>(W, Np, nullptr, l0, r0, r1, 0, 0, Np, PB, sB);
-    I8Gemm g2 = {2 * h, r0, l0, r0, r1, 0, r0, l0, l0, r0, -1.0};
+    I8Gemm g2 = {2 * h, r0, l0, r0, r1, 0, r0, l0, l0, r0, 0, -1.0};
     rc = launch_gemm_i8<S>(PA, PB, Np, sA, sB, Smat, Smat, g2, hr, st);
     if (rc) return rc;
     GPX_CHECK_LAUNCH();
