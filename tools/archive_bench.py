@@ -52,7 +52,7 @@ def mean(name):
 trmm, kc, fin = mean("trmm_sumsq_tma_kernel"), mean("kmat_cross_kernel<3>"), mean("predict_finalize_kernel")
 lines.append(f"# FP64 predict step (one 32768-point chunk) under ncu: trmm {trmm / 1e3:.2f} ms, kmat_cross {kc / 1e3:.2f} ms, "
              f"finalize {fin / 1e3:.3f} ms -> TRMM share {trmm / (trmm + kc + fin):.3f} (bench.py live: {d.get('fp64_dmma_mode', d)['roofline']['kernel_share_of_step']:.3f})")
-ti, ki = mean("trmm_sumsq_i8_kernel<6, 64, 1, 0>"), mean("kmat_cross_i8_kernel<3, 6>")
+ti, ki = mean("trmm_sumsq_i8_kernel<6, 64, 1>"), mean("kmat_cross_i8_kernel<3, 6>")
 if ti == ti:
     lines.append(f"# int8x6 predict step (one 32768-point chunk) under ncu: trmm_i8 {ti / 1e3:.2f} ms, kmat_cross_i8 {ki / 1e3:.2f} ms, "
                  f"finalize {fin / 1e3:.3f} ms -> integer-kernel share {ti / (ti + ki + fin):.3f}"
