@@ -79,7 +79,7 @@ for N in sizes:
             case[f"int8x{S}_mean_equal"] = bool(torch.equal(mu, mu0))
         print(json.dumps(case), flush=True)
         out["cases"].append(case)
-        if N >= 2048 and noise == 1e-2:
+        if N >= 1024 and noise == 1e-2:
             Mt = 32768
             Xt = torch.rand(Mt, D, dtype=F64, generator=g).to(dev)
             for prec in ("fp64", "int8x5", "int8x6", "tf32x3"):
