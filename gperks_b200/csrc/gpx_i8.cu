@@ -7,9 +7,13 @@
 // so that            V[m][i] = (1 / scale_i scale_K) sum_{g<S} 2^{-7(g+2)} sum_{a+b=g} <I_a(L^-1 row i), I_b(K* row m)>
 // up to the dropped products a+b >= S.  Every inner product is an integer GEMM whose int32 accumulation is exact
 // (|sum| <= 64*64*K*S < 2^31 for K <= 32768); the S diagonals are combined in FP64 in the epilogue.  With S = 5 the
-// predictive std agrees with the FP64 path to ~5e-8 relative (N = 8192, noise 1e-2; 5e-7 at noise 1e-4), S = 6 to ~5e-9
-// -- inside the 1e-6 bar of the FP64 mode, at the integer tensor-core rate instead of the DMMA rate
+// predictive std agrees with the FP64 path to ~5e-7 relative (measured, N = 8192, noise 1e-2; 7e-6 at noise 1e-4), S = 6 to
+// ~5e-9 (4e-8) -- inside the 1e-6 bar of the FP64 mode, at the integer tensor-core rate instead of the DMMA rate
 // (the variance contraction is the N^2 FLOP/point term that bounds predict).
+//
+// Contents: slice_i8_kernel / slice_i8_rows_kernel (FP64 -> int8 planes), trmm_sumsq_i8_kernel (predict: sum of squares
+// epilogue), gemm_i8_kernel (general NT product with a store epilogue: K_hat^-1 for the gradient, and the opt-in merge levels of
+// the triangular inverse), peak_i8mma_kernel (roofline probe).
 //
 // Tile: 128 test points (MMA M = TMEM lanes) x 64 rows of L^-1 (per slice), S accumulators of 64 TMEM columns, one per
 // diagonal g.  The S slices of the L^-1 tile are STACKED along MMA N in shared memory, so for the K* slice a one
