@@ -54,4 +54,7 @@ AUTO_I8_SLICES = 6
 AUTO_I8_MIN_N = 1024
 AUTO_I8_MAX_N = 32768
 AUTO_I8_MAX_SCALE_TO_NOISE = 1.0e5
+# ... and, once per factorisation, only if the sliced-integer std reproduces the FP64 (DMMA) std on up to 128 training inputs --
+# where the predictive variance cancels the most -- to this relative tolerance (one tiny predict pair + one host read)
+AUTO_I8_PROBE_TOL = 2.5e-7
 

@@ -90,6 +90,7 @@ class ExactGPEngine:
         self.S_hi: Optional[torch.Tensor] = None      # TF32 mode: (hi, lo) float split of L^-1
         self.S_lo: Optional[torch.Tensor] = None
         self.i8_slices = 0                            # sliced-integer mode: number of int8 slices of L^-1 held (0 = none)
+        self._i8_probe = None                         # ((n_factorizations, slices, tol), ok) of the last int8_probe_ok()
         # K_hat^-1 = L^-T L^-1 for the gradient: six-slice integer tensor-core product where its tiles pay and its int32 sums
         # cannot overflow (entries within ~1e-10 of their row/column scale of the DMMA result), else the FP64 DMMA lauum;
         # GPX_LAUUM=fp64 forces the latter
@@ -301,6 +302,22 @@ class ExactGPEngine:
             self._launch("gpx_split_tf32", nv.ptr(self.S), self.Np * self.Np, nv.ptr(self.S_hi), nv.ptr(self.S_lo),
                          self.Np, nv.stream_ptr())
         self.has_split = True
+
+    def int8_probe_ok(self, slices: int, tol: float) -> bool:
+        """Guard of ``precision="auto"``: True when the sliced-integer std agrees with the FP64 (DMMA) std to ``tol`` on up to 128
+        training inputs (the points of smallest predictive variance, i.e. of strongest cancellation in s + noise - q) for the
+        CURRENT factors.  Evaluated once per factorisation (two 128-point predicts and one host read), then cached."""
+        key = (self.n_factorizations, int(slices), float(tol))
+        if self._i8_probe is not None and self._i8_probe[0] == key:
+            return self._i8_probe[1]
+        n = min(128, self.N)
+        xp = self.X[:n]
+        zero = torch.zeros(n, dtype=F64, device=self.device)
+        _, s64 = self.predict(xp, prior_mean=zero, precision="fp64")
+        _, s8 = self.predict(xp, prior_mean=zero, precision=f"int8x{int(slices)}")
+        ok = bool(((s8 - s64).abs() <= tol * s64).all())
+        self._i8_probe = (key, ok)
+        return ok
 
     def _ensure_i8(self, slices: int) -> None:
         """int8 slices and row scales of L^-1 for the sliced-integer variance path; refreshed after every factorisation."""

@@ -31,6 +31,7 @@ from ..constants import (
     AUTO_I8_MAX_N,
     AUTO_I8_MAX_SCALE_TO_NOISE,
     AUTO_I8_MIN_N,
+    AUTO_I8_PROBE_TOL,
     AUTO_I8_SLICES,
     DEFAULT_PREDICT_CHUNK_BYTES,
     DEFAULT_TRAIN_MAX_EPOCH,
@@ -395,9 +396,12 @@ class GPEmulator(Trainable):
         the pinned H2D / D2H staging.  Returns ``(mean, std, linear_out)``."""
         cdev = self._compute_device()
         scx, scy = self.scaled_data.scx, self.scaled_data.scy
+        auto = precision == "auto"
         precision = self.resolve_precision(precision)
         with torch.no_grad(), torch.cuda.device(cdev):
             eng = self.model._factorized_engine()
+            if auto and precision.startswith("int8") and not eng.int8_probe_ok(int(precision[-1]), AUTO_I8_PROBE_TOL):
+                precision = "fp64"        # the sliced-integer std misses the FP64 std on the training inputs: stay on DMMA
             M = x_dev.shape[0]
             xa = torch.as_tensor(numpy.asarray(scx.a, dtype=numpy.float64).reshape(-1), device=cdev)
             xr = torch.as_tensor((numpy.asarray(scx.b, dtype=numpy.float64)

@@ -720,6 +720,28 @@ def test_emulator_auto_precision(dev):
         np.testing.assert_allclose(s_auto, s64, rtol=1e-6)
         if want == "fp64":
             assert np.array_equal(s_auto, s64)
+        else:
+            eng = em.model._factorized_engine()
+            assert eng.i8_slices == 6 and eng._i8_probe is not None and eng._i8_probe[1]       # the guard ran and passed
+    # the guard itself: with an unattainable tolerance "auto" must fall back to the FP64 path, bit for bit
+    import gperks_b200.train.emulator as E
+    old_tol = E.AUTO_I8_PROBE_TOL
+    try:
+        E.AUTO_I8_PROBE_TOL = 1e-13
+        X = rng.random((1100, D))
+        y = np.sin(3 * X[:, 0]) + 0.05 * rng.standard_normal(1100)
+        exp = GPExperiment(Dataset(X, y), GaussianLikelihood(), LinearMean(1, D), ScaleKernel(MaternKernel(nu=2.5, ard_num_dims=D)),
+                           n_restarts=1, seed=8)
+        em = GPEmulator(exp, "cuda:0")
+        em.model.likelihood.noise = 1e-2
+        assert em.resolve_precision("auto") == "int8x6"
+        Xq = rng.random((500, D))
+        m_a, s_a = em.predict(Xq)
+        m_f, s_f = em.predict(Xq, precision="fp64")
+        assert np.array_equal(m_a, m_f) and np.array_equal(s_a, s_f)
+        assert em.model._factorized_engine()._i8_probe[1] is False
+    finally:
+        E.AUTO_I8_PROBE_TOL = old_tol
 
 
 def test_emulator_predict_int8_precision(dev, goldens):
