@@ -38,7 +38,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 N_TRAIN, DIM = 8192, 8
-NCU_TRAFFIC_I8_BYTES = {"int8x6": 11.952e9}      # dram read+write per launch of trmm_sumsq_i8_kernel<6>, profiles/r01_ncu_i8.txt (N=8192, chunk 32768)
+NCU_TRAFFIC_I8_BYTES = {"int8x6": 11.877e9}      # dram read+write per launch of trmm_sumsq_i8_kernel<6>, profiles/r01_ncu_i8.txt (N=8192, chunk 32768)
 NCU_TRAFFIC_BYTES = 13.546e9   # dram read+write per launch, profiles/r01_ncu_trmm_tma.txt (N=8192, chunk 32768)
 KIND_NAME = "matern52"
 NOISE = 1e-2
