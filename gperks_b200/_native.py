@@ -15,6 +15,7 @@ _lib: Optional[C.CDLL] = None
 
 KIND_RBF, KIND_MATERN12, KIND_MATERN32, KIND_MATERN52 = 0, 1, 2, 3
 TILE = 128
+ABI_VERSION = 200          # gpx_version() of the library these ctypes signatures were written against
 
 _P = C.c_void_p
 _SIGS = {
@@ -44,19 +45,21 @@ _SIGS = {
     "gpx_predict_meanvar_tf32": (C.c_int, [_P, C.c_long, _P, C.c_int, C.c_int, _P, _P, _P, C.c_int, _P, _P, C.c_int, _P,
                                            _P, _P, C.c_int, C.c_int, _P, _P, C.c_double, C.c_double, C.c_double, _P,
                                            _P, _P, C.c_size_t, C.c_int, C.c_int, _P]),
-    "gpx_slice_i8": (C.c_int, [_P, C.c_int, C.c_int, C.c_long, _P, C.c_long, C.c_int, C.c_int, _P, _P, _P]),
+    "gpx_slice_i8": (C.c_int, [_P, C.c_int, C.c_int, C.c_long, _P, C.c_long, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "gpx_i8_row_tiles": (C.c_int, [C.c_int]),
+    "gpx_i8_max_n": (C.c_int, [C.c_int]),
     "gpx_kmat_cross_i8": (C.c_int, [_P, C.c_long, _P, C.c_int, C.c_int, _P, _P, _P, C.c_int, _P, _P, C.c_long, C.c_int, C.c_int,
-                                    _P, C.c_int, _P]),
-    "gpx_trmm_sumsq_i8": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.c_int, _P, _P, _P]),
+                                    C.c_int, _P, C.c_int, _P]),
+    "gpx_trmm_sumsq_i8": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "gpx_trtri_i8_workspace_bytes": (C.c_size_t, [C.c_int]),
     "gpx_trtri_i8": (C.c_int, [_P, _P, _P, _P, C.c_int, _P, C.c_size_t, _P]),
     "gpx_lauum_i8_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "gpx_lauum_i8": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, C.c_size_t, _P]),
     "gpx_predict_i8_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "gpx_predict_i8_planes_offset": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "gpx_predict_meanvar_i8": (C.c_int, [_P, C.c_long, _P, C.c_int, C.c_int, _P, _P, _P, C.c_int, _P, _P, C.c_int, C.c_int,
-                                         _P, _P, _P, C.c_int, C.c_int, _P, _P, C.c_double, C.c_double, C.c_double, _P,
-                                         _P, _P, C.c_size_t, C.c_int, _P]),
+                                         C.c_int, _P, _P, _P, C.c_int, C.c_int, _P, _P, C.c_double, C.c_double, C.c_double,
+                                         _P, _P, _P, C.c_size_t, C.c_int, _P, _P]),
     "gpx_implausibility": (C.c_int, [_P, _P, C.c_long, C.c_int, _P, _P, C.c_int, _P, _P, _P]),
     "gpx_peak_dmma": (C.c_double, [C.c_int, C.c_int, _P, _P]),
     "gpx_peak_i8mma": (C.c_double, [C.c_int, C.c_int, _P]),
@@ -78,6 +81,9 @@ def lib() -> C.CDLL:
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
+        if handle.gpx_version() != ABI_VERSION:      # a library built from other sources than these signatures: never call into it
+            raise RuntimeError(f"gperks_b200: {path} reports ABI {handle.gpx_version()}, this package binds ABI {ABI_VERSION}; "
+                               f"rebuild with `python -m gperks_b200._build`")
         _lib = handle
     return _lib
 

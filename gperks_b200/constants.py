@@ -45,16 +45,25 @@ DEFAULT_TMP_OUTFILE_DIR = Path(os.getcwd(), "tmp").as_posix()
 # B200 path
 DEFAULT_PREDICT_CHUNK_BYTES = 2 << 30      # HBM budget for one K* chunk in GPEmulator.predict
 
-# precision="auto" in GPEmulator.predict / predict_device: the sliced-integer variance path (tcgen05 kind::i8, six 7-bit
-# slices, exact int32 accumulation; measured std error vs the FP64 DMMA path <= 7e-8 at outputscale/noise = 1.3e4) is used
-# when its int32 sums cannot overflow, the problem is large enough for the tensor-core tiles to pay, and the
-# cancellation in  var = s + noise - ||L^-1 k*||^2  (amplification ~ outputscale / noise) leaves the error inside 1e-6;
-# otherwise the FP64 DMMA path.
-AUTO_I8_SLICES = 6
+# precision="auto" in GPEmulator.predict / predict_device: the sliced-integer variance path (tcgen05 kind::i8, exact int32
+# accumulation) is used when its int32 sums cannot overflow, the problem is large enough for the tensor-core tiles to pay, and
+# the cancellation in  var = s + noise - ||L^-1 k*||^2  (amplification ~ outputscale / noise) leaves the error inside 1e-6;
+# otherwise the FP64 DMMA path.  Candidates in order of speed (each is tried only inside its ratio limit):
+#   N_pad <= 16384:  "int8x5w" five 8-bit slices (40 bits, 15 slice products)  for outputscale/noise <= 1e4
+#                    "int8x6w" six  8-bit slices (48 bits, 21 products)        for outputscale/noise <= 1e7
+#   N_pad <= 32768:  "int8x6"  six  7-bit slices (42 bits, 21 products)        for outputscale/noise <= 1e5
+AUTO_I8_SLICES = 6                  # K_hat^-1 for the gradient (gpx_lauum_i8): six 7-bit slices
 AUTO_I8_MIN_N = 1024
 AUTO_I8_MAX_N = 32768
+AUTO_I8_WIDE_MAX_N = 16384
 AUTO_I8_MAX_SCALE_TO_NOISE = 1.0e5
-# ... and, once per factorisation, only if the sliced-integer std reproduces the FP64 (DMMA) std on up to 128 training inputs --
-# where the predictive variance cancels the most -- to this relative tolerance (one tiny predict pair + one host read)
+AUTO_I8_W5_MAX_SCALE_TO_NOISE = 1.0e4
+AUTO_I8_W6_MAX_SCALE_TO_NOISE = 1.0e7
+# ... and, once per factorisation, only if the sliced-integer std reproduces the FP64 (DMMA) std to this relative tolerance on
+# the probe set: the 128 training inputs of smallest FP64 predictive variance (out of up to 4096 evenly strided ones) -- where
+# s + noise - q cancels the most -- plus the same points moved by 1e-4 of the unit cube.  A candidate that fails hands over
+# to the next more accurate one, then to "fp64".
 AUTO_I8_PROBE_TOL = 2.5e-7
+AUTO_I8_PROBE_POOL = 4096
+AUTO_I8_PROBE_POINTS = 128
 

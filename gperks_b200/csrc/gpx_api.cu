@@ -21,21 +21,23 @@ int split_tf32_matrix(const double*, long, float*, float*, int, cudaStream_t);
 int trmm_sumsq_tf32(const float*, const float*, int, const float*, const float*, int, double*, int, cudaStream_t);
 int tf32_row_tiles(int);
 size_t predict_tf32_workspace_bytes(int, int);
-int slice_i8_matrix(const double*, int, int, long, int8_t*, long, int, int, double*, const double*, cudaStream_t);
+int slice_i8_matrix(const double*, int, int, long, int8_t*, long, int, int, int, double*, const double*, cudaStream_t);
 double peak_i8mma(int, int, cudaStream_t);
 size_t trtri_i8_workspace_bytes(int, int);
 int trtri_i8(const double*, double*, const double*, double*, int, void*, size_t, cudaStream_t);
 size_t lauum_i8_workspace_bytes(int, int);
 int lauum_i8(const double*, const double*, double*, int, int, void*, size_t, cudaStream_t);
 int kmat_cross_i8(const double*, long, const double*, int, int, const double*, const double*, const double*, int, const double*,
-                  int8_t*, long, int, int, double*, int, cudaStream_t);
-int trmm_sumsq_i8(const int8_t*, const double*, int, const int8_t*, int, int, const double*, double*, cudaStream_t);
+                  int8_t*, long, int, int, int, double*, int, cudaStream_t);
+int trmm_sumsq_i8(const int8_t*, const double*, int, const int8_t*, int, int, int, const double*, double*, cudaStream_t);
 int i8_row_tiles(int);
+int i8_max_np(int);
 size_t predict_i8_workspace_bytes(int, int, int);
+size_t predict_i8_planes_offset(int, int, int, int);
 int predict_meanvar_i8(const double*, long, const double*, int, int, const double*, const double*, const double*, int,
-                       const int8_t*, const double*, int, int, const double*, const double*, const int*, int, int,
+                       const int8_t*, const double*, int, int, int, const double*, const double*, const int*, int, int,
                        const double*, const double*, double, double, double, double*, double*, void*, size_t, int,
-                       cudaStream_t);
+                       cudaStream_t, cudaStream_t);
 int predict_meanvar_tf32(const double*, long, const double*, int, int, const double*, const double*, const double*, int,
                          const float*, const float*, int, const double*, const double*, const int*, int, int,
                          const double*, const double*, double, double, double, double*, double*, void*, size_t, int,
@@ -82,7 +84,7 @@ using namespace gpx;
 
 extern "C" {
 
-int gpx_version(void) { return 100; }
+int gpx_version(void) { return 200; }
 int gpx_padded(int n) { return round_up(n < 1 ? 1 : n, TILE); }
 int gpx_max_dim(void) { return MAXD; }
 
@@ -218,36 +220,41 @@ int gpx_predict_meanvar_tf32(const double* Xs, long M, const double* X, int N, i
 }
 
 int gpx_slice_i8(const double* src, int rows, int cols, long ld_src, signed char* planes, long plane_rows, int nslices,
-                 int tri, double* inv_scale, const double* amax_ptr, void* stream) {
+                 int bits, int tri, double* inv_scale, const double* amax_ptr, void* stream) {
     if (!src || !planes) return -1;
-    if (rows < 0 || cols <= 0 || cols % 8 || ld_src < cols || plane_rows < rows) return -2;
+    if (rows < 0 || cols <= 0 || cols % TILE || ld_src < cols || plane_rows < rows) return -2;
     if (nslices < 5 || nslices > 6) return -7;
-    if (tri ? !inv_scale : !amax_ptr) return -9;
-    return slice_i8_matrix(src, rows, cols, ld_src, reinterpret_cast<int8_t*>(planes), plane_rows, nslices, tri, inv_scale,
+    if (bits != 7 && bits != 8) return -8;
+    if (tri ? !inv_scale : !amax_ptr) return -10;
+    return slice_i8_matrix(src, rows, cols, ld_src, reinterpret_cast<int8_t*>(planes), plane_rows, nslices, bits, tri, inv_scale,
                            amax_ptr, ST(stream));
 }
+
+int gpx_i8_max_n(int bits) { return (bits == 7 || bits == 8) ? i8_max_np(bits) : 0; }
 
 int gpx_i8_row_tiles(int Np) { return i8_row_tiles(Np); }
 
 int gpx_kmat_cross_i8(const double* Xs, long m_valid, const double* X, int N, int D, const double* theta, const double* xa,
                       const double* xr, int kind, const double* alpha, signed char* planes, long plane_rows, int nslices,
-                      int Np, double* mean_part, int Mc, void* stream) {
+                      int bits, int Np, double* mean_part, int Mc, void* stream) {
     if (!Xs || !X || !theta || !alpha || !planes || !mean_part) return -1;
     if (D < 1 || D > MAXD) return -5;
     if (Np % TILE || Mc % TILE || Np < N || Mc <= 0 || plane_rows < Mc) return -3;
     if (nslices < 5 || nslices > 6) return -13;
+    if (bits != 7 && bits != 8) return -14;
     if ((xa == nullptr) != (xr == nullptr)) return -7;
     return kmat_cross_i8(Xs, m_valid, X, N, D, theta, xa, xr, kind, alpha, reinterpret_cast<int8_t*>(planes), plane_rows,
-                         nslices, Np, mean_part, Mc, ST(stream));
+                         nslices, bits, Np, mean_part, Mc, ST(stream));
 }
 
 int gpx_trmm_sumsq_i8(const signed char* Ls, const double* inv_scale, int Np, const signed char* Kp, int Mc, int nslices,
-                      const double* amax_ptr, double* qpart, void* stream) {
+                      int bits, const double* amax_ptr, double* qpart, void* stream) {
     if (!Ls || !inv_scale || !Kp || !amax_ptr || !qpart) return -1;
     if (Np % TILE || Mc % TILE || Np <= 0 || Mc <= 0) return -3;
     if (nslices < 5 || nslices > 6) return -6;
+    if (bits != 7 && bits != 8) return -7;
     return trmm_sumsq_i8(reinterpret_cast<const int8_t*>(Ls), inv_scale, Np, reinterpret_cast<const int8_t*>(Kp), Mc,
-                         nslices, amax_ptr, qpart, ST(stream));
+                         nslices, bits, amax_ptr, qpart, ST(stream));
 }
 
 size_t gpx_trtri_i8_workspace_bytes(int Np) { return trtri_i8_workspace_bytes(Np, 6); }
@@ -269,23 +276,27 @@ int gpx_lauum_i8(const double* S, const double* DT, double* Kinv, int Np, int ns
 }
 
 size_t gpx_predict_i8_workspace_bytes(int Np, int Mc, int nslices) { return predict_i8_workspace_bytes(Np, Mc, nslices); }
+size_t gpx_predict_i8_planes_offset(int Np, int Mc, int nslices, int buffer) {
+    return predict_i8_planes_offset(Np, Mc, nslices, buffer & 1);
+}
 
 int gpx_predict_meanvar_i8(const double* Xs, long M, const double* X, int N, int D, const double* theta, const double* xa,
-                           const double* xr, int kind, const signed char* Ls, const double* inv_scale, int nslices, int Np,
-                           const double* alpha, const double* prior_mean, const int* feat_idx, int n_feat, int degree,
+                           const double* xr, int kind, const signed char* Ls, const double* inv_scale, int nslices, int bits,
+                           int Np, const double* alpha, const double* prior_mean, const int* feat_idx, int n_feat, int degree,
                            const double* weights, const double* bias, double y_mu, double y_sigma, double min_var,
                            double* out_mean, double* out_std, void* workspace, size_t workspace_bytes, int Mc,
-                           void* stream) {
+                           void* stream, void* mma_stream) {
     if (!Xs || !X || !theta || !Ls || !inv_scale || !alpha || !out_mean || !out_std || !workspace) return -1;
     if (M < 0) return -2;
     if (nslices < 5 || nslices > 6) return -12;
-    if (Np > 32768) return -13;
+    if (bits != 7 && bits != 8) return -13;
+    if (Np > i8_max_np(bits)) return -14;
     if (M == 0) return 0;
     if ((xa == nullptr) != (xr == nullptr)) return -7;
     if (!prior_mean && weights && n_feat > 0 && (!feat_idx || degree < 1)) return -14;
     return predict_meanvar_i8(Xs, M, X, N, D, theta, xa, xr, kind, reinterpret_cast<const int8_t*>(Ls), inv_scale, nslices,
-                              Np, alpha, prior_mean, feat_idx, n_feat, degree, weights, bias, y_mu, y_sigma, min_var,
-                              out_mean, out_std, workspace, workspace_bytes, Mc, ST(stream));
+                              bits, Np, alpha, prior_mean, feat_idx, n_feat, degree, weights, bias, y_mu, y_sigma, min_var,
+                              out_mean, out_std, workspace, workspace_bytes, Mc, ST(stream), ST(mma_stream));
 }
 
 int gpx_implausibility(const double* mean, const double* std_, long M, int E, const double* z, const double* v,

@@ -211,6 +211,25 @@ __device__ __forceinline__ void gemm_foreach_pair_ref(double (&acc)[8][4][2], F 
         for (int n = 0; n < 4; ++n) f(wm * 64 + s * 8 + lr, wn * 32 + n * 8 + 2 * lc, acc[s][n][0], acc[s][n][1]);
 }
 
+// ---- digit formats of the sliced-integer mode (gpx_i8.cu, gpx_kmat.cu) ----
+// BITS = 8: the top balanced digit must stay <= 127, i.e. |x| * scale <= 127.4 / 256: one more bit of headroom when f > 0.9953
+template <int BITS>
+__device__ __forceinline__ int scale_exponent_b(double amax) {
+    if (!(amax > 0.0)) return 0;
+    int e;
+    const double f = frexp(amax, &e);
+    if (BITS == 8 && f > 0.9953) ++e;
+    return e;
+}
+// The S balanced radix-256 digits of v (|v| <= 127.4/256), most significant first: digit q = byte S-1-q of (V + bias) ^ 0x80..80
+template <int S>
+__device__ __forceinline__ unsigned long long balanced_digits(double v) {
+    constexpr unsigned long long BIAS = (S == 5) ? 0x8080808080ull : 0x808080808080ull;
+    const long long V = __double2ll_rn(v * (double)(1ull << (8 * S)));
+    return ((unsigned long long)V + BIAS) ^ BIAS;
+}
+__device__ __forceinline__ int perm128(int c) { return (c & ~127) | ((c & 15) << 3) | ((c & 127) >> 4); }
+
 #define GPX_CHECK_LAUNCH()                                  \
     do {                                                    \
         cudaError_t e__ = cudaGetLastError();               \

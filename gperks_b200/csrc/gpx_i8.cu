@@ -11,6 +11,17 @@
 // ~5e-9 (4e-8) -- inside the 1e-6 bar of the FP64 mode, at the integer tensor-core rate instead of the DMMA rate
 // (the variance contraction is the N^2 FLOP/point term that bounds predict).
 //
+// Two digit formats (template parameter BITS):
+//   BITS = 7: |I_j| <= 64 by repeated round-to-nearest (the formulas above); int32 sums safe for K <= 32768.
+//   BITS = 8: balanced radix-256 digits I_j in [-128, 127] of  V = rint(x * scale * 2^{8S})  (one rounding, 8S bits kept):
+//             x * scale = sum_j I_j 2^{-8(j+1)},  bytes of (V + sum_j 128 * 256^j) xor 0x80.  The scale keeps |x * scale| <= 127.4/256
+//             so the top digit fits.  |sum| <= 128*128*K*S < 2^31 for K <= 16384 -- five 8-bit slices (40 bits, 15 products)
+//             replace six 7-bit ones (42 bits, 21 products); six 8-bit slices carry 48 bits.
+// Plane layout of the predict operands (K* chunk and L^-1): inside every 128-block of the contraction index the entry of
+// column c sits at byte (c % 16) * 8 + c / 16 -- the same permutation on both operands leaves every inner product unchanged
+// and lets the K* builder (gpx_kmat.cu), whose threads own columns tx + 16 b, store 8 consecutive bytes per slice straight
+// from registers.
+//
 // Contents: slice_i8_kernel / slice_i8_rows_kernel (FP64 -> int8 planes), trmm_sumsq_i8_kernel (predict: sum of squares
 // epilogue), gemm_i8_kernel (general NT product with a store epilogue: K_hat^-1 for the gradient, and the opt-in merge levels of
 // the triangular inverse), peak_i8mma_kernel (roofline probe).
@@ -43,8 +54,8 @@ struct I8Cfg {
     static constexpr int A_BYTES = I_M * BKB;
     static constexpr int B_BYTES = I_N * BKB;
     static constexpr int STAGE_BYTES = S * (A_BYTES + B_BYTES);
-    // tiles | full[STAGES] empty[STAGES] acc_full | tmem slot | inverse scales [64] | partial sums [2][128]
-    static constexpr size_t SMEM_BYTES = 1024 + size_t(STAGES) * STAGE_BYTES + (2 * STAGES + 2) * 8 + I_N * 8 + 2 * I_M * 8;
+    // tiles | full[STAGES] empty[STAGES] acc_full acc_empty | tmem slot | inverse scales [64] | partial sums [2][128]
+    static constexpr size_t SMEM_BYTES = 1024 + size_t(STAGES) * STAGE_BYTES + (2 * STAGES + 3) * 8 + I_N * 8 + 2 * I_M * 8;
 };
 
 // power-of-two scale that brings |x| <= amax into [-1/2, 1/2]:  returns e with amax < 2^e, scale = 2^-(e+1)
@@ -54,13 +65,12 @@ __device__ __forceinline__ int scale_exponent(double amax) {
     frexp(amax, &e);            // amax = f 2^e, f in [1/2, 1)
     return e;
 }
-
 // ---- FP64 -> S int8 slices -------------------------------------------------------------------------------
-// One CTA per row.  planes[j][row][col] (row pitch = cols bytes, plane pitch = plane_rows * cols bytes).
+// One CTA per row.  planes[j][row][perm128(col)] (row pitch = cols bytes, plane pitch = plane_rows * cols bytes; cols % 128 == 0).
 // tri != 0: `src` is the mirrored inverse S (L^-1 below, L^-T above the diagonal blocks): entries right of the diagonal
 // are sliced as zero and the row's own maximum sets its scale, whose inverse is stored in inv_scale[row].
 // tri == 0: one scale for the whole matrix from *amax_ptr (K* <= outputscale).
-template <int S>
+template <int S, int BITS>
 __global__ void __launch_bounds__(256) slice_i8_kernel(const double* __restrict__ src, int cols, long ld_src,
                                                        int8_t* __restrict__ planes, long plane_rows, int tri,
                                                        double* __restrict__ inv_scale, const double* __restrict__ amax_ptr) {
@@ -78,42 +88,52 @@ __global__ void __launch_bounds__(256) slice_i8_kernel(const double* __restrict_
         __syncthreads();
         if (threadIdx.x == 0) {
             for (int w = 1; w < 8; ++w) a = fmax(a, red[w]);
-            s_e = scale_exponent(a);
+            s_e = scale_exponent_b<BITS>(a);
             inv_scale[row] = ldexp(1.0, s_e + 1);
         }
         __syncthreads();
     } else {
-        if (threadIdx.x == 0) s_e = scale_exponent(*amax_ptr);
+        if (threadIdx.x == 0) s_e = scale_exponent_b<BITS>(*amax_ptr);
         __syncthreads();
     }
-    const double scale = ldexp(1.0, -(s_e + 1) + I_BITS);       // first slice: rint(x * scale * 2^7)
+    const double scale = ldexp(1.0, -(s_e + 1) + (BITS == 7 ? I_BITS : 0));   // 7 bit: first slice = rint(x * scale * 2^7)
     const long pitch = plane_rows * (long)cols;
     int8_t* out = planes + (long)row * cols;
-    const int cend = tri ? min(cols, round_up(row + 1, TILE)) : cols;     // the MMA tiles never read beyond the row's 128-block
-    for (int c0 = threadIdx.x * 8; c0 < cend; c0 += 256 * 8) {
-        if (c0 >= kmax) {
-#pragma unroll
-            for (int j = 0; j < S; ++j) *reinterpret_cast<uint2*>(out + j * pitch + c0) = make_uint2(0u, 0u);
-            continue;
-        }
+    const int nblk = (tri ? min(cols, round_up(row + 1, TILE)) : cols) / TILE;   // the MMA tiles never read beyond the row's 128-block
+    // work item = (128-block, tx): the entries of columns blk*128 + tx + 16 u, u < 8, land in 8 consecutive bytes
+    for (int w = threadIdx.x; w < nblk * 16; w += 256) {
+        const int c0 = (w >> 4) * TILE + (w & 15);
         double r[8];
 #pragma unroll
-        for (int u = 0; u < 8; u += 2) {
-            const double2 v = *reinterpret_cast<const double2*>(x + c0 + u);
-            r[u] = (c0 + u < kmax) ? v.x * scale : 0.0;
-            r[u + 1] = (c0 + u + 1 < kmax) ? v.y * scale : 0.0;
-        }
+        for (int u = 0; u < 8; ++u) r[u] = (c0 + 16 * u < kmax) ? x[c0 + 16 * u] * scale : 0.0;
+        int8_t* dst = out + (w >> 4) * TILE + (w & 15) * 8;
+        if (BITS == 7) {
 #pragma unroll
-        for (int j = 0; j < S; ++j) {
-            uint32_t lo = 0, hi = 0;
+            for (int j = 0; j < S; ++j) {
+                uint32_t lo = 0, hi = 0;
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const double q = rint(r[u]);
-                r[u] = (r[u] - q) * 128.0;                       // exact: |r - q| <= 1/2
-                const uint32_t b = (uint32_t)(__double2int_rn(q) & 0xff);
-                if (u < 4) lo |= b << (8 * u); else hi |= b << (8 * (u - 4));
+                for (int u = 0; u < 8; ++u) {
+                    const double q = rint(r[u]);
+                    r[u] = (r[u] - q) * 128.0;                       // exact: |r - q| <= 1/2
+                    const uint32_t b = (uint32_t)(__double2int_rn(q) & 0xff);
+                    if (u < 4) lo |= b << (8 * u); else hi |= b << (8 * (u - 4));
+                }
+                *reinterpret_cast<uint2*>(dst + j * pitch) = make_uint2(lo, hi);
             }
-            *reinterpret_cast<uint2*>(out + j * pitch + c0) = make_uint2(lo, hi);
+        } else {
+            unsigned long long dg[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) dg[u] = balanced_digits<S>(r[u]);
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                uint32_t lo = 0, hi = 0;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const uint32_t b = (uint32_t)(dg[u] >> (8 * (S - 1 - j))) & 0xffu;
+                    if (u < 4) lo |= b << (8 * u); else hi |= b << (8 * (u - 4));
+                }
+                *reinterpret_cast<uint2*>(dst + j * pitch) = make_uint2(lo, hi);
+            }
         }
     }
 }
@@ -148,7 +168,7 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64
 // L2 serves the K* bytes -- two thirds of a stage -- once per pair: 60 -> 40 KB of L2 reads per CTA and stage (S = 5).
 // Both CTAs run the k extent of the odd tile (one extra stage of zero slices for the even one); a stage is refilled
 // only when both tensor cores have retired it (tcgen05.commit multicast onto both `empty` barriers, count 2).
-template <int S, int BKB, bool MC>
+template <int S, int BKB, bool MC, int BITS>
 __global__ void __launch_bounds__(I_THREADS, 1)
 trmm_sumsq_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int Np, int Mc,
                      const __grid_constant__ CUtensorMap tmAh, const double* __restrict__ inv_scale,
@@ -178,7 +198,8 @@ trmm_sumsq_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         it = n_it - 1 - rem / width;
         mb = band * I_BAND + rem % width;
         // entries right of the diagonal are zero slices up to the end of the row's 128-block, so a pair runs the odd tile's extent
-        kend = MC ? (it + 1) * 2 * I_N : round_up((it + 1) * I_N, BKB);
+        // (the k index is permuted inside 128-blocks, so extents are whole 128-blocks)
+        kend = MC ? (it + 1) * 2 * I_N : round_up((it + 1) * I_N, TILE);
         if (MC) it = 2 * it + (int)crank;
     }
     const int kstart = 0;
@@ -198,9 +219,9 @@ trmm_sumsq_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
     }
     if (tid < I_N) {
-        // V = (sum_g acc_g 2^{-7g}) * 2^{-14} / (scale_i * scale_K):  all powers of two, exact
-        const int ek = scale_exponent(*amax_ptr);
-        sinv[tid] = inv_scale[it * I_N + tid] * ldexp(1.0, ek + 1 - 2 * I_BITS);
+        // V = (sum_g acc_g 2^{-BITS g}) * 2^{-2 BITS} / (scale_i * scale_K):  all powers of two, exact
+        const int ek = scale_exponent_b<BITS>(*amax_ptr);
+        sinv[tid] = inv_scale[it * I_N + tid] * ldexp(1.0, ek + 1 - 2 * BITS);
     }
     tc_fence_before();
     __syncthreads();
@@ -275,7 +296,7 @@ trmm_sumsq_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             uint32_t v[32];
             tmem_ld_32x32b_x32(tmem_d + lane_base + (uint32_t)(g * I_N + half * 32), v);
             tmem_wait_ld();
-            const double wg = 1.0 / (double)(1ull << (I_BITS * g));
+            const double wg = 1.0 / (double)(1ull << (BITS * g));
 #pragma unroll
             for (int j = 0; j < 32; ++j) t[j] = fma((double)(int)v[j], wg, t[j]);
         }
@@ -301,6 +322,192 @@ trmm_sumsq_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
 }
 
+// ---- persistent edition (default) ---------------------------------------------------------------------------
+// One cluster of two CTAs per SM pair walks the list of (row-tile pair, point tile) work items with a fixed stride (the
+// list is band-major, heaviest rows first, so the clusters resident at any time share ~9 L^-1 tile pairs and 8 K* tiles
+// through L2).  The TMA ring, its phases and the TMEM allocation live across tiles: the producer runs ahead into the next
+// tile while the epilogue warps drain the accumulators, so neither the pipeline ramp (first L2/HBM round trip) nor the
+// prologue (barrier init, TMEM allocation, cluster sync) is paid per tile -- at N = 2048 those were ~20 % of a tile.
+// Pipelines: smem full/empty (TMA <-> MMA, count 2 on `empty`: both tensor cores of the pair must have retired a stage before
+// either producer multicasts into it), TMEM acc_full/acc_empty (MMA <-> 8 epilogue warps).
+// Epilogue: diagonals are combined 16 columns at a time (registers: the kernel must leave room for a K* builder CTA of the
+// next chunk on the same SM), int32 -> FP64 by the 2^52 trick (one LOP + one DADD instead of I2F.F64).
+template <int S, int BITS>
+__global__ void __launch_bounds__(I_THREADS, 2)      // "2" caps the kernel at 96 registers per thread: 30 K registers, the other half of the file is the builder's
+trmm_sumsq_i8p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmB, int Np, int Mc,
+                      const double* __restrict__ inv_scale, const double* __restrict__ amax_ptr, double* __restrict__ qpart) {
+    using C = I8Cfg<S, 64>;
+    constexpr int BKB = 64;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + size_t(C::STAGES) * C::STAGE_BYTES);     // full[3] empty[3] acc_full acc_empty
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 2);
+    double* sinv = reinterpret_cast<double*>(bars + 2 * C::STAGES + 3);      // [64]
+    double* red = sinv + I_N;                                                 // [2][128]
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + C::STAGES);
+    const uint32_t acc_full = smem_u32(bars + 2 * C::STAGES), acc_empty = smem_u32(bars + 2 * C::STAGES + 1);
+    const uint32_t tile0 = smem_u32(base);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t crank = cluster_ctarank();
+    const int n_mb = Mc / I_M, n_it = Np / (2 * I_N);          // n_it counts PAIRS of row tiles
+    const int n_items = n_mb * n_it;
+    const int cid = (int)(blockIdx.x >> 1), n_clusters = (int)(gridDim.x >> 1);
+    const int per_band = I_BAND * n_it;
+
+    if (tid == 0) {
+        for (int s = 0; s < C::STAGES; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, 2);
+        }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, 8);
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "n"(I_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();        // the peer's barriers must be initialised before anything is multicast at them
+    tc_fence_after();
+    const uint32_t tmem_d = *tmem_slot;
+
+    // work item id -> (pair of row tiles itp, point tile mb); both CTAs of the cluster take the same items
+    auto decode = [&](int id, int& itp, int& mb) {
+        const int band = id / per_band;
+        const int left = n_mb - band * I_BAND;
+        const int width = left < I_BAND ? left : I_BAND;
+        const int rem = id - band * per_band;
+        itp = n_it - 1 - rem / width;
+        mb = band * I_BAND + rem % width;
+    };
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            tma_prefetch_desc(&tmAh); tma_prefetch_desc(&tmB);
+            uint32_t git = 0;                                   // k iterations issued so far (over all tiles)
+            for (int id = cid; id < n_items; id += n_clusters) {
+                int itp, mb;
+                decode(id, itp, mb);
+                const int nk = (itp + 1) * 2 * I_N / BKB;       // the pair runs the odd tile's extent (zero slices beyond the diagonal)
+                const int it = 2 * itp + (int)crank;
+                for (int kt = 0; kt < nk; ++kt, ++git) {
+                    const uint32_t s = git % C::STAGES, round = git / C::STAGES;
+                    if (round > 0) mbar_wait(empty0 + 8 * s, (round - 1) & 1);
+                    mbar_arrive_expect_tx(full0 + 8 * s, C::STAGE_BYTES);
+                    const uint32_t dst = tile0 + s * C::STAGE_BYTES;
+                    const int k0 = kt * BKB;
+#pragma unroll
+                    for (int j = 0; j < S; ++j)     // my 64 points of every K* slice tile, delivered to both CTAs of the pair
+                        tma_load_2d_multicast(dst + j * C::A_BYTES + crank * (C::A_BYTES / 2), &tmAh, k0,
+                                              j * Mc + mb * I_M + (int)crank * (I_M / 2), full0 + 8 * s, 3);
+#pragma unroll
+                    for (int j = 0; j < S; ++j)
+                        tma_load_2d(dst + S * C::A_BYTES + j * C::B_BYTES, &tmB, k0, j * Np + it * I_N, full0 + 8 * s);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            uint32_t git = 0, tile_n = 0;
+            for (int id = cid; id < n_items; id += n_clusters, ++tile_n) {
+                int itp, mb;
+                decode(id, itp, mb);
+                const int nk = (itp + 1) * 2 * I_N / BKB;
+                if (tile_n > 0) {                               // the epilogue warps have drained the previous tile's accumulators
+                    mbar_wait(acc_empty, (tile_n - 1) & 1);
+                    tc_fence_after();
+                }
+                for (int kt = 0; kt < nk; ++kt, ++git) {
+                    const uint32_t s = git % C::STAGES, round = git / C::STAGES;
+                    mbar_wait(full0 + 8 * s, round & 1);
+                    tc_fence_after();
+                    const uint32_t st = tile0 + s * C::STAGE_BYTES;
+#pragma unroll
+                    for (int kk = 0; kk < BKB / 32; ++kk) {
+                        const uint64_t adv = (uint64_t)((kk * 32) >> 4);     // 32 int8 along K inside the swizzle atom
+#pragma unroll
+                        for (int a = 0; a < S; ++a) {
+                            const uint64_t da = umma_desc_kmajor<BKB>(st + a * C::A_BYTES) + adv;
+                            const int ncols = (S - a) * I_N;                  // L^-1 slices 0 .. S-1-a -> diagonals a .. S-1
+#pragma unroll
+                            for (int c0 = 0; c0 < ncols; c0 += 256) {
+                                const int w = (ncols - c0) < 256 ? (ncols - c0) : 256;
+                                const uint64_t db = umma_desc_kmajor<BKB>(st + S * C::A_BYTES + (c0 / I_N) * C::B_BYTES) + adv;
+                                // the first k step of K* slice 0 touches every accumulator once: it overwrites (no zero fill)
+                                umma_i8(tmem_d + (uint32_t)(a * I_N + c0), da, db, i8_idesc(w), (kt | kk | a) != 0 ? 1u : 0u);
+                            }
+                        }
+                    }
+                    umma_commit_multicast(empty0 + 8 * s, 3);     // both producers wait for both tensor cores
+                }
+                umma_commit(acc_full);
+            }
+        }
+    } else {
+        // ===== epilogue warps 2..9: TMEM lane quadrant = warp % 4, columns [32 half, 32 half + 32) of every diagonal =====
+        const int quad = warp & 3, half = (warp - 2) >> 2;
+        const int et = tid - 64;                                 // 0..255 among the epilogue threads
+        const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+        const int ek = scale_exponent_b<BITS>(*amax_ptr);
+        const double kfac = ldexp(1.0, ek + 1 - 2 * BITS);       // V = (sum_g acc_g 2^{-BITS g}) * 2^{-2 BITS} / (scale_i scale_K): exact
+        uint32_t tile_n = 0;
+        for (int id = cid; id < n_items; id += n_clusters, ++tile_n) {
+            int itp, mb;
+            decode(id, itp, mb);
+            const int it = 2 * itp + (int)crank;
+            if (et < I_N) sinv[et] = inv_scale[it * I_N + et] * kfac;
+            mbar_wait(acc_full, tile_n & 1);
+            tc_fence_after();
+            double ssum = 0.0;
+#pragma unroll
+            for (int cg = 0; cg < 2; ++cg) {
+                double t[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) t[j] = 0.0;
+#pragma unroll
+                for (int g = S - 1; g >= 0; --g) {          // smallest diagonal first
+                    uint32_t v[16];
+                    tmem_ld_32x32b_x16(tmem_d + lane_base + (uint32_t)(g * I_N + half * 32 + cg * 16), v);
+                    tmem_wait_ld();
+                    const double wg = 1.0 / (double)(1ull << (BITS * g));
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)            // (double)(int)v: 2^52 + 2^31 + (v xor 2^31) as a bit pattern, minus the offset
+                        t[j] = fma(__hiloint2double(0x43300000, (int)(v[j] ^ 0x80000000u)) - 4503601774854144.0, wg, t[j]);
+                }
+                if (cg == 1) {                               // every accumulator column of this warp has been read
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc_empty);
+                }
+                if (cg == 0) named_bar_sync(1, 256);         // sinv of this tile is in place
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const double x = t[j] * sinv[half * 32 + cg * 16 + j];
+                    ssum = fma(x, x, ssum);
+                }
+            }
+            red[half * I_M + quad * 32 + lane] = ssum;
+            named_bar_sync(1, 256);
+            if (half == 0) {
+                const int m = mb * I_M + quad * 32 + lane;
+                qpart[(long)it * Mc + m] = red[quad * 32 + lane] + red[I_M + quad * 32 + lane];
+            }
+            // (no third barrier: sinv is last read before the barrier above, red before the next tile's first one)
+        }
+    }
+    __syncthreads();
+    cluster_sync_all();        // nobody leaves while the peer may still multicast into / arrive on this CTA
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "n"(I_TMEM_COLS) : "memory");
+    }
+}
+
 // ---- host -------------------------------------------------------------------------------------------------
 static int encode_u8_rowmajor(CUtensorMap* tm, const int8_t* base, uint64_t rows, uint64_t cols, uint32_t box_cols,
                               uint32_t box_rows) {
@@ -316,83 +523,111 @@ static int encode_u8_rowmajor(CUtensorMap* tm, const int8_t* base, uint64_t rows
     return r == CUDA_SUCCESS ? 0 : -901 - (int)r;
 }
 
-static int i8_bkb() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("GPX_I8_BKB"); v = (e && atoi(e) == 128) ? 128 : 64; }   // GPX_I8_BKB=128: one-stage A/B edition
-    return v;
-}
-
 int i8_row_tiles(int Np) { return Np / I_N; }
 
 // planes <- slices of src [rows][cols] (ld_src); tri: mirrored inverse with per-row scales -> inv_scale[rows]
-int slice_i8_matrix(const double* src, int rows, int cols, long ld_src, int8_t* planes, long plane_rows, int nslices, int tri,
-                    double* inv_scale, const double* amax_ptr, cudaStream_t st) {
-    if (cols % 8 || nslices < 5 || nslices > I_SMAX) return -2;
+int slice_i8_matrix(const double* src, int rows, int cols, long ld_src, int8_t* planes, long plane_rows, int nslices, int bits,
+                    int tri, double* inv_scale, const double* amax_ptr, cudaStream_t st) {
+    if (cols % TILE || nslices < 5 || nslices > I_SMAX || (bits != 7 && bits != 8)) return -2;
     if (rows <= 0) return 0;
-    if (nslices == 5) slice_i8_kernel<5><<<rows, 256, 0, st>>>(src, cols, ld_src, planes, plane_rows, tri, inv_scale, amax_ptr);
-    else slice_i8_kernel<6><<<rows, 256, 0, st>>>(src, cols, ld_src, planes, plane_rows, tri, inv_scale, amax_ptr);
+#define GPX_SLICE(S_, B_) slice_i8_kernel<S_, B_><<<rows, 256, 0, st>>>(src, cols, ld_src, planes, plane_rows, tri, inv_scale, amax_ptr)
+    if (nslices == 5 && bits == 7) GPX_SLICE(5, 7);
+    else if (nslices == 6 && bits == 7) GPX_SLICE(6, 7);
+    else if (nslices == 5) GPX_SLICE(5, 8);
+    else GPX_SLICE(6, 8);
+#undef GPX_SLICE
     GPX_CHECK_LAUNCH();
     return 0;
 }
 
-static int i8_multicast() {
+// GPX_I8_IMPL: unset = persistent clusters (trmm_sumsq_i8p_kernel); "tile" = one work item per cluster (the round-1 edition);
+// "1cta" = no pairing at all
+static int i8_impl() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("GPX_I8_IMPL"); v = (e && e[0] == '1') ? 0 : 1; }   // GPX_I8_IMPL=1cta: no pairing
+    if (v < 0) {
+        const char* e = getenv("GPX_I8_IMPL");
+        v = (e && e[0] == '1') ? 1 : (e && e[0] == 't') ? 2 : 0;
+    }
     return v;
 }
 
-template <int S, int BKB, bool MC>
+static void cluster2_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* at, int grid, size_t smem, cudaStream_t st) {
+    cfg = cudaLaunchConfig_t{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(I_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+}
+
+template <int S, int BITS>
 static int launch_i8(const int8_t* Ls, const double* inv_scale, int Np, const int8_t* Kp, int Mc, const double* amax_ptr,
                      double* qpart, cudaStream_t st) {
-    using C = I8Cfg<S, BKB>;
+    using C = I8Cfg<S, 64>;
     static bool attr[64] = {false};
+    static int max_clusters[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
-    if (!(dev >= 0 && dev < 64 && attr[dev])) {
-        cudaFuncSetAttribute(trmm_sumsq_i8_kernel<S, BKB, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
-        if (dev >= 0 && dev < 64) attr[dev] = true;
+    if (dev < 0 || dev >= 64) return -30;
+    const int impl = i8_impl();
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute at[1];
+    if (!attr[dev]) {
+        cudaFuncSetAttribute(trmm_sumsq_i8p_kernel<S, BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+        cudaFuncSetAttribute(trmm_sumsq_i8_kernel<S, 64, true, BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+        cudaFuncSetAttribute(trmm_sumsq_i8_kernel<S, 64, false, BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+        cluster2_config(cfg, at, 2, C::SMEM_BYTES, st);
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, trmm_sumsq_i8p_kernel<S, BITS>, &cfg) != cudaSuccess || n < 1) {
+            cudaGetLastError();
+            cudaDeviceProp prop;
+            cudaGetDeviceProperties(&prop, dev);
+            n = prop.multiProcessorCount / 2;
+        }
+        max_clusters[dev] = n;
+        attr[dev] = true;
     }
     CUtensorMap tmA, tmAh, tmB;
     int rc;
-    if ((rc = encode_u8_rowmajor(&tmA, Kp, (uint64_t)S * Mc, Np, BKB, I_M))) return rc;
-    if ((rc = encode_u8_rowmajor(&tmAh, Kp, (uint64_t)S * Mc, Np, BKB, I_M / 2))) return rc;
-    if ((rc = encode_u8_rowmajor(&tmB, Ls, (uint64_t)S * Np, Np, BKB, I_N))) return rc;
+    if ((rc = encode_u8_rowmajor(&tmA, Kp, (uint64_t)S * Mc, Np, 64, I_M))) return rc;
+    if ((rc = encode_u8_rowmajor(&tmAh, Kp, (uint64_t)S * Mc, Np, 64, I_M / 2))) return rc;
+    if ((rc = encode_u8_rowmajor(&tmB, Ls, (uint64_t)S * Np, Np, 64, I_N))) return rc;
     const int tiles = (Np / I_N) * (Mc / I_M);
-    if (!MC) {
-        trmm_sumsq_i8_kernel<S, BKB, false><<<tiles, I_THREADS, C::SMEM_BYTES, st>>>(tmA, tmB, Np, Mc, tmAh, inv_scale, amax_ptr, qpart);
+    if (impl == 1) {
+        trmm_sumsq_i8_kernel<S, 64, false, BITS><<<tiles, I_THREADS, C::SMEM_BYTES, st>>>(tmA, tmB, Np, Mc, tmAh, inv_scale, amax_ptr, qpart);
+    } else if (impl == 2) {
+        cluster2_config(cfg, at, tiles, C::SMEM_BYTES, st);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, trmm_sumsq_i8_kernel<S, 64, true, BITS>, tmA, tmB, Np, Mc, tmAh, inv_scale, amax_ptr, qpart);
+        if (e != cudaSuccess) return -1000 - (int)e;
     } else {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(tiles);
-        cfg.blockDim = dim3(I_THREADS);
-        cfg.dynamicSmemBytes = C::SMEM_BYTES;
-        cfg.stream = st;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = 2;
-        at[0].val.clusterDim.y = 1;
-        at[0].val.clusterDim.z = 1;
-        cfg.attrs = at;
-        cfg.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, trmm_sumsq_i8_kernel<S, BKB, true>, tmA, tmB, Np, Mc, tmAh, inv_scale, amax_ptr, qpart);
+        const int items = tiles / 2;
+        const int clusters = items < max_clusters[dev] ? items : max_clusters[dev];
+        cluster2_config(cfg, at, 2 * clusters, C::SMEM_BYTES, st);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, trmm_sumsq_i8p_kernel<S, BITS>, tmAh, tmB, Np, Mc, inv_scale, amax_ptr, qpart);
         if (e != cudaSuccess) return -1000 - (int)e;
     }
     GPX_CHECK_LAUNCH();
     return 0;
 }
 
+// largest contraction length whose int32 sums cannot overflow: |digit| <= 64 (7 bit) / 128 (8 bit), S products per diagonal
+int i8_max_np(int bits) { return bits == 8 ? 16384 : 32768; }
+
 // qpart[it][m], it < Np/64.  Ls: S planes [Np][Np] of the sliced inverse, Kp: S planes [Mc][Np] of the sliced K* chunk.
-int trmm_sumsq_i8(const int8_t* Ls, const double* inv_scale, int Np, const int8_t* Kp, int Mc, int nslices,
+int trmm_sumsq_i8(const int8_t* Ls, const double* inv_scale, int Np, const int8_t* Kp, int Mc, int nslices, int bits,
                   const double* amax_ptr, double* qpart, cudaStream_t st) {
     if (Mc % I_M || Np % TILE) return -6;
-    if (Np > 32768) return -7;              // int32 accumulators: 64*64*K*S < 2^31
-    const bool wide = i8_bkb() == 128;
-    const bool mc = !wide && i8_multicast();
-    if (nslices == 5) return wide ? launch_i8<5, 128, false>(Ls, inv_scale, Np, Kp, Mc, amax_ptr, qpart, st)
-                           : mc   ? launch_i8<5, 64, true>(Ls, inv_scale, Np, Kp, Mc, amax_ptr, qpart, st)
-                                  : launch_i8<5, 64, false>(Ls, inv_scale, Np, Kp, Mc, amax_ptr, qpart, st);
-    if (nslices == 6) return wide ? launch_i8<6, 128, false>(Ls, inv_scale, Np, Kp, Mc, amax_ptr, qpart, st)
-                           : mc   ? launch_i8<6, 64, true>(Ls, inv_scale, Np, Kp, Mc, amax_ptr, qpart, st)
-                                  : launch_i8<6, 64, false>(Ls, inv_scale, Np, Kp, Mc, amax_ptr, qpart, st);
+    if (bits != 7 && bits != 8) return -7;
+    if (Np > i8_max_np(bits)) return -7;              // int32 accumulators
+    if (nslices == 5) return bits == 7 ? launch_i8<5, 7>(Ls, inv_scale, Np, Kp, Mc, amax_ptr, qpart, st)
+                                       : launch_i8<5, 8>(Ls, inv_scale, Np, Kp, Mc, amax_ptr, qpart, st);
+    if (nslices == 6) return bits == 7 ? launch_i8<6, 7>(Ls, inv_scale, Np, Kp, Mc, amax_ptr, qpart, st)
+                                       : launch_i8<6, 8>(Ls, inv_scale, Np, Kp, Mc, amax_ptr, qpart, st);
     return -8;
 }
 

@@ -181,11 +181,16 @@ kmat_cross_kernel(const double* __restrict__ Xs, long m_valid, const double* __r
 
 // ------------------------------------------------------------------------------------------------
 // Sliced-integer mode (gpx_i8.cu): K* evaluated in FP64 exactly like kmat_cross_kernel -- same micro-tile, same order of
-// the fused K* alpha partial sums, so the posterior mean is bit-identical -- and written directly as S signed 7-bit
-// slices (int8 planes [S][plane_rows][Np]) of  v * 2^-(e+1),  outputscale = f 2^e  (k <= outputscale), instead of 8-byte
-// values that a second kernel would read back and slice.  A warp owns two rows of every 16-row step; its bytes are
-// staged through 256 B of shared memory per slice so that each lane stores 8 consecutive bytes (128 B per row and slice).
-template <int KIND, int S>
+// the fused K* alpha partial sums, so the posterior mean is bit-identical -- and written directly as S int8 slices
+// (planes [S][plane_rows][Np]) of  v * 2^-(e+1)  (outputscale = f 2^e, k <= outputscale) instead of 8-byte values that a
+// second kernel would read back and slice.  BITS = 7: S rounds of round-to-nearest; BITS = 8: one FP64 -> int64 conversion and
+// the bytes of the biased integer (gpx_common.cuh: balanced_digits) -- two FP64 instructions per entry instead of 4 S.
+// A thread owns columns tx + 16 b (b < 8) of its row; the plane layout stores column c of a 128-block at byte
+// (c % 16) * 8 + c / 16 (the L^-1 planes use the same permutation), so the 8 bytes of a slice are assembled in two
+// registers with one PRMT per digit and leave as ONE 8-byte store per slice: a half-warp writes a full 128-byte row segment,
+// no shared-memory staging.  Shared memory holds only the 2 x D coordinate rows (sized by D, not MAXD), so a CTA of this
+// kernel fits beside the 183 KB CTA of the integer tensor-core kernel working on the previous chunk.
+template <int KIND, int S, int BITS>
 __global__ void __launch_bounds__(P_THREADS, 2)
 kmat_cross_i8_kernel(const double* __restrict__ Xs, long m_valid, const double* __restrict__ X, int N, int D,
                      const double* __restrict__ theta, const double* __restrict__ xa, const double* __restrict__ xr,
@@ -193,20 +198,18 @@ kmat_cross_i8_kernel(const double* __restrict__ Xs, long m_valid, const double* 
                      double* __restrict__ mean_part, int Mc) {
     const int jb = blockIdx.x, mb = blockIdx.y;
     extern __shared__ double sm[];
-    double* sa = sm;                    // test points (rows m)
-    double* sb = sm + MAXD * P_LD;      // train points (cols j)
-    double* sal = sb + MAXD * P_LD;     // alpha tile [128]
+    double* sa = sm;                    // test points (rows m)   [D][P_LD]
+    double* sb = sm + D * P_LD;         // train points (cols j)  [D][P_LD]
+    double* sal = sb + D * P_LD;        // alpha tile [128]
     double* smean = sal + TILE;         // [128]
-    unsigned char* stg = reinterpret_cast<unsigned char*>(smean + TILE) + (threadIdx.x >> 5) * (S * 256);   // [S][2][128] per warp
     stage_coords(sa, Xs, (long)mb * TILE, m_valid, D, theta, xa, xr);
     stage_coords(sb, X, (long)jb * TILE, N, D, theta, nullptr, nullptr);
     if (threadIdx.x < TILE) sal[threadIdx.x] = alpha[jb * TILE + threadIdx.x];
     __syncthreads();
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4, lane = threadIdx.x & 31;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const double s = theta[D];
-    int e = 0;
-    if (s > 0.0) frexp(s, &e);
-    const double scale = ldexp(1.0, 7 - (e + 1));            // first slice = rint(v * 2^-(e+1) * 2^7), |.| <= 64
+    const int e = scale_exponent_b<BITS>(s);
+    const double scale = ldexp(1.0, (BITS == 7 ? 7 : 0) - (e + 1));      // 7 bit: first slice = rint(v * 2^-(e+1) * 2^7), |.| <= 64
     const long pitch = plane_rows * (long)Np;
     double al[8];
 #pragma unroll
@@ -227,17 +230,37 @@ kmat_cross_i8_kernel(const double* __restrict__ Xs, long m_valid, const double* 
         }
         const long m = (long)mb * TILE + row;
         double part = 0.0;
+        uint32_t lo[S], hi[S];
+#pragma unroll
+        for (int q = 0; q < S; ++q) { lo[q] = 0u; hi[q] = 0u; }
 #pragma unroll
         for (int b = 0; b < 8; ++b) {
             const long j = (long)jb * TILE + tx + 16 * b;
             const double v = (j < N) ? kernel_value<KIND>(r2[b], s) : 0.0;
             part = fma(v, al[b], part);
-            double r = v * scale;
+            // byte b of the slice words: selector keeps the other three bytes and takes one byte of the digit word
+            constexpr uint32_t keep = 0x3210u;
+            const uint32_t pos = (uint32_t)(b & 3) * 4;
+            if (BITS == 7) {
+                double r = v * scale;
 #pragma unroll
-            for (int q = 0; q < S; ++q) {
-                const double qi = rint(r);
-                r = (r - qi) * 128.0;                            // exact: |r - qi| <= 1/2
-                stg[q * 256 + (ty & 1) * 128 + tx + 16 * b] = (unsigned char)(__double2int_rn(qi) & 0xff);
+                for (int q = 0; q < S; ++q) {
+                    const double qi = rint(r);
+                    r = (r - qi) * 128.0;                            // exact: |r - qi| <= 1/2
+                    const uint32_t w = (uint32_t)__double2int_rn(qi);
+                    const uint32_t sel = (keep & ~(0xFu << pos)) | (4u << pos);
+                    if (b < 4) lo[q] = __byte_perm(lo[q], w, sel); else hi[q] = __byte_perm(hi[q], w, sel);
+                }
+            } else {
+                const unsigned long long dg = balanced_digits<S>(v * scale);
+                const uint32_t w0 = (uint32_t)dg, w1 = (uint32_t)(dg >> 32);
+#pragma unroll
+                for (int q = 0; q < S; ++q) {
+                    const int src = S - 1 - q;                       // digit q = byte S-1-q
+                    const uint32_t sel = (keep & ~(0xFu << pos)) | ((uint32_t)(4 + (src & 3)) << pos);
+                    const uint32_t w = src < 4 ? w0 : w1;
+                    if (b < 4) lo[q] = __byte_perm(lo[q], w, sel); else hi[q] = __byte_perm(hi[q], w, sel);
+                }
             }
         }
         part += __shfl_xor_sync(0xffffffffu, part, 1);
@@ -245,13 +268,9 @@ kmat_cross_i8_kernel(const double* __restrict__ Xs, long m_valid, const double* 
         part += __shfl_xor_sync(0xffffffffu, part, 4);
         part += __shfl_xor_sync(0xffffffffu, part, 8);
         if (tx == 0) smean[row] = part;
-        __syncwarp();
-        // lane -> 8 consecutive bytes of its own row (lane >> 4 == ty & 1): columns 8 (lane & 15) ..
-        int8_t* dst = planes + m * Np + (long)jb * TILE + (lane & 15) * 8;
+        int8_t* dst = planes + m * Np + (long)jb * TILE + tx * 8;
 #pragma unroll
-        for (int q = 0; q < S; ++q)
-            *reinterpret_cast<uint2*>(dst + q * pitch) = *reinterpret_cast<const uint2*>(stg + q * 256 + lane * 8);
-        __syncwarp();
+        for (int q = 0; q < S; ++q) *reinterpret_cast<uint2*>(dst + q * pitch) = make_uint2(lo[q], hi[q]);
     }
     __syncthreads();
     if (threadIdx.x < TILE) mean_part[(long)jb * Mc + (long)mb * TILE + threadIdx.x] = smean[threadIdx.x];
@@ -260,20 +279,22 @@ kmat_cross_i8_kernel(const double* __restrict__ Xs, long m_valid, const double* 
 template <int KIND>
 static int launch_kmat_cross_i8(const double* Xs, long m_valid, const double* X, int N, int D, const double* theta,
                                 const double* xa, const double* xr, const double* alpha, int8_t* planes, long plane_rows,
-                                int nslices, int Np, double* mean_part, int Mc, cudaStream_t st) {
-    const size_t smem = size_t(2) * MAXD * P_LD * 8 + 2 * TILE * 8 + 8 * size_t(nslices) * 256;
+                                int nslices, int bits, int Np, double* mean_part, int Mc, cudaStream_t st) {
+    const size_t smem = (size_t(2) * D * P_LD + 2 * TILE) * 8;
     const dim3 grid(Np / TILE, Mc / TILE);
-    if (nslices == 5) {
-        cudaFuncSetAttribute(kmat_cross_i8_kernel<KIND, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kmat_cross_i8_kernel<KIND, 5><<<grid, P_THREADS, smem, st>>>(Xs, m_valid, X, N, D, theta, xa, xr, alpha, planes,
-                                                                    plane_rows, Np, mean_part, Mc);
-    } else if (nslices == 6) {
-        cudaFuncSetAttribute(kmat_cross_i8_kernel<KIND, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kmat_cross_i8_kernel<KIND, 6><<<grid, P_THREADS, smem, st>>>(Xs, m_valid, X, N, D, theta, xa, xr, alpha, planes,
-                                                                    plane_rows, Np, mean_part, Mc);
-    } else {
-        return -8;
-    }
+#define GPX_KX(S_, B_)                                                                                                        \
+    do {                                                                                                                      \
+        if (smem > 48 * 1024)                                                                                                 \
+            cudaFuncSetAttribute(kmat_cross_i8_kernel<KIND, S_, B_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        kmat_cross_i8_kernel<KIND, S_, B_><<<grid, P_THREADS, smem, st>>>(Xs, m_valid, X, N, D, theta, xa, xr, alpha, planes, \
+                                                                          plane_rows, Np, mean_part, Mc);                     \
+    } while (0)
+    if (nslices == 5 && bits == 7) GPX_KX(5, 7);
+    else if (nslices == 6 && bits == 7) GPX_KX(6, 7);
+    else if (nslices == 5 && bits == 8) GPX_KX(5, 8);
+    else if (nslices == 6 && bits == 8) GPX_KX(6, 8);
+    else return -8;
+#undef GPX_KX
     GPX_CHECK_LAUNCH();
     return 0;
 }
@@ -585,9 +606,9 @@ int kmat_cross(const double* Xs, long m_valid, const double* X, int N, int D, co
 
 // Sliced-integer mode: K* written as `nslices` int8 planes [nslices][plane_rows][Np] (gpx_i8.cu).
 int kmat_cross_i8(const double* Xs, long m_valid, const double* X, int N, int D, const double* theta, const double* xa,
-                  const double* xr, int kind, const double* alpha, int8_t* planes, long plane_rows, int nslices, int Np,
+                  const double* xr, int kind, const double* alpha, int8_t* planes, long plane_rows, int nslices, int bits, int Np,
                   double* mean_part, int Mc, cudaStream_t st) {
-#define C_(KD) launch_kmat_cross_i8<KD>(Xs, m_valid, X, N, D, theta, xa, xr, alpha, planes, plane_rows, nslices, Np, mean_part, Mc, st)
+#define C_(KD) launch_kmat_cross_i8<KD>(Xs, m_valid, X, N, D, theta, xa, xr, alpha, planes, plane_rows, nslices, bits, Np, mean_part, Mc, st)
     GPX_DISPATCH_KIND(kind, C_)
 #undef C_
 }

@@ -435,63 +435,121 @@ int predict_meanvar_tf32(const double* Xs, long M, const double* X, int N, int D
 }
 
 // ---- sliced-integer mode (tcgen05 kind::i8, gpx_i8.cu) -------------------------------------------------------
-int slice_i8_matrix(const double* src, int rows, int cols, long ld_src, int8_t* planes, long plane_rows, int nslices, int tri,
-                    double* inv_scale, const double* amax_ptr, cudaStream_t st);
-int trmm_sumsq_i8(const int8_t* Ls, const double* inv_scale, int Np, const int8_t* Kp, int Mc, int nslices,
+int trmm_sumsq_i8(const int8_t* Ls, const double* inv_scale, int Np, const int8_t* Kp, int Mc, int nslices, int bits,
                   const double* amax_ptr, double* qpart, cudaStream_t st);
 int i8_row_tiles(int Np);
+int i8_max_np(int bits);
 int kmat_cross_i8(const double* Xs, long m_valid, const double* X, int N, int D, const double* theta, const double* xa,
-                  const double* xr, int kind, const double* alpha, int8_t* planes, long plane_rows, int nslices, int Np,
+                  const double* xr, int kind, const double* alpha, int8_t* planes, long plane_rows, int nslices, int bits, int Np,
                   double* mean_part, int Mc, cudaStream_t st);
 
-static int i8_fused_builder() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("GPX_I8_BUILDER"); v = (e && e[0] == 's') ? 0 : 1; }   // GPX_I8_BUILDER=split: FP64 K* + slicing pass
-    return v;
-}
-
+// workspace: two K* slice buffers [S][Mc][Np] int8 | two mean_part [nb][Mc] | two qpart [nt][Mc]   (double-buffered per chunk)
 size_t predict_i8_workspace_bytes(int Np, int Mc, int nslices) {
     const size_t nb = Np / TILE;
-    return (size_t)Mc * Np * 8 + (size_t)nslices * Mc * Np + (nb + i8_row_tiles(Np)) * (size_t)Mc * 8;
+    return 2 * ((size_t)nslices * Mc * Np + (nb + i8_row_tiles(Np)) * (size_t)Mc * 8);
 }
+size_t predict_i8_planes_offset(int Np, int Mc, int nslices, int buffer) { return (size_t)buffer * nslices * Mc * Np; }
 
-// As predict_meanvar; the variance contraction runs on the integer tensor cores from `nslices` 7-bit slices of L^-1
-// (Ls, inv_scale: gpx_slice_i8 of S, once per factorisation) and of each K* chunk (sliced here).  K* itself, the
-// posterior mean and the final reduction are the FP64 path's kernels, so the mean is bit-identical to predict_meanvar.
+// As predict_meanvar; the variance contraction runs on the integer tensor cores from `nslices` slices of `bits` bits of L^-1
+// (Ls, inv_scale: gpx_slice_i8 of S, once per factorisation) and of each K* chunk (written directly as slices by the builder).
+// K*, the posterior mean and the final reduction are evaluated exactly like the FP64 path's, so the mean is bit-identical
+// to predict_meanvar.
+//
+// Chunk pipeline: with `mma` (a second, higher-priority stream owned by the caller) the tensor-core kernel of chunk c runs on
+// `mma` while the K* builder of chunk c+1 runs on `st`: the builder is FP64-ALU work in <= 128 registers and a few KB of shared
+// memory per CTA, so its CTAs are resident on the same SMs as the tensor-core kernel's (one 183 KB CTA per SM for five slices) and
+// fill pipes that kernel leaves idle.  Order on `st`: builder(0), builder(1), [wait mma(0)] finalize(0), builder(2), [wait mma(1)]
+// finalize(1), ... -- everything the caller sees is ordered on `st`; buffer (c & 1) is rewritten by builder(c+2) only after
+// finalize(c).  mma == nullptr (or a single chunk): the same launches back to back on `st`.
 int predict_meanvar_i8(const double* Xs, long M, const double* X, int N, int D, const double* theta, const double* xa,
-                       const double* xr, int kind, const int8_t* Ls, const double* inv_scale, int nslices, int Np,
+                       const double* xr, int kind, const int8_t* Ls, const double* inv_scale, int nslices, int bits, int Np,
                        const double* alpha, const double* prior_mean, const int* feat_idx, int n_feat, int degree,
                        const double* weights, const double* bias, double y_mu, double y_sigma, double min_var,
-                       double* out_mean, double* out_std, void* workspace, size_t workspace_bytes, int Mc, cudaStream_t st) {
+                       double* out_mean, double* out_std, void* workspace, size_t workspace_bytes, int Mc, cudaStream_t st,
+                       cudaStream_t mma) {
     if (Mc <= 0 || Mc % TILE != 0) return -25;
     if (Np % TILE != 0 || Np < N) return -11;
     if (D > MAXD || D < 1) return -5;
+    if (Np > i8_max_np(bits)) return -13;
     if (workspace_bytes < predict_i8_workspace_bytes(Np, Mc, nslices)) return -23;
     const int nb = Np / TILE, nt = i8_row_tiles(Np);
-    double* Ks = reinterpret_cast<double*>(workspace);
-    int8_t* Kp = reinterpret_cast<int8_t*>(Ks + (size_t)Mc * Np);
-    double* mean_part = reinterpret_cast<double*>(Kp + (size_t)nslices * Mc * Np);
-    double* qpart = mean_part + (size_t)nb * Mc;
+    int8_t* Kp[2];
+    double* mean_part[2];
+    double* qpart[2];
+    Kp[0] = reinterpret_cast<int8_t*>(workspace);
+    Kp[1] = Kp[0] + (size_t)nslices * Mc * Np;
+    mean_part[0] = reinterpret_cast<double*>(Kp[1] + (size_t)nslices * Mc * Np);
+    mean_part[1] = mean_part[0] + (size_t)nb * Mc;
+    qpart[0] = mean_part[1] + (size_t)nb * Mc;
+    qpart[1] = qpart[0] + (size_t)nt * Mc;
     const double* amax = theta + D;          // K* <= outputscale for every kernel family here
-    for (long m0 = 0; m0 < M; m0 += Mc) {
-        const long mv = (M - m0 < Mc) ? (M - m0) : Mc;
-        const int mc = round_up((int)mv, TILE);
-        const double* xs = Xs + m0 * D;
-        int rc;
-        if (i8_fused_builder()) {
-            rc = kmat_cross_i8(xs, mv, X, N, D, theta, xa, xr, kind, alpha, Kp, mc, nslices, Np, mean_part, mc, st);
-        } else {
-            rc = kmat_cross(xs, mv, X, N, D, theta, xa, xr, kind, alpha, Ks, Np, mean_part, mc, st);
-            if (rc) return rc;
-            rc = slice_i8_matrix(Ks, mc, Np, Np, Kp, mc, nslices, 0, nullptr, amax, st);
+    const long n_chunks = (M + Mc - 1) / Mc;
+    const bool overlap = mma != nullptr && mma != st && n_chunks > 1;
+    cudaEvent_t ev_built[2] = {nullptr, nullptr}, ev_mma[2] = {nullptr, nullptr};
+    if (overlap) {
+        for (int i = 0; i < 2; ++i) {
+            if (cudaEventCreateWithFlags(&ev_built[i], cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&ev_mma[i], cudaEventDisableTiming) != cudaSuccess)
+                return -31;
         }
-        if (rc) return rc;
-        rc = trmm_sumsq_i8(Ls, inv_scale, Np, Kp, mc, nslices, amax, qpart, st);
-        if (rc) return rc;
-        predict_finalize_kernel<<<(int)((mv + 255) / 256), 256, 0, st>>>(
-            xs, mv, D, xa, xr, theta, mean_part, qpart, nb, mc, prior_mean ? prior_mean + m0 : nullptr, feat_idx,
-            n_feat, degree, weights, bias, y_mu, y_sigma, min_var, out_mean + m0, out_std + m0, nt);
     }
+    int rc = 0;
+    auto chunk_args = [&](long c, long& m0, long& mv, int& mc) {
+        m0 = c * Mc;
+        mv = (M - m0 < Mc) ? (M - m0) : Mc;
+        mc = round_up((int)mv, TILE);
+    };
+    auto build = [&](long c) -> int {
+        long m0, mv; int mc;
+        chunk_args(c, m0, mv, mc);
+        const int b = (int)(c & 1);
+        int r = kmat_cross_i8(Xs + m0 * D, mv, X, N, D, theta, xa, xr, kind, alpha, Kp[b], mc, nslices, bits, Np, mean_part[b], mc, st);
+        if (r == 0 && overlap) {
+            cudaEventRecord(ev_built[b], st);
+            cudaStreamWaitEvent(mma, ev_built[b], 0);
+        }
+        return r;
+    };
+    auto contract = [&](long c) -> int {
+        long m0, mv; int mc;
+        chunk_args(c, m0, mv, mc);
+        const int b = (int)(c & 1);
+        int r = trmm_sumsq_i8(Ls, inv_scale, Np, Kp[b], mc, nslices, bits, amax, qpart[b], overlap ? mma : st);
+        if (r == 0 && overlap) cudaEventRecord(ev_mma[b], mma);
+        return r;
+    };
+    auto finalize = [&](long c) {
+        long m0, mv; int mc;
+        chunk_args(c, m0, mv, mc);
+        const int b = (int)(c & 1);
+        if (overlap) cudaStreamWaitEvent(st, ev_mma[b], 0);
+        predict_finalize_kernel<<<(int)((mv + 255) / 256), 256, 0, st>>>(
+            Xs + m0 * D, mv, D, xa, xr, theta, mean_part[b], qpart[b], nb, mc, prior_mean ? prior_mean + m0 : nullptr, feat_idx,
+            n_feat, degree, weights, bias, y_mu, y_sigma, min_var, out_mean + m0, out_std + m0, nt);
+    };
+    // software pipeline over chunks: build(c+1) is enqueued before the wait for contract(c)
+    rc = build(0);
+    if (rc == 0) rc = contract(0);
+    for (long c = 0; c < n_chunks && rc == 0; ++c) {
+        if (c + 1 < n_chunks) {
+            rc = build(c + 1);
+            if (rc == 0) rc = contract(c + 1);      // on `mma` it queues behind contract(c); serial mode: after build(c+1) on `st`
+            if (rc) break;
+        }
+        finalize(c);
+    }
+    if (overlap) {
+        if (rc) {                                   // never leave `mma` work un-joined
+            cudaEvent_t j = nullptr;
+            if (cudaEventCreateWithFlags(&j, cudaEventDisableTiming) == cudaSuccess) {
+                cudaEventRecord(j, mma);
+                cudaStreamWaitEvent(st, j, 0);
+                cudaEventDestroy(j);
+            }
+        }
+        for (int i = 0; i < 2; ++i) { cudaEventDestroy(ev_built[i]); cudaEventDestroy(ev_mma[i]); }
+    }
+    if (rc) return rc;
     GPX_CHECK_LAUNCH();
     return 0;
 }

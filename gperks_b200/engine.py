@@ -22,9 +22,13 @@ from typing import Optional, Sequence
 import torch
 
 from . import _native as nv
-from .constants import AUTO_I8_MAX_N, AUTO_I8_MIN_N, AUTO_I8_SLICES
+from .constants import AUTO_I8_MAX_N, AUTO_I8_MIN_N, AUTO_I8_PROBE_POINTS, AUTO_I8_PROBE_POOL, AUTO_I8_SLICES
 
 F64 = torch.float64
+
+# precision name -> (slices, bits per slice) of the sliced-integer variance path (gpx_i8.cu)
+I8_MODES = {"int8x5": (5, 7), "int8x6": (6, 7), "int8x5w": (5, 8), "int8x6w": (6, 8)}
+PRECISIONS = ("fp64", "tf32x3", "tf32x3_fast") + tuple(I8_MODES)
 
 
 class NotPSDError(RuntimeError):
@@ -89,8 +93,10 @@ class ExactGPEngine:
         self.has_split = False
         self.S_hi: Optional[torch.Tensor] = None      # TF32 mode: (hi, lo) float split of L^-1
         self.S_lo: Optional[torch.Tensor] = None
-        self.i8_slices = 0                            # sliced-integer mode: number of int8 slices of L^-1 held (0 = none)
-        self._i8_probe = None                         # ((n_factorizations, slices, tol), ok) of the last int8_probe_ok()
+        self.i8_mode = None                           # sliced-integer mode: (slices, bits) of the int8 planes of L^-1 held (None = stale)
+        self._i8_probe = {}                           # precision -> (n_factorizations, tol, ok) of int8_probe_ok()
+        self._probe_set = None                        # (n_factorizations, points, their FP64 std)
+        self._mma_stream: Optional[torch.cuda.Stream] = None   # high-priority stream of the tensor-core kernel (chunk pipeline)
         # K_hat^-1 = L^-T L^-1 for the gradient: six-slice integer tensor-core product where its tiles pay and its int32 sums
         # cannot overflow (entries within ~1e-10 of their row/column scale of the DMMA result), else the FP64 DMMA lauum;
         # GPX_LAUUM=fp64 forces the latter
@@ -161,10 +167,15 @@ class ExactGPEngine:
             self._launch("gpx_solve_alpha", p(self.S), p(self.DT), self.Np, p(self.r), p(self.u), p(self.alpha), st)
             self._launch("gpx_mll_value", p(self.r), p(self.alpha), self.Np, self.N, p(self.logdet_blk),
                          p(self.out), st)
-        self.has_kinv = False
-        self.has_split = False
-        self.i8_slices = 0
         self.factor_key = key
+        self._mark_factorized()
+
+    def _mark_factorized(self, has_kinv: bool = False) -> None:
+        """Python-side state after K, S, DT, alpha, out have been (re)computed on the device -- by ``factorize`` or by a replayed
+        CUDA graph (train/batched.py): every cache derived from the previous factors is stale."""
+        self.has_kinv = has_kinv
+        self.has_split = False
+        self.i8_mode = None
         self.factored = True
         self.n_factorizations += 1
 
@@ -241,13 +252,14 @@ class ExactGPEngine:
         if M == 0:
             return out_mean, out_std
         Mc = int(chunk) if chunk else self.pick_chunk(M)
-        if precision not in ("fp64", "tf32x3", "tf32x3_fast", "int8x5", "int8x6"):
-            raise ValueError("precision must be 'fp64', 'int8x5', 'int8x6', 'tf32x3' or 'tf32x3_fast'")
-        # int8x5 / int8x6: the FP64 contraction from 5 / 6 signed 7-bit slices per operand on the integer tensor cores
-        # (exact int32 accumulation): std within ~5e-8 / 5e-9 of fp64, mean bit-identical (gpx_i8.cu)
-        i8 = int(precision[-1]) if precision.startswith("int8") else 0
-        if i8 and self.Np > 32768:
-            raise ValueError("the sliced-integer mode holds its sums in int32: N <= 32768")
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {PRECISIONS}")
+        # int8x5 / int8x6 (7-bit slices), int8x5w / int8x6w (8-bit slices): the FP64 contraction from 5 / 6 int8 slices per
+        # operand on the integer tensor cores (exact int32 accumulation), mean bit-identical to fp64 (gpx_i8.cu)
+        i8, i8_bits = I8_MODES.get(precision, (0, 0))
+        if i8 and self.Np > int(self.lib.gpx_i8_max_n(i8_bits)):
+            raise ValueError(f"the sliced-integer mode holds its sums in int32: N <= {int(self.lib.gpx_i8_max_n(i8_bits))} "
+                             f"for {i8_bits}-bit slices")
         # tf32x3: K* evaluated in FP64 then split (posterior mean bit-identical to fp64; variance on tcgen05);
         # tf32x3_fast: K* evaluated in FP32 as well (mean moves by ~1e-4 of its scale for noise-like targets)
         tf32 = precision.startswith("tf32")
@@ -259,7 +271,7 @@ class ExactGPEngine:
             Mc = (Mc + 255) // 256 * 256         # the tcgen05 kernel works on pairs of 128-point tiles
             ws_bytes = int(self.lib.gpx_predict_tf32_workspace_bytes(self.Np, Mc))
         elif i8:
-            self._ensure_i8(i8)
+            self._ensure_i8(i8, i8_bits)
             ws_bytes = int(self.lib.gpx_predict_i8_workspace_bytes(self.Np, Mc, i8))
         else:
             ws_bytes = int(self.lib.gpx_predict_workspace_bytes(self.Np, Mc))
@@ -280,10 +292,17 @@ class ExactGPEngine:
                              n_feat, degree, p(wts), p(bias), float(y_mu), float(y_sigma), float(min_var),
                              p(out_mean), p(out_std), p(ws), ws_bytes, Mc, kchunk, nv.stream_ptr())
             elif i8:
+                # chunk pipeline: the tensor-core kernel of chunk c on a high-priority stream of this engine while the K*
+                # builder of chunk c+1 runs on the current stream (GPX_I8_OVERLAP=0: everything on the current stream)
+                mma = None
+                if M > Mc and os.environ.get("GPX_I8_OVERLAP", "1") != "0" and not torch.cuda.is_current_stream_capturing():
+                    if self._mma_stream is None:
+                        self._mma_stream = torch.cuda.Stream(device=self.device, priority=-1)
+                    mma = self._mma_stream.cuda_stream
                 self._launch("gpx_predict_meanvar_i8", p(Xs), M, p(self.X), self.N, self.D, p(theta), p(xa), p(xr),
-                             self.kind, p(self.S_i8), p(self.S_i8_inv_scale), i8, self.Np, p(self.alpha), p(prior_mean),
-                             p(feat), n_feat, degree, p(wts), p(bias), float(y_mu), float(y_sigma), float(min_var),
-                             p(out_mean), p(out_std), p(ws), ws_bytes, Mc, nv.stream_ptr())
+                             self.kind, p(self.S_i8), p(self.S_i8_inv_scale), i8, i8_bits, self.Np, p(self.alpha),
+                             p(prior_mean), p(feat), n_feat, degree, p(wts), p(bias), float(y_mu), float(y_sigma),
+                             float(min_var), p(out_mean), p(out_std), p(ws), ws_bytes, Mc, nv.stream_ptr(), mma)
             else:
                 self._launch("gpx_predict_meanvar", p(Xs), M, p(self.X), self.N, self.D, p(theta), p(xa), p(xr),
                              self.kind, p(self.S), self.Np, p(self.alpha), p(prior_mean), p(feat), n_feat, degree,
@@ -303,33 +322,53 @@ class ExactGPEngine:
                          self.Np, nv.stream_ptr())
         self.has_split = True
 
-    def int8_probe_ok(self, slices: int, tol: float) -> bool:
-        """Guard of ``precision="auto"``: True when the sliced-integer std agrees with the FP64 (DMMA) std to ``tol`` on up to 128
-        training inputs (the points of smallest predictive variance, i.e. of strongest cancellation in s + noise - q) for the
-        CURRENT factors.  Evaluated once per factorisation (two 128-point predicts and one host read), then cached."""
-        key = (self.n_factorizations, int(slices), float(tol))
-        if self._i8_probe is not None and self._i8_probe[0] == key:
-            return self._i8_probe[1]
-        n = min(128, self.N)
-        xp = self.X[:n]
-        zero = torch.zeros(n, dtype=F64, device=self.device)
-        _, s64 = self.predict(xp, prior_mean=zero, precision="fp64")
-        _, s8 = self.predict(xp, prior_mean=zero, precision=f"int8x{int(slices)}")
+    def _probe_points(self):
+        """Probe set of the ``precision="auto"`` guard for the CURRENT factors: out of up to AUTO_I8_PROBE_POOL evenly strided
+        training inputs, the AUTO_I8_PROBE_POINTS of smallest FP64 (DMMA) predictive std -- where s + noise - q cancels the most,
+        i.e. where an absolute error of q costs the most relative accuracy -- and the same points moved by 1e-4 (the training
+        inputs live in the unit cube) along a fixed pseudo-random direction, so near-duplicates of training inputs are covered
+        too.  Returns (points, their FP64 std)."""
+        if self._probe_set is not None and self._probe_set[0] == self.n_factorizations:
+            return self._probe_set[1], self._probe_set[2]
+        stride = max(1, -(-self.N // AUTO_I8_PROBE_POOL))
+        pool = self.X[::stride]
+        zero = torch.zeros(pool.shape[0], dtype=F64, device=self.device)
+        _, s_pool = self.predict(pool, prior_mean=zero, precision="fp64")
+        k = min(AUTO_I8_PROBE_POINTS, pool.shape[0])
+        idx = torch.topk(s_pool, k, largest=False).indices
+        base = pool.index_select(0, idx)
+        g = torch.Generator(device="cpu").manual_seed(8)
+        shift = (torch.rand(k, self.D, generator=g, dtype=F64) - 0.5).to(self.device) * 2e-4
+        pts = torch.cat([base, base + shift], 0).contiguous()
+        _, s64 = self.predict(pts, prior_mean=torch.zeros(2 * k, dtype=F64, device=self.device), precision="fp64")
+        self._probe_set = (self.n_factorizations, pts, s64.clone())
+        return pts, self._probe_set[2]
+
+    def int8_probe_ok(self, precision: str, tol: float) -> bool:
+        """Guard of ``precision="auto"``: True when the sliced-integer std of mode ``precision`` agrees with the FP64 (DMMA) std to
+        ``tol`` on the probe set of ``_probe_points`` for the CURRENT factors.  Evaluated once per factorisation and mode (one
+        FP64 predict of the pool, two small predicts and one host read), then cached."""
+        hit = self._i8_probe.get(precision)
+        if hit is not None and hit[0] == self.n_factorizations and hit[1] == float(tol):
+            return hit[2]
+        pts, s64 = self._probe_points()
+        _, s8 = self.predict(pts, prior_mean=torch.zeros(pts.shape[0], dtype=F64, device=self.device), precision=precision)
         ok = bool(((s8 - s64).abs() <= tol * s64).all())
-        self._i8_probe = (key, ok)
+        self._i8_probe[precision] = (self.n_factorizations, float(tol), ok)
         return ok
 
-    def _ensure_i8(self, slices: int) -> None:
+    def _ensure_i8(self, slices: int, bits: int) -> None:
         """int8 slices and row scales of L^-1 for the sliced-integer variance path; refreshed after every factorisation."""
-        if self.i8_slices == slices:
+        if self.i8_mode == (slices, bits):
             return
         if self.S_i8 is None or self.S_i8.shape[0] != slices:
+            self.S_i8 = None
             self.S_i8 = torch.empty(slices, self.Np, self.Np, dtype=torch.int8, device=self.device)
             self.S_i8_inv_scale = torch.empty(self.Np, dtype=F64, device=self.device)
         with torch.cuda.device(self.device):
-            self._launch("gpx_slice_i8", nv.ptr(self.S), self.Np, self.Np, self.Np, nv.ptr(self.S_i8), self.Np, slices, 1,
+            self._launch("gpx_slice_i8", nv.ptr(self.S), self.Np, self.Np, self.Np, nv.ptr(self.S_i8), self.Np, slices, bits, 1,
                          nv.ptr(self.S_i8_inv_scale), None, nv.stream_ptr())
-        self.i8_slices = slices
+        self.i8_mode = (slices, bits)
 
     # ------------------------------------------------------------------------------------------
     def cross_kernel(self, Xs: torch.Tensor, xa=None, xr=None) -> torch.Tensor:

@@ -154,9 +154,7 @@ class _Runner:
                     if self.X_val is not None:
                         eng.predict(self.X_val, prior_mean=self.val_prior[r], out_mean=self.pred_val[r, 0],
                                     out_std=self.pred_val[r, 1])
-                # the graph bypassed the engine's Python-side bookkeeping
-                eng.factored, eng.has_kinv, eng.has_split = True, True, False
-                eng.n_factorizations += 1
+                eng._mark_factorized(has_kinv=True)                  # the graph bypassed the engine's Python-side bookkeeping
         self._last = (list(rows), theta.clone(), resid.clone())
 
 

@@ -32,7 +32,9 @@ from ..constants import (
     AUTO_I8_MAX_SCALE_TO_NOISE,
     AUTO_I8_MIN_N,
     AUTO_I8_PROBE_TOL,
-    AUTO_I8_SLICES,
+    AUTO_I8_W5_MAX_SCALE_TO_NOISE,
+    AUTO_I8_W6_MAX_SCALE_TO_NOISE,
+    AUTO_I8_WIDE_MAX_N,
     DEFAULT_PREDICT_CHUNK_BYTES,
     DEFAULT_TRAIN_MAX_EPOCH,
     DEFAULT_TRAIN_SNAPSHOT_DIR,
@@ -40,7 +42,7 @@ from ..constants import (
     DEFAULT_TRAIN_SNAPSHOT_RESTART_TEMPLATE,
 )
 from ..constraints import GreaterThan
-from ..engine import PolyMeanSpec
+from ..engine import NotPSDError, PolyMeanSpec
 from ..gp.experiment import GPExperiment
 from ..log.logger import get_logger
 from ..mlls import ExactMarginalLogLikelihood
@@ -308,17 +310,24 @@ class GPEmulator(Trainable):
             try:
                 loss = -self.criterion(self.model(X), y)
                 loss.backward()
-            except RuntimeError:        # not PSD even after jitter: reject the step
+            except NotPSDError:         # not PSD even after jitter: reject the step (any other error propagates)
+                rejected[0] = True
                 return 1e10, numpy.zeros_like(x)
+            rejected[0] = False
             g = numpy.concatenate([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).cpu().numpy()
                                    for p in params]).astype(numpy.float64)
             return float(loss.item()), g
 
         log.info("Training emulator...")
         self.model.train()
+        rejected = [False]
         x0 = numpy.concatenate([p.detach().reshape(-1).cpu().numpy() for p in params]).astype(numpy.float64)
         with torch.cuda.device(cdev):
             res = minimize(closure, x0, jac=True, method="L-BFGS-B", options={"maxiter": maxiter})
+            if not numpy.all(numpy.isfinite(res.x)) or closure(res.x)[0] >= 1e10 or rejected[0]:
+                set_flat(x0)
+                raise NotPSDError("train_auto: L-BFGS-B stopped on a point whose kernel matrix is not positive definite; "
+                                  "the model was reset to its starting hyper-parameters")
         set_flat(res.x)
         self.model.eval()
         log.info("Trained emulator.")
@@ -372,21 +381,37 @@ class GPEmulator(Trainable):
             return PolyMeanSpec(feat[:0].to(dev), degree, torch.zeros(0, dtype=F64, device=dev), b)
         return PolyMeanSpec(feat.to(dev).contiguous(), degree, w, b)
 
-    def resolve_precision(self, precision: str) -> str:
-        """``"auto"`` -> ``"int8x6"`` (FP64-grade variance from the integer tensor cores) where it is both safe and
-        faster, else ``"fp64"`` (DMMA); any other value is returned unchanged.  The decision uses only host-side values
-        (train size, outputscale / noise), see ``constants.AUTO_I8_*``."""
-        if precision != "auto":
-            return precision
+    def auto_precisions(self):
+        """The candidates of ``precision="auto"`` for this emulator, fastest first, always ending in ``"fp64"``: sliced-integer
+        modes (FP64-grade variance from the integer tensor cores) whose int32 sums cannot overflow at this train size and whose
+        error, amplified by outputscale / noise, stays inside 1e-6 -- see ``constants.AUTO_I8_*``.  Host-side values only."""
         n = int(self.scaled_data.X_train.shape[0])
         if not (AUTO_I8_MIN_N <= n <= AUTO_I8_MAX_N):
-            return "fp64"
+            return ["fp64"]
         with torch.no_grad():
             s = float(self.model.covar_module.outputscale)
             nz = float(self.model.likelihood.noise)
-        if not (nz > 0.0 and s > 0.0 and s / nz <= AUTO_I8_MAX_SCALE_TO_NOISE):
-            return "fp64"
-        return f"int8x{AUTO_I8_SLICES}"
+        if not (nz > 0.0 and s > 0.0):
+            return ["fp64"]
+        ratio = s / nz
+        n_pad = (n + 127) // 128 * 128
+        cands = []
+        if n_pad <= AUTO_I8_WIDE_MAX_N:
+            if ratio <= AUTO_I8_W5_MAX_SCALE_TO_NOISE:
+                cands.append("int8x5w")
+            if ratio <= AUTO_I8_W6_MAX_SCALE_TO_NOISE:
+                cands.append("int8x6w")
+        elif ratio <= AUTO_I8_MAX_SCALE_TO_NOISE:
+            cands.append("int8x6")
+        return cands + ["fp64"]
+
+    def resolve_precision(self, precision: str) -> str:
+        """``"auto"`` -> its first candidate (``auto_precisions``); any other value is returned unchanged.  ``predict`` /
+        ``predict_device`` additionally check the candidate against the FP64 path on a probe set once per factorisation
+        (``ExactGPEngine.int8_probe_ok``) and move down the list when it misses."""
+        if precision != "auto":
+            return precision
+        return self.auto_precisions()[0]
 
     def predict_device(self, x_dev: torch.Tensor, precision: str = "auto", tf32_kchunk: int = 32,
                        out_mean: Optional[torch.Tensor] = None, out_std: Optional[torch.Tensor] = None):
@@ -397,11 +422,10 @@ class GPEmulator(Trainable):
         cdev = self._compute_device()
         scx, scy = self.scaled_data.scx, self.scaled_data.scy
         auto = precision == "auto"
-        precision = self.resolve_precision(precision)
         with torch.no_grad(), torch.cuda.device(cdev):
             eng = self.model._factorized_engine()
-            if auto and precision.startswith("int8") and not eng.int8_probe_ok(int(precision[-1]), AUTO_I8_PROBE_TOL):
-                precision = "fp64"        # the sliced-integer std misses the FP64 std on the training inputs: stay on DMMA
+            if auto:        # first candidate whose std reproduces the FP64 std on the probe set of the current factors
+                precision = next(c for c in self.auto_precisions() if c == "fp64" or eng.int8_probe_ok(c, AUTO_I8_PROBE_TOL))
             M = x_dev.shape[0]
             xa = torch.as_tensor(numpy.asarray(scx.a, dtype=numpy.float64).reshape(-1), device=cdev)
             xr = torch.as_tensor((numpy.asarray(scx.b, dtype=numpy.float64)

@@ -126,28 +126,39 @@ int gpx_predict_meanvar_tf32(const double* Xs, long M, const double* X, int N, i
 
 /* ---- sliced-integer mode of the predictive variance: FP64-grade results from the integer tensor cores -------------
  * (tcgen05 kind::i8, exact int32 accumulation in TMEM; gperks_b200/csrc/gpx_i8.cu).  Operands are scaled by powers of
- * two and cut into nslices (5 or 6) signed 7-bit slices; the products of slices a+b < nslices are integer GEMMs, combined
- * in FP64.  std agrees with gpx_predict_meanvar to ~5e-8 relative with 5 slices (5e-7 at noise 1e-4) and ~5e-9 with 6, i.e.
- * inside the 1e-6 bar of the FP64 mode; the posterior mean is bit-identical (K* and the mean stay on the FP64 kernels).
- * gpx_slice_i8: planes[j][row][col] (int8, row pitch = cols, plane pitch = plane_rows*cols) <- slices of src[rows][cols]
- *   (leading dimension ld_src).  tri != 0: src is the mirrored inverse S of gpx_trtri; entries right of the diagonal are
- *   sliced as zero (columns beyond the row's 128-block are left untouched: never read) and every row gets its own scale,
- *   inv_scale[row] = 1/scale.  tri == 0: one scale for the whole matrix from the device scalar *amax_ptr >= max|src|
- *   (K* <= outputscale).  Run once per factorisation on S and once per chunk on K*.
+ * two and cut into `nslices` (5 or 6) int8 digits of `bits` bits; the products of slices a+b < nslices are integer GEMMs,
+ * combined in FP64.
+ *   bits = 7: signed 7-bit slices (|digit| <= 64, repeated round-to-nearest); N <= 32768.  std agrees with gpx_predict_meanvar to
+ *             ~5e-8 relative with 5 slices (5e-7 at noise 1e-4) and ~5e-9 with 6.
+ *   bits = 8: balanced radix-256 digits in [-128, 127] of the operand rounded ONCE to 8*nslices bits; N <= 16384 (= gpx_i8_max_n(8)).
+ *             Five slices (40 bits, 15 slice products) stand in for six 7-bit ones (42 bits, 21 products); six carry 48 bits.
+ * The posterior mean is bit-identical to gpx_predict_meanvar in every case (K* and the mean are evaluated in FP64).
+ * Plane layout: planes[j][row][p(col)] (int8, row pitch = cols, plane pitch = plane_rows*cols) with p permuting the columns
+ * inside every 128-block, p(c) = (c & ~127) | (c % 16) * 8 | (c % 128) / 16 -- identical on both operands, so every inner
+ * product is unchanged; it lets the K* builder store 8 consecutive bytes per slice straight from registers.
+ * gpx_slice_i8: planes <- slices of src[rows][cols] (leading dimension ld_src, cols % 128 == 0).  tri != 0: src is the mirrored
+ *   inverse S of gpx_trtri; entries right of the diagonal are sliced as zero (columns beyond the row's 128-block are left
+ *   untouched: never read) and every row gets its own scale, inv_scale[row] = 1/scale.  tri == 0: one scale for the whole matrix
+ *   from the device scalar *amax_ptr >= max|src| (K* <= outputscale).  Run once per factorisation on S.
  * gpx_trmm_sumsq_i8: qpart[it][m] = sum over the 64 rows of tile `it` of (K* L^-T)[m][i]^2, it < gpx_i8_row_tiles(Np);
- *   Mc multiple of 128, Np <= 32768 (int32 accumulators).
- * gpx_predict_meanvar_i8: as gpx_predict_meanvar with the variance contraction on the integer tensor cores.
+ *   Mc multiple of 128, Np <= gpx_i8_max_n(bits) (int32 accumulators).
+ * gpx_predict_meanvar_i8: as gpx_predict_meanvar with the variance contraction on the integer tensor cores.  Chunks are
+ *   double-buffered in the workspace; with a non-null `mma_stream` (a second stream of the caller, ideally of higher priority)
+ *   the tensor-core kernel of chunk c runs there while the K* builder of chunk c+1 runs on `stream` -- the two kernels are
+ *   co-resident on every SM.  All results are ordered on `stream`; `mma_stream` is joined before the call's last kernel.
+ *   The call creates and destroys four cudaEvents (no other state).
  * replaces: the same call sites as gpx_predict_meanvar (GPErks/train/emulator.py:348-363). */
 int gpx_slice_i8(const double* src, int rows, int cols, long ld_src, signed char* planes, long plane_rows, int nslices,
-                 int tri, double* inv_scale, const double* amax_ptr, void* stream);
+                 int bits, int tri, double* inv_scale, const double* amax_ptr, void* stream);
 int gpx_i8_row_tiles(int Np);
+int gpx_i8_max_n(int bits);
 /* gpx_kmat_cross_i8: gpx_kmat_cross and gpx_slice_i8 (tri = 0, amax = outputscale) in one pass: the K* chunk is evaluated in
  * FP64 and written only as its int8 slices (same bytes, same mean_part as the two calls). */
 int gpx_kmat_cross_i8(const double* Xs, long m_valid, const double* X, int N, int D, const double* theta, const double* xa,
                       const double* xr, int kind, const double* alpha, signed char* planes, long plane_rows, int nslices,
-                      int Np, double* mean_part, int Mc, void* stream);
+                      int bits, int Np, double* mean_part, int Mc, void* stream);
 int gpx_trmm_sumsq_i8(const signed char* Ls, const double* inv_scale, int Np, const signed char* Kp, int Mc, int nslices,
-                      const double* amax_ptr, double* qpart, void* stream);
+                      int bits, const double* amax_ptr, double* qpart, void* stream);
 /* gpx_lauum_i8: gpx_lauum on the integer tensor cores.  The columns of L^-1 (rows of L^-T: DT inside the diagonal blocks, the
  * mirrored blocks of S beside them) are sliced with one power-of-two scale per column into the workspace, and
  * Kinv = L^-T L^-1 is formed by the same kind::i8 kernel (store epilogue) for the 128-tiles on and below the diagonal -- the
@@ -166,12 +177,14 @@ size_t gpx_lauum_i8_workspace_bytes(int Np, int nslices);
 int gpx_lauum_i8(const double* S, const double* DT, double* Kinv, int Np, int nslices, void* workspace, size_t workspace_bytes,
                  void* stream);
 size_t gpx_predict_i8_workspace_bytes(int Np, int Mc, int nslices);
+/* byte offset inside the workspace of the K* slice planes of chunk buffer 0 / 1 (what the last chunks left there; timing tools) */
+size_t gpx_predict_i8_planes_offset(int Np, int Mc, int nslices, int buffer);
 int gpx_predict_meanvar_i8(const double* Xs, long M, const double* X, int N, int D, const double* theta, const double* xa,
-                           const double* xr, int kind, const signed char* Ls, const double* inv_scale, int nslices, int Np,
-                           const double* alpha, const double* prior_mean, const int* feat_idx, int n_feat, int degree,
+                           const double* xr, int kind, const signed char* Ls, const double* inv_scale, int nslices, int bits,
+                           int Np, const double* alpha, const double* prior_mean, const int* feat_idx, int n_feat, int degree,
                            const double* weights, const double* bias, double y_mu, double y_sigma, double min_var,
                            double* out_mean, double* out_std, void* workspace, size_t workspace_bytes, int Mc,
-                           void* stream);
+                           void* stream, void* mma_stream);
 
 /* History-matching epilogue over E emulators: I[m] = maxno-th largest_e sqrt((mean[e][m]-z[e])^2/(std[e][m]^2+v[e])),
  * PV[m] = maxno-th largest_e std[e][m]^2/v[e]; inputs emulator-major [E][M]; 1 <= maxno <= min(E, 8).

@@ -520,67 +520,87 @@ def test_emulator_predict_tf32_precision(dev, goldens):
 # ----------------------------------------------------------------------------------------------------
 # Sliced-integer mode (tcgen05 kind::i8, exact int32 accumulation): inside the FP64 bar, rel 1e-6 on std
 # ----------------------------------------------------------------------------------------------------
-def test_i8_kernel_exact_on_integer_slices(dev):
+@pytest.mark.parametrize("bits", [7, 8])
+def test_i8_kernel_exact_on_integer_slices(dev, bits):
     """The integer contraction is exact: qpart must equal, bit for bit up to the FP64 combination of the diagonals, the same
-    slices multiplied in float64 -- pins the TMA swizzle, the stacked-slice UMMA descriptors and the TMEM epilogue."""
+    slices multiplied in float64 -- pins the TMA swizzle, the stacked-slice UMMA descriptors, the persistent tile loop (several
+    work items per cluster at the larger shapes) and the TMEM epilogue.  8-bit slices use the whole int8 range."""
     lib = nv.lib()
-    for S, Np, Mc in [(5, 128, 128), (5, 256, 256), (6, 384, 128), (5, 1024, 384), (6, 1152, 256)]:
+    lo_, hi_ = (-64, 65) if bits == 7 else (-128, 128)
+    for S, Np, Mc in [(5, 128, 128), (5, 256, 256), (6, 384, 128), (5, 1024, 384), (6, 1152, 256), (5, 2048, 2304), (6, 1024, 5120)]:
         g = torch.Generator(device="cpu").manual_seed(Np + S)
-        Ls = torch.randint(-64, 65, (S, Np, Np), generator=g, dtype=torch.int64).to(torch.int8)
+        Ls = torch.randint(lo_, hi_, (S, Np, Np), generator=g, dtype=torch.int64).to(torch.int8)
         Ls = torch.tril(Ls).contiguous().to(dev)
-        Kp = torch.randint(-64, 65, (S, Mc, Np), generator=g, dtype=torch.int64).to(torch.int8).to(dev)
+        Kp = torch.randint(lo_, hi_, (S, Mc, Np), generator=g, dtype=torch.int64).to(torch.int8).to(dev)
         e = torch.randint(-3, 4, (Np,), generator=g)
         inv_scale = torch.ldexp(torch.ones(Np, dtype=F64), e.to(torch.int32)).to(dev)
         amax = torch.tensor([1.3], dtype=F64, device=dev)           # frexp exponent 1 -> 1/scale_K = 4
         nt = lib.gpx_i8_row_tiles(Np)
         q = torch.full((nt, Mc), -1.0, dtype=F64, device=dev)
-        nv.check(lib.gpx_trmm_sumsq_i8(nv.ptr(Ls), nv.ptr(inv_scale), Np, nv.ptr(Kp), Mc, S, nv.ptr(amax), nv.ptr(q),
+        nv.check(lib.gpx_trmm_sumsq_i8(nv.ptr(Ls), nv.ptr(inv_scale), Np, nv.ptr(Kp), Mc, S, bits, nv.ptr(amax), nv.ptr(q),
                                        nv.stream_ptr()), "i8")
         V = torch.zeros(Np, Mc, dtype=F64, device=dev)
         for a in range(S):
             for b in range(S - a):
-                V += (Ls[b].double() @ Kp[a].double().T) * 2.0 ** (-7 * (a + b + 2))
+                V += (Ls[b].double() @ Kp[a].double().T) * 2.0 ** (-bits * (a + b + 2))
         V = V * inv_scale.view(-1, 1) * 4.0
         ref = (V * V).view(nt, 64, Mc).sum(1)
         np.testing.assert_allclose(q.cpu().numpy(), ref.cpu().numpy(), rtol=1e-13, atol=0)
 
 
-def test_i8_slices_reconstruct_the_operand(dev):
+def _unpermute_planes(planes):
+    """Plane column p(c) = (c % 16) * 8 + (c % 128) // 16 inside every 128-block holds logical column c (include/gpx.h)."""
+    cols = planes.shape[-1]
+    c = torch.arange(cols, device=planes.device)
+    p = (c // 128) * 128 + (c % 16) * 8 + (c % 128) // 16
+    return planes.index_select(-1, p)
+
+
+@pytest.mark.parametrize("bits", [7, 8])
+def test_i8_slices_reconstruct_the_operand(dev, bits):
     lib = nv.lib()
     g = torch.Generator(device="cpu").manual_seed(3)
     rows, cols = 300, 384
     A = (torch.randn(rows, cols, generator=g, dtype=F64) * torch.logspace(-3, 1, rows, dtype=F64).view(-1, 1)).to(dev)
+    A[7, 5] = A.abs().max() * 1.7        # the maximum sits at a known place ...
+    A[11, 300] = -0.998 * 8.0            # ... and one row's maximum is 0.998 * 2^3: 8-bit digits need the extra head-room bit there
+    digit_max = 64 if bits == 7 else 128
     for S in (5, 6):
-        w = torch.tensor([2.0 ** (-7 * (j + 1)) for j in range(S)], dtype=F64, device=dev).view(S, 1, 1)
+        w = torch.tensor([2.0 ** (-bits * (j + 1)) for j in range(S)], dtype=F64, device=dev).view(S, 1, 1)
         # one scale for the matrix
         amax = A.abs().max().reshape(1).contiguous()
         planes = torch.empty(S, rows, cols, dtype=torch.int8, device=dev)
-        nv.check(lib.gpx_slice_i8(nv.ptr(A), rows, cols, cols, nv.ptr(planes), rows, S, 0, None, nv.ptr(amax), nv.stream_ptr()), "slice")
-        assert int(planes.abs().max()) <= 64
+        nv.check(lib.gpx_slice_i8(nv.ptr(A), rows, cols, cols, nv.ptr(planes), rows, S, bits, 0, None, nv.ptr(amax), nv.stream_ptr()), "slice")
+        assert int(planes.to(torch.int32).abs().max()) <= digit_max
+        planes = _unpermute_planes(planes)
         import math
-        inv = 2.0 ** (math.frexp(float(amax))[1] + 1)
+        f, e = math.frexp(float(amax))
+        inv = 2.0 ** (e + 1 + (1 if bits == 8 and f > 0.9953 else 0))
         rec = (planes.double() * w).sum(0) * inv
-        assert float((rec - A).abs().max()) <= inv * 2.0 ** (-7 * S - 1) * (1 + 1e-12)
+        assert float((rec - A).abs().max()) <= inv * 2.0 ** (-bits * S - 1) * (1 + 1e-12)
         # per-row scales, entries right of the diagonal treated as zero (square input)
         B = A[:, :rows].contiguous() if rows <= cols else A
         Bp = torch.zeros(384, 384, dtype=F64, device=dev)
         Bp[:rows, :rows] = B
         planes = torch.zeros(S, 384, 384, dtype=torch.int8, device=dev)
         inv_scale = torch.empty(384, dtype=F64, device=dev)
-        nv.check(lib.gpx_slice_i8(nv.ptr(Bp), 384, 384, 384, nv.ptr(planes), 384, S, 1, nv.ptr(inv_scale), None, nv.stream_ptr()), "slice")
-        assert int(planes.abs().max()) <= 64
-        rec = (planes.double() * w).sum(0) * inv_scale.view(-1, 1)
+        nv.check(lib.gpx_slice_i8(nv.ptr(Bp), 384, 384, 384, nv.ptr(planes), 384, S, bits, 1, nv.ptr(inv_scale), None, nv.stream_ptr()), "slice")
+        assert int(planes.to(torch.int32).abs().max()) <= digit_max
+        rec = (_unpermute_planes(planes).double() * w).sum(0) * inv_scale.view(-1, 1)
         low = torch.tril(Bp)
         assert float(torch.triu(rec, 1).abs().max()) == 0.0
         err = (rec - low).abs().max(dim=1).values
-        assert bool((err <= inv_scale * 2.0 ** (-7 * S - 1) * (1 + 1e-12)).all())
+        assert bool((err <= inv_scale * 2.0 ** (-bits * S - 1) * (1 + 1e-12)).all())
         rowmax = low.abs().max(dim=1).values
         ok = rowmax > 0
-        assert bool((rowmax[ok] * 2 <= inv_scale[ok]).all()) and bool((inv_scale[ok] <= rowmax[ok] * 4).all())
+        assert bool((rowmax[ok] * 2 <= inv_scale[ok]).all()) and bool((inv_scale[ok] <= rowmax[ok] * (4 if bits == 7 else 8)).all())
+        if bits == 8:                    # the head-room rule: |x| / inv_scale <= 127.4 / 256 in every row
+            assert bool((rowmax[ok] / inv_scale[ok] <= 127.4 / 256).all())
 
 
+@pytest.mark.parametrize("bits", [7, 8])
 @pytest.mark.parametrize("kind", [O.KIND_RBF, O.KIND_MATERN12, O.KIND_MATERN32, O.KIND_MATERN52])
-def test_fused_i8_builder_equals_kmat_cross_plus_slicing(dev, kind):
+def test_fused_i8_builder_equals_kmat_cross_plus_slicing(dev, kind, bits):
     """gpx_kmat_cross_i8 writes the very bytes gpx_slice_i8 makes of gpx_kmat_cross' FP64 chunk, and the same mean partials."""
     lib = nv.lib()
     N, D, M = 300, 5, 200
@@ -595,11 +615,11 @@ def test_fused_i8_builder_equals_kmat_cross_plus_slicing(dev, kind):
     amax = eng.theta[D:D + 1].contiguous()
     for S in (5, 6):
         p1 = torch.empty(S, Mc, Np, dtype=torch.int8, device=dev)
-        nv.check(lib.gpx_slice_i8(nv.ptr(Ks), Mc, Np, Np, nv.ptr(p1), Mc, S, 0, None, nv.ptr(amax), nv.stream_ptr()), "slice")
+        nv.check(lib.gpx_slice_i8(nv.ptr(Ks), Mc, Np, Np, nv.ptr(p1), Mc, S, bits, 0, None, nv.ptr(amax), nv.stream_ptr()), "slice")
         p2 = torch.empty(S, Mc, Np, dtype=torch.int8, device=dev)
         mp2 = torch.empty(eng.nb, Mc, dtype=F64, device=dev)
         nv.check(lib.gpx_kmat_cross_i8(nv.ptr(xs), M, nv.ptr(eng.X), N, D, nv.ptr(eng.theta), None, None, kind, nv.ptr(eng.alpha),
-                                       nv.ptr(p2), Mc, S, Np, nv.ptr(mp2), Mc, nv.stream_ptr()), "kmat_cross_i8")
+                                       nv.ptr(p2), Mc, S, bits, Np, nv.ptr(mp2), Mc, nv.stream_ptr()), "kmat_cross_i8")
         assert torch.equal(p1, p2)
         assert torch.equal(mp1, mp2)
 
@@ -612,15 +632,16 @@ def test_int8_mode_within_fp64_tolerance(dev, N, D, M, kind, nz):
     eng = _engine(dev, X, y, kind, ls, s, nz, w, b)
     pm = (Xs @ w + b).to(dev)
     m64, s64 = eng.predict(Xs.to(dev), prior_mean=pm)
-    # five slices hold 1e-6 down to noise ~1e-3 of the outputscale (the cancellation in s + noise - q amplifies the slicing
-    # error by ~outputscale/noise); six slices hold 1e-7 at the likelihood's noise floor of 1e-4
-    for prec, tol in (("int8x5", 1e-6 if nz >= 1e-3 else 2e-5), ("int8x6", 2e-7)):
+    # five 7-bit slices hold 1e-6 down to noise ~1e-3 of the outputscale (the cancellation in s + noise - q amplifies the slicing
+    # error by ~outputscale/noise); six hold 1e-7 at the likelihood's noise floor of 1e-4; five 8-bit slices (40 bits) sit between
+    # the two and are what "auto" uses up to outputscale/noise = 1e4; six 8-bit slices (48 bits) are 64 x finer than six 7-bit ones
+    for prec, tol in (("int8x5", 1e-6 if nz >= 1e-3 else 2e-5), ("int8x6", 2e-7), ("int8x5w", 1e-6), ("int8x6w", 2e-8)):
         mi, si = eng.predict(Xs.to(dev), prior_mean=pm, precision=prec)
         assert torch.equal(m64, mi)               # K* and the mean stay on the FP64 kernels
         rel = float(((si - s64).abs() / s64).max())
         assert rel < tol, (prec, rel)
         mi2, si2 = eng.predict(Xs.to(dev), prior_mean=pm, precision=prec, chunk=256)
-        assert torch.equal(si, si2)               # chunking never changes a bit
+        assert torch.equal(si, si2) and torch.equal(mi, mi2)       # chunking (and the two-stream chunk pipeline) never changes a bit
     if N <= 1000:
         _, vref = O.predict(X, y, kind, ls, s, nz, X @ w + b, Xs, Xs @ w + b)
         np.testing.assert_allclose(si.cpu().numpy(), vref.sqrt().numpy(), rtol=1e-6)     # the FP64 bar of north_star
@@ -698,14 +719,15 @@ def test_emulator_auto_precision(dev):
     from gperks_b200.train.emulator import GPEmulator
     rng = np.random.default_rng(5)
     D = 4
-    for n, noise, want in ((1100, 1e-2, "int8x6"), (1100, 1e-4, "int8x6"), (1100, 1e-6, "fp64"), (300, 1e-2, "fp64")):
+    for n, noise, want in ((1100, 1e-2, "int8x5w"), (1100, 1e-4, "int8x6w"), (1100, 1e-6, "int8x6w"), (1100, 1e-7, "fp64"),
+                           (300, 1e-2, "fp64")):
         X = rng.random((n, D))
         y = np.sin(3 * X[:, 0]) + X[:, 1] * X[:, 2] + 0.05 * rng.standard_normal(n)
         exp = GPExperiment(Dataset(X, y), GaussianLikelihood(), LinearMean(1, D), ScaleKernel(MaternKernel(nu=2.5, ard_num_dims=D)),
                            n_restarts=1, seed=8)
         if noise < 1e-4:
             from gperks_b200.constraints import GreaterThan
-            exp.model.likelihood.noise_covar.register_constraint("raw_noise", GreaterThan(1e-7))
+            exp.model.likelihood.noise_covar.register_constraint("raw_noise", GreaterThan(1e-9))
         em = GPEmulator(exp, "cuda:0")
         em.model.covar_module.base_kernel.lengthscale = torch.tensor([0.4, 0.6, 0.9, 1.3], dtype=torch.float64)
         em.model.covar_module.outputscale = 1.5
@@ -722,7 +744,8 @@ def test_emulator_auto_precision(dev):
             assert np.array_equal(s_auto, s64)
         else:
             eng = em.model._factorized_engine()
-            assert eng.i8_slices == 6 and eng._i8_probe is not None and eng._i8_probe[1]       # the guard ran and passed
+            from gperks_b200.engine import I8_MODES
+            assert eng.i8_mode == I8_MODES[want] and eng._i8_probe[want][2]       # the guard ran and passed
     # the guard itself: with an unattainable tolerance "auto" must fall back to the FP64 path, bit for bit
     import gperks_b200.train.emulator as E
     old_tol = E.AUTO_I8_PROBE_TOL
@@ -734,12 +757,13 @@ def test_emulator_auto_precision(dev):
                            n_restarts=1, seed=8)
         em = GPEmulator(exp, "cuda:0")
         em.model.likelihood.noise = 1e-2
-        assert em.resolve_precision("auto") == "int8x6"
+        assert em.auto_precisions() == ["int8x5w", "int8x6w", "fp64"]
         Xq = rng.random((500, D))
         m_a, s_a = em.predict(Xq)
         m_f, s_f = em.predict(Xq, precision="fp64")
         assert np.array_equal(m_a, m_f) and np.array_equal(s_a, s_f)
-        assert em.model._factorized_engine()._i8_probe[1] is False
+        probe = em.model._factorized_engine()._i8_probe
+        assert probe["int8x5w"][2] is False and probe["int8x6w"][2] is False        # both candidates were tried and refused
     finally:
         E.AUTO_I8_PROBE_TOL = old_tol
 
@@ -750,9 +774,10 @@ def test_emulator_predict_int8_precision(dev, goldens):
     rng = np.random.default_rng(1)
     Xq = rng.random((3000, 2))
     m64, s64 = em.predict(Xq)
-    m8, s8 = em.predict(Xq, precision="int8x5")
-    assert np.array_equal(m64, m8)
-    np.testing.assert_allclose(s8, s64, rtol=1e-6)
+    for prec in ("int8x5", "int8x5w", "int8x6w"):
+        m8, s8 = em.predict(Xq, precision=prec)
+        assert np.array_equal(m64, m8)
+        np.testing.assert_allclose(s8, s64, rtol=1e-6)
 
 
 def test_validation_loss_and_covariance_kernels_match_oracle(dev):

@@ -80,13 +80,17 @@ def test_auto_precision_is_resolved_from_host_values():
     assert small.resolve_precision("auto") == "fp64"
     big.model.covar_module.outputscale = 1.0
     big.model.likelihood.noise = 1e-2
-    assert big.resolve_precision("auto") == f"int8x{K.AUTO_I8_SLICES}"
+    assert big.auto_precisions() == ["int8x5w", "int8x6w", "fp64"] and big.resolve_precision("auto") == "int8x5w"
     big.model.likelihood.noise = 1e-3
-    big.model.covar_module.outputscale = 0.99e-3 * K.AUTO_I8_MAX_SCALE_TO_NOISE
-    assert big.resolve_precision("auto") == f"int8x{K.AUTO_I8_SLICES}"
-    big.model.covar_module.outputscale = 1.01e-3 * K.AUTO_I8_MAX_SCALE_TO_NOISE          # outputscale / noise above the limit
-    assert big.resolve_precision("auto") == "fp64"
-    for p in ("fp64", "int8x5", "int8x6", "tf32x3", "tf32x3_fast"):
+    big.model.covar_module.outputscale = 0.99e-3 * K.AUTO_I8_W5_MAX_SCALE_TO_NOISE
+    assert big.resolve_precision("auto") == "int8x5w"
+    big.model.covar_module.outputscale = 1.01e-3 * K.AUTO_I8_W5_MAX_SCALE_TO_NOISE       # five 8-bit slices no longer hold 1e-6
+    assert big.auto_precisions() == ["int8x6w", "fp64"]
+    big.model.covar_module.outputscale = 1.01e-3 * K.AUTO_I8_W6_MAX_SCALE_TO_NOISE       # outputscale / noise above every limit
+    assert big.auto_precisions() == ["fp64"] and big.resolve_precision("auto") == "fp64"
+    # 8-bit slices keep their int32 sums exact up to a padded train size of 16384; beyond, six 7-bit slices up to 32768
+    assert K.AUTO_I8_WIDE_MAX_N == 16384 and K.AUTO_I8_MAX_N == 32768
+    for p in ("fp64", "int8x5", "int8x6", "int8x5w", "int8x6w", "tf32x3", "tf32x3_fast"):
         assert big.resolve_precision(p) == p
 
 
