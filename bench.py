@@ -1,20 +1,30 @@
 #!/usr/bin/env python
 """Headline benchmark: GPEmulator.predict (mean + noisy std) throughput, N_train=8192, D=8, Matern-5/2 ARD
-(BASELINE.json configs[1]), on 1..8 B200s of one node.
+(BASELINE.json configs[1]), on 1..8 B200s of one node, with MLL+gradient evaluations/s beside it.
 
     python bench.py --gpus 1 --steps 3 --warmup 3
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
     python bench.py --impl reference ...      # the reference's CPU path (float64 oracle, all host threads)
+    python bench.py --workload kfold ...      # BASELINE configs[4]: 5 folds x 8 restarts of N=32768, D=16, one fit per GPU
 
 A step = one pass of the predict hot path over M points per GPU (weak scaling: each rank owns its own M-point
 shard; factors L^-1 and alpha are replicated; the only collective is the final gather of the 16 B/point
 results).  `value` = points all ranks processed / max-over-ranks device time with X* resident in HBM;
 `e2e` = the same through GPEmulator.predict with host numpy buffers (pinned H2D + D2H inside the timed
-region).  Both run at the precision GPEmulator.predict uses by default for this emulator (`--precision auto`: the
-FP64 variance contraction from six 7-bit integer slices on tcgen05 kind::i8, std within 1e-8 of the FP64 DMMA path,
-reported under `accuracy`); the FP64 DMMA path itself is timed beside it (`fp64_dmma_mode`, or `--precision fp64` to
-make it the headline), as are the TF32 mode and the five-slice edition.  One JSON line on stdout (rank 0)."""
+region), `--steps` steps.  Both run at the precision GPEmulator.predict uses by default for this emulator
+(`--precision auto` -> five 8-bit integer slices on tcgen05 kind::i8, checked against the FP64 path in `config.accuracy`).
+
+Everything else the metric names lives in keys the driver keeps:
+  config.mll_grad          MLL + gradient evaluations/s at N=8192 (the second half of BASELINE's metric)
+  config.fp64_dmma_mode    the same predict with the variance contraction on the FP64 tensor path (DMMA) + its roofline
+  config.accuracy          every point of a timed step against the FP64 arm
+  config.strong_scaling    ONE fixed X* of 1e7 points through the product's multi-GPU API gperks_b200.parallel.sharded_predict
+                           (scatter rows from rank 0 -> predict -> gather to rank 0), wall clock on rank 0, and a bit-for-bit
+                           comparison of the gathered result with single-GPU predicts of two slices
+  config.config1           BASELINE configs[0] (N=200, D=8, RBF + LinearMean, Adam epochs, predict 1e4 points) beside the oracle on the host
+  roofline                 the dominant kernel of the headline step, timed alone with CUDA events on its stream
+One JSON line on stdout (rank 0)."""
 from __future__ import annotations
 
 import argparse
@@ -25,9 +35,8 @@ import subprocess
 import sys
 import threading
 import time
-from pathlib import Path
-
 import warnings
+from pathlib import Path
 
 import numpy as np
 import torch
@@ -38,10 +47,20 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 N_TRAIN, DIM = 8192, 8
-NCU_TRAFFIC_I8_BYTES = {"int8x6": 11.877e9}      # dram read+write per launch of trmm_sumsq_i8_kernel<6>, profiles/r01_ncu_i8.txt (N=8192, chunk 32768)
-NCU_TRAFFIC_BYTES = 13.546e9   # dram read+write per launch, profiles/r01_ncu_trmm_tma.txt (N=8192, chunk 32768)
 KIND_NAME = "matern52"
 NOISE = 1e-2
+WORKLOAD = "configs[1]: Matern-5/2 ARD emulator, N_train=8192 D=8, predict mean+noisy std"
+METRIC = "predict points/sec (mean+var) N=8192 D=8"
+
+
+def ncu_traffic_bytes(kernel_key: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
+    capture (profiles/ncu_traffic.json, written by tools/ncu_summary.py --traffic); None when no capture exists for it."""
+    try:
+        table = json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text())
+        return table.get(kernel_key, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
 
 
 def synthetic_problem(n_train=N_TRAIN, dim=DIM, m=1_000_000, seed=8, rank=0):
@@ -54,22 +73,22 @@ def synthetic_problem(n_train=N_TRAIN, dim=DIM, m=1_000_000, seed=8, rank=0):
     delta = np.random.default_rng(seed).random(dim)
     frac = X + delta - np.floor(X + delta)
     y = np.prod((2.0 * np.abs(2 * frac - 1) + a) / (1 + a), axis=1)
-    Xs = qmc.Sobol(d=dim, scramble=True, seed=seed + 1 + rank).random(m)
+    Xs = qmc.Sobol(d=dim, scramble=True, seed=seed + 1 + rank).random(m) if m > 0 else np.empty((0, dim))
     hyper = dict(lengthscale=[0.5 * (1 + d / dim) for d in range(dim)], outputscale=1.0, noise=NOISE,
                  weights=np.linspace(-1, 1, dim).tolist(), bias=0.1)
     return X, y, Xs, hyper
 
 
-def build_emulator(X, y, hyper, device):
+def build_emulator(X, y, hyper, device, kernel="matern52"):
     from gperks_b200.gp.data.dataset import Dataset
     from gperks_b200.gp.experiment import GPExperiment
     from gperks_b200.gp.mean import LinearMean
-    from gperks_b200.kernels import MaternKernel, ScaleKernel
+    from gperks_b200.kernels import MaternKernel, RBFKernel, ScaleKernel
     from gperks_b200.likelihoods import GaussianLikelihood
     from gperks_b200.train.emulator import GPEmulator
     D = X.shape[1]
-    exp = GPExperiment(Dataset(X, y), GaussianLikelihood(), LinearMean(1, D), ScaleKernel(MaternKernel(nu=2.5, ard_num_dims=D)),
-                       n_restarts=1, seed=8)
+    base = MaternKernel(nu=2.5, ard_num_dims=D) if kernel == "matern52" else RBFKernel(ard_num_dims=D)
+    exp = GPExperiment(Dataset(X, y), GaussianLikelihood(), LinearMean(1, D), ScaleKernel(base), n_restarts=1, seed=8)
     em = GPEmulator(exp, device)
     t = lambda v: torch.as_tensor(v, dtype=torch.float64)  # noqa: E731
     m = em.model
@@ -112,12 +131,14 @@ class ClockSampler:
         self._t.join(timeout=6)
 
     def summary(self):
-        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        num = lambda s: s.replace(".", "", 1).isdigit()  # noqa: E731
+        sm = [float(s[0]) for s in self.samples if s and num(s[0])]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and num(s[1])]
+        pw = [float(s[2]) for s in self.samples if len(s) > 2 and num(s[2])]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({n for s in self.samples for n, v in zip(names, s[3:7]) if v.lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.samples)}
+                "power_w_median": float(np.median(pw)) if pw else None, "reasons": reasons, "samples": len(self.samples)}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -194,19 +215,18 @@ def run_reference(args):
     if rank != 0:
         return
     X, y, Xs, hyper = synthetic_problem(m=max(args.ref_points, 4096))
-    rates, secs = [], []
+    secs = []
     for i in range(args.warmup + args.steps):
         r, t_pred, t_fac, threads = cpu_oracle_predict_rate(X, y, Xs, hyper, args.ref_points)
         if i >= args.warmup:
-            rates.append(r)
             secs.append(t_pred)
     value = args.ref_points * len(secs) / sum(secs)
     line = {
-        "impl": "reference", "metric": "predict points/sec (mean+var) N=8192 D=8", "value": value, "unit": "points/s",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "points/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "configs[1]: Matern-5/2 ARD emulator, N_train=8192 D=8, predict mean+noisy std",
-                   "points_per_step": args.ref_points, "note": "bounded sample of the same workload; cost is linear in M"},
+        "config": {"workload": WORKLOAD, "points_per_step": args.ref_points,
+                   "note": "bounded sample of the same workload: the metric is a rate and the cost is linear in the number of points"},
         "cpu_baseline": {"value": value, "unit": "points/s", "cores": threads, "kind": "port",
                          "sample": f"{args.ref_points} of the 1e6 X* points per step, chunks of 4096, factorisation ({t_fac:.1f} s) excluded"},
         "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -216,29 +236,222 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------------
+def cuda_time(fn, reps, warm=1):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+def config1_block(dev):
+    """BASELINE configs[0] (examples/example_1.py-style): N=200, D=8, ScaleKernel(RBF ARD) + LinearMean, Adam on -MLL/N with
+    the two train-set metrics per epoch, then predict 1e4 points -- this package on the GPU beside the oracle (torch float64
+    autograd) on the host cores, same data, same starting hyper-parameters."""
+    from oracle import gp_oracle as O
+    from gperks_b200.train.early_stop import NoEarlyStoppingCriterion
+    from gperks_b200.train.snapshot import NeverSaveSnapshottingCriterion
+    X, y, Xs, hyper = synthetic_problem(n_train=200, dim=8, m=10_000, seed=8)
+    em = build_emulator(X, y, hyper, str(dev), kernel="rbf")
+    epochs = 100
+    import tempfile
+    snap = NeverSaveSnapshottingCriterion(tempfile.mkdtemp(prefix="gpx_c1_") + "/restart_{restart}", "epoch_{epoch}.pth")
+    opt = torch.optim.Adam(em.model.parameters(), lr=0.1)
+    em.train(opt, NoEarlyStoppingCriterion(5), snap)                       # warm: library load, allocator, kernels' first launch
+    em = build_emulator(X, y, hyper, str(dev), kernel="rbf")
+    opt = torch.optim.Adam(em.model.parameters(), lr=0.1)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    em.train(opt, NoEarlyStoppingCriterion(epochs), snap)
+    torch.cuda.synchronize()
+    train_s = time.perf_counter() - t0
+    em.predict(Xs[:2000])
+    t0 = time.perf_counter()
+    for _ in range(5):
+        em.predict(Xs)
+    pred_s = (time.perf_counter() - t0) / 5
+    # the oracle on the host: the same loop (Adam on the raw parameters through torch autograd, float64) and predict
+    torch.set_num_threads(os.cpu_count() or 1)
+    orc = O.OracleEmulator(X, y, kind=O.KIND_RBF, lengthscale=hyper["lengthscale"], outputscale=hyper["outputscale"],
+                           noise=hyper["noise"], weights=hyper["weights"], bias=hyper["bias"], degree=1)
+    raw = [torch.nn.Parameter(t.clone()) for t in (orc.ls.log(), orc.s.log().reshape(1), orc.noise.log().reshape(1), orc.w.clone(), orc.b.clone())]
+    oopt = torch.optim.Adam(raw, lr=0.1)
+    n_cpu_epochs = 30
+    t0 = time.perf_counter()
+    for _ in range(n_cpu_epochs):
+        oopt.zero_grad()
+        ls, s, nz = raw[0].exp(), raw[1].exp().reshape(()), raw[2].exp().reshape(())
+        K = O.kernel_matrix(orc.X, orc.X, orc.kind, ls, s) + nz * torch.eye(orc.X.shape[0], dtype=torch.float64)
+        L = torch.linalg.cholesky(K)
+        r = orc.y - (orc.X @ raw[3].reshape(-1) + raw[4].reshape(()))
+        a = torch.cholesky_solve(r.reshape(-1, 1), L).reshape(-1)
+        n = orc.X.shape[0]
+        loss = (0.5 * r @ a + L.diagonal().log().sum() + 0.5 * n * math.log(2 * math.pi)) / n
+        loss.backward()
+        oopt.step()
+        with torch.no_grad():                       # the two train-set metrics of every epoch (GPErks/train/emulator.py:335-346)
+            V = torch.linalg.solve_triangular(L.detach(), K.detach() - nz.detach() * torch.eye(n, dtype=torch.float64), upper=False)
+            _ = (s.detach() - (V * V).sum(0) + nz.detach())
+    cpu_epoch_ms = (time.perf_counter() - t0) / n_cpu_epochs * 1e3
+    t0 = time.perf_counter()
+    orc.predict(Xs)
+    cpu_pred_s = time.perf_counter() - t0
+    return {"workload": "configs[0]: N=200 D=8 RBF ARD + LinearMean, Adam 100 epochs (2 train-set metrics per epoch), predict 1e4 points",
+            "gpu_epoch_ms": train_s / epochs * 1e3, "gpu_train_100_epochs_s": train_s, "gpu_predict_1e4_ms": pred_s * 1e3,
+            "cpu_oracle_epoch_ms": cpu_epoch_ms, "cpu_oracle_predict_1e4_ms": cpu_pred_s * 1e3, "cpu_threads": torch.get_num_threads(),
+            "gpu_vs_cpu_epoch": cpu_epoch_ms / (train_s / epochs * 1e3), "gpu_vs_cpu_predict": cpu_pred_s / pred_s,
+            "note": "through GPEmulator.train / predict (host numpy in and out); at this size both sides are latency-bound"}
+
+
+def strong_scaling_block(em, world, rank, dev, total_points, precision):
+    """ONE fixed X* of `total_points` rows, held on rank 0, through the product's multi-GPU API
+    (gperks_b200.parallel.sharded_predict: NCCL scatter of the rows -> predict_device -> NCCL gather to rank 0)."""
+    import torch.distributed as dist
+    from gperks_b200.parallel import shard_bounds, sharded_predict
+    Xbig = None
+    if rank == 0:
+        from scipy.stats import qmc
+        Xbig = qmc.Sobol(d=DIM, scramble=True, seed=12345).random(total_points)
+    kw = {} if precision == "auto" else {"precision": precision}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    if world > 1:                                               # warm the communicator and the staging buffers
+        sharded_predict(em, Xbig[: 4096 * world] if rank == 0 else None, **kw)
+    barrier()
+    t0 = time.perf_counter()
+    mean, std = sharded_predict(em, Xbig, **kw) if world > 1 else em.predict(Xbig, **kw)
+    barrier()
+    dt = time.perf_counter() - t0
+    out = None
+    if rank == 0:
+        # bit-for-bit: the gathered result against single-GPU predicts of the first rows and of the rows around a shard boundary
+        lo1 = shard_bounds(total_points, world, min(1, world - 1))[0]
+        spans = [(0, min(65536, total_points)), (max(0, lo1 - 20000), min(total_points, lo1 + 20000))]
+        equal = True
+        for a, b in spans:
+            m1, s1 = em.predict(Xbig[a:b], **kw)
+            equal = equal and np.array_equal(m1, mean[a:b]) and np.array_equal(s1, std[a:b])
+        out = {"points": int(total_points), "seconds": dt, "points_per_s": total_points / dt, "n_gpus": world,
+               "api": "gperks_b200.parallel.sharded_predict(emulator, X* on rank 0)" if world > 1 else "GPEmulator.predict(X*)",
+               "bitwise_equal_to_single_gpu_slices": bool(equal), "checked_rows": [list(s) for s in spans],
+               "timing": "wall clock on rank 0 between barriers: host X* -> device, scatter, predict, gather, device -> host"}
+    return out
+
+
+def run_kfold(args):
+    """BASELINE configs[4]: 5-fold cross-validation x 8 restarts of an N=32768, D=16 RBF emulator -- 40 independent fits of
+    26214/26215 training points, one fit per GPU at a time (GPErks/perks/cross_validation.py:99-143 deals folds over devices;
+    here the (fold, restart) jobs are dealt round-robin over the ranks, gperks_b200.parallel.run_jobs_round_robin, and each job
+    is the product's own train_restart_job).  A step = one Adam epoch of one fit (MLL + gradient, optimizer step, the train-set
+    metrics and the left-out-fold validation loss); `value` = epochs/s summed over all ranks, wall clock between barriers."""
+    import torch.distributed as dist
+    from sklearn.model_selection import KFold
+    from gperks_b200.gp.data.dataset import Dataset
+    from gperks_b200.gp.experiment import GPExperiment
+    from gperks_b200.gp.mean import LinearMean
+    from gperks_b200.kernels import RBFKernel, ScaleKernel
+    from gperks_b200.likelihoods import GaussianLikelihood
+    from gperks_b200.parallel import run_jobs_round_robin
+    from gperks_b200.train.early_stop import NoEarlyStoppingCriterion
+    from gperks_b200.train.emulator import train_restart_job
+    from gperks_b200.train.snapshot import NeverSaveSnapshottingCriterion
+    from gperks_b200.utils.metrics import MeanSquaredError, R2Score
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    N, D, n_splits, n_restarts, epochs = args.kfold_n, 16, 5, 8, args.kfold_epochs
+    X, y, _, _ = synthetic_problem(n_train=N, dim=D, m=0)
+    splits = list(KFold(n_splits=n_splits).split(X))
+    jobs = [(i, r) for i in range(n_splits) for r in range(1, n_restarts + 1)]
+    import tempfile
+    snap_root = tempfile.mkdtemp(prefix="gpx_kfold_")
+
+    def run(job):
+        i, r = job
+        tr, lo = splits[i]
+        ds = Dataset(X[tr], y[tr], X_val=X[lo], y_val=y[lo], X_test=X[lo], y_test=y[lo])
+        torch.manual_seed(8)
+        exp = GPExperiment(ds, GaussianLikelihood(), LinearMean(1, D), ScaleKernel(RBFKernel(ard_num_dims=D)), n_restarts=n_restarts,
+                           seed=8, metrics=[MeanSquaredError(), R2Score()])
+        snpc = NeverSaveSnapshottingCriterion(f"{snap_root}/split_{i}/restart_{{restart}}", "epoch_{epoch}.pth")
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        stats, best_epoch = train_restart_job(exp, None, f"cuda:{local_rank}", r, torch.get_rng_state(), (torch.optim.Adam, {"lr": 0.1}),
+                                              NoEarlyStoppingCriterion(epochs), snpc)
+        torch.cuda.synchronize()
+        return {"fold": i, "restart": r, "rank": rank, "seconds": time.perf_counter() - t0, "final_train_loss": float(stats.train_loss[-1]),
+                "final_val_loss": float(stats.val_loss[-1]) if len(stats.val_loss) else None}
+
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    with ClockSampler(local_rank) as clocks:
+        t0 = time.perf_counter()
+        results = run_jobs_round_robin(jobs, run)
+        if world > 1:
+            dist.barrier()
+        wall = time.perf_counter() - t0
+    if rank == 0:
+        per_rank = [sum(r["seconds"] for r in results if r["rank"] == k) for k in range(world)]
+        line = {"metric": "k-fold x restart Adam epochs/sec (5 folds x 8 restarts, N=32768 D=16 RBF)", "value": len(jobs) * epochs / wall,
+                "unit": "epochs/s", "n_gpus": world, "steps": epochs, "warmup": 0, "ms_per_step": 1e3 * wall / (epochs * math.ceil(len(jobs) / world)),
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64 (K_hat^-1 for the gradient from six 7-bit integer slices)",
+                "data": "synthetic",
+                "config": {"workload": "configs[4]: 5-fold cross-validation x 8 restarts, N_train=32768 D=16 RBF, one fit per GPU",
+                           "fits": len(jobs), "fold_train_size": int(len(splits[0][0])), "epochs_per_fit": epochs,
+                           "note": "epoch count scaled to the benchmark budget (the reference's default is 100 per restart); every epoch is a full "
+                                   "MLL+gradient evaluation, an Adam step, two train-set metrics and the validation loss on the left-out fold",
+                           "wall_seconds": wall, "busy_fraction_per_gpu": [s / wall for s in per_rank],
+                           "seconds_per_fit": [round(r["seconds"], 2) for r in results],
+                           "final_train_loss_per_fit": [round(r["final_train_loss"], 5) for r in results]},
+                "gpu_launches": None, "clocks": clocks.summary()}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="predict", choices=["predict", "kfold"])
     ap.add_argument("--points", type=int, default=1_000_000, help="predict points per GPU per step")
     ap.add_argument("--ref-points", type=int, default=65536, help="points per step of the CPU reference arm")
     ap.add_argument("--cpu-sample", type=int, default=98304, help="points of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--mll-evals", type=int, default=3)
-    ap.add_argument("--no-tf32", action="store_true", help="skip the TF32-mode (tcgen05) arm")
-    ap.add_argument("--no-int8", action="store_true", help="skip the sliced-integer (tcgen05 kind::i8) arm")
+    ap.add_argument("--mll-evals", type=int, default=5)
+    ap.add_argument("--side-steps", type=int, default=3, help="timed steps of the side arms (FP64 DMMA, TF32, other slice counts)")
+    ap.add_argument("--no-side-arms", action="store_true", help="skip the TF32 / other-int8 arms")
+    ap.add_argument("--strong-points", type=int, default=10_000_000, help="rows of the fixed X* of the strong-scaling arm (0: skip)")
+    ap.add_argument("--no-config1", action="store_true")
     ap.add_argument("--precision", default="auto",
-                    help="precision of the headline arms: auto (GPEmulator.predict's default: int8x6 for this workload), fp64, int8x5, int8x6")
-    ap.add_argument("--ncu-traffic", type=float, default=None,
-                    help="dram bytes per launch of the dominant kernel from an ncu --set full capture (profiles/)")
+                    help="precision of the headline arms: auto (GPEmulator.predict's default), fp64, int8x5w, int8x6w, int8x5, int8x6")
+    ap.add_argument("--kfold-epochs", type=int, default=3)
+    ap.add_argument("--kfold-n", type=int, default=32768)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "kfold":
+        return run_kfold(args)
 
     import torch.distributed as dist
     from gperks_b200 import _native as nv
+    from gperks_b200.engine import I8_MODES
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -255,34 +468,39 @@ def main():
     X, y, Xs, hyper = synthetic_problem(m=M, rank=rank)
     em = build_emulator(X, y, hyper, f"cuda:{local_rank}")
     lib = nv.lib()
+    side_steps = max(1, min(args.steps, args.side_steps))
 
-    # ---- factorise once (replicated on every rank), time MLL+grad evaluations as the secondary metric
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- factorise once (replicated on every rank), time MLL+grad evaluations: the second half of the metric
     eng = em.model._factorized_engine()
     torch.cuda.synchronize()
     theta, resid = eng.theta_in.clone(), eng.r[:eng.N].clone()
-    def time_mll():
-        ms = []
-        for i in range(args.mll_evals + 1 if args.mll_evals > 0 else 0):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            eng.factorize(theta, resid)
-            eng.gradients()
-            b.record()
-            torch.cuda.synchronize()
-            if i > 0:
-                ms.append(a.elapsed_time(b))
-        return ms
-    mll_ms = time_mll()                      # the engine's default: K_hat^-1 on the integer tensor cores at this size
+
+    def mll_once():
+        eng.factorize(theta, resid)
+        eng.gradients()
+    mll_ms = cuda_time(mll_once, max(1, args.mll_evals), warm=2)
     lauum_default = eng.lauum_slices
     eng.lauum_slices = 0                     # all-FP64 edition (DMMA lauum) beside it
-    mll_ms_fp64 = time_mll() if lauum_default else mll_ms
+    mll_ms_fp64 = cuda_time(mll_once, max(1, args.mll_evals), warm=1) if lauum_default else mll_ms
     eng.lauum_slices = lauum_default
-    mll_ms_i8_trtri = None
-    if getattr(eng, "_trtri_i8_capable", False):      # experimental, opt-in: the top merge levels of the inverse on the integer tensor cores too
-        eng.trtri_i8 = True
-        mll_ms_i8_trtri = time_mll()
-        eng.trtri_i8 = False
     eng.factorize(theta, resid)
+    mll_grad = {"evals_per_s": 1e3 / mll_ms, "ms_per_eval": mll_ms, "n_train": eng.N, "dim": eng.D,
+                "what": "K_hat build + Cholesky + L^-1 + alpha + -mll + K_hat^-1 + gradient reduce (ExactGPEngine.factorize + gradients)",
+                "k_inverse": (f"six 7-bit slices on tcgen05 kind::i8 (gpx_lauum_i8)" if lauum_default else "FP64 DMMA lauum"),
+                "ms_per_eval_all_fp64": mll_ms_fp64,
+                "algorithmic_flops_per_eval": float(eng.N) ** 3,
+                "fp64_equiv_tflops": float(eng.N) ** 3 / (mll_ms / 1e3) / 1e12}
 
     # ---- device-resident arm (`value`)
     scx, scy = em.scaled_data.scx, em.scaled_data.scy
@@ -294,24 +512,25 @@ def main():
     out_std = torch.empty(M, dtype=torch.float64, device=dev)
     Mc = eng.pick_chunk(M)
     n_chunks = math.ceil(M / Mc)
-    PREC = em.resolve_precision(args.precision)        # what GPEmulator.predict(X) runs by default for this emulator
+    # what GPEmulator.predict(X) runs by default for this emulator: first "auto" candidate that passes the probe against FP64
+    if args.precision == "auto":
+        from gperks_b200.constants import AUTO_I8_PROBE_TOL
+        PREC = next(c for c in em.auto_precisions() if c == "fp64" or eng.int8_probe_ok(c, AUTO_I8_PROBE_TOL))
+    else:
+        PREC = args.precision
     gathered = [torch.empty(2, M, dtype=torch.float64, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
     local_out = torch.empty(2, M, dtype=torch.float64, device=dev)
+    pk = dict(xa=xa, xr=xr, poly=poly, y_mu=float(scy.mu), y_sigma=float(scy.sigma), chunk=Mc)
 
     def step():
-        eng.predict(x_dev, xa=xa, xr=xr, poly=poly, y_mu=float(scy.mu), y_sigma=float(scy.sigma),
-                    out_mean=out_mean, out_std=out_std, chunk=Mc, precision=PREC)
+        eng.predict(x_dev, out_mean=out_mean, out_std=out_std, precision=PREC, **pk)
         if world > 1:       # the path's only exchange: gather the 16 B/point results on rank 0
             local_out[0].copy_(out_mean)
             local_out[1].copy_(out_std)
             dist.gather(local_out, gathered, dst=0)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         step()
     barrier()
     with ClockSampler(local_rank) as clocks:
@@ -322,195 +541,95 @@ def main():
         b.record()
         barrier()
         elapsed_ms = a.elapsed_time(b)
-    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(t.item())
+    elapsed_ms = max_over_ranks(elapsed_ms)
     value = world * M * args.steps / (elapsed_ms / 1e3)
+
+    # ---- end-to-end arm: GPEmulator.predict on host numpy buffers (pinned H2D + D2H inside), --steps steps
+    ekw = {} if args.precision == "auto" else {"precision": args.precision}
+    em.predict(Xs[: min(M, 300_000)], **ekw)       # warm the pinned staging slots
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        y_mean, y_std = em.predict(Xs, **ekw)
+    barrier()
+    e2e_value = world * M * args.steps / max_over_ranks(time.perf_counter() - t0)
+    parity = float(np.max(np.abs(y_mean - out_mean.cpu().numpy()))) + float(np.max(np.abs(y_std - out_std.cpu().numpy())))
 
     # ---- the FP64 DMMA arm (precision="fp64"): the reference point every other mode's error is measured against
     f_mean = torch.empty(M, dtype=torch.float64, device=dev)
     f_std = torch.empty(M, dtype=torch.float64, device=dev)
 
     def f64_step():
-        eng.predict(x_dev, xa=xa, xr=xr, poly=poly, y_mu=float(scy.mu), y_sigma=float(scy.sigma),
-                    out_mean=f_mean, out_std=f_std, chunk=Mc, precision="fp64")
+        eng.predict(x_dev, out_mean=f_mean, out_std=f_std, precision="fp64", **pk)
     f64_step()
     barrier()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    for _ in range(args.steps):
+    for _ in range(side_steps):
         f64_step()
     b.record()
     barrier()
-    t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    f64_ms = float(t.item())
-    f64_value = world * M * args.steps / (f64_ms / 1e3)
-    headline_err_std = float(((out_std - f_std).abs() / f_std).max())
-    headline_err_mean = float((out_mean - f_mean).abs().max() / f_mean.abs().max())
+    f64_ms = max_over_ranks(a.elapsed_time(b))
+    f64_value = world * M * side_steps / (f64_ms / 1e3)
+    rel_std = (out_std - f_std).abs() / f_std
+    accuracy = {"max_rel_err_std_vs_fp64_dmma_path": float(rel_std.max()), "median_rel_err_std": float(rel_std.median()),
+                "max_err_mean_vs_fp64_dmma_path_rel_to_scale": float((out_mean - f_mean).abs().max() / f_mean.abs().max()),
+                "mean_bit_identical": bool(torch.equal(out_mean, f_mean)), "tolerance": 1e-6, "points": int(M),
+                "note": "every point of a timed step of the headline precision against the precision='fp64' (DMMA) arm of the same run; "
+                        "the FP64 arm is itself checked against independent cuSOLVER/cuBLAS FP64 math and the CPU oracle in tests/"}
 
     # ---- the FP64 variance TRMM alone on one full chunk, CUDA events on its stream
-    ws = eng._workspace(int(lib.gpx_predict_workspace_bytes(eng.Np, Mc)))
-    Ks_ptr = ws.data_ptr()
-    qpart = torch.empty(eng.nb * Mc, dtype=torch.float64, device=dev)
     st = nv.stream_ptr()
-    k_ms = []
-    for i in range(4):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        nv.check(lib.gpx_trmm_sumsq(nv.ptr(eng.S), eng.Np, Ks_ptr, Mc, nv.ptr(qpart), st), "trmm")
-        b.record()
-        torch.cuda.synchronize()
-        if i > 0:
-            k_ms.append(a.elapsed_time(b))
-    k_ms = sum(k_ms) / len(k_ms)
+    ws = eng._workspace(int(lib.gpx_predict_workspace_bytes(eng.Np, Mc)))
+    qpart = torch.empty(eng.nb * Mc, dtype=torch.float64, device=dev)
+    k_ms = cuda_time(lambda: nv.check(lib.gpx_trmm_sumsq(nv.ptr(eng.S), eng.Np, ws.data_ptr(), Mc, nv.ptr(qpart), st), "trmm"), 3)
     flops_per_launch = float(eng.N) ** 2 * Mc            # N^2 FLOP per point for the variance
-    achieved = flops_per_launch / (k_ms / 1e3) / 1e12
     sink = torch.zeros(8, dtype=torch.float64, device=dev)
     peak_ms = []
-    for i in range(3):
+    for _ in range(3):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         peak_flops = lib.gpx_peak_dmma(148 * 8, 20000, nv.ptr(sink), st)
         b.record()
         torch.cuda.synchronize()
         peak_ms.append(a.elapsed_time(b))
-    peak = peak_flops / (min(peak_ms) / 1e3) / 1e12
-    kernel_share = k_ms * (M / Mc) / (f64_ms / args.steps)      # TRMM work is linear in the points
+    dmma_peak = peak_flops / (min(peak_ms) / 1e3) / 1e12
+    fp64_roofline = {"kernel": "trmm_sumsq_tma_kernel (variance contraction L^-1 K*^T: TMA + mbarrier ring, FP64 DMMA)", "bound": "tensor",
+                     "achieved": flops_per_launch / (k_ms / 1e3) / 1e12, "peak": dmma_peak, "unit": "TFLOP/s",
+                     "frac": flops_per_launch / (k_ms / 1e3) / 1e12 / dmma_peak, "traffic": ncu_traffic_bytes("trmm_sumsq_tma_kernel"),
+                     "peak_source": "gpx_peak_dmma probe measured in this run (FP64 DMMA.8x8x4 issue peak; MEASURED_PEAKS.json has no FP64 figure)",
+                     "algorithmic_flops_per_launch": flops_per_launch, "kernel_ms": k_ms,
+                     "kernel_share_of_step": k_ms * (M / Mc) / (f64_ms / side_steps)}
+    fp64_mode = {"value": f64_value, "unit": "points/s", "ms_per_step": f64_ms / side_steps, "steps": side_steps, "roofline": fp64_roofline,
+                 "note": "precision='fp64': the same predict with the variance contraction on the FP64 tensor path (DMMA)"}
 
-    # ---- end-to-end arm: GPEmulator.predict on host numpy buffers (pinned H2D + D2H inside)
-    e2e_steps = max(1, min(args.steps, 2))
-    em.predict(Xs[: min(M, 200_000)], precision=args.precision)       # warm the pinned allocator
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        y_mean, y_std = em.predict(Xs, precision=args.precision)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * M * e2e_steps / float(t.item())
-    parity = float(np.max(np.abs(y_mean - out_mean.cpu().numpy())))     # the two arms must agree bit for bit
-
-    # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel (one chunk of Mc points) from the
-    # committed `ncu --set full` capture (profiles/r01_ncu_trmm_tma.txt); only valid for the default chunk size
-    TRAFFIC = args.ncu_traffic if args.ncu_traffic is not None else (NCU_TRAFFIC_BYTES if Mc == 32768 and eng.N == 8192 else None)
-
-    # ---- TF32 mode (tcgen05 3xTF32 variance contraction), reported beside the FP64 headline
-    tf32 = None
-    if not args.no_tf32:
-        s64 = f_std
-        tmean = torch.empty_like(out_mean)
-        tstd = torch.empty_like(out_std)
-
-        def tf32_arm(precision):
-            def tf32_step():
-                eng.predict(x_dev, xa=xa, xr=xr, poly=poly, y_mu=float(scy.mu), y_sigma=float(scy.sigma),
-                            out_mean=tmean, out_std=tstd, chunk=Mc, precision=precision)
-            for _ in range(3):
-                tf32_step()
-            barrier()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for _ in range(args.steps):
-                tf32_step()
-            b.record()
-            barrier()
-            t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-            rel_s = ((tstd - s64).abs() / s64)
-            rel_m = (tmean - f_mean).abs().max() / f_mean.abs().max()
-            return {"value": world * M * args.steps / (ms / 1e3), "unit": "points/s", "ms_per_step": ms / args.steps,
-                    "max_rel_err_std_vs_fp64": float(rel_s.max()), "median_rel_err_std_vs_fp64": float(rel_s.median()),
-                    "max_err_mean_vs_fp64_rel_to_scale": float(rel_m)}
-        fast = tf32_arm("tf32x3_fast")
-        exact = tf32_arm("tf32x3")
-        tf32_ms = exact["ms_per_step"] * args.steps
-        rel = ((tstd - s64).abs() / s64)
-        # the tensor-core kernel alone, and the cuBLAS TF32 GEMM rate measured here as its denominator
-        Khi = ws.view(torch.float32)[: Mc * eng.Np]
-        Klo = ws.view(torch.float32)[Mc * eng.Np: 2 * Mc * eng.Np]
-        nt = int(lib.gpx_tf32_row_tiles(eng.Np))
-        qp = torch.empty(nt * Mc, dtype=torch.float64, device=dev)
-        tk = []
-        for i in range(4):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            nv.check(lib.gpx_trmm_sumsq_tf32(nv.ptr(eng.S_hi), nv.ptr(eng.S_lo), eng.Np, Khi.data_ptr(), Klo.data_ptr(), Mc,
-                                             nv.ptr(qp), 32, st), "tf32 trmm")
-            b.record()
-            torch.cuda.synchronize()
-            if i > 0:
-                tk.append(a.elapsed_time(b))
-        tk = sum(tk) / len(tk)
-        a32 = torch.randn(8192, 8192, device=dev)
-        b32 = torch.randn(8192, 8192, device=dev)
-        torch.backends.cuda.matmul.allow_tf32 = True
-        tg = []
-        for i in range(4):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            torch.matmul(a32, b32)
-            b.record()
-            torch.cuda.synchronize()
-            if i > 0:
-                tg.append(a.elapsed_time(b))
-        torch.backends.cuda.matmul.allow_tf32 = False
-        tf32_peak = 2 * 8192 ** 3 / (min(tg) / 1e3) / 1e12
-        raw = 3.0 * float(eng.N) ** 2 * Mc / (tk / 1e3) / 1e12
-        tf32 = {"tf32x3": exact, "tf32x3_fast": fast, "tolerance": 1e-3, "kchunk": 32,
-                "note": "tf32x3: K* evaluated in FP64 (mean bit-identical to fp64); tf32x3_fast: K* evaluated in FP32",
-                "roofline": {"kernel": "trmm_sumsq_tf32_kernel (tcgen05.mma kind::tf32, 3 MMAs per product, TMEM accumulators)",
-                             "bound": "tensor", "achieved": raw, "peak": tf32_peak, "unit": "TFLOP/s (TF32, raw = 3 x useful)",
-                             "frac": raw / tf32_peak, "useful_tflops": raw / 3.0, "kernel_ms": tk,
-                             "peak_source": "cuBLAS TF32 GEMM 8192^3 (torch.matmul, allow_tf32) measured in this run"}}
-
-    # ---- sliced-integer mode (tcgen05 kind::i8, exact int32 accumulation; std inside the FP64 bar of 1e-6), beside the headline
-    int8 = None
-    if not args.no_int8 or PREC.startswith("int8"):
-        s64 = f_std
-        imean = torch.empty_like(out_mean)
-        istd = torch.empty_like(out_std)
-        f_std_host = f_std.cpu().numpy()
-        int8 = {"tolerance": 1e-6, "note": "FP64 contraction from S signed 7-bit slices per operand on the integer tensor cores; "
-                                           "K* and the posterior mean stay on the FP64 kernels (mean bit-identical)"}
+    # ---- integer tensor-core roofline denominators: the kind::i8 MMA issue rate probed here, the cuBLASLt int8 GEMM beside it
+    i8_info = {}
+    roofline = fp64_roofline
+    dtype = "f64"
+    launches_per_chunk = 3
+    if PREC in I8_MODES:
+        S_, bits_ = I8_MODES[PREC]
         try:
             ai = torch.randint(-64, 64, (8192, 8192), device=dev, dtype=torch.int8)
             bi = torch.randint(-64, 64, (8192, 8192), device=dev, dtype=torch.int8)
-            tg = []
-            for i in range(4):
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
-                torch._int_mm(ai, bi)
-                b.record()
-                torch.cuda.synchronize()
-                if i > 0:
-                    tg.append(a.elapsed_time(b))
-            i8_peak = 2 * 8192 ** 3 / (min(tg) / 1e3) / 1e12
+            i8_gemm = 2 * 8192 ** 3 / (cuda_time(lambda: torch._int_mm(ai, bi), 3) / 1e3) / 1e12
             del ai, bi
-        except Exception as exc:          # noqa: BLE001 -- the probe is optional; the mode itself never falls back
-            i8_peak = None
-            int8["peak_probe_error"] = repr(exc)[:200]
-        # the tensor core's own limit: kind::i8 MMAs (M=128, N=256, K=32) issued back to back from resident shared memory
-        # burst: best of three 5 ms launches after an idle gap; sustained: 1.5 s of back-to-back launches, the second half timed
-        # (what a kernel inside a long step can get once the power cap has pulled the clock down)
+        except Exception as exc:          # noqa: BLE001 -- the library probe is optional; the product path never falls back
+            i8_gemm = None
+            i8_info["cublaslt_probe_error"] = repr(exc)[:200]
         torch.cuda.synchronize()
         time.sleep(0.5)
-        pk = []
-        for i in range(3):
+        pkms = []
+        for _ in range(3):                # burst: best of three 5 ms launches after an idle gap
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             pk_ops = lib.gpx_peak_i8mma(148, 40000, st)
             b.record()
             torch.cuda.synchronize()
-            pk.append(a.elapsed_time(b))
-        i8_issue_peak_burst = pk_ops / (min(pk) / 1e3) / 1e12
-        n_sus = 280
+            pkms.append(a.elapsed_time(b))
+        peak_burst = pk_ops / (min(pkms) / 1e3) / 1e12
+        n_sus = 280                       # sustained: 1.5 s of back-to-back probe launches, the second half timed
         for _ in range(n_sus // 2):
             lib.gpx_peak_i8mma(148, 40000, st)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -519,131 +638,91 @@ def main():
             lib.gpx_peak_i8mma(148, 40000, st)
         b.record()
         torch.cuda.synchronize()
-        i8_issue_peak = pk_ops * (n_sus // 2) / (a.elapsed_time(b) / 1e3) / 1e12
-        int8["int8_mma_issue_peak_tops"] = i8_issue_peak
-        int8["int8_mma_issue_peak_burst_tops"] = i8_issue_peak_burst
-        int8["cublaslt_int8_gemm_tops"] = i8_peak
-        for S_ in (5, 6):
-            prec = f"int8x{S_}"
+        peak_sus = pk_ops * (n_sus // 2) / (a.elapsed_time(b) / 1e3) / 1e12
+        # the integer tensor-core kernel and the K* builder alone, on the slices the last chunk left in the workspace
+        eng.predict(x_dev[: 2 * Mc], out_mean=out_mean[: 2 * Mc], out_std=out_std[: 2 * Mc], precision=PREC, **pk)
+        ws8 = eng._workspace(int(lib.gpx_predict_i8_workspace_bytes(eng.Np, Mc, S_)))
+        Kp_ptr = ws8.data_ptr() + int(lib.gpx_predict_i8_planes_offset(eng.Np, Mc, S_, 0))
+        nt8 = int(lib.gpx_i8_row_tiles(eng.Np))
+        qp8 = torch.empty(nt8 * Mc, dtype=torch.float64, device=dev)
+        mp8 = torch.empty(eng.nb * Mc, dtype=torch.float64, device=dev)
+        n_rep = 20
+        with ClockSampler(local_rank) as kclk:
+            tk = cuda_time(lambda: nv.check(lib.gpx_trmm_sumsq_i8(nv.ptr(eng.S_i8), nv.ptr(eng.S_i8_inv_scale), eng.Np, Kp_ptr, Mc, S_, bits_,
+                                                                 nv.ptr(eng.theta) + 8 * DIM, nv.ptr(qp8), st), "i8 trmm"), n_rep, warm=10)
+        tb = cuda_time(lambda: nv.check(lib.gpx_kmat_cross_i8(nv.ptr(x_dev), Mc, nv.ptr(eng.X), eng.N, eng.D, nv.ptr(eng.theta), nv.ptr(xa),
+                                                             nv.ptr(xr), eng.kind, nv.ptr(eng.alpha), Kp_ptr, Mc, S_, bits_, eng.Np,
+                                                             nv.ptr(mp8), Mc, st), "i8 builder"), 5)
+        n_prod = S_ * (S_ + 1) // 2
+        raw = n_prod * float(eng.N) ** 2 * Mc / (tk / 1e3) / 1e12
+        step_ms = elapsed_ms / args.steps
+        roofline = {
+            "kernel": f"trmm_sumsq_i8p_kernel<{S_},{bits_}> (persistent clusters, tcgen05.mma kind::i8, {n_prod} slice products of {bits_}-bit digits, int32 TMEM accumulators)",
+            "bound": "tensor", "achieved": raw, "peak": peak_sus, "unit": "TOP/s (int8, raw)", "frac": raw / peak_sus,
+            "traffic": ncu_traffic_bytes(f"trmm_sumsq_i8p_kernel<{S_},{bits_}>"),
+            "peak_burst": peak_burst, "frac_of_burst_peak": raw / peak_burst, "nominal_int8_peak_tops": 4500.0,
+            "cublaslt_int8_gemm_tops": i8_gemm, "frac_of_cublaslt_int8_gemm": (raw / i8_gemm) if i8_gemm else None,
+            "algorithmic_flops_per_launch": flops_per_launch, "fp64_equivalent_tflops": flops_per_launch / (tk / 1e3) / 1e12,
+            "fp64_equivalent_vs_dmma_peak": flops_per_launch / (tk / 1e3) / 1e12 / dmma_peak,
+            "kernel_ms": tk, "kernel_sm_mhz": kclk.summary()["sm_mhz"], "kernel_share_of_step": tk * (M / Mc) / step_ms,
+            "builder_kernel": f"kmat_cross_i8_kernel<matern52,{S_},{bits_}> (FP64 K* evaluation -> int8 slices + posterior-mean partial sums)",
+            "builder_kernel_ms": tb, "builder_share_of_step_if_serial": tb * (M / Mc) / step_ms,
+            "peak_source": "gpx_peak_i8mma probe measured in this run (kind::i8 MMA issue rate from resident shared memory, one CTA per SM; "
+                           "MEASURED_PEAKS.json has no int8 figure): `peak` = SUSTAINED (1.5 s of back-to-back probe launches, second half "
+                           "timed: the step runs under the 1 kW power cap), `peak_burst` = best 5 ms launch after an idle gap; the cuBLASLt "
+                           "int8 GEMM 8192^3 (torch._int_mm) rate of the same run is the second source",
+            "note": "the step is power-capped (clocks.reasons): at a fixed power the time of a launch follows the energy it spends, so the "
+                    "fewer slice products of the 8-bit digits (15 instead of 21) shorten the launch even where `frac` does not move"}
+        dtype = (f"i8 slices ({S_} x {bits_} bit, exact i32 accumulation on tcgen05, FP64 combination): f64-equivalent, see config.accuracy")
+        launches_per_chunk = 3       # kmat_cross_i8, trmm_sumsq_i8p, predict_finalize
 
-            def i8_step():
-                eng.predict(x_dev, xa=xa, xr=xr, poly=poly, y_mu=float(scy.mu), y_sigma=float(scy.sigma),
-                            out_mean=imean, out_std=istd, chunk=Mc, precision=prec)
-            for _ in range(3):
-                i8_step()
-            barrier()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for _ in range(args.steps):
-                i8_step()
-            b.record()
-            barrier()
-            t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-            rel_s = ((istd - s64).abs() / s64)
-            entry = {"value": world * M * args.steps / (ms / 1e3), "unit": "points/s", "ms_per_step": ms / args.steps,
-                     "max_rel_err_std_vs_fp64": float(rel_s.max()), "median_rel_err_std_vs_fp64": float(rel_s.median()),
-                     "mean_bit_identical_to_fp64": bool(torch.equal(imean, f_mean))}
-            # end to end through GPEmulator.predict(numpy)
-            em.predict(Xs[: min(M, 200_000)], precision=prec)
-            barrier()
-            t0 = time.perf_counter()
-            ym8, ys8 = em.predict(Xs, precision=prec)
-            barrier()
-            t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            entry["e2e"] = {"value": world * M / float(t.item()), "unit": "points/s", "api": f"GPEmulator.predict(numpy, precision='{prec}')",
-                            "max_rel_err_std_vs_fp64_e2e": float(np.max(np.abs(ys8 - f_std_host) / f_std_host))}
-            # the integer tensor-core kernel alone on the slices left in the workspace by the last chunk
-            ws8 = eng._workspace(int(lib.gpx_predict_i8_workspace_bytes(eng.Np, Mc, S_)))
-            Kp_ptr = ws8.data_ptr() + Mc * eng.Np * 8
-            nt8 = int(lib.gpx_i8_row_tiles(eng.Np))
-            qp8 = torch.empty(nt8 * Mc, dtype=torch.float64, device=dev)
-            tk = []
-            for i in range(4):
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
-                nv.check(lib.gpx_trmm_sumsq_i8(nv.ptr(eng.S_i8), nv.ptr(eng.S_i8_inv_scale), eng.Np, Kp_ptr, Mc, S_,
-                                               nv.ptr(eng.theta) + 8 * DIM, nv.ptr(qp8), st), "i8 trmm")
-                b.record()
-                torch.cuda.synchronize()
-                if i > 0:
-                    tk.append(a.elapsed_time(b))
-            tk = sum(tk) / len(tk)
-            raw = (S_ * (S_ + 1) / 2) * float(eng.N) ** 2 * Mc / (tk / 1e3) / 1e12
-            entry["roofline"] = {"kernel": f"trmm_sumsq_i8_kernel<{S_}> (tcgen05.mma kind::i8, {S_ * (S_ + 1) // 2} slice products, int32 TMEM accumulators)",
-                                 "bound": "tensor", "achieved": raw, "peak": i8_issue_peak, "unit": "TOP/s (int8, raw)",
-                                 "frac": raw / i8_issue_peak, "peak_burst": i8_issue_peak_burst, "frac_of_burst_peak": raw / i8_issue_peak_burst,
-                                 "frac_of_cublaslt_int8_gemm": (raw / i8_peak) if i8_peak else None,
-                                 "fp64_equivalent_tflops": float(eng.N) ** 2 * Mc / (tk / 1e3) / 1e12,
-                                 "kernel_ms": tk, "kernel_share_of_step": tk * (M / Mc) / (ms / args.steps),
-                                 "peak_source": "gpx_peak_i8mma probe measured in this run (kind::i8 MMA issue rate from resident shared memory, "
-                                                "one CTA per SM; MEASURED_PEAKS.json has no int8 figure): `peak` = SUSTAINED (1.5 s of back-to-back "
-                                                "probe launches, second half timed -- this kernel is timed inside a long, power-capped run), "
-                                                "`peak_burst` = best 5 ms launch after an idle gap; the cuBLASLt int8 GEMM 8192^3 (torch._int_mm) "
-                                                "rate of the same run is recorded beside them"}
-            int8[prec] = entry
+    # ---- side arms: TF32 mode and the other slice counts (bounded number of steps)
+    side = {}
+    if not args.no_side_arms and world == 1:
+        tmean = torch.empty_like(out_mean)
+        tstd = torch.empty_like(out_std)
+        for prec in ("tf32x3", "tf32x3_fast", "int8x5w", "int8x6w", "int8x6"):
+            if prec == PREC:
+                continue
+            ms = cuda_time(lambda: eng.predict(x_dev, out_mean=tmean, out_std=tstd, precision=prec, **pk), side_steps, warm=1)
+            rel = (tstd - f_std).abs() / f_std
+            side[prec] = {"value": M / ms * 1e3, "unit": "points/s", "ms_per_step": ms, "max_rel_err_std_vs_fp64": float(rel.max()),
+                          "mean_bit_identical_to_fp64": bool(torch.equal(tmean, f_mean)),
+                          "tolerance": 1e-3 if prec.startswith("tf32") else 1e-6}
 
-    fp64_roofline = {"kernel": "trmm_sumsq_tma_kernel (variance contraction L^-1 K*^T: TMA + mbarrier ring, FP64 DMMA)", "bound": "tensor",
-                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": TRAFFIC,
-                     "peak_source": "gpx_peak_dmma probe measured in this run (FP64 DMMA.8x8x4 issue peak; MEASURED_PEAKS.json "
-                                    "has no FP64 figure; cuBLAS DGEMM 8192^3 measured 35.5 TF/s on this pool, see profiles/)",
-                     "algorithmic_flops_per_launch": flops_per_launch, "kernel_ms": k_ms, "kernel_share_of_step": kernel_share}
-    if PREC.startswith("int8") and int8 is not None and PREC in int8:
-        # headline = the sliced-integer path: its dominant kernel is the integer tensor-core contraction.  `achieved` counts the
-        # int8 operations the kernel actually issues (S(S+1)/2 slice products of the algorithmic N^2/2 multiply-adds per
-        # point); the FP64-equivalent rate (algorithmic N^2 FLOP per point / time) is given beside it.
-        roofline = dict(int8[PREC]["roofline"])
-        roofline["traffic"] = args.ncu_traffic if args.ncu_traffic is not None else (
-            NCU_TRAFFIC_I8_BYTES.get(PREC) if Mc == 32768 and eng.N == 8192 else None)
-        roofline["algorithmic_flops_per_launch"] = flops_per_launch
-        roofline["nominal_int8_peak_tops"] = 4500.0
-        roofline["kernel_share_of_step"] = roofline["kernel_ms"] * (M / Mc) / (elapsed_ms / args.steps)
-        dtype = f"i8 slices ({PREC[-1]} x 7 bit, exact i32 accumulation on tcgen05, FP64 combination): f64-equivalent, see accuracy"
-        launches_per_chunk = 4       # kmat_cross, slice_i8, trmm_sumsq_i8, predict_finalize
-    else:
-        roofline, dtype, launches_per_chunk = fp64_roofline, "f64", 3
+    config = {"workload": WORKLOAD, "points_per_gpu_per_step": M, "chunk_points": Mc,
+              "parallelism": f"x*-shard x{world}, L^-1/alpha replicated", "precision": PREC, "precision_requested": args.precision,
+              "l2": "working set per chunk (K* slices 1.3 GiB + L^-1 slices 0.3 GiB) exceeds the 126 MB L2; no flush needed",
+              "warmup_run": warm, "accuracy": accuracy, "mll_grad": mll_grad, "fp64_dmma_mode": fp64_mode}
+    if side:
+        config["other_modes"] = side
+    if args.strong_points > 0:
+        ss = strong_scaling_block(em, world, rank, dev, args.strong_points, args.precision)
+        if rank == 0:
+            config["strong_scaling"] = ss
+    if rank == 0 and not args.no_config1 and world == 1:
+        try:
+            config["config1"] = config1_block(dev)
+        except Exception as exc:      # noqa: BLE001 -- a side measurement must not lose the headline line
+            config["config1"] = {"error": repr(exc)[:300]}
     line = {
-        "metric": "predict points/sec (mean+var) N=8192 D=8", "value": value, "unit": "points/s", "n_gpus": world,
-        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+        "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
-        "config": {"workload": "configs[1]: Matern-5/2 ARD emulator, N_train=8192 D=8, predict mean+noisy std",
-                   "points_per_gpu_per_step": M, "chunk_points": Mc, "parallelism": f"x*-shard x{world}, L^-1/alpha replicated",
-                   "precision": PREC, "precision_requested": args.precision,
-                   "l2": "working set per chunk (K* 2 GiB + its slices + L^-1) exceeds the 126 MB L2; no flush needed"},
-        "accuracy": {"max_rel_err_std_vs_fp64_dmma_path": headline_err_std, "max_err_mean_vs_fp64_dmma_path_rel_to_scale": headline_err_mean,
-                     "tolerance": 1e-6, "points": int(M),
-                     "note": "every point of the timed step compared with the precision='fp64' (DMMA) arm of the same run; "
-                             "the FP64 arm itself is within 3e-12 / 5e-13 of cuSOLVER/cuBLAS FP64 math (tests)"},
+        "config": config,
         "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": int(M * DIM * 8), "d2h_bytes_per_step": int(M * 16),
-                "steps": e2e_steps, "api": "GPEmulator.predict(numpy)  [default precision='auto']", "max_abs_diff_vs_device_arm": parity},
+                "steps": args.steps, "api": "GPEmulator.predict(numpy)  [default precision='auto']" if args.precision == "auto"
+                else f"GPEmulator.predict(numpy, precision='{args.precision}')", "max_abs_diff_vs_device_arm": parity},
         "gpu_launches": int(args.steps * n_chunks * launches_per_chunk),
         "roofline": roofline,
-        "fp64_dmma_mode": {"value": f64_value, "unit": "points/s", "ms_per_step": f64_ms / args.steps, "roofline": fp64_roofline,
-                           "note": "precision='fp64': the same predict with the variance contraction on the FP64 tensor path (DMMA)"},
-        "mll_grad": ({"evals_per_s": 1e3 / (sum(mll_ms) / len(mll_ms)), "ms_per_eval": sum(mll_ms) / len(mll_ms),
-                      "n_train": eng.N, "what": "K_hat build + Cholesky + L^-1 + alpha + -mll + K_hat^-1 + gradient reduce",
-                      "k_inverse": (f"int8x{lauum_default} slices on tcgen05 kind::i8 (gpx_lauum_i8)" if lauum_default else "FP64 DMMA lauum"),
-                      "ms_per_eval_all_fp64": sum(mll_ms_fp64) / len(mll_ms_fp64),
-                      "ms_per_eval_experimental_i8_trtri": (sum(mll_ms_i8_trtri) / len(mll_ms_i8_trtri)) if mll_ms_i8_trtri else None,
-                      "experimental_i8_trtri_note": "opt-in (GPX_TRTRI=i8): L^-1 accurate to ~1e-8 of its norm -- enough for loss and "
-                                                    "gradients, not for the predictive variance at small noise; not used by any other number here"}
-                     if mll_ms else None),
-        "tf32_mode": tf32,
-        "int8_mode": int8,
         "clocks": clocks.summary(),
     }
     if rank == 0 and not args.no_cpu_baseline and world == 1:
-        Xc, yc, Xsc, hyp = X, y, Xs, hyper
-        r, t_pred, t_fac, threads = cpu_oracle_predict_rate(Xc, yc, Xsc, hyp, min(args.cpu_sample, M))
+        r, t_pred, t_fac, threads = cpu_oracle_predict_rate(X, y, Xs, hyper, min(args.cpu_sample, M))
         line["cpu_baseline"] = {"value": r, "unit": "points/s", "cores": threads, "kind": "port",
                                 "sample": f"first {min(args.cpu_sample, M)} X* points, chunks of 4096, {t_pred:.1f} s "
                                           f"(factorisation {t_fac:.1f} s excluded)"}
-    if rank == 0 and not args.no_cpu_baseline and world == 1:
-        line["torch_gpu_baseline"] = torch_gpu_predict_rate(X, y, Xs, hyper, dev, min(32768, M))
+        line["config"]["torch_gpu_baseline"] = torch_gpu_predict_rate(X, y, Xs, hyper, dev, min(32768, M))
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -48,6 +48,7 @@ _SIGS = {
     "gpx_slice_i8": (C.c_int, [_P, C.c_int, C.c_int, C.c_long, _P, C.c_long, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "gpx_i8_row_tiles": (C.c_int, [C.c_int]),
     "gpx_i8_max_n": (C.c_int, [C.c_int]),
+    "gpx_i8_clusters": (C.c_int, []),
     "gpx_kmat_cross_i8": (C.c_int, [_P, C.c_long, _P, C.c_int, C.c_int, _P, _P, _P, C.c_int, _P, _P, C.c_long, C.c_int, C.c_int,
                                     C.c_int, _P, C.c_int, _P]),
     "gpx_trmm_sumsq_i8": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),

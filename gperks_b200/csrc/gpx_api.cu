@@ -32,6 +32,7 @@ int kmat_cross_i8(const double*, long, const double*, int, int, const double*, c
 int trmm_sumsq_i8(const int8_t*, const double*, int, const int8_t*, int, int, int, const double*, double*, cudaStream_t);
 int i8_row_tiles(int);
 int i8_max_np(int);
+int i8_clusters();
 size_t predict_i8_workspace_bytes(int, int, int);
 size_t predict_i8_planes_offset(int, int, int, int);
 int predict_meanvar_i8(const double*, long, const double*, int, int, const double*, const double*, const double*, int,
@@ -231,6 +232,7 @@ int gpx_slice_i8(const double* src, int rows, int cols, long ld_src, signed char
 }
 
 int gpx_i8_max_n(int bits) { return (bits == 7 || bits == 8) ? i8_max_np(bits) : 0; }
+int gpx_i8_clusters(void) { return i8_clusters(); }
 
 int gpx_i8_row_tiles(int Np) { return i8_row_tiles(Np); }
 

@@ -565,6 +565,9 @@ static void cluster2_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* at, in
     cfg.numAttrs = 1;
 }
 
+static int g_i8_clusters = 0;
+int i8_clusters() { return g_i8_clusters; }     // clusters of the last configured persistent kernel (diagnostics)
+
 template <int S, int BITS>
 static int launch_i8(const int8_t* Ls, const double* inv_scale, int Np, const int8_t* Kp, int Mc, const double* amax_ptr,
                      double* qpart, cudaStream_t st) {
@@ -579,6 +582,8 @@ static int launch_i8(const int8_t* Ls, const double* inv_scale, int Np, const in
     cudaLaunchAttribute at[1];
     if (!attr[dev]) {
         cudaFuncSetAttribute(trmm_sumsq_i8p_kernel<S, BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+        // the whole 228 KB as shared memory: the SM's carve-out must also hold the K* builder CTA that runs beside this kernel
+        cudaFuncSetAttribute(trmm_sumsq_i8p_kernel<S, BITS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(trmm_sumsq_i8_kernel<S, 64, true, BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
         cudaFuncSetAttribute(trmm_sumsq_i8_kernel<S, 64, false, BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
         cluster2_config(cfg, at, 2, C::SMEM_BYTES, st);
@@ -590,6 +595,7 @@ static int launch_i8(const int8_t* Ls, const double* inv_scale, int Np, const in
             n = prop.multiProcessorCount / 2;
         }
         max_clusters[dev] = n;
+        g_i8_clusters = n;
         attr[dev] = true;
     }
     CUtensorMap tmA, tmAh, tmB;

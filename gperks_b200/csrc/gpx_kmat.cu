@@ -286,6 +286,8 @@ static int launch_kmat_cross_i8(const double* Xs, long m_valid, const double* X,
     do {                                                                                                                      \
         if (smem > 48 * 1024)                                                                                                 \
             cudaFuncSetAttribute(kmat_cross_i8_kernel<KIND, S_, B_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        cudaFuncSetAttribute(kmat_cross_i8_kernel<KIND, S_, B_>, cudaFuncAttributePreferredSharedMemoryCarveout,              \
+                             cudaSharedmemCarveoutMaxShared);                                                                 \
         kmat_cross_i8_kernel<KIND, S_, B_><<<grid, P_THREADS, smem, st>>>(Xs, m_valid, X, N, D, theta, xa, xr, alpha, planes, \
                                                                           plane_rows, Np, mean_part, Mc);                     \
     } while (0)

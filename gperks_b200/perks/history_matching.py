@@ -77,13 +77,14 @@ class Wave:
                 PV[lo:hi] = PVd.cpu().numpy()
         return I, PV
 
-    def compute_impl_sharded(self, X, group=None, block_points: int = 4_000_000):
+    def compute_impl_sharded(self, X, group=None, block_points: int = 4_000_000, src: int = 0, all_ranks: bool = False):
         """``compute_impl`` over all ranks of an initialised ``torch.distributed`` group (one process per GPU, every rank
-        holding the same emulators and the same X): rank r scores a contiguous slice of the points with all emulators
-        resident on its own GPU, so the per-point maximum over emulators stays local, and only (I, PV) -- 16 B/point --
-        are exchanged.  Bitwise identical to the single-GPU result.  """
+        holding the same emulators): the rows of ``X`` -- read on group rank ``src`` only, pass None elsewhere -- are
+        scattered contiguously over the ranks, rank r scores its slice with all emulators resident on its own GPU, so the
+        per-point maximum over emulators stays local, and only (I, PV) -- 16 B/point -- are gathered back to ``src``
+        (``all_ranks=True``: broadcast to everyone).  Bitwise identical to the single-GPU result.  """
         from ..parallel import sharded_predict
-        return sharded_predict(lambda x: self.compute_impl(x, block_points), X, group=group)
+        return sharded_predict(lambda x: self.compute_impl(x, block_points), X, group=group, src=src, all_ranks=all_ranks)
 
     def find_regions(self, X):
         n_samples = X.shape[0]

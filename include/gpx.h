@@ -152,6 +152,7 @@ int gpx_slice_i8(const double* src, int rows, int cols, long ld_src, signed char
                  int bits, int tri, double* inv_scale, const double* amax_ptr, void* stream);
 int gpx_i8_row_tiles(int Np);
 int gpx_i8_max_n(int bits);
+int gpx_i8_clusters(void);   /* diagnostics: resident 2-CTA clusters of the persistent tensor-core kernel configured last (0 = none yet) */
 /* gpx_kmat_cross_i8: gpx_kmat_cross and gpx_slice_i8 (tri = 0, amax = outputscale) in one pass: the K* chunk is evaluated in
  * FP64 and written only as its int8 slices (same bytes, same mean_part as the two calls). */
 int gpx_kmat_cross_i8(const double* Xs, long m_valid, const double* X, int N, int D, const double* theta, const double* xa,

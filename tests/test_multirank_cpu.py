@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from gperks_b200.parallel import run_jobs_round_robin, shard_bounds, sharded_predict
+from gperks_b200.parallel import run_jobs_round_robin, scatter_rows, shard_bounds, sharded_predict
 
 
 def test_shard_bounds_cover_and_balance():
@@ -32,9 +32,22 @@ def _worker(rank, world, port, M, q):
     try:
         rng = np.random.default_rng(0)
         X = rng.random((M, 3))
-        mean, std = sharded_predict(_fake_predict, X)
         ref_m, ref_s = _fake_predict(X)
-        ok = np.array_equal(mean, ref_m) and np.array_equal(std, ref_s)
+        # the product contract: X* lives on the source rank only, rows are scattered, results gathered back to it
+        mean, std = sharded_predict(_fake_predict, X if rank == 0 else None)
+        if rank == 0:
+            ok = np.array_equal(mean, ref_m) and np.array_equal(std, ref_s)
+        else:
+            ok = mean is None and std is None
+        # another source rank, result broadcast to everyone
+        mean, std = sharded_predict(_fake_predict, X if rank == 1 else None, src=1, all_ranks=True)
+        ok = ok and np.array_equal(mean, ref_m) and np.array_equal(std, ref_s)
+        # every rank already holds X*: no scatter
+        mean, std = sharded_predict(_fake_predict, X, replicated=True)
+        ok = ok and ((np.array_equal(mean, ref_m) and np.array_equal(std, ref_s)) if rank == 0 else mean is None)
+        # the row dealer on its own
+        rows, lo, hi, m_all = scatter_rows(X if rank == 0 else None)
+        ok = ok and m_all == M and (lo, hi) == shard_bounds(M, world, rank) and np.array_equal(rows.numpy(), X[lo:hi])
         jobs = list(range(5))
         res = run_jobs_round_robin(jobs, lambda j: {"job": j, "rank": dist.get_rank(), "score": j * j})
         ok = ok and [r["job"] for r in res] == jobs and [r["rank"] for r in res] == [j % world for j in jobs]

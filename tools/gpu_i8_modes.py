@@ -28,7 +28,19 @@ lib = nv.lib()
 out = {"impl": os.environ.get("GPX_I8_IMPL", "persistent"), "cases": []}
 
 
-def timed(fn, reps=3):
+def smi_clock():
+    import subprocess
+    try:
+        return float(subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm", "--format=csv,noheader,nounits", "-i", "0"],
+                                    capture_output=True, text=True, timeout=5).stdout.strip())
+    except Exception:
+        return None
+
+
+LAST_CLOCK = [None]
+
+
+def timed(fn, reps=3, clock=False):
     fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -36,6 +48,8 @@ def timed(fn, reps=3):
     for _ in range(reps):
         fn()
     e1.record()
+    if clock:                      # sampled while the launches above are still running
+        LAST_CLOCK[0] = smi_clock()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
 
@@ -95,10 +109,13 @@ for spec in args.sizes:
                 st = nv.stream_ptr()
                 t["chunk"] = Mc
                 t["mma_kernel_ms"] = timed(lambda: nv.check(lib.gpx_trmm_sumsq_i8(
-                    nv.ptr(eng.S_i8), nv.ptr(eng.S_i8_inv_scale), eng.Np, Kp, Mc, S, bits, nv.ptr(eng.theta) + 8 * D, nv.ptr(qp), st), "mma"))
+                    nv.ptr(eng.S_i8), nv.ptr(eng.S_i8_inv_scale), eng.Np, Kp, Mc, S, bits, nv.ptr(eng.theta) + 8 * D, nv.ptr(qp), st), "mma"),
+                    reps=max(3, int(300 / max(t["ms_serial"] * Mc / M, 0.1))), clock=True)
                 t["builder_kernel_ms"] = timed(lambda: nv.check(lib.gpx_kmat_cross_i8(
                     nv.ptr(Xt), Mc, nv.ptr(eng.X), N, D, nv.ptr(eng.theta), None, None, 3, nv.ptr(eng.alpha), Kp, Mc, S, bits, eng.Np,
                     nv.ptr(mp), Mc, st), "builder"))
+                t["clusters"] = int(lib.gpx_i8_clusters())
+                t["sm_mhz_during_mma_kernel"] = LAST_CLOCK[0]
                 t["mma_raw_int8_tops"] = S * (S + 1) / 2 * N * N * Mc / t["mma_kernel_ms"] / 1e9
                 t["mma_fp64_equiv_tflops"] = N * N * Mc / t["mma_kernel_ms"] / 1e9
             print(json.dumps(t), flush=True)
