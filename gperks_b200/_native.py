@@ -62,11 +62,24 @@ _SIGS = {
                                          C.c_int, _P, _P, _P, C.c_int, C.c_int, _P, _P, C.c_double, C.c_double, C.c_double,
                                          _P, _P, _P, C.c_size_t, C.c_int, _P, _P]),
     "gpx_implausibility": (C.c_int, [_P, _P, C.c_long, C.c_int, _P, _P, C.c_int, _P, _P, _P]),
+    "gpx_wave_i8_workspace_bytes": (C.c_size_t, [_P, C.c_int, C.c_int]),
+    "gpx_wave_i8": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_long, _P, _P, C.c_int, _P, _P, _P, _P, _P, C.c_size_t, C.c_int, _P, _P]),
+    "gpx_compact_below_workspace_bytes": (C.c_size_t, [C.c_long]),
+    "gpx_compact_below": (C.c_int, [_P, C.c_long, C.c_double, _P, _P, _P, C.c_size_t, _P]),
     "gpx_peak_dmma": (C.c_double, [C.c_int, C.c_int, _P, _P]),
     "gpx_peak_i8mma": (C.c_double, [C.c_int, C.c_int, _P]),
     "gpx_peak_dfma": (C.c_double, [C.c_int, C.c_int, _P, _P]),
 }
 EXPORTS = tuple(_SIGS)
+
+
+class I8EmulatorDesc(C.Structure):
+    """gpx_i8_emulator of include/gpx.h: a host struct of device pointers describing one factorised emulator."""
+    _fields_ = [("X", _P), ("theta", _P), ("xa", _P), ("xr", _P), ("alpha", _P), ("Ls", _P), ("inv_scale", _P),
+                ("feat_idx", _P), ("weights", _P), ("bias", _P),
+                ("y_mu", C.c_double), ("y_sigma", C.c_double), ("min_var", C.c_double),
+                ("N", C.c_int), ("Np", C.c_int), ("kind", C.c_int), ("nslices", C.c_int), ("bits", C.c_int),
+                ("n_feat", C.c_int), ("degree", C.c_int), ("reserved", C.c_int)]
 
 
 def lib() -> C.CDLL:

@@ -43,8 +43,14 @@ int predict_meanvar_tf32(const double*, long, const double*, int, int, const dou
                          const float*, const float*, int, const double*, const double*, const int*, int, int,
                          const double*, const double*, double, double, double, double*, double*, void*, size_t, int,
                          int, cudaStream_t);
-int implausibility(const double*, const double*, long, int, const double*, const double*, int, double*, double*,
+int implausibility(const double*, const double*, long, long, int, const double*, const double*, int, double*, double*,
                    cudaStream_t);
+struct I8Emulator;
+size_t wave_i8_workspace_bytes(const I8Emulator*, int, int);
+int wave_i8(const I8Emulator*, int, int, const double*, long, const double*, const double*, int, double*, double*, double*, double*,
+            void*, size_t, int, cudaStream_t, cudaStream_t);
+size_t compact_below_workspace_bytes(long);
+int compact_below(const double*, long, double, long long*, long long*, void*, size_t, cudaStream_t);
 int predict_meanvar(const double*, long, const double*, int, int, const double*, const double*, const double*, int,
                     const double*, int, const double*, const double*, const int*, int, int, const double*,
                     const double*, double, double, double, double*, double*, void*, size_t, int, cudaStream_t);
@@ -305,7 +311,36 @@ int gpx_implausibility(const double* mean, const double* std_, long M, int E, co
                        int maxno, double* I, double* PV, void* stream) {
     if (!mean || !std_ || !z || !v || !I || !PV) return -1;
     if (M < 0 || E < 1) return -3;
-    return implausibility(mean, std_, M, E, z, v, maxno, I, PV, ST(stream));
+    return implausibility(mean, std_, M, M, E, z, v, maxno, I, PV, ST(stream));
+}
+
+size_t gpx_wave_i8_workspace_bytes(const gpx_i8_emulator* em, int E, int Mc) {
+    if (!em || E < 1 || Mc <= 0) return 0;
+    return wave_i8_workspace_bytes(reinterpret_cast<const I8Emulator*>(em), E, Mc);
+}
+
+int gpx_wave_i8(const gpx_i8_emulator* em, int E, int D, const double* Xs, long M, const double* z, const double* v, int maxno,
+                double* I, double* PV, double* mean_out, double* std_out, void* workspace, size_t workspace_bytes, int Mc,
+                void* stream, void* mma_stream) {
+    if (!em || !Xs || !z || !v || !I || !PV || !workspace) return -1;
+    if (M < 0) return -5;
+    if ((mean_out == nullptr) != (std_out == nullptr)) return -11;
+    for (int e = 0; e < E; ++e) {
+        const gpx_i8_emulator& m = em[e];
+        if (!m.X || !m.theta || !m.alpha || !m.Ls || !m.inv_scale) return -1;
+        if ((m.xa == nullptr) != (m.xr == nullptr)) return -1;
+        if (m.weights && m.n_feat > 0 && (!m.feat_idx || m.degree < 1)) return -1;
+    }
+    return wave_i8(reinterpret_cast<const I8Emulator*>(em), E, D, Xs, M, z, v, maxno, I, PV, mean_out, std_out, workspace,
+                   workspace_bytes, Mc, ST(stream), ST(mma_stream));
+}
+
+size_t gpx_compact_below_workspace_bytes(long M) { return compact_below_workspace_bytes(M < 0 ? 0 : M); }
+
+int gpx_compact_below(const double* values, long M, double cutoff, long long* idx, long long* count, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+    if (!values || !idx || !count || !workspace) return -1;
+    return compact_below(values, M, cutoff, idx, count, workspace, workspace_bytes, ST(stream));
 }
 
 double gpx_peak_dmma(int blocks, int iters, double* sink, void* stream) {

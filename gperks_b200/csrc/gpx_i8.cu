@@ -335,7 +335,8 @@ trmm_sumsq_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 template <int S, int BITS>
 __global__ void __launch_bounds__(I_THREADS, 2)      // "2" caps the kernel at 96 registers per thread: 30 K registers, the other half of the file is the builder's
 trmm_sumsq_i8p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmB, int Np, int Mc,
-                      const double* __restrict__ inv_scale, const double* __restrict__ amax_ptr, double* __restrict__ qpart) {
+                      const double* __restrict__ inv_scale, const double* __restrict__ amax_ptr, double* __restrict__ qpart,
+                      const int probe) {      // probe != 0 (GPX_I8_PROBE=nofill, timing experiments only): the ring is filled once, never refilled
     using C = I8Cfg<S, 64>;
     constexpr int BKB = 64;
     extern __shared__ unsigned char smem_raw[];
@@ -396,6 +397,7 @@ trmm_sumsq_i8p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
                 const int it = 2 * itp + (int)crank;
                 for (int kt = 0; kt < nk; ++kt, ++git) {
                     const uint32_t s = git % C::STAGES, round = git / C::STAGES;
+                    if (probe && round > 0) continue;
                     if (round > 0) mbar_wait(empty0 + 8 * s, (round - 1) & 1);
                     mbar_arrive_expect_tx(full0 + 8 * s, C::STAGE_BYTES);
                     const uint32_t dst = tile0 + s * C::STAGE_BYTES;
@@ -424,7 +426,7 @@ trmm_sumsq_i8p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
                 }
                 for (int kt = 0; kt < nk; ++kt, ++git) {
                     const uint32_t s = git % C::STAGES, round = git / C::STAGES;
-                    mbar_wait(full0 + 8 * s, round & 1);
+                    if (!probe || round == 0) mbar_wait(full0 + 8 * s, round & 1);
                     tc_fence_after();
                     const uint32_t st = tile0 + s * C::STAGE_BYTES;
 #pragma unroll
@@ -443,7 +445,7 @@ trmm_sumsq_i8p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
                             }
                         }
                     }
-                    umma_commit_multicast(empty0 + 8 * s, 3);     // both producers wait for both tensor cores
+                    if (!probe) umma_commit_multicast(empty0 + 8 * s, 3);     // both producers wait for both tensor cores
                 }
                 umma_commit(acc_full);
             }
@@ -614,7 +616,9 @@ static int launch_i8(const int8_t* Ls, const double* inv_scale, int Np, const in
         const int items = tiles / 2;
         const int clusters = items < max_clusters[dev] ? items : max_clusters[dev];
         cluster2_config(cfg, at, 2 * clusters, C::SMEM_BYTES, st);
-        cudaError_t e = cudaLaunchKernelEx(&cfg, trmm_sumsq_i8p_kernel<S, BITS>, tmAh, tmB, Np, Mc, inv_scale, amax_ptr, qpart);
+        static int probe = -1;
+        if (probe < 0) { const char* pe = getenv("GPX_I8_PROBE"); probe = (pe && pe[0] == 'n') ? 1 : 0; }
+        cudaError_t e = cudaLaunchKernelEx(&cfg, trmm_sumsq_i8p_kernel<S, BITS>, tmAh, tmB, Np, Mc, inv_scale, amax_ptr, qpart, probe);
         if (e != cudaSuccess) return -1000 - (int)e;
     }
     GPX_CHECK_LAUNCH();

@@ -443,48 +443,43 @@ int kmat_cross_i8(const double* Xs, long m_valid, const double* X, int N, int D,
                   const double* xr, int kind, const double* alpha, int8_t* planes, long plane_rows, int nslices, int bits, int Np,
                   double* mean_part, int Mc, cudaStream_t st);
 
-// workspace: two K* slice buffers [S][Mc][Np] int8 | two mean_part [nb][Mc] | two qpart [nt][Mc]   (double-buffered per chunk)
-size_t predict_i8_workspace_bytes(int Np, int Mc, int nslices) {
-    const size_t nb = Np / TILE;
-    return 2 * ((size_t)nslices * Mc * Np + (nb + i8_row_tiles(Np)) * (size_t)Mc * 8);
-}
-size_t predict_i8_planes_offset(int Np, int Mc, int nslices, int buffer) { return (size_t)buffer * nslices * Mc * Np; }
+int implausibility(const double* mean, const double* std_, long M, long ld, int E, const double* z, const double* v, int maxno,
+                   double* I, double* PV, cudaStream_t st);
 
-// As predict_meanvar; the variance contraction runs on the integer tensor cores from `nslices` slices of `bits` bits of L^-1
-// (Ls, inv_scale: gpx_slice_i8 of S, once per factorisation) and of each K* chunk (written directly as slices by the builder).
-// K*, the posterior mean and the final reduction are evaluated exactly like the FP64 path's, so the mean is bit-identical
-// to predict_meanvar.
-//
-// Chunk pipeline: with `mma` (a second, higher-priority stream owned by the caller) the tensor-core kernel of chunk c runs on
-// `mma` while the K* builder of chunk c+1 runs on `st`: the builder is FP64-ALU work in <= 128 registers and a few KB of shared
-// memory per CTA, so its CTAs are resident on the same SMs as the tensor-core kernel's (one 183 KB CTA per SM for five slices) and
-// fill pipes that kernel leaves idle.  Order on `st`: builder(0), builder(1), [wait mma(0)] finalize(0), builder(2), [wait mma(1)]
-// finalize(1), ... -- everything the caller sees is ordered on `st`; buffer (c & 1) is rewritten by builder(c+2) only after
-// finalize(c).  mma == nullptr (or a single chunk): the same launches back to back on `st`.
-int predict_meanvar_i8(const double* Xs, long M, const double* X, int N, int D, const double* theta, const double* xa,
-                       const double* xr, int kind, const int8_t* Ls, const double* inv_scale, int nslices, int bits, int Np,
-                       const double* alpha, const double* prior_mean, const int* feat_idx, int n_feat, int degree,
-                       const double* weights, const double* bias, double y_mu, double y_sigma, double min_var,
-                       double* out_mean, double* out_std, void* workspace, size_t workspace_bytes, int Mc, cudaStream_t st,
-                       cudaStream_t mma) {
-    if (Mc <= 0 || Mc % TILE != 0) return -25;
-    if (Np % TILE != 0 || Np < N) return -11;
-    if (D > MAXD || D < 1) return -5;
-    if (Np > i8_max_np(bits)) return -13;
-    if (workspace_bytes < predict_i8_workspace_bytes(Np, Mc, nslices)) return -23;
-    const int nb = Np / TILE, nt = i8_row_tiles(Np);
-    int8_t* Kp[2];
-    double* mean_part[2];
-    double* qpart[2];
-    Kp[0] = reinterpret_cast<int8_t*>(workspace);
-    Kp[1] = Kp[0] + (size_t)nslices * Mc * Np;
-    mean_part[0] = reinterpret_cast<double*>(Kp[1] + (size_t)nslices * Mc * Np);
-    mean_part[1] = mean_part[0] + (size_t)nb * Mc;
-    qpart[0] = mean_part[1] + (size_t)nb * Mc;
-    qpart[1] = qpart[0] + (size_t)nt * Mc;
-    const double* amax = theta + D;          // K* <= outputscale for every kernel family here
-    const long n_chunks = (M + Mc - 1) / Mc;
-    const bool overlap = mma != nullptr && mma != st && n_chunks > 1;
+// ---- the chunk pipeline shared by the one-emulator predict and the multi-emulator history-matching wave ----------------
+// A work item = (emulator, chunk of <= Mc test points).  With `mma` (a second, higher-priority stream owned by the caller) the
+// tensor-core kernel of item i runs on `mma` while the K* builder of item i+1 runs on `st`: the builder is FP64-ALU work in
+// <= 128 registers and a few KB of shared memory per CTA, so its CTAs are resident on the same SMs as the tensor-core kernel's
+// (one 188 KB CTA per SM for five slices).  Order on `st`: builder(0), builder(1), [wait mma(0)] finalize(0), builder(2),
+// [wait mma(1)] finalize(1), ... -- everything the caller sees is ordered on `st`; buffer (i & 1) is rewritten by builder(i+2)
+// only after finalize(i).  mma == nullptr (or a single item): the same launches back to back on `st`.
+struct I8Emulator {          // device pointers of one factorised emulator (mirrors gpx_i8_emulator of include/gpx.h)
+    const double* X; const double* theta; const double* xa; const double* xr; const double* alpha;
+    const int8_t* Ls; const double* inv_scale;
+    const int* feat_idx; const double* weights; const double* bias;
+    double y_mu, y_sigma, min_var;
+    int N, Np, kind, nslices, bits, n_feat, degree, reserved;
+};
+static_assert(sizeof(I8Emulator) == 10 * 8 + 3 * 8 + 8 * 4, "I8Emulator must match gpx_i8_emulator (include/gpx.h)");
+struct I8Item {
+    const I8Emulator* em;
+    const double* xs;        // first test point of the chunk (raw inputs, D columns)
+    long mv;                 // valid points
+    const double* prior;     // prior mean of those points, or null (polynomial / none)
+    double* out_mean;
+    double* out_std;
+};
+
+static size_t i8_item_bytes(int Np, int Mc, int nslices) {
+    const size_t nb = Np / TILE;
+    return (size_t)nslices * Mc * Np + (nb + i8_row_tiles(Np)) * (size_t)Mc * 8;
+}
+
+template <class ItemAt, class AfterFinalize>
+static int run_i8_pipeline(long n_items, ItemAt item_at, AfterFinalize after_finalize, int D, size_t buf_bytes, void* workspace,
+                           cudaStream_t st, cudaStream_t mma) {
+    unsigned char* buf[2] = {reinterpret_cast<unsigned char*>(workspace), reinterpret_cast<unsigned char*>(workspace) + buf_bytes};
+    const bool overlap = mma != nullptr && mma != st && n_items > 1;
     cudaEvent_t ev_built[2] = {nullptr, nullptr}, ev_mma[2] = {nullptr, nullptr};
     if (overlap) {
         for (int i = 0; i < 2; ++i) {
@@ -494,49 +489,58 @@ int predict_meanvar_i8(const double* Xs, long M, const double* X, int N, int D, 
         }
     }
     int rc = 0;
-    auto chunk_args = [&](long c, long& m0, long& mv, int& mc) {
-        m0 = c * Mc;
-        mv = (M - m0 < Mc) ? (M - m0) : Mc;
-        mc = round_up((int)mv, TILE);
+    // item buffer = [slice planes of the item | mean_part | qpart], sized by the caller for the largest item
+    auto parts = [&](long i, const I8Item& it, int8_t*& Kp, double*& mean_part, double*& qpart, int& mc) {
+        const I8Emulator& e = *it.em;
+        mc = round_up((int)it.mv, TILE);
+        Kp = reinterpret_cast<int8_t*>(buf[i & 1]);
+        const size_t plane_bytes = ((size_t)e.nslices * mc * e.Np + 255) / 256 * 256;
+        mean_part = reinterpret_cast<double*>(buf[i & 1] + plane_bytes);
+        qpart = mean_part + (size_t)(e.Np / TILE) * mc;
     };
-    auto build = [&](long c) -> int {
-        long m0, mv; int mc;
-        chunk_args(c, m0, mv, mc);
-        const int b = (int)(c & 1);
-        int r = kmat_cross_i8(Xs + m0 * D, mv, X, N, D, theta, xa, xr, kind, alpha, Kp[b], mc, nslices, bits, Np, mean_part[b], mc, st);
+    auto build = [&](long i) -> int {
+        const I8Item it = item_at(i);
+        const I8Emulator& e = *it.em;
+        int8_t* Kp; double *mean_part, *qpart; int mc;
+        parts(i, it, Kp, mean_part, qpart, mc);
+        int r = kmat_cross_i8(it.xs, it.mv, e.X, e.N, D, e.theta, e.xa, e.xr, e.kind, e.alpha, Kp, mc, e.nslices, e.bits, e.Np,
+                              mean_part, mc, st);
         if (r == 0 && overlap) {
-            cudaEventRecord(ev_built[b], st);
-            cudaStreamWaitEvent(mma, ev_built[b], 0);
+            cudaEventRecord(ev_built[i & 1], st);
+            cudaStreamWaitEvent(mma, ev_built[i & 1], 0);
         }
         return r;
     };
-    auto contract = [&](long c) -> int {
-        long m0, mv; int mc;
-        chunk_args(c, m0, mv, mc);
-        const int b = (int)(c & 1);
-        int r = trmm_sumsq_i8(Ls, inv_scale, Np, Kp[b], mc, nslices, bits, amax, qpart[b], overlap ? mma : st);
-        if (r == 0 && overlap) cudaEventRecord(ev_mma[b], mma);
+    auto contract = [&](long i) -> int {
+        const I8Item it = item_at(i);
+        const I8Emulator& e = *it.em;
+        int8_t* Kp; double *mean_part, *qpart; int mc;
+        parts(i, it, Kp, mean_part, qpart, mc);
+        int r = trmm_sumsq_i8(e.Ls, e.inv_scale, e.Np, Kp, mc, e.nslices, e.bits, e.theta + D, qpart, overlap ? mma : st);
+        if (r == 0 && overlap) cudaEventRecord(ev_mma[i & 1], mma);
         return r;
     };
-    auto finalize = [&](long c) {
-        long m0, mv; int mc;
-        chunk_args(c, m0, mv, mc);
-        const int b = (int)(c & 1);
-        if (overlap) cudaStreamWaitEvent(st, ev_mma[b], 0);
-        predict_finalize_kernel<<<(int)((mv + 255) / 256), 256, 0, st>>>(
-            Xs + m0 * D, mv, D, xa, xr, theta, mean_part[b], qpart[b], nb, mc, prior_mean ? prior_mean + m0 : nullptr, feat_idx,
-            n_feat, degree, weights, bias, y_mu, y_sigma, min_var, out_mean + m0, out_std + m0, nt);
+    auto finalize = [&](long i) -> int {
+        const I8Item it = item_at(i);
+        const I8Emulator& e = *it.em;
+        int8_t* Kp; double *mean_part, *qpart; int mc;
+        parts(i, it, Kp, mean_part, qpart, mc);
+        if (overlap) cudaStreamWaitEvent(st, ev_mma[i & 1], 0);
+        predict_finalize_kernel<<<(int)((it.mv + 255) / 256), 256, 0, st>>>(
+            it.xs, it.mv, D, e.xa, e.xr, e.theta, mean_part, qpart, e.Np / TILE, mc, it.prior, e.feat_idx, e.n_feat, e.degree,
+            e.weights, e.bias, e.y_mu, e.y_sigma, e.min_var, it.out_mean, it.out_std, i8_row_tiles(e.Np));
+        return after_finalize(i);
     };
-    // software pipeline over chunks: build(c+1) is enqueued before the wait for contract(c)
+    // software pipeline: build(i+1) (and the enqueue of contract(i+1)) precede the wait for contract(i)
     rc = build(0);
     if (rc == 0) rc = contract(0);
-    for (long c = 0; c < n_chunks && rc == 0; ++c) {
-        if (c + 1 < n_chunks) {
-            rc = build(c + 1);
-            if (rc == 0) rc = contract(c + 1);      // on `mma` it queues behind contract(c); serial mode: after build(c+1) on `st`
+    for (long i = 0; i < n_items && rc == 0; ++i) {
+        if (i + 1 < n_items) {
+            rc = build(i + 1);
+            if (rc == 0) rc = contract(i + 1);      // on `mma` it queues behind contract(i); serial mode: after build(i+1) on `st`
             if (rc) break;
         }
-        finalize(c);
+        rc = finalize(i);
     }
     if (overlap) {
         if (rc) {                                   // never leave `mma` work un-joined
@@ -552,6 +556,91 @@ int predict_meanvar_i8(const double* Xs, long M, const double* X, int N, int D, 
     if (rc) return rc;
     GPX_CHECK_LAUNCH();
     return 0;
+}
+
+// workspace: two item buffers, each [K* slice planes [S][mc][Np] int8 | mean_part [nb][mc] | qpart [nt][mc]]
+size_t predict_i8_workspace_bytes(int Np, int Mc, int nslices) { return 2 * (i8_item_bytes(Np, Mc, nslices) + 256); }
+size_t predict_i8_planes_offset(int Np, int Mc, int nslices, int buffer) { return (size_t)buffer * (i8_item_bytes(Np, Mc, nslices) + 256); }
+
+// As predict_meanvar; the variance contraction runs on the integer tensor cores from `nslices` slices of `bits` bits of L^-1
+// (Ls, inv_scale: gpx_slice_i8 of S, once per factorisation) and of each K* chunk (written directly as slices by the builder).
+// K*, the posterior mean and the final reduction are evaluated exactly like the FP64 path's, so the mean is bit-identical
+// to predict_meanvar.
+int predict_meanvar_i8(const double* Xs, long M, const double* X, int N, int D, const double* theta, const double* xa,
+                       const double* xr, int kind, const int8_t* Ls, const double* inv_scale, int nslices, int bits, int Np,
+                       const double* alpha, const double* prior_mean, const int* feat_idx, int n_feat, int degree,
+                       const double* weights, const double* bias, double y_mu, double y_sigma, double min_var,
+                       double* out_mean, double* out_std, void* workspace, size_t workspace_bytes, int Mc, cudaStream_t st,
+                       cudaStream_t mma) {
+    if (Mc <= 0 || Mc % TILE != 0) return -25;
+    if (Np % TILE != 0 || Np < N) return -11;
+    if (D > MAXD || D < 1) return -5;
+    if (Np > i8_max_np(bits)) return -13;
+    if (workspace_bytes < predict_i8_workspace_bytes(Np, Mc, nslices)) return -23;
+    const I8Emulator em = {X, theta, xa, xr, alpha, Ls, inv_scale, feat_idx, weights, bias, y_mu, y_sigma, min_var,
+                           N, Np, kind, nslices, bits, n_feat, degree, 0};
+    const long n_chunks = (M + Mc - 1) / Mc;
+    auto item_at = [&](long c) {
+        const long m0 = c * Mc;
+        I8Item it = {&em, Xs + m0 * D, (M - m0 < Mc) ? (M - m0) : (long)Mc, prior_mean ? prior_mean + m0 : nullptr, out_mean + m0,
+                     out_std + m0};
+        return it;
+    };
+    return run_i8_pipeline(n_chunks, item_at, [](long) { return 0; }, D, i8_item_bytes(Np, Mc, nslices) + 256, workspace, st, mma);
+}
+
+// ---- multi-emulator history-matching wave -------------------------------------------------------
+// Replaces the body of Wave.compute_impl (GPErks/perks/history_matching.py:43-64): for every chunk of test points all E emulators
+// predict from the same device-resident X* rows -- the (chunk, emulator) items run through ONE chunk pipeline, so the K* builder of
+// emulator e+1 overlaps the tensor-core kernel of emulator e -- into chunk-local [E][Mc] buffers, and the implausibility epilogue
+// (maxno-th largest over the emulators) turns them into I / PV: per-emulator predictions never leave the chip unless asked for.
+size_t wave_i8_workspace_bytes(const I8Emulator* em, int E, int Mc) {
+    size_t item = 0;
+    for (int e = 0; e < E; ++e) {
+        const size_t b = i8_item_bytes(em[e].Np, Mc, em[e].nslices) + 256;
+        item = b > item ? b : item;
+    }
+    return 2 * item + (size_t)2 * E * Mc * 8;
+}
+
+int wave_i8(const I8Emulator* em, int E, int D, const double* Xs, long M, const double* z, const double* v, int maxno,
+            double* I, double* PV, double* mean_out, double* std_out, void* workspace, size_t workspace_bytes, int Mc,
+            cudaStream_t st, cudaStream_t mma) {
+    if (E < 1 || E > 64) return -2;
+    if (Mc <= 0 || Mc % TILE != 0) return -15;
+    if (D > MAXD || D < 1) return -3;
+    for (int e = 0; e < E; ++e) {
+        if (em[e].Np % TILE || em[e].Np < em[e].N || em[e].Np > i8_max_np(em[e].bits)) return -1;
+        if (em[e].nslices < 5 || em[e].nslices > 6) return -1;
+    }
+    if (workspace_bytes < wave_i8_workspace_bytes(em, E, Mc)) return -13;
+    if (M == 0) return 0;
+    size_t item = 0;
+    for (int e = 0; e < E; ++e) {
+        const size_t b = i8_item_bytes(em[e].Np, Mc, em[e].nslices) + 256;
+        item = b > item ? b : item;
+    }
+    double* cmean = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(workspace) + 2 * item);      // [E][Mc] chunk-local
+    double* cstd = cmean + (size_t)E * Mc;
+    const long n_chunks = (M + Mc - 1) / Mc;
+    const bool full = mean_out != nullptr && std_out != nullptr;
+    auto item_at = [&](long i) {
+        const long c = i / E;
+        const int e = (int)(i - c * E);
+        const long m0 = c * Mc;
+        I8Item it = {em + e, Xs + m0 * D, (M - m0 < Mc) ? (M - m0) : (long)Mc, nullptr,
+                     full ? mean_out + (size_t)e * M + m0 : cmean + (size_t)e * Mc, full ? std_out + (size_t)e * M + m0 : cstd + (size_t)e * Mc};
+        return it;
+    };
+    auto after = [&](long i) -> int {
+        const long c = i / E;
+        if ((int)(i - c * E) != E - 1) return 0;
+        const long m0 = c * Mc;
+        const long mv = (M - m0 < Mc) ? (M - m0) : (long)Mc;
+        return full ? implausibility(mean_out + m0, std_out + m0, mv, M, E, z, v, maxno, I + m0, PV + m0, st)
+                    : implausibility(cmean, cstd, mv, Mc, E, z, v, maxno, I + m0, PV + m0, st);
+    };
+    return run_i8_pipeline(n_chunks * E, item_at, after, D, item, workspace, st, mma);
 }
 
 static void set_pred_attrs() {

@@ -413,6 +413,43 @@ class GPEmulator(Trainable):
             return precision
         return self.auto_precisions()[0]
 
+    def i8_descriptor(self, precision: str = "auto"):
+        """``(desc, keepalive)`` -- the ``gpx_i8_emulator`` struct (include/gpx.h) of this emulator's CURRENT factors for the
+        multi-emulator device entry points (``gpx_wave_i8``), or ``None`` when the emulator cannot take that path: ``auto``
+        resolves to the FP64 path (or a TF32 mode was asked for), the prior mean is not one of the package's polynomial means, or
+        the output scaler is not the linear StandardScaler.  ``keepalive`` holds the device tensors the struct points into."""
+        from ..engine import I8_MODES
+        cdev = self._compute_device()
+        scx, scy = self.scaled_data.scx, self.scaled_data.scy
+        if type(scy).__name__ != "StandardScaler":
+            return None
+        with torch.no_grad(), torch.cuda.device(cdev):
+            self.model.eval()
+            self.model.likelihood.eval()
+            eng = self.model._factorized_engine()
+            if precision == "auto":
+                precision = next(c for c in self.auto_precisions() if c == "fp64" or eng.int8_probe_ok(c, AUTO_I8_PROBE_TOL))
+            if precision not in I8_MODES:
+                return None
+            poly = self._poly_spec(cdev)
+            if poly is None:
+                return None
+            S, bits = I8_MODES[precision]
+            eng._ensure_i8(S, bits)
+            xa = torch.as_tensor(numpy.asarray(scx.a, dtype=numpy.float64).reshape(-1), device=cdev)
+            xr = torch.as_tensor((numpy.asarray(scx.b, dtype=numpy.float64)
+                                  - numpy.asarray(scx.a, dtype=numpy.float64)).reshape(-1), device=cdev)
+            n_feat = int(poly.feat_idx.shape[0])
+            keep = (eng, xa, xr, poly, eng.S_i8, eng.S_i8_inv_scale)
+            p = nv.ptr
+            desc = nv.I8EmulatorDesc(
+                X=p(eng.X), theta=p(eng.theta), xa=p(xa), xr=p(xr), alpha=p(eng.alpha), Ls=p(eng.S_i8), inv_scale=p(eng.S_i8_inv_scale),
+                feat_idx=p(poly.feat_idx) if n_feat else None, weights=p(poly.weights) if n_feat else None,
+                bias=p(poly.bias) if poly.bias is not None else None,
+                y_mu=float(scy.mu), y_sigma=float(scy.sigma), min_var=1e-10,
+                N=eng.N, Np=eng.Np, kind=eng.kind, nslices=S, bits=bits, n_feat=n_feat, degree=int(poly.degree), reserved=0)
+        return desc, keep
+
     def predict_device(self, x_dev: torch.Tensor, precision: str = "auto", tf32_kchunk: int = 32,
                        out_mean: Optional[torch.Tensor] = None, out_std: Optional[torch.Tensor] = None):
         """Device-resident predict: raw (unscaled) inputs ``x_dev`` [M, D] already in HBM -> (mean, std) device

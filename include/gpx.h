@@ -193,6 +193,33 @@ int gpx_predict_meanvar_i8(const double* Xs, long M, const double* X, int N, int
 int gpx_implausibility(const double* mean, const double* std_, long M, int E, const double* z, const double* v,
                        int maxno, double* I, double* PV, void* stream);
 
+/* ---- multi-emulator history-matching wave ---------------------------------------------------------
+ * gpx_i8_emulator: the device pointers of one factorised emulator on a sliced-integer mode (a HOST struct; every pointer inside is
+ *   a device pointer): X[N][D] scaled training inputs, theta[D+2], xa/xr[D] unit-cube scaler of the raw test inputs (nullable
+ *   pair), alpha[Np], Ls / inv_scale: gpx_slice_i8(tri = 1) of the inverse factor, polynomial prior mean (feat_idx[n_feat][degree],
+ *   weights[n_feat], bias[1]; nullable), output un-standardisation (y_mu, y_sigma), variance floor.
+ * gpx_wave_i8: for every chunk of Mc rows of Xs[M][D] all E emulators predict from the same device-resident rows -- the (chunk,
+ *   emulator) items run through one two-stream chunk pipeline (see gpx_predict_meanvar_i8) -- and the implausibility epilogue
+ *   writes I[M], PV[M].  mean_out / std_out (both or neither; emulator-major [E][M]) additionally keep every emulator's
+ *   predictions; with NULL they only exist chunk by chunk inside the workspace.
+ * gpx_compact_below: idx[0 .. *count) = the ascending indices m with values[m] < cutoff (deterministic, no atomics); idx must hold
+ *   M entries.  replaces: np.where(I < cutoff) of Wave.find_regions, GPErks/perks/history_matching.py:66-77.
+ * replaces: Wave.compute_impl, GPErks/perks/history_matching.py:43-64. */
+typedef struct gpx_i8_emulator {
+    const double* X; const double* theta; const double* xa; const double* xr; const double* alpha;
+    const signed char* Ls; const double* inv_scale;
+    const int* feat_idx; const double* weights; const double* bias;
+    double y_mu, y_sigma, min_var;
+    int N, Np, kind, nslices, bits, n_feat, degree, reserved;
+} gpx_i8_emulator;
+size_t gpx_wave_i8_workspace_bytes(const gpx_i8_emulator* em, int E, int Mc);
+int gpx_wave_i8(const gpx_i8_emulator* em, int E, int D, const double* Xs, long M, const double* z, const double* v, int maxno,
+                double* I, double* PV, double* mean_out, double* std_out, void* workspace, size_t workspace_bytes, int Mc,
+                void* stream, void* mma_stream);
+size_t gpx_compact_below_workspace_bytes(long M);
+int gpx_compact_below(const double* values, long M, double cutoff, long long* idx, long long* count, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
 /* Microbenchmarks for the roofline denominators: enqueue `iters` dependent-chain-free DMMA.8x8x4
  * (or DFMA) per warp on `blocks` CTAs of 256 threads; returns the FLOP count of the launch. */
 double gpx_peak_dmma(int blocks, int iters, double* sink, void* stream);

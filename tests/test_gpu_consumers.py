@@ -68,6 +68,64 @@ def test_history_matching_matches_reference_loop(dev):
         assert (W.I[-50:] < W.cutoff).all()
 
 
+def test_multi_emulator_wave_equals_per_emulator_loop(dev):
+    """gpx_wave_i8 (all emulators of a wave through ONE two-stream chunk pipeline + the implausibility epilogue, per-emulator
+    predictions kept on chip) against the per-emulator predict_device loop + gpx_implausibility: byte-identical I / PV, with
+    emulators of different train sizes, kernel families and slice modes; kept indices from the device compaction ==
+    np.where(I < cutoff).  Replaces GPErks/perks/history_matching.py:43-77."""
+    from gperks_b200.gp.data.dataset import Dataset
+    from gperks_b200.gp.experiment import GPExperiment
+    from gperks_b200.gp.mean import LinearMean
+    from gperks_b200.kernels import MaternKernel, RBFKernel, ScaleKernel
+    from gperks_b200.likelihoods import GaussianLikelihood
+    from gperks_b200.perks.history_matching import Wave
+    from gperks_b200.train.emulator import GPEmulator
+    rng = np.random.default_rng(4)
+    D = 3
+    ems = []
+    for e, (n, noise) in enumerate(((1100, 1e-2), (1300, 1e-4), (2048, 3e-3), (1024, 1e-2))):
+        X = rng.random((n, D))
+        y = np.sin(3 * X[:, 0] + e) + X[:, 1] * X[:, 2] + 0.05 * rng.standard_normal(n)
+        base = MaternKernel(nu=(2.5, 1.5, 0.5, 2.5)[e], ard_num_dims=D) if e != 2 else RBFKernel(ard_num_dims=D)
+        exp = GPExperiment(Dataset(X, y), GaussianLikelihood(), LinearMean(1 + (e % 2), D), ScaleKernel(base), n_restarts=1, seed=8)
+        em = GPEmulator(exp, "cuda:0")
+        em.model.covar_module.base_kernel.lengthscale = torch.tensor([0.4, 0.7, 1.1], dtype=torch.float64)
+        em.model.covar_module.outputscale = 0.8 + 0.3 * e
+        em.model.likelihood.noise = noise
+        ems.append(em)
+    assert [em.auto_precisions()[0] for em in ems] == ["int8x5w", "int8x6w", "int8x6w", "int8x5w"]
+    Xq = rng.random((70_001, D)) * 1.1 - 0.05
+    z, v = [0.2, 0.5, -0.1, 0.4], [0.05, 0.02, 0.1, 0.03]
+    for maxno in (1, 3):
+        W = Wave(emulator=ems, Itrain=np.array([[0.0, 1.0]] * D), cutoff=2.5, maxno=maxno, mean=z, var=v)
+        assert W._wave_descriptors(dev)[0] is not None                  # the fused path is the one that runs
+        I, PV = W.compute_impl(Xq, block_points=40_000)                 # two blocks: the pinned ring and the chunk tail
+        W2 = Wave(emulator=ems, Itrain=W.Itrain, cutoff=2.5, maxno=maxno, mean=z, var=v)
+        W2._wave_descriptors = lambda dev_: (None, None)                # force the per-emulator loop
+        I2, PV2 = W2.compute_impl(Xq, block_points=40_000)
+        assert np.array_equal(I, I2) and np.array_equal(PV, PV2)
+        W.find_regions(Xq, block_points=40_000)
+        assert np.array_equal(np.asarray(W.nimp_idx), np.where(W.I < W.cutoff)[0])
+        assert np.array_equal(W.I, I) and len(W.nimp_idx) + len(W.imp_idx) == Xq.shape[0]
+        assert np.array_equal(W.reconstruct_tests(), Xq)
+
+
+@pytest.mark.parametrize("M", [0, 1, 255, 4095, 4096, 4097, 1_000_003])
+def test_compact_below_c_abi(dev, M):
+    from gperks_b200 import _native as nv
+    lib = nv.lib()
+    g = torch.Generator(device="cpu").manual_seed(M)
+    vals = torch.rand(max(M, 1), generator=g, dtype=torch.float64).to(dev)
+    for cutoff in (-1.0, 0.3, 2.0):
+        idx = torch.full((max(M, 1),), -7, dtype=torch.int64, device=dev)
+        cnt = torch.full((1,), -1, dtype=torch.int64, device=dev)
+        ws = torch.empty(int(lib.gpx_compact_below_workspace_bytes(M)), dtype=torch.uint8, device=dev)
+        nv.check(lib.gpx_compact_below(nv.ptr(vals), M, cutoff, nv.ptr(idx), nv.ptr(cnt), nv.ptr(ws), ws.numel(), nv.stream_ptr()), "compact")
+        ref = torch.nonzero(vals[:M] < cutoff).reshape(-1)
+        assert int(cnt) == ref.numel()
+        assert torch.equal(idx[: ref.numel()], ref)
+
+
 @pytest.mark.parametrize("E,maxno", [(1, 1), (3, 2), (4, 1), (5, 5), (8, 1), (8, 3), (8, 8), (11, 2), (13, 7)])
 def test_implausibility_c_abi_is_byte_identical_to_numpy(dev, E, maxno):
     """gpx_implausibility for every code path of the kernel (blocks of four emulators + remainder, every list length),

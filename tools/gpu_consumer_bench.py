@@ -81,8 +81,13 @@ torch.cuda.synchronize()
 t0 = time.perf_counter()
 I, PV = W.compute_impl(X4)
 t_hm = time.perf_counter() - t0
+t0 = time.perf_counter()
+W.find_regions(X4)
+t_fr = time.perf_counter() - t0
 out["config4"] = {"emulators": 8, "N": 2048, "D": 6, "M": M, "seconds": t_hm, "points_per_s": M / t_hm,
                   "emulator_evals_per_s": 8 * M / t_hm, "nimp_fraction": float((I < 3.0).mean()),
+                  "find_regions_seconds": t_fr, "fused_wave_path": W._wave_descriptors(torch.device("cuda:0"))[0] is not None,
+                  "precisions": [e.auto_precisions()[0] for e in ems], "overlap": os.environ.get("GPX_I8_OVERLAP", "1"),
                   "reference_python_loop_us_per_point": 8.4}
 print(json.dumps(out["config4"]), flush=True)
 
@@ -103,4 +108,4 @@ out["config3"] = {"N": 4096, "D": 12, "n": 2 ** 19, "evaluations": int(Xd.shape[
                   "ST": np.round(gsa.ST[0], 4).tolist()}
 print(json.dumps(out["config3"]), flush=True)
 (ROOT / "gpurun_out").mkdir(exist_ok=True)
-(ROOT / "gpurun_out" / "consumer_bench.json").write_text(json.dumps(out, indent=1))
+(ROOT / "gpurun_out" / f"{os.environ.get('GPX_TAG', 'r02')}_consumer_bench.json").write_text(json.dumps(out, indent=1))
