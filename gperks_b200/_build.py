@@ -12,7 +12,7 @@ CSRC = PKG / "csrc"
 LIBDIR = PKG / "lib"
 LIB = LIBDIR / "libgpx.so"
 STAMP = LIBDIR / "libgpx.so.sha256"
-SOURCES = ["gpx_api.cu", "gpx_kmat.cu", "gpx_chol.cu", "gpx_predict.cu", "gpx_hm.cu", "gpx_tf32.cu", "gpx_i8.cu"]
+SOURCES = ["gpx_api.cu", "gpx_kmat.cu", "gpx_chol.cu", "gpx_predict.cu", "gpx_hm.cu", "gpx_gsa.cu", "gpx_tf32.cu", "gpx_i8.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

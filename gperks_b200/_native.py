@@ -64,6 +64,11 @@ _SIGS = {
     "gpx_implausibility": (C.c_int, [_P, _P, C.c_long, C.c_int, _P, _P, C.c_int, _P, _P, _P]),
     "gpx_wave_i8_workspace_bytes": (C.c_size_t, [_P, C.c_int, C.c_int]),
     "gpx_wave_i8": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_long, _P, _P, C.c_int, _P, _P, _P, _P, _P, C.c_size_t, C.c_int, _P, _P]),
+    "gpx_predict_mean": (C.c_int, [_P, C.c_long, _P, C.c_int, C.c_int, _P, _P, _P, C.c_int, _P, C.c_int, _P, _P, C.c_int, C.c_int, _P, _P,
+                                   C.c_double, C.c_double, _P, _P]),
+    "gpx_saltelli_chunk_rows": (C.c_int, []),
+    "gpx_saltelli_partial": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_long, C.c_int, C.c_long, C.c_long, C.c_int, C.c_ulonglong, _P, _P]),
+    "gpx_saltelli_reduce": (C.c_int, [_P, C.c_long, C.c_int, C.c_int, _P, _P]),
     "gpx_compact_below_workspace_bytes": (C.c_size_t, [C.c_long]),
     "gpx_compact_below": (C.c_int, [_P, C.c_long, C.c_double, _P, _P, _P, C.c_size_t, _P]),
     "gpx_peak_dmma": (C.c_double, [C.c_int, C.c_int, _P, _P]),

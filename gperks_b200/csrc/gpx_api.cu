@@ -49,6 +49,12 @@ struct I8Emulator;
 size_t wave_i8_workspace_bytes(const I8Emulator*, int, int);
 int wave_i8(const I8Emulator*, int, int, const double*, long, const double*, const double*, int, double*, double*, double*, double*,
             void*, size_t, int, cudaStream_t, cudaStream_t);
+int predict_mean(const double*, long, const double*, int, int, const double*, const double*, const double*, int, const double*, int,
+                 const double*, const int*, int, int, const double*, const double*, double, double, double*, cudaStream_t);
+int saltelli_chunk_rows();
+int saltelli_partial(const double*, const double*, const double*, const double*, const double*, const double*, long, int, long, long,
+                     int, unsigned long long, double*, cudaStream_t);
+int saltelli_reduce(const double*, long, int, int, double*, cudaStream_t);
 size_t compact_below_workspace_bytes(long);
 int compact_below(const double*, long, double, long long*, long long*, void*, size_t, cudaStream_t);
 int predict_meanvar(const double*, long, const double*, int, int, const double*, const double*, const double*, int,
@@ -333,6 +339,36 @@ int gpx_wave_i8(const gpx_i8_emulator* em, int E, int D, const double* Xs, long 
     }
     return wave_i8(reinterpret_cast<const I8Emulator*>(em), E, D, Xs, M, z, v, maxno, I, PV, mean_out, std_out, workspace,
                    workspace_bytes, Mc, ST(stream), ST(mma_stream));
+}
+
+int gpx_predict_mean(const double* Xs, long M, const double* X, int N, int D, const double* theta, const double* xa, const double* xr,
+                     int kind, const double* alpha, int Np, const double* prior_mean, const int* feat_idx, int n_feat, int degree,
+                     const double* weights, const double* bias, double y_mu, double y_sigma, double* out_mean, void* stream) {
+    if (!Xs || !X || !theta || !alpha || !out_mean) return -1;
+    if (M < 0) return -2;
+    if (check_np(N, Np)) return -11;
+    if (D < 1 || D > MAXD) return -5;
+    if ((xa == nullptr) != (xr == nullptr)) return -7;
+    if (!prior_mean && weights && n_feat > 0 && (!feat_idx || degree < 1)) return -14;
+    return predict_mean(Xs, M, X, N, D, theta, xa, xr, kind, alpha, Np, prior_mean, feat_idx, n_feat, degree, weights, bias, y_mu,
+                        y_sigma, out_mean, ST(stream));
+}
+
+int gpx_saltelli_chunk_rows(void) { return saltelli_chunk_rows(); }
+
+int gpx_saltelli_partial(const double* mean_A, const double* mean_B, const double* mean_AB, const double* std_A, const double* std_B,
+                         const double* std_AB, long n, int d, long j_begin, long j_end, int n_draws, unsigned long long seed,
+                         double* partial, void* stream) {
+    if (!mean_A || !mean_B || !mean_AB || !partial) return -1;
+    if (n_draws > 0 && (!std_A || !std_B || !std_AB)) return -4;
+    if (n_draws < 0) return -11;
+    return saltelli_partial(mean_A, mean_B, mean_AB, std_A, std_B, std_AB, n, d, j_begin, j_end, n_draws, seed, partial, ST(stream));
+}
+
+int gpx_saltelli_reduce(const double* partial, long n_chunks, int d, int n_draws, double* sums, void* stream) {
+    if (!partial || !sums) return -1;
+    if (n_chunks < 1 || d < 1 || n_draws < 0) return -2;
+    return saltelli_reduce(partial, n_chunks, d, n_draws, sums, ST(stream));
 }
 
 size_t gpx_compact_below_workspace_bytes(long M) { return compact_below_workspace_bytes(M < 0 ? 0 : M); }

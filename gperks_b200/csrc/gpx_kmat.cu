@@ -302,6 +302,112 @@ static int launch_kmat_cross_i8(const double* Xs, long m_valid, const double* X,
 }
 
 // ------------------------------------------------------------------------------------------------
+// Posterior MEAN only:  mu*_m = m(x*_m) + sum_j k(x*_m, X_j) alpha_j, un-standardised.  One CTA owns 128 test points and
+// walks all train tiles; K* never exists in memory (8 D bytes in, 8 bytes out per point; N (3 D + c) FP64 FLOP per point).
+// Same micro-tile, same fused partial sums (FMA chain over the thread's 8 columns, xor-shuffle tree over the half-warp) and the
+// same order of the per-tile partials and of the prior-mean terms as kmat_cross_kernel + predict_finalize_kernel, so the
+// result is bit-identical to the mean of gpx_predict_meanvar.  Used where the variance is not needed: Sobol' indices of the
+// emulator's posterior mean over 1e7-point Saltelli designs (GPErks/perks/gsa.py:66-88 evaluates the emulator there).
+template <int KIND>
+__global__ void __launch_bounds__(P_THREADS, 2)
+predict_mean_kernel(const double* __restrict__ Xs, long m_valid, const double* __restrict__ X, int N, int D,
+                    const double* __restrict__ theta, const double* __restrict__ xa, const double* __restrict__ xr,
+                    const double* __restrict__ alpha, int nb, const double* __restrict__ prior_mean,
+                    const int* __restrict__ feat_idx, int n_feat, int degree, const double* __restrict__ weights,
+                    const double* __restrict__ bias, double y_mu, double y_sigma, double* __restrict__ out_mean) {
+    const long mb = blockIdx.x;
+    extern __shared__ double sm[];
+    double* sa = sm;                    // test points (rows m)   [D][P_LD]
+    double* sb = sm + D * P_LD;         // train points (cols j)  [D][P_LD]
+    double* sal = sb + D * P_LD;        // alpha tile [128]
+    double* smean = sal + TILE;         // [128]
+    stage_coords(sa, Xs, mb * TILE, m_valid, D, theta, xa, xr);
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const double s = theta[D];
+    if (threadIdx.x < TILE) smean[threadIdx.x] = 0.0;      // running sum over the train tiles, owned by the row's tx == 0 lane
+    for (int jb = 0; jb < nb; ++jb) {
+        __syncthreads();                // previous tile's sb / sal are no longer read (and sa is staged before the first use)
+        stage_coords(sb, X, (long)jb * TILE, N, D, theta, nullptr, nullptr);
+        if (threadIdx.x < TILE) sal[threadIdx.x] = alpha[jb * TILE + threadIdx.x];
+        __syncthreads();
+        double al[8];
+#pragma unroll
+        for (int b = 0; b < 8; ++b) al[b] = sal[tx + 16 * b];
+#pragma unroll 1
+        for (int a = 0; a < 8; ++a) {           // rolled: one row of 8 kernel evaluations keeps the body inside the I-cache
+            const int row = ty + 16 * a;
+            double r2[8];
+#pragma unroll
+            for (int b = 0; b < 8; ++b) r2[b] = 0.0;
+            for (int d = 0; d < D; ++d) {
+                const double xa_ = sa[d * P_LD + row];
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    const double df = xa_ - sb[d * P_LD + tx + 16 * b];
+                    r2[b] = fma(df, df, r2[b]);
+                }
+            }
+            double part = 0.0;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                const long j = (long)jb * TILE + tx + 16 * b;
+                const double v = (j < N) ? kernel_value<KIND>(r2[b], s) : 0.0;
+                part = fma(v, al[b], part);
+            }
+            part += __shfl_xor_sync(0xffffffffu, part, 1);
+            part += __shfl_xor_sync(0xffffffffu, part, 2);
+            part += __shfl_xor_sync(0xffffffffu, part, 4);
+            part += __shfl_xor_sync(0xffffffffu, part, 8);
+            if (tx == 0) smean[row] += part;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < TILE) {
+        const long m = mb * TILE + threadIdx.x;
+        if (m < m_valid) {
+            double mean = 0.0;
+            if (prior_mean != nullptr) {
+                mean = prior_mean[m];
+            } else {
+                if (weights != nullptr) {
+                    for (int p = 0; p < n_feat; ++p) {
+                        double f = 1.0;
+                        for (int q = 0; q < degree; ++q) {
+                            const int d = feat_idx[p * degree + q];
+                            if (d >= 0) {
+                                double x = Xs[m * D + d];
+                                if (xa != nullptr) x = (x - xa[d]) / xr[d];
+                                f *= x;
+                            }
+                        }
+                        mean = fma(weights[p], f, mean);
+                    }
+                }
+                if (bias != nullptr) mean += bias[0];
+            }
+            mean += smean[threadIdx.x];
+            out_mean[m] = y_sigma * mean + y_mu;
+        }
+    }
+}
+
+template <int KIND>
+static int launch_predict_mean(const double* Xs, long M, const double* X, int N, int D, const double* theta, const double* xa,
+                               const double* xr, const double* alpha, int Np, const double* prior_mean, const int* feat_idx,
+                               int n_feat, int degree, const double* weights, const double* bias, double y_mu, double y_sigma,
+                               double* out_mean, cudaStream_t st) {
+    const size_t smem = (size_t(2) * D * P_LD + 2 * TILE) * 8;
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(predict_mean_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const long blocks = (M + TILE - 1) / TILE;
+    predict_mean_kernel<KIND><<<(unsigned)blocks, P_THREADS, smem, st>>>(Xs, M, X, N, D, theta, xa, xr, alpha, Np / TILE, prior_mean,
+                                                                          feat_idx, n_feat, degree, weights, bias, y_mu, y_sigma,
+                                                                          out_mean);
+    GPX_CHECK_LAUNCH();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // TF32-mode cross kernel: K* evaluated in FP32 (coordinates are scaled in FP64, rounded once) and written as the
 // (hi, lo) TF32 operand pair of the 3xTF32 contraction; the posterior-mean partials accumulate in FP64.
 // Relative error of an entry ~3e-7 -- far inside the mode's 1e-3 tolerance -- at ~1/5 of the FP64 builder's cost.
@@ -611,6 +717,15 @@ int kmat_cross_i8(const double* Xs, long m_valid, const double* X, int N, int D,
                   const double* xr, int kind, const double* alpha, int8_t* planes, long plane_rows, int nslices, int bits, int Np,
                   double* mean_part, int Mc, cudaStream_t st) {
 #define C_(KD) launch_kmat_cross_i8<KD>(Xs, m_valid, X, N, D, theta, xa, xr, alpha, planes, plane_rows, nslices, bits, Np, mean_part, Mc, st)
+    GPX_DISPATCH_KIND(kind, C_)
+#undef C_
+}
+
+int predict_mean(const double* Xs, long M, const double* X, int N, int D, const double* theta, const double* xa, const double* xr,
+                 int kind, const double* alpha, int Np, const double* prior_mean, const int* feat_idx, int n_feat, int degree,
+                 const double* weights, const double* bias, double y_mu, double y_sigma, double* out_mean, cudaStream_t st) {
+    if (M <= 0) return 0;
+#define C_(KD) launch_predict_mean<KD>(Xs, M, X, N, D, theta, xa, xr, alpha, Np, prior_mean, feat_idx, n_feat, degree, weights, bias, y_mu, y_sigma, out_mean, st)
     GPX_DISPATCH_KIND(kind, C_)
 #undef C_
 }

@@ -310,6 +310,37 @@ class ExactGPEngine:
                              p(ws), ws_bytes, Mc, nv.stream_ptr())
         return out_mean, out_std
 
+    def predict_mean(self, Xs: torch.Tensor, *, xa: Optional[torch.Tensor] = None, xr: Optional[torch.Tensor] = None,
+                     prior_mean: Optional[torch.Tensor] = None, poly: Optional[PolyMeanSpec] = None, y_mu: float = 0.0,
+                     y_sigma: float = 1.0, out_mean: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Posterior mean only for device-resident points Xs [M, D] (``gpx_predict_mean``: K* is never materialised and the
+        variance contraction -- N^2 FLOP per point -- is skipped); bit-identical to the mean ``predict`` returns."""
+        if not self.factored:
+            raise RuntimeError("predict_mean() before factorize()")
+        if Xs.dim() == 1:
+            Xs = Xs.unsqueeze(-1)
+        Xs = Xs.to(self.device, F64).contiguous()
+        M = Xs.shape[0]
+        if Xs.shape[1] != self.D:
+            raise ValueError(f"expected inputs with {self.D} columns, got {Xs.shape[1]}")
+        if out_mean is None:
+            out_mean = torch.empty(M, dtype=F64, device=self.device)
+        if M == 0:
+            return out_mean
+        p = nv.ptr
+        feat = wts = bias = None
+        n_feat = degree = 0
+        if prior_mean is not None:
+            prior_mean = prior_mean.detach().to(self.device, F64).contiguous()
+        elif poly is not None:
+            feat, wts, bias = poly.feat_idx, poly.weights, poly.bias
+            n_feat, degree = int(feat.shape[0]), int(poly.degree)
+        with torch.cuda.device(self.device):
+            self._launch("gpx_predict_mean", p(Xs), M, p(self.X), self.N, self.D, p(self.theta), p(xa), p(xr), self.kind,
+                         p(self.alpha), self.Np, p(prior_mean), p(feat), n_feat, degree, p(wts), p(bias), float(y_mu),
+                         float(y_sigma), p(out_mean), nv.stream_ptr())
+        return out_mean
+
     def _ensure_split(self) -> None:
         """(hi, lo) TF32 split of L^-1 for the tensor-core variance path; refreshed after every factorisation."""
         if self.has_split:

@@ -69,49 +69,142 @@ class SobolGSA:
         self.ST = np.atleast_2d(indices.total_order)
         self.S1 = np.atleast_2d(indices.first_order)
 
-    def estimate_Sobol_indices_with_emulator_mean(self, emulator, block_points: int = 4_000_000, group=None):
-        """Saltelli-2010 indices of the emulator's posterior mean; predictions and sums stay on the device.
-        With an initialised ``torch.distributed`` process group (one process per GPU, the same emulator and seed on every
-        rank) the design rows are split contiguously over the ranks and only the 8 B/point means are all-gathered; the
-        sums are then formed redundantly on every rank, so the result does not depend on the number of GPUs."""
+    # ---- device pipeline ---------------------------------------------------------------------
+    def _base_design(self) -> np.ndarray:
+        """The 2d-column scrambled Sobol' block scipy's ``sample_A_B`` draws (``qmc.Sobol(d=2d, seed, bits=64).random(n)``), as a
+        C-contiguous [n, 2d] host array, cached per (n, seed).  A = U[:, :d] * scale + loc and B = U[:, d:] * scale + loc are
+        exactly scipy's ``dist.ppf`` values for the uniform marginals this class uses -- formed on the device -- and the AB rows
+        are assembled there too, so the n (d + 2) x d matrix of ``saltelli_design`` never exists on the host."""
+        key = (self.n, self.seed)
+        if getattr(self, "_design_key", None) != key:
+            from scipy.stats import qmc
+            self._design = np.ascontiguousarray(qmc.Sobol(d=2 * self.d, seed=self.seed, bits=64).random(self.n))
+            self._design_key = key
+        return self._design
+
+    def estimate_Sobol_indices_with_emulator_device(self, emulator, n_draws: int = 0, draw_seed: Optional[int] = None,
+                                                    block_rows: int = 65536, group=None):
+        """Saltelli-2010 first-order / total indices with everything after the base Sobol' block on the GPU: A, B and the AB rows
+        are formed on the device, all n (d + 2) design points are predicted there in blocks of ``block_rows`` design rows, and
+        the sums scipy's estimators need are reduced by ``gpx_saltelli_partial`` / ``gpx_saltelli_reduce``; only (n_draws, d)
+        indices come back (``self.S1``, ``self.ST``, like GPErks/perks/gsa.py:66-88).
+
+        ``n_draws = 0``: indices of the posterior MEAN (one row); only the mean is evaluated (``gpx_predict_mean``).
+        ``n_draws > 0``: per-draw indices from MARGINAL posterior-predictive draws, f_k(x) = mean(x) + std(x) z_k(x) with z
+        independent per point (Philox keyed by ``draw_seed``).  The reference draws jointly over all points, which needs the
+        dense n(d+2)-square covariance and is impossible at these sizes; marginal draws keep every point's predictive law but
+        drop the correlation between points, so the spread of the indices over draws is a lower bound of the joint one.
+        With an initialised ``torch.distributed`` group (one process per GPU, same emulator everywhere) rank 0's base block is
+        broadcast, the chunks of design rows are dealt contiguously over the ranks, the per-chunk partial sums are gathered on
+        rank 0 and added in chunk order: bitwise identical for any number of GPUs; every rank receives the indices."""
         import torch.distributed as dist
+        from .. import _native as nv
         from ..parallel import shard_bounds
-        _, _, X = self.saltelli_design()
+        lib = nv.lib()
         n, d = self.n, self.d
         dev = emulator._compute_device()
         sharded = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
         world, rank = (dist.get_world_size(group), dist.get_rank(group)) if sharded else (1, 0)
-        row_lo, row_hi = shard_bounds(X.shape[0], world, rank)
+        F64 = torch.float64
+        JC = int(lib.gpx_saltelli_chunk_rows())
+        n_chunks = (n + JC - 1) // JC
+        c_lo, c_hi = shard_bounds(n_chunks, world, rank)
+        j_lo, j_hi = c_lo * JC, min(n, c_hi * JC)
+        NS, kd = 4 + 3 * d, max(int(n_draws), 1)
+        seed = int(self.seed if draw_seed is None and self.seed is not None else (draw_seed or 0)) & (2 ** 64 - 1)
         with torch.no_grad(), torch.cuda.device(dev):
-            f = torch.empty(X.shape[0], dtype=torch.float64, device=dev)
-            for lo in range(row_lo, row_hi, block_points):
-                hi = min(row_hi, lo + block_points)
-                x_dev = torch.from_numpy(np.ascontiguousarray(X[lo:hi])).pin_memory().to(dev, non_blocking=True)
-                emulator.model.eval()
-                mu, _, linear = emulator.predict_device(x_dev)
+            emulator.model.eval()
+            emulator.model.likelihood.eval()
+            if sharded and rank != 0:
+                U = torch.empty(n, 2 * d, dtype=F64, device=dev)
+            else:
+                U = torch.from_numpy(self._base_design()).to(dev)
+            if sharded:
+                src = dist.get_global_rank(group, 0) if group is not None else 0
+                if dist.get_backend(group) == "nccl":
+                    dist.broadcast(U, src=src, group=group)
+                else:
+                    Uc = U.cpu()
+                    dist.broadcast(Uc, src=src, group=group)
+                    U = Uc.to(dev)
+            loc = torch.as_tensor(np.asarray(self.minmax[:, 0], dtype=np.float64), device=dev)
+            scale = torch.as_tensor(np.asarray(self.minmax[:, 1] - self.minmax[:, 0], dtype=np.float64), device=dev)
+            m_loc = j_hi - j_lo
+            fm = torch.empty(max(m_loc, 1) * (d + 2), dtype=F64, device=dev)            # [A | B | AB] of MY rows
+            fs = torch.empty(max(m_loc, 1) * (d + 2), dtype=F64, device=dev) if n_draws > 0 else None
+            for lo in range(j_lo, j_hi, block_rows):
+                hi = min(j_hi, lo + block_rows)
+                m = hi - lo
+                A = U[lo:hi, :d] * scale + loc                       # uniform.ppf(u) = u * scale + loc, scipy's operation order
+                B = U[lo:hi, d:] * scale + loc
+                AB = A.repeat_interleave(d, dim=0).view(m, d, d)      # row (j, p): A_j with coordinate p from B_j
+                AB.diagonal(dim1=1, dim2=2).copy_(B)
+                X = torch.cat([A, B, AB.view(m * d, d)], 0).contiguous()
+                o = lo - j_lo
+                if n_draws > 0:
+                    mu, sd, linear = emulator.predict_device(X)
+                else:
+                    (mu, linear), sd = emulator.predict_mean_device(X), None
                 if not linear:
                     raise NotImplementedError("device-side GSA needs the (linear) StandardScaler on the outputs")
-                f[lo:hi] = mu
+                for dst, src_t in ((fm, mu), (fs, sd)):
+                    if dst is None:
+                        continue
+                    dst[o:o + m] = src_t[:m]
+                    dst[m_loc + o: m_loc + o + m] = src_t[m:2 * m]
+                    dst[2 * m_loc + o * d: 2 * m_loc + (o + m) * d] = src_t[2 * m:]
+            my_chunks = c_hi - c_lo
+            partial = torch.zeros(max(my_chunks, 1) * kd * NS, dtype=F64, device=dev)
+            if my_chunks > 0:
+                p = nv.ptr
+                mA, mB, mAB = fm[:m_loc], fm[m_loc:2 * m_loc], fm[2 * m_loc:]
+                sA = sB = sAB = None
+                if fs is not None:
+                    sA, sB, sAB = fs[:m_loc], fs[m_loc:2 * m_loc], fs[2 * m_loc:]
+                # the kernel indexes rows globally (the Philox counter is the design row): pass pointers shifted back by j_lo
+                sh = lambda t, w=1: (p(t) - 8 * j_lo * w) if t is not None else None  # noqa: E731
+                nv.check(lib.gpx_saltelli_partial(sh(mA), sh(mB), sh(mAB, d), sh(sA), sh(sB), sh(sAB, d), n, d, j_lo, j_hi,
+                                                  int(n_draws), seed, p(partial), nv.stream_ptr()), "gpx_saltelli_partial")
             if sharded:
-                bounds = [shard_bounds(X.shape[0], world, r) for r in range(world)]
-                width = max(h - l for l, h in bounds)
-                local = torch.zeros(width, dtype=torch.float64, device=dev)
-                local[: row_hi - row_lo] = f[row_lo:row_hi]
-                if dist.get_backend(group) != "nccl":
-                    local = local.cpu()
-                parts = [torch.empty_like(local) for _ in range(world)]
-                dist.all_gather(parts, local, group=group)
-                for (l, h), part in zip(bounds, parts):
-                    f[l:h] = part[: h - l].to(dev)
-            f_A, f_B = f[:n], f[n:2 * n]
-            f_AB = f[2 * n:].reshape(n, d)                       # row j, column p: A_j with coordinate p from B_j
-            mean = torch.cat([f_A, f_B]).mean()
-            f_A, f_B, f_AB = f_A - mean, f_B - mean, f_AB - mean
-            var = torch.cat([f_A, f_B]).var(unbiased=False)
-            S1 = (f_B.unsqueeze(1) * (f_AB - f_A.unsqueeze(1))).mean(0) / var
-            ST = 0.5 * ((f_A.unsqueeze(1) - f_AB) ** 2).mean(0) / var
-            self.S1 = S1.cpu().numpy().reshape(1, -1)
-            self.ST = ST.cpu().numpy().reshape(1, -1)
+                counts = [shard_bounds(n_chunks, world, r) for r in range(world)]
+                width = max(max(h - l for l, h in counts), 1) * kd * NS
+                block = torch.zeros(width, dtype=F64, device=dev)
+                block[: my_chunks * kd * NS] = partial[: my_chunks * kd * NS]
+                gloo = dist.get_backend(group) != "nccl"
+                if gloo:
+                    block = block.cpu()
+                parts = [torch.empty_like(block) for _ in range(world)] if rank == 0 else None
+                gdst = dist.get_global_rank(group, 0) if group is not None else 0
+                dist.gather(block, parts, dst=gdst, group=group)
+                if rank == 0:
+                    partial = torch.cat([pt[: (h - l) * kd * NS] for (l, h), pt in zip(counts, parts)]).to(dev)
+            out = torch.empty(2, kd, d, dtype=F64, device=dev)
+            if rank == 0:
+                sums = torch.empty(kd * NS, dtype=F64, device=dev)
+                nv.check(lib.gpx_saltelli_reduce(nv.ptr(partial), n_chunks, d, int(n_draws), nv.ptr(sums), nv.stream_ptr()),
+                         "gpx_saltelli_reduce")
+                sums = sums.view(kd, NS)
+                mean = (sums[:, 0] + sums[:, 1]) / (2 * n)
+                var = (sums[:, 2] + sums[:, 3]) / (2 * n) - mean * mean
+                per_p = sums[:, 4:].reshape(kd, d, 3)
+                out[0] = (per_p[:, :, 0] - mean.unsqueeze(1) * per_p[:, :, 1]) / n / var.unsqueeze(1)      # first order
+                out[1] = 0.5 * per_p[:, :, 2] / n / var.unsqueeze(1)                                        # total order
+            if sharded:
+                if dist.get_backend(group) == "nccl":
+                    dist.broadcast(out, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+                else:
+                    oc = out.cpu()
+                    dist.broadcast(oc, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+                    out = oc
+            res = out.cpu().numpy()
+        self.S1, self.ST = res[0], res[1]
+
+    def estimate_Sobol_indices_with_emulator_mean(self, emulator, block_points: int = 4_000_000, group=None):
+        """Saltelli-2010 indices of the emulator's posterior mean over a design of any size (n = 2^19 ... 2^20): one row of
+        indices; design rows, predictions and sums all stay on the device (``estimate_Sobol_indices_with_emulator_device`` with
+        ``n_draws = 0``)."""
+        rows = max(1024, int(block_points) // (self.d + 2))
+        self.estimate_Sobol_indices_with_emulator_device(emulator, n_draws=0, block_rows=rows, group=group)
 
     def correct_Sobol_indices(self, threshold: float = DEFAULT_GSA_THRESHOLD):
         for S in (self.ST, self.S1):

@@ -479,6 +479,26 @@ class GPEmulator(Trainable):
                 precision=precision, tf32_kchunk=tf32_kchunk, out_mean=out_mean, out_std=out_std)
         return mean_d, std_d, linear_out
 
+    def predict_mean_device(self, x_dev: torch.Tensor, out_mean: Optional[torch.Tensor] = None):
+        """Posterior mean only of raw device-resident inputs ``x_dev`` [M, D] -> (mean device tensor, linear_out): the variance
+        contraction is skipped (``gpx_predict_mean``), the values equal ``predict_device``'s mean bit for bit."""
+        cdev = self._compute_device()
+        scx, scy = self.scaled_data.scx, self.scaled_data.scy
+        with torch.no_grad(), torch.cuda.device(cdev):
+            eng = self.model._factorized_engine()
+            xa = torch.as_tensor(numpy.asarray(scx.a, dtype=numpy.float64).reshape(-1), device=cdev)
+            xr = torch.as_tensor((numpy.asarray(scx.b, dtype=numpy.float64)
+                                  - numpy.asarray(scx.a, dtype=numpy.float64)).reshape(-1), device=cdev)
+            poly = self._poly_spec(cdev)
+            prior = None
+            if poly is None:
+                prior = self.model.mean_module((x_dev - xa) / xr).to(cdev, F64)
+            linear_out = type(scy).__name__ == "StandardScaler"
+            mean_d = eng.predict_mean(x_dev, xa=xa, xr=xr, prior_mean=prior, poly=poly,
+                                      y_mu=float(scy.mu) if linear_out else 0.0, y_sigma=float(scy.sigma) if linear_out else 1.0,
+                                      out_mean=out_mean)
+        return mean_d, linear_out
+
     def predict(self, X_new, with_covar: bool = False, precision: str = "auto", tf32_kchunk: int = 32):
         """(y_mean, y_std[, y_covar]) as numpy float64 -- GPErks/train/emulator.py:348-383.
 

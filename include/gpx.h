@@ -220,6 +220,28 @@ size_t gpx_compact_below_workspace_bytes(long M);
 int gpx_compact_below(const double* values, long M, double cutoff, long long* idx, long long* count, void* workspace,
                       size_t workspace_bytes, void* stream);
 
+/* ---- Saltelli / Sobol' GSA on the device ----------------------------------------------------------
+ * gpx_predict_mean: posterior mean only (K* never materialised; bit-identical to the mean of gpx_predict_meanvar), for the
+ *   indices of the emulator's posterior mean over Saltelli designs of 1e7 points.
+ * gpx_saltelli_partial / gpx_saltelli_reduce: with mean (and std) of every design point resident -- layout A[n], B[n],
+ *   AB[n][d] (row j = A_j with coordinate p taken from B_j) -- the sums scipy.stats.sobol_indices needs, per draw k:
+ *   sums[k][0..4) = sum f_A, sum f_B, sum f_A^2, sum f_B^2;  sums[k][4 + 3p ..) = sum f_B D_p, sum D_p, sum D_p^2, D_p = f_AB^(p) - f_A,
+ *   where f = mean + std * z, z ~ N(0,1) independent per point and draw (Philox4x32-10 keyed by seed; n_draws = 0: the noise-free
+ *   sums of the mean, one row).  Rows are processed in chunks of gpx_saltelli_chunk_rows(); `partial` holds one [draws][4 + 3d]
+ *   block per chunk of [j_begin, j_end) (j_begin chunk-aligned) and gpx_saltelli_reduce adds the blocks in chunk order, so the
+ *   result does not depend on how chunks are dealt over GPUs.  The arrays are indexed by the GLOBAL design row (it is also the
+ *   Philox counter): a rank that holds only rows [j_begin, j_end) passes base pointers shifted back by j_begin rows.
+ * replaces: emulator.sample + the per-draw scipy estimators of SobolGSA.estimate_Sobol_indices_with_emulator,
+ *   GPErks/perks/gsa.py:66-88. */
+int gpx_predict_mean(const double* Xs, long M, const double* X, int N, int D, const double* theta, const double* xa, const double* xr,
+                     int kind, const double* alpha, int Np, const double* prior_mean, const int* feat_idx, int n_feat, int degree,
+                     const double* weights, const double* bias, double y_mu, double y_sigma, double* out_mean, void* stream);
+int gpx_saltelli_chunk_rows(void);
+int gpx_saltelli_partial(const double* mean_A, const double* mean_B, const double* mean_AB, const double* std_A, const double* std_B,
+                         const double* std_AB, long n, int d, long j_begin, long j_end, int n_draws, unsigned long long seed,
+                         double* partial, void* stream);
+int gpx_saltelli_reduce(const double* partial, long n_chunks, int d, int n_draws, double* sums, void* stream);
+
 /* Microbenchmarks for the roofline denominators: enqueue `iters` dependent-chain-free DMMA.8x8x4
  * (or DFMA) per warp on `blocks` CTAs of 256 threads; returns the FLOP count of the launch. */
 double gpx_peak_dmma(int blocks, int iters, double* sink, void* stream);

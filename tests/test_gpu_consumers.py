@@ -188,6 +188,77 @@ def test_sobol_gsa_against_analytic_indices(dev):
     assert set(small.df.columns) == {"Parameter", "Index", "Value"}
 
 
+def test_sobol_gsa_marginal_draws_on_device(dev):
+    """Per-draw indices (n_draws, d) from marginal posterior-predictive draws, reduced on the device (gpx_saltelli_partial):
+    deterministic for a seed, different across seeds, centred on the indices of the posterior mean, every row a valid set of
+    indices; and the mean-only predict kernel equals the mean of the full predict bit for bit."""
+    from functools import partial
+    from gperks_b200.perks.gsa import SobolGSA
+    from gperks_b200.utils.test_functions_gsa import SobolGstar
+    d = 3
+    f = partial(SobolGstar, a=[0.0, 1.0, 9.0], delta=[0.2, 0.4, 0.6], alpha=[1.0] * d)
+    em, ds = _fit(f, d, 200, l_bounds=[0.0] * d, u_bounds=[1.0] * d)
+    g0 = SobolGSA(ds, n=2 ** 14, seed=8)
+    g0.estimate_Sobol_indices_with_emulator_device(em, n_draws=0)
+    g = SobolGSA(ds, n=2 ** 14, seed=8)
+    g.estimate_Sobol_indices_with_emulator_device(em, n_draws=200, draw_seed=5, block_rows=5000)    # ragged blocks, 4 chunks of 4096 rows
+    assert g.S1.shape == (200, d) and g.ST.shape == (200, d)
+    S1a, STa = g.S1.copy(), g.ST.copy()
+    g.estimate_Sobol_indices_with_emulator_device(em, n_draws=200, draw_seed=5, block_rows=16384)
+    assert np.array_equal(S1a, g.S1) and np.array_equal(STa, g.ST)              # blocks never change a bit, draws are keyed by (seed, row, draw)
+    g.estimate_Sobol_indices_with_emulator_device(em, n_draws=200, draw_seed=6)
+    assert not np.array_equal(S1a, g.S1)
+    assert np.all(np.isfinite(S1a)) and np.all(STa > -1e-3) and STa.std(axis=0).max() > 0
+    # marginal noise adds variance to f: indices shrink towards zero by var_f / (var_f + mean noise^2), slightly; centre stays close
+    np.testing.assert_allclose(np.median(STa, axis=0), g0.ST[0], atol=0.03)
+    np.testing.assert_allclose(np.median(S1a, axis=0), g0.S1[0], atol=0.03)
+    # mean-only kernel == mean of the full predict
+    x = torch.rand(5000, d, dtype=torch.float64, device=dev)
+    m_full, _, _ = em.predict_device(x)
+    m_only, _ = em.predict_mean_device(x)
+    assert torch.equal(m_full, m_only)
+
+
+def test_saltelli_sums_c_abi(dev):
+    """gpx_saltelli_partial / gpx_saltelli_reduce against numpy on known inputs: the noise-free sums exactly (up to summation
+    order), and the Philox normals through their first two moments and their independence across points."""
+    from gperks_b200 import _native as nv
+    lib = nv.lib()
+    n, d = 10_000, 5
+    JC = lib.gpx_saltelli_chunk_rows()
+    rng = np.random.default_rng(0)
+    fA, fB, fAB = rng.standard_normal(n), rng.standard_normal(n), rng.standard_normal((n, d))
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev)  # noqa: E731
+    dA, dB, dAB = t(fA), t(fB), t(fAB)
+    n_chunks = (n + JC - 1) // JC
+    NS = 4 + 3 * d
+    part = torch.zeros(n_chunks * NS, dtype=torch.float64, device=dev)
+    sums = torch.zeros(NS, dtype=torch.float64, device=dev)
+    nv.check(lib.gpx_saltelli_partial(nv.ptr(dA), nv.ptr(dB), nv.ptr(dAB), None, None, None, n, d, 0, n, 0, 1, nv.ptr(part), nv.stream_ptr()), "partial")
+    nv.check(lib.gpx_saltelli_reduce(nv.ptr(part), n_chunks, d, 0, nv.ptr(sums), nv.stream_ptr()), "reduce")
+    D = fAB - fA[:, None]
+    ref = np.concatenate([[fA.sum(), fB.sum(), (fA ** 2).sum(), (fB ** 2).sum()],
+                          np.stack([(fB[:, None] * D).sum(0), D.sum(0), (D ** 2).sum(0)], 1).ravel()])
+    np.testing.assert_allclose(sums.cpu().numpy(), ref, rtol=1e-12, atol=1e-10)
+    # unit normals: mean 0, std 1 everywhere -> sum f_A^2 / n -> 1, sum f_A / n -> 0, sum f_B D_p / n -> 0 (independence), sum D^2 / n -> 2
+    K = 64
+    z0, o1 = torch.zeros(n, dtype=torch.float64, device=dev), torch.ones(n, dtype=torch.float64, device=dev)
+    z0d, o1d = torch.zeros(n, d, dtype=torch.float64, device=dev), torch.ones(n, d, dtype=torch.float64, device=dev)
+    part = torch.zeros(n_chunks * K * NS, dtype=torch.float64, device=dev)
+    sums = torch.zeros(K * NS, dtype=torch.float64, device=dev)
+    nv.check(lib.gpx_saltelli_partial(nv.ptr(z0), nv.ptr(z0), nv.ptr(z0d), nv.ptr(o1), nv.ptr(o1), nv.ptr(o1d), n, d, 0, n, K, 12345,
+                                      nv.ptr(part), nv.stream_ptr()), "partial")
+    nv.check(lib.gpx_saltelli_reduce(nv.ptr(part), n_chunks, d, K, nv.ptr(sums), nv.stream_ptr()), "reduce")
+    S = sums.view(K, NS).cpu().numpy() / n
+    assert abs(S[:, 0].mean()) < 4 / np.sqrt(n * K) and abs(S[:, 1].mean()) < 4 / np.sqrt(n * K)
+    assert abs(S[:, 2].mean() - 1) < 6 * np.sqrt(2 / (n * K)) and abs(S[:, 3].mean() - 1) < 6 * np.sqrt(2 / (n * K))
+    per_p = S[:, 4:].reshape(K, d, 3)
+    assert np.abs(per_p[:, :, 0].mean(0)).max() < 6 * np.sqrt(2 / (n * K))          # f_B independent of f_AB - f_A
+    assert np.abs(per_p[:, :, 2].mean(0) - 2).max() < 6 * np.sqrt(8 / (n * K))      # var(z_AB - z_A) = 2: the two are independent
+    assert np.unique(np.round(S[:, 2], 12)).size == K                               # every draw is a different stream
+    assert lib.gpx_saltelli_partial(nv.ptr(dA), nv.ptr(dB), nv.ptr(dAB), None, None, None, n, d, 100, n, 0, 1, nv.ptr(part), nv.stream_ptr()) < 0
+
+
 def test_inference_and_diagnostics_reproduce_notebook(dev, goldens):
     from test_gpu_parity import _emulator_from_golden
     from gperks_b200.perks.diagnostics import Diagnostics
