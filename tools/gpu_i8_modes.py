@@ -114,6 +114,27 @@ for spec in args.sizes:
                 t["builder_kernel_ms"] = timed(lambda: nv.check(lib.gpx_kmat_cross_i8(
                     nv.ptr(Xt), Mc, nv.ptr(eng.X), N, D, nv.ptr(eng.theta), None, None, 3, nv.ptr(eng.alpha), Kp, Mc, S, bits, eng.Np,
                     nv.ptr(mp), Mc, st), "builder"))
+                # co-residency probe: the tensor-core kernel on a high-priority stream and the K* builder (writing the OTHER plane
+                # buffer) on the current stream, launched together; ~max(mma, builder) when both are resident on every SM
+                Kp1 = ws.data_ptr() + int(lib.gpx_predict_i8_planes_offset(eng.Np, Mc, S, 1))
+                hp = torch.cuda.Stream(priority=-1)
+                cur = torch.cuda.current_stream()
+
+                def both(order):
+                    ev = torch.cuda.Event()
+                    ev.record(cur)
+                    hp.wait_event(ev)
+                    launch_m = lambda: nv.check(lib.gpx_trmm_sumsq_i8(nv.ptr(eng.S_i8), nv.ptr(eng.S_i8_inv_scale), eng.Np, Kp, Mc, S, bits,  # noqa: E731
+                                                                      nv.ptr(eng.theta) + 8 * D, nv.ptr(qp), hp.cuda_stream), "mma")
+                    launch_b = lambda: nv.check(lib.gpx_kmat_cross_i8(nv.ptr(Xt), Mc, nv.ptr(eng.X), N, D, nv.ptr(eng.theta), None, None, 3,  # noqa: E731
+                                                                      nv.ptr(eng.alpha), Kp1, Mc, S, bits, eng.Np, nv.ptr(mp), Mc, st), "builder")
+                    for f in ((launch_m, launch_b) if order == "mb" else (launch_b, launch_m)):
+                        f()
+                    ev2 = torch.cuda.Event()
+                    ev2.record(hp)
+                    cur.wait_event(ev2)
+                t["concurrent_mma_then_builder_ms"] = timed(lambda: both("mb"), reps=10)
+                t["concurrent_builder_then_mma_ms"] = timed(lambda: both("bm"), reps=10)
                 t["clusters"] = int(lib.gpx_i8_clusters())
                 t["sm_mhz_during_mma_kernel"] = LAST_CLOCK[0]
                 t["mma_raw_int8_tops"] = S * (S + 1) / 2 * N * N * Mc / t["mma_kernel_ms"] / 1e9
