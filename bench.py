@@ -497,16 +497,24 @@ def main():
     def mll_once():
         eng.factorize(theta, resid)
         eng.gradients()
+    mll_ms_exact = cuda_time(mll_once, max(1, args.mll_evals), warm=2)      # FP64 inverse (what a prediction needs)
+    eng.approx_inverse_ok = True             # what GPEmulator.train / train_auto run inside their loops: integer-tensor-core inverse
     mll_ms = cuda_time(mll_once, max(1, args.mll_evals), warm=2)
+    loss_train_mode, grad_train_mode = float(eng.loss), eng.grad.clone()
+    eng.approx_inverse_ok = False
     lauum_default = eng.lauum_slices
-    eng.lauum_slices = 0                     # all-FP64 edition (DMMA lauum) beside it
-    mll_ms_fp64 = cuda_time(mll_once, max(1, args.mll_evals), warm=1) if lauum_default else mll_ms
+    eng.lauum_slices = 0                     # all-FP64 edition (DMMA inverse and lauum) beside it
+    mll_ms_fp64 = cuda_time(mll_once, max(1, args.mll_evals), warm=1) if lauum_default else mll_ms_exact
+    loss_fp64, grad_fp64 = float(eng.loss), eng.grad.clone()
     eng.lauum_slices = lauum_default
     eng.factorize(theta, resid)
     mll_grad = {"evals_per_s": 1e3 / mll_ms, "ms_per_eval": mll_ms, "n_train": eng.N, "dim": eng.D,
-                "what": "K_hat build + Cholesky + L^-1 + alpha + -mll + K_hat^-1 + gradient reduce (ExactGPEngine.factorize + gradients)",
+                "what": "K_hat build + Cholesky + L^-1 + alpha + -mll + K_hat^-1 + gradient reduce (ExactGPEngine.factorize + gradients) "
+                        "as GPEmulator.train runs it: FP64 Cholesky, L^-1 merge levels >= 1024 rows and K_hat^-1 on the integer tensor cores",
                 "k_inverse": (f"six 7-bit slices on tcgen05 kind::i8 (gpx_lauum_i8)" if lauum_default else "FP64 DMMA lauum"),
-                "ms_per_eval_all_fp64": mll_ms_fp64,
+                "ms_per_eval_fp64_inverse": mll_ms_exact, "ms_per_eval_all_fp64": mll_ms_fp64,
+                "training_mode_vs_all_fp64": {"loss_rel_diff": abs(loss_train_mode - loss_fp64) / abs(loss_fp64),
+                                              "grad_max_rel_diff": float(((grad_train_mode - grad_fp64).abs() / grad_fp64.abs().max()).max())},
                 "algorithmic_flops_per_eval": float(eng.N) ** 3,
                 "fp64_equiv_tflops": float(eng.N) ** 3 / (mll_ms / 1e3) / 1e12}
 

@@ -24,7 +24,7 @@ size_t predict_tf32_workspace_bytes(int, int);
 int slice_i8_matrix(const double*, int, int, long, int8_t*, long, int, int, int, double*, const double*, cudaStream_t);
 double peak_i8mma(int, int, cudaStream_t);
 size_t trtri_i8_workspace_bytes(int, int);
-int trtri_i8(const double*, double*, const double*, double*, int, void*, size_t, cudaStream_t);
+int trtri_i8(const double*, double*, const double*, double*, int, int, void*, size_t, cudaStream_t);
 size_t lauum_i8_workspace_bytes(int, int);
 int lauum_i8(const double*, const double*, double*, int, int, void*, size_t, cudaStream_t);
 int kmat_cross_i8(const double*, long, const double*, int, int, const double*, const double*, const double*, int, const double*,
@@ -273,11 +273,11 @@ int gpx_trmm_sumsq_i8(const signed char* Ls, const double* inv_scale, int Np, co
 
 size_t gpx_trtri_i8_workspace_bytes(int Np) { return trtri_i8_workspace_bytes(Np, 6); }
 
-int gpx_trtri_i8(const double* L, double* S, const double* DT, double* W, int Np, void* workspace, size_t workspace_bytes,
+int gpx_trtri_i8(const double* L, double* S, const double* DT, double* W, int Np, int bits, void* workspace, size_t workspace_bytes,
                  void* stream) {
     if (!L || !S || !DT || !W || !workspace) return -1;
     if (Np <= 0 || Np % TILE) return -4;
-    return trtri_i8(L, S, DT, W, Np, workspace, workspace_bytes, ST(stream));
+    return trtri_i8(L, S, DT, W, Np, bits, workspace, workspace_bytes, ST(stream));
 }
 
 size_t gpx_lauum_i8_workspace_bytes(int Np, int nslices) { return lauum_i8_workspace_bytes(Np, nslices); }

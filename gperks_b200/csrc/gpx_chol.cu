@@ -1459,26 +1459,27 @@ static int inverse_narrow_tiles() {       // GPX_INV_NARROW=0: 128-row tiles onl
 
 // gpx_i8.cu: one merge level on the integer tensor cores
 int trtri_i8_merge(const double* L, double* Smat, const double* DT, double* W, int Np, int left, int h, int hr, void* workspace,
-                   cudaStream_t st);
+                   int bits, cudaStream_t st);
 size_t trtri_i8_workspace_bytes(int Np, int nslices);
 constexpr int TRTRI_I8_MIN_H = 8;        // merge levels whose segments have >= 1024 rows run as sliced-integer GEMMs
 
-static int trtri_impl(const double* L, double* S, const double* DT, double* W, int Np, void* i8_ws, cudaStream_t st);
+static int trtri_impl(const double* L, double* S, const double* DT, double* W, int Np, void* i8_ws, int i8_bits, cudaStream_t st);
 
 int trtri(const double* L, double* S, const double* DT, double* W, int Np, cudaStream_t st) {
-    return trtri_impl(L, S, DT, W, Np, nullptr, st);
+    return trtri_impl(L, S, DT, W, Np, nullptr, 0, st);
 }
 
 // As trtri; the top merge levels (segments of >= 1024 rows) run on the integer tensor cores from six 7-bit slices per operand
 // (entries of L^-1 then agree with the all-FP64 result to ~1e-11 of their row/column scales).
-int trtri_i8(const double* L, double* S, const double* DT, double* W, int Np, void* workspace, size_t workspace_bytes,
+int trtri_i8(const double* L, double* S, const double* DT, double* W, int Np, int bits, void* workspace, size_t workspace_bytes,
              cudaStream_t st) {
-    if (Np > 32768) return -4;
+    if (bits != 7 && bits != 8) return -6;
+    if (Np > (bits == 8 ? 16384 : 32768)) return -4;
     if (workspace_bytes < trtri_i8_workspace_bytes(Np, 6)) return -7;
-    return trtri_impl(L, S, DT, W, Np, workspace, st);
+    return trtri_impl(L, S, DT, W, Np, workspace, bits, st);
 }
 
-static int trtri_impl(const double* L, double* S, const double* DT, double* W, int Np, void* i8_ws, cudaStream_t st) {
+static int trtri_impl(const double* L, double* S, const double* DT, double* W, int Np, void* i8_ws, int i8_bits, cudaStream_t st) {
     set_gemm_attrs();
     const int nb = Np / TILE;
     const bool tma = use_chol_tma();
@@ -1504,7 +1505,7 @@ static int trtri_impl(const double* L, double* S, const double* DT, double* W, i
                 const int left = 2 * h * q, right = left + h;
                 if (right >= nb) continue;
                 const int hr = (nb - right) < h ? (nb - right) : h;
-                const int rc = trtri_i8_merge(L, S, DT, W, Np, left, h, hr, i8_ws, st);
+                const int rc = trtri_i8_merge(L, S, DT, W, Np, left, h, hr, i8_ws, i8_bits, st);
                 if (rc) return rc;
             }
         } else if (tma && narrow && tiles <= 300) {             // 32-row strips

@@ -657,7 +657,7 @@ struct I8Gemm {
     double sign;
 };
 
-template <int S>
+template <int S, int BITS>
 __global__ void __launch_bounds__(I_THREADS, 1)
 gemm_i8_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmB, int Np,
                const double* __restrict__ sa, const double* __restrict__ sb, double* __restrict__ Cout,
@@ -695,7 +695,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
     }
-    if (tid < I_N) sinv[tid] = sb[brow + tid] * ldexp(1.0, -2 * I_BITS);
+    if (tid < I_N) sinv[tid] = sb[brow + tid] * ldexp(1.0, -2 * BITS);
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();
@@ -759,7 +759,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             uint32_t v[32];
             tmem_ld_32x32b_x32(tmem_d + lane_base + (uint32_t)(gi * I_N + half * 32), v);
             tmem_wait_ld();
-            const double wg = 1.0 / (double)(1ull << (I_BITS * gi));
+            const double wg = 1.0 / (double)(1ull << (BITS * gi));
 #pragma unroll
             for (int j = 0; j < 32; ++j) t[j] = fma((double)(int)v[j], wg, t[j]);
         }
@@ -788,7 +788,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
 // Rows [r0, r0 + gridDim.x) of a row-major FP64 matrix -> int8 slices over the live columns [lo(r), hi(r)):
 //   lo(r) = lo_row ? r : c0,  hi(r) = hi_row ? r + 1 : c1;  the written range is the enclosing 128-aligned one, zero outside
 //   the live part.  DT != null: inside the row's own 128-block the value comes from DT[block][r % 128][c % 128].
-template <int S>
+template <int S, int BITS>
 __global__ void __launch_bounds__(256) slice_i8_rows_kernel(const double* __restrict__ src, long ld, const double* __restrict__ DT,
                                                             int r0, int c0, int c1, int lo_row, int hi_row, int Np,
                                                             int8_t* __restrict__ planes, double* __restrict__ inv_scale) {
@@ -808,11 +808,11 @@ __global__ void __launch_bounds__(256) slice_i8_rows_kernel(const double* __rest
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int w = 1; w < 8; ++w) a = fmax(a, red[w]);
-        s_e = scale_exponent(a);
+        s_e = scale_exponent_b<BITS>(a);
         inv_scale[row] = ldexp(1.0, s_e + 1);
     }
     __syncthreads();
-    const double scale = ldexp(1.0, -(s_e + 1) + I_BITS);
+    const double scale = ldexp(1.0, -(s_e + 1) + (BITS == 7 ? I_BITS : 0));
     const long pitch = (long)Np * Np;
     int8_t* out = planes + (long)row * Np;
     for (int cc = wlo + threadIdx.x * 8; cc < whi; cc += 256 * 8) {
@@ -822,14 +822,24 @@ __global__ void __launch_bounds__(256) slice_i8_rows_kernel(const double* __rest
             const int c = cc + u;
             r[u] = (c >= lo && c < hi) ? ((xd && c >= blo && c < bhi) ? xd[c] : xs[c]) * scale : 0.0;
         }
+        unsigned long long dg[8];
+        if (BITS == 8) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) dg[u] = balanced_digits<S>(r[u]);
+        }
 #pragma unroll
         for (int j = 0; j < S; ++j) {
             uint32_t l32 = 0, h32 = 0;
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                const double q = rint(r[u]);
-                r[u] = (r[u] - q) * 128.0;
-                const uint32_t bb = (uint32_t)(__double2int_rn(q) & 0xff);
+                uint32_t bb;
+                if (BITS == 7) {
+                    const double q = rint(r[u]);
+                    r[u] = (r[u] - q) * 128.0;
+                    bb = (uint32_t)(__double2int_rn(q) & 0xff);
+                } else {
+                    bb = (uint32_t)(dg[u] >> (8 * (S - 1 - j))) & 0xffu;
+                }
                 if (u < 4) l32 |= bb << (8 * u); else h32 |= bb << (8 * (u - 4));
             }
             *reinterpret_cast<uint2*>(out + j * pitch + cc) = make_uint2(l32, h32);
@@ -839,7 +849,7 @@ __global__ void __launch_bounds__(256) slice_i8_rows_kernel(const double* __rest
 
 size_t trtri_i8_workspace_bytes(int Np, int nslices) { return 2 * ((size_t)nslices * Np * Np + (size_t)Np * 8); }
 
-template <int S>
+template <int S, int BITS>
 static int launch_gemm_i8(const int8_t* PA, const int8_t* PB, int Np, const double* sa, const double* sb, double* Cout, double* Cmir,
                           const I8Gemm& g, int n_mi, cudaStream_t st) {
     using C = I8Cfg<S, 64>;
@@ -847,7 +857,7 @@ static int launch_gemm_i8(const int8_t* PA, const int8_t* PB, int Np, const doub
     int dev = 0;
     cudaGetDevice(&dev);
     if (!(dev >= 0 && dev < 64 && attr[dev])) {
-        cudaFuncSetAttribute(gemm_i8_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+        cudaFuncSetAttribute(gemm_i8_kernel<S, BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
         if (dev >= 0 && dev < 64) attr[dev] = true;
     }
     CUtensorMap tmAh, tmB;
@@ -866,7 +876,7 @@ static int launch_gemm_i8(const int8_t* PA, const int8_t* PB, int Np, const doub
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_i8_kernel<S>, tmAh, tmB, Np, sa, sb, Cout, Cmir, g);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_i8_kernel<S, BITS>, tmAh, tmB, Np, sa, sb, Cout, Cmir, g);
     return e == cudaSuccess ? 0 : -1000 - (int)e;
 }
 
@@ -887,17 +897,18 @@ int lauum_i8(const double* Smat, const double* DT, double* W, int Np, int nslice
     const int nbt = Np / I_M;
     const I8Gemm g = {2 * nbt, 0, 0, 0, Np, 1, 0, 0, -1, 0, 1, 1.0};
     if (nslices == 5) {
-        slice_i8_rows_kernel<5><<<Np, 256, 0, st>>>(Smat, Np, DT, 0, 0, Np, 1, 0, Np, planes, inv_scale);
-        return launch_gemm_i8<5>(planes, planes, Np, inv_scale, inv_scale, W, nullptr, g, nbt, st);
+        slice_i8_rows_kernel<5, 7><<<Np, 256, 0, st>>>(Smat, Np, DT, 0, 0, Np, 1, 0, Np, planes, inv_scale);
+        return launch_gemm_i8<5, 7>(planes, planes, Np, inv_scale, inv_scale, W, nullptr, g, nbt, st);
     }
-    slice_i8_rows_kernel<6><<<Np, 256, 0, st>>>(Smat, Np, DT, 0, 0, Np, 1, 0, Np, planes, inv_scale);
-    return launch_gemm_i8<6>(planes, planes, Np, inv_scale, inv_scale, W, nullptr, g, nbt, st);
+    slice_i8_rows_kernel<6, 7><<<Np, 256, 0, st>>>(Smat, Np, DT, 0, 0, Np, 1, 0, Np, planes, inv_scale);
+    return launch_gemm_i8<6, 7>(planes, planes, Np, inv_scale, inv_scale, W, nullptr, g, nbt, st);
 }
 
 // One merge level of the recursive inverse (gpx_chol.cu: trtri) for the pair of segments [left, left+h) | [right, right+hr) (in
 // 128-blocks) on the integer tensor cores:  T = L[right,left] A^-1 (stored transposed in W), X21 = -C^-1 T -> S (+ mirror).
-int trtri_i8_merge(const double* L, double* Smat, const double* DT, double* W, int Np, int left, int h, int hr, void* workspace,
-                   cudaStream_t st) {
+template <int BITS>
+static int trtri_i8_merge_t(const double* L, double* Smat, const double* DT, double* W, int Np, int left, int h, int hr, void* workspace,
+                            cudaStream_t st) {
     constexpr int S = 6;
     const size_t plane_bytes = (size_t)S * Np * Np;
     double* sA = reinterpret_cast<double*>(workspace);
@@ -907,19 +918,26 @@ int trtri_i8_merge(const double* L, double* Smat, const double* DT, double* W, i
     const int right = left + h;
     const int l0 = left * TILE, r0 = right * TILE, r1 = (right + hr) * TILE;
     // step 1: M side = columns of A^-1 as rows (left segment, k from the row to the end of the segment), N side = L[right, left]
-    slice_i8_rows_kernel<S><<<h * TILE, 256, 0, st>>>(Smat, Np, DT, l0, 0, r0, 1, 0, Np, PA, sA);
-    slice_i8_rows_kernel<S><<<hr * TILE, 256, 0, st>>>(L, Np, nullptr, r0, l0, r0, 0, 0, Np, PB, sB);
+    slice_i8_rows_kernel<S, BITS><<<h * TILE, 256, 0, st>>>(Smat, Np, DT, l0, 0, r0, 1, 0, Np, PA, sA);
+    slice_i8_rows_kernel<S, BITS><<<hr * TILE, 256, 0, st>>>(L, Np, nullptr, r0, l0, r0, 0, 0, Np, PB, sB);
     I8Gemm g1 = {2 * hr, l0, r0, l0, r0, 1, l0, r0, -1, 0, 0, 1.0};
-    int rc = launch_gemm_i8<S>(PA, PB, Np, sA, sB, W, nullptr, g1, h, st);
+    int rc = launch_gemm_i8<S, BITS>(PA, PB, Np, sA, sB, W, nullptr, g1, h, st);
     if (rc) return rc;
     // step 2: M side = rows of C^-1 (right segment, k from the segment start to the row), N side = T^T = W[left, right]
-    slice_i8_rows_kernel<S><<<hr * TILE, 256, 0, st>>>(Smat, Np, nullptr, r0, r0, 0, 0, 1, Np, PA, sA);
-    slice_i8_rows_kernel<S><<<h * TILE, 256, 0, st>>>(W, Np, nullptr, l0, r0, r1, 0, 0, Np, PB, sB);
+    slice_i8_rows_kernel<S, BITS><<<hr * TILE, 256, 0, st>>>(Smat, Np, nullptr, r0, r0, 0, 0, 1, Np, PA, sA);
+    slice_i8_rows_kernel<S, BITS><<<h * TILE, 256, 0, st>>>(W, Np, nullptr, l0, r0, r1, 0, 0, Np, PB, sB);
     I8Gemm g2 = {2 * h, r0, l0, r0, r1, 0, r0, l0, l0, r0, 0, -1.0};
-    rc = launch_gemm_i8<S>(PA, PB, Np, sA, sB, Smat, Smat, g2, hr, st);
+    rc = launch_gemm_i8<S, BITS>(PA, PB, Np, sA, sB, Smat, Smat, g2, hr, st);
     if (rc) return rc;
     GPX_CHECK_LAUNCH();
     return 0;
+}
+
+// bits = 8: balanced radix-256 digits (48 bits per operand instead of 42; Np <= 16384 keeps the int32 sums exact)
+int trtri_i8_merge(const double* L, double* Smat, const double* DT, double* W, int Np, int left, int h, int hr, void* workspace,
+                   int bits, cudaStream_t st) {
+    return bits == 8 ? trtri_i8_merge_t<8>(L, Smat, DT, W, Np, left, h, hr, workspace, st)
+                     : trtri_i8_merge_t<7>(L, Smat, DT, W, Np, left, h, hr, workspace, st);
 }
 
 // ---- roofline probe: the rate at which one SM retires kind::i8 MMAs from shared memory that is already resident ----

@@ -102,16 +102,21 @@ class ExactGPEngine:
         # GPX_LAUUM=fp64 forces the latter
         self.lauum_slices = (AUTO_I8_SLICES if (AUTO_I8_MIN_N <= self.N <= AUTO_I8_MAX_N
                                                 and os.environ.get("GPX_LAUUM", "") != "fp64") else 0)
-        # EXPERIMENTAL, opt-in (GPX_TRTRI=i8 or engine.trtri_i8 = True before factorize): the merge levels of the recursive inverse
-        # with segments of >= 1024 rows on the integer tensor cores as well.  L^-1 then carries ~1e-8 of its norm (six slices,
-        # errors compound over the levels) instead of ~1e-13 -- enough for the loss and its gradients, NOT for the predictive
-        # variance at small noise (amplification ~ outputscale / noise), so it is off by default.
+        # The merge levels of the recursive inverse with segments of >= 1024 rows can run on the integer tensor cores as well
+        # (gpx_trtri_i8: six slices of 8 bits for Np <= 16384, of 7 bits above).  L^-1 then carries ~1e-10 (8 bit) / ~1e-8 (7 bit) of
+        # its norm instead of ~1e-13 -- enough for the loss, its gradients and the per-epoch metrics, NOT for predictions at small
+        # noise (amplification ~ outputscale / noise).  So it is used only while ``approx_inverse_ok`` is set -- GPEmulator's
+        # training loops set it around their epochs -- and the first prediction afterwards completes the factors with the FP64
+        # inverse (``ensure_exact_inverse``).  GPX_TRTRI=i8 (or engine.trtri_i8 = True) forces the integer inverse everywhere
+        # (experiments); GPX_TRTRI=fp64 disables it.
         self.trtri_i8 = bool(self.lauum_slices and self.Np >= 2048 and os.environ.get("GPX_TRTRI", "") == "i8")
-        self._trtri_i8_capable = bool(self.lauum_slices and self.Np >= 2048)
+        self._trtri_i8_capable = bool(self.lauum_slices and self.Np >= 2048 and os.environ.get("GPX_TRTRI", "") != "fp64")
+        self.approx_inverse_ok = False       # True inside a training loop: factorize() may use the integer inverse
+        self.inverse_exact = True            # False while S / alpha / out come from the integer inverse
         self._lauum_ws: Optional[torch.Tensor] = None
         if self.lauum_slices:       # one workspace for both, allocated up front: gradients() may run inside a CUDA-graph capture
             nbytes = int(self.lib.gpx_lauum_i8_workspace_bytes(self.Np, self.lauum_slices))
-            if self.trtri_i8:
+            if self._trtri_i8_capable:
                 nbytes = max(nbytes, int(self.lib.gpx_trtri_i8_workspace_bytes(self.Np)))
             self._lauum_ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         self.S_i8: Optional[torch.Tensor] = None      # [slices, Np, Np] int8 planes of L^-1
@@ -156,12 +161,13 @@ class ExactGPEngine:
                     raise NotPSDError(f"Matrix not positive definite after repeatedly adding jitter up to "
                                       f"{jitter:.1e} (first non-positive pivot at {info}).")
             self.jitter_used = jitter
-            if self.trtri_i8 and self._trtri_i8_capable:
+            use_i8 = self._trtri_i8_capable and (self.trtri_i8 or self.approx_inverse_ok)
+            if use_i8:
                 need = int(self.lib.gpx_trtri_i8_workspace_bytes(self.Np))
                 if self._lauum_ws is None or self._lauum_ws.numel() < need:      # switched on after construction
                     self._lauum_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
-                self._launch("gpx_trtri_i8", p(self.K), p(self.S), p(self.DT), p(self.W), self.Np, p(self._lauum_ws),
-                             self._lauum_ws.numel(), st)
+                self._launch("gpx_trtri_i8", p(self.K), p(self.S), p(self.DT), p(self.W), self.Np,
+                             8 if self.Np <= int(self.lib.gpx_i8_max_n(8)) else 7, p(self._lauum_ws), self._lauum_ws.numel(), st)
             else:
                 self._launch("gpx_trtri", p(self.K), p(self.S), p(self.DT), p(self.W), self.Np, st)
             self._launch("gpx_solve_alpha", p(self.S), p(self.DT), self.Np, p(self.r), p(self.u), p(self.alpha), st)
@@ -169,6 +175,23 @@ class ExactGPEngine:
                          p(self.out), st)
         self.factor_key = key
         self._mark_factorized()
+        self.inverse_exact = not (use_i8 and not self.trtri_i8)      # a forced integer inverse (GPX_TRTRI=i8) is never completed
+
+    def ensure_exact_inverse(self) -> None:
+        """Completes factors whose inverse came from the integer tensor cores (training loop) with the FP64 inverse: L is still in
+        ``K``, so only trtri, alpha and the loss are redone (~40 % of a factorisation); every derived cache is dropped."""
+        if self.inverse_exact or not self.factored:
+            return
+        with torch.cuda.device(self.device):
+            st, p = nv.stream_ptr(), nv.ptr
+            # the diagonal blocks of S / DT are potrf's (exact, untouched by either inverse): every merge level is simply redone
+            self._launch("gpx_trtri", p(self.K), p(self.S), p(self.DT), p(self.W), self.Np, st)
+            self._launch("gpx_solve_alpha", p(self.S), p(self.DT), self.Np, p(self.r), p(self.u), p(self.alpha), st)
+            self._launch("gpx_mll_value", p(self.r), p(self.alpha), self.Np, self.N, p(self.logdet_blk), p(self.out), st)
+        self._mark_factorized()
+        self.n_factorizations -= 1           # same factorisation, new version of its derived quantities
+        self.n_inverse_refreshes = getattr(self, "n_inverse_refreshes", 0) + 1
+        self.inverse_exact = True
 
     def _mark_factorized(self, has_kinv: bool = False) -> None:
         """Python-side state after K, S, DT, alpha, out have been (re)computed on the device -- by ``factorize`` or by a replayed
@@ -239,6 +262,8 @@ class ExactGPEngine:
         are already scaled.  Returns (mean, std) device tensors, un-standardised with (y_mu, y_sigma)."""
         if not self.factored:
             raise RuntimeError("predict() before factorize()")
+        if not self.approx_inverse_ok:
+            self.ensure_exact_inverse()
         if Xs.dim() == 1:
             Xs = Xs.unsqueeze(-1)
         Xs = Xs.to(self.device, F64).contiguous()
@@ -317,6 +342,8 @@ class ExactGPEngine:
         variance contraction -- N^2 FLOP per point -- is skipped); bit-identical to the mean ``predict`` returns."""
         if not self.factored:
             raise RuntimeError("predict_mean() before factorize()")
+        if not self.approx_inverse_ok:
+            self.ensure_exact_inverse()
         if Xs.dim() == 1:
             Xs = Xs.unsqueeze(-1)
         Xs = Xs.to(self.device, F64).contiguous()
@@ -422,6 +449,8 @@ class ExactGPEngine:
         K** - (L^-1 K*^T)^T (L^-1 K*^T) [+ noise I], every product on the DMMA/TMA tile engine."""
         if not self.factored:
             raise RuntimeError("predict_covar() before factorize()")
+        if not self.approx_inverse_ok:
+            self.ensure_exact_inverse()
         if Xs.dim() == 1:
             Xs = Xs.unsqueeze(-1)
         Xs = Xs.detach().to(self.device, F64).contiguous()
@@ -451,6 +480,8 @@ class ExactGPEngine:
 
     def linv(self) -> torch.Tensor:
         """Dense lower-triangular L^-1 [N, N] (copy; for the small-M covariance paths and tests)."""
+        if not self.approx_inverse_ok:
+            self.ensure_exact_inverse()
         return torch.tril(self.S[: self.N, : self.N])
 
     def chol(self) -> torch.Tensor:

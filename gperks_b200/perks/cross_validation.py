@@ -122,7 +122,8 @@ class KFoldCrossValidation(Trainable):
         tasks = {(i, r): (opt_spec, early_stopping_criterion, snapshotting_criterion, i, r, next(devices),
                           X[tr], y[tr], X[lo], y[lo])
                  for i, (tr, lo) in enumerate(splits) for r in range(1, n_restarts + 1)}
-        results = execute_task_in_parallel(self._train_split_restart, tasks, self.max_workers)
+        # one worker per device, bound to it: (fold, restart) jobs are pulled by whichever GPU becomes free (argument 5 = device)
+        results = execute_task_in_parallel(self._train_split_restart, tasks, self.max_workers, devices=self.devices, device_arg=5)
         models, stats, scores, idx = {}, {}, {}, {}
         for i, (tr, lo) in enumerate(splits):
             # best restart of the fold, its snapshot and its test scores: same selection as GPEmulator.train

@@ -162,7 +162,8 @@ class GPEmulator(Trainable):
         opt_spec = (optimizer.__class__, dict(optimizer.defaults))
         tasks = {r: (self.experiment, self.init_state, devices[(r - 1) % len(devices)], r, rng_state, opt_spec,
                      early_stopping_criterion, snapshotting_criterion) for r in range(1, n + 1)}
-        results = execute_task_in_parallel(train_restart_job, tasks, max_workers or len(devices))
+        # one worker per device, bound to it (argument 2 = device): restarts are pulled by whichever GPU becomes free
+        results = execute_task_in_parallel(train_restart_job, tasks, max_workers or len(devices), devices=devices, device_arg=2)
         torch.set_rng_state(rng_state)          # (in-process jobs moved it) leave the caller's random stream where the
         for _ in range(n):                      # sequential loop would
             self._draw_restart_init()
@@ -226,6 +227,28 @@ class GPEmulator(Trainable):
         best_epoch: Optional[int] = None
         max_epochs = early_stopping_criterion.max_epochs
         width = len(str(max_epochs))
+        try:
+            # inside the epoch loop the factors may carry the integer-tensor-core inverse (loss, gradients and the per-epoch metrics
+            # tolerate its ~1e-10); the first prediction after the loop completes them in FP64 (ExactGPEngine.ensure_exact_inverse)
+            self._set_approx_inverse(True)
+            best_epoch = self._epoch_loop(X_train, y_train, optimizer, X_val, y_val, early_stopping_criterion,
+                                          snapshotting_criterion, stats, max_epochs, width)
+        finally:
+            self._set_approx_inverse(False)
+
+        stats.best_epoch = best_epoch
+        stats.save_to_file(posix_path(snapshotting_criterion.snapshot_dir.format(restart=self.restart_idx),
+                                      "train_stats.json"))
+        snapshotting_criterion.keep_snapshots_until(self.restart_idx, best_epoch)
+        return stats, best_epoch
+
+    def _set_approx_inverse(self, flag: bool) -> None:
+        with torch.cuda.device(self._compute_device()):
+            self.model._get_engine().approx_inverse_ok = bool(flag)
+
+    def _epoch_loop(self, X_train, y_train, optimizer, X_val, y_val, early_stopping_criterion, snapshotting_criterion, stats,
+                    max_epochs, width):
+        best_epoch: Optional[int] = None
         while not early_stopping_criterion.is_verified:
             stats.current_epoch += 1
             train_loss = self._train_step(X_train, y_train, optimizer)
@@ -253,12 +276,7 @@ class GPEmulator(Trainable):
             if early_stopping_criterion.is_verified:
                 snapshotting_criterion.model = best_model
                 snapshotting_criterion.save(self.restart_idx, best_epoch)
-
-        stats.best_epoch = best_epoch
-        stats.save_to_file(posix_path(snapshotting_criterion.snapshot_dir.format(restart=self.restart_idx),
-                                      "train_stats.json"))
-        snapshotting_criterion.keep_snapshots_until(self.restart_idx, best_epoch)
-        return stats, best_epoch
+        return best_epoch
 
     def _train_step(self, X_train, y_train, optimizer) -> float:
         self.model.train()
@@ -323,7 +341,11 @@ class GPEmulator(Trainable):
         rejected = [False]
         x0 = numpy.concatenate([p.detach().reshape(-1).cpu().numpy() for p in params]).astype(numpy.float64)
         with torch.cuda.device(cdev):
-            res = minimize(closure, x0, jac=True, method="L-BFGS-B", options={"maxiter": maxiter})
+            try:
+                self._set_approx_inverse(True)
+                res = minimize(closure, x0, jac=True, method="L-BFGS-B", options={"maxiter": maxiter})
+            finally:
+                self._set_approx_inverse(False)
             if not numpy.all(numpy.isfinite(res.x)) or closure(res.x)[0] >= 1e10 or rejected[0]:
                 set_flat(x0)
                 raise NotPSDError("train_auto: L-BFGS-B stopped on a point whose kernel matrix is not positive definite; "

@@ -170,9 +170,10 @@ int gpx_trmm_sumsq_i8(const signed char* Ls, const double* inv_scale, int Np, co
  * FLOPs at Np = 8192) on the integer tensor cores: per level and segment pair the four operands (L[right,left], the columns of
  * A^-1, the rows of C^-1, T^T) are sliced with per-row scales into the workspace and the two products run on a kind::i8 NT GEMM
  * with a store epilogue (negate, transposed mirror).  Entries of L^-1 agree with gpx_trtri to ~1e-11 of their row/column scale.
- * Np <= 32768.  replaces: the same call sites as gpx_trtri. */
+ * bits = 7: Np <= 32768; bits = 8 (balanced radix-256 digits, 48 bits per operand, ~64 x finer): Np <= 16384.
+ * replaces: the same call sites as gpx_trtri. */
 size_t gpx_trtri_i8_workspace_bytes(int Np);
-int gpx_trtri_i8(const double* L, double* S, const double* DT, double* W, int Np, void* workspace, size_t workspace_bytes,
+int gpx_trtri_i8(const double* L, double* S, const double* DT, double* W, int Np, int bits, void* workspace, size_t workspace_bytes,
                  void* stream);
 size_t gpx_lauum_i8_workspace_bytes(int Np, int nslices);
 int gpx_lauum_i8(const double* S, const double* DT, double* Kinv, int Np, int nslices, void* workspace, size_t workspace_bytes,

@@ -710,6 +710,74 @@ def test_int8_trtri_opt_in_accuracy(dev, N):
     np.testing.assert_allclose(s8.cpu().numpy(), s64.cpu().numpy(), rtol=1e-4)
 
 
+@pytest.mark.parametrize("N", [2048, 4300])
+def test_training_mode_inverse_is_completed_before_predictions(dev, N):
+    """Inside a training loop (``approx_inverse_ok``) the merge levels of L^-1 run on the integer tensor cores (six 8-bit slices):
+    loss and gradients stay within 1e-9 / 1e-7 of the all-FP64 evaluation, and the first prediction after the loop completes the
+    factors with the FP64 inverse -- bit for bit what a fresh FP64 factorisation gives."""
+    X, y, Xs, ls, s, w, b = _problem(N, 6, 400, seed=N)
+    eng = _engine(dev, X, y, O.KIND_MATERN52, ls, s, 1e-2, w, b)
+    assert eng.inverse_exact and eng._trtri_i8_capable
+    S64, alpha64, loss64 = eng.S.clone(), eng.alpha.clone(), float(eng.loss)
+    g64 = eng.gradients().clone()
+    m64, s64 = eng.predict(Xs.to(dev), precision="fp64")
+    eng.approx_inverse_ok = True
+    eng.factorize(eng.theta_in.clone(), eng.r[:N].clone())
+    assert not eng.inverse_exact
+    g8 = eng.gradients().clone()
+    blk = torch.arange(eng.Np, device=dev) // 128
+    offdiag = blk.view(-1, 1) != blk.view(1, -1)
+    err = float(((eng.S - S64).abs() * offdiag).max() / S64.abs().max())
+    assert 0 < err < 2e-9, err                                                   # 48-bit operands: ~64 x finer than the 7-bit edition
+    assert abs(float(eng.loss) - loss64) <= 1e-9 * abs(loss64)
+    np.testing.assert_allclose(g8.cpu().numpy(), g64.cpu().numpy(), rtol=1e-7, atol=1e-9 * float(g64.abs().max()))
+    m8, s8 = eng.predict(Xs.to(dev), precision="fp64")                           # allowed inside the loop: the per-epoch metrics
+    assert not eng.inverse_exact
+    np.testing.assert_allclose(s8.cpu().numpy(), s64.cpu().numpy(), rtol=1e-6)
+    np.testing.assert_allclose(m8.cpu().numpy(), m64.cpu().numpy(), rtol=0, atol=1e-7 * float(m64.abs().max()))
+    eng.approx_inverse_ok = False                                                # the loop is over
+    m2, s2 = eng.predict(Xs.to(dev), precision="fp64")
+    assert eng.inverse_exact and torch.equal(eng.S, S64) and torch.equal(eng.alpha, alpha64) and float(eng.loss) == loss64
+    assert torch.equal(m2, m64) and torch.equal(s2, s64)
+    g2 = eng.gradients()
+    assert torch.equal(g2, g64)
+
+
+def test_emulator_training_leaves_exact_factors_for_predict(dev, tmp_path):
+    """GPEmulator.train at a size where the loop uses the integer inverse: predictions after training equal those of a fresh
+    emulator loaded with the trained state, bit for bit."""
+    from gperks_b200.gp.data.dataset import Dataset
+    from gperks_b200.gp.experiment import GPExperiment
+    from gperks_b200.gp.mean import LinearMean
+    from gperks_b200.kernels import MaternKernel, ScaleKernel
+    from gperks_b200.likelihoods import GaussianLikelihood
+    from gperks_b200.train.early_stop import NoEarlyStoppingCriterion
+    from gperks_b200.train.emulator import GPEmulator
+    from gperks_b200.train.snapshot import NeverSaveSnapshottingCriterion
+    rng = np.random.default_rng(7)
+    N, D = 2100, 3
+    X = rng.random((N, D))
+    y = np.sin(4 * X[:, 0]) + X[:, 1] * X[:, 2] + 0.05 * rng.standard_normal(N)
+
+    def make():
+        exp = GPExperiment(Dataset(X, y), GaussianLikelihood(), LinearMean(1, D), ScaleKernel(MaternKernel(nu=2.5, ard_num_dims=D)),
+                           n_restarts=1, seed=8)
+        return GPEmulator(exp, "cuda:0")
+    em = make()
+    snap = NeverSaveSnapshottingCriterion(str(tmp_path / "restart_{restart}"), "epoch_{epoch}.pth")
+    best_state, stats = em.train(torch.optim.Adam(em.model.parameters(), lr=0.1), NoEarlyStoppingCriterion(6), snap)
+    assert stats.train_loss[-1] < stats.train_loss[0]
+    eng = em.model._get_engine()
+    assert eng._trtri_i8_capable and not eng.approx_inverse_ok
+    Xq = rng.random((3000, D))
+    m1, s1 = em.predict(Xq)
+    assert eng.inverse_exact
+    em2 = make()
+    em2.model.load_state_dict(best_state)
+    m2, s2 = em2.predict(Xq)
+    assert np.array_equal(m1, m2) and np.array_equal(s1, s2)
+
+
 def test_emulator_auto_precision(dev):
     """precision="auto" (the default of GPEmulator.predict) resolves from host-side values only and stays inside 1e-6."""
     from gperks_b200.gp.data.dataset import Dataset
