@@ -661,11 +661,12 @@ def main():
         Kp_ptr = ws8.data_ptr() + int(lib.gpx_predict_i8_planes_offset(eng.Np, Mc, S_, 0))
         nt8 = int(lib.gpx_i8_row_tiles(eng.Np))
         qp8 = torch.empty(nt8 * Mc, dtype=torch.float64, device=dev)
+        sched8 = torch.zeros(2, dtype=torch.int32, device=dev)
         mp8 = torch.empty(eng.nb * Mc, dtype=torch.float64, device=dev)
         n_rep = 20
         with ClockSampler(local_rank) as kclk:
             tk = cuda_time(lambda: nv.check(lib.gpx_trmm_sumsq_i8(nv.ptr(eng.S_i8), nv.ptr(eng.S_i8_inv_scale), eng.Np, Kp_ptr, Mc, S_, bits_,
-                                                                 nv.ptr(eng.theta) + 8 * DIM, nv.ptr(qp8), st), "i8 trmm"), n_rep, warm=10)
+                                                                 nv.ptr(eng.theta) + 8 * DIM, nv.ptr(qp8), nv.ptr(sched8), st), "i8 trmm"), n_rep, warm=10)
         tb = cuda_time(lambda: nv.check(lib.gpx_kmat_cross_i8(nv.ptr(x_dev), Mc, nv.ptr(eng.X), eng.N, eng.D, nv.ptr(eng.theta), nv.ptr(xa),
                                                              nv.ptr(xr), eng.kind, nv.ptr(eng.alpha), Kp_ptr, Mc, S_, bits_, eng.Np,
                                                              nv.ptr(mp8), Mc, st), "i8 builder"), 5)

@@ -51,7 +51,7 @@ _SIGS = {
     "gpx_i8_clusters": (C.c_int, []),
     "gpx_kmat_cross_i8": (C.c_int, [_P, C.c_long, _P, C.c_int, C.c_int, _P, _P, _P, C.c_int, _P, _P, C.c_long, C.c_int, C.c_int,
                                     C.c_int, _P, C.c_int, _P]),
-    "gpx_trmm_sumsq_i8": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "gpx_trmm_sumsq_i8": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
     "gpx_trtri_i8_workspace_bytes": (C.c_size_t, [C.c_int]),
     "gpx_trtri_i8": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P, C.c_size_t, _P]),
     "gpx_lauum_i8_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),

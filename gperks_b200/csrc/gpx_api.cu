@@ -29,7 +29,7 @@ size_t lauum_i8_workspace_bytes(int, int);
 int lauum_i8(const double*, const double*, double*, int, int, void*, size_t, cudaStream_t);
 int kmat_cross_i8(const double*, long, const double*, int, int, const double*, const double*, const double*, int, const double*,
                   int8_t*, long, int, int, int, double*, int, cudaStream_t);
-int trmm_sumsq_i8(const int8_t*, const double*, int, const int8_t*, int, int, int, const double*, double*, cudaStream_t);
+int trmm_sumsq_i8(const int8_t*, const double*, int, const int8_t*, int, int, int, const double*, double*, int*, cudaStream_t);
 int i8_row_tiles(int);
 int i8_max_np(int);
 int i8_clusters();
@@ -262,13 +262,13 @@ int gpx_kmat_cross_i8(const double* Xs, long m_valid, const double* X, int N, in
 }
 
 int gpx_trmm_sumsq_i8(const signed char* Ls, const double* inv_scale, int Np, const signed char* Kp, int Mc, int nslices,
-                      int bits, const double* amax_ptr, double* qpart, void* stream) {
+                      int bits, const double* amax_ptr, double* qpart, int* sched, void* stream) {
     if (!Ls || !inv_scale || !Kp || !amax_ptr || !qpart) return -1;
     if (Np % TILE || Mc % TILE || Np <= 0 || Mc <= 0) return -3;
     if (nslices < 5 || nslices > 6) return -6;
     if (bits != 7 && bits != 8) return -7;
     return trmm_sumsq_i8(reinterpret_cast<const int8_t*>(Ls), inv_scale, Np, reinterpret_cast<const int8_t*>(Kp), Mc,
-                         nslices, bits, amax_ptr, qpart, ST(stream));
+                         nslices, bits, amax_ptr, qpart, sched, ST(stream));
 }
 
 size_t gpx_trtri_i8_workspace_bytes(int Np) { return trtri_i8_workspace_bytes(Np, 6); }

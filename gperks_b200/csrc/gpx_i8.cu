@@ -47,6 +47,7 @@ constexpr int I_THREADS = 320;
 constexpr int I_BAND = 8;       // m tiles that share L^-1 tiles through L2
 constexpr int I_TMEM_COLS = 512;
 constexpr int I_SMAX = 6;
+constexpr int I_RING = 8;       // work-item slots of the dynamic scheduler (no role is ever 8 items behind the scheduler)
 
 template <int S, int BKB>
 struct I8Cfg {
@@ -54,8 +55,9 @@ struct I8Cfg {
     static constexpr int A_BYTES = I_M * BKB;
     static constexpr int B_BYTES = I_N * BKB;
     static constexpr int STAGE_BYTES = S * (A_BYTES + B_BYTES);
-    // tiles | full[STAGES] empty[STAGES] acc_full acc_empty | tmem slot | inverse scales [64] | partial sums [2][128]
-    static constexpr size_t SMEM_BYTES = 1024 + size_t(STAGES) * STAGE_BYTES + (2 * STAGES + 3) * 8 + I_N * 8 + 2 * I_M * 8;
+    // tiles | full[STAGES] empty[STAGES] acc_full acc_empty | tmem slot | inverse scales [64] | partial sums [2][128] |
+    // item_full[I_RING] | item ring [I_RING]
+    static constexpr size_t SMEM_BYTES = 1024 + size_t(STAGES) * STAGE_BYTES + (2 * STAGES + 3) * 8 + I_N * 8 + 2 * I_M * 8 + I_RING * 12 + 32;
 };
 
 // power-of-two scale that brings |x| <= amax into [-1/2, 1/2]:  returns e with amax < 2^e, scale = 2^-(e+1)
@@ -332,11 +334,19 @@ trmm_sumsq_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 // either producer multicasts into it), TMEM acc_full/acc_empty (MMA <-> 8 epilogue warps).
 // Epilogue: diagonals are combined 16 columns at a time (registers: the kernel must leave room for a K* builder CTA of the
 // next chunk on the same SM), int32 -> FP64 by the 2^52 trick (one LOP + one DADD instead of I2F.F64).
+// Work distribution: sched != null -> items are handed out IN ORDER from an atomic counter (sched[0]); the producer thread of the
+// cluster's first CTA fetches the next item and publishes it into an 8-slot ring in BOTH CTAs' shared memory (st.shared::cluster
+// + mbarrier.arrive.release.cluster; every role waits on its own CTA's slot barrier).  Ordered hand-out keeps the clusters that are
+// resident at any time inside one band of point tiles whatever their items weigh (the static stride let them drift over two
+// bands: 24 GB of DRAM reads per launch instead of ~10, profiles/r02_ncu_i8p.txt), and balances the load exactly.  The last
+// cluster to finish resets the counters (sched[1] counts finished clusters), so the two ints only need zeroing once.
+// sched == null: static stride (item = cluster + t * clusters).
 template <int S, int BITS>
 __global__ void __launch_bounds__(I_THREADS, 2)      // "2" caps the kernel at 96 registers per thread: 30 K registers, the other half of the file is the builder's
 trmm_sumsq_i8p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmB, int Np, int Mc,
                       const double* __restrict__ inv_scale, const double* __restrict__ amax_ptr, double* __restrict__ qpart,
-                      const int probe) {      // probe != 0 (GPX_I8_PROBE=nofill, timing experiments only): the ring is filled once, never refilled
+                      const int probe,        // probe != 0 (GPX_I8_PROBE=nofill, timing experiments only): the ring is filled once, never refilled
+                      int* __restrict__ sched) {
     using C = I8Cfg<S, 64>;
     constexpr int BKB = 64;
     extern __shared__ unsigned char smem_raw[];
@@ -345,8 +355,11 @@ trmm_sumsq_i8p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 2);
     double* sinv = reinterpret_cast<double*>(bars + 2 * C::STAGES + 3);      // [64]
     double* red = sinv + I_N;                                                 // [2][128]
+    uint64_t* item_bars = reinterpret_cast<uint64_t*>(red + 2 * I_M);         // [I_RING]
+    volatile int* item_ring = reinterpret_cast<volatile int*>(item_bars + I_RING);     // [I_RING]
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + C::STAGES);
     const uint32_t acc_full = smem_u32(bars + 2 * C::STAGES), acc_empty = smem_u32(bars + 2 * C::STAGES + 1);
+    const uint32_t item_full0 = smem_u32(item_bars), item_ring0 = smem_u32(const_cast<int*>(item_ring));
     const uint32_t tile0 = smem_u32(base);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t crank = cluster_ctarank();
@@ -354,6 +367,7 @@ trmm_sumsq_i8p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
     const int n_items = n_mb * n_it;
     const int cid = (int)(blockIdx.x >> 1), n_clusters = (int)(gridDim.x >> 1);
     const int per_band = I_BAND * n_it;
+    const bool dynamic = sched != nullptr;
 
     if (tid == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
@@ -362,6 +376,7 @@ trmm_sumsq_i8p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
         }
         mbar_init(acc_full, 1);
         mbar_init(acc_empty, 8);
+        for (int r = 0; r < I_RING; ++r) mbar_init(item_full0 + 8 * r, 1);
         mbar_fence_init();
     }
     if (warp == 1) {
@@ -376,6 +391,27 @@ trmm_sumsq_i8p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
     const uint32_t tmem_d = *tmem_slot;
 
     // work item id -> (pair of row tiles itp, point tile mb); both CTAs of the cluster take the same items
+    // item of iteration t of this cluster (-1: none left); every role of both CTAs sees the same sequence
+    auto item_at = [&](uint32_t t) -> int {
+        if (!dynamic) {
+            const long id = (long)cid + (long)t * n_clusters;
+            return id < n_items ? (int)id : -1;
+        }
+        const uint32_t slot = t % I_RING;
+        mbar_wait_cluster(item_full0 + 8 * slot, (t / I_RING) & 1);
+        return item_ring[slot];
+    };
+    // the scheduler (producer thread of the cluster's first CTA) fetches iteration t's item and publishes it to both CTAs
+    auto publish_item = [&](uint32_t t) {
+        int id = atomicAdd(sched, 1);
+        if (id >= n_items) id = -1;
+        const uint32_t slot = t % I_RING;
+#pragma unroll
+        for (uint32_t r = 0; r < 2; ++r) {
+            st_shared_cluster_u32(mapa_shared(item_ring0 + 4 * slot, r), (uint32_t)id);
+            mbar_arrive_cluster(mapa_shared(item_full0 + 8 * slot, r));
+        }
+    };
     auto decode = [&](int id, int& itp, int& mb) {
         const int band = id / per_band;
         const int left = n_mb - band * I_BAND;
@@ -390,7 +426,10 @@ trmm_sumsq_i8p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
         if (lane == 0) {
             tma_prefetch_desc(&tmAh); tma_prefetch_desc(&tmB);
             uint32_t git = 0;                                   // k iterations issued so far (over all tiles)
-            for (int id = cid; id < n_items; id += n_clusters) {
+            for (uint32_t t = 0;; ++t) {
+                if (dynamic && crank == 0) publish_item(t);
+                const int id = item_at(t);
+                if (id < 0) break;
                 int itp, mb;
                 decode(id, itp, mb);
                 const int nk = (itp + 1) * 2 * I_N / BKB;       // the pair runs the odd tile's extent (zero slices beyond the diagonal)
@@ -411,12 +450,22 @@ trmm_sumsq_i8p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
                         tma_load_2d(dst + S * C::A_BYTES + j * C::B_BYTES, &tmB, k0, j * Np + it * I_N, full0 + 8 * s);
                 }
             }
+            if (dynamic && crank == 0) {            // the last cluster to run out of items rewinds the counters for the next launch
+                __threadfence();
+                if (atomicAdd(sched + 1, 1) == n_clusters - 1) {
+                    sched[0] = 0;
+                    sched[1] = 0;
+                    __threadfence();
+                }
+            }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            uint32_t git = 0, tile_n = 0;
-            for (int id = cid; id < n_items; id += n_clusters, ++tile_n) {
+            uint32_t git = 0;
+            for (uint32_t tile_n = 0;; ++tile_n) {
+                const int id = item_at(tile_n);
+                if (id < 0) break;
                 int itp, mb;
                 decode(id, itp, mb);
                 const int nk = (itp + 1) * 2 * I_N / BKB;
@@ -457,8 +506,9 @@ trmm_sumsq_i8p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
         const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
         const int ek = scale_exponent_b<BITS>(*amax_ptr);
         const double kfac = ldexp(1.0, ek + 1 - 2 * BITS);       // V = (sum_g acc_g 2^{-BITS g}) * 2^{-2 BITS} / (scale_i scale_K): exact
-        uint32_t tile_n = 0;
-        for (int id = cid; id < n_items; id += n_clusters, ++tile_n) {
+        for (uint32_t tile_n = 0;; ++tile_n) {
+            const int id = item_at(tile_n);
+            if (id < 0) break;
             int itp, mb;
             decode(id, itp, mb);
             const int it = 2 * itp + (int)crank;
@@ -572,7 +622,7 @@ int i8_clusters() { return g_i8_clusters; }     // clusters of the last configur
 
 template <int S, int BITS>
 static int launch_i8(const int8_t* Ls, const double* inv_scale, int Np, const int8_t* Kp, int Mc, const double* amax_ptr,
-                     double* qpart, cudaStream_t st) {
+                     double* qpart, int* sched, cudaStream_t st) {
     using C = I8Cfg<S, 64>;
     static bool attr[64] = {false};
     static int max_clusters[64] = {0};
@@ -618,7 +668,10 @@ static int launch_i8(const int8_t* Ls, const double* inv_scale, int Np, const in
         cluster2_config(cfg, at, 2 * clusters, C::SMEM_BYTES, st);
         static int probe = -1;
         if (probe < 0) { const char* pe = getenv("GPX_I8_PROBE"); probe = (pe && pe[0] == 'n') ? 1 : 0; }
-        cudaError_t e = cudaLaunchKernelEx(&cfg, trmm_sumsq_i8p_kernel<S, BITS>, tmAh, tmB, Np, Mc, inv_scale, amax_ptr, qpart, probe);
+        static int sched_off = -1;      // GPX_I8_SCHED=static: fixed stride instead of the ordered atomic hand-out
+        if (sched_off < 0) { const char* se = getenv("GPX_I8_SCHED"); sched_off = (se && se[0] == 's') ? 1 : 0; }
+        cudaError_t e = cudaLaunchKernelEx(&cfg, trmm_sumsq_i8p_kernel<S, BITS>, tmAh, tmB, Np, Mc, inv_scale, amax_ptr, qpart, probe,
+                                           sched_off ? (int*)nullptr : sched);
         if (e != cudaSuccess) return -1000 - (int)e;
     }
     GPX_CHECK_LAUNCH();
@@ -629,15 +682,17 @@ static int launch_i8(const int8_t* Ls, const double* inv_scale, int Np, const in
 int i8_max_np(int bits) { return bits == 8 ? 16384 : 32768; }
 
 // qpart[it][m], it < Np/64.  Ls: S planes [Np][Np] of the sliced inverse, Kp: S planes [Mc][Np] of the sliced K* chunk.
+// sched: two device ints, zero before the first launch that uses them (the kernel rewinds them itself), not shared by launches that
+// can run at the same time; null = static work distribution.
 int trmm_sumsq_i8(const int8_t* Ls, const double* inv_scale, int Np, const int8_t* Kp, int Mc, int nslices, int bits,
-                  const double* amax_ptr, double* qpart, cudaStream_t st) {
+                  const double* amax_ptr, double* qpart, int* sched, cudaStream_t st) {
     if (Mc % I_M || Np % TILE) return -6;
     if (bits != 7 && bits != 8) return -7;
     if (Np > i8_max_np(bits)) return -7;              // int32 accumulators
-    if (nslices == 5) return bits == 7 ? launch_i8<5, 7>(Ls, inv_scale, Np, Kp, Mc, amax_ptr, qpart, st)
-                                       : launch_i8<5, 8>(Ls, inv_scale, Np, Kp, Mc, amax_ptr, qpart, st);
-    if (nslices == 6) return bits == 7 ? launch_i8<6, 7>(Ls, inv_scale, Np, Kp, Mc, amax_ptr, qpart, st)
-                                       : launch_i8<6, 8>(Ls, inv_scale, Np, Kp, Mc, amax_ptr, qpart, st);
+    if (nslices == 5) return bits == 7 ? launch_i8<5, 7>(Ls, inv_scale, Np, Kp, Mc, amax_ptr, qpart, sched, st)
+                                       : launch_i8<5, 8>(Ls, inv_scale, Np, Kp, Mc, amax_ptr, qpart, sched, st);
+    if (nslices == 6) return bits == 7 ? launch_i8<6, 7>(Ls, inv_scale, Np, Kp, Mc, amax_ptr, qpart, sched, st)
+                                       : launch_i8<6, 8>(Ls, inv_scale, Np, Kp, Mc, amax_ptr, qpart, sched, st);
     return -8;
 }
 

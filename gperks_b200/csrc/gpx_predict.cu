@@ -436,7 +436,7 @@ int predict_meanvar_tf32(const double* Xs, long M, const double* X, int N, int D
 
 // ---- sliced-integer mode (tcgen05 kind::i8, gpx_i8.cu) -------------------------------------------------------
 int trmm_sumsq_i8(const int8_t* Ls, const double* inv_scale, int Np, const int8_t* Kp, int Mc, int nslices, int bits,
-                  const double* amax_ptr, double* qpart, cudaStream_t st);
+                  const double* amax_ptr, double* qpart, int* sched, cudaStream_t st);
 int i8_row_tiles(int Np);
 int i8_max_np(int bits);
 int kmat_cross_i8(const double* Xs, long m_valid, const double* X, int N, int D, const double* theta, const double* xa,
@@ -478,7 +478,10 @@ static size_t i8_item_bytes(int Np, int Mc, int nslices) {
 template <class ItemAt, class AfterFinalize>
 static int run_i8_pipeline(long n_items, ItemAt item_at, AfterFinalize after_finalize, int D, size_t buf_bytes, void* workspace,
                            cudaStream_t st, cudaStream_t mma) {
-    unsigned char* buf[2] = {reinterpret_cast<unsigned char*>(workspace), reinterpret_cast<unsigned char*>(workspace) + buf_bytes};
+    // workspace = [256 B: the two scheduler counters of the tensor-core kernel | item buffer 0 | item buffer 1 | caller's tail]
+    int* sched = reinterpret_cast<int*>(workspace);
+    cudaMemsetAsync(sched, 0, 2 * sizeof(int), st);      // ordered before the first tensor-core launch through its build event
+    unsigned char* buf[2] = {reinterpret_cast<unsigned char*>(workspace) + 256, reinterpret_cast<unsigned char*>(workspace) + 256 + buf_bytes};
     const bool overlap = mma != nullptr && mma != st && n_items > 1;
     cudaEvent_t ev_built[2] = {nullptr, nullptr}, ev_mma[2] = {nullptr, nullptr};
     if (overlap) {
@@ -516,7 +519,7 @@ static int run_i8_pipeline(long n_items, ItemAt item_at, AfterFinalize after_fin
         const I8Emulator& e = *it.em;
         int8_t* Kp; double *mean_part, *qpart; int mc;
         parts(i, it, Kp, mean_part, qpart, mc);
-        int r = trmm_sumsq_i8(e.Ls, e.inv_scale, e.Np, Kp, mc, e.nslices, e.bits, e.theta + D, qpart, overlap ? mma : st);
+        int r = trmm_sumsq_i8(e.Ls, e.inv_scale, e.Np, Kp, mc, e.nslices, e.bits, e.theta + D, qpart, sched, overlap ? mma : st);
         if (r == 0 && overlap) cudaEventRecord(ev_mma[i & 1], mma);
         return r;
     };
@@ -559,8 +562,8 @@ static int run_i8_pipeline(long n_items, ItemAt item_at, AfterFinalize after_fin
 }
 
 // workspace: two item buffers, each [K* slice planes [S][mc][Np] int8 | mean_part [nb][mc] | qpart [nt][mc]]
-size_t predict_i8_workspace_bytes(int Np, int Mc, int nslices) { return 2 * (i8_item_bytes(Np, Mc, nslices) + 256); }
-size_t predict_i8_planes_offset(int Np, int Mc, int nslices, int buffer) { return (size_t)buffer * (i8_item_bytes(Np, Mc, nslices) + 256); }
+size_t predict_i8_workspace_bytes(int Np, int Mc, int nslices) { return 256 + 2 * (i8_item_bytes(Np, Mc, nslices) + 256); }
+size_t predict_i8_planes_offset(int Np, int Mc, int nslices, int buffer) { return 256 + (size_t)buffer * (i8_item_bytes(Np, Mc, nslices) + 256); }
 
 // As predict_meanvar; the variance contraction runs on the integer tensor cores from `nslices` slices of `bits` bits of L^-1
 // (Ls, inv_scale: gpx_slice_i8 of S, once per factorisation) and of each K* chunk (written directly as slices by the builder).
@@ -600,7 +603,7 @@ size_t wave_i8_workspace_bytes(const I8Emulator* em, int E, int Mc) {
         const size_t b = i8_item_bytes(em[e].Np, Mc, em[e].nslices) + 256;
         item = b > item ? b : item;
     }
-    return 2 * item + (size_t)2 * E * Mc * 8;
+    return 256 + 2 * item + (size_t)2 * E * Mc * 8;
 }
 
 int wave_i8(const I8Emulator* em, int E, int D, const double* Xs, long M, const double* z, const double* v, int maxno,
@@ -620,7 +623,7 @@ int wave_i8(const I8Emulator* em, int E, int D, const double* Xs, long M, const 
         const size_t b = i8_item_bytes(em[e].Np, Mc, em[e].nslices) + 256;
         item = b > item ? b : item;
     }
-    double* cmean = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(workspace) + 2 * item);      // [E][Mc] chunk-local
+    double* cmean = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(workspace) + 256 + 2 * item);      // [E][Mc] chunk-local
     double* cstd = cmean + (size_t)E * Mc;
     const long n_chunks = (M + Mc - 1) / Mc;
     const bool full = mean_out != nullptr && std_out != nullptr;

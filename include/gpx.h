@@ -141,7 +141,9 @@ int gpx_predict_meanvar_tf32(const double* Xs, long M, const double* X, int N, i
  *   untouched: never read) and every row gets its own scale, inv_scale[row] = 1/scale.  tri == 0: one scale for the whole matrix
  *   from the device scalar *amax_ptr >= max|src| (K* <= outputscale).  Run once per factorisation on S.
  * gpx_trmm_sumsq_i8: qpart[it][m] = sum over the 64 rows of tile `it` of (K* L^-T)[m][i]^2, it < gpx_i8_row_tiles(Np);
- *   Mc multiple of 128, Np <= gpx_i8_max_n(bits) (int32 accumulators).
+ *   Mc multiple of 128, Np <= gpx_i8_max_n(bits) (int32 accumulators).  sched: two device ints, zero before the first launch that
+ *   uses them, from which the persistent kernel's clusters draw their work items in order (it rewinds them when it finishes; do not
+ *   share them between launches that may overlap); NULL = static work distribution.
  * gpx_predict_meanvar_i8: as gpx_predict_meanvar with the variance contraction on the integer tensor cores.  Chunks are
  *   double-buffered in the workspace; with a non-null `mma_stream` (a second stream of the caller, ideally of higher priority)
  *   the tensor-core kernel of chunk c runs there while the K* builder of chunk c+1 runs on `stream` -- the two kernels are
@@ -159,7 +161,7 @@ int gpx_kmat_cross_i8(const double* Xs, long m_valid, const double* X, int N, in
                       const double* xr, int kind, const double* alpha, signed char* planes, long plane_rows, int nslices,
                       int bits, int Np, double* mean_part, int Mc, void* stream);
 int gpx_trmm_sumsq_i8(const signed char* Ls, const double* inv_scale, int Np, const signed char* Kp, int Mc, int nslices,
-                      int bits, const double* amax_ptr, double* qpart, void* stream);
+                      int bits, const double* amax_ptr, double* qpart, int* sched, void* stream);
 /* gpx_lauum_i8: gpx_lauum on the integer tensor cores.  The columns of L^-1 (rows of L^-T: DT inside the diagonal blocks, the
  * mirrored blocks of S beside them) are sliced with one power-of-two scale per column into the workspace, and
  * Kinv = L^-T L^-1 is formed by the same kind::i8 kernel (store epilogue) for the 128-tiles on and below the diagonal -- the

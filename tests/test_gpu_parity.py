@@ -537,8 +537,16 @@ def test_i8_kernel_exact_on_integer_slices(dev, bits):
         amax = torch.tensor([1.3], dtype=F64, device=dev)           # frexp exponent 1 -> 1/scale_K = 4
         nt = lib.gpx_i8_row_tiles(Np)
         q = torch.full((nt, Mc), -1.0, dtype=F64, device=dev)
+        sched = torch.zeros(2, dtype=torch.int32, device=dev)          # ordered atomic hand-out of the work items
         nv.check(lib.gpx_trmm_sumsq_i8(nv.ptr(Ls), nv.ptr(inv_scale), Np, nv.ptr(Kp), Mc, S, bits, nv.ptr(amax), nv.ptr(q),
-                                       nv.stream_ptr()), "i8")
+                                       nv.ptr(sched), nv.stream_ptr()), "i8")
+        q_static = torch.full((nt, Mc), -1.0, dtype=F64, device=dev)    # static stride: same bits
+        nv.check(lib.gpx_trmm_sumsq_i8(nv.ptr(Ls), nv.ptr(inv_scale), Np, nv.ptr(Kp), Mc, S, bits, nv.ptr(amax), nv.ptr(q_static),
+                                       None, nv.stream_ptr()), "i8")
+        q2 = torch.full((nt, Mc), -1.0, dtype=F64, device=dev)          # second launch on the same counters: the kernel rewound them
+        nv.check(lib.gpx_trmm_sumsq_i8(nv.ptr(Ls), nv.ptr(inv_scale), Np, nv.ptr(Kp), Mc, S, bits, nv.ptr(amax), nv.ptr(q2),
+                                       nv.ptr(sched), nv.stream_ptr()), "i8")
+        assert torch.equal(q, q_static) and torch.equal(q, q2) and int(sched.abs().sum()) == 0
         V = torch.zeros(Np, Mc, dtype=F64, device=dev)
         for a in range(S):
             for b in range(S - a):

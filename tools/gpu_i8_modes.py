@@ -105,11 +105,12 @@ for spec in args.sizes:
                 Kp = ws.data_ptr() + int(lib.gpx_predict_i8_planes_offset(eng.Np, Mc, S, 0))
                 nt = int(lib.gpx_i8_row_tiles(eng.Np))
                 qp = torch.empty(nt * Mc, dtype=F64, device=dev)
+                sched = torch.zeros(2, dtype=torch.int32, device=dev)
                 mp = torch.empty(eng.nb * Mc, dtype=F64, device=dev)
                 st = nv.stream_ptr()
                 t["chunk"] = Mc
                 t["mma_kernel_ms"] = timed(lambda: nv.check(lib.gpx_trmm_sumsq_i8(
-                    nv.ptr(eng.S_i8), nv.ptr(eng.S_i8_inv_scale), eng.Np, Kp, Mc, S, bits, nv.ptr(eng.theta) + 8 * D, nv.ptr(qp), st), "mma"),
+                    nv.ptr(eng.S_i8), nv.ptr(eng.S_i8_inv_scale), eng.Np, Kp, Mc, S, bits, nv.ptr(eng.theta) + 8 * D, nv.ptr(qp), nv.ptr(sched), st), "mma"),
                     reps=max(3, int(300 / max(t["ms_serial"] * Mc / M, 0.1))), clock=True)
                 t["builder_kernel_ms"] = timed(lambda: nv.check(lib.gpx_kmat_cross_i8(
                     nv.ptr(Xt), Mc, nv.ptr(eng.X), N, D, nv.ptr(eng.theta), None, None, 3, nv.ptr(eng.alpha), Kp, Mc, S, bits, eng.Np,
@@ -125,7 +126,7 @@ for spec in args.sizes:
                     ev.record(cur)
                     hp.wait_event(ev)
                     launch_m = lambda: nv.check(lib.gpx_trmm_sumsq_i8(nv.ptr(eng.S_i8), nv.ptr(eng.S_i8_inv_scale), eng.Np, Kp, Mc, S, bits,  # noqa: E731
-                                                                      nv.ptr(eng.theta) + 8 * D, nv.ptr(qp), hp.cuda_stream), "mma")
+                                                                      nv.ptr(eng.theta) + 8 * D, nv.ptr(qp), nv.ptr(sched), hp.cuda_stream), "mma")
                     launch_b = lambda: nv.check(lib.gpx_kmat_cross_i8(nv.ptr(Xt), Mc, nv.ptr(eng.X), N, D, nv.ptr(eng.theta), None, None, 3,  # noqa: E731
                                                                       nv.ptr(eng.alpha), Kp1, Mc, S, bits, eng.Np, nv.ptr(mp), Mc, st), "builder")
                     for f in ((launch_m, launch_b) if order == "mb" else (launch_b, launch_m)):
