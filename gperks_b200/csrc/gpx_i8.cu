@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(I_THREADS, 2)      // "2" caps the kernel at 9
 trmm_sumsq_i8p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmB, int Np, int Mc,
                       const double* __restrict__ inv_scale, const double* __restrict__ amax_ptr, double* __restrict__ qpart,
                       const int probe,        // probe != 0 (GPX_I8_PROBE=nofill, timing experiments only): the ring is filled once, never refilled
-                      int* __restrict__ sched) {
+                      int* __restrict__ sched, const int band_w) {      // band_w: point tiles per band (I_BAND; GPX_I8_BAND overrides)
     using C = I8Cfg<S, 64>;
     constexpr int BKB = 64;
     extern __shared__ unsigned char smem_raw[];
@@ -366,7 +366,7 @@ trmm_sumsq_i8p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
     const int n_mb = Mc / I_M, n_it = Np / (2 * I_N);          // n_it counts PAIRS of row tiles
     const int n_items = n_mb * n_it;
     const int cid = (int)(blockIdx.x >> 1), n_clusters = (int)(gridDim.x >> 1);
-    const int per_band = I_BAND * n_it;
+    const int per_band = band_w * n_it;
     const bool dynamic = sched != nullptr;
 
     if (tid == 0) {
@@ -414,11 +414,11 @@ trmm_sumsq_i8p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
     };
     auto decode = [&](int id, int& itp, int& mb) {
         const int band = id / per_band;
-        const int left = n_mb - band * I_BAND;
-        const int width = left < I_BAND ? left : I_BAND;
+        const int left = n_mb - band * band_w;
+        const int width = left < band_w ? left : band_w;
         const int rem = id - band * per_band;
         itp = n_it - 1 - rem / width;
-        mb = band * I_BAND + rem % width;
+        mb = band * band_w + rem % width;
     };
 
     if (warp == 0) {
@@ -670,8 +670,10 @@ static int launch_i8(const int8_t* Ls, const double* inv_scale, int Np, const in
         if (probe < 0) { const char* pe = getenv("GPX_I8_PROBE"); probe = (pe && pe[0] == 'n') ? 1 : 0; }
         static int sched_off = -1;      // GPX_I8_SCHED=static: fixed stride instead of the ordered atomic hand-out
         if (sched_off < 0) { const char* se = getenv("GPX_I8_SCHED"); sched_off = (se && se[0] == 's') ? 1 : 0; }
+        static int band_w = -1;
+        if (band_w < 0) { const char* be = getenv("GPX_I8_BAND"); band_w = (be && atoi(be) > 0) ? atoi(be) : I_BAND; }
         cudaError_t e = cudaLaunchKernelEx(&cfg, trmm_sumsq_i8p_kernel<S, BITS>, tmAh, tmB, Np, Mc, inv_scale, amax_ptr, qpart, probe,
-                                           sched_off ? (int*)nullptr : sched);
+                                           sched_off ? (int*)nullptr : sched, band_w);
         if (e != cudaSuccess) return -1000 - (int)e;
     }
     GPX_CHECK_LAUNCH();

@@ -113,7 +113,8 @@ class PosteriorDistribution:
                 def compute(eng):
                     xd = self.x.detach().to(eng.device, F64).contiguous()
                     prior = self.model.mean_module(self.x.detach()).detach().to(eng.device, F64)
-                    mean, std = eng.predict(xd, prior_mean=prior, noisy=self.noisy)
+                    # large emulators: the variance contraction on the integer tensor cores where that keeps 1e-6 (engine.auto_precision)
+                    mean, std = eng.predict(xd, prior_mean=prior, noisy=self.noisy, precision=eng.auto_precision(self.noisy))
                     return (mean, std * std)
                 self._mv = self.model._cached_prediction(self._x_orig, self.noisy, compute)
         return self._mv

@@ -22,7 +22,18 @@ from typing import Optional, Sequence
 import torch
 
 from . import _native as nv
-from .constants import AUTO_I8_MAX_N, AUTO_I8_MIN_N, AUTO_I8_PROBE_POINTS, AUTO_I8_PROBE_POOL, AUTO_I8_SLICES
+from .constants import (
+    AUTO_I8_MAX_N,
+    AUTO_I8_MAX_SCALE_TO_NOISE,
+    AUTO_I8_MIN_N,
+    AUTO_I8_PROBE_POINTS,
+    AUTO_I8_PROBE_POOL,
+    AUTO_I8_PROBE_TOL,
+    AUTO_I8_SLICES,
+    AUTO_I8_W5_MAX_SCALE_TO_NOISE,
+    AUTO_I8_W6_MAX_SCALE_TO_NOISE,
+    AUTO_I8_WIDE_MAX_N,
+)
 
 F64 = torch.float64
 
@@ -379,6 +390,39 @@ class ExactGPEngine:
             self._launch("gpx_split_tf32", nv.ptr(self.S), self.Np * self.Np, nv.ptr(self.S_hi), nv.ptr(self.S_lo),
                          self.Np, nv.stream_ptr())
         self.has_split = True
+
+    @staticmethod
+    def auto_candidates(n: int, outputscale: float, noise: float):
+        """Candidates of ``precision="auto"`` for a train size and an outputscale / noise ratio, fastest first, always ending in
+        ``"fp64"`` (``constants.AUTO_I8_*``; the limits come from measured error constants)."""
+        if not (AUTO_I8_MIN_N <= n <= AUTO_I8_MAX_N) or not (noise > 0.0 and outputscale > 0.0):
+            return ["fp64"]
+        ratio = outputscale / noise
+        cands = []
+        if nv.padded(n) <= AUTO_I8_WIDE_MAX_N:
+            if ratio <= AUTO_I8_W5_MAX_SCALE_TO_NOISE:
+                cands.append("int8x5w")
+            if ratio <= AUTO_I8_W6_MAX_SCALE_TO_NOISE:
+                cands.append("int8x6w")
+        elif ratio <= AUTO_I8_MAX_SCALE_TO_NOISE:
+            cands.append("int8x6")
+        return cands + ["fp64"]
+
+    def auto_precision(self, noisy: bool = True) -> str:
+        """What ``model(x).variance`` / ``likelihood(model(x))`` use for the CURRENT factors: the first ``auto`` candidate -- checked
+        against the FP64 path on the probe set outside training loops, by its ratio limit alone inside them (per-epoch metrics).
+        The latent variance (``noisy=False``) has no noise floor under its cancellation and stays on the FP64 path."""
+        if not noisy or not self.factored:
+            return "fp64"
+        key = self.n_factorizations
+        if getattr(self, "_auto_key", None) != key:
+            th = self.theta[self.D:].tolist()              # one small host read per factorisation
+            self._auto_cands = self.auto_candidates(self.N, float(th[0]), float(th[1]))
+            self._auto_key = key
+        for c in self._auto_cands:
+            if c == "fp64" or self.approx_inverse_ok or self.int8_probe_ok(c, AUTO_I8_PROBE_TOL):
+                return c
+        return "fp64"
 
     def _probe_points(self):
         """Probe set of the ``precision="auto"`` guard for the CURRENT factors: out of up to AUTO_I8_PROBE_POOL evenly strided

@@ -407,25 +407,11 @@ class GPEmulator(Trainable):
         """The candidates of ``precision="auto"`` for this emulator, fastest first, always ending in ``"fp64"``: sliced-integer
         modes (FP64-grade variance from the integer tensor cores) whose int32 sums cannot overflow at this train size and whose
         error, amplified by outputscale / noise, stays inside 1e-6 -- see ``constants.AUTO_I8_*``.  Host-side values only."""
-        n = int(self.scaled_data.X_train.shape[0])
-        if not (AUTO_I8_MIN_N <= n <= AUTO_I8_MAX_N):
-            return ["fp64"]
+        from ..engine import ExactGPEngine
         with torch.no_grad():
-            s = float(self.model.covar_module.outputscale)
+            s = float(torch.as_tensor(self.model._kernel_parts()[0]).reshape(-1)[0])        # 1 for a bare (unscaled) kernel
             nz = float(self.model.likelihood.noise)
-        if not (nz > 0.0 and s > 0.0):
-            return ["fp64"]
-        ratio = s / nz
-        n_pad = (n + 127) // 128 * 128
-        cands = []
-        if n_pad <= AUTO_I8_WIDE_MAX_N:
-            if ratio <= AUTO_I8_W5_MAX_SCALE_TO_NOISE:
-                cands.append("int8x5w")
-            if ratio <= AUTO_I8_W6_MAX_SCALE_TO_NOISE:
-                cands.append("int8x6w")
-        elif ratio <= AUTO_I8_MAX_SCALE_TO_NOISE:
-            cands.append("int8x6")
-        return cands + ["fp64"]
+        return ExactGPEngine.auto_candidates(int(self.scaled_data.X_train.shape[0]), s, nz)
 
     def resolve_precision(self, precision: str) -> str:
         """``"auto"`` -> its first candidate (``auto_precisions``); any other value is returned unchanged.  ``predict`` /
