@@ -42,7 +42,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     edited or freshly pulled source tree is never paired with a stale library.  When the sources are unreadable or nvcc is
     absent (a deployed wheel), an existing library is used as it is; ``_native.lib()`` still checks its ABI version."""
     srcs = [CSRC / s for s in SOURCES]
-    deps = srcs + [CSRC / "gpx_common.cuh", CSRC / "gpx_tma.cuh", CSRC / "gpx_gemm_tma.cuh", CSRC / "gpx_tc.cuh", PKG.parent / "include" / "gpx.h"]
+    deps = srcs + [CSRC / "gpx_common.cuh", CSRC / "gpx_math.cuh", CSRC / "gpx_tma.cuh", CSRC / "gpx_gemm_tma.cuh", CSRC / "gpx_tc.cuh", PKG.parent / "include" / "gpx.h"]
     try:
         digest = source_digest(deps)
     except OSError:

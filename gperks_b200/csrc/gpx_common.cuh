@@ -8,6 +8,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "gpx_math.cuh"
 
 namespace gpx {
 
@@ -42,41 +43,41 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // ---------------------------------------------------------------------------------------------
 template <int KIND>
 __device__ __forceinline__ double kernel_value(double r2, double s) {
-    if (KIND == RBF) return s * exp(-0.5 * r2);
-    double r = sqrt(fmax(r2, 1e-30));
-    if (KIND == MATERN12) return s * exp(-r);
+    if (KIND == RBF) return s * exp_neg(0.5 * r2);
+    const double r = sqrt_pos(r2 + 1e-30);          // r2 = 0 (a point against itself) -> r = 1e-15, k = s to the last bit
+    if (KIND == MATERN12) return s * exp_neg(r);
     if (KIND == MATERN32) {
-        const double c = 1.7320508075688772;
-        return s * (1.0 + c * r) * exp(-c * r);
+        const double cr = 1.7320508075688772 * r;
+        return (s * (1.0 + cr)) * exp_neg(cr);
     }
-    const double c = 2.23606797749979;
-    return s * (1.0 + c * r + (5.0 / 3.0) * r2) * exp(-c * r);
+    const double cr = 2.23606797749979 * r;
+    return (s * fma(r2, 5.0 / 3.0, 1.0 + cr)) * exp_neg(cr);
 }
 
 // returns k and writes g
 template <int KIND>
 __device__ __forceinline__ double kernel_value_grad(double r2, double s, double& g) {
     if (KIND == RBF) {
-        double k = s * exp(-0.5 * r2);
+        double k = s * exp_neg(0.5 * r2);
         g = k;
         return k;
     }
-    double r = sqrt(fmax(r2, 1e-30));
+    const double r = sqrt_pos(r2 + 1e-30);
     if (KIND == MATERN12) {
-        double e = s * exp(-r);
+        double e = s * exp_neg(r);
         g = (r2 > 0.0) ? e / r : 0.0;
         return e;
     }
     if (KIND == MATERN32) {
-        const double c = 1.7320508075688772;
-        double e = s * exp(-c * r);
+        const double cr = 1.7320508075688772 * r;
+        double e = s * exp_neg(cr);
         g = 3.0 * e;
-        return (1.0 + c * r) * e;
+        return (1.0 + cr) * e;
     }
-    const double c = 2.23606797749979;
-    double e = s * exp(-c * r);
-    g = (5.0 / 3.0) * (1.0 + c * r) * e;
-    return (1.0 + c * r + (5.0 / 3.0) * r2) * e;
+    const double cr = 2.23606797749979 * r;
+    double e = s * exp_neg(cr);
+    g = (5.0 / 3.0) * (1.0 + cr) * e;
+    return fma(r2, 5.0 / 3.0, 1.0 + cr) * e;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -227,6 +228,15 @@ __device__ __forceinline__ unsigned long long balanced_digits(double v) {
     constexpr unsigned long long BIAS = (S == 5) ? 0x8080808080ull : 0x808080808080ull;
     const long long V = __double2ll_rn(v * (double)(1ull << (8 * S)));
     return ((unsigned long long)V + BIAS) ^ BIAS;
+}
+// Same digits from V = v * 2^(8S) already formed (|V| < 2^(8S-1)): adding 1.5 * 2^52 + BIAS rounds V to the nearest integer
+// (ties to even, like cvt.rni: the constant is even) and leaves V + BIAS in the low mantissa bits -- one DADD instead of
+// DMUL + F2I + a 64-bit integer add.  Only bytes 0..S-1 of the result are meaningful.
+template <int S>
+__device__ __forceinline__ unsigned long long balanced_digits_prescaled(double V) {
+    constexpr unsigned long long BIAS = (S == 5) ? 0x8080808080ull : 0x808080808080ull;
+    const double t = V + (6755399441055744.0 + (double)BIAS);
+    return (unsigned long long)__double_as_longlong(t) ^ BIAS;
 }
 __device__ __forceinline__ int perm128(int c) { return (c & ~127) | ((c & 15) << 3) | ((c & 127) >> 4); }
 

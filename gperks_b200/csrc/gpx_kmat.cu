@@ -93,13 +93,9 @@ __global__ void __launch_bounds__(P_THREADS, 2) kmat_sym_kernel(const double* __
 #pragma unroll
         for (int b = 0; b < 8; ++b) {
             const long j = (long)bj * TILE + tx + 16 * b;
-            double v;
-            if (i < N && j < N) {
-                v = kernel_value<KIND>(r2[b], s);
-                if (i == j) v += noise;
-            } else {
-                v = (i == j) ? 1.0 : 0.0;
-            }
+            const bool in = (i < N && j < N);
+            double v = kernel_value<KIND>(r2[b], in ? s : 0.0);              // branch-free; the padding block is the identity
+            if (i == j) v += in ? noise : 1.0;
             K[i * Np + j] = v;
         }
     }
@@ -153,7 +149,7 @@ kmat_cross_kernel(const double* __restrict__ Xs, long m_valid, const double* __r
 #pragma unroll
         for (int b = 0; b < 8; ++b) {
             const long j = (long)jb * TILE + tx + 16 * b;
-            double v = (j < N) ? kernel_value<KIND>(r2[b], s) : 0.0;
+            double v = kernel_value<KIND>(r2[b], (j < N) ? s : 0.0);     // masked by the outputscale: no branch around the evaluation
             if (Khi != nullptr) {       // TF32 mode: 3xTF32 operand split (hi = tf32(x), lo = tf32(x - hi))
                 uint32_t h, l;
                 float fh, fl;
@@ -207,13 +203,17 @@ kmat_cross_i8_kernel(const double* __restrict__ Xs, long m_valid, const double* 
     if (threadIdx.x < TILE) sal[threadIdx.x] = alpha[jb * TILE + threadIdx.x];
     __syncthreads();
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    const double s = theta[D];
-    const int e = scale_exponent_b<BITS>(s);
+    const int e = scale_exponent_b<BITS>(theta[D]);
     const double scale = ldexp(1.0, (BITS == 7 ? 7 : 0) - (e + 1));      // 7 bit: first slice = rint(v * 2^-(e+1) * 2^7), |.| <= 64
+    // 8 bit: the kernel is evaluated with the outputscale pre-multiplied by the power of two  scale * 2^(8S)  (exact, commutes
+    // with every rounding), so v8 = V-to-be-rounded directly, and alpha is divided by the same power: v8 * al8 == v * al bit for
+    // bit and the fused mean sums stay those of the FP64 path.
+    const double pre = (BITS == 8) ? scale * (double)(1ull << (8 * S)) : 1.0;
+    const double s = theta[D] * pre;
     const long pitch = plane_rows * (long)Np;
     double al[8];
 #pragma unroll
-    for (int b = 0; b < 8; ++b) al[b] = sal[tx + 16 * b];
+    for (int b = 0; b < 8; ++b) al[b] = sal[tx + 16 * b] * (1.0 / pre);
 #pragma unroll 1
     for (int a = 0; a < 8; ++a) {
         const int row = ty + 16 * a;
@@ -236,7 +236,7 @@ kmat_cross_i8_kernel(const double* __restrict__ Xs, long m_valid, const double* 
 #pragma unroll
         for (int b = 0; b < 8; ++b) {
             const long j = (long)jb * TILE + tx + 16 * b;
-            const double v = (j < N) ? kernel_value<KIND>(r2[b], s) : 0.0;
+            const double v = kernel_value<KIND>(r2[b], (j < N) ? s : 0.0);   // masked by the outputscale: no branch
             part = fma(v, al[b], part);
             // byte b of the slice words: selector keeps the other three bytes and takes one byte of the digit word
             constexpr uint32_t keep = 0x3210u;
@@ -252,7 +252,7 @@ kmat_cross_i8_kernel(const double* __restrict__ Xs, long m_valid, const double* 
                     if (b < 4) lo[q] = __byte_perm(lo[q], w, sel); else hi[q] = __byte_perm(hi[q], w, sel);
                 }
             } else {
-                const unsigned long long dg = balanced_digits<S>(v * scale);
+                const unsigned long long dg = balanced_digits_prescaled<S>(v);
                 const uint32_t w0 = (uint32_t)dg, w1 = (uint32_t)(dg >> 32);
 #pragma unroll
                 for (int q = 0; q < S; ++q) {
@@ -351,7 +351,7 @@ predict_mean_kernel(const double* __restrict__ Xs, long m_valid, const double* _
 #pragma unroll
             for (int b = 0; b < 8; ++b) {
                 const long j = (long)jb * TILE + tx + 16 * b;
-                const double v = (j < N) ? kernel_value<KIND>(r2[b], s) : 0.0;
+                const double v = kernel_value<KIND>(r2[b], (j < N) ? s : 0.0);   // masked by the outputscale: no branch
                 part = fma(v, al[b], part);
             }
             part += __shfl_xor_sync(0xffffffffu, part, 1);
@@ -584,11 +584,10 @@ mll_grad_tile_kernel(const double* __restrict__ X, int N, int D, const double* _
 #pragma unroll
         for (int b = 0; b < 8; ++b) {
             const long j = (long)bj * TILE + tx + 16 * b;
-            double w = 0.0, g = 0.0, k = 0.0;
-            if (i < N && j < N) {
-                w = wcur[b] - ai * salj[tx + 16 * b];
-                k = kernel_value_grad<KIND>(r2[b], s, g);
-            }
+            const bool in = (i < N && j < N);
+            double g;
+            const double k = kernel_value_grad<KIND>(r2[b], s, g);          // evaluated unconditionally (branch-free); w masks it
+            const double w = in ? wcur[b] - ai * salj[tx + 16 * b] : 0.0;
             acc_s = fma(w, k, acc_s);
             if (i == j) acc_n += w;
             wg[b] = w * g;

@@ -72,6 +72,34 @@ def test_stagewise_parity_with_oracle(dev, kind, N, D):
     np.testing.assert_allclose(eng.W[:N, :N].cpu().numpy(), Kinv.numpy(), rtol=0, atol=1e-9 * float(Kinv.abs().max()))
 
 
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("ls_scale", [1.0, 0.02])
+def test_kernel_function_values_to_the_last_bits(dev, kind, ls_scale):
+    """The branch-free FP64 exp / sqrt of csrc/gpx_math.cuh, device build, through gpx_kmat_sym: every entry of K_hat against
+    the oracle's kernel (libm exp / sqrt) to 4 ulp of the entry, including the diagonal (r = 0) and, with the short
+    lengthscales, arguments of exp down to -150 (entries of 1e-65 must still carry full relative precision)."""
+    N, D = 333, 5
+    X, y, Xs, ls, s, w, b = _problem(N, D, 1, seed=kind)
+    ls = ls * ls_scale
+    nz = 1e-2
+    theta = torch.cat([1.0 / ls, s.reshape(1), torch.tensor([nz], dtype=F64)]).to(dev)
+    Np = (N + 127) // 128 * 128
+    Kh = torch.zeros(Np, Np, dtype=F64, device=dev)
+    Xd = X.to(dev).contiguous()
+    nv.check(nv.lib().gpx_kmat_sym(nv.ptr(Xd), N, D, nv.ptr(theta), kind, nv.ptr(Kh), Np, nv.stream_ptr()), "kmat")
+    got = torch.tril(Kh[:N, :N]).cpu()
+    ref = torch.tril(O.kernel_matrix(X, X, kind, ls, s) + nz * torch.eye(N, dtype=F64))
+    rel = ((got - ref).abs() / ref.abs().clamp_min(1e-300)).max()
+    # conditioning, common to both sides: the scaled coordinates a = x / l carry one rounding each (the device multiplies by 1/l),
+    # so r^2 is known to ~ulp * |a| * |a - b| per dimension, and d log k = r dr (RBF) or <= sqrt(5) dr (Matern)
+    amax = float((X / ls).abs().max())
+    rmax = float(O.sq_dist(X, X, ls).max().sqrt())
+    amp = 1.0 + 2.0 * amax * (rmax if kind == O.KIND_RBF else 2.3 * math.sqrt(D))
+    assert float(rel) <= 4.5e-16 * amp, (float(rel), amp)
+    assert torch.equal(got.diagonal(), torch.full((N,), float(s) + nz, dtype=F64))
+    assert torch.equal(Kh[N:, N:].cpu(), torch.eye(Np - N, dtype=F64)) and float(Kh[N:, :N].abs().sum()) == 0.0
+
+
 @pytest.mark.parametrize("N,D,kind", [(1500, 5, O.KIND_MATERN32), (2048, 6, O.KIND_MATERN52), (4200, 7, O.KIND_RBF)])
 def test_mid_size_mll_and_gradients_against_oracle_on_device(dev, N, D, kind):
     """Sizes where the schedule choices differ from both the small cases above and N=8192: 32- and 64-row strip editions
