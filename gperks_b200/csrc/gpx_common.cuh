@@ -41,6 +41,24 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // stationary kernel profile k(r^2) and the radial derivative factor g(r) with
 //   dk/dl_d = g(r) * delta_d^2 / l_d^3           
 // ---------------------------------------------------------------------------------------------
+// The builders of K_hat and K* (gpx_kmat.cu) stage their coordinates pre-multiplied by coord_scale<KIND>() / lengthscale and
+// start every squared-distance accumulator at 1e-30, so that q = c^2 r^2 + 1e-30 arrives ready for the profile:
+//   RBF (c^2 = 1/2): s exp(-q)       Matern: u = sqrt(q) = c r;  1/2: s exp(-u);  3/2: (s + s u) exp(-u);
+//   5/2: (s + s u + (s/3) q) exp(-u).   q = 1e-30 (a point against itself) gives u = 1e-15 and k = s to the last bit for nu > 1/2.
+// s may be 0 (masked entry): every form then returns exactly 0.  s3 = s / 3 is formed once per thread.
+template <int KIND>
+__host__ __device__ constexpr double coord_scale() {
+    return KIND == RBF ? 0.70710678118654752 : KIND == MATERN12 ? 1.0 : KIND == MATERN32 ? 1.7320508075688772 : 2.23606797749979;
+}
+template <int KIND>
+__device__ __forceinline__ double kernel_profile(double q, double s, double s3) {
+    if (KIND == RBF) return s * exp_neg(q);
+    const double u = sqrt_pos(q);
+    if (KIND == MATERN12) return s * exp_neg(u);
+    if (KIND == MATERN32) return fma(u, s, s) * exp_neg(u);
+    return fma(q, s3, fma(u, s, s)) * exp_neg(u);
+}
+
 template <int KIND>
 __device__ __forceinline__ double kernel_value(double r2, double s) {
     if (KIND == RBF) return s * exp_neg(0.5 * r2);

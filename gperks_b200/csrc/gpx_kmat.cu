@@ -12,6 +12,8 @@
 // All three share one tile body: a 128 x 128 tile per CTA, 256 threads, each thread an 8 x 8 micro-tile
 // strided by 16 so that a warp's stores cover two full 128-byte row segments.  Coordinates are
 // pre-multiplied by 1/lengthscale while being staged (transposed) into shared memory.
+#include <cstdlib>
+#include <type_traits>
 #include "gpx_common.cuh"
 
 namespace gpx {
@@ -19,20 +21,41 @@ namespace gpx {
 constexpr int P_THREADS = 256;
 constexpr int P_LD = TILE + 1;   // padded smem row (transposed coordinate tile [d][128])
 
-// Stage rows [row0, row0+128) of X (row-major, ld = D) as z = ((x - a)/range) * inv_ls, transposed.
-// Rows >= n_valid are filled with zeros.  xa/xr may be null (training inputs are already scaled).
+// Stage rows [row0, row0+128) of X (row-major, ld = D) as z = ((x - a)/range) * inv_ls * cmul, transposed, into Dp >= D rows
+// (rows D..Dp-1 are zero: the distance loops run over an even number of dimensions).  Rows >= n_valid are filled with zeros.
+// xa/xr may be null (training inputs are already scaled).  Thread t owns tile row t % 128 and every second dimension.
 __device__ __forceinline__ void stage_coords(double* sm, const double* __restrict__ X, long row0, long n_valid, int D,
                                              const double* __restrict__ theta, const double* __restrict__ xa,
-                                             const double* __restrict__ xr) {
-    for (int e = threadIdx.x; e < TILE * D; e += P_THREADS) {
-        int r = e / D, d = e - r * D;
+                                             const double* __restrict__ xr, double cmul = 1.0, int Dp = -1) {
+    if (Dp < 0) Dp = D;
+    const int r = threadIdx.x & (TILE - 1);
+    const bool valid = row0 + r < n_valid;
+    for (int d = threadIdx.x >> 7; d < Dp; d += P_THREADS / TILE) {
         double v = 0.0;
-        if (row0 + r < n_valid) {
+        if (valid && d < D) {
             v = X[(row0 + r) * (long)D + d];
             if (xa != nullptr) v = (v - xa[d]) / xr[d];
-            v *= theta[d];
+            v *= theta[d] * cmul;
         }
         sm[d * P_LD + r] = v;
+    }
+}
+
+// q[b] = 1e-30 + sum_d (sa[d][row] - sb[d][tx + 16 b])^2 over the Dp (even) staged coordinate rows: one rolled loop of two
+// dimensions per trip (9 LDS + 16 FP64 per dimension for 8 entries), no remainder code.
+__device__ __forceinline__ void row_q(double (&q)[8], const double* sa, const double* sb, int Dp, int row, int tx) {
+#pragma unroll
+    for (int b = 0; b < 8; ++b) q[b] = 1e-30;
+#pragma unroll 1
+    for (int d = 0; d < Dp; d += 2) {
+        const double x0 = sa[d * P_LD + row], x1 = sa[(d + 1) * P_LD + row];
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const double d0 = x0 - sb[d * P_LD + tx + 16 * b];
+            const double d1 = x1 - sb[(d + 1) * P_LD + tx + 16 * b];
+            q[b] = fma(d0, d0, q[b]);
+            q[b] = fma(d1, d1, q[b]);
+        }
     }
 }
 
@@ -70,31 +93,23 @@ __global__ void __launch_bounds__(P_THREADS, 2) kmat_sym_kernel(const double* __
     extern __shared__ double sm[];
     double* sa = sm;
     double* sb = sm + MAXD * P_LD;
-    stage_coords(sa, X, (long)bi * TILE, N, D, theta, nullptr, nullptr);
-    stage_coords(sb, X, (long)bj * TILE, N, D, theta, nullptr, nullptr);
+    const int Dp = D + (D & 1);
+    stage_coords(sa, X, (long)bi * TILE, N, D, theta, nullptr, nullptr, coord_scale<KIND>(), Dp);
+    stage_coords(sb, X, (long)bj * TILE, N, D, theta, nullptr, nullptr, coord_scale<KIND>(), Dp);
     __syncthreads();
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    const double s = theta[D], noise = theta[D + 1];
+    const double s = theta[D], noise = theta[D + 1], s3 = s / 3.0;
 #pragma unroll 1
     for (int a = 0; a < 8; ++a) {
         const int row = ty + 16 * a;
-        double r2[8];
-#pragma unroll
-        for (int b = 0; b < 8; ++b) r2[b] = 0.0;
-        for (int d = 0; d < D; ++d) {
-            const double xa_ = sa[d * P_LD + row];
-#pragma unroll
-            for (int b = 0; b < 8; ++b) {
-                const double df = xa_ - sb[d * P_LD + tx + 16 * b];
-                r2[b] = fma(df, df, r2[b]);
-            }
-        }
+        double q[8];
+        row_q(q, sa, sb, Dp, row, tx);
         const long i = (long)bi * TILE + row;
 #pragma unroll
         for (int b = 0; b < 8; ++b) {
             const long j = (long)bj * TILE + tx + 16 * b;
             const bool in = (i < N && j < N);
-            double v = kernel_value<KIND>(r2[b], in ? s : 0.0);              // branch-free; the padding block is the identity
+            double v = kernel_profile<KIND>(q[b], in ? s : 0.0, in ? s3 : 0.0);   // branch-free; the padding block is the identity
             if (i == j) v += in ? noise : 1.0;
             K[i * Np + j] = v;
         }
@@ -121,12 +136,13 @@ kmat_cross_kernel(const double* __restrict__ Xs, long m_valid, const double* __r
     double* sb = sm + MAXD * P_LD;      // train points (cols j)
     double* sal = sb + MAXD * P_LD;     // alpha tile [128]
     double* smean = sal + TILE;         // [128]
-    stage_coords(sa, Xs, (long)mb * TILE, m_valid, D, theta, xa, xr);
-    stage_coords(sb, X, (long)jb * TILE, N, D, theta, nullptr, nullptr);
+    const int Dp = D + (D & 1);
+    stage_coords(sa, Xs, (long)mb * TILE, m_valid, D, theta, xa, xr, coord_scale<KIND>(), Dp);
+    stage_coords(sb, X, (long)jb * TILE, N, D, theta, nullptr, nullptr, coord_scale<KIND>(), Dp);
     if (threadIdx.x < TILE) sal[threadIdx.x] = alpha[jb * TILE + threadIdx.x];   // alpha is zero-padded to Np
     __syncthreads();
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    const double s = theta[D];
+    const double s = theta[D], s3 = s / 3.0;
     double al[8];
 #pragma unroll
     for (int b = 0; b < 8; ++b) al[b] = sal[tx + 16 * b];
@@ -134,22 +150,14 @@ kmat_cross_kernel(const double* __restrict__ Xs, long m_valid, const double* __r
     for (int a = 0; a < 8; ++a) {
         const int row = ty + 16 * a;
         double r2[8];
-#pragma unroll
-        for (int b = 0; b < 8; ++b) r2[b] = 0.0;
-        for (int d = 0; d < D; ++d) {
-            const double xa_ = sa[d * P_LD + row];
-#pragma unroll
-            for (int b = 0; b < 8; ++b) {
-                const double df = xa_ - sb[d * P_LD + tx + 16 * b];
-                r2[b] = fma(df, df, r2[b]);
-            }
-        }
+        row_q(r2, sa, sb, Dp, row, tx);
         const long m = (long)mb * TILE + row;
-        double part = 0.0;
+        double part = 0.0, part1 = 0.0;          // columns 0..63 / 64..127 as two chains (the order gpx_kmat_cross_i8 sums in)
 #pragma unroll
         for (int b = 0; b < 8; ++b) {
             const long j = (long)jb * TILE + tx + 16 * b;
-            double v = kernel_value<KIND>(r2[b], (j < N) ? s : 0.0);     // masked by the outputscale: no branch around the evaluation
+            const bool in = j < N;
+            double v = kernel_profile<KIND>(r2[b], in ? s : 0.0, in ? s3 : 0.0);     // masked by the outputscale: no branch around the evaluation
             if (Khi != nullptr) {       // TF32 mode: 3xTF32 operand split (hi = tf32(x), lo = tf32(x - hi))
                 uint32_t h, l;
                 float fh, fl;
@@ -162,8 +170,9 @@ kmat_cross_kernel(const double* __restrict__ Xs, long m_valid, const double* __r
             } else {
                 Ks[m * Np + j] = v;
             }
-            part = fma(v, al[b], part);
+            if (b < 4) part = fma(v, al[b], part); else part1 = fma(v, al[b], part1);
         }
+        part += part1;
         // reduce over the 16 tx lanes (a half-warp holds one row)
         part += __shfl_xor_sync(0xffffffffu, part, 1);
         part += __shfl_xor_sync(0xffffffffu, part, 2);
@@ -181,97 +190,124 @@ kmat_cross_kernel(const double* __restrict__ Xs, long m_valid, const double* __r
 // (planes [S][plane_rows][Np]) of  v * 2^-(e+1)  (outputscale = f 2^e, k <= outputscale) instead of 8-byte values that a
 // second kernel would read back and slice.  BITS = 7: S rounds of round-to-nearest; BITS = 8: one FP64 -> int64 conversion and
 // the bytes of the biased integer (gpx_common.cuh: balanced_digits) -- two FP64 instructions per entry instead of 4 S.
-// A thread owns columns tx + 16 b (b < 8) of its row; the plane layout stores column c of a 128-block at byte
-// (c % 16) * 8 + c / 16 (the L^-1 planes use the same permutation), so the 8 bytes of a slice are assembled in two
-// registers with one PRMT per digit and leave as ONE 8-byte store per slice: a half-warp writes a full 128-byte row segment,
-// no shared-memory staging.  Shared memory holds only the 2 x D coordinate rows (sized by D, not MAXD), so a CTA of this
+// A thread owns FOUR columns tx + 16 (4 h + b) (b < 4) of its row -- half of the FP64 kernels' micro-tile row, so that it
+// runs in 85 registers and three CTAs (24 warps) share an SM: with two CTAs of 126-register threads ptxas serialised most of
+// the polynomial chains and the FP64 pipe idled 40 % of the time waiting on its own latency.  The plane layout stores column c
+// of a 128-block at byte (c % 16) * 8 + c / 16 (the L^-1 planes use the same permutation), so the 4 bytes of a slice are
+// assembled in one register with one PRMT per digit and leave as ONE 4-byte store per slice: a warp writes a full 128-byte
+// row segment, no shared-memory staging.  Shared memory holds only the 2 x D coordinate rows (sized by D, not MAXD), so a CTA of this
 // kernel fits beside the 183 KB CTA of the integer tensor-core kernel working on the previous chunk.
-template <int KIND, int S, int BITS>
-__global__ void __launch_bounds__(P_THREADS, 2)
+template <int KIND, int S, int BITS, int EPT>
+__global__ void __launch_bounds__(P_THREADS, EPT == 4 ? 3 : 2)
 kmat_cross_i8_kernel(const double* __restrict__ Xs, long m_valid, const double* __restrict__ X, int N, int D,
                      const double* __restrict__ theta, const double* __restrict__ xa, const double* __restrict__ xr,
                      const double* __restrict__ alpha, int8_t* __restrict__ planes, long plane_rows, int Np,
                      double* __restrict__ mean_part, int Mc) {
     const int jb = blockIdx.x, mb = blockIdx.y;
     extern __shared__ double sm[];
-    double* sa = sm;                    // test points (rows m)   [D][P_LD]
-    double* sb = sm + D * P_LD;         // train points (cols j)  [D][P_LD]
-    double* sal = sb + D * P_LD;        // alpha tile [128]
+    const int Dp = D + (D & 1);
+    double* sa = sm;                    // test points (rows m)   [Dp][P_LD]
+    double* sb = sm + Dp * P_LD;        // train points (cols j)  [Dp][P_LD]
+    double* sal = sb + Dp * P_LD;       // alpha tile [128]
     double* smean = sal + TILE;         // [128]
-    stage_coords(sa, Xs, (long)mb * TILE, m_valid, D, theta, xa, xr);
-    stage_coords(sb, X, (long)jb * TILE, N, D, theta, nullptr, nullptr);
+    stage_coords(sa, Xs, (long)mb * TILE, m_valid, D, theta, xa, xr, coord_scale<KIND>(), Dp);
+    stage_coords(sb, X, (long)jb * TILE, N, D, theta, nullptr, nullptr, coord_scale<KIND>(), Dp);
     if (threadIdx.x < TILE) sal[threadIdx.x] = alpha[jb * TILE + threadIdx.x];
     __syncthreads();
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    // thread (tx, h, ty): columns tx + 16 (4 h + b), b < 4, of rows ty + 8 a, a < 16.  A warp holds one row: (tx, h) = lane.
+    // (EPT = 8, the FP64 kernels' mapping: eight columns tx + 16 b of rows ty + 16 a, one uint2 store per slice.)
+    constexpr int NH = 8 / EPT;                 // threads sharing one 8-byte group of a row
+    constexpr int NW = EPT / 4;                 // 32-bit words per slice and thread
+    const int tx = threadIdx.x & 15, h = (threadIdx.x >> 4) & (NH - 1), ty = threadIdx.x / (16 * NH);
     const int e = scale_exponent_b<BITS>(theta[D]);
     const double scale = ldexp(1.0, (BITS == 7 ? 7 : 0) - (e + 1));      // 7 bit: first slice = rint(v * 2^-(e+1) * 2^7), |.| <= 64
     // 8 bit: the kernel is evaluated with the outputscale pre-multiplied by the power of two  scale * 2^(8S)  (exact, commutes
     // with every rounding), so v8 = V-to-be-rounded directly, and alpha is divided by the same power: v8 * al8 == v * al bit for
     // bit and the fused mean sums stay those of the FP64 path.
     const double pre = (BITS == 8) ? scale * (double)(1ull << (8 * S)) : 1.0;
-    const double s = theta[D] * pre;
+    const double s = theta[D] * pre, s3 = s / 3.0;
     const long pitch = plane_rows * (long)Np;
-    double al[8];
+    const int c0 = tx + 16 * EPT * h;                                      // first of the thread's EPT columns (stride 16)
+    double al[EPT];
 #pragma unroll
-    for (int b = 0; b < 8; ++b) al[b] = sal[tx + 16 * b] * (1.0 / pre);
+    for (int b = 0; b < EPT; ++b) al[b] = sal[c0 + 16 * b] * (1.0 / pre);
+    // Only the last train tile can hold columns j >= N (their K* entries must be 0: the padding block of L^-1 is the identity);
+    // the choice is uniform per CTA, so every other CTA runs the copy of the row loop without the per-entry mask.
+    auto rows = [&](auto masked_tag) {
+        constexpr bool MASKED = decltype(masked_tag)::value;
 #pragma unroll 1
-    for (int a = 0; a < 8; ++a) {
-        const int row = ty + 16 * a;
-        double r2[8];
+        for (int a = 0; a < 8 * NH; ++a) {
+            const int row = ty + (16 / NH) * a;
+            double q[EPT];
 #pragma unroll
-        for (int b = 0; b < 8; ++b) r2[b] = 0.0;
-        for (int d = 0; d < D; ++d) {
-            const double xa_ = sa[d * P_LD + row];
+            for (int b = 0; b < EPT; ++b) q[b] = 1e-30;
+#pragma unroll 1
+            for (int d = 0; d < Dp; d += 2) {
+                const double x0 = sa[d * P_LD + row], x1 = sa[(d + 1) * P_LD + row];
 #pragma unroll
-            for (int b = 0; b < 8; ++b) {
-                const double df = xa_ - sb[d * P_LD + tx + 16 * b];
-                r2[b] = fma(df, df, r2[b]);
-            }
-        }
-        const long m = (long)mb * TILE + row;
-        double part = 0.0;
-        uint32_t lo[S], hi[S];
-#pragma unroll
-        for (int q = 0; q < S; ++q) { lo[q] = 0u; hi[q] = 0u; }
-#pragma unroll
-        for (int b = 0; b < 8; ++b) {
-            const long j = (long)jb * TILE + tx + 16 * b;
-            const double v = kernel_value<KIND>(r2[b], (j < N) ? s : 0.0);   // masked by the outputscale: no branch
-            part = fma(v, al[b], part);
-            // byte b of the slice words: selector keeps the other three bytes and takes one byte of the digit word
-            constexpr uint32_t keep = 0x3210u;
-            const uint32_t pos = (uint32_t)(b & 3) * 4;
-            if (BITS == 7) {
-                double r = v * scale;
-#pragma unroll
-                for (int q = 0; q < S; ++q) {
-                    const double qi = rint(r);
-                    r = (r - qi) * 128.0;                            // exact: |r - qi| <= 1/2
-                    const uint32_t w = (uint32_t)__double2int_rn(qi);
-                    const uint32_t sel = (keep & ~(0xFu << pos)) | (4u << pos);
-                    if (b < 4) lo[q] = __byte_perm(lo[q], w, sel); else hi[q] = __byte_perm(hi[q], w, sel);
-                }
-            } else {
-                const unsigned long long dg = balanced_digits_prescaled<S>(v);
-                const uint32_t w0 = (uint32_t)dg, w1 = (uint32_t)(dg >> 32);
-#pragma unroll
-                for (int q = 0; q < S; ++q) {
-                    const int src = S - 1 - q;                       // digit q = byte S-1-q
-                    const uint32_t sel = (keep & ~(0xFu << pos)) | ((uint32_t)(4 + (src & 3)) << pos);
-                    const uint32_t w = src < 4 ? w0 : w1;
-                    if (b < 4) lo[q] = __byte_perm(lo[q], w, sel); else hi[q] = __byte_perm(hi[q], w, sel);
+                for (int b = 0; b < EPT; ++b) {
+                    const double d0 = x0 - sb[d * P_LD + c0 + 16 * b];
+                    const double d1 = x1 - sb[(d + 1) * P_LD + c0 + 16 * b];
+                    q[b] = fma(d0, d0, q[b]);
+                    q[b] = fma(d1, d1, q[b]);
                 }
             }
-        }
-        part += __shfl_xor_sync(0xffffffffu, part, 1);
-        part += __shfl_xor_sync(0xffffffffu, part, 2);
-        part += __shfl_xor_sync(0xffffffffu, part, 4);
-        part += __shfl_xor_sync(0xffffffffu, part, 8);
-        if (tx == 0) smean[row] = part;
-        int8_t* dst = planes + m * Np + (long)jb * TILE + tx * 8;
+            double part = 0.0, part1 = 0.0;
+            uint32_t word[S][NW];
 #pragma unroll
-        for (int q = 0; q < S; ++q) *reinterpret_cast<uint2*>(dst + q * pitch) = make_uint2(lo[q], hi[q]);
-    }
+            for (int k = 0; k < S; ++k)
+#pragma unroll
+                for (int w = 0; w < NW; ++w) word[k][w] = 0u;
+#pragma unroll
+            for (int b = 0; b < EPT; ++b) {
+                const bool in = !MASKED || jb * TILE + c0 + 16 * b < N;
+                const double v = kernel_profile<KIND>(q[b], in ? s : 0.0, in ? s3 : 0.0);   // masked by the outputscale: no branch
+                if (b < 4) part = fma(v, al[b], part); else part1 = fma(v, al[b], part1);
+                // byte b of the slice words: selector keeps the other three bytes and takes one byte of the digit word
+                constexpr uint32_t keep = 0x3210u;
+                const uint32_t pos = (uint32_t)(b & 3) * 4;
+                const int wi = b >> 2;
+                if (BITS == 7) {
+                    double r = v * scale;
+#pragma unroll
+                    for (int k = 0; k < S; ++k) {
+                        const double qi = rint(r);
+                        r = (r - qi) * 128.0;                            // exact: |r - qi| <= 1/2
+                        const uint32_t w = (uint32_t)__double2int_rn(qi);
+                        const uint32_t sel = (keep & ~(0xFu << pos)) | (4u << pos);
+                        word[k][wi] = __byte_perm(word[k][wi], w, sel);
+                    }
+                } else {
+                    // biased digits (V + BIAS in the low mantissa bits of one DADD); the ^ 0x80 of every byte that makes them
+                    // balanced is applied to the assembled slice words below
+                    const unsigned long long dg = (unsigned long long)__double_as_longlong(
+                        v + (6755399441055744.0 + (double)((S == 5) ? 0x8080808080ull : 0x808080808080ull)));
+                    const uint32_t w0 = (uint32_t)dg, w1 = (uint32_t)(dg >> 32);
+#pragma unroll
+                    for (int k = 0; k < S; ++k) {
+                        const int src = S - 1 - k;                       // digit k = byte S-1-k
+                        const uint32_t sel = (keep & ~(0xFu << pos)) | ((uint32_t)(4 + (src & 3)) << pos);
+                        word[k][wi] = __byte_perm(word[k][wi], src < 4 ? w0 : w1, sel);
+                    }
+                }
+            }
+            // same order as the FP64 kernels: (columns 0..63 chain) + (columns 64..127 chain), then the tree over tx
+            if (NH == 2) part += __shfl_xor_sync(0xffffffffu, part, 16); else part += part1;
+            part += __shfl_xor_sync(0xffffffffu, part, 1);
+            part += __shfl_xor_sync(0xffffffffu, part, 2);
+            part += __shfl_xor_sync(0xffffffffu, part, 4);
+            part += __shfl_xor_sync(0xffffffffu, part, 8);
+            if (tx == 0 && h == 0) smean[row] = part;
+            int8_t* dst = planes + ((long)mb * TILE + row) * Np + (long)jb * TILE + tx * 8 + 4 * h;   // 128 contiguous bytes per row
+#pragma unroll
+            for (int k = 0; k < S; ++k) {
+                constexpr uint32_t flip = (BITS == 8) ? 0x80808080u : 0u;
+                if (NW == 1) *reinterpret_cast<uint32_t*>(dst + k * pitch) = word[k][0] ^ flip;
+                else *reinterpret_cast<uint2*>(dst + k * pitch) = make_uint2(word[k][0] ^ flip, word[k][NW - 1] ^ flip);
+            }
+        }
+    };
+    if ((jb + 1) * TILE <= N) rows(std::false_type{}); else rows(std::true_type{});
     __syncthreads();
     if (threadIdx.x < TILE) mean_part[(long)jb * Mc + (long)mb * TILE + threadIdx.x] = smean[threadIdx.x];
 }
@@ -280,22 +316,29 @@ template <int KIND>
 static int launch_kmat_cross_i8(const double* Xs, long m_valid, const double* X, int N, int D, const double* theta,
                                 const double* xa, const double* xr, const double* alpha, int8_t* planes, long plane_rows,
                                 int nslices, int bits, int Np, double* mean_part, int Mc, cudaStream_t st) {
-    const size_t smem = (size_t(2) * D * P_LD + 2 * TILE) * 8;
+    const size_t smem = (size_t(2) * (D + (D & 1)) * P_LD + 2 * TILE) * 8;
     const dim3 grid(Np / TILE, Mc / TILE);
-#define GPX_KX(S_, B_)                                                                                                        \
-    do {                                                                                                                      \
-        if (smem > 48 * 1024)                                                                                                 \
-            cudaFuncSetAttribute(kmat_cross_i8_kernel<KIND, S_, B_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        cudaFuncSetAttribute(kmat_cross_i8_kernel<KIND, S_, B_>, cudaFuncAttributePreferredSharedMemoryCarveout,              \
-                             cudaSharedmemCarveoutMaxShared);                                                                 \
-        kmat_cross_i8_kernel<KIND, S_, B_><<<grid, P_THREADS, smem, st>>>(Xs, m_valid, X, N, D, theta, xa, xr, alpha, planes, \
-                                                                          plane_rows, Np, mean_part, Mc);                     \
+#define GPX_KX2(S_, B_, E_)                                                                                                      \
+    do {                                                                                                                         \
+        if (smem > 48 * 1024)                                                                                                    \
+            cudaFuncSetAttribute(kmat_cross_i8_kernel<KIND, S_, B_, E_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        cudaFuncSetAttribute(kmat_cross_i8_kernel<KIND, S_, B_, E_>, cudaFuncAttributePreferredSharedMemoryCarveout,             \
+                             cudaSharedmemCarveoutMaxShared);                                                                    \
+        kmat_cross_i8_kernel<KIND, S_, B_, E_><<<grid, P_THREADS, smem, st>>>(Xs, m_valid, X, N, D, theta, xa, xr, alpha, planes, \
+                                                                              plane_rows, Np, mean_part, Mc);                    \
     } while (0)
+#define GPX_KX(S_, B_)                          \
+    do {                                        \
+        if (ept == 8) GPX_KX2(S_, B_, 8);       \
+        else GPX_KX2(S_, B_, 4);                \
+    } while (0)
+    static const int ept = [] { const char* e = getenv("GPX_KX_EPT"); return (e && atoi(e) == 8) ? 8 : 4; }();
     if (nslices == 5 && bits == 7) GPX_KX(5, 7);
     else if (nslices == 6 && bits == 7) GPX_KX(6, 7);
     else if (nslices == 5 && bits == 8) GPX_KX(5, 8);
     else if (nslices == 6 && bits == 8) GPX_KX(6, 8);
     else return -8;
+#undef GPX_KX2
 #undef GPX_KX
     GPX_CHECK_LAUNCH();
     return 0;
@@ -317,17 +360,18 @@ predict_mean_kernel(const double* __restrict__ Xs, long m_valid, const double* _
                     const double* __restrict__ bias, double y_mu, double y_sigma, double* __restrict__ out_mean) {
     const long mb = blockIdx.x;
     extern __shared__ double sm[];
-    double* sa = sm;                    // test points (rows m)   [D][P_LD]
-    double* sb = sm + D * P_LD;         // train points (cols j)  [D][P_LD]
-    double* sal = sb + D * P_LD;        // alpha tile [128]
+    const int Dp = D + (D & 1);
+    double* sa = sm;                    // test points (rows m)   [Dp][P_LD]
+    double* sb = sm + Dp * P_LD;        // train points (cols j)  [Dp][P_LD]
+    double* sal = sb + Dp * P_LD;       // alpha tile [128]
     double* smean = sal + TILE;         // [128]
-    stage_coords(sa, Xs, mb * TILE, m_valid, D, theta, xa, xr);
+    stage_coords(sa, Xs, mb * TILE, m_valid, D, theta, xa, xr, coord_scale<KIND>(), Dp);
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    const double s = theta[D];
+    const double s = theta[D], s3 = s / 3.0;
     if (threadIdx.x < TILE) smean[threadIdx.x] = 0.0;      // running sum over the train tiles, owned by the row's tx == 0 lane
     for (int jb = 0; jb < nb; ++jb) {
         __syncthreads();                // previous tile's sb / sal are no longer read (and sa is staged before the first use)
-        stage_coords(sb, X, (long)jb * TILE, N, D, theta, nullptr, nullptr);
+        stage_coords(sb, X, (long)jb * TILE, N, D, theta, nullptr, nullptr, coord_scale<KIND>(), Dp);
         if (threadIdx.x < TILE) sal[threadIdx.x] = alpha[jb * TILE + threadIdx.x];
         __syncthreads();
         double al[8];
@@ -337,23 +381,16 @@ predict_mean_kernel(const double* __restrict__ Xs, long m_valid, const double* _
         for (int a = 0; a < 8; ++a) {           // rolled: one row of 8 kernel evaluations keeps the body inside the I-cache
             const int row = ty + 16 * a;
             double r2[8];
-#pragma unroll
-            for (int b = 0; b < 8; ++b) r2[b] = 0.0;
-            for (int d = 0; d < D; ++d) {
-                const double xa_ = sa[d * P_LD + row];
-#pragma unroll
-                for (int b = 0; b < 8; ++b) {
-                    const double df = xa_ - sb[d * P_LD + tx + 16 * b];
-                    r2[b] = fma(df, df, r2[b]);
-                }
-            }
-            double part = 0.0;
+            row_q(r2, sa, sb, Dp, row, tx);
+            double part = 0.0, part1 = 0.0;      // columns 0..63 / 64..127 as two chains, like kmat_cross_kernel
 #pragma unroll
             for (int b = 0; b < 8; ++b) {
                 const long j = (long)jb * TILE + tx + 16 * b;
-                const double v = kernel_value<KIND>(r2[b], (j < N) ? s : 0.0);   // masked by the outputscale: no branch
-                part = fma(v, al[b], part);
+                const bool in = j < N;
+                const double v = kernel_profile<KIND>(r2[b], in ? s : 0.0, in ? s3 : 0.0);   // masked by the outputscale: no branch
+                if (b < 4) part = fma(v, al[b], part); else part1 = fma(v, al[b], part1);
             }
+            part += part1;
             part += __shfl_xor_sync(0xffffffffu, part, 1);
             part += __shfl_xor_sync(0xffffffffu, part, 2);
             part += __shfl_xor_sync(0xffffffffu, part, 4);
@@ -396,7 +433,7 @@ static int launch_predict_mean(const double* Xs, long M, const double* X, int N,
                                const double* xr, const double* alpha, int Np, const double* prior_mean, const int* feat_idx,
                                int n_feat, int degree, const double* weights, const double* bias, double y_mu, double y_sigma,
                                double* out_mean, cudaStream_t st) {
-    const size_t smem = (size_t(2) * D * P_LD + 2 * TILE) * 8;
+    const size_t smem = (size_t(2) * (D + (D & 1)) * P_LD + 2 * TILE) * 8;
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(predict_mean_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const long blocks = (M + TILE - 1) / TILE;

@@ -13,7 +13,8 @@
 //   exp_neg(y) = exp(-y), y >= 0 (clamped at 700):  n = rint(-y log2 e) by the 1.5*2^52 shift, r = -y - n ln2 in two FMAs
 //       (ln2_hi has 27 trailing zero bits: n ln2_hi is exact), exp(r) = 1 + r + r^2 q(r) with q the degree-9 interpolant of
 //       (e^r - 1 - r)/r^2 at the Chebyshev nodes of |r| <= 1.001 ln2/2 (max relative error of the polynomial 1.6e-17,
-//       coefficients from tools/fit_exp_poly.py), 2^n added into the exponent field (result >= 2^-1011: always normal).
+//       coefficients from tools/fit_exp_poly.py; evaluated as two interleaved Horner chains in r^2), 2^n added into the exponent
+//       field (result >= 2^-1011: always normal).
 //
 // The functions are __host__ __device__ so that tests/test_math_host.py can sweep them against libm on the CPU (the host
 // build seeds the square root with 1/sqrtf and reads the coefficients from a plain array).
@@ -73,18 +74,40 @@ __host__ __device__ __forceinline__ double sqrt_pos(double x) {
     return fma(res, hi_add(y1, -0x100000), g);      // y1 / 2 on the integer pipe
 }
 
+// min(y, ~700) for y >= 0 on the integer pipe: the upper words of non-negative doubles order like the doubles themselves, so
+// clamping the upper word at that of 700.0 (0x4085E000) leaves y untouched below 700 and maps anything above to
+// 700 + (low word) * 2^-43 <= 700.0005 (one IMNMX instead of DSETP + 2 SEL).  NaN / negative inputs are the caller's business.
+__host__ __device__ __forceinline__ double clamp700(double y) {
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(min(__double2hiint(y), 0x4085E000), __double2loint(y));
+#else
+    uint64_t u;
+    std::memcpy(&u, &y, 8);
+    uint32_t hi = (uint32_t)(u >> 32);
+    if ((int32_t)hi > 0x4085E000) hi = 0x4085E000u;
+    u = ((uint64_t)hi << 32) | (u & 0xffffffffull);
+    std::memcpy(&y, &u, 8);
+    return y;
+#endif
+}
+
 __host__ __device__ __forceinline__ double exp_neg(double y) {
-    y = fmin(y, 700.0);
+    y = clamp700(y);
     const double magic = GPX_MC(13);
     const double t = fma(-y, GPX_MC(10), magic);
     const double nd = t - magic;
     double r = fma(nd, -GPX_MC(11), -y);
     r = fma(nd, -GPX_MC(12), r);
-    double p = GPX_MC(9);
+    // exp(r) = 1 + (r + r^2 q(r)),  q = qe(r^2) + r qo(r^2): two independent Horner chains of four FMAs (depth 8 instead of 11, so a
+    // thread that runs out of registers for interleaving several entries still keeps the FP64 pipe fed)
+    const double r2 = r * r;
+    double qe = GPX_MC(8), qo = GPX_MC(9);
 #pragma unroll
-    for (int i = 8; i >= 0; --i) p = fma(p, r, GPX_MC(i));
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
+    for (int i = 3; i >= 0; --i) {
+        qe = fma(qe, r2, GPX_MC(2 * i));
+        qo = fma(qo, r2, GPX_MC(2 * i + 1));
+    }
+    double p = fma(fma(qo, r, qe), r2, r) + 1.0;
 #if defined(__CUDA_ARCH__)
     const int n = __double2loint(t);
 #else

