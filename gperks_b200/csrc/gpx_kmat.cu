@@ -59,6 +59,30 @@ __device__ __forceinline__ void row_q(double (&q)[8], const double* sa, const do
     }
 }
 
+// Two rows (row0 and row0 + 16) per pass: every train coordinate read from shared memory feeds two entries.  The distance loop
+// is bound by shared-memory wavefronts (an LDS.64 delivers 16 lanes' worth per wavefront), not by the FP64 pipe: 1.25 wavefronts
+// per entry and dimension here against 2.25 for one row per pass.
+__device__ __forceinline__ void rows_q2(double (&q)[2][8], const double* sa, const double* sb, int Dp, int row0, int tx) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) q[r][b] = 1e-30;
+#pragma unroll 1
+    for (int d = 0; d < Dp; d += 2) {
+        const double x00 = sa[d * P_LD + row0], x01 = sa[(d + 1) * P_LD + row0];
+        const double x10 = sa[d * P_LD + row0 + 16], x11 = sa[(d + 1) * P_LD + row0 + 16];
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const double y0 = sb[d * P_LD + tx + 16 * b], y1 = sb[(d + 1) * P_LD + tx + 16 * b];
+            const double d00 = x00 - y0, d01 = x01 - y1, d10 = x10 - y0, d11 = x11 - y1;
+            q[0][b] = fma(d00, d00, q[0][b]);
+            q[0][b] = fma(d01, d01, q[0][b]);
+            q[1][b] = fma(d10, d10, q[1][b]);
+            q[1][b] = fma(d11, d11, q[1][b]);
+        }
+    }
+}
+
 // r2[a][b] for rows ty+16a (from sa) and cols tx+16b (from sb)
 __device__ __forceinline__ void tile_r2(double (&r2)[8][8], const double* sa, const double* sb, int D, int ty, int tx) {
 #pragma unroll
@@ -100,10 +124,13 @@ __global__ void __launch_bounds__(P_THREADS, 2) kmat_sym_kernel(const double* __
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const double s = theta[D], noise = theta[D + 1], s3 = s / 3.0;
 #pragma unroll 1
-    for (int a = 0; a < 8; ++a) {
-        const int row = ty + 16 * a;
-        double q[8];
-        row_q(q, sa, sb, Dp, row, tx);
+    for (int a0 = 0; a0 < 8; a0 += 2) {           // two rows per pass (rows_q2), evaluated one after the other
+        double qq[2][8];
+        rows_q2(qq, sa, sb, Dp, ty + 16 * a0, tx);
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+        const int row = ty + 16 * (a0 + rr);
+        const double (&q)[8] = qq[rr];
         const long i = (long)bi * TILE + row;
 #pragma unroll
         for (int b = 0; b < 8; ++b) {
@@ -112,6 +139,7 @@ __global__ void __launch_bounds__(P_THREADS, 2) kmat_sym_kernel(const double* __
             double v = kernel_profile<KIND>(q[b], in ? s : 0.0, in ? s3 : 0.0);   // branch-free; the padding block is the identity
             if (i == j) v += in ? noise : 1.0;
             K[i * Np + j] = v;
+        }
         }
     }
 }
@@ -147,10 +175,13 @@ kmat_cross_kernel(const double* __restrict__ Xs, long m_valid, const double* __r
 #pragma unroll
     for (int b = 0; b < 8; ++b) al[b] = sal[tx + 16 * b];
 #pragma unroll 1
-    for (int a = 0; a < 8; ++a) {
-        const int row = ty + 16 * a;
-        double r2[8];
-        row_q(r2, sa, sb, Dp, row, tx);
+    for (int a0 = 0; a0 < 8; a0 += 2) {           // two rows per pass (rows_q2), evaluated one after the other
+        double qq[2][8];
+        rows_q2(qq, sa, sb, Dp, ty + 16 * a0, tx);
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+        const int row = ty + 16 * (a0 + rr);
+        const double (&r2)[8] = qq[rr];
         const long m = (long)mb * TILE + row;
         double part = 0.0, part1 = 0.0;          // columns 0..63 / 64..127 as two chains (the order gpx_kmat_cross_i8 sums in)
 #pragma unroll
@@ -179,6 +210,7 @@ kmat_cross_kernel(const double* __restrict__ Xs, long m_valid, const double* __r
         part += __shfl_xor_sync(0xffffffffu, part, 4);
         part += __shfl_xor_sync(0xffffffffu, part, 8);
         if (tx == 0) smean[row] = part;
+        }
     }
     __syncthreads();
     if (threadIdx.x < TILE) mean_part[(long)jb * Mc + (long)mb * TILE + threadIdx.x] = smean[threadIdx.x];
@@ -198,7 +230,7 @@ kmat_cross_kernel(const double* __restrict__ Xs, long m_valid, const double* __r
 // row segment, no shared-memory staging.  Shared memory holds only the 2 x D coordinate rows (sized by D, not MAXD), so a CTA of this
 // kernel fits beside the 183 KB CTA of the integer tensor-core kernel working on the previous chunk.
 template <int KIND, int S, int BITS, int EPT>
-__global__ void __launch_bounds__(P_THREADS, EPT == 4 ? 3 : 2)
+__global__ void __launch_bounds__(P_THREADS, 2)
 kmat_cross_i8_kernel(const double* __restrict__ Xs, long m_valid, const double* __restrict__ X, int N, int D,
                      const double* __restrict__ theta, const double* __restrict__ xa, const double* __restrict__ xr,
                      const double* __restrict__ alpha, int8_t* __restrict__ planes, long plane_rows, int Np,
@@ -235,23 +267,40 @@ kmat_cross_i8_kernel(const double* __restrict__ Xs, long m_valid, const double* 
     // the choice is uniform per CTA, so every other CTA runs the copy of the row loop without the per-entry mask.
     auto rows = [&](auto masked_tag) {
         constexpr bool MASKED = decltype(masked_tag)::value;
+        // R rows per pass share every train coordinate read from shared memory: the distance loop is bound by shared-memory
+        // wavefronts, not by the FP64 pipe (an LDS.64 delivers 16 lanes' worth per wavefront; with one row per pass it cost
+        // 2.25 wavefronts per entry and dimension = 9 SM cycles against 4 FP64 pipe cycles -- measured 10 cycles per dimension)
+        constexpr int R = (EPT == 4) ? 4 : 2, RSTEP = 16 / NH;
 #pragma unroll 1
-        for (int a = 0; a < 8 * NH; ++a) {
-            const int row = ty + (16 / NH) * a;
-            double q[EPT];
+        for (int a0 = 0; a0 < 8 * NH; a0 += R) {
+            double qq[R][EPT];
 #pragma unroll
-            for (int b = 0; b < EPT; ++b) q[b] = 1e-30;
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int b = 0; b < EPT; ++b) qq[r][b] = 1e-30;
 #pragma unroll 1
             for (int d = 0; d < Dp; d += 2) {
-                const double x0 = sa[d * P_LD + row], x1 = sa[(d + 1) * P_LD + row];
+                double x0[R], x1[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    x0[r] = sa[d * P_LD + ty + RSTEP * (a0 + r)];
+                    x1[r] = sa[(d + 1) * P_LD + ty + RSTEP * (a0 + r)];
+                }
 #pragma unroll
                 for (int b = 0; b < EPT; ++b) {
-                    const double d0 = x0 - sb[d * P_LD + c0 + 16 * b];
-                    const double d1 = x1 - sb[(d + 1) * P_LD + c0 + 16 * b];
-                    q[b] = fma(d0, d0, q[b]);
-                    q[b] = fma(d1, d1, q[b]);
+                    const double y0 = sb[d * P_LD + c0 + 16 * b], y1 = sb[(d + 1) * P_LD + c0 + 16 * b];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const double d0 = x0[r] - y0, d1 = x1[r] - y1;
+                        qq[r][b] = fma(d0, d0, qq[r][b]);
+                        qq[r][b] = fma(d1, d1, qq[r][b]);
+                    }
                 }
             }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+            const int row = ty + RSTEP * (a0 + r);
+            const double (&q)[EPT] = qq[r];
             double part = 0.0, part1 = 0.0;
             uint32_t word[S][NW];
 #pragma unroll
@@ -305,6 +354,7 @@ kmat_cross_i8_kernel(const double* __restrict__ Xs, long m_valid, const double* 
                 if (NW == 1) *reinterpret_cast<uint32_t*>(dst + k * pitch) = word[k][0] ^ flip;
                 else *reinterpret_cast<uint2*>(dst + k * pitch) = make_uint2(word[k][0] ^ flip, word[k][NW - 1] ^ flip);
             }
+            }
         }
     };
     if ((jb + 1) * TILE <= N) rows(std::false_type{}); else rows(std::true_type{});
@@ -332,7 +382,7 @@ static int launch_kmat_cross_i8(const double* Xs, long m_valid, const double* X,
         if (ept == 8) GPX_KX2(S_, B_, 8);       \
         else GPX_KX2(S_, B_, 4);                \
     } while (0)
-    static const int ept = [] { const char* e = getenv("GPX_KX_EPT"); return (e && atoi(e) == 8) ? 8 : 4; }();
+    static const int ept = [] { const char* e = getenv("GPX_KX_EPT"); return (e && atoi(e) == 4) ? 4 : 8; }();
     if (nslices == 5 && bits == 7) GPX_KX(5, 7);
     else if (nslices == 6 && bits == 7) GPX_KX(6, 7);
     else if (nslices == 5 && bits == 8) GPX_KX(5, 8);
@@ -378,10 +428,13 @@ predict_mean_kernel(const double* __restrict__ Xs, long m_valid, const double* _
 #pragma unroll
         for (int b = 0; b < 8; ++b) al[b] = sal[tx + 16 * b];
 #pragma unroll 1
-        for (int a = 0; a < 8; ++a) {           // rolled: one row of 8 kernel evaluations keeps the body inside the I-cache
-            const int row = ty + 16 * a;
-            double r2[8];
-            row_q(r2, sa, sb, Dp, row, tx);
+        for (int a0 = 0; a0 < 8; a0 += 2) {           // two rows per pass (rows_q2), evaluated one after the other
+            double qq[2][8];
+            rows_q2(qq, sa, sb, Dp, ty + 16 * a0, tx);
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+            const int row = ty + 16 * (a0 + rr);
+            const double (&r2)[8] = qq[rr];
             double part = 0.0, part1 = 0.0;      // columns 0..63 / 64..127 as two chains, like kmat_cross_kernel
 #pragma unroll
             for (int b = 0; b < 8; ++b) {
@@ -396,6 +449,7 @@ predict_mean_kernel(const double* __restrict__ Xs, long m_valid, const double* _
             part += __shfl_xor_sync(0xffffffffu, part, 4);
             part += __shfl_xor_sync(0xffffffffu, part, 8);
             if (tx == 0) smean[row] += part;
+            }
         }
     }
     __syncthreads();
