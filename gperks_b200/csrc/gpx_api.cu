@@ -8,7 +8,8 @@ int kmat_cross(const double*, long, const double*, int, int, const double*, cons
                const double*, double*, int, double*, int, cudaStream_t);
 int mll_grad(const double*, int, int, const double*, int, const double*, int, const double*, double*, double*,
              cudaStream_t);
-int potrf(double*, int, int, double*, double*, double*, int*, cudaStream_t);
+int potrf(double*, int, int, double*, double*, double*, int*, cudaStream_t, void*, size_t);
+size_t potrf_i8_workspace_bytes(int);
 int trtri(const double*, double*, const double*, double*, int, cudaStream_t);
 int lauum(const double*, const double*, double*, int, cudaStream_t);
 int solve_alpha(const double*, const double*, int, const double*, double*, double*, cudaStream_t);
@@ -97,7 +98,7 @@ using namespace gpx;
 
 extern "C" {
 
-int gpx_version(void) { return 200; }
+int gpx_version(void) { return 201; }
 int gpx_padded(int n) { return round_up(n < 1 ? 1 : n, TILE); }
 int gpx_max_dim(void) { return MAXD; }
 
@@ -124,7 +125,17 @@ int gpx_kmat_cross(const double* Xs, long m_valid, const double* X, int N, int D
 int gpx_potrf(double* K, int Np, int N, double* S, double* DT, double* logdet_blk, int* info, void* stream) {
     if (!K || !S || !DT || !logdet_blk || !info) return -1;
     if (check_np(N, Np)) return -2;
-    return potrf(K, Np, N, S, DT, logdet_blk, info, ST(stream));
+    return potrf(K, Np, N, S, DT, logdet_blk, info, ST(stream), nullptr, 0);
+}
+
+size_t gpx_potrf_i8_workspace_bytes(int Np) { return potrf_i8_workspace_bytes(Np); }
+
+int gpx_potrf_i8(double* K, int Np, int N, double* S, double* DT, double* logdet_blk, int* info, void* workspace,
+                 size_t workspace_bytes, void* stream) {
+    if (!K || !S || !DT || !logdet_blk || !info || !workspace) return -1;
+    if (check_np(N, Np)) return -2;
+    if (workspace_bytes < potrf_i8_workspace_bytes(Np)) return -7;
+    return potrf(K, Np, N, S, DT, logdet_blk, info, ST(stream), workspace, workspace_bytes);
 }
 
 int gpx_trtri(const double* L, double* S, const double* DT, double* W, int Np, void* stream) {

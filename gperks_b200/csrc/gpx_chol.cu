@@ -1291,7 +1291,15 @@ static int use_lookahead() {
 // Right-looking with a one-panel look-ahead: after panel p, the next block column is updated on the caller's
 // stream (critical path: diag p+1, panel p+1), while the rest of the trailing matrix is updated on a helper
 // stream.
-int potrf(double* K, int Np, int N, double* S, double* DT, double* logdet_blk, int* info, cudaStream_t st_caller) {
+// gpx_i8.cu: the bulk trailing update of one outer block on the integer tensor cores
+int potrf_trailing_i8(double* K, int Np, int c0, int c1, int r0, void* workspace, size_t workspace_bytes, cudaStream_t st);
+
+// i8_ws != null (training mode, gpx_potrf_i8): the bulk trailing updates of the two-level schedule -- everything right of the
+// look-ahead columns, once per outer block -- run as sliced-integer products (six 8-bit digits per operand, exact int32 sums)
+// instead of FP64 DMMA; the panels, the in-block updates, the look-ahead columns and the chain-bound tail stay FP64.  Outer
+// blocks are then OB = 4 panels wide by default (K = 512 per integer product; 3, 6 and 8 measured within 4 % of it at Np = 8192).
+int potrf(double* K, int Np, int N, double* S, double* DT, double* logdet_blk, int* info, cudaStream_t st_caller, void* i8_ws,
+          size_t i8_bytes) {
     set_gemm_attrs();
     cudaStream_t st = st_caller;
     const int nb = Np / TILE;
@@ -1355,7 +1363,9 @@ int potrf(double* K, int Np, int N, double* S, double* DT, double* logdet_blk, i
     static int ob_env = -1, sw_env = -1;
     if (ob_env < 0) { const char* e = getenv("GPX_POTRF_OB"); ob_env = (e && e[0] >= '1' && e[0] <= '8') ? e[0] - '0' : 0; }
     if (sw_env < 0) { const char* e = getenv("GPX_POTRF_SWITCH"); sw_env = e ? atoi(e) : 32; }
-    const int OB = ob_env ? ob_env : (nb >= 96 ? 4 : 3);
+    static int ob8_env = -1;
+    if (ob8_env < 0) { const char* e = getenv("GPX_POTRF_OB_I8"); ob8_env = (e && e[0] >= '1' && e[0] <= '8') ? e[0] - '0' : 0; }
+    const int OB = i8_ws != nullptr ? (ob8_env ? ob8_env : 4) : (ob_env ? ob_env : (nb >= 96 ? 4 : 3));
     int p_start = 0;
     if (tma && la != nullptr && st != st_caller && OB >= 2 && nb > sw_env) {
         // Two-level schedule.  Panels are still 128 wide (diag + panel on the critical path), but the bulk of the
@@ -1388,8 +1398,13 @@ int potrf(double* K, int Np, int N, double* S, double* DT, double* logdet_blk, i
             // the look-ahead columns were last written by the helper's previous outer update
             if (pending) cudaStreamWaitEvent(st, la->ev_side[(q_idx - 1) & 1], 0);
             if (rest > 0) {
-                potrf_trailing_tma_kernel<<<dim3(rest, rest), GT_THREADS, GT_SMEM_BYTES, la->side>>>(tmK, K, Np, q, qe + la_cols,
-                                                                                                 qe + la_cols, kp);
+                if (i8_ws != nullptr) {
+                    const int rc8 = potrf_trailing_i8(K, Np, q * TILE, qe * TILE, (qe + la_cols) * TILE, i8_ws, i8_bytes, la->side);
+                    if (rc8) return rc8;
+                } else {
+                    potrf_trailing_tma_kernel<<<dim3(rest, rest), GT_THREADS, GT_SMEM_BYTES, la->side>>>(tmK, K, Np, q, qe + la_cols,
+                                                                                                     qe + la_cols, kp);
+                }
                 cudaEventRecord(la->ev_side[q_idx & 1], la->side);
                 pending = true;
             } else {

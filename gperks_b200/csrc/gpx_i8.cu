@@ -712,6 +712,7 @@ struct I8Gemm {
     int m_row0, m_col0;         // mirror C2[m_row0 + j][m_col0 + i]; m_row0 < 0: none
     int tri;                    // 1: only the N tiles of the first mi + 1 pairs exist (tiles on or below the block diagonal)
     double sign;
+    int accumulate;             // 1: C += sign * product (the Cholesky trailing update), 0: C = sign * product
 };
 
 template <int S, int BITS>
@@ -734,7 +735,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     const int cid = (int)(blockIdx.x >> 1);
     const int mi = cid / pairs, nj = 2 * (cid - mi * pairs) + (int)crank;
     if (g.tri && (nj >> 1) > mi) return;          // both CTAs of the pair leave together, before any barrier exists
-    const int kstart = g.k_from ? g.k_base + mi * I_M : g.k_base;
+    const int kstart = g.k_from == 1 ? g.k_base + mi * I_M : g.k_base;            // k_from = 2: the same range [k_base, k_end) for every tile
     const int kend = g.k_from ? g.k_end : g.k_base + (mi + 1) * I_M;
     const int nk = (kend - kstart) / BKB;
     const int arow = g.a_row0 + mi * I_M, brow = g.b_row0 + nj * I_N;
@@ -825,6 +826,14 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
 #pragma unroll
         for (int j = 0; j < 32; ++j) t[j] *= sinv[half * 32 + j] * si;
         double* dst = Cout + (long)(g.c_row0 + mi * I_M + r) * Np + g.c_col0 + nj * I_N + half * 32;
+        if (g.accumulate) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+                const double2 c = *reinterpret_cast<const double2*>(dst + j);
+                t[j] += c.x;
+                t[j + 1] += c.y;
+            }
+        }
 #pragma unroll
         for (int j = 0; j < 32; j += 2) *reinterpret_cast<double2*>(dst + j) = make_double2(t[j], t[j + 1]);
         if (g.m_row0 >= 0) {       // transposed copy: consecutive lanes write consecutive doubles of one mirror row
@@ -952,7 +961,7 @@ int lauum_i8(const double* Smat, const double* DT, double* W, int Np, int nslice
     double* inv_scale = reinterpret_cast<double*>(workspace);
     int8_t* planes = reinterpret_cast<int8_t*>(inv_scale + Np);
     const int nbt = Np / I_M;
-    const I8Gemm g = {2 * nbt, 0, 0, 0, Np, 1, 0, 0, -1, 0, 1, 1.0};
+    const I8Gemm g = {2 * nbt, 0, 0, 0, Np, 1, 0, 0, -1, 0, 1, 1.0, 0};
     if (nslices == 5) {
         slice_i8_rows_kernel<5, 7><<<Np, 256, 0, st>>>(Smat, Np, DT, 0, 0, Np, 1, 0, Np, planes, inv_scale);
         return launch_gemm_i8<5, 7>(planes, planes, Np, inv_scale, inv_scale, W, nullptr, g, nbt, st);
@@ -977,14 +986,35 @@ static int trtri_i8_merge_t(const double* L, double* Smat, const double* DT, dou
     // step 1: M side = columns of A^-1 as rows (left segment, k from the row to the end of the segment), N side = L[right, left]
     slice_i8_rows_kernel<S, BITS><<<h * TILE, 256, 0, st>>>(Smat, Np, DT, l0, 0, r0, 1, 0, Np, PA, sA);
     slice_i8_rows_kernel<S, BITS><<<hr * TILE, 256, 0, st>>>(L, Np, nullptr, r0, l0, r0, 0, 0, Np, PB, sB);
-    I8Gemm g1 = {2 * hr, l0, r0, l0, r0, 1, l0, r0, -1, 0, 0, 1.0};
+    I8Gemm g1 = {2 * hr, l0, r0, l0, r0, 1, l0, r0, -1, 0, 0, 1.0, 0};
     int rc = launch_gemm_i8<S, BITS>(PA, PB, Np, sA, sB, W, nullptr, g1, h, st);
     if (rc) return rc;
     // step 2: M side = rows of C^-1 (right segment, k from the segment start to the row), N side = T^T = W[left, right]
     slice_i8_rows_kernel<S, BITS><<<hr * TILE, 256, 0, st>>>(Smat, Np, nullptr, r0, r0, 0, 0, 1, Np, PA, sA);
     slice_i8_rows_kernel<S, BITS><<<h * TILE, 256, 0, st>>>(W, Np, nullptr, l0, r0, r1, 0, 0, Np, PB, sB);
-    I8Gemm g2 = {2 * h, r0, l0, r0, r1, 0, r0, l0, l0, r0, 0, -1.0};
+    I8Gemm g2 = {2 * h, r0, l0, r0, r1, 0, r0, l0, l0, r0, 0, -1.0, 0};
     rc = launch_gemm_i8<S, BITS>(PA, PB, Np, sA, sB, Smat, Smat, g2, hr, st);
+    if (rc) return rc;
+    GPX_CHECK_LAUNCH();
+    return 0;
+}
+
+// ---- Cholesky bulk trailing update on the integer tensor cores (training mode; gpx_chol.cu: potrf) ----------------------
+//   K[i][j] -= sum_{k in [c0, c1)} K[i][k] K[j][k]      for the 128-tiles on or below the block diagonal of rows/columns >= r0
+// The rows of the finished panels [c0, c1) are sliced into six 8-bit digits (48 bits, one power-of-two scale per row; the sums
+// run over c1 - c0 <= 1024 entries, far inside the int32 range at any Np) and multiplied with themselves.
+size_t potrf_i8_workspace_bytes(int Np) { return (size_t)6 * Np * Np + (size_t)Np * 8; }
+
+int potrf_trailing_i8(double* K, int Np, int c0, int c1, int r0, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    constexpr int S = 6, BITS = 8;
+    if (Np % TILE || r0 % TILE || c0 % TILE || c1 % TILE || c1 > r0 || r0 >= Np) return -4;
+    if (workspace_bytes < potrf_i8_workspace_bytes(Np)) return -7;
+    double* sA = reinterpret_cast<double*>(workspace);
+    int8_t* PA = reinterpret_cast<int8_t*>(sA + Np);
+    slice_i8_rows_kernel<S, BITS><<<Np - r0, 256, 0, st>>>(K, Np, nullptr, r0, c0, c1, 0, 0, Np, PA, sA);
+    const int nbt = (Np - r0) / I_M;
+    const I8Gemm g = {2 * nbt, r0, r0, c0, c1, 2, r0, r0, -1, 0, 1, -1.0, 1};
+    const int rc = launch_gemm_i8<S, BITS>(PA, PA, Np, sA, sA, K, nullptr, g, nbt, st);
     if (rc) return rc;
     GPX_CHECK_LAUNCH();
     return 0;

@@ -122,13 +122,20 @@ class ExactGPEngine:
         # (experiments); GPX_TRTRI=fp64 disables it.
         self.trtri_i8 = bool(self.lauum_slices and self.Np >= 2048 and os.environ.get("GPX_TRTRI", "") == "i8")
         self._trtri_i8_capable = bool(self.lauum_slices and self.Np >= 2048 and os.environ.get("GPX_TRTRI", "") != "fp64")
-        self.approx_inverse_ok = False       # True inside a training loop: factorize() may use the integer inverse
+        # Inside the same loops the Cholesky factorisation itself sends its bulk trailing updates through the integer tensor
+        # cores (gpx_potrf_i8: six 8-bit digits per operand, L to ~1e-12 of its scale); GPX_POTRF=fp64 keeps them on FP64 DMMA.
+        # Needs the two-level schedule (more than 32 block columns) to have any bulk update at all.
+        self._potrf_i8_capable = bool(self._trtri_i8_capable and self.Np > 32 * 128 and os.environ.get("GPX_POTRF", "") != "fp64")
+        self.approx_inverse_ok = False       # True inside a training loop: factorize() may use the integer inverse / Cholesky
         self.inverse_exact = True            # False while S / alpha / out come from the integer inverse
+        self.chol_exact = True               # False while L itself comes from gpx_potrf_i8
         self._lauum_ws: Optional[torch.Tensor] = None
         if self.lauum_slices:       # one workspace for both, allocated up front: gradients() may run inside a CUDA-graph capture
             nbytes = int(self.lib.gpx_lauum_i8_workspace_bytes(self.Np, self.lauum_slices))
             if self._trtri_i8_capable:
                 nbytes = max(nbytes, int(self.lib.gpx_trtri_i8_workspace_bytes(self.Np)))
+            if self._potrf_i8_capable:
+                nbytes = max(nbytes, int(self.lib.gpx_potrf_i8_workspace_bytes(self.Np)))
             self._lauum_ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         self.S_i8: Optional[torch.Tensor] = None      # [slices, Np, Np] int8 planes of L^-1
         self.S_i8_inv_scale: Optional[torch.Tensor] = None   # [Np] inverse power-of-two row scales
@@ -153,6 +160,11 @@ class ExactGPEngine:
             self.r[: self.N].copy_(resid.detach().reshape(-1))
             p = nv.ptr
             jitter = 0.0
+            potrf_i8 = self._potrf_i8_capable and self.approx_inverse_ok and not self.trtri_i8
+            if potrf_i8:
+                need = int(self.lib.gpx_potrf_i8_workspace_bytes(self.Np))
+                if self._lauum_ws is None or self._lauum_ws.numel() < need:
+                    self._lauum_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
             for attempt in range(4):
                 if attempt > 0:
                     new_jitter = 1e-8 * 10 ** (attempt - 1)
@@ -161,8 +173,12 @@ class ExactGPEngine:
                     jitter = new_jitter
                 self._launch("gpx_kmat_sym", p(self.X), self.N, self.D, p(self.theta), self.kind, p(self.K),
                              self.Np, st)
-                self._launch("gpx_potrf", p(self.K), self.Np, self.N, p(self.S), p(self.DT), p(self.logdet_blk),
-                             p(self.info), st)
+                if potrf_i8:
+                    self._launch("gpx_potrf_i8", p(self.K), self.Np, self.N, p(self.S), p(self.DT), p(self.logdet_blk),
+                                 p(self.info), p(self._lauum_ws), self._lauum_ws.numel(), st)
+                else:
+                    self._launch("gpx_potrf", p(self.K), self.Np, self.N, p(self.S), p(self.DT), p(self.logdet_blk),
+                                 p(self.info), st)
                 if not check:
                     break
                 info = int(self.info.item())       # the one host sync of a factorisation
@@ -187,11 +203,23 @@ class ExactGPEngine:
         self.factor_key = key
         self._mark_factorized()
         self.inverse_exact = not (use_i8 and not self.trtri_i8)      # a forced integer inverse (GPX_TRTRI=i8) is never completed
+        self.chol_exact = not potrf_i8
 
     def ensure_exact_inverse(self) -> None:
         """Completes factors whose inverse came from the integer tensor cores (training loop) with the FP64 inverse: L is still in
         ``K``, so only trtri, alpha and the loss are redone (~40 % of a factorisation); every derived cache is dropped."""
         if self.inverse_exact or not self.factored:
+            return
+        if not self.chol_exact:
+            # L itself came from the integer tensor cores: the whole factorisation is redone in FP64 for the same inputs
+            ok, self.approx_inverse_ok = self.approx_inverse_ok, False
+            try:
+                nf = self.n_factorizations
+                self.factorize(self.theta_in.clone(), self.r[: self.N].clone(), key=self.factor_key)
+                self.n_factorizations = nf       # same factorisation, new version of its derived quantities
+            finally:
+                self.approx_inverse_ok = ok
+            self.n_inverse_refreshes = getattr(self, "n_inverse_refreshes", 0) + 1
             return
         with torch.cuda.device(self.device):
             st, p = nv.stream_ptr(), nv.ptr

@@ -174,6 +174,16 @@ int gpx_trmm_sumsq_i8(const signed char* Ls, const double* inv_scale, int Np, co
  * with a store epilogue (negate, transposed mirror).  Entries of L^-1 agree with gpx_trtri to ~1e-11 of their row/column scale.
  * bits = 7: Np <= 32768; bits = 8 (balanced radix-256 digits, 48 bits per operand, ~64 x finer): Np <= 16384.
  * replaces: the same call sites as gpx_trtri. */
+/* gpx_potrf_i8: gpx_potrf for training loops.  Same schedule, same outputs; the bulk trailing updates (everything right of the
+ * look-ahead columns, once per outer block of 4 panels -- ~70 % of the FLOPs at Np = 8192) run on the integer tensor cores:
+ * the finished panel rows are sliced into six 8-bit digits with one power-of-two scale per row (workspace) and
+ * K[i][j] -= sum_k L[i][k] L[j][k] is formed by the kind::i8 NT GEMM kernel with an accumulate epilogue; int32 sums are exact
+ * (at most 512 terms), so every update carries ~2^-46 of sqrt(K_ii K_jj), against ~2^-52 sqrt(512) for FP64 DMMA.  Panels,
+ * diagonal blocks, look-ahead columns and the chain-bound tail (last 32 block columns) are the FP64 kernels of gpx_potrf.
+ * replaces: the same call sites as gpx_potrf, inside GPEmulator.train / train_auto loops only. */
+size_t gpx_potrf_i8_workspace_bytes(int Np);
+int gpx_potrf_i8(double* K, int Np, int N, double* S, double* DT, double* logdet_blk, int* info, void* workspace,
+                 size_t workspace_bytes, void* stream);
 size_t gpx_trtri_i8_workspace_bytes(int Np);
 int gpx_trtri_i8(const double* L, double* S, const double* DT, double* W, int Np, int bits, void* workspace, size_t workspace_bytes,
                  void* stream);

@@ -751,7 +751,7 @@ def test_int8_trtri_opt_in_accuracy(dev, N):
     np.testing.assert_allclose(s8.cpu().numpy(), s64.cpu().numpy(), rtol=1e-4)
 
 
-@pytest.mark.parametrize("N", [2048, 4300])
+@pytest.mark.parametrize("N", [2048, 4300, 6100])
 def test_training_mode_inverse_is_completed_before_predictions(dev, N):
     """Inside a training loop (``approx_inverse_ok``) the merge levels of L^-1 run on the integer tensor cores (six 8-bit slices):
     loss and gradients stay within 1e-9 / 1e-7 of the all-FP64 evaluation, and the first prediction after the loop completes the
@@ -760,11 +760,17 @@ def test_training_mode_inverse_is_completed_before_predictions(dev, N):
     eng = _engine(dev, X, y, O.KIND_MATERN52, ls, s, 1e-2, w, b)
     assert eng.inverse_exact and eng._trtri_i8_capable
     S64, alpha64, loss64 = eng.S.clone(), eng.alpha.clone(), float(eng.loss)
+    L64 = eng.chol().clone()
     g64 = eng.gradients().clone()
     m64, s64 = eng.predict(Xs.to(dev), precision="fp64")
     eng.approx_inverse_ok = True
     eng.factorize(eng.theta_in.clone(), eng.r[:N].clone())
     assert not eng.inverse_exact
+    # above 32 block columns the Cholesky factorisation itself runs its bulk trailing updates on the integer tensor cores
+    # (gpx_potrf_i8, six 8-bit digits): L within 1e-10 of its largest entry (measured 3e-12 to 1.2e-11), and flagged so that it is redone before predictions
+    assert eng.chol_exact == (eng.Np <= 4096)
+    errL = float((eng.chol() - L64).abs().max() / L64.abs().max())
+    assert (errL == 0.0) if eng.chol_exact else (0 < errL < 1e-10), errL
     g8 = eng.gradients().clone()
     blk = torch.arange(eng.Np, device=dev) // 128
     offdiag = blk.view(-1, 1) != blk.view(1, -1)
@@ -778,7 +784,8 @@ def test_training_mode_inverse_is_completed_before_predictions(dev, N):
     np.testing.assert_allclose(m8.cpu().numpy(), m64.cpu().numpy(), rtol=0, atol=1e-7 * float(m64.abs().max()))
     eng.approx_inverse_ok = False                                                # the loop is over
     m2, s2 = eng.predict(Xs.to(dev), precision="fp64")
-    assert eng.inverse_exact and torch.equal(eng.S, S64) and torch.equal(eng.alpha, alpha64) and float(eng.loss) == loss64
+    assert eng.inverse_exact and eng.chol_exact and torch.equal(eng.chol(), L64)
+    assert torch.equal(eng.S, S64) and torch.equal(eng.alpha, alpha64) and float(eng.loss) == loss64
     assert torch.equal(m2, m64) and torch.equal(s2, s64)
     g2 = eng.gradients()
     assert torch.equal(g2, g64)
