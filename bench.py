@@ -510,7 +510,11 @@ def main():
     eng.factorize(theta, resid)
     mll_grad = {"evals_per_s": 1e3 / mll_ms, "ms_per_eval": mll_ms, "n_train": eng.N, "dim": eng.D,
                 "what": "K_hat build + Cholesky + L^-1 + alpha + -mll + K_hat^-1 + gradient reduce (ExactGPEngine.factorize + gradients) "
-                        "as GPEmulator.train runs it: FP64 Cholesky, L^-1 merge levels >= 1024 rows and K_hat^-1 on the integer tensor cores",
+                        "as GPEmulator.train runs it: the Cholesky's bulk trailing updates (gpx_potrf_i8), the L^-1 merge levels >= 1024 rows "
+                        "and K_hat^-1 on the integer tensor cores (six 8-bit digits per operand, exact int32 sums); panels, diagonal "
+                        "blocks and the chain-bound tail in FP64 DMMA",
+                "cholesky": ("gpx_potrf_i8 (bulk trailing updates on tcgen05 kind::i8)" if getattr(eng, "_potrf_i8_capable", False)
+                             else "gpx_potrf (FP64 DMMA)"),
                 "k_inverse": (f"six 7-bit slices on tcgen05 kind::i8 (gpx_lauum_i8)" if lauum_default else "FP64 DMMA lauum"),
                 "ms_per_eval_fp64_inverse": mll_ms_exact, "ms_per_eval_all_fp64": mll_ms_fp64,
                 "training_mode_vs_all_fp64": {"loss_rel_diff": abs(loss_train_mode - loss_fp64) / abs(loss_fp64),

@@ -1292,12 +1292,15 @@ static int use_lookahead() {
 // stream (critical path: diag p+1, panel p+1), while the rest of the trailing matrix is updated on a helper
 // stream.
 // gpx_i8.cu: the bulk trailing update of one outer block on the integer tensor cores
-int potrf_trailing_i8(double* K, int Np, int c0, int c1, int r0, void* workspace, size_t workspace_bytes, cudaStream_t st);
+int potrf_i8_slice(const double* K, int Np, int c0, int c1, int r0, void* workspace, size_t workspace_bytes, int buf, cudaStream_t st);
+int potrf_i8_update(double* K, int Np, int c0, int c1, int r0, int ncol_blocks, void* workspace, int buf, cudaStream_t st);
 
-// i8_ws != null (training mode, gpx_potrf_i8): the bulk trailing updates of the two-level schedule -- everything right of the
-// look-ahead columns, once per outer block -- run as sliced-integer products (six 8-bit digits per operand, exact int32 sums)
-// instead of FP64 DMMA; the panels, the in-block updates, the look-ahead columns and the chain-bound tail stay FP64.  Outer
-// blocks are then OB = 4 panels wide by default (K = 512 per integer product; 3, 6 and 8 measured within 4 % of it at Np = 8192).
+// i8_ws != null (training mode, gpx_potrf_i8): the trailing updates of the two-level schedule -- once per outer block, the
+// look-ahead columns on the critical-path stream and everything right of them on the helper stream -- run as sliced-integer
+// products (six 8-bit digits per operand, exact int32 sums; the finished panels are sliced once per outer block, into
+// alternating plane buffers) instead of FP64 DMMA; the panels, the in-block updates and the chain-bound tail stay FP64.  Outer
+// blocks are then OB = 4 panels wide by default (K = 512 per integer product; 3, 6 and 8 measured within 4 % of it at Np = 8192),
+// 6 from 96 block columns and 8 from 192 (Np = 26240: 107 -> 91 ms).
 int potrf(double* K, int Np, int N, double* S, double* DT, double* logdet_blk, int* info, cudaStream_t st_caller, void* i8_ws,
           size_t i8_bytes) {
     set_gemm_attrs();
@@ -1365,7 +1368,7 @@ int potrf(double* K, int Np, int N, double* S, double* DT, double* logdet_blk, i
     if (sw_env < 0) { const char* e = getenv("GPX_POTRF_SWITCH"); sw_env = e ? atoi(e) : 32; }
     static int ob8_env = -1;
     if (ob8_env < 0) { const char* e = getenv("GPX_POTRF_OB_I8"); ob8_env = (e && e[0] >= '1' && e[0] <= '8') ? e[0] - '0' : 0; }
-    const int OB = i8_ws != nullptr ? (ob8_env ? ob8_env : 4) : (ob_env ? ob_env : (nb >= 96 ? 4 : 3));
+    const int OB = i8_ws != nullptr ? (ob8_env ? ob8_env : (nb >= 192 ? 8 : nb >= 96 ? 6 : 4)) : (ob_env ? ob_env : (nb >= 96 ? 4 : 3));
     int p_start = 0;
     if (tma && la != nullptr && st != st_caller && OB >= 2 && nb > sw_env) {
         // Two-level schedule.  Panels are still 128 wide (diag + panel on the critical path), but the bulk of the
@@ -1391,6 +1394,11 @@ int potrf(double* K, int Np, int N, double* S, double* DT, double* logdet_blk, i
             const int kp = qe - q;
             const int la_cols = (qe + OB < nb) ? OB : nb - qe;          // look-ahead: the next outer block's columns
             const int rest = nb - qe - la_cols;                          // helper stream: everything right of them
+            if (i8_ws != nullptr) {  // digits of the outer block's panels, every row below them (buffer q_idx & 1: the helper's
+                                     // update q_idx - 2 that read it last was waited for during outer block q_idx - 1)
+                const int rc8 = potrf_i8_slice(K, Np, q * TILE, qe * TILE, qe * TILE, i8_ws, i8_bytes, q_idx & 1, st);
+                if (rc8) return rc8;
+            }
             if (rest > 0) {          // the helper only needs this outer block's panels
                 cudaEventRecord(la->ev_main[q_idx & 1], st);
                 cudaStreamWaitEvent(la->side, la->ev_main[q_idx & 1], 0);
@@ -1399,7 +1407,7 @@ int potrf(double* K, int Np, int N, double* S, double* DT, double* logdet_blk, i
             if (pending) cudaStreamWaitEvent(st, la->ev_side[(q_idx - 1) & 1], 0);
             if (rest > 0) {
                 if (i8_ws != nullptr) {
-                    const int rc8 = potrf_trailing_i8(K, Np, q * TILE, qe * TILE, (qe + la_cols) * TILE, i8_ws, i8_bytes, la->side);
+                    const int rc8 = potrf_i8_update(K, Np, q * TILE, qe * TILE, (qe + la_cols) * TILE, -1, i8_ws, q_idx & 1, la->side);
                     if (rc8) return rc8;
                 } else {
                     potrf_trailing_tma_kernel<<<dim3(rest, rest), GT_THREADS, GT_SMEM_BYTES, la->side>>>(tmK, K, Np, q, qe + la_cols,
@@ -1410,7 +1418,12 @@ int potrf(double* K, int Np, int N, double* S, double* DT, double* logdet_blk, i
             } else {
                 pending = false;
             }
-            potrf_trailing_tma_kernel<<<dim3(la_cols, nb - qe), GT_THREADS, GT_SMEM_BYTES, st>>>(tmK, K, Np, q, qe, qe, kp);
+            if (i8_ws != nullptr) {
+                const int rc8 = potrf_i8_update(K, Np, q * TILE, qe * TILE, qe * TILE, la_cols, i8_ws, q_idx & 1, st);
+                if (rc8) return rc8;
+            } else {
+                potrf_trailing_tma_kernel<<<dim3(la_cols, nb - qe), GT_THREADS, GT_SMEM_BYTES, st>>>(tmK, K, Np, q, qe, qe, kp);
+            }
             p_start = qe;
         }
         // hand over to the one-panel loop with the whole trailing matrix up to date

@@ -819,7 +819,8 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             tmem_wait_ld();
             const double wg = 1.0 / (double)(1ull << (BITS * gi));
 #pragma unroll
-            for (int j = 0; j < 32; ++j) t[j] = fma((double)(int)v[j], wg, t[j]);
+            for (int j = 0; j < 32; ++j)        // (double)(int)v by the 2^52 trick: one LOP + one DADD instead of I2F.F64 on the XU pipe
+                t[j] = fma(__hiloint2double(0x43300000, (int)(v[j] ^ 0x80000000u)) - 4503601774854144.0, wg, t[j]);
         }
         const int r = quad * 32 + lane;
         const double si = sa[arow + r] * g.sign;
@@ -1003,17 +1004,35 @@ static int trtri_i8_merge_t(const double* L, double* Smat, const double* DT, dou
 //   K[i][j] -= sum_{k in [c0, c1)} K[i][k] K[j][k]      for the 128-tiles on or below the block diagonal of rows/columns >= r0
 // The rows of the finished panels [c0, c1) are sliced into six 8-bit digits (48 bits, one power-of-two scale per row; the sums
 // run over c1 - c0 <= 1024 entries, far inside the int32 range at any Np) and multiplied with themselves.
-size_t potrf_i8_workspace_bytes(int Np) { return (size_t)6 * Np * Np + (size_t)Np * 8; }
+// Two plane buffers: the critical-path stream slices the panels of outer block q + 1 while the helper stream's bulk update of
+// outer block q still reads the other buffer.
+size_t potrf_i8_workspace_bytes(int Np) { return 2 * ((size_t)6 * Np * Np + (size_t)Np * 8); }
 
-int potrf_trailing_i8(double* K, int Np, int c0, int c1, int r0, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+static inline double* potrf_i8_scales(void* workspace, int Np, int buf) {
+    return reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(workspace) + (size_t)buf * ((size_t)6 * Np * Np + (size_t)Np * 8));
+}
+
+// digits of K[r0.., c0..c1) (the finished panels of one outer block, every row below them) into plane buffer `buf`
+int potrf_i8_slice(const double* K, int Np, int c0, int c1, int r0, void* workspace, size_t workspace_bytes, int buf, cudaStream_t st) {
     constexpr int S = 6, BITS = 8;
     if (Np % TILE || r0 % TILE || c0 % TILE || c1 % TILE || c1 > r0 || r0 >= Np) return -4;
-    if (workspace_bytes < potrf_i8_workspace_bytes(Np)) return -7;
-    double* sA = reinterpret_cast<double*>(workspace);
+    if (workspace_bytes < potrf_i8_workspace_bytes(Np) || (buf & ~1)) return -7;
+    double* sA = potrf_i8_scales(workspace, Np, buf);
     int8_t* PA = reinterpret_cast<int8_t*>(sA + Np);
     slice_i8_rows_kernel<S, BITS><<<Np - r0, 256, 0, st>>>(K, Np, nullptr, r0, c0, c1, 0, 0, Np, PA, sA);
+    GPX_CHECK_LAUNCH();
+    return 0;
+}
+
+// K[i][j] -= sum_k ...  for the 128-tiles (i, j), i >= j, of block rows >= r0 / 128 and block columns [r0 / 128, r0 / 128 + ncol_blocks)
+// (ncol_blocks < 0: every block column down to the end -- the whole trailing triangle), from plane buffer `buf`.
+int potrf_i8_update(double* K, int Np, int c0, int c1, int r0, int ncol_blocks, void* workspace, int buf, cudaStream_t st) {
+    constexpr int S = 6, BITS = 8;
+    double* sA = potrf_i8_scales(workspace, Np, buf);
+    int8_t* PA = reinterpret_cast<int8_t*>(sA + Np);
     const int nbt = (Np - r0) / I_M;
-    const I8Gemm g = {2 * nbt, r0, r0, c0, c1, 2, r0, r0, -1, 0, 1, -1.0, 1};
+    const int ncb = (ncol_blocks < 0 || ncol_blocks > nbt) ? nbt : ncol_blocks;
+    const I8Gemm g = {2 * ncb, r0, r0, c0, c1, 2, r0, r0, -1, 0, 1, -1.0, 1};
     const int rc = launch_gemm_i8<S, BITS>(PA, PA, Np, sA, sA, K, nullptr, g, nbt, st);
     if (rc) return rc;
     GPX_CHECK_LAUNCH();

@@ -1,6 +1,9 @@
 """Summarise an .ncu-rep (ncu --set full) into the text form kept under profiles/: one block per kernel launch with the
 duration, DRAM bytes and throughput, L2 hit rate, pipe utilisation and the leading stall reasons.
-usage: python tools/ncu_summary.py gpurun_out/x.ncu-rep [kernel-name regex] > profiles/rNN_ncu_x.txt"""
+usage: python tools/ncu_summary.py gpurun_out/x.ncu-rep [kernel-name regex] > profiles/rNN_ncu_x.txt
+       python tools/ncu_summary.py --traffic gpurun_out/x.ncu-rep [kernel-name regex]
+           merges dram__bytes_read.sum + dram__bytes_write.sum of the LARGEST launch of every kernel of the capture into
+           profiles/ncu_traffic.json, keyed "name<template args>" (what bench.py's roofline.traffic reads)"""
 import csv
 import io
 import re
@@ -24,12 +27,41 @@ METRICS = [
     "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
 ]
-rep = sys.argv[1]
-pat = re.compile(sys.argv[2]) if len(sys.argv) > 2 else None
+argv = [a for a in sys.argv[1:] if a != "--traffic"]
+traffic_mode = "--traffic" in sys.argv[1:]
+rep = argv[0]
+pat = re.compile(argv[1]) if len(argv) > 1 else None
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units = rows[0], rows[1]
 col = {h: i for i, h in enumerate(hdr)}
+if traffic_mode:
+    import json
+    from pathlib import Path
+
+    def to_bytes(v, unit):
+        mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+        return float(v.replace(",", "")) * mult[unit]
+    path = Path(__file__).resolve().parent.parent / "profiles" / "ncu_traffic.json"
+    table = json.loads(path.read_text()) if path.exists() else {}
+    for r in rows[2:]:
+        name = r[col["Kernel Name"]]
+        if pat and not pat.search(name):
+            continue
+        m = re.match(r"(?:void )?(?:\w+::)*(\w+)(?:<([^>]*)>)?", name)
+        targs = ",".join(re.sub(r"\(\w+\)", "", a).strip() for a in (m.group(2) or "").split(",")) if m.group(2) else ""
+        key = m.group(1) + (f"<{targs}>" if targs else "")
+        rd = to_bytes(r[col["dram__bytes_read.sum"]], units[col["dram__bytes_read.sum"]])
+        wr = to_bytes(r[col["dram__bytes_write.sum"]], units[col["dram__bytes_write.sum"]])
+        us = r[col["gpu__time_duration.sum"]] + " " + units[col["gpu__time_duration.sum"]]
+        if key not in table or rd + wr > table[key]["dram_bytes_per_launch"] or table[key].get("capture") != rep:
+            if key in table and table[key].get("capture") == rep and rd + wr <= table[key]["dram_bytes_per_launch"]:
+                continue
+            table[key] = {"dram_bytes_per_launch": rd + wr, "dram_bytes_read": rd, "dram_bytes_write": wr, "grid": r[col["Grid Size"]],
+                          "duration_under_ncu": us, "capture": rep}
+    path.write_text(json.dumps(table, indent=1) + "\n")
+    print(json.dumps(table, indent=1))
+    sys.exit(0)
 print(f"# ncu --set full --clock-control none: {rep}")
 for r in rows[2:]:
     name = r[col["Kernel Name"]]
