@@ -713,7 +713,11 @@ struct I8Gemm {
     int tri;                    // 1: only the N tiles of the first mi + 1 pairs exist (tiles on or below the block diagonal)
     double sign;
     int accumulate;             // 1: C += sign * product (the Cholesky trailing update), 0: C = sign * product
+    int n_mi;                   // M tiles (set by launch_gemm_i8)
 };
+constexpr int I8G_BAND = 12;    // M tiles per band of the tile order: the ~74 resident clusters then cover 12 M tiles x 12 N tiles
+                                // (24 operand tiles per k step instead of 1 + 148), so each k step's operands are read from
+                                // DRAM once and served to the other CTAs from L2
 
 template <int S, int BITS>
 __global__ void __launch_bounds__(I_THREADS, 1)
@@ -733,7 +737,11 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     const uint32_t crank = cluster_ctarank();
     const int pairs = g.n_nj / 2;
     const int cid = (int)(blockIdx.x >> 1);
-    const int mi = cid / pairs, nj = 2 * (cid - mi * pairs) + (int)crank;
+    // band-major tile order: inside a band of I8G_BAND M tiles the M index runs fastest
+    const int band = cid / (I8G_BAND * pairs), within = cid - band * (I8G_BAND * pairs);
+    const int gm = (g.n_mi - band * I8G_BAND) < I8G_BAND ? (g.n_mi - band * I8G_BAND) : I8G_BAND;
+    const int pr = within / gm;
+    const int mi = band * I8G_BAND + (within - pr * gm), nj = 2 * pr + (int)crank;
     if (g.tri && (nj >> 1) > mi) return;          // both CTAs of the pair leave together, before any barrier exists
     const int kstart = g.k_from == 1 ? g.k_base + mi * I_M : g.k_base;            // k_from = 2: the same range [k_base, k_end) for every tile
     const int kend = g.k_from ? g.k_end : g.k_base + (mi + 1) * I_M;
@@ -807,6 +815,17 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     } else {
         const int quad = warp & 3, half = (warp - 2) >> 2;
         const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+        const int r = quad * 32 + lane;
+        double* dst = Cout + (long)(g.c_row0 + mi * I_M + r) * Np + g.c_col0 + nj * I_N + half * 32;
+        double c_old[32];               // accumulate mode: the old values of C are fetched while the MMAs run
+        if (g.accumulate) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+                const double2 c = *reinterpret_cast<const double2*>(dst + j);
+                c_old[j] = c.x;
+                c_old[j + 1] = c.y;
+            }
+        }
         mbar_wait(acc_full, 0);
         tc_fence_after();
         double t[32];
@@ -822,18 +841,13 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             for (int j = 0; j < 32; ++j)        // (double)(int)v by the 2^52 trick: one LOP + one DADD instead of I2F.F64 on the XU pipe
                 t[j] = fma(__hiloint2double(0x43300000, (int)(v[j] ^ 0x80000000u)) - 4503601774854144.0, wg, t[j]);
         }
-        const int r = quad * 32 + lane;
         const double si = sa[arow + r] * g.sign;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) t[j] *= sinv[half * 32 + j] * si;
-        double* dst = Cout + (long)(g.c_row0 + mi * I_M + r) * Np + g.c_col0 + nj * I_N + half * 32;
         if (g.accumulate) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-                const double2 c = *reinterpret_cast<const double2*>(dst + j);
-                t[j] += c.x;
-                t[j + 1] += c.y;
-            }
+            for (int j = 0; j < 32; ++j) t[j] = fma(t[j], sinv[half * 32 + j] * si, c_old[j]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) t[j] *= sinv[half * 32 + j] * si;
         }
 #pragma unroll
         for (int j = 0; j < 32; j += 2) *reinterpret_cast<double2*>(dst + j) = make_double2(t[j], t[j + 1]);
@@ -943,7 +957,9 @@ static int launch_gemm_i8(const int8_t* PA, const int8_t* PB, int Np, const doub
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_i8_kernel<S, BITS>, tmAh, tmB, Np, sa, sb, Cout, Cmir, g);
+    I8Gemm gg = g;
+    gg.n_mi = n_mi;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_i8_kernel<S, BITS>, tmAh, tmB, Np, sa, sb, Cout, Cmir, gg);
     return e == cudaSuccess ? 0 : -1000 - (int)e;
 }
 
@@ -962,7 +978,7 @@ int lauum_i8(const double* Smat, const double* DT, double* W, int Np, int nslice
     double* inv_scale = reinterpret_cast<double*>(workspace);
     int8_t* planes = reinterpret_cast<int8_t*>(inv_scale + Np);
     const int nbt = Np / I_M;
-    const I8Gemm g = {2 * nbt, 0, 0, 0, Np, 1, 0, 0, -1, 0, 1, 1.0, 0};
+    const I8Gemm g = {2 * nbt, 0, 0, 0, Np, 1, 0, 0, -1, 0, 1, 1.0, 0, 0};
     if (nslices == 5) {
         slice_i8_rows_kernel<5, 7><<<Np, 256, 0, st>>>(Smat, Np, DT, 0, 0, Np, 1, 0, Np, planes, inv_scale);
         return launch_gemm_i8<5, 7>(planes, planes, Np, inv_scale, inv_scale, W, nullptr, g, nbt, st);
@@ -987,13 +1003,13 @@ static int trtri_i8_merge_t(const double* L, double* Smat, const double* DT, dou
     // step 1: M side = columns of A^-1 as rows (left segment, k from the row to the end of the segment), N side = L[right, left]
     slice_i8_rows_kernel<S, BITS><<<h * TILE, 256, 0, st>>>(Smat, Np, DT, l0, 0, r0, 1, 0, Np, PA, sA);
     slice_i8_rows_kernel<S, BITS><<<hr * TILE, 256, 0, st>>>(L, Np, nullptr, r0, l0, r0, 0, 0, Np, PB, sB);
-    I8Gemm g1 = {2 * hr, l0, r0, l0, r0, 1, l0, r0, -1, 0, 0, 1.0, 0};
+    I8Gemm g1 = {2 * hr, l0, r0, l0, r0, 1, l0, r0, -1, 0, 0, 1.0, 0, 0};
     int rc = launch_gemm_i8<S, BITS>(PA, PB, Np, sA, sB, W, nullptr, g1, h, st);
     if (rc) return rc;
     // step 2: M side = rows of C^-1 (right segment, k from the segment start to the row), N side = T^T = W[left, right]
     slice_i8_rows_kernel<S, BITS><<<hr * TILE, 256, 0, st>>>(Smat, Np, nullptr, r0, r0, 0, 0, 1, Np, PA, sA);
     slice_i8_rows_kernel<S, BITS><<<h * TILE, 256, 0, st>>>(W, Np, nullptr, l0, r0, r1, 0, 0, Np, PB, sB);
-    I8Gemm g2 = {2 * h, r0, l0, r0, r1, 0, r0, l0, l0, r0, 0, -1.0, 0};
+    I8Gemm g2 = {2 * h, r0, l0, r0, r1, 0, r0, l0, l0, r0, 0, -1.0, 0, 0};
     rc = launch_gemm_i8<S, BITS>(PA, PB, Np, sA, sB, Smat, Smat, g2, hr, st);
     if (rc) return rc;
     GPX_CHECK_LAUNCH();
@@ -1032,7 +1048,7 @@ int potrf_i8_update(double* K, int Np, int c0, int c1, int r0, int ncol_blocks, 
     int8_t* PA = reinterpret_cast<int8_t*>(sA + Np);
     const int nbt = (Np - r0) / I_M;
     const int ncb = (ncol_blocks < 0 || ncol_blocks > nbt) ? nbt : ncol_blocks;
-    const I8Gemm g = {2 * ncb, r0, r0, c0, c1, 2, r0, r0, -1, 0, 1, -1.0, 1};
+    const I8Gemm g = {2 * ncb, r0, r0, c0, c1, 2, r0, r0, -1, 0, 1, -1.0, 1, 0};
     const int rc = launch_gemm_i8<S, BITS>(PA, PA, Np, sA, sA, K, nullptr, g, nbt, st);
     if (rc) return rc;
     GPX_CHECK_LAUNCH();
