@@ -15,7 +15,7 @@ _lib: Optional[C.CDLL] = None
 
 KIND_RBF, KIND_MATERN12, KIND_MATERN32, KIND_MATERN52 = 0, 1, 2, 3
 TILE = 128
-ABI_VERSION = 201          # gpx_version() of the library these ctypes signatures were written against
+ABI_VERSION = 202          # gpx_version() of the library these ctypes signatures were written against
 
 _P = C.c_void_p
 _SIGS = {
@@ -54,6 +54,7 @@ _SIGS = {
     "gpx_trmm_sumsq_i8": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
     "gpx_potrf_i8_workspace_bytes": (C.c_size_t, [C.c_int]),
     "gpx_potrf_i8": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "gpx_predict_covar_i8": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P, _P, C.c_int, _P, C.c_size_t, _P]),
     "gpx_trtri_i8_workspace_bytes": (C.c_size_t, [C.c_int]),
     "gpx_trtri_i8": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P, C.c_size_t, _P]),
     "gpx_lauum_i8_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),

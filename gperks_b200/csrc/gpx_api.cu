@@ -10,6 +10,7 @@ int mll_grad(const double*, int, int, const double*, int, const double*, int, co
              cudaStream_t);
 int potrf(double*, int, int, double*, double*, double*, int*, cudaStream_t, void*, size_t);
 size_t potrf_i8_workspace_bytes(int);
+int predict_covar_i8(const double*, int, const double*, int, double*, double*, double*, int, void*, size_t, cudaStream_t);
 int trtri(const double*, double*, const double*, double*, int, cudaStream_t);
 int lauum(const double*, const double*, double*, int, cudaStream_t);
 int solve_alpha(const double*, const double*, int, const double*, double*, double*, cudaStream_t);
@@ -98,7 +99,7 @@ using namespace gpx;
 
 extern "C" {
 
-int gpx_version(void) { return 201; }
+int gpx_version(void) { return 202; }
 int gpx_padded(int n) { return round_up(n < 1 ? 1 : n, TILE); }
 int gpx_max_dim(void) { return MAXD; }
 
@@ -289,6 +290,12 @@ int gpx_trtri_i8(const double* L, double* S, const double* DT, double* W, int Np
     if (!L || !S || !DT || !W || !workspace) return -1;
     if (Np <= 0 || Np % TILE) return -4;
     return trtri_i8(L, S, DT, W, Np, bits, workspace, workspace_bytes, ST(stream));
+}
+
+int gpx_predict_covar_i8(const double* S, int Np, const double* Ks, int Mp, double* Vt, double* C, double* W, int bits, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+    if (!S || !Ks || !Vt || !C || !W || !workspace) return -1;
+    return predict_covar_i8(S, Np, Ks, Mp, Vt, C, W, bits, workspace, workspace_bytes, ST(stream));
 }
 
 size_t gpx_lauum_i8_workspace_bytes(int Np, int nslices) { return lauum_i8_workspace_bytes(Np, nslices); }

@@ -714,6 +714,7 @@ struct I8Gemm {
     double sign;
     int accumulate;             // 1: C += sign * product (the Cholesky trailing update), 0: C = sign * product
     int n_mi;                   // M tiles (set by launch_gemm_i8)
+    int ldc;                    // leading dimension of C (0: Np); the mirror always has Np
 };
 constexpr int I8G_BAND = 12;    // M tiles per band of the tile order: the ~74 resident clusters then cover 12 M tiles x 12 N tiles
                                 // (24 operand tiles per k step instead of 1 + 148), so each k step's operands are read from
@@ -816,7 +817,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         const int quad = warp & 3, half = (warp - 2) >> 2;
         const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
         const int r = quad * 32 + lane;
-        double* dst = Cout + (long)(g.c_row0 + mi * I_M + r) * Np + g.c_col0 + nj * I_N + half * 32;
+        double* dst = Cout + (long)(g.c_row0 + mi * I_M + r) * (g.ldc ? g.ldc : Np) + g.c_col0 + nj * I_N + half * 32;
         double c_old[32];               // accumulate mode: the old values of C are fetched while the MMAs run
         if (g.accumulate) {
 #pragma unroll
@@ -978,7 +979,7 @@ int lauum_i8(const double* Smat, const double* DT, double* W, int Np, int nslice
     double* inv_scale = reinterpret_cast<double*>(workspace);
     int8_t* planes = reinterpret_cast<int8_t*>(inv_scale + Np);
     const int nbt = Np / I_M;
-    const I8Gemm g = {2 * nbt, 0, 0, 0, Np, 1, 0, 0, -1, 0, 1, 1.0, 0, 0};
+    const I8Gemm g = {2 * nbt, 0, 0, 0, Np, 1, 0, 0, -1, 0, 1, 1.0, 0, 0, 0};
     if (nslices == 5) {
         slice_i8_rows_kernel<5, 7><<<Np, 256, 0, st>>>(Smat, Np, DT, 0, 0, Np, 1, 0, Np, planes, inv_scale);
         return launch_gemm_i8<5, 7>(planes, planes, Np, inv_scale, inv_scale, W, nullptr, g, nbt, st);
@@ -1003,13 +1004,13 @@ static int trtri_i8_merge_t(const double* L, double* Smat, const double* DT, dou
     // step 1: M side = columns of A^-1 as rows (left segment, k from the row to the end of the segment), N side = L[right, left]
     slice_i8_rows_kernel<S, BITS><<<h * TILE, 256, 0, st>>>(Smat, Np, DT, l0, 0, r0, 1, 0, Np, PA, sA);
     slice_i8_rows_kernel<S, BITS><<<hr * TILE, 256, 0, st>>>(L, Np, nullptr, r0, l0, r0, 0, 0, Np, PB, sB);
-    I8Gemm g1 = {2 * hr, l0, r0, l0, r0, 1, l0, r0, -1, 0, 0, 1.0, 0, 0};
+    I8Gemm g1 = {2 * hr, l0, r0, l0, r0, 1, l0, r0, -1, 0, 0, 1.0, 0, 0, 0};
     int rc = launch_gemm_i8<S, BITS>(PA, PB, Np, sA, sB, W, nullptr, g1, h, st);
     if (rc) return rc;
     // step 2: M side = rows of C^-1 (right segment, k from the segment start to the row), N side = T^T = W[left, right]
     slice_i8_rows_kernel<S, BITS><<<hr * TILE, 256, 0, st>>>(Smat, Np, nullptr, r0, r0, 0, 0, 1, Np, PA, sA);
     slice_i8_rows_kernel<S, BITS><<<h * TILE, 256, 0, st>>>(W, Np, nullptr, l0, r0, r1, 0, 0, Np, PB, sB);
-    I8Gemm g2 = {2 * h, r0, l0, r0, r1, 0, r0, l0, l0, r0, 0, -1.0, 0, 0};
+    I8Gemm g2 = {2 * h, r0, l0, r0, r1, 0, r0, l0, l0, r0, 0, -1.0, 0, 0, 0};
     rc = launch_gemm_i8<S, BITS>(PA, PB, Np, sA, sB, Smat, Smat, g2, hr, st);
     if (rc) return rc;
     GPX_CHECK_LAUNCH();
@@ -1048,11 +1049,48 @@ int potrf_i8_update(double* K, int Np, int c0, int c1, int r0, int ncol_blocks, 
     int8_t* PA = reinterpret_cast<int8_t*>(sA + Np);
     const int nbt = (Np - r0) / I_M;
     const int ncb = (ncol_blocks < 0 || ncol_blocks > nbt) ? nbt : ncol_blocks;
-    const I8Gemm g = {2 * ncb, r0, r0, c0, c1, 2, r0, r0, -1, 0, 1, -1.0, 1, 0};
+    const I8Gemm g = {2 * ncb, r0, r0, c0, c1, 2, r0, r0, -1, 0, 1, -1.0, 1, 0, 0};
     const int rc = launch_gemm_i8<S, BITS>(PA, PA, Np, sA, sA, K, nullptr, g, nbt, st);
     if (rc) return rc;
     GPX_CHECK_LAUNCH();
     return 0;
+}
+
+// ---- dense predictive covariance on the integer tensor cores (training loops: the validation loss of every epoch) ----------
+//   Vt[m][i] = sum_{k <= i} Ks[m][k] L^-1[i][k]          (Mp x Np, the layout gpx_trmm_store writes)
+//   C[m][m'] -= sum_i Vt[m][i] Vt[m'][i]                 (C = K** on entry; only the 128-tiles on or below the diagonal)
+// Step 1 puts the rows of L^-1 on the M side (k range of tile row mi ends with its diagonal block) and the test points on the
+// N side; V itself goes to the scratch matrix W, its transpose -- what step 2 slices -- to Vt through the mirror store.
+template <int BITS>
+static int predict_covar_i8_t(const double* Smat, int Np, const double* Ks, int Mp, double* Vt, double* C, double* W, void* workspace,
+                              cudaStream_t st) {
+    constexpr int S = 6;
+    const size_t plane_bytes = (size_t)S * Np * Np;
+    double* sA = reinterpret_cast<double*>(workspace);
+    double* sB = sA + Np;
+    int8_t* PA = reinterpret_cast<int8_t*>(sB + Np);
+    int8_t* PB = PA + plane_bytes;
+    slice_i8_rows_kernel<S, BITS><<<Np, 256, 0, st>>>(Smat, Np, nullptr, 0, 0, 0, 0, 1, Np, PA, sA);
+    slice_i8_rows_kernel<S, BITS><<<Mp, 256, 0, st>>>(Ks, Np, nullptr, 0, 0, Np, 0, 0, Np, PB, sB);
+    const I8Gemm g1 = {2 * (Mp / I_M), 0, 0, 0, Np, 0, 0, 0, 0, 0, 0, 1.0, 0, 0, 0};
+    int rc = launch_gemm_i8<S, BITS>(PA, PB, Np, sA, sB, W, Vt, g1, Np / I_M, st);
+    if (rc) return rc;
+    slice_i8_rows_kernel<S, BITS><<<Mp, 256, 0, st>>>(Vt, Np, nullptr, 0, 0, Np, 0, 0, Np, PA, sA);
+    const I8Gemm g2 = {2 * (Mp / I_M), 0, 0, 0, Np, 2, 0, 0, -1, 0, 1, -1.0, 1, 0, Mp};
+    rc = launch_gemm_i8<S, BITS>(PA, PA, Np, sA, sA, C, nullptr, g2, Mp / I_M, st);
+    if (rc) return rc;
+    GPX_CHECK_LAUNCH();
+    return 0;
+}
+
+int predict_covar_i8(const double* Smat, int Np, const double* Ks, int Mp, double* Vt, double* C, double* W, int bits, void* workspace,
+                     size_t workspace_bytes, cudaStream_t st) {
+    if (Np % TILE || Mp % TILE || Mp > Np || Mp <= 0) return -4;
+    if (workspace_bytes < trtri_i8_workspace_bytes(Np, 6)) return -7;
+    if (bits == 8 && Np > 16384) return -5;
+    if (Np > 32768) return -5;
+    return bits == 8 ? predict_covar_i8_t<8>(Smat, Np, Ks, Mp, Vt, C, W, workspace, st)
+                     : predict_covar_i8_t<7>(Smat, Np, Ks, Mp, Vt, C, W, workspace, st);
 }
 
 // bits = 8: balanced radix-256 digits (48 bits per operand instead of 42; Np <= 16384 keeps the int32 sums exact)

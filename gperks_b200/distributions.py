@@ -99,6 +99,7 @@ class PosteriorDistribution:
         self.x = x if x.dim() > 1 else x.unsqueeze(-1)
         self.noisy = noisy
         self._mv = None
+        self._m = None
         self._cov = None
         self._cov_mean = None
 
@@ -106,6 +107,21 @@ class PosteriorDistribution:
     def _out(self, t: torch.Tensor) -> torch.Tensor:
         dt = self.x.dtype if self.x.dtype.is_floating_point else F64
         return t.to(self.x.device, dt)
+
+    def _mean_device(self) -> torch.Tensor:
+        """Posterior mean alone (``gpx_predict_mean``: bit-identical to the mean of the full predict at ~1 % of its cost) -- what the
+        per-epoch metrics of a training loop ask of ``likelihood(model(X))``; the variance contraction runs only when a moment
+        that needs it is read."""
+        if self._mv is not None:
+            return self._mv[0]
+        if self._m is None:
+            with torch.no_grad():
+                def compute(eng):
+                    xd = self.x.detach().to(eng.device, F64).contiguous()
+                    prior = self.model.mean_module(self.x.detach()).detach().to(eng.device, F64)
+                    return eng.predict_mean(xd, prior_mean=prior)
+                self._m = self.model._cached_prediction(self._x_orig, "mean", compute)
+        return self._m
 
     def _mean_var_device(self):
         if self._mv is None:
@@ -132,7 +148,7 @@ class PosteriorDistribution:
     # -- gpytorch API ---------------------------------------------------------------------------
     @property
     def mean(self) -> torch.Tensor:
-        return self._out(self._mean_var_device()[0])
+        return self._out(self._mean_device())
 
     loc = mean
 

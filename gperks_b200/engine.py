@@ -539,13 +539,26 @@ class ExactGPEngine:
             st = nv.stream_ptr()
             self._launch("gpx_kmat_cross", p(Xs), M, p(self.X), self.N, self.D, p(self.theta), None, None, self.kind,
                          p(self.alpha), p(Ks), Np, p(mpart), Mp, st)
-            self._launch("gpx_trmm_store", p(self.S), Np, p(Ks), Mp, p(Vt), st)
+            # inside a training loop (the validation loss of every epoch) both products run on the integer tensor cores
+            i8 = bool(self.approx_inverse_ok and self._trtri_i8_capable and Mp <= Np and Mp >= 1024 and self._lauum_ws is not None
+                      and self._lauum_ws.numel() >= int(self.lib.gpx_trtri_i8_workspace_bytes(Np)))
+            if not i8:
+                self._launch("gpx_trmm_store", p(self.S), Np, p(Ks), Mp, p(Vt), st)
             self._launch("gpx_kmat_cross", p(Xs), M, p(Xs), M, self.D, p(self.theta_latent), None, None, self.kind,
                          p(zeros), p(Kss), Mp, p(mpart2), Mp, st)
-            self._launch("gpx_syrk_sub", p(Vt), Mp, Np, p(Kss), st)
+            if i8:
+                self._launch("gpx_predict_covar_i8", p(self.S), Np, p(Ks), Mp, p(Vt), p(Kss), p(self.W),
+                             8 if Np <= int(self.lib.gpx_i8_max_n(8)) else 7, p(self._lauum_ws), self._lauum_ws.numel(), st)
+                self.has_kinv = False            # W served as scratch
+            else:
+                self._launch("gpx_syrk_sub", p(Vt), Mp, Np, p(Kss), st)
         mean = prior_mean.detach().to(dev, F64).reshape(-1) + mpart[:, :M].sum(0)
         cov = Kss[:M, :M]
-        cov = 0.5 * (cov + cov.T)
+        if i8:                                   # only the tiles on or below the diagonal were formed
+            low = torch.tril(cov)
+            cov = low + torch.tril(cov, -1).T
+        else:
+            cov = 0.5 * (cov + cov.T)
         if noisy:
             cov = cov + self.theta[self.D + 1] * torch.eye(M, dtype=F64, device=dev)
         return mean, cov

@@ -95,6 +95,7 @@ class ExactGP(Module):
         if not eng.matches(theta, resid):
             eng.factorize(theta, resid)
             self._pred_cache = None
+            self._pred_cache_mean = None
         return eng
 
     def _cached_prediction(self, x: torch.Tensor, noisy: bool, compute):
@@ -102,12 +103,14 @@ class ExactGP(Module):
         (mean, variance) keyed on the input tensor, its version and the factorisation they were computed from."""
         eng = self._factorized_engine()
         key = (x._version, tuple(x.shape), noisy, eng.n_factorizations)
-        cache = getattr(self, "_pred_cache", None)
+        # ``noisy == "mean"``: the mean-only prediction (its own slot: a later request for the variance must not evict it mid-epoch)
+        slot = "_pred_cache_mean" if noisy == "mean" else "_pred_cache"
+        cache = getattr(self, slot, None)
         # the weak reference guards against a new tensor re-using the id of a collected one
         if cache is not None and cache[0] == key and cache[1]() is x:
             return cache[2]
         value = compute(eng)
-        self._pred_cache = (key, weakref.ref(x), value)
+        setattr(self, slot, (key, weakref.ref(x), value))
         return value
 
     # -- gpytorch calling convention ------------------------------------------------------------

@@ -187,6 +187,14 @@ int gpx_potrf_i8(double* K, int Np, int N, double* S, double* DT, double* logdet
 size_t gpx_trtri_i8_workspace_bytes(int Np);
 int gpx_trtri_i8(const double* L, double* S, const double* DT, double* W, int Np, int bits, void* workspace, size_t workspace_bytes,
                  void* stream);
+/* gpx_predict_covar_i8: gpx_trmm_store + gpx_syrk_sub on the integer tensor cores, for the dense predictive covariance that the
+ * validation loss of every training epoch needs (six digits per operand: 8 bit for Np <= 16384, 7 bit up to 32768).  Ks[Mp][Np]
+ * (gpx_kmat_cross) and C[Mp][Mp] = K** on entry; on exit Vt[Mp][Np] = K* L^-T and the 128-tiles of C on or below the diagonal
+ * hold K** - Vt Vt^T (tiles above it are untouched).  W is an Np x Np scratch matrix (receives V), workspace as for gpx_trtri_i8.
+ * Mp <= Np.  Entries of Vt within ~2^-46 (8 bit) / 2^-40 (7 bit) of their row and column scales.
+ * replaces: the same call sites as gpx_trmm_store / gpx_syrk_sub, inside GPEmulator.train loops only. */
+int gpx_predict_covar_i8(const double* S, int Np, const double* Ks, int Mp, double* Vt, double* C, double* W, int bits, void* workspace,
+                         size_t workspace_bytes, void* stream);
 size_t gpx_lauum_i8_workspace_bytes(int Np, int nslices);
 int gpx_lauum_i8(const double* S, const double* DT, double* Kinv, int Np, int nslices, void* workspace, size_t workspace_bytes,
                  void* stream);

@@ -919,6 +919,38 @@ def test_validation_loss_and_covariance_kernels_match_oracle(dev):
     assert lp == pytest.approx(float(ref), rel=1e-9)
 
 
+@pytest.mark.parametrize("N,M", [(2300, 1100), (4300, 1500)])
+def test_training_mode_predictive_covariance_on_integer_tensor_cores(dev, N, M):
+    """Inside a training loop the dense predictive covariance of the validation points (the validation loss of every epoch) is
+    formed by gpx_predict_covar_i8 (six 8-bit digits per operand): entries within 1e-9 of the outputscale of the FP64 kernels'
+    (gpx_trmm_store + gpx_syrk_sub), the log density of the validation targets within 1e-7 relative."""
+    from gperks_b200.engine import DenseCholesky
+    X, y, Xs, ls, s, w, b = _problem(N, 6, M, seed=N + 1)
+    eng = _engine(dev, X, y, O.KIND_MATERN52, ls, s, 1e-2, w, b)
+    prior = (Xs @ w + b).to(dev)
+    m64, c64 = eng.predict_covar(Xs.to(dev), prior, noisy=True)
+    yv = torch.randn(M, dtype=F64, generator=torch.Generator().manual_seed(5)).to(dev) * 0.3 + m64
+
+    def logp(mean, cov):
+        ch = DenseCholesky(cov, need_inverse=True)
+        z = ch.solve_lower(yv - mean)
+        return -0.5 * float(z @ z) - float(ch.logdet_half) - 0.5 * M * math.log(2 * math.pi)
+    eng.approx_inverse_ok = True
+    eng.factorize(eng.theta_in.clone(), eng.r[:N].clone())
+    eng.gradients()
+    assert eng.has_kinv
+    m8, c8 = eng.predict_covar(Xs.to(dev), prior, noisy=True)
+    assert not eng.has_kinv                                   # W was the scratch of the integer product
+    assert torch.equal(c8, c8.T)
+    err = float((c8 - c64).abs().max() / float(s))
+    assert 0 < err < 1e-9, err
+    np.testing.assert_allclose(m8.cpu().numpy(), m64.cpu().numpy(), rtol=0, atol=1e-7 * float(m64.abs().max()))   # alpha of the training-mode factors
+    assert logp(m8, c8) == pytest.approx(logp(m64, c64), rel=1e-7)
+    g = eng.gradients()                                       # K_hat^-1 is formed again on demand
+    assert eng.has_kinv and bool(torch.isfinite(g).all())
+    eng.approx_inverse_ok = False
+
+
 @pytest.mark.parametrize("variant", ["zero_mean_shared_ls", "constant_mean_bare_kernel", "fixed_noise_quadratic_mean"])
 def test_api_variants_match_oracle(dev, variant):
     """Less common module combinations through the public API: shared (non-ARD) lengthscale, kernels without a
