@@ -692,6 +692,9 @@ def main():
             "algorithmic_flops_per_launch": flops_per_launch, "fp64_equivalent_tflops": flops_per_launch / (tk / 1e3) / 1e12,
             "fp64_equivalent_vs_dmma_peak": flops_per_launch / (tk / 1e3) / 1e12 / dmma_peak,
             "kernel_ms": tk, "kernel_sm_mhz": kclk.summary()["sm_mhz"], "kernel_share_of_step": tk * (M / Mc) / step_ms,
+            # the nominal issue rate scales with the SM clock; under the power cap the kernel runs at kernel_sm_mhz, not at 1965 MHz
+            "frac_of_nominal_at_kernel_clock": (raw / (4500.0 * kclk.summary()["sm_mhz"] / 1965.0)) if kclk.summary().get("sm_mhz") else None,
+            "dram_bytes_algorithmic_per_launch": float(S_) * Mc * eng.N + float(S_) * eng.N * eng.N / 2 + 8.0 * nt8 * Mc,
             "builder_kernel": f"kmat_cross_i8_kernel<matern52,{S_},{bits_}> (FP64 K* evaluation -> int8 slices + posterior-mean partial sums)",
             "builder_kernel_ms": tb, "builder_share_of_step_if_serial": tb * (M / Mc) / step_ms,
             "peak_source": "gpx_peak_i8mma probe measured in this run (kind::i8 MMA issue rate from resident shared memory, one CTA per SM; "
