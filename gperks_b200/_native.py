@@ -15,7 +15,7 @@ _lib: Optional[C.CDLL] = None
 
 KIND_RBF, KIND_MATERN12, KIND_MATERN32, KIND_MATERN52 = 0, 1, 2, 3
 TILE = 128
-ABI_VERSION = 202          # gpx_version() of the library these ctypes signatures were written against
+ABI_VERSION = 203          # gpx_version() of the library these ctypes signatures were written against
 
 _P = C.c_void_p
 _SIGS = {
@@ -48,6 +48,8 @@ _SIGS = {
     "gpx_slice_i8": (C.c_int, [_P, C.c_int, C.c_int, C.c_long, _P, C.c_long, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "gpx_i8_row_tiles": (C.c_int, [C.c_int]),
     "gpx_i8_max_n": (C.c_int, [C.c_int]),
+    "gpx_i8_safe_n": (C.c_int, [C.c_int]),
+    "gpx_i8_digit_bound": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
     "gpx_i8_clusters": (C.c_int, []),
     "gpx_kmat_cross_i8": (C.c_int, [_P, C.c_long, _P, C.c_int, C.c_int, _P, _P, _P, C.c_int, _P, _P, C.c_long, C.c_int, C.c_int,
                                     C.c_int, _P, C.c_int, _P]),

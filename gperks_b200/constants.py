@@ -51,7 +51,10 @@ DEFAULT_PREDICT_CHUNK_BYTES = 2 << 30      # HBM budget for one K* chunk in GPEm
 # otherwise the FP64 DMMA path.  Candidates in order of speed (each is tried only inside its ratio limit):
 #   N_pad <= 16384:  "int8x5w" five 8-bit slices (40 bits, 15 slice products)  for outputscale/noise <= 3e2
 #                    "int8x6w" six  8-bit slices (48 bits, 21 products)        for outputscale/noise <= 1e5
-#   N_pad <= 32768:  "int8x6"  six  7-bit slices (42 bits, 21 products)        for outputscale/noise <= 2e3
+#   N_pad <= 32768:  "int8x5w" as above, when the digits of the factorised L^-1 keep the int32 sums exact (8-bit digits are exact for
+#                    ANY data only up to 16384 rows; above, 128 x the largest row sum of |digits| must stay below 2^31 --
+#                    ExactGPEngine.i8_sums_exact / gpx_i8_digit_bound, measured 2 x below the limit at N_pad = 26240), then
+#                    "int8x6"  six  7-bit slices (42 bits, 21 products)        for outputscale/noise <= 2e3
 # Measured worst relative error of std against the FP64 path over points ON and 1e-4 beside training inputs (N = 2048 and 8192,
 # profiles/r02_i8_modes_*.json) ~ c * outputscale/noise with c = 2.6e-10 (int8x5w), 1.2e-12 (int8x6w), 8e-11 (int8x6): the
 # limits keep that product at or below 1e-7, a factor 10 inside the 1e-6 bar (tests/test_gpu_baseline_shapes.py measured

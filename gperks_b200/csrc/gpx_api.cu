@@ -34,6 +34,8 @@ int kmat_cross_i8(const double*, long, const double*, int, int, const double*, c
 int trmm_sumsq_i8(const int8_t*, const double*, int, const int8_t*, int, int, int, const double*, double*, int*, cudaStream_t);
 int i8_row_tiles(int);
 int i8_max_np(int);
+int i8_safe_np(int);
+int i8_digit_bound(const int8_t*, int, int, unsigned long long*, cudaStream_t);
 int i8_clusters();
 size_t predict_i8_workspace_bytes(int, int, int);
 size_t predict_i8_planes_offset(int, int, int, int);
@@ -99,7 +101,7 @@ using namespace gpx;
 
 extern "C" {
 
-int gpx_version(void) { return 202; }
+int gpx_version(void) { return 203; }
 int gpx_padded(int n) { return round_up(n < 1 ? 1 : n, TILE); }
 int gpx_max_dim(void) { return MAXD; }
 
@@ -256,6 +258,11 @@ int gpx_slice_i8(const double* src, int rows, int cols, long ld_src, signed char
 }
 
 int gpx_i8_max_n(int bits) { return (bits == 7 || bits == 8) ? i8_max_np(bits) : 0; }
+int gpx_i8_safe_n(int bits) { return i8_safe_np(bits); }
+int gpx_i8_digit_bound(const signed char* planes, int nslices, int Np, unsigned long long* out, void* stream) {
+    if (!planes || !out) return -1;
+    return i8_digit_bound(reinterpret_cast<const int8_t*>(planes), nslices, Np, out, ST(stream));
+}
 int gpx_i8_clusters(void) { return i8_clusters(); }
 
 int gpx_i8_row_tiles(int Np) { return i8_row_tiles(Np); }

@@ -681,7 +681,48 @@ static int launch_i8(const int8_t* Ls, const double* inv_scale, int Np, const in
 }
 
 // largest contraction length whose int32 sums cannot overflow: |digit| <= 64 (7 bit) / 128 (8 bit), S products per diagonal
-int i8_max_np(int bits) { return bits == 8 ? 16384 : 32768; }
+// Largest padded train size the kernels accept / the largest one whose int32 sums are exact whatever the digits are:
+//   |sum| <= (S digit products per accumulator) * 128 * 128 * K < 2^31  <=>  K <= 16384 for 8-bit digits (S <= 6),
+//   |digit| <= 64 keeps 7-bit digits exact to K = 32768.
+// Between the two, 8-bit digits are exact when the ACTUAL digits of L^-1 allow it: every accumulator is bounded by
+//   128 * max_i sum_{planes b} sum_k |digit_b(L^-1[i][k])|      (|K* digit| <= 128),
+// which i8_digit_bound() evaluates on the sliced planes (typical: 2.5 x below 2^31 at Np = 26240, five digits).
+int i8_max_np(int bits) { return (bits == 7 || bits == 8) ? 32768 : 0; }
+int i8_safe_np(int bits) { return bits == 8 ? 16384 : (bits == 7 ? 32768 : 0); }
+
+// out[0] = max over rows of  sum_{plane, k} |digit|   (one block per row of the S planes [Np][Np]); out must be zero on entry
+__global__ void __launch_bounds__(256) i8_digit_bound_kernel(const int8_t* __restrict__ planes, int S, int Np,
+                                                             unsigned long long* __restrict__ out) {
+    const int row = blockIdx.x;
+    unsigned int acc = 0;
+    for (int j = 0; j < S; ++j) {
+        const int4* src = reinterpret_cast<const int4*>(planes + ((long)j * Np + row) * Np);
+        for (int c = threadIdx.x; c < Np / 16; c += 256) {
+            const int4 v = src[c];
+            const unsigned int w[4] = {(unsigned int)v.x, (unsigned int)v.y, (unsigned int)v.z, (unsigned int)v.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc = __dp4a(__vabs4(w[q]), 0x01010101u, acc);      // |-128| -> 128 (unsigned bytes)
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    __shared__ unsigned int red[8];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        atomicMax(out, t);
+    }
+}
+
+int i8_digit_bound(const int8_t* planes, int nslices, int Np, unsigned long long* out, cudaStream_t st) {
+    if (Np % TILE || nslices < 1 || nslices > I_SMAX) return -4;
+    cudaMemsetAsync(out, 0, sizeof(unsigned long long), st);
+    i8_digit_bound_kernel<<<Np, 256, 0, st>>>(planes, nslices, Np, out);
+    GPX_CHECK_LAUNCH();
+    return 0;
+}
 
 // qpart[it][m], it < Np/64.  Ls: S planes [Np][Np] of the sliced inverse, Kp: S planes [Mc][Np] of the sliced K* chunk.
 // sched: two device ints, zero before the first launch that uses them (the kernel rewinds them itself), not shared by launches that

@@ -106,6 +106,7 @@ class ExactGPEngine:
         self.S_lo: Optional[torch.Tensor] = None
         self.i8_mode = None                           # sliced-integer mode: (slices, bits) of the int8 planes of L^-1 held (None = stale)
         self._i8_probe = {}                           # precision -> (n_factorizations, tol, ok) of int8_probe_ok()
+        self._i8_bound = {}                           # precision -> (key, ok, bound) of i8_sums_exact()
         self._probe_set = None                        # (n_factorizations, points, their FP64 std)
         self._mma_stream: Optional[torch.cuda.Stream] = None   # high-priority stream of the tensor-core kernel (chunk pipeline)
         # K_hat^-1 = L^-T L^-1 for the gradient: six-slice integer tensor-core product where its tiles pay and its int32 sums
@@ -194,7 +195,7 @@ class ExactGPEngine:
                 if self._lauum_ws is None or self._lauum_ws.numel() < need:      # switched on after construction
                     self._lauum_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
                 self._launch("gpx_trtri_i8", p(self.K), p(self.S), p(self.DT), p(self.W), self.Np,
-                             8 if self.Np <= int(self.lib.gpx_i8_max_n(8)) else 7, p(self._lauum_ws), self._lauum_ws.numel(), st)
+                             8 if self.Np <= int(self.lib.gpx_i8_safe_n(8)) else 7, p(self._lauum_ws), self._lauum_ws.numel(), st)
             else:
                 self._launch("gpx_trtri", p(self.K), p(self.S), p(self.DT), p(self.W), self.Np, st)
             self._launch("gpx_solve_alpha", p(self.S), p(self.DT), self.Np, p(self.r), p(self.u), p(self.alpha), st)
@@ -324,6 +325,9 @@ class ExactGPEngine:
         if i8 and self.Np > int(self.lib.gpx_i8_max_n(i8_bits)):
             raise ValueError(f"the sliced-integer mode holds its sums in int32: N <= {int(self.lib.gpx_i8_max_n(i8_bits))} "
                              f"for {i8_bits}-bit slices")
+        if i8 and not self.i8_sums_exact(precision):
+            raise ValueError(f"precision={precision!r}: the digits of this L^-1 do not keep the int32 sums of {i8_bits}-bit slices exact at "
+                             f"N_pad = {self.Np} (above {int(self.lib.gpx_i8_safe_n(i8_bits))} that depends on the data); use 'int8x6'")
         # tf32x3: K* evaluated in FP64 then split (posterior mean bit-identical to fp64; variance on tcgen05);
         # tf32x3_fast: K* evaluated in FP32 as well (mean moves by ~1e-4 of its scale for noise-like targets)
         tf32 = precision.startswith("tf32")
@@ -432,8 +436,13 @@ class ExactGPEngine:
                 cands.append("int8x5w")
             if ratio <= AUTO_I8_W6_MAX_SCALE_TO_NOISE:
                 cands.append("int8x6w")
-        elif ratio <= AUTO_I8_MAX_SCALE_TO_NOISE:
-            cands.append("int8x6")
+        else:
+            # 8-bit digits above 16384 rows: exact only if the digits of this L^-1 allow it (i8_sums_exact, checked where the
+            # candidate is picked); five of them are 1.4 x cheaper than the six 7-bit digits that are always safe
+            if ratio <= AUTO_I8_W5_MAX_SCALE_TO_NOISE:
+                cands.append("int8x5w")
+            if ratio <= AUTO_I8_MAX_SCALE_TO_NOISE:
+                cands.append("int8x6")
         return cands + ["fp64"]
 
     def auto_precision(self, noisy: bool = True) -> str:
@@ -448,7 +457,11 @@ class ExactGPEngine:
             self._auto_cands = self.auto_candidates(self.N, float(th[0]), float(th[1]))
             self._auto_key = key
         for c in self._auto_cands:
-            if c == "fp64" or self.approx_inverse_ok or self.int8_probe_ok(c, AUTO_I8_PROBE_TOL):
+            if c == "fp64":
+                return c
+            if not self.i8_sums_exact(c):            # 8-bit digits above 16384 rows whose int32 sums this L^-1 does not bound
+                continue
+            if self.approx_inverse_ok or self.int8_probe_ok(c, AUTO_I8_PROBE_TOL):
                 return c
         return "fp64"
 
@@ -481,10 +494,36 @@ class ExactGPEngine:
         hit = self._i8_probe.get(precision)
         if hit is not None and hit[0] == self.n_factorizations and hit[1] == float(tol):
             return hit[2]
+        if not self.i8_sums_exact(precision):        # the mode's int32 sums are not bounded for these factors: not a candidate
+            self._i8_probe[precision] = (self.n_factorizations, float(tol), False)
+            return False
         pts, s64 = self._probe_points()
         _, s8 = self.predict(pts, prior_mean=torch.zeros(pts.shape[0], dtype=F64, device=self.device), precision=precision)
         ok = bool(((s8 - s64).abs() <= tol * s64).all())
         self._i8_probe[precision] = (self.n_factorizations, float(tol), ok)
+        return ok
+
+    def i8_sums_exact(self, precision: str) -> bool:
+        """True when the int32 accumulators of sliced-integer mode ``precision`` cannot overflow for the CURRENT factors: always up to
+        ``gpx_i8_safe_n(bits)`` (any digits); above it (8-bit digits, 16384 < N_pad <= 32768) when 128 x the largest row sum of
+        |digits| of the sliced L^-1 stays below 2^31 (``gpx_i8_digit_bound``: one pass over the planes and one host read per
+        factorisation and mode)."""
+        slices, bits = I8_MODES[precision]
+        if self.Np <= int(self.lib.gpx_i8_safe_n(bits)):
+            return True
+        if self.Np > int(self.lib.gpx_i8_max_n(bits)):
+            return False
+        key = (precision, self.n_factorizations, self.inverse_exact)
+        hit = self._i8_bound.get(precision)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        self._ensure_i8(slices, bits)
+        out = torch.zeros(1, dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            self._launch("gpx_i8_digit_bound", nv.ptr(self.S_i8), slices, self.Np, nv.ptr(out), nv.stream_ptr())
+        bound = int(out.item())
+        ok = 128 * bound < 2 ** 31
+        self._i8_bound[precision] = (key, ok, bound)
         return ok
 
     def _ensure_i8(self, slices: int, bits: int) -> None:
@@ -548,7 +587,7 @@ class ExactGPEngine:
                          p(zeros), p(Kss), Mp, p(mpart2), Mp, st)
             if i8:
                 self._launch("gpx_predict_covar_i8", p(self.S), Np, p(Ks), Mp, p(Vt), p(Kss), p(self.W),
-                             8 if Np <= int(self.lib.gpx_i8_max_n(8)) else 7, p(self._lauum_ws), self._lauum_ws.numel(), st)
+                             8 if Np <= int(self.lib.gpx_i8_safe_n(8)) else 7, p(self._lauum_ws), self._lauum_ws.numel(), st)
                 self.has_kinv = False            # W served as scratch
             else:
                 self._launch("gpx_syrk_sub", p(Vt), Mp, Np, p(Kss), st)

@@ -130,7 +130,10 @@ int gpx_predict_meanvar_tf32(const double* Xs, long M, const double* X, int N, i
  * combined in FP64.
  *   bits = 7: signed 7-bit slices (|digit| <= 64, repeated round-to-nearest); N <= 32768.  std agrees with gpx_predict_meanvar to
  *             ~5e-8 relative with 5 slices (5e-7 at noise 1e-4) and ~5e-9 with 6.
- *   bits = 8: balanced radix-256 digits in [-128, 127] of the operand rounded ONCE to 8*nslices bits; N <= 16384 (= gpx_i8_max_n(8)).
+ *   bits = 8: balanced radix-256 digits in [-128, 127] of the operand rounded ONCE to 8*nslices bits.  The int32 sums are exact
+ *             for ANY digits up to N_pad = 16384 (= gpx_i8_safe_n(8)); from there to 32768 (= gpx_i8_max_n(8)) they are exact when
+ *             128 * gpx_i8_digit_bound(planes of L^-1) < 2^31 -- the caller checks that once per factorisation (the Python engine
+ *             does, and falls back to 7-bit digits otherwise); the kernels do not.
  *             Five slices (40 bits, 15 slice products) stand in for six 7-bit ones (42 bits, 21 products); six carry 48 bits.
  * The posterior mean is bit-identical to gpx_predict_meanvar in every case (K* and the mean are evaluated in FP64).
  * Plane layout: planes[j][row][p(col)] (int8, row pitch = cols, plane pitch = plane_rows*cols) with p permuting the columns
@@ -154,6 +157,9 @@ int gpx_slice_i8(const double* src, int rows, int cols, long ld_src, signed char
                  int bits, int tri, double* inv_scale, const double* amax_ptr, void* stream);
 int gpx_i8_row_tiles(int Np);
 int gpx_i8_max_n(int bits);
+int gpx_i8_safe_n(int bits);
+/* out[0] (device) = max over the rows i of L^-1 of sum_{planes} sum_k |digit|: bounds every int32 accumulator by 128 * out[0] */
+int gpx_i8_digit_bound(const signed char* planes, int nslices, int Np, unsigned long long* out, void* stream);
 int gpx_i8_clusters(void);   /* diagnostics: resident 2-CTA clusters of the persistent tensor-core kernel configured last (0 = none yet) */
 /* gpx_kmat_cross_i8: gpx_kmat_cross and gpx_slice_i8 (tri = 0, amax = outputscale) in one pass: the K* chunk is evaluated in
  * FP64 and written only as its int8 slices (same bytes, same mean_part as the two calls). */

@@ -183,8 +183,20 @@ def test_default_predict_at_config5_fold_shape(dev):
     em = _emulator(X, y, "rbf", hyper["lengthscale"], hyper["outputscale"], 1e-2, hyper["weights"], hyper["bias"])
     chk = DeviceChecker(em, "rbf", dev)
     Xq = _query_points(X, 20_000, np.random.default_rng(4))
-    worst, _ = _assert_matches(em, chk, Xq, expect_precision="int8x6")       # padded size > 16384: six 7-bit slices
-    print(f"config5 fold: worst rel std error {worst:.2e}")
+    # padded size 26240 > 16384: five 8-bit digits are used because the digits of THIS L^-1 bound every int32 accumulator
+    # (ExactGPEngine.i8_sums_exact: 128 x the largest row sum of |digits| < 2^31); otherwise it would be six 7-bit ones
+    eng0 = em.model._factorized_engine()
+    assert eng0.Np > int(eng0.lib.gpx_i8_safe_n(8)) and eng0.i8_sums_exact("int8x5w") and eng0.i8_sums_exact("int8x6")
+    bound = eng0._i8_bound["int8x5w"][2]
+    planes = eng0.S_i8
+    rows = torch.randint(0, eng0.N, (64,), device=dev)
+    ref = planes[:, rows, :].to(torch.int32).abs().sum(dim=(0, 2)).max()
+    assert 0 < int(ref) <= bound < 2 ** 24                                  # the kernel's maximum covers the sampled rows
+    worst, picked = _assert_matches(em, chk, Xq, expect_precision="int8x5w")
+    print(f"config5 fold: {picked}, digit bound {bound} (limit {2 ** 24}), worst rel std error {worst:.2e}")
+    _, s6 = em.predict(Xq[:4096], precision="int8x6")                       # the always-safe 7-bit mode still agrees
+    _, s5 = em.predict(Xq[:4096], precision="int8x5w")
+    np.testing.assert_allclose(s5, s6, rtol=2e-7)
     # the training objective at this size against the same independent factorisation
     eng = em.model._factorized_engine()
     N = 26214

@@ -63,7 +63,10 @@ res["chol_rel_err"] = float((eng.chol() - L).abs().max() / L.abs().max())
 M = 65536
 Xs = torch.rand(M, D, dtype=F64, device=dev)
 pm = torch.zeros(M, dtype=F64, device=dev)
-for prec in ("fp64", "int8x6", "tf32x3"):
+for prec in ("fp64", "int8x6", "int8x5w", "tf32x3"):
+    if prec == "int8x5w":
+        res["int8x5w_sums_exact"] = bool(eng.i8_sums_exact(prec))
+        res["int8x5w_digit_bound"] = eng._i8_bound.get(prec, (None, None, None))[2]
     eng.predict(Xs[:4096], prior_mean=pm[:4096], precision=prec)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
