@@ -125,7 +125,8 @@ class KFoldCrossValidation(Trainable):
         # one worker per device, bound to it: (fold, restart) jobs are pulled by whichever GPU becomes free (argument 5 = device)
         results = execute_task_in_parallel(self._train_split_restart, tasks, self.max_workers, devices=self.devices, device_arg=5)
         models, stats, scores, idx = {}, {}, {}, {}
-        for i, (tr, lo) in enumerate(splits):
+
+        def finish_fold(i, tr, lo):
             # best restart of the fold, its snapshot and its test scores: same selection as GPEmulator.train
             emulator = GPEmulator(self._fold_experiment(self._fold_dataset(X[tr], y[tr], X[lo], y[lo])),
                                   self.devices[i % len(self.devices)])
@@ -135,8 +136,20 @@ class KFoldCrossValidation(Trainable):
                 [results[(i, r)][1] for r in range(1, n_restarts + 1)], snpc)
             inference = Inference(emulator)
             inference.summary(printtoconsole=False)
-            models[i] = {k: torch.as_tensor(v) for k, v in best_model.items()}
-            stats[i], scores[i], idx[i] = best_stats, inference.scores_dct, [tr, lo]
+            return {k: torch.as_tensor(v) for k, v in best_model.items()}, best_stats, inference.scores_dct
+
+        # every fold's selection + test-set scores on its own GPU, side by side (the device work -- an FP64 factorisation of the
+        # fold and a predict -- releases the GIL); one fold after the other when there is a single device
+        if len(self.devices) > 1 and len(splits) > 1:
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(max_workers=min(len(self.devices), len(splits))) as pool:
+                futs = {i: pool.submit(finish_fold, i, tr, lo) for i, (tr, lo) in enumerate(splits)}
+                done = {i: f.result() for i, f in futs.items()}
+        else:
+            done = {i: finish_fold(i, tr, lo) for i, (tr, lo) in enumerate(splits)}
+        for i, (tr, lo) in enumerate(splits):
+            models[i], stats[i], scores[i] = done[i]
+            idx[i] = [tr, lo]
         return self._finish(models, stats, scores, idx)
 
     def _train_split_restart(self, opt_spec, early_stopping_criterion, snapshotting_criterion, i, restart, device,

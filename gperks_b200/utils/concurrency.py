@@ -6,12 +6,19 @@ import multiprocessing
 _WORKER_DEVICE = None
 
 
-def _bind_worker(device_queue):
+def _bind_worker(device_queue, n_workers=1):
     """Pool initializer: every worker process takes ONE device for its whole life, so at most ``len(devices)`` fits run at a
     time and never two on the same GPU (job-indexed devices let a free worker start a second fit on a busy GPU while another
-    GPU idles: measured 55 % busy GPUs and 106 GB on one device at BASELINE configs[4])."""
+    GPU idles: measured 55 % busy GPUs and 106 GB on one device at BASELINE configs[4]).  The host's cores are shared out between
+    the workers: with every worker at torch's default (all cores) eight of them spent more time contending for 16 threads
+    than fitting -- 2.2 s per config-5 fit against 0.9 s (the fits are GPU-bound; the host side is small tensor bookkeeping)."""
     global _WORKER_DEVICE
     _WORKER_DEVICE = device_queue.get()
+    try:
+        import torch
+        torch.set_num_threads(max(1, (multiprocessing.cpu_count() or 1) // max(1, int(n_workers))))
+    except Exception:       # pragma: no cover - thread pools already fixed by the embedding application
+        pass
 
 
 def _call_on_worker_device(task_fn, device_arg, args):
@@ -37,7 +44,7 @@ def execute_task_in_parallel(task_fn, inputs, max_workers=None, devices=None, de
         q = ctx.Queue()
         for d in list(devices)[:max_workers]:
             q.put(d)
-        pool_kw = dict(initializer=_bind_worker, initargs=(q,))
+        pool_kw = dict(initializer=_bind_worker, initargs=(q, max_workers))
         submit = lambda pool, args: pool.submit(_call_on_worker_device, task_fn, device_arg, args)  # noqa: E731
     else:
         pool_kw = {}
