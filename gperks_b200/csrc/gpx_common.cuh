@@ -247,15 +247,6 @@ __device__ __forceinline__ unsigned long long balanced_digits(double v) {
     const long long V = __double2ll_rn(v * (double)(1ull << (8 * S)));
     return ((unsigned long long)V + BIAS) ^ BIAS;
 }
-// Same digits from V = v * 2^(8S) already formed (|V| < 2^(8S-1)): adding 1.5 * 2^52 + BIAS rounds V to the nearest integer
-// (ties to even, like cvt.rni: the constant is even) and leaves V + BIAS in the low mantissa bits -- one DADD instead of
-// DMUL + F2I + a 64-bit integer add.  Only bytes 0..S-1 of the result are meaningful.
-template <int S>
-__device__ __forceinline__ unsigned long long balanced_digits_prescaled(double V) {
-    constexpr unsigned long long BIAS = (S == 5) ? 0x8080808080ull : 0x808080808080ull;
-    const double t = V + (6755399441055744.0 + (double)BIAS);
-    return (unsigned long long)__double_as_longlong(t) ^ BIAS;
-}
 __device__ __forceinline__ int perm128(int c) { return (c & ~127) | ((c & 15) << 3) | ((c & 127) >> 4); }
 
 #define GPX_CHECK_LAUNCH()                                  \

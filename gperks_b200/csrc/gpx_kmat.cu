@@ -222,14 +222,16 @@ kmat_cross_kernel(const double* __restrict__ Xs, long m_valid, const double* __r
 // (planes [S][plane_rows][Np]) of  v * 2^-(e+1)  (outputscale = f 2^e, k <= outputscale) instead of 8-byte values that a
 // second kernel would read back and slice.  BITS = 7: S rounds of round-to-nearest; BITS = 8: one FP64 -> int64 conversion and
 // the bytes of the biased integer (gpx_common.cuh: balanced_digits) -- two FP64 instructions per entry instead of 4 S.
-// A thread owns FOUR columns tx + 16 (4 h + b) (b < 4) of its row -- half of the FP64 kernels' micro-tile row, so that it
-// runs in 85 registers and three CTAs (24 warps) share an SM: with two CTAs of 126-register threads ptxas serialised most of
-// the polynomial chains and the FP64 pipe idled 40 % of the time waiting on its own latency.  The plane layout stores column c
-// of a 128-block at byte (c % 16) * 8 + c / 16 (the L^-1 planes use the same permutation), so the 4 bytes of a slice are
-// assembled in one register with one PRMT per digit and leave as ONE 4-byte store per slice: a warp writes a full 128-byte
-// row segment, no shared-memory staging.  Shared memory holds only the 2 x D coordinate rows (sized by D, not MAXD), so a CTA of this
-// kernel fits beside the 183 KB CTA of the integer tensor-core kernel working on the previous chunk.
-template <int KIND, int S, int BITS, int EPT>
+// BITS = 8 as built now: the outputscale carries the power-of-two digit scale, so the profile's value IS the integer to be rounded
+// and its digits are the low mantissa bytes of ONE add of 1.5 * 2^52 + bias (below).
+// A thread owns the eight columns tx + 16 b of two rows per pass (the FP64 kernels' mapping).  The plane layout stores column c
+// of a 128-block at byte (c % 16) * 8 + c / 16 (the L^-1 planes use the same permutation), so the 8 bytes of a slice are
+// assembled in two registers with one PRMT per digit and leave as ONE 8-byte store per slice: a half-warp writes a full 128-byte
+// row segment, no shared-memory staging.  (A variant with four columns x four rows per thread -- 78 registers, three CTAs per
+// SM -- measured 3-5 % slower at every shape, profiles/r02_builder_bench.json; occupancy is not what limits this kernel.)
+// Shared memory holds only the 2 x D coordinate rows (sized by D, not MAXD), so a CTA of this kernel fits beside the 183 KB CTA
+// of the integer tensor-core kernel working on the previous chunk.
+template <int KIND, int S, int BITS>
 __global__ void __launch_bounds__(P_THREADS, 2)
 kmat_cross_i8_kernel(const double* __restrict__ Xs, long m_valid, const double* __restrict__ X, int N, int D,
                      const double* __restrict__ theta, const double* __restrict__ xa, const double* __restrict__ xr,
@@ -246,9 +248,8 @@ kmat_cross_i8_kernel(const double* __restrict__ Xs, long m_valid, const double* 
     stage_coords(sb, X, (long)jb * TILE, N, D, theta, nullptr, nullptr, coord_scale<KIND>(), Dp);
     if (threadIdx.x < TILE) sal[threadIdx.x] = alpha[jb * TILE + threadIdx.x];
     __syncthreads();
-    // thread (tx, h, ty): columns tx + 16 (4 h + b), b < 4, of rows ty + 8 a, a < 16.  A warp holds one row: (tx, h) = lane.
-    // (EPT = 8, the FP64 kernels' mapping: eight columns tx + 16 b of rows ty + 16 a, one uint2 store per slice.)
-    constexpr int NH = 8 / EPT;                 // threads sharing one 8-byte group of a row
+    constexpr int EPT = 8;                      // entries (columns) per thread and row
+    constexpr int NH = 8 / EPT;                 // threads sharing one 8-byte group of a row (1)
     constexpr int NW = EPT / 4;                 // 32-bit words per slice and thread
     const int tx = threadIdx.x & 15, h = (threadIdx.x >> 4) & (NH - 1), ty = threadIdx.x / (16 * NH);
     const int e = scale_exponent_b<BITS>(theta[D]);
@@ -270,7 +271,7 @@ kmat_cross_i8_kernel(const double* __restrict__ Xs, long m_valid, const double* 
         // R rows per pass share every train coordinate read from shared memory: the distance loop is bound by shared-memory
         // wavefronts, not by the FP64 pipe (an LDS.64 delivers 16 lanes' worth per wavefront; with one row per pass it cost
         // 2.25 wavefronts per entry and dimension = 9 SM cycles against 4 FP64 pipe cycles -- measured 10 cycles per dimension)
-        constexpr int R = (EPT == 4) ? 4 : 2, RSTEP = 16 / NH;
+        constexpr int R = 2, RSTEP = 16 / NH;
 #pragma unroll 1
         for (int a0 = 0; a0 < 8 * NH; a0 += R) {
             double qq[R][EPT];
@@ -341,7 +342,7 @@ kmat_cross_i8_kernel(const double* __restrict__ Xs, long m_valid, const double* 
                 }
             }
             // same order as the FP64 kernels: (columns 0..63 chain) + (columns 64..127 chain), then the tree over tx
-            if (NH == 2) part += __shfl_xor_sync(0xffffffffu, part, 16); else part += part1;
+            part += part1;
             part += __shfl_xor_sync(0xffffffffu, part, 1);
             part += __shfl_xor_sync(0xffffffffu, part, 2);
             part += __shfl_xor_sync(0xffffffffu, part, 4);
@@ -368,27 +369,20 @@ static int launch_kmat_cross_i8(const double* Xs, long m_valid, const double* X,
                                 int nslices, int bits, int Np, double* mean_part, int Mc, cudaStream_t st) {
     const size_t smem = (size_t(2) * (D + (D & 1)) * P_LD + 2 * TILE) * 8;
     const dim3 grid(Np / TILE, Mc / TILE);
-#define GPX_KX2(S_, B_, E_)                                                                                                      \
-    do {                                                                                                                         \
-        if (smem > 48 * 1024)                                                                                                    \
-            cudaFuncSetAttribute(kmat_cross_i8_kernel<KIND, S_, B_, E_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        cudaFuncSetAttribute(kmat_cross_i8_kernel<KIND, S_, B_, E_>, cudaFuncAttributePreferredSharedMemoryCarveout,             \
-                             cudaSharedmemCarveoutMaxShared);                                                                    \
-        kmat_cross_i8_kernel<KIND, S_, B_, E_><<<grid, P_THREADS, smem, st>>>(Xs, m_valid, X, N, D, theta, xa, xr, alpha, planes, \
-                                                                              plane_rows, Np, mean_part, Mc);                    \
+#define GPX_KX(S_, B_)                                                                                                        \
+    do {                                                                                                                      \
+        if (smem > 48 * 1024)                                                                                                 \
+            cudaFuncSetAttribute(kmat_cross_i8_kernel<KIND, S_, B_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        cudaFuncSetAttribute(kmat_cross_i8_kernel<KIND, S_, B_>, cudaFuncAttributePreferredSharedMemoryCarveout,              \
+                             cudaSharedmemCarveoutMaxShared);                                                                 \
+        kmat_cross_i8_kernel<KIND, S_, B_><<<grid, P_THREADS, smem, st>>>(Xs, m_valid, X, N, D, theta, xa, xr, alpha, planes, \
+                                                                          plane_rows, Np, mean_part, Mc);                     \
     } while (0)
-#define GPX_KX(S_, B_)                          \
-    do {                                        \
-        if (ept == 8) GPX_KX2(S_, B_, 8);       \
-        else GPX_KX2(S_, B_, 4);                \
-    } while (0)
-    static const int ept = [] { const char* e = getenv("GPX_KX_EPT"); return (e && atoi(e) == 4) ? 4 : 8; }();
     if (nslices == 5 && bits == 7) GPX_KX(5, 7);
     else if (nslices == 6 && bits == 7) GPX_KX(6, 7);
     else if (nslices == 5 && bits == 8) GPX_KX(5, 8);
     else if (nslices == 6 && bits == 8) GPX_KX(6, 8);
     else return -8;
-#undef GPX_KX2
 #undef GPX_KX
     GPX_CHECK_LAUNCH();
     return 0;
