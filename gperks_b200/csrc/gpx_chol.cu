@@ -1365,22 +1365,25 @@ int potrf(double* K, int Np, int N, double* S, double* DT, double* logdet_blk, i
     };
     static int ob_env = -1, sw_env = -1;
     if (ob_env < 0) { const char* e = getenv("GPX_POTRF_OB"); ob_env = (e && e[0] >= '1' && e[0] <= '8') ? e[0] - '0' : 0; }
-    if (sw_env < 0) { const char* e = getenv("GPX_POTRF_SWITCH"); sw_env = e ? atoi(e) : 32; }
+    if (sw_env < 0) { const char* e = getenv("GPX_POTRF_SWITCH"); sw_env = e ? atoi(e) : 0; }
     static int ob8_env = -1;
     if (ob8_env < 0) { const char* e = getenv("GPX_POTRF_OB_I8"); ob8_env = (e && e[0] >= '1' && e[0] <= '8') ? e[0] - '0' : 0; }
+    // block columns left to the one-panel loop: 32 with FP64 updates; 24 when the outer blocks' updates are integer products
+    // (cheaper, so the two-level schedule pays a little longer: 4.71 -> 4.61 ms at Np = 8192)
+    const int sw = sw_env > 0 ? sw_env : (i8_ws != nullptr ? 24 : 32);
     const int OB = i8_ws != nullptr ? (ob8_env ? ob8_env : (nb >= 192 ? 8 : nb >= 96 ? 6 : 4)) : (ob_env ? ob_env : (nb >= 96 ? 4 : 3));
     int p_start = 0;
-    if (tma && la != nullptr && st != st_caller && OB >= 2 && nb > sw_env) {
+    if (tma && la != nullptr && st != st_caller && OB >= 2 && nb > sw) {
         // Two-level schedule.  Panels are still 128 wide (diag + panel on the critical path), but the bulk of the
         // trailing matrix is updated once per OUTER block of OB panels with K = OB*128, which halves (OB = 2) the
         // prologue/epilogue share of every output tile.  Inside an outer block the panels only update the block's own
         // columns; afterwards the next outer block's columns are updated on the critical-path stream (look-ahead) and
         // everything to the right of them on the low-priority helper stream.  Only while the trailing matrix is large
-        // enough to be throughput-bound: the last `sw_env` block columns are chain-bound and go through the one-panel
+        // enough to be throughput-bound: the last `sw` block columns are chain-bound and go through the one-panel
         // look-ahead loop below, whose critical path per panel is shorter.
         bool pending = false;
         int q_idx = 0;
-        for (int q = 0; q < nb && nb - q > sw_env; q += OB, ++q_idx) {
+        for (int q = 0; q < nb && nb - q > sw; q += OB, ++q_idx) {
             const int qe = (q + OB < nb) ? q + OB : nb;
             for (int p = q; p < qe; ++p) {
                 diag(p);

@@ -125,8 +125,8 @@ class ExactGPEngine:
         self._trtri_i8_capable = bool(self.lauum_slices and self.Np >= 2048 and os.environ.get("GPX_TRTRI", "") != "fp64")
         # Inside the same loops the Cholesky factorisation itself sends its bulk trailing updates through the integer tensor
         # cores (gpx_potrf_i8: six 8-bit digits per operand, L to ~1e-12 of its scale); GPX_POTRF=fp64 keeps them on FP64 DMMA.
-        # Needs the two-level schedule (more than 32 block columns) to have any bulk update at all.
-        self._potrf_i8_capable = bool(self._trtri_i8_capable and self.Np > 32 * 128 and os.environ.get("GPX_POTRF", "") != "fp64")
+        # Needs the two-level schedule (more than 24 block columns with integer updates) to have any bulk update at all.
+        self._potrf_i8_capable = bool(self._trtri_i8_capable and self.Np > 24 * 128 and os.environ.get("GPX_POTRF", "") != "fp64")
         self.approx_inverse_ok = False       # True inside a training loop: factorize() may use the integer inverse / Cholesky
         self.inverse_exact = True            # False while S / alpha / out come from the integer inverse
         self.chol_exact = True               # False while L itself comes from gpx_potrf_i8

@@ -180,12 +180,14 @@ int gpx_trmm_sumsq_i8(const signed char* Ls, const double* inv_scale, int Np, co
  * with a store epilogue (negate, transposed mirror).  Entries of L^-1 agree with gpx_trtri to ~1e-11 of their row/column scale.
  * bits = 7: Np <= 32768; bits = 8 (balanced radix-256 digits, 48 bits per operand, ~64 x finer): Np <= 16384.
  * replaces: the same call sites as gpx_trtri. */
-/* gpx_potrf_i8: gpx_potrf for training loops.  Same schedule, same outputs; the bulk trailing updates (everything right of the
- * look-ahead columns, once per outer block of 4 panels -- ~70 % of the FLOPs at Np = 8192) run on the integer tensor cores:
- * the finished panel rows are sliced into six 8-bit digits with one power-of-two scale per row (workspace) and
+/* gpx_potrf_i8: gpx_potrf for training loops.  Same schedule, same outputs; the trailing updates of the two-level schedule (once
+ * per outer block of 4 / 6 / 8 panels: the look-ahead columns on the critical-path stream, everything right of them on the helper
+ * stream -- ~70 % of the FLOPs at Np = 8192, ~90 % at 26240) run on the integer tensor cores: the finished panel rows are sliced
+ * into six 8-bit digits with one power-of-two scale per row (alternating plane buffers in the workspace) and
  * K[i][j] -= sum_k L[i][k] L[j][k] is formed by the kind::i8 NT GEMM kernel with an accumulate epilogue; int32 sums are exact
- * (at most 512 terms), so every update carries ~2^-46 of sqrt(K_ii K_jj), against ~2^-52 sqrt(512) for FP64 DMMA.  Panels,
- * diagonal blocks, look-ahead columns and the chain-bound tail (last 32 block columns) are the FP64 kernels of gpx_potrf.
+ * (at most 1024 terms), so every update carries ~2^-46 of sqrt(K_ii K_jj), against ~2^-52 sqrt(k) for FP64 DMMA.  Panels, diagonal
+ * blocks, the K = 128 updates inside an outer block and the chain-bound tail (last 24 block columns) are the FP64 kernels of
+ * gpx_potrf.  L within ~4e-12 of gpx_potrf's at Np = 8192.  Np > 3072 (below, it is gpx_potrf).
  * replaces: the same call sites as gpx_potrf, inside GPEmulator.train / train_auto loops only. */
 size_t gpx_potrf_i8_workspace_bytes(int Np);
 int gpx_potrf_i8(double* K, int Np, int N, double* S, double* DT, double* logdet_blk, int* info, void* workspace,
