@@ -665,6 +665,37 @@ def test_fused_i8_builder_equals_kmat_cross_plus_slicing(dev, kind, bits):
         assert torch.equal(mp1, mp2)
 
 
+@pytest.mark.parametrize("D,kind", [(1, O.KIND_MATERN52), (31, O.KIND_RBF), (32, O.KIND_MATERN32), (17, O.KIND_MATERN12)])
+def test_dimension_extremes_through_every_builder(dev, D, kind):
+    """One input dimension, the largest supported (32) and odd ones (the distance loops run over an even number of staged
+    coordinate rows, the last one zero): K_hat, both K* builders and the mean-only kernel against the oracle, the integer mode
+    against the FP64 mode, on a ragged N with masked padding columns in the last train tile."""
+    N, M = 333, 700
+    g = torch.Generator().manual_seed(100 + D)
+    X = torch.rand(N, D, dtype=F64, generator=g)
+    y = torch.randn(N, dtype=F64, generator=g)
+    Xs = torch.rand(M, D, dtype=F64, generator=g)
+    ls = torch.tensor([(0.7 + 0.5 * (d % 3)) * max(1.0, D ** 0.5) for d in range(D)], dtype=F64)
+    s, nz = torch.tensor(1.3, dtype=F64), 1e-2
+    w, b = torch.linspace(-1, 1, D, dtype=F64) if D > 1 else torch.tensor([0.5], dtype=F64), torch.tensor(0.1, dtype=F64)
+    eng = _engine(dev, X, y, kind, ls, s, nz, w, b)
+    pm = (Xs @ w + b).to(dev)
+    m64, s64 = eng.predict(Xs.to(dev), prior_mean=pm)
+    mref, vref = O.predict(X, y, kind, ls, s, nz, X @ w + b, Xs, Xs @ w + b)
+    np.testing.assert_allclose(m64.cpu().numpy(), mref.numpy(), rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(s64.cpu().numpy(), vref.sqrt().numpy(), rtol=1e-8)
+    for prec, tol in (("int8x5w", 1e-7), ("int8x6", 2e-7)):
+        mi, si = eng.predict(Xs.to(dev), prior_mean=pm, precision=prec)
+        assert torch.equal(mi, m64)
+        assert float(((si - s64).abs() / s64).max()) < tol
+    assert torch.equal(eng.predict_mean(Xs.to(dev), prior_mean=pm), m64)
+    loss = float(O.neg_mll(X, y, kind, ls, s, nz, X @ w + b))
+    assert float(eng.loss) == pytest.approx(loss, rel=1e-10)
+    gr = O.neg_mll_analytic_grads(X, y, kind, ls, s, torch.tensor(nz, dtype=F64), X @ w + b)
+    gref = torch.cat([gr["lengthscale"], gr["outputscale"].reshape(1), gr["noise"].reshape(1)]).numpy()
+    np.testing.assert_allclose(eng.gradients().cpu().numpy(), gref, rtol=1e-8, atol=1e-11 * np.abs(gref).max())
+
+
 @pytest.mark.parametrize("N,D,M,kind,nz", [(20, 2, 25, O.KIND_RBF, 1e-2), (300, 3, 1000, O.KIND_RBF, 1e-2),
                                            (1000, 5, 777, O.KIND_MATERN32, 1e-2), (200, 8, 500, O.KIND_MATERN12, 1e-4),
                                            (2048, 6, 8192, O.KIND_MATERN52, 1e-2), (2048, 6, 4096, O.KIND_MATERN52, 1e-4)])
