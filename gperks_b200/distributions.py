@@ -5,7 +5,7 @@
 * ``PosteriorDistribution`` -- eval-mode predictive distribution; ``.mean`` / ``.variance`` run the fused
   predict kernels, ``.covariance_matrix`` / ``.sample`` / ``.log_prob`` form the dense M x M covariance
   (test-set sized M) with the TRMM-store / SYRK kernels and factor it with the blocked CUDA Cholesky
-  (``engine.DenseCholesky``); only the final ``L @ z`` of a draw is a plain library GEMM.
+  (``engine.DenseCholesky``); the ``L z`` of a draw is the same TRMM-store kernel (``_lower_times``) -- no library GEMM on the path.
 
 They stand in for gpytorch.distributions.MultivariateNormal as used at GPErks/gp/model.py:21 and
 GPErks/train/emulator.py:336-346, 356-360, 392-394."""
@@ -27,6 +27,24 @@ def _psd_safe_cholesky(A: torch.Tensor) -> torch.Tensor:
     nv.require_cuda()
     dev = A.device if A.is_cuda else torch.device("cuda", torch.cuda.current_device())
     return DenseCholesky(A.detach().to(dev, F64).contiguous()).L.to(A.device)
+
+
+def _lower_times(L: torch.Tensor, z: torch.Tensor) -> torch.Tensor:
+    """(L z)^T -> [n, M] for a lower-triangular L [M, M] and z [M, n], on the FP64 DMMA tile engine: gpx_trmm_store computes
+    out[r][i] = sum_{k <= i} Zt[r][k] L[i][k] -- the kernel behind V^T = K* L^-T, handed L itself and z^T as its two operands."""
+    from . import _native as nv
+    nv.require_cuda()
+    dev = L.device if L.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    M, n = z.shape
+    Mp, npad = nv.padded(M), nv.padded(n)
+    Lp = torch.zeros(Mp, Mp, dtype=F64, device=dev)
+    Lp[:M, :M] = torch.tril(L.detach().to(dev, F64))
+    Zt = torch.zeros(npad, Mp, dtype=F64, device=dev)
+    Zt[:n, :M] = z.detach().to(dev, F64).T
+    out = torch.empty(npad, Mp, dtype=F64, device=dev)
+    with torch.cuda.device(dev):
+        nv.check(nv.lib().gpx_trmm_store(nv.ptr(Lp), Mp, nv.ptr(Zt), npad, nv.ptr(out), nv.stream_ptr()), "gpx_trmm_store")
+    return out[:n, :M].to(L.device)
 
 
 class MultivariateNormal:
@@ -78,7 +96,7 @@ class MultivariateNormal:
         L = _psd_safe_cholesky(K.to(F64))
         n = int(torch.Size(sample_shape).numel()) if len(sample_shape) else 1
         z = torch.randn(K.shape[-1], n, dtype=F64, device=K.device)
-        draws = (self._mean.to(K.device, F64).unsqueeze(-1) + L @ z).T
+        draws = self._mean.to(K.device, F64).unsqueeze(0) + _lower_times(L, z)
         return draws.reshape(*sample_shape, K.shape[-1]).to(self._mean.dtype)
 
     def sample(self, sample_shape=torch.Size()) -> torch.Tensor:
@@ -181,7 +199,7 @@ class PosteriorDistribution:
         shape = torch.Size(sample_shape)
         n = int(shape.numel()) if len(shape) else 1
         z = torch.randn(mean.shape[0], n, dtype=F64, device=mean.device)
-        draws = (mean.unsqueeze(-1) + L @ z).T
+        draws = mean.unsqueeze(0) + _lower_times(L, z)
         return self._out(draws.reshape(*shape, mean.shape[0]))
 
     def sample(self, sample_shape=torch.Size()) -> torch.Tensor:

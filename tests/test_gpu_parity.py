@@ -982,6 +982,19 @@ def test_training_mode_predictive_covariance_on_integer_tensor_cores(dev, N, M):
     eng.approx_inverse_ok = False
 
 
+@pytest.mark.parametrize("M,n", [(1, 1), (130, 7), (700, 300)])
+def test_draws_use_the_tile_engine_for_L_times_z(dev, M, n):
+    """The L z of posterior / prior draws runs on gpx_trmm_store (no library GEMM on the sample path): against torch.matmul."""
+    from gperks_b200.distributions import _lower_times
+    g = torch.Generator().manual_seed(M + n)
+    L = torch.tril(torch.randn(M, M, dtype=F64, generator=g)).to(dev)
+    z = torch.randn(M, n, dtype=F64, generator=g).to(dev)
+    got = _lower_times(L, z)
+    ref = (L @ z).T
+    assert got.shape == (n, M)
+    np.testing.assert_allclose(got.cpu().numpy(), ref.cpu().numpy(), rtol=0, atol=1e-12 * float(ref.abs().max() + 1.0))
+
+
 @pytest.mark.parametrize("variant", ["zero_mean_shared_ls", "constant_mean_bare_kernel", "fixed_noise_quadratic_mean"])
 def test_api_variants_match_oracle(dev, variant):
     """Less common module combinations through the public API: shared (non-ARD) lengthscale, kernels without a
