@@ -15,16 +15,18 @@
 //   BITS = 7: |I_j| <= 64 by repeated round-to-nearest (the formulas above); int32 sums safe for K <= 32768.
 //   BITS = 8: balanced radix-256 digits I_j in [-128, 127] of  V = rint(x * scale * 2^{8S})  (one rounding, 8S bits kept):
 //             x * scale = sum_j I_j 2^{-8(j+1)},  bytes of (V + sum_j 128 * 256^j) xor 0x80.  The scale keeps |x * scale| <= 127.4/256
-//             so the top digit fits.  |sum| <= 128*128*K*S < 2^31 for K <= 16384 -- five 8-bit slices (40 bits, 15 products)
+//             so the top digit fits.  |sum| <= 128*128*K*S < 2^31 for K <= 16384 whatever the digits are -- above, up to 32768, when
+//             the digits of the sliced L^-1 allow it (i8_digit_bound below).  Five 8-bit slices (40 bits, 15 products)
 //             replace six 7-bit ones (42 bits, 21 products); six 8-bit slices carry 48 bits.
 // Plane layout of the predict operands (K* chunk and L^-1): inside every 128-block of the contraction index the entry of
 // column c sits at byte (c % 16) * 8 + c / 16 -- the same permutation on both operands leaves every inner product unchanged
 // and lets the K* builder (gpx_kmat.cu), whose threads own columns tx + 16 b, store 8 consecutive bytes per slice straight
 // from registers.
 //
-// Contents: slice_i8_kernel / slice_i8_rows_kernel (FP64 -> int8 planes), trmm_sumsq_i8_kernel (predict: sum of squares
-// epilogue), gemm_i8_kernel (general NT product with a store epilogue: K_hat^-1 for the gradient, and the opt-in merge levels of
-// the triangular inverse), peak_i8mma_kernel (roofline probe).
+// Contents: slice_i8_kernel / slice_i8_rows_kernel (FP64 -> int8 planes), trmm_sumsq_i8_kernel / trmm_sumsq_i8p_kernel (predict:
+// sum of squares epilogue; one tile per cluster / persistent), gemm_i8_kernel (general NT product with a store, mirror or accumulate
+// epilogue: K_hat^-1 for the gradient, the merge levels of the triangular inverse, the Cholesky trailing updates and the
+// validation covariance of training loops), i8_digit_bound_kernel, peak_i8mma_kernel (roofline probe).
 //
 // Tile: 128 test points (MMA M = TMEM lanes) x 64 rows of L^-1 (per slice), S accumulators of 64 TMEM columns, one per
 // diagonal g.  The S slices of the L^-1 tile are STACKED along MMA N in shared memory, so for the K* slice a one

@@ -9,9 +9,12 @@
 //   mll_grad   : (1/2N) sum_ij (K_hat^-1 - alpha alpha^T)_ij dK_hat_ij/dtheta, kernel recomputed in
 //                registers, two-stage deterministic reduction (no N^2*D tensor ever materialised).
 //
-// All three share one tile body: a 128 x 128 tile per CTA, 256 threads, each thread an 8 x 8 micro-tile
-// strided by 16 so that a warp's stores cover two full 128-byte row segments.  Coordinates are
-// pre-multiplied by 1/lengthscale while being staged (transposed) into shared memory.
+// All share one tile body: a 128 x 128 tile per CTA, 256 threads, each thread an 8 x 8 micro-tile strided by 16 so that a warp's
+// stores cover two full 128-byte row segments, walked two rows per pass (the distance loop is bound by shared-memory
+// wavefronts: rows_q2).  Coordinates are staged (transposed, zero-padded to an even number of dimensions) pre-multiplied by
+// coord_scale<KIND>() / lengthscale, and the squared-distance accumulators start at 1e-30, so the profile is evaluated from
+// q = c^2 r^2 + 1e-30 by the branch-free exp / sqrt of gpx_math.cuh (kernel_profile, gpx_common.cuh).  The gradient kernel
+// (mll_grad) keeps plain 1 / lengthscale coordinates (it needs the per-dimension squared differences themselves).
 #include <cstdlib>
 #include <type_traits>
 #include "gpx_common.cuh"
