@@ -88,8 +88,16 @@ def test_auto_precision_is_resolved_from_host_values():
     assert big.auto_precisions() == ["int8x6w", "fp64"]
     big.model.covar_module.outputscale = 1.01e-3 * K.AUTO_I8_W6_MAX_SCALE_TO_NOISE       # outputscale / noise above every limit
     assert big.auto_precisions() == ["fp64"] and big.resolve_precision("auto") == "fp64"
-    # 8-bit slices keep their int32 sums exact up to a padded train size of 16384; beyond, six 7-bit slices up to 32768
+    # 8-bit slices keep their int32 sums exact for ANY digits up to a padded train size of 16384; beyond (to 32768) five 8-bit
+    # slices stay a candidate that the engine admits only after bounding the sums with the actual digits of L^-1
+    # (ExactGPEngine.i8_sums_exact, a device pass: tests/test_gpu_baseline_shapes.py), followed by the always-safe six 7-bit slices
     assert K.AUTO_I8_WIDE_MAX_N == 16384 and K.AUTO_I8_MAX_N == 32768
+    from gperks_b200.engine import ExactGPEngine
+    assert ExactGPEngine.auto_candidates(26214, 1.0, 1e-2) == ["int8x5w", "int8x6", "fp64"]
+    assert ExactGPEngine.auto_candidates(26214, 1.0, 1e-3) == ["int8x6", "fp64"]            # ratio 1000 > 300: five slices no longer hold 1e-6
+    assert ExactGPEngine.auto_candidates(26214, 1.0, 1e-4) == ["fp64"]
+    assert ExactGPEngine.auto_candidates(16384, 1.0, 1e-2) == ["int8x5w", "int8x6w", "fp64"]
+    assert ExactGPEngine.auto_candidates(32769, 1.0, 1e-2) == ["fp64"]
     for p in ("fp64", "int8x5", "int8x6", "int8x5w", "int8x6w", "tf32x3", "tf32x3_fast"):
         assert big.resolve_precision(p) == p
 
