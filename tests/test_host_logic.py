@@ -397,3 +397,23 @@ def test_settings_shim_accepts_gpytorch_idioms():
         pass
     with settings.fast_computations(covar_root_decomposition=False, log_prob=False, solves=False):
         assert settings.fast_pred_var.on() and not settings.fast_pred_var.off()
+
+
+def test_worker_initializer_binds_a_device_and_shares_out_the_cores():
+    """Pool workers of train(devices=...) / KFoldCrossValidation(devices=...): one device per worker for its whole life, and the
+    host's cores split between the workers (eight workers at torch's default thread count contended for the same 16 threads and
+    a config-5 fit took 2.2 s instead of 0.9 s)."""
+    import multiprocessing
+    import queue
+    from gperks_b200.utils import concurrency as cc
+    q = queue.Queue()
+    q.put("cuda:3")
+    n0 = torch.get_num_threads()
+    try:
+        cc._bind_worker(q, 4)
+        assert cc._WORKER_DEVICE == "cuda:3"
+        assert torch.get_num_threads() == max(1, multiprocessing.cpu_count() // 4)
+        assert cc._call_on_worker_device(lambda a, b: (a, b), 1, ("x", "cuda:0")) == ("x", "cuda:3")
+    finally:
+        torch.set_num_threads(n0)
+        cc._WORKER_DEVICE = None
