@@ -692,14 +692,17 @@ static int launch_i8(const int8_t* Ls, const double* inv_scale, int Np, const in
 int i8_max_np(int bits) { return (bits == 7 || bits == 8) ? 32768 : 0; }
 int i8_safe_np(int bits) { return bits == 8 ? 16384 : (bits == 7 ? 32768 : 0); }
 
-// out[0] = max over rows of  sum_{plane, k} |digit|   (one block per row of the S planes [Np][Np]); out must be zero on entry
+// out[0] = max over rows of  sum_{plane, k} |digit|   (one block per row of the S planes [Np][Np]); out must be zero on entry.
+// Only the columns up to the end of the row's own 128-block count: that is the k range the tensor-core kernel reads for the row
+// (gpx_slice_i8 with tri = 1 leaves everything right of it untouched).
 __global__ void __launch_bounds__(256) i8_digit_bound_kernel(const int8_t* __restrict__ planes, int S, int Np,
                                                              unsigned long long* __restrict__ out) {
     const int row = blockIdx.x;
+    const int kend = (row / TILE + 1) * TILE;
     unsigned int acc = 0;
     for (int j = 0; j < S; ++j) {
         const int4* src = reinterpret_cast<const int4*>(planes + ((long)j * Np + row) * Np);
-        for (int c = threadIdx.x; c < Np / 16; c += 256) {
+        for (int c = threadIdx.x; c < kend / 16; c += 256) {
             const int4 v = src[c];
             const unsigned int w[4] = {(unsigned int)v.x, (unsigned int)v.y, (unsigned int)v.z, (unsigned int)v.w};
 #pragma unroll

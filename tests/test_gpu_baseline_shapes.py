@@ -190,7 +190,8 @@ def test_default_predict_at_config5_fold_shape(dev):
     bound = eng0._i8_bound["int8x5w"][2]
     planes = eng0.S_i8
     rows = torch.randint(0, eng0.N, (64,), device=dev)
-    ref = planes[:, rows, :].to(torch.int32).abs().sum(dim=(0, 2)).max()
+    live = torch.arange(eng0.Np, device=dev).view(1, -1) < ((rows // 128 + 1) * 128).view(-1, 1)   # the k range read per row
+    ref = (planes[:, rows, :].to(torch.int32).abs() * live.unsqueeze(0)).sum(dim=(0, 2)).max()
     assert 0 < int(ref) <= bound < 2 ** 24                                  # the kernel's maximum covers the sampled rows
     worst, picked = _assert_matches(em, chk, Xq, expect_precision="int8x5w")
     print(f"config5 fold: {picked}, digit bound {bound} (limit {2 ** 24}), worst rel std error {worst:.2e}")

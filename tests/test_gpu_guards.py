@@ -136,3 +136,54 @@ def test_wave_compaction_saltelli_and_mean_stay_inside_their_buffers(dev):
     assert idx.intact() and cnt.intact() and cws.intact() and part.intact() and sums.intact() and om.intact()
     assert torch.equal(om.view(F64, M), means[0])
     assert C.sizeof(nv.I8EmulatorDesc) == 136
+
+
+def test_training_mode_integer_kernels_stay_inside_their_buffers(dev):
+    """gpx_potrf_i8 (sliced panels in alternating plane buffers, accumulate epilogue into K), gpx_predict_covar_i8 (V -> W, V^T -> Vt
+    through the mirror store, accumulate into C with its own leading dimension) and gpx_i8_digit_bound, every buffer exactly sized
+    between canaries, at a train size whose last block column is ragged and whose outer blocks leave a ragged rest."""
+    lib = nv.lib()
+    p = nv.ptr
+    N, D = 3150, 4                                      # Np = 3200: 25 block columns -> one outer block of the two-level schedule
+    eng = _engine(dev, N, D)
+    Np, nb = eng.Np, eng.Np // 128
+    assert Np == 3200 and eng._potrf_i8_capable
+    L64 = eng.chol().clone()
+    st = nv.stream_ptr()
+    K = Guarded(Np * Np * 8, dev)
+    S, DT, logdet, info = Guarded(Np * Np * 8, dev), Guarded(nb * 128 * 128 * 8, dev), Guarded(nb * 8, dev), Guarded(4, dev)
+    ws = Guarded(lib.gpx_potrf_i8_workspace_bytes(Np), dev)
+    nv.check(lib.gpx_kmat_sym(p(eng.X), N, D, p(eng.theta), eng.kind, K.ptr, Np, st), "kmat")
+    nv.check(lib.gpx_potrf_i8(K.ptr, Np, N, S.ptr, DT.ptr, logdet.ptr, info.ptr, ws.ptr, ws.n, st), "potrf_i8")
+    torch.cuda.synchronize()
+    assert K.intact() and S.intact() and DT.intact() and logdet.intact() and info.intact() and ws.intact()
+    assert int(info.view(torch.int32, 1).item()) == 0
+    L8 = torch.tril(K.view(F64, Np * Np).view(Np, Np)[:N, :N])
+    err = float((L8 - L64).abs().max() / L64.abs().max())
+    assert 0 < err < 1e-10, err
+    # dense predictive covariance of M validation points on the integer GEMM
+    M = 1100
+    Mp = nv.padded(M)
+    Xs = torch.rand(M, D, dtype=F64, device=dev)
+    Ks, Vt, Cc, W = Guarded(Mp * Np * 8, dev), Guarded(Mp * Np * 8, dev), Guarded(Mp * Mp * 8, dev), Guarded(Np * Np * 8, dev)
+    mp1, mp2 = Guarded(nb * Mp * 8, dev), Guarded((Mp // 128) * Mp * 8, dev)
+    zeros = torch.zeros(Mp, dtype=F64, device=dev)
+    ws2 = Guarded(lib.gpx_trtri_i8_workspace_bytes(Np), dev)
+    nv.check(lib.gpx_kmat_cross(p(Xs), M, p(eng.X), N, D, p(eng.theta), None, None, eng.kind, p(eng.alpha), Ks.ptr, Np, mp1.ptr, Mp, st), "cross")
+    nv.check(lib.gpx_kmat_cross(p(Xs), M, p(Xs), M, D, p(eng.theta_latent), None, None, eng.kind, p(zeros), Cc.ptr, Mp, mp2.ptr, Mp, st), "kss")
+    nv.check(lib.gpx_predict_covar_i8(p(eng.S), Np, Ks.ptr, Mp, Vt.ptr, Cc.ptr, W.ptr, 8, ws2.ptr, ws2.n, st), "covar_i8")
+    torch.cuda.synchronize()
+    assert Ks.intact() and Vt.intact() and Cc.intact() and W.intact() and mp1.intact() and mp2.intact() and ws2.intact()
+    _, cref = eng.predict_covar(Xs, torch.zeros(M, dtype=F64, device=dev), noisy=False)
+    got = torch.tril(Cc.view(F64, Mp * Mp).view(Mp, Mp)[:M, :M])
+    assert float((got - torch.tril(cref)).abs().max()) < 1e-9 * float(eng.theta[D])
+    # the digit bound of the sliced L^-1
+    eng._ensure_i8(5, 8)
+    out = Guarded(8, dev)
+    nv.check(lib.gpx_i8_digit_bound(p(eng.S_i8), 5, Np, out.ptr, st), "digit_bound")
+    torch.cuda.synchronize()
+    assert out.intact()
+    rows = torch.arange(Np, device=dev)
+    live = torch.arange(Np, device=dev).view(1, -1) < ((rows // 128 + 1) * 128).view(-1, 1)     # the k range the MMA kernel reads per row
+    ref = (eng.S_i8.to(torch.int32).abs() * live.unsqueeze(0)).sum(dim=(0, 2)).max()
+    assert int(out.view(torch.int64, 1).item()) == int(ref)
